@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""bench.py -- encrypted comparisons/s (and PBS/s) on N B200s, one process per GPU.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU arm (oracle port on the host cores)
+
+Workload (BASELINE.json configs[1]): `search` over DOCS synthetic encrypted documents per
+GPU, d=128 features, 8-bit quantization.  A *step* is one pass of the encrypted-compare hot
+path over all resident documents: the encrypted dot product of every document's
+ciphertexts with the quantized weights (server), then decrypt + dequantize of the encrypted
+scores (client kernels).  `value` times that with ciphertexts already resident in HBM;
+`e2e` times FHESimilarityModel.predict_encrypted-style calls with HOST float buffers
+(quantize -> encrypt -> dot -> decrypt on the device, H2D/D2H inside the timed region) plus
+the host-side threshold / sort / top-k of the search.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+D_FEATURES = 128
+N_BITS = 8
+DATA_SEED, KEY_SEED, ENC_SEED, EVK_SEED = 20261018, 0x5EED0001, 0x5EED0002, 0x5EED0003
+METRIC = "encrypted_comparisons_per_sec"
+UNIT = "comparisons/s"
+
+
+def build_model(device=None):
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=D_FEATURES, n_bits=N_BITS, seed=DATA_SEED, key_seed=KEY_SEED, enc_seed=ENC_SEED,
+                           device=device, verbose=False)
+    X, _ = m.train()
+    m.compile(X[:10])
+    return m, X
+
+
+def synthetic_docs(n_docs: int, seed: int):
+    """Unit-norm query and documents, half of them correlated with the query as in the
+    reference's generator (fhe_similarity.py:41-51); X = query * docs (the clear product the
+    reference feeds the circuit, batch_operations.py:273)."""
+    rng = np.random.RandomState(seed)
+    q = rng.randn(D_FEATURES).astype(np.float32)
+    q /= np.linalg.norm(q)
+    docs = rng.randn(n_docs, D_FEATURES).astype(np.float32)
+    docs /= np.linalg.norm(docs, axis=1, keepdims=True)
+    mask = rng.rand(n_docs) > 0.5
+    docs[mask] = q + 0.2 * rng.randn(int(mask.sum()), D_FEATURES)
+    docs /= np.linalg.norm(docs, axis=1, keepdims=True)
+    return q, docs, (q[None, :] * docs).astype(np.float32)
+
+
+def top_k(scores: np.ndarray, k: int, min_similarity: float):
+    """Reference semantics (batch_operations.py:278-284): filter >=, stable sort descending, [:k]."""
+    sims = [(i, float(s)) for i, s in enumerate(scores) if s >= min_similarity]
+    sims.sort(key=lambda x: x[1], reverse=True)
+    return sims[:k]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------- CPU arm
+def cpu_reference(model, X, target_seconds: float, threads=None):
+    """Oracle port of predict_encrypted on the host cores: quantize -> encrypt -> dot -> decrypt."""
+    from oracle import oracle as O
+    if threads:
+        O.lib().orc_set_num_threads(int(threads))
+    c = model.model.fhe_circuit
+    spec = c.spec
+    s = O.secret_key(c.key_seed, 2, c.lwe.n)
+    W = np.stack([spec.q_weights, np.ones_like(spec.q_weights)]) if c.two_outputs else spec.q_weights[None]
+
+    def run(rows):
+        t0 = time.perf_counter()
+        q = O.quantize(X[:rows], spec.input_q.scale, spec.input_q.zero_point, spec.input_q.offset, spec.input_q.n_bits)
+        ct = O.lwe_encrypt(s, q, c.lwe.shift, c.lwe.sigma_abs, c.enc_seed, ct_base=0, stride=c.lwe.stride)
+        out = O.lincomb(ct.reshape(rows, spec.d, -1), W, c.lwe.n)
+        m = O.lwe_decrypt(s, out, c.lwe.shift)
+        qy = m[:, 0] - (int(spec.weight_q.zero_point) * m[:, 1] if c.two_outputs else 0) + int(spec.q_bias)
+        y = spec.dequantize_output(qy)
+        return time.perf_counter() - t0, y
+
+    t_probe, _ = run(min(16, len(X)))
+    per_row = t_probe / min(16, len(X))
+    rows = int(max(16, min(len(X), target_seconds / max(per_row, 1e-9))))
+    t, y = run(rows)
+    assert np.array_equal(y, model.predict_clear(X[:rows])), "oracle result != clear circuit"
+    return rows / t, rows, t, O.num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    model, _ = build_model()
+    _, _, X = synthetic_docs(args.docs, DATA_SEED + 1)
+    vals = []
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    rows = 0
+    threads = 0
+    for i in range(args.warmup + args.steps):
+        v, rows, _, threads = cpu_reference(model, X, per_step)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    c = model.model.fhe_circuit
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * rows / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, c),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{rows} of {args.docs} documents per step, quantize+encrypt+dot+decrypt, "
+                                   "oracle/fhe_oracle.c with OpenMP on all host cores (Concrete itself is not installable)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "published_reference": {"value": 5.0, "unit": UNIT, "note": "1/0.20 s per 8-bit sample, hardware unstated "
+                                "(reference SESSION_REPORT.md:70)"},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, c):
+    return {"workload": f"search top-k=3 over {args.docs} synthetic encrypted documents per GPU "
+                        "(BASELINE.json configs[1])",
+            "docs_per_gpu": args.docs, "d": D_FEATURES, "n_bits": N_BITS, "lwe_n": c.lwe.n,
+            "ciphertext_words": c.lwe.stride, "log2_delta": c.lwe.shift, "log2_sigma": round(c.lwe.log2_sigma, 2),
+            "outputs_per_comparison": 2 if c.two_outputs else 1,
+            "bytes_per_comparison": comparison_bytes(c),
+            "l2_policy": "inputs larger than L2 (ciphertext set per step >= 1 GB vs 126 MB L2), no flush",
+            "seeds": {"data": DATA_SEED, "key": KEY_SEED, "enc": ENC_SEED}}
+
+
+def comparison_bytes(c) -> int:
+    M = 2 if c.two_outputs else 1
+    return (D_FEATURES + M) * (c.lwe.n + 1) * 8
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from fhe_icp_b200 import _native as N
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    model, _ = build_model(device=local_rank)
+    c = model.model.fhe_circuit
+    ctx = N.context(local_rank)
+    # each rank owns a contiguous shard of the collection (weak scaling: DOCS per GPU)
+    _, _, X = synthetic_docs(args.docs, DATA_SEED + 1 + rank)
+    B = args.docs
+    M = 2 if c.two_outputs else 1
+
+    # resident ciphertexts (client-side encryption happens once, outside the timed region)
+    c.ct_counter = rank * (1 << 40)
+    ct = model.encrypt(X)
+    out = torch.empty((B, M, c.lwe.stride), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+
+    gathered = None
+    if world > 1:
+        gathered = torch.empty((world * B, M, c.lwe.stride), dtype=torch.int64, device=dev)
+
+    def step():
+        model.run(ct, out=out)                       # server: encrypted dot products
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)  # encrypted scores -> the decrypting client
+        return model.decrypt(out)                    # client kernels: decrypt + dequantize (device)
+
+    for _ in range(max(args.warmup, 3)):
+        y_dev = step()
+    torch.cuda.synchronize()
+    ref = model.predict_clear(X)
+    assert np.array_equal(y_dev, ref), "GPU scores differ from the clear quantized circuit"
+
+    # --- timed region: K steps, device-resident inputs
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        evs[i][0].record()
+        model.run(ct, out=out)
+        evs[i][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        _decrypt_device(model, out)
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = ctx.launch_count() - launches0
+    elapsed_ms = t0.elapsed_time(t1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+
+    # --- e2e: host float buffers in, host scores out, + host top-k
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        model.predict_encrypted(X)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        scores = model.predict_encrypted(X)
+        hits = top_k(scores, 3, -np.inf)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * e2e_steps / e2e_s
+    assert [i for i, _ in hits] == [i for i, _ in top_k(ref, 3, -np.inf)], "top-k ranking differs from the clear circuit"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak_gbs()
+    bytes_per_launch = comparison_bytes(c) * B
+    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": workload_config(args, c),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * D_FEATURES * 4),
+                "d2h_bytes_per_step": int(B * 16), "steps": e2e_steps,
+                "call": "fhe_b200_similarity_predict_host (FHESimilarityModel.predict_encrypted) + host top-k"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "lincomb_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms": kern_ms},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world >= 1:
+        v, rows, t, threads = cpu_reference(model, X, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{rows} of {B} documents, quantize+encrypt+dot+decrypt in {t:.1f} s, "
+                                          "oracle/fhe_oracle.c (OpenMP)"}
+    try:
+        from fhe_icp_b200 import pbs_bench
+        line["pbs"] = pbs_bench.measure(dev, args)
+    except ImportError:
+        pass
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _decrypt_device(model, out):
+    """decrypt + dequantize kernels without the device->host copy (device-resident timing)."""
+    import ctypes as C
+    import torch
+    from fhe_icp_b200 import _native as N
+    c = model.model.fhe_circuit
+    B = out.shape[0]
+    if not hasattr(model, "_bench_y") or model._bench_y.shape[0] != B:
+        model._bench_y = torch.empty(B, dtype=torch.float64, device=out.device)
+        model._bench_qy = torch.empty(B, dtype=torch.int64, device=out.device)
+    st = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+    N.check(N.lib().fhe_b200_similarity_decrypt(c.handle, C.c_void_p(out.data_ptr()), B,
+                                                C.c_void_p(model._bench_y.data_ptr()),
+                                                C.c_void_p(model._bench_qy.data_ptr()), st))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--docs", type=int, default=1000, help="documents per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pbs-batch", type=int, default=0, help="PBS microbench batch (0 = default sweep)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,442 @@
+// api.cu -- the C-ABI (include/fhe_b200.h): context, argument checking, error strings,
+// and the host-buffer entry point that mirrors FHESimilarityModel.predict_encrypted
+// (/root/reference/fhe_similarity.py:142-160).  No CPU fallback anywhere: every compute
+// call launches kernels of this library on the context's device.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "kernels.h"
+
+namespace {
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(FHE_B200_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+#define CU(expr)                                         \
+    do {                                                 \
+        cudaError_t _e = (expr);                         \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr); \
+    } while (0)
+#define REQUIRE(cond, msg)                                              \
+    do {                                                                \
+        if (!(cond)) return fail(FHE_B200_ERR_INVALID, "%s: %s", __func__, msg); \
+    } while (0)
+}  // namespace
+
+namespace fhe {
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+}  // namespace fhe
+
+struct fhe_b200_ctx {
+    int device;
+    cudaDeviceProp prop;
+    uint64_t launches_at_create;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct fhe_b200_similarity {
+    fhe_b200_ctx* ctx;
+    fhe_b200_similarity_spec spec;
+    int M;
+    bool second_is_sum;
+    uint8_t* d_key = nullptr;
+    int64_t* d_W = nullptr;  // [M][d]
+    cudaStream_t stream = nullptr;
+    // grow-only workspaces for the host-buffer entry point
+    DevBuf X, q, ct, out, m, y, qy;
+    PinBuf hX, hy, hqy;
+};
+
+extern "C" {
+
+int fhe_b200_abi_version(void) { return FHE_B200_ABI_VERSION; }
+const char* fhe_b200_last_error(void) { return g_err.c_str(); }
+
+int fhe_b200_ctx_create(int device, fhe_b200_ctx** ctx) {
+    if (!ctx) return fail(FHE_B200_ERR_INVALID, "ctx_create: null out pointer");
+    *ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(FHE_B200_ERR_NO_DEVICE,
+                    "ctx_create: no CUDA device (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(FHE_B200_ERR_INVALID, "ctx_create: device %d out of range", device);
+    CU(cudaSetDevice(device));
+    fhe_b200_ctx* c = new (std::nothrow) fhe_b200_ctx();
+    if (!c) return fail(FHE_B200_ERR_INVALID, "ctx_create: out of host memory");
+    c->device = device;
+    e = cudaGetDeviceProperties(&c->prop, device);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaGetDeviceProperties"); }
+    if (c->prop.major < 10) {
+        int maj = c->prop.major, min = c->prop.minor;
+        delete c;
+        return fail(FHE_B200_ERR_NO_DEVICE, "ctx_create: device is sm_%d%d; this library is built for sm_100a only", maj, min);
+    }
+    c->launches_at_create = g_launches.load();
+    *ctx = c;
+    return FHE_B200_OK;
+}
+
+int fhe_b200_ctx_destroy(fhe_b200_ctx* ctx) {
+    delete ctx;
+    return FHE_B200_OK;
+}
+
+int fhe_b200_device_info(fhe_b200_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
+                         uint64_t* total_mem) {
+    REQUIRE(ctx, "null ctx");
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    if (total_mem) *total_mem = (uint64_t)ctx->prop.totalGlobalMem;
+    return FHE_B200_OK;
+}
+
+uint64_t fhe_b200_launch_count(fhe_b200_ctx* ctx) {
+    return g_launches.load() - (ctx ? ctx->launches_at_create : 0);
+}
+
+// ------------------------------------------------------------------------------- client side
+int fhe_b200_secret_key(fhe_b200_ctx* ctx, uint64_t key_seed, uint32_t key_id, int64_t dim, uint8_t* d_key,
+                        void* stream) {
+    REQUIRE(ctx && d_key, "null argument");
+    REQUIRE(dim > 0 && key_id < 256, "dim must be > 0 and key_id < 256");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_secret_key(key_seed, key_id, dim, d_key, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+static int check_lwe_shape(int32_t n, int64_t stride, const char* fn) {
+    if (n <= 0) return fail(FHE_B200_ERR_INVALID, "%s: n must be > 0", fn);
+    if (stride < n + 1 || (stride & 1)) return fail(FHE_B200_ERR_INVALID, "%s: stride must be even and >= n+1", fn);
+    return FHE_B200_OK;
+}
+
+int fhe_b200_lwe_encrypt(fhe_b200_ctx* ctx, const uint8_t* d_key, int32_t n, int64_t stride, const int64_t* d_msgs,
+                         int64_t count, int32_t shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base,
+                         uint32_t purpose, uint64_t* d_ct, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(count >= 0, "negative count");
+    if (count == 0) return FHE_B200_OK;
+    REQUIRE(d_key && d_msgs && d_ct, "null device pointer");
+    REQUIRE(shift >= 0 && shift < 64 && purpose < 256, "shift must be in [0,64), purpose < 256");
+    if (int r = check_lwe_shape(n, stride, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_encrypt(d_key, n, stride, d_msgs, count, shift, sigma_abs, enc_seed, ct_base, purpose, d_ct,
+                               (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_lwe_phase(fhe_b200_ctx* ctx, const uint8_t* d_key, int32_t n, int64_t stride, const uint64_t* d_ct,
+                       int64_t count, uint64_t* d_phase, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(count >= 0, "negative count");
+    if (count == 0) return FHE_B200_OK;
+    REQUIRE(d_key && d_ct && d_phase, "null device pointer");
+    if (int r = check_lwe_shape(n, stride, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_phase(d_key, n, stride, d_ct, count, 0, false, d_phase, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_lwe_decrypt(fhe_b200_ctx* ctx, const uint8_t* d_key, int32_t n, int64_t stride, const uint64_t* d_ct,
+                         int64_t count, int32_t shift, int64_t* d_msgs, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(count >= 0, "negative count");
+    if (count == 0) return FHE_B200_OK;
+    REQUIRE(d_key && d_ct && d_msgs, "null device pointer");
+    REQUIRE(shift >= 0 && shift < 64, "shift must be in [0,64)");
+    if (int r = check_lwe_shape(n, stride, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_phase(d_key, n, stride, d_ct, count, shift, true, (uint64_t*)d_msgs, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------- server side
+int fhe_b200_lincomb(fhe_b200_ctx* ctx, const uint64_t* d_ct, int64_t B, int32_t d, int32_t n, int64_t stride,
+                     const int64_t* d_W, int32_t M, const int64_t* h_bias, int32_t shift, uint64_t* d_out,
+                     void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_ct && d_W && d_out, "null device pointer");
+    REQUIRE(d > 0 && d <= 4096, "d must be in [1,4096]");
+    REQUIRE(M == 1 || M == 2, "M must be 1 or 2");
+    REQUIRE(shift >= 0 && shift < 64, "shift must be in [0,64)");
+    if (int r = check_lwe_shape(n, stride, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    int64_t b0 = h_bias ? h_bias[0] : 0, b1 = (h_bias && M == 2) ? h_bias[1] : 0;
+    CU(fhe::launch_lincomb(d_ct, B, d, n, stride, d_W, M, false, b0, b1, shift, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_accumulate(fhe_b200_ctx* ctx, uint64_t* d_acc, const uint64_t* d_x, int64_t words, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(words >= 0, "negative size");
+    if (words == 0) return FHE_B200_OK;
+    REQUIRE(d_acc && d_x, "null device pointer");
+    REQUIRE((((uintptr_t)d_acc | (uintptr_t)d_x) & 15) == 0, "buffers must be 16-byte aligned");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_accumulate(d_acc, d_x, words, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------- KS / PBS
+static int check_pbs_params(const fhe_b200_pbs_params* p, const char* fn) {
+    if (!p) return fail(FHE_B200_ERR_INVALID, "%s: null params", fn);
+    const char* why = nullptr;
+    if (!fhe::pbs_params_supported(*p, &why)) return fail(FHE_B200_ERR_INVALID, "%s: unsupported parameters: %s", fn, why);
+    return FHE_B200_OK;
+}
+
+uint64_t fhe_b200_ksk_words(const fhe_b200_pbs_params* p) {
+    return p ? (uint64_t)p->k * p->N * p->l_ks * (uint64_t)(p->n + 1) : 0;
+}
+uint64_t fhe_b200_bsk_words(const fhe_b200_pbs_params* p) {
+    return p ? (uint64_t)p->n * (p->k + 1) * p->l_pbs * (uint64_t)(p->k + 1) * p->N : 0;
+}
+
+int fhe_b200_ksk_gen(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint8_t* d_S_big,
+                     const uint8_t* d_s_small, uint64_t evk_seed, uint64_t* d_ksk, void* stream) {
+    REQUIRE(ctx && d_S_big && d_s_small && d_ksk, "null argument");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_ksk_gen(*p, d_S_big, d_s_small, evk_seed, d_ksk, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_bsk_gen(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint8_t* d_s_small,
+                     const uint8_t* d_S_big, uint64_t evk_seed, uint64_t* d_bsk, void* stream) {
+    REQUIRE(ctx && d_S_big && d_s_small && d_bsk, "null argument");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_bsk_gen(*p, d_s_small, d_S_big, evk_seed, d_bsk, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_bsk_to_fourier(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint64_t* d_bsk, double* d_bskf,
+                            void* stream) {
+    REQUIRE(ctx && d_bsk && d_bskf, "null argument");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_bsk_to_fourier(*p, d_bsk, d_bskf, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_keyswitch(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint64_t* d_ksk, const uint64_t* d_in,
+                       int64_t B, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_ksk && d_in && d_out, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_keyswitch(*p, d_ksk, d_in, B, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_pbs(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_bskf, const uint64_t* d_in,
+                 int64_t B, const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_bskf && d_in && d_luts && d_out, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_pbs(*p, d_bskf, d_in, B, d_luts, d_lut_index, d_out, ctx->prop.multiProcessorCount,
+                       (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------- similarity model
+int fhe_b200_similarity_create(fhe_b200_ctx* ctx, const fhe_b200_similarity_spec* spec, const int64_t* h_q_w,
+                               fhe_b200_similarity** sim) {
+    REQUIRE(ctx && spec && h_q_w && sim, "null argument");
+    *sim = nullptr;
+    REQUIRE(spec->d > 0 && spec->d <= 4096, "d must be in [1,4096]");
+    REQUIRE(spec->n_bits >= 1 && spec->n_bits <= 16, "n_bits must be in [1,16]");
+    REQUIRE(spec->shift >= 0 && spec->shift < 64, "shift must be in [0,64)");
+    if (int r = check_lwe_shape(spec->n, spec->stride, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    fhe_b200_similarity* s = new (std::nothrow) fhe_b200_similarity();
+    if (!s) return fail(FHE_B200_ERR_INVALID, "similarity_create: out of host memory");
+    s->ctx = ctx;
+    s->spec = *spec;
+    s->M = spec->two_outputs ? 2 : 1;
+    s->second_is_sum = spec->two_outputs != 0;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) goto bad;
+    if ((e = cudaMalloc(&s->d_key, (size_t)spec->n)) != cudaSuccess) goto bad;
+    if ((e = cudaMalloc(&s->d_W, sizeof(int64_t) * (size_t)s->M * spec->d)) != cudaSuccess) goto bad;
+    if ((e = cudaMemcpyAsync(s->d_W, h_q_w, sizeof(int64_t) * spec->d, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess) goto bad;
+    if (s->M == 2) {
+        // second weight row is all ones (the kernel special-cases it, the row is kept for clarity)
+        int64_t* ones = new int64_t[spec->d];
+        for (int i = 0; i < spec->d; ++i) ones[i] = 1;
+        e = cudaMemcpyAsync(s->d_W + spec->d, ones, sizeof(int64_t) * spec->d, cudaMemcpyHostToDevice, s->stream);
+        cudaStreamSynchronize(s->stream);
+        delete[] ones;
+        if (e != cudaSuccess) goto bad;
+    }
+    if ((e = fhe::launch_secret_key(spec->key_seed, 2, spec->n, s->d_key, s->stream)) != cudaSuccess) goto bad;
+    if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) goto bad;
+    *sim = s;
+    return FHE_B200_OK;
+bad:
+    fhe_b200_similarity_destroy(s);
+    return cuda_fail(e, "similarity_create");
+}
+
+int fhe_b200_similarity_destroy(fhe_b200_similarity* s) {
+    if (!s) return FHE_B200_OK;
+    cudaSetDevice(s->ctx->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->d_key) cudaFree(s->d_key);
+    if (s->d_W) cudaFree(s->d_W);
+    s->X.release(); s->q.release(); s->ct.release(); s->out.release(); s->m.release(); s->y.release(); s->qy.release();
+    s->hX.release(); s->hy.release(); s->hqy.release();
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_encrypt(fhe_b200_similarity* s, const float* d_X, int64_t B, uint64_t enc_seed,
+                                uint64_t ct_base, uint64_t* d_ct, void* stream) {
+    REQUIRE(s, "null model");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_X && d_ct, "null device pointer");
+    const auto& sp = s->spec;
+    CU(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t cnt = B * sp.d;
+    CU(s->q.reserve(sizeof(int64_t) * (size_t)cnt));
+    const int64_t qmin = -sp.x_offset, qmax = (1LL << sp.n_bits) - 1 - sp.x_offset;
+    CU(fhe::launch_quantize(d_X, cnt, sp.x_scale, sp.x_zero_point, qmin, qmax, (int64_t*)s->q.p, st));
+    CU(fhe::launch_lwe_encrypt(s->d_key, sp.n, sp.stride, (const int64_t*)s->q.p, cnt, sp.shift, sp.sigma_abs,
+                               enc_seed, ct_base, FHE_B200_PUR_INPUT, d_ct, st));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_run(fhe_b200_similarity* s, const uint64_t* d_ct, int64_t B, uint64_t* d_out, void* stream) {
+    REQUIRE(s, "null model");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_ct && d_out, "null device pointer");
+    const auto& sp = s->spec;
+    CU(cudaSetDevice(s->ctx->device));
+    CU(fhe::launch_lincomb(d_ct, B, sp.d, sp.n, sp.stride, s->d_W, s->M, s->second_is_sum, 0, 0, sp.shift, d_out,
+                           (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_decrypt(fhe_b200_similarity* s, const uint64_t* d_out, int64_t B, double* d_y,
+                                int64_t* d_q_y, void* stream) {
+    REQUIRE(s, "null model");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_out && (d_y || d_q_y), "null device pointer");
+    const auto& sp = s->spec;
+    CU(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(s->m.reserve(sizeof(int64_t) * (size_t)B * s->M));
+    CU(fhe::launch_lwe_phase(s->d_key, sp.n, sp.stride, d_out, B * s->M, sp.shift, true, (uint64_t*)s->m.p, st));
+    CU(fhe::launch_similarity_finalize((const int64_t*)s->m.p, B, s->M, sp.w_zero_point, sp.q_bias, sp.out_scale,
+                                       sp.out_zero_point, d_y, d_q_y, st));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, int64_t B, uint64_t enc_seed,
+                                     uint64_t ct_base, double* h_y, int64_t* h_q_y) {
+    REQUIRE(s, "null model");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(h_X && (h_y || h_q_y), "null host pointer");
+    const auto& sp = s->spec;
+    CU(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->stream;
+    const size_t xbytes = sizeof(float) * (size_t)B * sp.d;
+    CU(s->X.reserve(xbytes));
+    CU(s->hX.reserve(xbytes));
+    // ciphertexts are materialised in HBM in chunks of at most ~2 GiB
+    const size_t row_bytes = sizeof(uint64_t) * (size_t)sp.d * sp.stride;
+    int64_t chunk = (int64_t)(((size_t)2 << 30) / row_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    CU(s->ct.reserve(row_bytes * (size_t)chunk));
+    CU(s->out.reserve(sizeof(uint64_t) * (size_t)chunk * s->M * sp.stride));
+    CU(s->y.reserve(sizeof(double) * (size_t)B));
+    CU(s->qy.reserve(sizeof(int64_t) * (size_t)B));
+    CU(s->hy.reserve(sizeof(double) * (size_t)B));
+    CU(s->hqy.reserve(sizeof(int64_t) * (size_t)B));
+    memcpy(s->hX.p, h_X, xbytes);  // stage through pinned memory so the copy is truly async
+    CU(cudaMemcpyAsync(s->X.p, s->hX.p, xbytes, cudaMemcpyHostToDevice, st));
+    for (int64_t r0 = 0; r0 < B; r0 += chunk) {
+        const int64_t rows = (B - r0 < chunk) ? (B - r0) : chunk;
+        if (int r = fhe_b200_similarity_encrypt(s, (const float*)s->X.p + r0 * sp.d, rows, enc_seed,
+                                                ct_base + (uint64_t)(r0 * sp.d), (uint64_t*)s->ct.p, st)) return r;
+        if (int r = fhe_b200_similarity_run(s, (const uint64_t*)s->ct.p, rows, (uint64_t*)s->out.p, st)) return r;
+        if (int r = fhe_b200_similarity_decrypt(s, (const uint64_t*)s->out.p, rows, (double*)s->y.p + r0,
+                                                (int64_t*)s->qy.p + r0, st)) return r;
+    }
+    CU(cudaMemcpyAsync(s->hy.p, s->y.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s->hqy.p, s->qy.p, sizeof(int64_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_y) memcpy(h_y, s->hy.p, sizeof(double) * (size_t)B);
+    if (h_q_y) memcpy(h_q_y, s->hqy.p, sizeof(int64_t) * (size_t)B);
+    return FHE_B200_OK;
+}
+
+}  // extern "C"

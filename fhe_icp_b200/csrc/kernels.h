@@ -1,0 +1,46 @@
+// kernels.h -- internal launcher interface between api.cu and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/fhe_b200.h"
+
+namespace fhe {
+
+void count_launch(int n = 1);  // api.cu: bumps the per-process launch counter
+
+// lwe.cu
+cudaError_t launch_secret_key(uint64_t key_seed, uint32_t key_id, int64_t dim, uint8_t* d_key, cudaStream_t s);
+cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
+                               int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
+                               uint64_t* d_ct, cudaStream_t s);
+cudaError_t launch_lwe_phase(const uint8_t* d_key, int n, int64_t stride, const uint64_t* d_ct, int64_t count,
+                             int shift, bool decode, uint64_t* d_out, cudaStream_t s);
+cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_t stride, const int64_t* d_W, int M,
+                           bool second_is_sum, int64_t bias0, int64_t bias1, int shift, uint64_t* d_out,
+                           cudaStream_t s);
+cudaError_t launch_accumulate(uint64_t* d_acc, const uint64_t* d_x, int64_t words, cudaStream_t s);
+cudaError_t launch_quantize(const float* d_X, int64_t count, double scale, int64_t zp, int64_t qmin, int64_t qmax,
+                            int64_t* d_q, cudaStream_t s);
+cudaError_t launch_similarity_finalize(const int64_t* d_m, int64_t B, int M, int64_t zp_w, int64_t q_bias,
+                                       double out_scale, int64_t out_zp, double* d_y, int64_t* d_q_y,
+                                       cudaStream_t s);
+
+// keys.cu
+cudaError_t launch_ksk_gen(const fhe_b200_pbs_params& p, const uint8_t* d_S_big, const uint8_t* d_s_small,
+                           uint64_t evk_seed, uint64_t* d_ksk, cudaStream_t s);
+cudaError_t launch_bsk_gen(const fhe_b200_pbs_params& p, const uint8_t* d_s_small, const uint8_t* d_S_big,
+                           uint64_t evk_seed, uint64_t* d_bsk, cudaStream_t s);
+
+// keyswitch.cu
+cudaError_t launch_keyswitch(const fhe_b200_pbs_params& p, const uint64_t* d_ksk, const uint64_t* d_in, int64_t B,
+                             uint64_t* d_out, cudaStream_t s);
+
+// pbs.cu
+cudaError_t launch_bsk_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* d_bsk, double* d_bskf,
+                                  cudaStream_t s);
+cudaError_t launch_pbs(const fhe_b200_pbs_params& p, const double* d_bskf, const uint64_t* d_in, int64_t B,
+                       const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
+                       cudaStream_t s);
+bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why);
+
+}  // namespace fhe

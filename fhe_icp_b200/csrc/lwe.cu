@@ -1,0 +1,309 @@
+// lwe.cu -- LWE over the 64-bit torus: key sampling, batched encrypt / decrypt, and the
+// batched encrypted dot product (LWE linear combination) that is the reference's whole
+// compiled circuit (Concrete-ML LinearRegression, /root/reference/fhe_similarity.py:88-90,151;
+// SURVEY.md Appendix A.3).  All arithmetic is wrapping u64 and therefore bit-exact.
+//
+// Roofline: every kernel here is HBM-bound (0.125 u64 MAC per byte for the dot product).
+// Layout: ciphertext rows of `stride` u64 words (stride even => every row is 16-byte
+// aligned), so a warp reads 512 contiguous bytes per 128-bit load instruction.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fhe {
+
+// ----------------------------------------------------------------------------- secret key
+// bit j of key `key_id` = bit (j%32) of word (j%128)/32 of Philox block j/128.
+__global__ void secret_key_kernel(uint64_t key_seed, uint32_t key_id, int64_t dim, uint8_t* __restrict__ key) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    u32x4 r = rng_block(key_seed, FHE_B200_KIND_SK | (key_id << 8), 0, (uint32_t)(j >> 7));
+    uint32_t w = (uint32_t)(j & 127) >> 5;
+    uint32_t word = w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w));
+    key[j] = (word >> (j & 31)) & 1u;
+}
+
+cudaError_t launch_secret_key(uint64_t key_seed, uint32_t key_id, int64_t dim, uint8_t* d_key, cudaStream_t s) {
+    if (dim <= 0) return cudaSuccess;
+    secret_key_kernel<<<(unsigned)((dim + 255) / 256), 256, 0, s>>>(key_seed, key_id, dim, d_key);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------- encrypt
+// One warp per ciphertext.  Lane L generates Philox blocks L, L+32, ... (two mask words
+// each), stores them with one 128-bit store (512 B per warp instruction) and accumulates
+// <a, s> against the key bits held in shared memory.
+constexpr int ENC_WARPS = 8;
+
+__global__ void __launch_bounds__(ENC_WARPS * 32)
+lwe_encrypt_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, const int64_t* __restrict__ msgs,
+                   int64_t count, int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base,
+                   uint32_t purpose, uint64_t* __restrict__ out) {
+    extern __shared__ uint32_t skey[];  // packed key bits, ceil(n/32) words (+1 pad)
+    const int kw = (n + 31) / 32 + 1;
+    for (int i = threadIdx.x; i < kw; i += blockDim.x) {
+        uint32_t w = 0;
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {
+            int j = i * 32 + b;
+            if (j < n) w |= (uint32_t)(key[j] & 1u) << b;
+        }
+        skey[i] = w;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
+    if (c >= count) return;
+    const uint64_t id = ct_base + (uint64_t)c;
+    uint64_t* ct = out + c * stride;
+    const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
+    uint64_t dot = 0;
+    const int nblk = (n + 1) / 2;
+    for (int blk = lane; blk < nblk; blk += 32) {
+        u32x4 r = rng_block(enc_seed, dom, id, (uint32_t)blk);
+        uint64_t a0 = lo64(r), a1 = hi64(r);
+        const int w = 2 * blk;
+        uint32_t bits = skey[w >> 5] >> (w & 31);  // w even => bit w and w+1 live in the same word
+        dot += a0 & (0 - (uint64_t)(bits & 1u));
+        if (w + 1 < n) {
+            dot += a1 & (0 - (uint64_t)((bits >> 1) & 1u));
+            st_stream_u64x2(ct + w, u64x2{a0, a1});
+        } else {
+            ct[w] = a0;  // n odd: the second word of the last block is unused
+        }
+    }
+    dot = warp_sum_u64(dot);
+    if (lane == 0) {
+        int64_t e = gaussian_i64(enc_seed, FHE_B200_KIND_NOISE | (purpose << 8), id, 0, sigma_abs);
+        ct[n] = dot + ((uint64_t)msgs[c] << shift) + (uint64_t)e;
+    }
+    for (int64_t w = n + 1 + lane; w < stride; w += 32) ct[w] = 0;
+}
+
+cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
+                               int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
+                               uint64_t* d_ct, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
+    unsigned grid = (unsigned)((count + ENC_WARPS - 1) / ENC_WARPS);
+    lwe_encrypt_kernel<<<grid, ENC_WARPS * 32, smem, s>>>(d_key, n, stride, d_msgs, count, shift, sigma_abs,
+                                                          enc_seed, ct_base, purpose, d_ct);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------- phase / decrypt
+// One warp per ciphertext: mu = b - <a, s>;  decode: m = (mu + Delta/2) >> shift (arithmetic).
+constexpr int DEC_WARPS = 8;
+
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+lwe_phase_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, const uint64_t* __restrict__ cts,
+                 int64_t count, int shift, bool decode, uint64_t* __restrict__ out) {
+    extern __shared__ uint32_t skey[];
+    const int kw = (n + 31) / 32 + 1;
+    for (int i = threadIdx.x; i < kw; i += blockDim.x) {
+        uint32_t w = 0;
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {
+            int j = i * 32 + b;
+            if (j < n) w |= (uint32_t)(key[j] & 1u) << b;
+        }
+        skey[i] = w;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
+    if (c >= count) return;
+    const uint64_t* ct = cts + c * stride;
+    uint64_t dot = 0;
+    const int nvec = n / 2;  // full pairs of mask words
+#pragma unroll 4
+    for (int v = lane; v < nvec; v += 32) {
+        u64x2 a = ld_stream_u64x2(ct + 2 * v);
+        uint32_t bits = skey[(2 * v) >> 5] >> ((2 * v) & 31);
+        dot += a.x & (0 - (uint64_t)(bits & 1u));
+        dot += a.y & (0 - (uint64_t)((bits >> 1) & 1u));
+    }
+    if ((n & 1) && lane == 0) {
+        int w = n - 1;
+        dot += ct[w] & (0 - (uint64_t)((skey[w >> 5] >> (w & 31)) & 1u));
+    }
+    dot = warp_sum_u64(dot);
+    if (lane == 0) {
+        uint64_t mu = ct[n] - dot;
+        if (decode) {
+            uint64_t v = mu + (shift > 0 ? (1ULL << (shift - 1)) : 0ULL);
+            out[c] = (uint64_t)((int64_t)v >> shift);
+        } else {
+            out[c] = mu;
+        }
+    }
+}
+
+cudaError_t launch_lwe_phase(const uint8_t* d_key, int n, int64_t stride, const uint64_t* d_ct, int64_t count,
+                             int shift, bool decode, uint64_t* d_out, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
+    unsigned grid = (unsigned)((count + DEC_WARPS - 1) / DEC_WARPS);
+    lwe_phase_kernel<<<grid, DEC_WARPS * 32, smem, s>>>(d_key, n, stride, d_ct, count, shift, decode, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------- encrypted dot product
+// out[b][m][:] = sum_j W[m][j] * ct[b][j][:].  Each thread owns one 16-byte column pair of
+// one row b and streams the d ciphertexts of that row (stride*8 bytes apart); UNROLL
+// independent 128-bit loads are in flight per thread.  Inputs are read exactly once
+// (L1::no_allocate), the M output rows are written once.
+constexpr int LC_THREADS = 256;
+
+template <int M, bool SECOND_IS_SUM, int UNROLL>
+__global__ void __launch_bounds__(LC_THREADS)
+lincomb_kernel(const uint64_t* __restrict__ ct, int d, int n_words, int64_t stride, int chunks,
+               const int64_t* __restrict__ W, uint64_t bias0, uint64_t bias1, uint64_t* __restrict__ out) {
+    extern __shared__ int64_t sW[];  // [M][d]
+    for (int i = threadIdx.x; i < M * d; i += blockDim.x) sW[i] = W[i];
+    __syncthreads();
+    const int64_t b = blockIdx.x / chunks;
+    const int chunk = blockIdx.x - (int)(b * chunks);
+    const int w0 = 2 * (chunk * LC_THREADS + threadIdx.x);
+    if (w0 >= stride) return;
+    const uint64_t* p = ct + (size_t)b * d * stride + w0;
+    uint64_t a0x = 0, a0y = 0, a1x = 0, a1y = 0;
+    int j = 0;
+    for (; j + UNROLL <= d; j += UNROLL) {
+        u64x2 x[UNROLL];
+        static_assert(UNROLL % 4 == 0, "loads are issued in blocks of four");
+#pragma unroll
+        for (int u = 0; u < UNROLL; u += 4) {
+            const uint64_t* q = p + (size_t)(j + u) * stride;
+            ld_stream_u64x2_x4(q, q + stride, q + 2 * stride, q + 3 * stride, x[u], x[u + 1], x[u + 2], x[u + 3]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            uint64_t w = (uint64_t)sW[j + u];
+            a0x += w * x[u].x;
+            a0y += w * x[u].y;
+            if (M == 2) {
+                if (SECOND_IS_SUM) {
+                    a1x += x[u].x;
+                    a1y += x[u].y;
+                } else {
+                    uint64_t w1 = (uint64_t)sW[d + j + u];
+                    a1x += w1 * x[u].x;
+                    a1y += w1 * x[u].y;
+                }
+            }
+        }
+    }
+    for (; j < d; ++j) {
+        u64x2 x = ld_stream_u64x2(p + (size_t)j * stride);
+        uint64_t w = (uint64_t)sW[j];
+        a0x += w * x.x;
+        a0y += w * x.y;
+        if (M == 2) {
+            uint64_t w1 = SECOND_IS_SUM ? 1ULL : (uint64_t)sW[d + j];
+            a1x += w1 * x.x;
+            a1y += w1 * x.y;
+        }
+    }
+    // body word gets the clear bias; padding words are forced to zero
+    const int nb = n_words - 1;
+    if (w0 == nb) { a0x += bias0; a1x += bias1; }
+    if (w0 + 1 == nb) { a0y += bias0; a1y += bias1; }
+    if (w0 >= n_words) { a0x = 0; a1x = 0; }
+    if (w0 + 1 >= n_words) { a0y = 0; a1y = 0; }
+    uint64_t* o = out + (size_t)b * M * stride + w0;
+    st_stream_u64x2(o, u64x2{a0x, a0y});
+    if (M == 2) st_stream_u64x2(o + stride, u64x2{a1x, a1y});
+}
+
+cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_t stride, const int64_t* d_W, int M,
+                           bool second_is_sum, int64_t bias0, int64_t bias1, int shift, uint64_t* d_out,
+                           cudaStream_t s) {
+    if (B <= 0) return cudaSuccess;
+    const int vecs = (int)(stride / 2);
+    const int chunks = (vecs + LC_THREADS - 1) / LC_THREADS;
+    const int64_t grid64 = B * chunks;
+    if (grid64 > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)grid64;
+    const size_t smem = (size_t)M * d * sizeof(int64_t);
+    const uint64_t b0 = (uint64_t)bias0 << shift, b1 = (uint64_t)bias1 << shift;
+    constexpr int U = 8;
+    if (M == 1)
+        lincomb_kernel<1, false, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, chunks, d_W, b0, b1, d_out);
+    else if (second_is_sum)
+        lincomb_kernel<2, true, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, chunks, d_W, b0, b1, d_out);
+    else
+        lincomb_kernel<2, false, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, chunks, d_W, b0, b1, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------- accumulation
+__global__ void accumulate_kernel(uint64_t* __restrict__ acc, const uint64_t* __restrict__ x, int64_t words) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < words) {
+        u64x2 a = *reinterpret_cast<const u64x2*>(acc + i);
+        u64x2 b = ld_stream_u64x2(x + i);
+        a.x += b.x;
+        a.y += b.y;
+        *reinterpret_cast<u64x2*>(acc + i) = a;
+    } else if (i < words) {
+        acc[i] += x[i];
+    }
+}
+
+cudaError_t launch_accumulate(uint64_t* d_acc, const uint64_t* d_x, int64_t words, cudaStream_t s) {
+    if (words <= 0) return cudaSuccess;
+    int64_t vecs = (words + 1) / 2;
+    accumulate_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, s>>>(d_acc, d_x, words);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------- quantize / finalize
+// q = clip(rint(x / scale + zp), qmin, qmax) in float64, the UniformQuantizer rule
+// (SURVEY.md Appendix A.1); IEEE div/add/rint => identical to numpy.
+__global__ void quantize_kernel(const float* __restrict__ X, int64_t count, double scale, double zp, double qmin,
+                                double qmax, int64_t* __restrict__ q) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double v = rint(__dadd_rn(__ddiv_rn((double)X[i], scale), zp));
+    v = fmin(fmax(v, qmin), qmax);
+    q[i] = (int64_t)v;
+}
+
+cudaError_t launch_quantize(const float* d_X, int64_t count, double scale, int64_t zp, int64_t qmin, int64_t qmax,
+                            int64_t* d_q, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    quantize_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_X, count, scale, (double)zp, (double)qmin,
+                                                                   (double)qmax, d_q);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// q_y = m0 - zp_w * m1 + q_bias;  y = out_scale * (q_y - out_zp)   
+__global__ void similarity_finalize_kernel(const int64_t* __restrict__ m, int64_t B, int M, int64_t zp_w,
+                                           int64_t q_bias, double out_scale, int64_t out_zp,
+                                           double* __restrict__ y, int64_t* __restrict__ q_y) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int64_t m0 = m[b * M];
+    int64_t m1 = M == 2 ? m[b * M + 1] : 0;
+    int64_t q = m0 - zp_w * m1 + q_bias;
+    if (q_y) q_y[b] = q;
+    if (y) y[b] = __dmul_rn(out_scale, (double)(q - out_zp));
+}
+
+cudaError_t launch_similarity_finalize(const int64_t* d_m, int64_t B, int M, int64_t zp_w, int64_t q_bias,
+                                       double out_scale, int64_t out_zp, double* d_y, int64_t* d_q_y,
+                                       cudaStream_t s) {
+    if (B <= 0) return cudaSuccess;
+    similarity_finalize_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(d_m, B, M, zp_w, q_bias, out_scale,
+                                                                         out_zp, d_y, d_q_y);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace fhe

@@ -1,0 +1,185 @@
+"""Torch-tensor front end over the C-ABI: torch owns device memory and streams, every
+operation is a kernel of libfhe_b200.so (see include/fhe_b200.h).  u64 torus words are
+carried in ``torch.int64`` tensors (same bits)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _dev(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("fhe_icp_b200 requires a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _stream(dev: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t: torch.Tensor):
+    return C.c_void_p(t.data_ptr())
+
+
+def _ctx(dev: torch.device) -> N.Context:
+    return N.context(dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+def even_stride(n: int) -> int:
+    """Smallest even row length holding n mask words + the body."""
+    return (n + 2) & ~1
+
+
+def to_u64_numpy(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+def from_u64_numpy(a: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to(device)
+
+
+# ------------------------------------------------------------------------------- client side
+def secret_key(key_seed: int, key_id: int, dim: int, device=None) -> torch.Tensor:
+    dev = _dev(device)
+    key = torch.empty(dim, dtype=torch.uint8, device=dev)
+    N.check(N.lib().fhe_b200_secret_key(_ctx(dev).handle, key_seed, key_id, dim, _ptr(key), _stream(dev)))
+    return key
+
+
+def lwe_encrypt(key: torch.Tensor, msgs: torch.Tensor, shift: int, sigma_abs: float, enc_seed: int,
+                ct_base: int = 0, purpose: int = N.PUR_INPUT, stride: int | None = None) -> torch.Tensor:
+    dev = key.device
+    n = key.numel()
+    stride = stride or even_stride(n)
+    m = msgs.to(device=dev, dtype=torch.int64).contiguous()
+    ct = torch.empty(tuple(m.shape) + (stride,), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_lwe_encrypt(_ctx(dev).handle, _ptr(key), n, stride, _ptr(m), m.numel(), shift,
+                                         float(sigma_abs), enc_seed, ct_base, purpose, _ptr(ct), _stream(dev)))
+    return ct
+
+
+def lwe_phase(key: torch.Tensor, ct: torch.Tensor) -> torch.Tensor:
+    dev = key.device
+    n, stride = key.numel(), ct.shape[-1]
+    ct = ct.contiguous()
+    out = torch.empty(ct.shape[:-1], dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_lwe_phase(_ctx(dev).handle, _ptr(key), n, stride, _ptr(ct), out.numel(), _ptr(out),
+                                       _stream(dev)))
+    return out
+
+
+def lwe_decrypt(key: torch.Tensor, ct: torch.Tensor, shift: int) -> torch.Tensor:
+    dev = key.device
+    n, stride = key.numel(), ct.shape[-1]
+    ct = ct.contiguous()
+    out = torch.empty(ct.shape[:-1], dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_lwe_decrypt(_ctx(dev).handle, _ptr(key), n, stride, _ptr(ct), out.numel(), shift,
+                                         _ptr(out), _stream(dev)))
+    return out
+
+
+# ------------------------------------------------------------------------------- server side
+def lincomb(ct: torch.Tensor, W: torch.Tensor, n: int, bias=None, shift: int = 0,
+            out: torch.Tensor | None = None) -> torch.Tensor:
+    """ct [B,d,stride], W [M,d] (M in {1,2}) -> [B,M,stride]."""
+    dev = ct.device
+    B, d, stride = ct.shape
+    W = W.to(device=dev, dtype=torch.int64).reshape(-1, d).contiguous()
+    M = W.shape[0]
+    if out is None:
+        out = torch.empty((B, M, stride), dtype=torch.int64, device=dev)
+    hb = None
+    if bias is not None:
+        hb = (C.c_int64 * M)(*[int(x) for x in bias])
+    N.check(N.lib().fhe_b200_lincomb(_ctx(dev).handle, _ptr(ct.contiguous()), B, d, n, stride, _ptr(W), M, hb,
+                                     shift, _ptr(out), _stream(dev)))
+    return out
+
+
+def accumulate(acc: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    dev = acc.device
+    assert acc.is_contiguous() and x.is_contiguous() and acc.numel() == x.numel()
+    N.check(N.lib().fhe_b200_accumulate(_ctx(dev).handle, _ptr(acc), _ptr(x), acc.numel(), _stream(dev)))
+    return acc
+
+
+# ------------------------------------------------------------------------------- KS / PBS
+def make_pbs_params(n=742, k=1, N_poly=2048, l_pbs=1, beta_pbs=23, l_ks=5, beta_ks=3,
+                    log2_sigma_lwe=-17.1, log2_sigma_glwe=-51.6) -> N.PBSParams:
+    """Default = the 4-bit (message 2 + carry 2) KS->PBS set stated in DESIGN.md."""
+    return N.PBSParams(n, k, N_poly, l_pbs, beta_pbs, l_ks, beta_ks, 0,
+                       2.0 ** (64 + log2_sigma_lwe), 2.0 ** (64 + log2_sigma_glwe))
+
+
+def ksk_gen(p: N.PBSParams, S_big: torch.Tensor, s_small: torch.Tensor, evk_seed: int) -> torch.Tensor:
+    dev = S_big.device
+    ksk = torch.empty((p.k * p.N, p.l_ks, p.n + 1), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_ksk_gen(_ctx(dev).handle, C.byref(p), _ptr(S_big), _ptr(s_small), evk_seed,
+                                     _ptr(ksk), _stream(dev)))
+    return ksk
+
+
+def bsk_gen(p: N.PBSParams, s_small: torch.Tensor, S_big: torch.Tensor, evk_seed: int) -> torch.Tensor:
+    dev = S_big.device
+    bsk = torch.empty((p.n, p.k + 1, p.l_pbs, p.k + 1, p.N), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_bsk_gen(_ctx(dev).handle, C.byref(p), _ptr(s_small), _ptr(S_big), evk_seed,
+                                     _ptr(bsk), _stream(dev)))
+    return bsk
+
+
+def bsk_to_fourier(p: N.PBSParams, bsk: torch.Tensor) -> torch.Tensor:
+    dev = bsk.device
+    bskf = torch.empty((p.n, p.k + 1, p.l_pbs, p.k + 1, p.N // 2, 2), dtype=torch.float64, device=dev)
+    N.check(N.lib().fhe_b200_bsk_to_fourier(_ctx(dev).handle, C.byref(p), _ptr(bsk.contiguous()), _ptr(bskf),
+                                            _stream(dev)))
+    return bskf
+
+
+def keyswitch(p: N.PBSParams, ksk: torch.Tensor, ct: torch.Tensor) -> torch.Tensor:
+    dev = ct.device
+    ct = ct.contiguous()
+    B = ct.shape[0]
+    assert ct.shape[1] == p.k * p.N + 1
+    out = torch.empty((B, p.n + 1), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_keyswitch(_ctx(dev).handle, C.byref(p), _ptr(ksk), _ptr(ct), B, _ptr(out),
+                                       _stream(dev)))
+    return out
+
+
+def pbs(p: N.PBSParams, bskf: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor,
+        lut_index: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    dev = ct.device
+    ct = ct.contiguous()
+    B = ct.shape[0]
+    assert ct.shape[1] == p.n + 1
+    luts = luts.to(device=dev, dtype=torch.int64).reshape(-1, p.N).contiguous()
+    if out is None:
+        out = torch.empty((B, p.k * p.N + 1), dtype=torch.int64, device=dev)
+    li = None
+    if lut_index is not None:
+        lut_index = lut_index.to(device=dev, dtype=torch.int32).contiguous()
+        li = _ptr(lut_index)
+    N.check(N.lib().fhe_b200_pbs(_ctx(dev).handle, C.byref(p), _ptr(bskf), _ptr(ct), B, _ptr(luts), li, _ptr(out),
+                                 _stream(dev)))
+    return out
+
+
+def make_lut_poly(table, p_bits: int, N_poly: int, delta_out_log2: int) -> np.ndarray:
+    """Accumulator polynomial of a p-bit table lookup (message + 1 padding bit): box m holds
+    table[m] << delta_out_log2 and the polynomial is multiplied by X^(-box/2)."""
+    box = N_poly >> p_bits
+    t = np.asarray(table, dtype=np.int64)
+    if t.size != (1 << p_bits):
+        raise ValueError("table must have 2^p_bits entries")
+    p0 = np.repeat(t, box).astype(np.uint64) << np.uint64(delta_out_log2)
+    half = box // 2
+    out = np.empty(N_poly, dtype=np.uint64)
+    out[: N_poly - half] = p0[half:]
+    out[N_poly - half:] = np.uint64(0) - p0[:half]
+    return out

@@ -1,0 +1,156 @@
+/*
+ * fhe_b200.h -- C-ABI of the B200-native encrypted-similarity engine.
+ *
+ * This is the drop-in boundary for the reference's FHE hot path.  The reference
+ * (shipstone-labs/fhe-icp) has no native interface of its own: it reaches the
+ * arithmetic through Concrete-ML's Python estimator.  Each entry point below cites
+ * the reference call it replaces (paths are relative to the reference tree).
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (FHE_B200_OK) or an error code; the message for the
+ *     calling thread is available from fhe_b200_last_error(); nothing throws.
+ *   - `d_*` pointers are DEVICE pointers owned by the caller (e.g. torch tensors);
+ *     `h_*` pointers are HOST pointers.  `stream` is a cudaStream_t passed as void*.
+ *   - an LWE ciphertext is `stride` little-endian u64 words: n mask words, the body at
+ *     index n, zero padding up to `stride` (stride even, >= n+1).
+ *   - there is no CPU fallback: without a CUDA device ctx_create fails.
+ */
+#ifndef FHE_B200_H
+#define FHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FHE_B200_ABI_VERSION 1
+
+enum {
+    FHE_B200_OK = 0,
+    FHE_B200_ERR_INVALID = 1, /* bad argument */
+    FHE_B200_ERR_CUDA = 2,    /* CUDA runtime error (see last_error) */
+    FHE_B200_ERR_NO_DEVICE = 3,
+    FHE_B200_ERR_STATE = 4    /* object used before it was initialised */
+};
+
+/* RNG stream tags (DESIGN.md "Deterministic randomness") */
+enum { FHE_B200_KIND_SK = 1, FHE_B200_KIND_MASK = 2, FHE_B200_KIND_NOISE = 3 };
+enum { FHE_B200_PUR_INPUT = 0, FHE_B200_PUR_KSK = 1, FHE_B200_PUR_BSK = 2 };
+
+typedef struct fhe_b200_ctx fhe_b200_ctx;
+typedef struct fhe_b200_similarity fhe_b200_similarity;
+
+/* TFHE parameter set for keyswitch + programmable bootstrap.  The reference circuit
+ * fixes none (its compiled circuit has no table lookup, fhe_similarity.py:88-90);
+ * these are the engine's own, stated in DESIGN.md. */
+typedef struct {
+    int32_t n;        /* small LWE dimension */
+    int32_t k;        /* GLWE dimension */
+    int32_t N;        /* polynomial size, power of two */
+    int32_t l_pbs;    /* PBS gadget levels */
+    int32_t beta_pbs; /* PBS gadget base log */
+    int32_t l_ks;     /* keyswitch levels */
+    int32_t beta_ks;  /* keyswitch base log */
+    int32_t _pad;
+    double sigma_lwe_abs;  /* noise std in 2^-64 torus steps */
+    double sigma_glwe_abs;
+} fhe_b200_pbs_params;
+
+/* Quantized linear model + LWE parameters of one compiled similarity circuit.
+ * Mirrors what `LinearRegression(n_bits).fit().compile()` fixes in the reference
+ * (fhe_similarity.py:88-94,120). */
+typedef struct {
+    int32_t d;          /* input features (128 at the reference's configs) */
+    int32_t n_bits;     /* input quantization bits */
+    int32_t n;          /* LWE dimension */
+    int32_t stride;     /* u64 words per ciphertext row */
+    int32_t shift;      /* log2(Delta): message m is encoded as m << shift */
+    int32_t two_outputs;/* 1: also return sum_j ct_j (needed when zp_w != 0) */
+    double sigma_abs;   /* fresh-encryption noise std, 2^-64 torus steps */
+    double x_scale;     /* input quantizer */
+    int64_t x_zero_point;
+    int64_t x_offset;   /* 2^(n_bits-1) for signed inputs */
+    int64_t w_zero_point;
+    int64_t q_bias;
+    double out_scale;   /* y = out_scale * (q_y - out_zero_point) */
+    int64_t out_zero_point;
+    uint64_t key_seed;  /* client secret key seed (key_id 2) */
+} fhe_b200_similarity_spec;
+
+/* ---- context ---------------------------------------------------------------- */
+int fhe_b200_abi_version(void);
+const char *fhe_b200_last_error(void);
+int fhe_b200_ctx_create(int device, fhe_b200_ctx **ctx);
+int fhe_b200_ctx_destroy(fhe_b200_ctx *ctx);
+int fhe_b200_device_info(fhe_b200_ctx *ctx, int32_t *sm_count, int32_t *cc_major,
+                         int32_t *cc_minor, uint64_t *total_mem);
+/* number of kernels this library has launched since ctx creation (bench.py's gpu_launches) */
+uint64_t fhe_b200_launch_count(fhe_b200_ctx *ctx);
+
+/* ---- client side: keys, encrypt, decrypt --------------------------------------
+ * replaces the lazy keygen / encrypt / decrypt inside
+ * `fhe_circuit.encrypt_run_decrypt` reached from fhe_similarity.py:151 */
+int fhe_b200_secret_key(fhe_b200_ctx *ctx, uint64_t key_seed, uint32_t key_id, int64_t dim,
+                        uint8_t *d_key, void *stream);
+int fhe_b200_lwe_encrypt(fhe_b200_ctx *ctx, const uint8_t *d_key, int32_t n, int64_t stride,
+                         const int64_t *d_msgs, int64_t count, int32_t shift, double sigma_abs,
+                         uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, uint64_t *d_ct,
+                         void *stream);
+int fhe_b200_lwe_phase(fhe_b200_ctx *ctx, const uint8_t *d_key, int32_t n, int64_t stride,
+                       const uint64_t *d_ct, int64_t count, uint64_t *d_phase, void *stream);
+int fhe_b200_lwe_decrypt(fhe_b200_ctx *ctx, const uint8_t *d_key, int32_t n, int64_t stride,
+                         const uint64_t *d_ct, int64_t count, int32_t shift, int64_t *d_msgs,
+                         void *stream);
+
+/* ---- server side: the encrypted dot product -----------------------------------
+ * out[b][m][:] = sum_j W[m][j] * ct[b][j][:]  (+ bias[m] << shift on the body)
+ * replaces the `run` stage of predict(..., fhe="execute"), fhe_similarity.py:151.
+ * d_ct [B][d][stride], d_W [M][d] (M = 1 or 2), h_bias [M] or NULL, d_out [B][M][stride]. */
+int fhe_b200_lincomb(fhe_b200_ctx *ctx, const uint64_t *d_ct, int64_t B, int32_t d, int32_t n,
+                     int64_t stride, const int64_t *d_W, int32_t M, const int64_t *h_bias,
+                     int32_t shift, uint64_t *d_out, void *stream);
+/* ciphertext accumulation: d_acc[i] += d_x[i] over `words` u64 words (wrapping) */
+int fhe_b200_accumulate(fhe_b200_ctx *ctx, uint64_t *d_acc, const uint64_t *d_x, int64_t words,
+                        void *stream);
+
+/* ---- keyswitch + programmable bootstrap ---------------------------------------
+ * north-star primitives; not exercised by the reference's compiled circuit. */
+int fhe_b200_ksk_gen(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_S_big,
+                     const uint8_t *d_s_small, uint64_t evk_seed, uint64_t *d_ksk, void *stream);
+int fhe_b200_bsk_gen(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_s_small,
+                     const uint8_t *d_S_big, uint64_t evk_seed, uint64_t *d_bsk, void *stream);
+uint64_t fhe_b200_ksk_words(const fhe_b200_pbs_params *p);
+uint64_t fhe_b200_bsk_words(const fhe_b200_pbs_params *p);
+int fhe_b200_bsk_to_fourier(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p,
+                            const uint64_t *d_bsk, double *d_bskf, void *stream);
+int fhe_b200_keyswitch(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_ksk,
+                       const uint64_t *d_in, int64_t B, uint64_t *d_out, void *stream);
+int fhe_b200_pbs(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf,
+                 const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
+                 const int32_t *d_lut_index, uint64_t *d_out, void *stream);
+
+/* ---- the reference-facing call with HOST buffers ------------------------------
+ * FHESimilarityModel.predict_encrypted(X) (fhe_similarity.py:142-160): quantize ->
+ * encrypt d ciphertexts per row -> encrypted dot product -> decrypt -> dequantize,
+ * every stage a kernel of this library, ciphertexts materialised in HBM between them. */
+int fhe_b200_similarity_create(fhe_b200_ctx *ctx, const fhe_b200_similarity_spec *spec,
+                               const int64_t *h_q_w, fhe_b200_similarity **sim);
+int fhe_b200_similarity_destroy(fhe_b200_similarity *sim);
+int fhe_b200_similarity_predict_host(fhe_b200_similarity *sim, const float *h_X, int64_t B,
+                                     uint64_t enc_seed, uint64_t ct_base, double *h_y,
+                                     int64_t *h_q_y);
+/* stage-wise variants on device buffers (client encrypt / server run / client decrypt) */
+int fhe_b200_similarity_encrypt(fhe_b200_similarity *sim, const float *d_X, int64_t B,
+                                uint64_t enc_seed, uint64_t ct_base, uint64_t *d_ct, void *stream);
+int fhe_b200_similarity_run(fhe_b200_similarity *sim, const uint64_t *d_ct, int64_t B,
+                            uint64_t *d_out, void *stream);
+int fhe_b200_similarity_decrypt(fhe_b200_similarity *sim, const uint64_t *d_out, int64_t B,
+                                double *d_y, int64_t *d_q_y, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FHE_B200_H */

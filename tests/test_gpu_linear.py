@@ -1,0 +1,168 @@
+"""Parity of the CUDA linear path (through the C-ABI) against the CPU oracle: bit-exact on
+key bits, ciphertext words, linear combinations and decrypted integers."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _u64(t):
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("dim,key_id", [(1, 0), (127, 0), (128, 1), (1423, 2), (2048, 1), (4097, 5)])
+def test_secret_key_bits_match_oracle(O, cuda_dev, dim, key_id):
+    from fhe_icp_b200 import engine as E
+    k = E.secret_key(1234567, key_id, dim, cuda_dev).cpu().numpy()
+    assert np.array_equal(k, O.secret_key(1234567, key_id, dim))
+
+
+@pytest.mark.parametrize("n", [15, 16, 630, 1023, 1423])
+def test_encrypt_words_match_oracle(O, cuda_dev, n):
+    import torch
+    from fhe_icp_b200 import engine as E
+    rng = np.random.RandomState(n)
+    msgs = rng.randint(-128, 128, size=37)
+    shift, sigma = 42, 2.0 ** (64 - 30.0)
+    key = E.secret_key(99, 2, n, cuda_dev)
+    stride = E.even_stride(n)
+    ct = E.lwe_encrypt(key, torch.as_tensor(msgs), shift, sigma, enc_seed=555, ct_base=1000, stride=stride)
+    ref = O.lwe_encrypt(O.secret_key(99, 2, n), msgs, shift, sigma, 555, ct_base=1000, stride=stride)
+    assert np.array_equal(_u64(ct), ref)
+    dec = E.lwe_decrypt(key, ct, shift).cpu().numpy()
+    assert np.array_equal(dec, msgs)
+    ph = _u64(E.lwe_phase(key, ct))
+    assert np.array_equal(ph, O.lwe_phase(O.secret_key(99, 2, n), ref))
+
+
+def test_gaussian_noise_stream_matches_oracle(O, cuda_dev):
+    """Noise is the body minus <a,s> minus the message: compare 4096 samples bit for bit."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    n, shift, sigma = 16, 40, 2.0 ** 39.3
+    key = E.secret_key(5, 2, n, cuda_dev)
+    msgs = np.zeros(4096, dtype=np.int64)
+    ct = E.lwe_encrypt(key, torch.as_tensor(msgs), shift, sigma, enc_seed=77, ct_base=1 << 40)
+    ref = O.lwe_encrypt(O.secret_key(5, 2, n), msgs, shift, sigma, 77, ct_base=1 << 40, stride=E.even_stride(n))
+    assert np.array_equal(_u64(ct), ref)
+    noise = O.lwe_phase(O.secret_key(5, 2, n), ref).view(np.int64).astype(np.float64)
+    assert abs(noise.std() / sigma - 1.0) < 0.05 and abs(noise.mean()) < 0.1 * sigma
+
+
+@pytest.mark.parametrize("B,d,n,M", [(1, 128, 1423, 2), (3, 128, 1023, 1), (5, 7, 33, 2), (2, 256, 630, 2),
+                                      (4, 1, 15, 1), (9, 130, 200, 2)])
+def test_lincomb_bit_exact(O, cuda_dev, B, d, n, M):
+    import torch
+    from fhe_icp_b200 import engine as E
+    rng = np.random.RandomState(B * 1000 + d)
+    stride = E.even_stride(n)
+    ct = rng.randint(0, 2 ** 63, size=(B, d, stride), dtype=np.int64).astype(np.uint64) * np.uint64(2) + \
+        rng.randint(0, 2, size=(B, d, stride)).astype(np.uint64)
+    ct[..., n + 1:] = 0
+    W = rng.randint(-2 ** 40, 2 ** 40, size=(M, d))
+    W[0, : min(d, 3)] = [-128, 127, 0][: min(d, 3)]
+    bias = rng.randint(-1000, 1000, size=M)
+    out = E.lincomb(E.from_u64_numpy(ct, cuda_dev), torch.as_tensor(W), n, bias=bias, shift=41)
+    ref = O.lincomb(ct, W, n, bias=bias, shift=41)
+    assert np.array_equal(_u64(out), ref)
+
+
+def test_lincomb_empty_batch(cuda_dev):
+    import torch
+    from fhe_icp_b200 import engine as E
+    ct = torch.empty((0, 8, 16), dtype=torch.int64, device=cuda_dev)
+    out = E.lincomb(ct, torch.ones((1, 8), dtype=torch.int64), 15)
+    assert out.shape == (0, 1, 16)
+
+
+def test_accumulate(cuda_dev):
+    import torch
+    from fhe_icp_b200 import engine as E
+    rng = np.random.RandomState(0)
+    a = rng.randint(-2 ** 62, 2 ** 62, size=1001, dtype=np.int64)
+    b = rng.randint(-2 ** 62, 2 ** 62, size=1001, dtype=np.int64)
+    acc = torch.as_tensor(a).to(cuda_dev)
+    E.accumulate(acc, torch.as_tensor(b).to(cuda_dev))
+    assert np.array_equal(acc.cpu().numpy().view(np.uint64), a.view(np.uint64) + b.view(np.uint64))
+
+
+@pytest.mark.parametrize("fit_dtype,n_bits", [(np.float32, 8), (np.float64, 8), (np.float32, 4), (np.float32, 12)])
+def test_predict_encrypted_equals_clear_circuit(O, cuda_dev, fit_dtype, n_bits):
+    """The reference's invariant (test_fhe.py:56-57; fhe_similarity.py:268-269): FHE result ==
+    clear quantized result -- here exactly, on the integers and on the float scores."""
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=n_bits, seed=7, verbose=False)
+    X, y = m._prepare_training_data(600)
+    m.train(X.astype(fit_dtype), y.astype(fit_dtype))
+    m.compile(X[:10])
+    Xt = X[:200]
+    fhe = m.predict_encrypted(Xt)
+    clear = m.predict_clear(Xt)
+    assert np.array_equal(fhe, clear)
+    # independent restatement of the quantizer + circuit (oracle/oracle.py)
+    s = m.model.spec
+    sc, zp, off = O.uniform_quantizer_params(X.astype(fit_dtype), n_bits, True)
+    assert (sc, zp, off) == (s.input_q.scale, s.input_q.zero_point, s.input_q.offset)
+    q = O.quantize(Xt, sc, zp, off, n_bits)
+    qy = O.clear_circuit(q, s.q_weights, s.weight_q.zero_point, s.q_bias)
+    y2, qy2 = m.model.fhe_circuit.encrypt_run_decrypt(Xt, return_q=True)
+    assert np.array_equal(qy2, qy)
+    assert np.array_equal(y2, clear)
+
+
+def test_split_api_ciphertexts_match_oracle(O, cuda_dev):
+    """keygen / encrypt / run / decrypt: every intermediate ciphertext equals the oracle's."""
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=3, verbose=False)
+    X, _ = m.train(n_samples=300)
+    m.compile(X[:10])
+    c = m.model.fhe_circuit
+    Xt = X[:6]
+    ct = m.encrypt(Xt)
+    s = O.secret_key(c.key_seed, 2, c.lwe.n)
+    q = m.model.quantize_input(Xt)
+    ref_ct = O.lwe_encrypt(s, q, c.lwe.shift, c.lwe.sigma_abs, c.enc_seed, ct_base=0, stride=c.lwe.stride)
+    assert np.array_equal(_u64(ct).reshape(-1, c.lwe.stride), ref_ct)
+    out = m.run(ct)
+    W = np.stack([c.spec.q_weights, np.ones_like(c.spec.q_weights)]) if c.two_outputs else c.spec.q_weights[None]
+    ref_out = O.lincomb(ref_ct.reshape(6, 128, -1), W, c.lwe.n)
+    assert np.array_equal(_u64(out), ref_out)
+    y, qy = m.decrypt(out, return_q=True)
+    assert np.array_equal(qy, c.spec.circuit(q))
+    assert np.array_equal(y, m.predict_clear(Xt))
+
+
+def test_toy_linear_model_y_equals_2x(cuda_dev):
+    """The reference's smoke test (test_fhe.py:10-57): y = 2x, x = 7 -> ~14, |fhe - clear| < 0.01."""
+    from fhe_icp_b200 import LinearRegression
+    X = np.array([[1], [2], [3], [4], [5], [6]], dtype=np.float32)
+    y = np.array([2, 4, 6, 8, 10, 12], dtype=np.float32)
+    model = LinearRegression(n_bits=8)
+    model.fit(X, y)
+    model.compile(X)
+    t = np.array([[7]], dtype=np.float32)
+    clear = model.predict(t)
+    fhe = model.predict(t, fhe="execute")
+    assert abs(fhe[0] - clear[0]) < 0.01 and fhe[0] == clear[0]
+    assert abs(clear[0] - 12.0) < 0.2  # x=7 clips to the calibrated range [1,6] -> 12
+    assert model.fhe_circuit.graph.maximum_integer_bit_width() >= 8
+
+
+def test_noise_variance_within_bound(O, cuda_dev):
+    """Output noise of the dot product: measured variance vs sum_j w_j^2 sigma^2 (north star:
+    'noise variance within a stated bound')."""
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=11, verbose=False)
+    X, _ = m.train(n_samples=400)
+    m.compile(X[:10])
+    c = m.model.fhe_circuit
+    Xt = np.tile(X[:64], (8, 1))
+    out = m.run(m.encrypt(Xt))
+    s = O.secret_key(c.key_seed, 2, c.lwe.n)
+    ph = O.lwe_phase(s, _u64(out)).view(np.int64)
+    q = m.model.quantize_input(Xt)
+    exp0 = (q @ c.spec.q_weights).astype(np.int64) << c.lwe.shift
+    err = (ph[:, 0] - exp0).astype(np.float64)
+    pred_std = c.lwe.sigma_abs * np.sqrt(float((c.spec.q_weights.astype(np.float64) ** 2).sum()))
+    assert 0.8 < err.std() / pred_std < 1.2
+    assert np.abs(err).max() < 2.0 ** (c.lwe.shift - 1)
