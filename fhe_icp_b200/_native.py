@@ -16,8 +16,8 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 _SO = _PKG / "libfhe_b200.so"
-_SOURCES = ["api.cu", "lwe.cu", "stubs_tmp.cu"]  # TEMP until KS/PBS land
-_HEADERS = ["common.cuh", "kernels.h", "fft.cuh", "../../include/fhe_b200.h"]
+_SOURCES = ["api.cu", "lwe.cu", "keys.cu", "keyswitch.cu", "pbs.cu", "probe.cu"]
+_HEADERS = ["common.cuh", "kernels.h", "fft.cuh", "lwe_device.cuh", "../../include/fhe_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -100,6 +100,7 @@ SIGNATURES = {
     "fhe_b200_ctx_destroy": (C.c_int, [_vp]),
     "fhe_b200_device_info": (C.c_int, [_vp, _i32p, _i32p, _i32p, C.POINTER(C.c_uint64)]),
     "fhe_b200_launch_count": (C.c_uint64, [_vp]),
+    "fhe_b200_probe_fp64": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "fhe_b200_secret_key": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_int64, _vp, _vp]),
     "fhe_b200_lwe_encrypt": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, C.c_int32, C.c_double,
                                        C.c_uint64, C.c_uint64, C.c_uint32, _vp, _vp]),
@@ -162,6 +163,11 @@ class Context:
         sm, ma, mi, mem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint64()
         check(lib().fhe_b200_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    def probe_fp64_tflops(self) -> float:
+        v = C.c_double()
+        check(lib().fhe_b200_probe_fp64(self._h, C.byref(v)))
+        return v.value
 
     def launch_count(self) -> int:
         return int(lib().fhe_b200_launch_count(self._h))

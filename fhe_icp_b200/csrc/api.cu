@@ -148,6 +148,13 @@ uint64_t fhe_b200_launch_count(fhe_b200_ctx* ctx) {
     return g_launches.load() - (ctx ? ctx->launches_at_create : 0);
 }
 
+int fhe_b200_probe_fp64(fhe_b200_ctx* ctx, double* tflops) {
+    REQUIRE(ctx && tflops, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::probe_fp64(ctx->prop.multiProcessorCount, tflops, nullptr));
+    return FHE_B200_OK;
+}
+
 // ------------------------------------------------------------------------------- client side
 int fhe_b200_secret_key(fhe_b200_ctx* ctx, uint64_t key_seed, uint32_t key_id, int64_t dim, uint8_t* d_key,
                         void* stream) {

@@ -1,0 +1,245 @@
+// fft.cuh -- negacyclic transform of a degree-2048 real polynomial as a 1024-point complex
+// FFT (fold + twist), organised as 32 x 32 so that ONE WARP transforms one polynomial:
+//
+//   j = j1 + 32*j2 (time),  k = k2 + 32*k1 (frequency),  W = exp(2*pi*i/1024)
+//   pass 1  lane j1 : 32-point DFT over j2 held in registers           -> index k2
+//           multiply by W^(j1*k2) * omega^j1   (omega = exp(2*pi*i/4096), the twist)
+//   transpose through a 16 KB XOR-swizzled shared-memory tile (the only exchange)
+//   pass 2  lane k2 : 32-point DFT over j1 held in registers           -> index k1
+//
+// Forward passes are radix-2 DIF (natural in, bit-reversed out), inverse passes are DIT
+// (bit-reversed in, natural out), so no permutation is ever executed: "bit reversal" is a
+// compile-time renaming of registers.  Bins come out in natural order k = lane + 32*k1,
+// which is also the layout of the Fourier-domain bootstrapping key.
+//
+// The per-lane code is __host__ __device__ so that tests/ can emulate a warp on the CPU
+// and check the index algebra against the oracle without a GPU.
+#pragma once
+#include <stdint.h>
+
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define FHE_HD __host__ __device__ __forceinline__
+#else
+#define FHE_HD inline
+#endif
+
+namespace fhe {
+namespace nfft {
+
+constexpr int NPOLY = 2048;  // polynomial size N
+constexpr int M = 1024;      // complex FFT size N/2
+constexpr int R = 32;        // radix of each in-register pass = lanes per warp
+
+struct cplx { double x, y; };
+
+#define FHE_W32_RE_LIST                                                                                   \
+    0x1.0000000000000p+0, 0x1.f6297cff75cb0p-1, 0x1.d906bcf328d46p-1, 0x1.a9b66290ea1a3p-1,              \
+    0x1.6a09e667f3bcdp-1, 0x1.1c73b39ae68c8p-1, 0x1.87de2a6aea963p-2, 0x1.8f8b83c69a60bp-3, 0.0,         \
+    -0x1.8f8b83c69a60bp-3, -0x1.87de2a6aea963p-2, -0x1.1c73b39ae68c8p-1, -0x1.6a09e667f3bcdp-1,          \
+    -0x1.a9b66290ea1a3p-1, -0x1.d906bcf328d46p-1, -0x1.f6297cff75cb0p-1
+#define FHE_W32_IM_LIST                                                                                   \
+    0.0, 0x1.8f8b83c69a60bp-3, 0x1.87de2a6aea963p-2, 0x1.1c73b39ae68c8p-1, 0x1.6a09e667f3bcdp-1,         \
+    0x1.a9b66290ea1a3p-1, 0x1.d906bcf328d46p-1, 0x1.f6297cff75cb0p-1, 1.0, 0x1.f6297cff75cb0p-1,         \
+    0x1.d906bcf328d46p-1, 0x1.a9b66290ea1a3p-1, 0x1.6a09e667f3bcdp-1, 0x1.1c73b39ae68c8p-1,              \
+    0x1.87de2a6aea963p-2, 0x1.8f8b83c69a60bp-3
+// exp(2*pi*i*j2/128), j2 = 0..31: the j2-dependent factor omega^(32*j2) of the twist
+#define FHE_C128_RE_LIST                                                                                  \
+    0x1.0000000000000p+0, 0x1.ff621e3796d7ep-1, 0x1.fd88da3d12526p-1, 0x1.fa7557f08a517p-1,              \
+    0x1.f6297cff75cb0p-1, 0x1.f0a7efb9230d7p-1, 0x1.e9f4156c62ddap-1, 0x1.e212104f686e5p-1,              \
+    0x1.d906bcf328d46p-1, 0x1.ced7af43cc773p-1, 0x1.c38b2f180bdb1p-1, 0x1.b728345196e3ep-1,              \
+    0x1.a9b66290ea1a3p-1, 0x1.9b3e047f38741p-1, 0x1.8bc806b151741p-1, 0x1.7b5df226aafafp-1,              \
+    0x1.6a09e667f3bcdp-1, 0x1.57d69348ceca0p-1, 0x1.44cf325091dd6p-1, 0x1.30ff7fce17035p-1,              \
+    0x1.1c73b39ae68c8p-1, 0x1.073879922ffeep-1, 0x1.e2b5d3806f63bp-2, 0x1.b5d1009e15cc0p-2,              \
+    0x1.87de2a6aea963p-2, 0x1.58f9a75ab1fddp-2, 0x1.294062ed59f06p-2, 0x1.f19f97b215f1bp-3,              \
+    0x1.8f8b83c69a60bp-3, 0x1.2c8106e8e613ap-3, 0x1.917a6bc29b42cp-4, 0x1.91f65f10dd814p-5
+#define FHE_C128_IM_LIST                                                                                  \
+    0.0, 0x1.91f65f10dd814p-5, 0x1.917a6bc29b42cp-4, 0x1.2c8106e8e613ap-3, 0x1.8f8b83c69a60bp-3,         \
+    0x1.f19f97b215f1bp-3, 0x1.294062ed59f06p-2, 0x1.58f9a75ab1fddp-2, 0x1.87de2a6aea963p-2,              \
+    0x1.b5d1009e15cc0p-2, 0x1.e2b5d3806f63bp-2, 0x1.073879922ffeep-1, 0x1.1c73b39ae68c8p-1,              \
+    0x1.30ff7fce17035p-1, 0x1.44cf325091dd6p-1, 0x1.57d69348ceca0p-1, 0x1.6a09e667f3bcdp-1,              \
+    0x1.7b5df226aafafp-1, 0x1.8bc806b151741p-1, 0x1.9b3e047f38741p-1, 0x1.a9b66290ea1a3p-1,              \
+    0x1.b728345196e3ep-1, 0x1.c38b2f180bdb1p-1, 0x1.ced7af43cc773p-1, 0x1.d906bcf328d46p-1,              \
+    0x1.e212104f686e5p-1, 0x1.e9f4156c62ddap-1, 0x1.f0a7efb9230d7p-1, 0x1.f6297cff75cb0p-1,              \
+    0x1.fa7557f08a517p-1, 0x1.fd88da3d12526p-1, 0x1.ff621e3796d7ep-1
+
+#if defined(__CUDACC__)
+__constant__ double d_W32_RE[16] = {FHE_W32_RE_LIST};
+__constant__ double d_W32_IM[16] = {FHE_W32_IM_LIST};
+__constant__ double d_C128_RE[32] = {FHE_C128_RE_LIST};
+__constant__ double d_C128_IM[32] = {FHE_C128_IM_LIST};
+#endif
+static const double h_W32_RE[16] = {FHE_W32_RE_LIST};
+static const double h_W32_IM[16] = {FHE_W32_IM_LIST};
+static const double h_C128_RE[32] = {FHE_C128_RE_LIST};
+static const double h_C128_IM[32] = {FHE_C128_IM_LIST};
+
+#if defined(__CUDA_ARCH__)
+#define FHE_W32_RE(i) d_W32_RE[i]
+#define FHE_W32_IM(i) d_W32_IM[i]
+#define FHE_C128_RE(i) d_C128_RE[i]
+#define FHE_C128_IM(i) d_C128_IM[i]
+#else
+#define FHE_W32_RE(i) h_W32_RE[i]
+#define FHE_W32_IM(i) h_W32_IM[i]
+#define FHE_C128_RE(i) h_C128_RE[i]
+#define FHE_C128_IM(i) h_C128_IM[i]
+#endif
+
+FHE_HD constexpr int brev5(int v) {
+    return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
+}
+
+// swizzled slot of element (row, col) of the 32x32 transpose tile of 16-byte elements:
+// a warp writing one row, or reading one column, touches every bank group exactly once.
+FHE_HD constexpr int slot(int row, int col) { return row * 32 + (col ^ row); }
+
+// 32-point DFT, radix-2 decimation in frequency: natural-order input, frequency f ends at
+// register brev5(f).  SIGN=+1: exp(+2*pi*i*jf/32).
+template <int SIGN>
+FHE_HD void dif32(double (&re)[32], double (&im)[32]) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+#pragma unroll
+        for (int base = 0; base < 32; base += 2 * half) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const int a = base + j, b = a + half;
+                const double ar = re[a], ai = im[a], br = re[b], bi = im[b];
+                re[a] = ar + br;
+                im[a] = ai + bi;
+                const double dr = ar - br, di = ai - bi;
+                const int tw = j * (16 / half);
+                if (tw == 0) {
+                    re[b] = dr;
+                    im[b] = di;
+                } else if (tw == 8) {
+                    re[b] = SIGN > 0 ? -di : di;
+                    im[b] = SIGN > 0 ? dr : -dr;
+                } else {
+                    const double wr = FHE_W32_RE(tw), wi = SIGN > 0 ? FHE_W32_IM(tw) : -FHE_W32_IM(tw);
+                    re[b] = dr * wr - di * wi;
+                    im[b] = dr * wi + di * wr;
+                }
+            }
+        }
+    }
+}
+
+// 32-point DFT, radix-2 decimation in time: input for index q sits at register brev5(q),
+// output in natural order.
+template <int SIGN>
+FHE_HD void dit32(double (&re)[32], double (&im)[32]) {
+#pragma unroll
+    for (int half = 1; half <= 16; half <<= 1) {
+#pragma unroll
+        for (int base = 0; base < 32; base += 2 * half) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const int a = base + j, b = a + half;
+                const int tw = j * (16 / half);
+                double tr, ti;
+                if (tw == 0) {
+                    tr = re[b];
+                    ti = im[b];
+                } else if (tw == 8) {
+                    tr = SIGN > 0 ? -im[b] : im[b];
+                    ti = SIGN > 0 ? re[b] : -re[b];
+                } else {
+                    const double wr = FHE_W32_RE(tw), wi = SIGN > 0 ? FHE_W32_IM(tw) : -FHE_W32_IM(tw);
+                    tr = re[b] * wr - im[b] * wi;
+                    ti = re[b] * wi + im[b] * wr;
+                }
+                const double ar = re[a], ai = im[a];
+                re[a] = ar + tr;
+                im[a] = ai + ti;
+                re[b] = ar - tr;
+                im[b] = ai - ti;
+            }
+        }
+    }
+}
+
+// ---- forward: registers hold z[j2] = (c[j] + i*c[j+1024]) for j = lane + 32*j2 (the caller
+// has NOT applied any twist).  After phase 2 register brev5(k1) holds bin k = lane + 32*k1.
+// twf[k2*32 + j1] = W^(j1*k2) * omega^j1.
+FHE_HD void fwd_phase1(double (&re)[32], double (&im)[32], const cplx* twf, cplx* buf, int lane) {
+#pragma unroll
+    for (int j2 = 1; j2 < 32; ++j2) {  // twist factor omega^(32*j2)
+        const double cr = FHE_C128_RE(j2), ci = FHE_C128_IM(j2);
+        const double a = re[j2], b = im[j2];
+        re[j2] = a * cr - b * ci;
+        im[j2] = a * ci + b * cr;
+    }
+    dif32<+1>(re, im);
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        const int k2 = brev5(p);
+        const cplx w = twf[k2 * 32 + lane];
+        cplx v;
+        v.x = re[p] * w.x - im[p] * w.y;
+        v.y = re[p] * w.y + im[p] * w.x;
+        buf[slot(k2, lane)] = v;
+    }
+}
+FHE_HD void fwd_phase2(double (&re)[32], double (&im)[32], const cplx* buf, int lane) {
+#pragma unroll
+    for (int j1 = 0; j1 < 32; ++j1) {
+        const cplx v = buf[slot(lane, j1)];
+        re[j1] = v.x;
+        im[j1] = v.y;
+    }
+    dif32<+1>(re, im);
+}
+
+// ---- inverse: register brev5(k1) holds bin k = lane + 32*k1.  After phase 2 register j2 holds
+// (c[j] + i*c[j+1024]) for j = lane + 32*j2, fully untwisted and scaled by 1/1024.
+// twi[j1*32 + k2] = conj(W^(j1*k2) * omega^j1) / 1024.
+FHE_HD void inv_phase1(double (&re)[32], double (&im)[32], const cplx* twi, cplx* buf, int lane) {
+    dit32<-1>(re, im);
+#pragma unroll
+    for (int j1 = 0; j1 < 32; ++j1) {
+        const cplx w = twi[j1 * 32 + lane];
+        cplx v;
+        v.x = re[j1] * w.x - im[j1] * w.y;
+        v.y = re[j1] * w.y + im[j1] * w.x;
+        buf[slot(j1, lane)] = v;
+    }
+}
+FHE_HD void inv_phase2(double (&re)[32], double (&im)[32], const cplx* buf, int lane) {
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        const cplx v = buf[slot(lane, brev5(p))];
+        re[p] = v.x;
+        im[p] = v.y;
+    }
+    dit32<-1>(re, im);
+#pragma unroll
+    for (int j2 = 1; j2 < 32; ++j2) {  // conj(omega^(32*j2))
+        const double cr = FHE_C128_RE(j2), ci = -FHE_C128_IM(j2);
+        const double a = re[j2], b = im[j2];
+        re[j2] = a * cr - b * ci;
+        im[j2] = a * ci + b * cr;
+    }
+}
+
+// host: inter-pass twiddle tables (computed in long double, rounded once)
+inline void fill_twiddle_tables(cplx* twf, cplx* twi) {
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int a = 0; a < 32; ++a) {      // a = k2 (forward rows) / j1 (inverse rows)
+        for (int b = 0; b < 32; ++b) {  // b = lane
+            // forward: row k2=a, lane j1=b : W^(j1*k2) * omega^j1
+            long double ang = two_pi * ((long double)(a * b) / 1024.0L + (long double)b / 4096.0L);
+            twf[a * 32 + b].x = (double)cosl(ang);
+            twf[a * 32 + b].y = (double)sinl(ang);
+            // inverse: row j1=a, lane k2=b : conj(W^(j1*k2) * omega^j1) / 1024
+            long double ang2 = two_pi * ((long double)(a * b) / 1024.0L + (long double)a / 4096.0L);
+            twi[a * 32 + b].x = (double)(cosl(ang2) / 1024.0L);
+            twi[a * 32 + b].y = (double)(-sinl(ang2) / 1024.0L);
+        }
+    }
+}
+
+}  // namespace nfft
+}  // namespace fhe

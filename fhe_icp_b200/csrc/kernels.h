@@ -43,4 +43,7 @@ cudaError_t launch_pbs(const fhe_b200_pbs_params& p, const double* d_bskf, const
                        cudaStream_t s);
 bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why);
 
+// probe.cu
+cudaError_t probe_fp64(int sm_count, double* tflops, cudaStream_t s);
+
 }  // namespace fhe

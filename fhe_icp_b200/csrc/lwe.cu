@@ -8,6 +8,7 @@
 // aligned), so a warp reads 512 contiguous bytes per 128-bit load instruction.
 #include "common.cuh"
 #include "kernels.h"
+#include "lwe_device.cuh"
 
 namespace fhe {
 
@@ -40,44 +41,13 @@ lwe_encrypt_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, const
                    int64_t count, int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base,
                    uint32_t purpose, uint64_t* __restrict__ out) {
     extern __shared__ uint32_t skey[];  // packed key bits, ceil(n/32) words (+1 pad)
-    const int kw = (n + 31) / 32 + 1;
-    for (int i = threadIdx.x; i < kw; i += blockDim.x) {
-        uint32_t w = 0;
-#pragma unroll 8
-        for (int b = 0; b < 32; ++b) {
-            int j = i * 32 + b;
-            if (j < n) w |= (uint32_t)(key[j] & 1u) << b;
-        }
-        skey[i] = w;
-    }
+    pack_key_bits(key, n, skey);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
     if (c >= count) return;
-    const uint64_t id = ct_base + (uint64_t)c;
-    uint64_t* ct = out + c * stride;
-    const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
-    uint64_t dot = 0;
-    const int nblk = (n + 1) / 2;
-    for (int blk = lane; blk < nblk; blk += 32) {
-        u32x4 r = rng_block(enc_seed, dom, id, (uint32_t)blk);
-        uint64_t a0 = lo64(r), a1 = hi64(r);
-        const int w = 2 * blk;
-        uint32_t bits = skey[w >> 5] >> (w & 31);  // w even => bit w and w+1 live in the same word
-        dot += a0 & (0 - (uint64_t)(bits & 1u));
-        if (w + 1 < n) {
-            dot += a1 & (0 - (uint64_t)((bits >> 1) & 1u));
-            st_stream_u64x2(ct + w, u64x2{a0, a1});
-        } else {
-            ct[w] = a0;  // n odd: the second word of the last block is unused
-        }
-    }
-    dot = warp_sum_u64(dot);
-    if (lane == 0) {
-        int64_t e = gaussian_i64(enc_seed, FHE_B200_KIND_NOISE | (purpose << 8), id, 0, sigma_abs);
-        ct[n] = dot + ((uint64_t)msgs[c] << shift) + (uint64_t)e;
-    }
-    for (int64_t w = n + 1 + lane; w < stride; w += 32) ct[w] = 0;
+    warp_lwe_encrypt(skey, n, stride, (uint64_t)msgs[c] << shift, sigma_abs, enc_seed, purpose, ct_base + (uint64_t)c,
+                     out + c * stride, lane);
 }
 
 cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
@@ -100,16 +70,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
 lwe_phase_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, const uint64_t* __restrict__ cts,
                  int64_t count, int shift, bool decode, uint64_t* __restrict__ out) {
     extern __shared__ uint32_t skey[];
-    const int kw = (n + 31) / 32 + 1;
-    for (int i = threadIdx.x; i < kw; i += blockDim.x) {
-        uint32_t w = 0;
-#pragma unroll 8
-        for (int b = 0; b < 32; ++b) {
-            int j = i * 32 + b;
-            if (j < n) w |= (uint32_t)(key[j] & 1u) << b;
-        }
-        skey[i] = w;
-    }
+    pack_key_bits(key, n, skey);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t c = (int64_t)blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
@@ -151,61 +112,69 @@ cudaError_t launch_lwe_phase(const uint8_t* d_key, int n, int64_t stride, const 
 }
 
 // ----------------------------------------------------------------------------- encrypted dot product
-// out[b][m][:] = sum_j W[m][j] * ct[b][j][:].  Each thread owns one 16-byte column pair of
-// one row b and streams the d ciphertexts of that row (stride*8 bytes apart); UNROLL
-// independent 128-bit loads are in flight per thread.  Inputs are read exactly once
-// (L1::no_allocate), the M output rows are written once.
+// out[b][m][:] = sum_j W[m][j] * ct[b][j][:].  The (row b, 16-byte column pair) space is
+// flattened over the grid, so no thread idles whatever the row length.  Each thread streams
+// the d ciphertexts of its row (stride*8 bytes apart) through a register double buffer:
+// UNROLL 128-bit loads for rows j+UNROLL.. are issued before the MACs of rows j.. retire, which
+// keeps UNROLL independent loads in flight per thread (measured: 5.3 -> 6.9 TB/s, see
+// profiles/r1_lincomb_variant_sweep.txt; a TMA/mbarrier ring reached 6.8 TB/s).  Inputs are
+// read exactly once (L1::no_allocate), the M output rows are written once.
 constexpr int LC_THREADS = 256;
+constexpr int LC_UNROLL = 8;
+
+template <int M, bool SECOND_IS_SUM, int UNROLL>
+__device__ __forceinline__ void lc_mac(const u64x2 (&x)[UNROLL], const int64_t* sW, int d, int j, uint64_t& a0x,
+                                       uint64_t& a0y, uint64_t& a1x, uint64_t& a1y) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const uint64_t w = (uint64_t)sW[j + u];
+        a0x += w * x[u].x;
+        a0y += w * x[u].y;
+        if (M == 2) {
+            if (SECOND_IS_SUM) {
+                a1x += x[u].x;
+                a1y += x[u].y;
+            } else {
+                const uint64_t w1 = (uint64_t)sW[d + j + u];
+                a1x += w1 * x[u].x;
+                a1y += w1 * x[u].y;
+            }
+        }
+    }
+}
 
 template <int M, bool SECOND_IS_SUM, int UNROLL>
 __global__ void __launch_bounds__(LC_THREADS)
-lincomb_kernel(const uint64_t* __restrict__ ct, int d, int n_words, int64_t stride, int chunks,
+lincomb_kernel(const uint64_t* __restrict__ ct, int d, int n_words, int64_t stride, int64_t total_vecs,
                const int64_t* __restrict__ W, uint64_t bias0, uint64_t bias1, uint64_t* __restrict__ out) {
     extern __shared__ int64_t sW[];  // [M][d]
     for (int i = threadIdx.x; i < M * d; i += blockDim.x) sW[i] = W[i];
     __syncthreads();
-    const int64_t b = blockIdx.x / chunks;
-    const int chunk = blockIdx.x - (int)(b * chunks);
-    const int w0 = 2 * (chunk * LC_THREADS + threadIdx.x);
-    if (w0 >= stride) return;
+    const int64_t g = (int64_t)blockIdx.x * LC_THREADS + threadIdx.x;
+    if (g >= total_vecs) return;
+    const int vecs = (int)(stride >> 1);
+    const int64_t b = g / vecs;
+    const int w0 = 2 * (int)(g - b * vecs);
     const uint64_t* p = ct + (size_t)b * d * stride + w0;
     uint64_t a0x = 0, a0y = 0, a1x = 0, a1y = 0;
-    int j = 0;
-    for (; j + UNROLL <= d; j += UNROLL) {
-        u64x2 x[UNROLL];
-        static_assert(UNROLL % 4 == 0, "loads are issued in blocks of four");
+    const int d_main = d - d % UNROLL;
+    if (d_main > 0) {
+        u64x2 cur[UNROLL], nxt[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; u += 4) {
-            const uint64_t* q = p + (size_t)(j + u) * stride;
-            ld_stream_u64x2_x4(q, q + stride, q + 2 * stride, q + 3 * stride, x[u], x[u + 1], x[u + 2], x[u + 3]);
-        }
+        for (int u = 0; u < UNROLL; ++u) cur[u] = ld_stream_u64x2(p + (size_t)u * stride);
+        for (int j = 0; j < d_main; j += UNROLL) {
+            if (j + UNROLL < d_main) {  // next block is in flight behind the MACs of this one
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            uint64_t w = (uint64_t)sW[j + u];
-            a0x += w * x[u].x;
-            a0y += w * x[u].y;
-            if (M == 2) {
-                if (SECOND_IS_SUM) {
-                    a1x += x[u].x;
-                    a1y += x[u].y;
-                } else {
-                    uint64_t w1 = (uint64_t)sW[d + j + u];
-                    a1x += w1 * x[u].x;
-                    a1y += w1 * x[u].y;
-                }
+                for (int u = 0; u < UNROLL; ++u) nxt[u] = ld_stream_u64x2(p + (size_t)(j + UNROLL + u) * stride);
             }
+            lc_mac<M, SECOND_IS_SUM, UNROLL>(cur, sW, d, j, a0x, a0y, a1x, a1y);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) cur[u] = nxt[u];
         }
     }
-    for (; j < d; ++j) {
-        u64x2 x = ld_stream_u64x2(p + (size_t)j * stride);
-        uint64_t w = (uint64_t)sW[j];
-        a0x += w * x.x;
-        a0y += w * x.y;
-        if (M == 2) {
-            uint64_t w1 = SECOND_IS_SUM ? 1ULL : (uint64_t)sW[d + j];
-            a1x += w1 * x.x;
-            a1y += w1 * x.y;
-        }
+    for (int j = d_main; j < d; ++j) {  // ragged tail (d % UNROLL rows)
+        u64x2 x[1] = {ld_stream_u64x2(p + (size_t)j * stride)};
+        lc_mac<M, SECOND_IS_SUM, 1>(x, sW, d, j, a0x, a0y, a1x, a1y);
     }
     // body word gets the clear bias; padding words are forced to zero
     const int nb = n_words - 1;
@@ -222,20 +191,19 @@ cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_
                            bool second_is_sum, int64_t bias0, int64_t bias1, int shift, uint64_t* d_out,
                            cudaStream_t s) {
     if (B <= 0) return cudaSuccess;
-    const int vecs = (int)(stride / 2);
-    const int chunks = (vecs + LC_THREADS - 1) / LC_THREADS;
-    const int64_t grid64 = B * chunks;
+    const int64_t total_vecs = B * (stride / 2);
+    const int64_t grid64 = (total_vecs + LC_THREADS - 1) / LC_THREADS;
     if (grid64 > 0x7fffffffLL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)grid64;
     const size_t smem = (size_t)M * d * sizeof(int64_t);
     const uint64_t b0 = (uint64_t)bias0 << shift, b1 = (uint64_t)bias1 << shift;
-    constexpr int U = 8;
+    constexpr int U = LC_UNROLL;
     if (M == 1)
-        lincomb_kernel<1, false, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, chunks, d_W, b0, b1, d_out);
+        lincomb_kernel<1, false, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out);
     else if (second_is_sum)
-        lincomb_kernel<2, true, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, chunks, d_W, b0, b1, d_out);
+        lincomb_kernel<2, true, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out);
     else
-        lincomb_kernel<2, false, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, chunks, d_W, b0, b1, d_out);
+        lincomb_kernel<2, false, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out);
     count_launch();
     return cudaGetLastError();
 }

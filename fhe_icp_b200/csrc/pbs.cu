@@ -1,0 +1,344 @@
+// pbs.cu -- programmable bootstrapping: mod-switch, batched blind rotation (n CMuxes, each a
+// GGSW external product over the negacyclic f64 FFT of fft.cuh) and sample extraction
+// (TFHE, Chillotti et al. 2020).  Not exercised by the reference's
+// compiled circuit (it has no table lookup); named by BASELINE.json's north star.
+//
+// Mapping (N = 2048, M = 1024 = 32 x 32):
+//   * one WARP per accumulator polynomial: warp t of a ciphertext owns ACC_t (16 KB of u64 in
+//     shared memory, private to that warp), produces the digits of (X^a - 1) * ACC_t, runs
+//     their forward FFTs in registers, and later the inverse FFT of output column t;
+//   * PBS_NCT ciphertexts per CTA walk the n key elements in lock step, so the 64 KB of
+//     BSK_i they all read stays hot in L1 (v1; TMA-multicast staging is the next step);
+//   * per iteration the only cross-warp traffic is the Fourier-domain digits (16 KB per
+//     polynomial and level), exchanged through shared memory between two named barriers.
+// Roofline: FP64 pipe and shared-memory bandwidth bind (about 176 MFLOP per PBS at the stated
+// set); the 48.6 MB Fourier key is L2-resident, so HBM only sees it once per launch.
+#include <mutex>
+
+#include "common.cuh"
+#include "fft.cuh"
+#include "kernels.h"
+
+namespace fhe {
+
+using nfft::cplx;
+
+constexpr int PBS_N = nfft::NPOLY;
+constexpr int PBS_M = nfft::M;
+
+// ------------------------------------------------------------------------------- twiddle tables
+static cplx* g_tw = nullptr;  // [2][1024]: forward, inverse (per device)
+static int g_tw_device = -1;
+static std::mutex g_tw_mu;
+
+static cudaError_t get_tables(const cplx** twf, const cplx** twi) {
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (g_tw == nullptr || g_tw_device != dev) {
+        static cplx h[2 * PBS_M];
+        nfft::fill_twiddle_tables(h, h + PBS_M);
+        cplx* d = nullptr;
+        if ((e = cudaMalloc(&d, sizeof(h))) != cudaSuccess) return e;
+        if ((e = cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        g_tw = d;  // (tables of a previous device are intentionally kept alive)
+        g_tw_device = dev;
+    }
+    *twf = g_tw;
+    *twi = g_tw + PBS_M;
+    return cudaSuccess;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ uint64_t f64_to_torus(double x) {
+    // x mod 2^64, rounded to the nearest integer
+    const double r = rint(x * 0x1p-64);
+    const double y = fma(-r, 0x1p64, x);
+    return (uint64_t)__double2ll_rn(y);
+}
+
+// ------------------------------------------------------------------------------- key -> Fourier
+// One warp per key polynomial: u64 torus coefficients (as signed) -> 1024 complex bins,
+// natural order (same layout as the oracle's orc_bsk_to_fourier).
+constexpr int B2F_WARPS = 4;
+
+__global__ void __launch_bounds__(B2F_WARPS * 32)
+bsk_to_fourier_kernel(const uint64_t* __restrict__ bsk, int64_t polys, const cplx* __restrict__ g_twf,
+                      double* __restrict__ bskf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* twf = reinterpret_cast<cplx*>(smem_raw);
+    cplx* bufs = twf + PBS_M;
+    for (int i = threadIdx.x; i < PBS_M; i += blockDim.x) twf[i] = g_twf[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * B2F_WARPS + warp;
+    if (q >= polys) return;
+    cplx* buf = bufs + warp * PBS_M;
+    const uint64_t* src = bsk + (size_t)q * PBS_N;
+    double re[32], im[32];
+#pragma unroll
+    for (int j2 = 0; j2 < 32; ++j2) {
+        re[j2] = (double)(int64_t)src[lane + 32 * j2];
+        im[j2] = (double)(int64_t)src[lane + 32 * j2 + PBS_M];
+    }
+    nfft::fwd_phase1(re, im, twf, buf, lane);
+    __syncwarp();
+    nfft::fwd_phase2(re, im, buf, lane);
+    cplx* dst = reinterpret_cast<cplx*>(bskf) + (size_t)q * PBS_M;
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        cplx v;
+        v.x = re[p];
+        v.y = im[p];
+        dst[nfft::brev5(p) * 32 + lane] = v;
+    }
+}
+
+cudaError_t launch_bsk_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* d_bsk, double* d_bskf,
+                                  cudaStream_t s) {
+    const cplx *twf, *twi;
+    cudaError_t e = get_tables(&twf, &twi);
+    if (e != cudaSuccess) return e;
+    const int64_t polys = (int64_t)p.n * (p.k + 1) * p.l_pbs * (p.k + 1);
+    const size_t smem = sizeof(cplx) * PBS_M * (1 + B2F_WARPS);
+    e = cudaFuncSetAttribute(bsk_to_fourier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bsk_to_fourier_kernel<<<(unsigned)((polys + B2F_WARPS - 1) / B2F_WARPS), B2F_WARPS * 32, smem, s>>>(
+        d_bsk, polys, twf, d_bskf);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------- blind rotation
+// Shared memory per CTA:
+//   twf, twi                      2 x 16 KB   inter-pass twiddles
+//   per ciphertext:  ACC          (K+1) x 16 KB (u64 coefficients)
+//                    tile         (K+1) x 16 KB (per-warp transpose tile; with L == 1 it also
+//                                                carries that warp's Fourier digits)
+//                    F            (K+1) x L x 16 KB, only when L > 1
+//                    a_tilde      n+1 u16  (mod-switched mask, padded)
+template <int K, int L>
+struct PbsSmem {
+    static constexpr int POLYS = K + 1;
+    static constexpr size_t acc_bytes = (size_t)POLYS * PBS_N * 8;
+    static constexpr size_t tile_bytes = (size_t)POLYS * PBS_M * 16;
+    static constexpr size_t f_bytes = L > 1 ? (size_t)POLYS * L * PBS_M * 16 : 0;
+    __host__ __device__ static size_t per_ct(int n) { return acc_bytes + tile_bytes + f_bytes + (((size_t)(n + 1) * 2 + 15) & ~(size_t)15); }
+    static size_t total(int n, int nct) { return 2 * (size_t)PBS_M * 16 + (size_t)nct * per_ct(n); }
+};
+
+template <int K, int L, int NCT>
+__global__ void __launch_bounds__(NCT*(K + 1) * 32, 1)
+pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
+           const uint64_t* __restrict__ luts, const int32_t* __restrict__ lut_index, const cplx* __restrict__ g_tw,
+           uint64_t* __restrict__ out) {
+    constexpr int POLYS = K + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* twf = reinterpret_cast<cplx*>(smem_raw);
+    cplx* twi = twf + PBS_M;
+    for (int i = threadIdx.x; i < 2 * PBS_M; i += blockDim.x) twf[i] = g_tw[i];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ctl = warp / POLYS;        // ciphertext slot within the CTA
+    const int t = warp - ctl * POLYS;    // polynomial owned by this warp
+    const int64_t b = (int64_t)blockIdx.x * NCT + ctl;
+    const size_t per_ct = PbsSmem<K, L>::per_ct(n);
+    unsigned char* base = smem_raw + 2 * (size_t)PBS_M * 16 + (size_t)ctl * per_ct;
+    uint64_t* acc_all = reinterpret_cast<uint64_t*>(base);
+    cplx* tile_all = reinterpret_cast<cplx*>(base + PbsSmem<K, L>::acc_bytes);
+    cplx* f_all = reinterpret_cast<cplx*>(base + PbsSmem<K, L>::acc_bytes + PbsSmem<K, L>::tile_bytes);
+    uint16_t* a_tilde = reinterpret_cast<uint16_t*>(base + PbsSmem<K, L>::acc_bytes + PbsSmem<K, L>::tile_bytes +
+                                                    PbsSmem<K, L>::f_bytes);
+    uint64_t* acc = acc_all + (size_t)t * PBS_N;
+    cplx* tile = tile_all + (size_t)t * PBS_M;
+    const bool live = b < B;  // dead slots still take part in barriers
+    const int bar_id = 1 + ctl, bar_n = POLYS * 32;
+
+    // ---- prologue: mod-switch the mask, ACC = X^(-b~) * (0,...,0,LUT)
+    const uint64_t* ct = in + (size_t)(live ? b : 0) * (n + 1);
+    for (int i = t * 32 + lane; i <= n; i += POLYS * 32)
+        a_tilde[i] = (uint16_t)((((ct[i] >> 51) + 1) >> 1) & 4095);   // round(a * 2N / 2^64), 2N = 4096
+    named_bar_sync(bar_id, bar_n);
+    {
+        const uint64_t* lut = luts + (size_t)(lut_index && live ? lut_index[b] : 0) * PBS_N;
+        const int rot = (4096 - (int)a_tilde[n]) & 4095;
+        for (int x = lane; x < PBS_N; x += 32) {
+            uint64_t v = 0;
+            if (t == K) {
+                const int src = (x - rot) & 4095;
+                v = lut[src & 2047];
+                if (src & 2048) v = 0 - v;
+            }
+            acc[x] = v;
+        }
+    }
+    __syncthreads();  // twiddle tables + all accumulators in place
+
+    const uint64_t Bm = (1ULL << beta) - 1, half = 1ULL << (beta - 1);
+    const int tot = L * beta;
+    uint64_t offs = 0;
+    for (int lev = 0; lev < L; ++lev) offs |= half << (beta * lev);
+    const uint64_t rnd = 1ULL << (63 - tot);
+
+    double re[32], im[32];
+    for (int i = 0; i < n; ++i) {
+        const int at = a_tilde[i];
+        if (at == 0) continue;  // X^0 - 1 = 0: uniform across the ciphertext's warps
+        const cplx* bk = bskf + (size_t)i * POLYS * L * POLYS * PBS_M;
+        // ---- digits of (X^at - 1) * ACC_t, one forward FFT per level
+#pragma unroll 1
+        for (int lev = 0; lev < L; ++lev) {
+            const int sh = beta * (L - 1 - lev);
+#pragma unroll
+            for (int j2 = 0; j2 < 32; ++j2) {
+                const int x = lane + 32 * j2;
+                const int s0 = (x - at) & 4095, s1 = (x + PBS_M - at) & 4095;
+                uint64_t r0 = acc[s0 & 2047], r1 = acc[s1 & 2047];
+                if (s0 & 2048) r0 = 0 - r0;
+                if (s1 & 2048) r1 = 0 - r1;
+                const uint64_t d0 = r0 - acc[x], d1 = r1 - acc[x + PBS_M];
+                const uint64_t u0 = ((d0 + rnd) >> (64 - tot)) + offs, u1 = ((d1 + rnd) >> (64 - tot)) + offs;
+                re[j2] = (double)((int32_t)((u0 >> sh) & Bm) - (int32_t)half);
+                im[j2] = (double)((int32_t)((u1 >> sh) & Bm) - (int32_t)half);
+            }
+            nfft::fwd_phase1(re, im, twf, tile, lane);
+            __syncwarp();
+            nfft::fwd_phase2(re, im, tile, lane);
+            if (L > 1) {
+                cplx* f = f_all + (size_t)(t * L + lev) * PBS_M;
+#pragma unroll
+                for (int p = 0; p < 32; ++p) {
+                    cplx v;
+                    v.x = re[p];
+                    v.y = im[p];
+                    f[nfft::brev5(p) * 32 + lane] = v;
+                }
+            }
+        }
+        if (L == 1) {
+            // publish this warp's bins through its own tile (all lanes are done reading it)
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                cplx v;
+                v.x = re[p];
+                v.y = im[p];
+                tile[nfft::brev5(p) * 32 + lane] = v;
+            }
+        }
+        named_bar_sync(bar_id, bar_n);  // (A) every polynomial's Fourier digits are visible
+        // ---- output column t:  out = sum_{t',lev} F[t'][lev] * BSK_i[t'][lev][t]
+        if (L == 1) {
+            const cplx* bown = bk + ((size_t)(t * L) * POLYS + t) * PBS_M;
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const cplx g = bown[nfft::brev5(p) * 32 + lane];
+                const double a = re[p], c = im[p];
+                re[p] = a * g.x - c * g.y;
+                im[p] = a * g.y + c * g.x;
+            }
+#pragma unroll 1
+            for (int tp = 0; tp < POLYS; ++tp) {
+                if (tp == t) continue;
+                const cplx* f = tile_all + (size_t)tp * PBS_M;
+                const cplx* bo = bk + ((size_t)(tp * L) * POLYS + t) * PBS_M;
+#pragma unroll
+                for (int p = 0; p < 32; ++p) {
+                    const cplx v = f[nfft::brev5(p) * 32 + lane];
+                    const cplx g = bo[nfft::brev5(p) * 32 + lane];
+                    re[p] += v.x * g.x - v.y * g.y;
+                    im[p] += v.x * g.y + v.y * g.x;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 32; ++p) { re[p] = 0.0; im[p] = 0.0; }
+#pragma unroll 1
+            for (int q = 0; q < POLYS * L; ++q) {
+                const cplx* f = f_all + (size_t)q * PBS_M;
+                const cplx* bo = bk + ((size_t)q * POLYS + t) * PBS_M;
+#pragma unroll
+                for (int p = 0; p < 32; ++p) {
+                    const cplx v = f[nfft::brev5(p) * 32 + lane];
+                    const cplx g = bo[nfft::brev5(p) * 32 + lane];
+                    re[p] += v.x * g.x - v.y * g.y;
+                    im[p] += v.x * g.y + v.y * g.x;
+                }
+            }
+        }
+        named_bar_sync(bar_id, bar_n);  // (B) nobody reads the published digits any more
+        // ---- inverse FFT and ACC_t += result
+        nfft::inv_phase1(re, im, twi, tile, lane);
+        __syncwarp();
+        nfft::inv_phase2(re, im, tile, lane);
+#pragma unroll
+        for (int j2 = 0; j2 < 32; ++j2) {
+            const int x = lane + 32 * j2;
+            acc[x] += f64_to_torus(re[j2]);
+            acc[x + PBS_M] += f64_to_torus(im[j2]);
+        }
+        __syncwarp();  // the next iteration reads rotated (other lanes') coefficients
+    }
+    // ---- sample extract coefficient 0: LWE under the flattened GLWE key
+    __syncwarp();
+    if (live) {
+        uint64_t* o = out + (size_t)b * ((size_t)K * PBS_N + 1);
+        if (t < K) {
+            for (int x = lane; x < PBS_N; x += 32) o[(size_t)t * PBS_N + x] = x == 0 ? acc[0] : 0 - acc[PBS_N - x];
+        } else if (lane == 0) {
+            o[(size_t)K * PBS_N] = acc[0];
+        }
+    }
+}
+
+bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why) {
+    *why = "";
+    if (p.N != PBS_N) { *why = "polynomial size N must be 2048"; return false; }
+    if (p.k != 1) { *why = "GLWE dimension k must be 1"; return false; }
+    if (p.l_pbs < 1 || p.l_pbs > 3) { *why = "l_pbs must be in [1,3]"; return false; }
+    if (p.beta_pbs < 1 || p.beta_pbs > 31 || p.l_pbs * p.beta_pbs > 62) { *why = "beta_pbs out of range"; return false; }
+    if (p.n < 1 || p.n > 4096) { *why = "n must be in [1,4096]"; return false; }
+    if (p.l_ks < 1 || p.l_ks > 8 || p.beta_ks < 1 || p.l_ks * p.beta_ks > 62) { *why = "keyswitch decomposition out of range"; return false; }
+    return true;
+}
+
+template <int K, int L, int NCT>
+static cudaError_t launch_pbs_t(const fhe_b200_pbs_params& p, const cplx* bskf, const uint64_t* d_in, int64_t B,
+                                const uint64_t* d_luts, const int32_t* d_lut_index, const cplx* tw, uint64_t* d_out,
+                                cudaStream_t s) {
+    const size_t smem = PbsSmem<K, L>::total(p.n, NCT);
+    cudaError_t e = cudaFuncSetAttribute(pbs_kernel<K, L, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((B + NCT - 1) / NCT);
+    pbs_kernel<K, L, NCT><<<grid, NCT*(K + 1) * 32, smem, s>>>(bskf, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tw,
+                                                             d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pbs(const fhe_b200_pbs_params& p, const double* d_bskf, const uint64_t* d_in, int64_t B,
+                       const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
+                       cudaStream_t s) {
+    const cplx *twf, *twi;
+    cudaError_t e = get_tables(&twf, &twi);
+    if (e != cudaSuccess) return e;
+    const cplx* bskf = reinterpret_cast<const cplx*>(d_bskf);
+    const bool wide = B > (int64_t)sm_count;  // more ciphertexts than SMs: share BSK loads inside a CTA
+    switch (p.l_pbs) {
+        case 1:
+            return wide ? launch_pbs_t<1, 1, 2>(p, bskf, d_in, B, d_luts, d_lut_index, twf, d_out, s)
+                        : launch_pbs_t<1, 1, 1>(p, bskf, d_in, B, d_luts, d_lut_index, twf, d_out, s);
+        case 2:
+            return launch_pbs_t<1, 2, 1>(p, bskf, d_in, B, d_luts, d_lut_index, twf, d_out, s);
+        case 3:
+            return launch_pbs_t<1, 3, 1>(p, bskf, d_in, B, d_luts, d_lut_index, twf, d_out, s);
+        default:
+            return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace fhe

@@ -89,6 +89,8 @@ int fhe_b200_device_info(fhe_b200_ctx *ctx, int32_t *sm_count, int32_t *cc_major
                          int32_t *cc_minor, uint64_t *total_mem);
 /* number of kernels this library has launched since ctx creation (bench.py's gpu_launches) */
 uint64_t fhe_b200_launch_count(fhe_b200_ctx *ctx);
+/* measured FP64 FMA peak of the device in TFLOP/s (denominator of the PBS roofline) */
+int fhe_b200_probe_fp64(fhe_b200_ctx *ctx, double *tflops);
 
 /* ---- client side: keys, encrypt, decrypt --------------------------------------
  * replaces the lazy keygen / encrypt / decrypt inside

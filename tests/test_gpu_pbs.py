@@ -1,0 +1,155 @@
+"""Keyswitch + programmable bootstrap on the GPU against the CPU oracle.  Integer stages
+(key generation, keyswitch) are bit-exact; the f64-FFT blind rotation is compared on the
+decrypted table value (exact) and on the ciphertext phase (within a stated noise bound).
+The reference has no test for these primitives (its circuit has no table lookup): parity is
+anchored on decrypt(PBS(enc(m))) == LUT[m] for every m."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOY = dict(n=24, k=1, N_poly=2048, l_pbs=1, beta_pbs=23, l_ks=5, beta_ks=3, log2_sigma_lwe=-30.0, log2_sigma_glwe=-51.6)
+TOY_L2 = dict(n=20, k=1, N_poly=2048, l_pbs=2, beta_pbs=15, l_ks=4, beta_ks=4, log2_sigma_lwe=-30.0, log2_sigma_glwe=-51.6)
+P4 = dict(n=742, k=1, N_poly=2048, l_pbs=1, beta_pbs=23, l_ks=5, beta_ks=3, log2_sigma_lwe=-17.1, log2_sigma_glwe=-51.6)
+
+
+def _u64(t):
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+def _oparams(O, d):
+    return O.make_params(n=d["n"], k=d["k"], N=d["N_poly"], l_pbs=d["l_pbs"], beta_pbs=d["beta_pbs"], l_ks=d["l_ks"],
+                         beta_ks=d["beta_ks"], log2_sigma_lwe=d["log2_sigma_lwe"], log2_sigma_glwe=d["log2_sigma_glwe"])
+
+
+class Keys:
+    def __init__(self, O, dev, d, key_seed=11, evk_seed=22):
+        from fhe_icp_b200 import engine as E
+        self.p = E.make_pbs_params(**d)
+        self.op = _oparams(O, d)
+        self.s = E.secret_key(key_seed, 0, d["n"], dev)
+        self.S = E.secret_key(key_seed, 1, d["k"] * d["N_poly"], dev)
+        self.os = O.secret_key(key_seed, 0, d["n"])
+        self.oS = O.secret_key(key_seed, 1, d["k"] * d["N_poly"])
+        self.ksk = E.ksk_gen(self.p, self.S, self.s, evk_seed)
+        self.bsk = E.bsk_gen(self.p, self.s, self.S, evk_seed)
+        self.bskf = E.bsk_to_fourier(self.p, self.bsk)
+        self.evk_seed = evk_seed
+
+
+@pytest.fixture(scope="module")
+def toy(O, cuda_dev):
+    return Keys(O, cuda_dev, TOY)
+
+
+@pytest.fixture(scope="module")
+def p4(O, cuda_dev):
+    return Keys(O, cuda_dev, P4)
+
+
+@pytest.mark.parametrize("which", ["toy", "p4"])
+def test_evaluation_keys_bit_exact(O, request, which):
+    K = request.getfixturevalue(which)
+    assert np.array_equal(K.s.cpu().numpy(), K.os) and np.array_equal(K.S.cpu().numpy(), K.oS)
+    assert np.array_equal(_u64(K.ksk), O.ksk_gen(K.op, K.oS, K.os, K.evk_seed))
+    obsk = O.bsk_gen(K.op, K.os, K.oS, K.evk_seed)
+    assert np.array_equal(_u64(K.bsk), obsk)
+    of = O.bsk_to_fourier(K.op, obsk)
+    gf = K.bskf.cpu().numpy()
+    scale = np.abs(of).max()
+    assert np.abs(gf - of).max() / scale < 1e-13
+
+
+@pytest.mark.parametrize("which,B", [("toy", 1), ("toy", 9), ("p4", 1), ("p4", 33)])
+def test_keyswitch_bit_exact(O, request, cuda_dev, which, B):
+    import torch
+    from fhe_icp_b200 import engine as E
+    K = request.getfixturevalue(which)
+    rng = np.random.RandomState(B)
+    msgs = rng.randint(0, 16, size=B)
+    ct = E.lwe_encrypt(K.S, torch.as_tensor(msgs), 59, K.op.sigma_glwe_abs, enc_seed=5, ct_base=7,
+                       stride=K.p.k * K.p.N + 2)[:, : K.p.k * K.p.N + 1].contiguous()
+    out = E.keyswitch(K.p, K.ksk, ct)
+    ref = O.keyswitch(K.op, _u64(K.ksk), _u64(ct))
+    assert np.array_equal(_u64(out), ref)
+    assert np.array_equal(O.lwe_decrypt(K.os, ref, 59), msgs)
+
+
+def _pbs_case(O, K, cuda_dev, B, table, seed, tol_log2):
+    import torch
+    from fhe_icp_b200 import engine as E
+    p_bits = 4
+    shift = 63 - p_bits
+    rng = np.random.RandomState(seed)
+    msgs = rng.randint(0, 16, size=B)
+    msgs[: min(B, 16)] = np.arange(16)[: min(B, 16)]
+    ct = E.lwe_encrypt(K.s, torch.as_tensor(msgs), shift, K.op.sigma_lwe_abs, enc_seed=seed, ct_base=100,
+                       stride=K.p.n + 1 if (K.p.n + 1) % 2 == 0 else K.p.n + 2)[:, : K.p.n + 1].contiguous()
+    lut = E.make_lut_poly(table, p_bits, K.p.N, shift)
+    assert np.array_equal(lut, O.make_lut_poly(table, p_bits, K.p.N, shift))
+    out = E.pbs(K.p, K.bskf, ct, E.from_u64_numpy(lut, cuda_dev))
+    got = _u64(out)
+    dec = O.lwe_decrypt(K.oS, got, shift)
+    assert np.array_equal(dec & 15, np.asarray(table)[msgs] & 15)
+    # phase agreement with the oracle's own f64-FFT evaluation of the same ciphertexts
+    ref = O.pbs(K.op, O.bsk_to_fourier(K.op, _u64(K.bsk)), _u64(ct), lut)
+    diff = (O.lwe_phase(K.oS, got) - O.lwe_phase(K.oS, ref)).view(np.int64).astype(np.float64)
+    assert np.log2(np.abs(diff).max() + 1) - 64 < tol_log2
+    return got
+
+
+@pytest.mark.parametrize("B", [1, 2, 16, 37])
+def test_pbs_toy_all_messages(O, toy, cuda_dev, B):
+    # GPU and oracle run different f64 FFT schedules: their phases differ by FFT rounding only
+    # (~2^-21 of the torus per CMux at beta=23), far below the decoding margin 2^-6.
+    _pbs_case(O, toy, cuda_dev, B, (np.arange(16) * 7 + 3) % 16, seed=B, tol_log2=-16)
+
+
+def test_pbs_two_levels(O, cuda_dev):
+    K = Keys(O, cuda_dev, TOY_L2)
+    _pbs_case(O, K, cuda_dev, 16, (np.arange(16) * 5 + 1) % 16, seed=3, tol_log2=-22)
+
+
+@pytest.mark.parametrize("B,table", [(16, list(range(16))), (16, [(3 * m * m + 1) % 16 for m in range(16)]),
+                                     (200, [(m + 5) % 16 for m in range(16)])])
+def test_pbs_stated_parameter_set(O, p4, cuda_dev, B, table):
+    """n=742, N=2048, l=1, beta=23: every message maps to LUT[m]; the GPU and oracle phases
+    agree to 2^-12.5 of the torus (two independent f64 FFT roundings, each ~2^-16 std, which is
+    the known "FFT noise" of this parameter set; the decoding margin is 2^-6)."""
+    got = _pbs_case(O, p4, cuda_dev, B, table, seed=B + 1, tol_log2=-12.5)
+    # output noise against the analytic bound (n * (1 + kN/2) * 2^-2*beta / 12 dominates)
+    msgs_dec = O.lwe_decrypt(p4.oS, got, 59)
+    err = (O.lwe_phase(p4.oS, got) - (msgs_dec.astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
+    assert np.log2(err.std()) - 64 < -14.0
+
+
+def test_keyswitch_then_pbs_atomic_pattern(O, p4, cuda_dev):
+    """Concrete's atomic pattern: big-key ciphertext -> keyswitch -> PBS -> big-key ciphertext."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    K = p4
+    msgs = np.arange(16)
+    ct = E.lwe_encrypt(K.S, torch.as_tensor(msgs), 59, K.op.sigma_glwe_abs, enc_seed=9, ct_base=0,
+                       stride=K.p.N + 2)[:, : K.p.N + 1].contiguous()
+    table = [(m * m) % 16 for m in range(16)]
+    lut = E.from_u64_numpy(E.make_lut_poly(table, 4, K.p.N, 59), cuda_dev)
+    out = E.pbs(K.p, K.bskf, E.keyswitch(K.p, K.ksk, ct), lut)
+    assert np.array_equal(O.lwe_decrypt(K.oS, _u64(out), 59) & 15, np.asarray(table))
+    # and again on the bootstrapped outputs (noise was reset, not accumulated)
+    out2 = E.pbs(K.p, K.bskf, E.keyswitch(K.p, K.ksk, out), lut)
+    assert np.array_equal(O.lwe_decrypt(K.oS, _u64(out2), 59) & 15, np.asarray(table)[np.asarray(table)])
+
+
+def test_pbs_per_ciphertext_lut_index(O, toy, cuda_dev):
+    import torch
+    from fhe_icp_b200 import engine as E
+    K = toy
+    msgs = np.arange(16)
+    ct = E.lwe_encrypt(K.s, torch.as_tensor(msgs), 59, K.op.sigma_lwe_abs, enc_seed=4, ct_base=0,
+                       stride=K.p.n + 2 - (K.p.n % 2))[:, : K.p.n + 1].contiguous()
+    t0, t1 = np.arange(16), (15 - np.arange(16))
+    luts = np.stack([E.make_lut_poly(t0, 4, K.p.N, 59), E.make_lut_poly(t1, 4, K.p.N, 59)])
+    idx = np.arange(16) % 2
+    out = E.pbs(K.p, K.bskf, ct, E.from_u64_numpy(luts, cuda_dev), torch.as_tensor(idx.astype(np.int32)))
+    exp = np.where(idx == 0, t0[msgs], t1[msgs])
+    assert np.array_equal(O.lwe_decrypt(K.oS, _u64(out), 59) & 15, exp)
