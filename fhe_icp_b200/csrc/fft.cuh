@@ -161,10 +161,13 @@ FHE_HD void dit32(double (&re)[32], double (&im)[32]) {
     }
 }
 
+// One 16 KB twiddle table serves both directions: tw[slot(k2, j1)] = W^(j1*k2) * omega^j1.
+// The forward pass reads row k2 across lanes j1, the inverse pass reads, per lane k2, the
+// conjugates along j1; the XOR swizzle makes both patterns bank-conflict free.
+//
 // ---- forward: registers hold z[j2] = (c[j] + i*c[j+1024]) for j = lane + 32*j2 (the caller
 // has NOT applied any twist).  After phase 2 register brev5(k1) holds bin k = lane + 32*k1.
-// twf[k2*32 + j1] = W^(j1*k2) * omega^j1.
-FHE_HD void fwd_phase1(double (&re)[32], double (&im)[32], const cplx* twf, cplx* buf, int lane) {
+FHE_HD void fwd_phase1(double (&re)[32], double (&im)[32], const cplx* tw, cplx* buf, int lane) {
 #pragma unroll
     for (int j2 = 1; j2 < 32; ++j2) {  // twist factor omega^(32*j2)
         const double cr = FHE_C128_RE(j2), ci = FHE_C128_IM(j2);
@@ -176,7 +179,7 @@ FHE_HD void fwd_phase1(double (&re)[32], double (&im)[32], const cplx* twf, cplx
 #pragma unroll
     for (int p = 0; p < 32; ++p) {
         const int k2 = brev5(p);
-        const cplx w = twf[k2 * 32 + lane];
+        const cplx w = tw[slot(k2, lane)];
         cplx v;
         v.x = re[p] * w.x - im[p] * w.y;
         v.y = re[p] * w.y + im[p] * w.x;
@@ -195,15 +198,14 @@ FHE_HD void fwd_phase2(double (&re)[32], double (&im)[32], const cplx* buf, int 
 
 // ---- inverse: register brev5(k1) holds bin k = lane + 32*k1.  After phase 2 register j2 holds
 // (c[j] + i*c[j+1024]) for j = lane + 32*j2, fully untwisted and scaled by 1/1024.
-// twi[j1*32 + k2] = conj(W^(j1*k2) * omega^j1) / 1024.
-FHE_HD void inv_phase1(double (&re)[32], double (&im)[32], const cplx* twi, cplx* buf, int lane) {
+FHE_HD void inv_phase1(double (&re)[32], double (&im)[32], const cplx* tw, cplx* buf, int lane) {
     dit32<-1>(re, im);
 #pragma unroll
     for (int j1 = 0; j1 < 32; ++j1) {
-        const cplx w = twi[j1 * 32 + lane];
+        const cplx w = tw[slot(lane, j1)];  // multiply by conj(w)
         cplx v;
-        v.x = re[j1] * w.x - im[j1] * w.y;
-        v.y = re[j1] * w.y + im[j1] * w.x;
+        v.x = re[j1] * w.x + im[j1] * w.y;
+        v.y = im[j1] * w.x - re[j1] * w.y;
         buf[slot(j1, lane)] = v;
     }
 }
@@ -215,28 +217,25 @@ FHE_HD void inv_phase2(double (&re)[32], double (&im)[32], const cplx* buf, int 
         im[p] = v.y;
     }
     dit32<-1>(re, im);
+    re[0] *= 0x1p-10;
+    im[0] *= 0x1p-10;
 #pragma unroll
-    for (int j2 = 1; j2 < 32; ++j2) {  // conj(omega^(32*j2))
-        const double cr = FHE_C128_RE(j2), ci = -FHE_C128_IM(j2);
+    for (int j2 = 1; j2 < 32; ++j2) {  // conj(omega^(32*j2)) / 1024 (power-of-two scale: exact)
+        const double cr = FHE_C128_RE(j2) * 0x1p-10, ci = -FHE_C128_IM(j2) * 0x1p-10;
         const double a = re[j2], b = im[j2];
         re[j2] = a * cr - b * ci;
         im[j2] = a * ci + b * cr;
     }
 }
 
-// host: inter-pass twiddle tables (computed in long double, rounded once)
-inline void fill_twiddle_tables(cplx* twf, cplx* twi) {
+// host: the inter-pass twiddle table (computed in long double, rounded once)
+inline void fill_twiddle_table(cplx* tw) {
     const long double two_pi = 6.283185307179586476925286766559005768L;
-    for (int a = 0; a < 32; ++a) {      // a = k2 (forward rows) / j1 (inverse rows)
-        for (int b = 0; b < 32; ++b) {  // b = lane
-            // forward: row k2=a, lane j1=b : W^(j1*k2) * omega^j1
-            long double ang = two_pi * ((long double)(a * b) / 1024.0L + (long double)b / 4096.0L);
-            twf[a * 32 + b].x = (double)cosl(ang);
-            twf[a * 32 + b].y = (double)sinl(ang);
-            // inverse: row j1=a, lane k2=b : conj(W^(j1*k2) * omega^j1) / 1024
-            long double ang2 = two_pi * ((long double)(a * b) / 1024.0L + (long double)a / 4096.0L);
-            twi[a * 32 + b].x = (double)(cosl(ang2) / 1024.0L);
-            twi[a * 32 + b].y = (double)(-sinl(ang2) / 1024.0L);
+    for (int k2 = 0; k2 < 32; ++k2) {
+        for (int j1 = 0; j1 < 32; ++j1) {
+            long double ang = two_pi * ((long double)(j1 * k2) / 1024.0L + (long double)j1 / 4096.0L);
+            tw[slot(k2, j1)].x = (double)cosl(ang);
+            tw[slot(k2, j1)].y = (double)sinl(ang);
         }
     }
 }

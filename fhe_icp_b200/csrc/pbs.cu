@@ -27,26 +27,25 @@ constexpr int PBS_N = nfft::NPOLY;
 constexpr int PBS_M = nfft::M;
 
 // ------------------------------------------------------------------------------- twiddle tables
-static cplx* g_tw = nullptr;  // [2][1024]: forward, inverse (per device)
+static cplx* g_tw = nullptr;  // [1024] swizzled inter-pass twiddles (per device)
 static int g_tw_device = -1;
 static std::mutex g_tw_mu;
 
-static cudaError_t get_tables(const cplx** twf, const cplx** twi) {
+static cudaError_t get_tables(const cplx** tw) {
     std::lock_guard<std::mutex> lk(g_tw_mu);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (g_tw == nullptr || g_tw_device != dev) {
-        static cplx h[2 * PBS_M];
-        nfft::fill_twiddle_tables(h, h + PBS_M);
+        static cplx h[PBS_M];
+        nfft::fill_twiddle_table(h);
         cplx* d = nullptr;
         if ((e = cudaMalloc(&d, sizeof(h))) != cudaSuccess) return e;
         if ((e = cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
         g_tw = d;  // (tables of a previous device are intentionally kept alive)
         g_tw_device = dev;
     }
-    *twf = g_tw;
-    *twi = g_tw + PBS_M;
+    *tw = g_tw;
     return cudaSuccess;
 }
 
@@ -100,8 +99,8 @@ bsk_to_fourier_kernel(const uint64_t* __restrict__ bsk, int64_t polys, const cpl
 
 cudaError_t launch_bsk_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* d_bsk, double* d_bskf,
                                   cudaStream_t s) {
-    const cplx *twf, *twi;
-    cudaError_t e = get_tables(&twf, &twi);
+    const cplx* twf;
+    cudaError_t e = get_tables(&twf);
     if (e != cudaSuccess) return e;
     const int64_t polys = (int64_t)p.n * (p.k + 1) * p.l_pbs * (p.k + 1);
     const size_t smem = sizeof(cplx) * PBS_M * (1 + B2F_WARPS);
@@ -115,7 +114,9 @@ cudaError_t launch_bsk_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* 
 
 // ------------------------------------------------------------------------------- blind rotation
 // Shared memory per CTA:
-//   twf, twi                      2 x 16 KB   inter-pass twiddles
+//   tw                            16 KB    inter-pass twiddles (swizzled, both directions)
+//   BSK stage (L == 1 only)       64 KB    BSK_i, filled by one TMA bulk copy per iteration from a
+//                                          producer warp while the workers run their FFTs
 //   per ciphertext:  ACC          (K+1) x 16 KB (u64 coefficients)
 //                    tile         (K+1) x 16 KB (per-warp transpose tile; with L == 1 it also
 //                                                carries that warp's Fourier digits)
@@ -124,38 +125,69 @@ cudaError_t launch_bsk_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* 
 template <int K, int L>
 struct PbsSmem {
     static constexpr int POLYS = K + 1;
+    static constexpr bool STAGE = (L == 1);
+    static constexpr size_t tw_bytes = (size_t)PBS_M * 16;
+    static constexpr size_t stage_bytes = STAGE ? (size_t)POLYS * L * POLYS * PBS_M * 16 : 0;
+    static constexpr size_t bar_bytes = 128;
+    static constexpr size_t head_bytes = tw_bytes + stage_bytes + bar_bytes;
     static constexpr size_t acc_bytes = (size_t)POLYS * PBS_N * 8;
     static constexpr size_t tile_bytes = (size_t)POLYS * PBS_M * 16;
     static constexpr size_t f_bytes = L > 1 ? (size_t)POLYS * L * PBS_M * 16 : 0;
-    __host__ __device__ static size_t per_ct(int n) { return acc_bytes + tile_bytes + f_bytes + (((size_t)(n + 1) * 2 + 15) & ~(size_t)15); }
-    static size_t total(int n, int nct) { return 2 * (size_t)PBS_M * 16 + (size_t)nct * per_ct(n); }
+    __host__ __device__ static size_t per_ct(int n) {
+        return acc_bytes + tile_bytes + f_bytes + (((size_t)(n + 1) * 2 + 127) & ~(size_t)127);
+    }
+    static size_t total(int n, int nct) { return head_bytes + (size_t)nct * per_ct(n); }
 };
 
 template <int K, int L, int NCT>
-__global__ void __launch_bounds__(NCT*(K + 1) * 32, 1)
+__global__ void __launch_bounds__(NCT*(K + 1) * 32 + (L == 1 ? 32 : 0), 1)
 pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
            const uint64_t* __restrict__ luts, const int32_t* __restrict__ lut_index, const cplx* __restrict__ g_tw,
            uint64_t* __restrict__ out) {
+    using S = PbsSmem<K, L>;
     constexpr int POLYS = K + 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* twf = reinterpret_cast<cplx*>(smem_raw);
-    cplx* twi = twf + PBS_M;
-    for (int i = threadIdx.x; i < 2 * PBS_M; i += blockDim.x) twf[i] = g_tw[i];
+    constexpr bool STAGE = S::STAGE;
+    constexpr int WORKERS = NCT * POLYS * 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* tw = reinterpret_cast<cplx*>(smem_raw);
+    cplx* stage = reinterpret_cast<cplx*>(smem_raw + S::tw_bytes);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + S::tw_bytes + S::stage_bytes);
+    uint64_t* bar_empty = bar_full + 1;
+    for (int i = threadIdx.x; i < PBS_M; i += blockDim.x) tw[i] = g_tw[i];
+    if (STAGE && threadIdx.x == 0) {
+        mbar_init(bar_full, 1);
+        mbar_init(bar_empty, NCT * POLYS);
+        mbar_fence_init();
+    }
+    constexpr uint32_t STAGE_BYTES = (uint32_t)S::stage_bytes;
+    const size_t bsk_elems = (size_t)POLYS * L * POLYS * PBS_M;  // complex elements of one BSK_i
+
+    if (STAGE && threadIdx.x >= WORKERS) {
+        // ===== producer warp: stream BSK_0 .. BSK_{n-1} through the single stage buffer
+        __syncthreads();
+        if (threadIdx.x == WORKERS) {
+            for (int i = 0; i < n; ++i) {
+                if (i > 0) mbar_wait(bar_empty, (uint32_t)((i - 1) & 1));
+                mbar_expect_tx(bar_full, STAGE_BYTES);
+                tma_load_1d(stage, bskf + (size_t)i * bsk_elems, STAGE_BYTES, bar_full);
+            }
+        }
+        return;
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ctl = warp / POLYS;        // ciphertext slot within the CTA
     const int t = warp - ctl * POLYS;    // polynomial owned by this warp
     const int64_t b = (int64_t)blockIdx.x * NCT + ctl;
-    const size_t per_ct = PbsSmem<K, L>::per_ct(n);
-    unsigned char* base = smem_raw + 2 * (size_t)PBS_M * 16 + (size_t)ctl * per_ct;
+    const size_t per_ct = S::per_ct(n);
+    unsigned char* base = smem_raw + S::head_bytes + (size_t)ctl * per_ct;
     uint64_t* acc_all = reinterpret_cast<uint64_t*>(base);
-    cplx* tile_all = reinterpret_cast<cplx*>(base + PbsSmem<K, L>::acc_bytes);
-    cplx* f_all = reinterpret_cast<cplx*>(base + PbsSmem<K, L>::acc_bytes + PbsSmem<K, L>::tile_bytes);
-    uint16_t* a_tilde = reinterpret_cast<uint16_t*>(base + PbsSmem<K, L>::acc_bytes + PbsSmem<K, L>::tile_bytes +
-                                                    PbsSmem<K, L>::f_bytes);
+    cplx* tile_all = reinterpret_cast<cplx*>(base + S::acc_bytes);
+    cplx* f_all = reinterpret_cast<cplx*>(base + S::acc_bytes + S::tile_bytes);
+    uint16_t* a_tilde = reinterpret_cast<uint16_t*>(base + S::acc_bytes + S::tile_bytes + S::f_bytes);
     uint64_t* acc = acc_all + (size_t)t * PBS_N;
     cplx* tile = tile_all + (size_t)t * PBS_M;
-    const bool live = b < B;  // dead slots still take part in barriers
+    const bool live = b < B;  // dead slots still take part in every barrier
     const int bar_id = 1 + ctl, bar_n = POLYS * 32;
 
     // ---- prologue: mod-switch the mask, ACC = X^(-b~) * (0,...,0,LUT)
@@ -176,7 +208,7 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
             acc[x] = v;
         }
     }
-    __syncthreads();  // twiddle tables + all accumulators in place
+    __syncthreads();  // twiddle table, mbarriers and all accumulators in place
 
     const uint64_t Bm = (1ULL << beta) - 1, half = 1ULL << (beta - 1);
     const int tot = L * beta;
@@ -187,8 +219,8 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
     double re[32], im[32];
     for (int i = 0; i < n; ++i) {
         const int at = a_tilde[i];
-        if (at == 0) continue;  // X^0 - 1 = 0: uniform across the ciphertext's warps
-        const cplx* bk = bskf + (size_t)i * POLYS * L * POLYS * PBS_M;
+        if (!STAGE && at == 0) continue;  // X^0 - 1 = 0 (staged kernel: every warp must consume BSK_i)
+        const cplx* bk = STAGE ? stage : bskf + (size_t)i * bsk_elems;
         // ---- digits of (X^at - 1) * ACC_t, one forward FFT per level
 #pragma unroll 1
         for (int lev = 0; lev < L; ++lev) {
@@ -205,7 +237,7 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
                 re[j2] = (double)((int32_t)((u0 >> sh) & Bm) - (int32_t)half);
                 im[j2] = (double)((int32_t)((u1 >> sh) & Bm) - (int32_t)half);
             }
-            nfft::fwd_phase1(re, im, twf, tile, lane);
+            nfft::fwd_phase1(re, im, tw, tile, lane);
             __syncwarp();
             nfft::fwd_phase2(re, im, tile, lane);
             if (L > 1) {
@@ -231,6 +263,7 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
             }
         }
         named_bar_sync(bar_id, bar_n);  // (A) every polynomial's Fourier digits are visible
+        if (STAGE) mbar_wait(bar_full, (uint32_t)(i & 1));  // BSK_i has landed in shared memory
         // ---- output column t:  out = sum_{t',lev} F[t'][lev] * BSK_i[t'][lev][t]
         if (L == 1) {
             const cplx* bown = bk + ((size_t)(t * L) * POLYS + t) * PBS_M;
@@ -270,9 +303,13 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
                 }
             }
         }
+        if (STAGE) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty);  // this warp is done with BSK_i
+        }
         named_bar_sync(bar_id, bar_n);  // (B) nobody reads the published digits any more
         // ---- inverse FFT and ACC_t += result
-        nfft::inv_phase1(re, im, twi, tile, lane);
+        nfft::inv_phase1(re, im, tw, tile, lane);
         __syncwarp();
         nfft::inv_phase2(re, im, tile, lane);
 #pragma unroll
@@ -314,8 +351,8 @@ static cudaError_t launch_pbs_t(const fhe_b200_pbs_params& p, const cplx* bskf, 
     cudaError_t e = cudaFuncSetAttribute(pbs_kernel<K, L, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((B + NCT - 1) / NCT);
-    pbs_kernel<K, L, NCT><<<grid, NCT*(K + 1) * 32, smem, s>>>(bskf, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tw,
-                                                             d_out);
+    const unsigned threads = NCT * (K + 1) * 32 + (L == 1 ? 32 : 0);
+    pbs_kernel<K, L, NCT><<<grid, threads, smem, s>>>(bskf, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tw, d_out);
     count_launch();
     return cudaGetLastError();
 }
@@ -323,19 +360,19 @@ static cudaError_t launch_pbs_t(const fhe_b200_pbs_params& p, const cplx* bskf, 
 cudaError_t launch_pbs(const fhe_b200_pbs_params& p, const double* d_bskf, const uint64_t* d_in, int64_t B,
                        const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
                        cudaStream_t s) {
-    const cplx *twf, *twi;
-    cudaError_t e = get_tables(&twf, &twi);
+    const cplx* tw;
+    cudaError_t e = get_tables(&tw);
     if (e != cudaSuccess) return e;
     const cplx* bskf = reinterpret_cast<const cplx*>(d_bskf);
-    const bool wide = B > (int64_t)sm_count;  // more ciphertexts than SMs: share BSK loads inside a CTA
+    const bool wide = B > (int64_t)sm_count;  // more ciphertexts than SMs: share the staged BSK_i inside a CTA
     switch (p.l_pbs) {
         case 1:
-            return wide ? launch_pbs_t<1, 1, 2>(p, bskf, d_in, B, d_luts, d_lut_index, twf, d_out, s)
-                        : launch_pbs_t<1, 1, 1>(p, bskf, d_in, B, d_luts, d_lut_index, twf, d_out, s);
+            return wide ? launch_pbs_t<1, 1, 2>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s)
+                        : launch_pbs_t<1, 1, 1>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s);
         case 2:
-            return launch_pbs_t<1, 2, 1>(p, bskf, d_in, B, d_luts, d_lut_index, twf, d_out, s);
+            return launch_pbs_t<1, 2, 1>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s);
         case 3:
-            return launch_pbs_t<1, 3, 1>(p, bskf, d_in, B, d_luts, d_lut_index, twf, d_out, s);
+            return launch_pbs_t<1, 3, 1>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s);
         default:
             return cudaErrorInvalidValue;
     }

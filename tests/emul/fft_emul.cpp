@@ -7,12 +7,12 @@ using namespace fhe::nfft;
 extern "C" {
 // coef: 2048 doubles -> bins: 1024 complex (re,im interleaved), natural order
 void emul_forward(const double* coef, double* bins) {
-    std::vector<cplx> twf(1024), twi(1024), buf(1024);
-    fill_twiddle_tables(twf.data(), twi.data());
+    std::vector<cplx> tw(1024), buf(1024);
+    fill_twiddle_table(tw.data());
     static double re[32][32], im[32][32];
     for (int lane = 0; lane < 32; ++lane) {
         for (int j2 = 0; j2 < 32; ++j2) { re[lane][j2] = coef[lane + 32 * j2]; im[lane][j2] = coef[lane + 32 * j2 + 1024]; }
-        fwd_phase1(re[lane], im[lane], twf.data(), buf.data(), lane);
+        fwd_phase1(re[lane], im[lane], tw.data(), buf.data(), lane);
     }
     for (int lane = 0; lane < 32; ++lane) {
         fwd_phase2(re[lane], im[lane], buf.data(), lane);
@@ -23,15 +23,15 @@ void emul_forward(const double* coef, double* bins) {
     }
 }
 void emul_inverse(const double* bins, double* coef) {
-    std::vector<cplx> twf(1024), twi(1024), buf(1024);
-    fill_twiddle_tables(twf.data(), twi.data());
+    std::vector<cplx> tw(1024), buf(1024);
+    fill_twiddle_table(tw.data());
     static double re[32][32], im[32][32];
     for (int lane = 0; lane < 32; ++lane) {
         for (int k1 = 0; k1 < 32; ++k1) {
             re[lane][brev5(k1)] = bins[2 * (lane + 32 * k1)];
             im[lane][brev5(k1)] = bins[2 * (lane + 32 * k1) + 1];
         }
-        inv_phase1(re[lane], im[lane], twi.data(), buf.data(), lane);
+        inv_phase1(re[lane], im[lane], tw.data(), buf.data(), lane);
     }
     for (int lane = 0; lane < 32; ++lane) {
         inv_phase2(re[lane], im[lane], buf.data(), lane);

@@ -100,9 +100,12 @@ def _pbs_case(O, K, cuda_dev, B, table, seed, tol_log2):
 
 @pytest.mark.parametrize("B", [1, 2, 16, 37])
 def test_pbs_toy_all_messages(O, toy, cuda_dev, B):
-    # GPU and oracle run different f64 FFT schedules: their phases differ by FFT rounding only
-    # (~2^-21 of the torus per CMux at beta=23), far below the decoding margin 2^-6.
-    _pbs_case(O, toy, cuda_dev, B, (np.arange(16) * 7 + 3) % 16, seed=B, tol_log2=-16)
+    # GPU and oracle run different f64 FFT schedules.  Their accumulators differ by FFT rounding
+    # (~2^-21 of the torus per CMux at beta=23), which flips some 23-bit digit roundings in the next
+    # CMux, so the two outputs are independent realisations of the gadget rounding noise
+    # (std ~2^-19.8 per CMux): the phase difference is bounded by the PBS noise bound, not by
+    # FFT rounding alone.  The decoding margin is 2^-6, so decrypted values are identical.
+    _pbs_case(O, toy, cuda_dev, B, (np.arange(16) * 7 + 3) % 16, seed=B, tol_log2=-14)
 
 
 def test_pbs_two_levels(O, cuda_dev):
@@ -114,9 +117,9 @@ def test_pbs_two_levels(O, cuda_dev):
                                      (200, [(m + 5) % 16 for m in range(16)])])
 def test_pbs_stated_parameter_set(O, p4, cuda_dev, B, table):
     """n=742, N=2048, l=1, beta=23: every message maps to LUT[m]; the GPU and oracle phases
-    agree to 2^-12.5 of the torus (two independent f64 FFT roundings, each ~2^-16 std, which is
-    the known "FFT noise" of this parameter set; the decoding margin is 2^-6)."""
-    got = _pbs_case(O, p4, cuda_dev, B, table, seed=B + 1, tol_log2=-12.5)
+    agree to 2^-12 of the torus (each output carries the set's PBS noise, std ~2^-15.5, with
+    independent rounding realisations; the decoding margin is 2^-6)."""
+    got = _pbs_case(O, p4, cuda_dev, B, table, seed=B + 1, tol_log2=-12)
     # output noise against the analytic bound (n * (1 + kN/2) * 2^-2*beta / 12 dominates)
     msgs_dec = O.lwe_decrypt(p4.oS, got, 59)
     err = (O.lwe_phase(p4.oS, got) - (msgs_dec.astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
