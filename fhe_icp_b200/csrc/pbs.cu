@@ -115,8 +115,8 @@ cudaError_t launch_bsk_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* 
 // ------------------------------------------------------------------------------- blind rotation
 // Shared memory per CTA:
 //   tw                            16 KB    inter-pass twiddles (swizzled, both directions)
-//   BSK stage (L == 1 only)       64 KB    BSK_i, filled by one TMA bulk copy per iteration from a
-//                                          producer warp while the workers run their FFTs
+//   BSK stage (L == 1 only)       64 KB    BSK_i, filled by one TMA bulk copy per iteration while
+//                                          the warps run their inverse / forward FFTs
 //   per ciphertext:  ACC          (K+1) x 16 KB (u64 coefficients)
 //                    tile         (K+1) x 16 KB (per-warp transpose tile; with L == 1 it also
 //                                                carries that warp's Fourier digits)
@@ -140,7 +140,7 @@ struct PbsSmem {
 };
 
 template <int K, int L, int NCT>
-__global__ void __launch_bounds__(NCT*(K + 1) * 32 + (L == 1 ? 32 : 0), 1)
+__global__ void __launch_bounds__(NCT*(K + 1) * 32, 1)
 pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
            const uint64_t* __restrict__ luts, const int32_t* __restrict__ lut_index, const cplx* __restrict__ g_tw,
            uint64_t* __restrict__ out) {
@@ -161,19 +161,6 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
     }
     constexpr uint32_t STAGE_BYTES = (uint32_t)S::stage_bytes;
     const size_t bsk_elems = (size_t)POLYS * L * POLYS * PBS_M;  // complex elements of one BSK_i
-
-    if (STAGE && threadIdx.x >= WORKERS) {
-        // ===== producer warp: stream BSK_0 .. BSK_{n-1} through the single stage buffer
-        __syncthreads();
-        if (threadIdx.x == WORKERS) {
-            for (int i = 0; i < n; ++i) {
-                if (i > 0) mbar_wait(bar_empty, (uint32_t)((i - 1) & 1));
-                mbar_expect_tx(bar_full, STAGE_BYTES);
-                tma_load_1d(stage, bskf + (size_t)i * bsk_elems, STAGE_BYTES, bar_full);
-            }
-        }
-        return;
-    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ctl = warp / POLYS;        // ciphertext slot within the CTA
@@ -209,6 +196,13 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
         }
     }
     __syncthreads();  // twiddle table, mbarriers and all accumulators in place
+    // BSK_i is streamed through the single stage buffer by thread 0: BSK_0 now, BSK_{i+1} as soon as
+    // every warp of the CTA has finished reading BSK_i (checked between its own inverse-FFT passes,
+    // when the other warps have normally arrived already, so the wait does not spin).
+    if (STAGE && threadIdx.x == 0) {
+        mbar_expect_tx(bar_full, STAGE_BYTES);
+        tma_load_1d(stage, bskf, STAGE_BYTES, bar_full);
+    }
 
     const uint64_t Bm = (1ULL << beta) - 1, half = 1ULL << (beta - 1);
     const int tot = L * beta;
@@ -310,6 +304,11 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
         named_bar_sync(bar_id, bar_n);  // (B) nobody reads the published digits any more
         // ---- inverse FFT and ACC_t += result
         nfft::inv_phase1(re, im, tw, tile, lane);
+        if (STAGE && threadIdx.x == 0 && i + 1 < n) {
+            mbar_wait(bar_empty, (uint32_t)(i & 1));
+            mbar_expect_tx(bar_full, STAGE_BYTES);
+            tma_load_1d(stage, bskf + (size_t)(i + 1) * bsk_elems, STAGE_BYTES, bar_full);
+        }
         __syncwarp();
         nfft::inv_phase2(re, im, tile, lane);
 #pragma unroll
@@ -351,7 +350,7 @@ static cudaError_t launch_pbs_t(const fhe_b200_pbs_params& p, const cplx* bskf, 
     cudaError_t e = cudaFuncSetAttribute(pbs_kernel<K, L, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((B + NCT - 1) / NCT);
-    const unsigned threads = NCT * (K + 1) * 32 + (L == 1 ? 32 : 0);
+    const unsigned threads = NCT * (K + 1) * 32;
     pbs_kernel<K, L, NCT><<<grid, threads, smem, s>>>(bskf, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tw, d_out);
     count_launch();
     return cudaGetLastError();

@@ -1,0 +1,171 @@
+"""Host-side logic and the C-ABI surface (no GPU): the FHESimilarityModel / estimator mirror of
+the reference interface, quantizers, parameter selection, and that libfhe_b200.so loads and
+exports every symbol include/fhe_b200.h declares."""
+import ctypes as C
+import pickle
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+# ------------------------------------------------------------------------------- C-ABI
+def test_library_exports_every_declared_symbol():
+    from fhe_icp_b200 import _native as N
+    header = (ROOT / "include" / "fhe_b200.h").read_text()
+    declared = set(re.findall(r"\b(fhe_b200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = N.lib()  # builds if stale, binds argtypes for every entry of N.SIGNATURES
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/fhe_b200.h but not exported"
+    assert declared == set(N.SIGNATURES), "ctypes table and header disagree"
+    assert lib.fhe_b200_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from fhe_icp_b200 import _native as N
+    assert C.sizeof(N.PBSParams) == 48          # 8 x int32 + 2 x double
+    assert C.sizeof(N.SimilaritySpec) == 6 * 4 + 2 * 8 + 4 * 8 + 8 + 8 + 8
+    assert N.SimilaritySpec.key_seed.offset == 88
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from fhe_icp_b200 import _native as N
+    with pytest.raises(N.FheB200Error) as e:
+        N.Context(0)
+    assert e.value.code == N.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=8, n_bits=8, seed=0, verbose=False)
+    X, _ = m.train(n_samples=50)
+    m.compile(X[:10])
+    with pytest.raises(N.FheB200Error):
+        m.predict_encrypted(X[:2])        # fhe="execute" must fail loudly, never fall back
+    assert m.predict_clear(X[:2]).shape == (2,)
+
+
+def test_product_never_imports_the_oracle():
+    for f in (ROOT / "fhe_icp_b200").rglob("*"):
+        if f.suffix in (".py", ".cu", ".cuh", ".h"):
+            txt = f.read_text()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+            assert not re.search(r"#\s*include\s*[<\"].*oracle", txt), f
+            assert "liboracle" not in txt, f
+
+
+def test_invalid_arguments_return_errors_not_crashes():
+    from fhe_icp_b200 import _native as N
+    lib = N.lib()
+    assert lib.fhe_b200_ctx_create(0, None) == N.ERR_INVALID
+    assert lib.fhe_b200_lincomb(None, None, 1, 1, 1, 2, None, 1, None, 0, None, None) == N.ERR_INVALID
+    assert b"null ctx" in lib.fhe_b200_last_error()
+    assert lib.fhe_b200_ksk_words(None) == 0
+
+
+# ------------------------------------------------------------------------------- model surface
+def test_model_surface_metrics_and_errors(tmp_path):
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=42, verbose=False)
+    with pytest.raises(RuntimeError, match="Model not trained"):
+        m.compile(np.zeros((2, 128), dtype=np.float32))
+    with pytest.raises(RuntimeError, match="Model not trained"):
+        m.predict_clear(np.zeros((2, 128), dtype=np.float32))
+    with pytest.raises(RuntimeError, match="Model not compiled"):
+        m.predict_encrypted(np.zeros((2, 128), dtype=np.float32))
+    X, y = m.train()
+    assert X.shape == (1000, 128) and X.dtype == np.float32 and y.shape == (1000,)
+    assert {"train_time", "train_score"} <= set(m.metrics) and m.metrics["train_score"] > 0.99
+    m.compile(X[:10])
+    assert m.compiled and {"compile_time", "compile_memory_mb", "circuit_max_bits"} <= set(m.metrics)
+    assert m.model.fhe_circuit.graph.maximum_integer_bit_width() == m.metrics["circuit_max_bits"]
+    assert np.abs(m.predict_clear(X) - y).max() < 0.1      # accuracy envelope (test_fixed_pipeline.py:77)
+    with pytest.raises(ValueError, match="Unknown similarity type"):
+        FHESimilarityModel(similarity_type="nope", verbose=False)._prepare_training_data(4)
+    p = tmp_path / "m.pkl"
+    m.save(str(p))
+    data = pickle.load(open(p, "rb"))
+    assert {"input_dim", "n_bits", "similarity_type", "metrics", "model_params"} <= set(data)
+    m2 = FHESimilarityModel.load(str(p))
+    assert not m2.compiled and np.array_equal(m2.predict_clear(X[:5]), m.predict_clear(X[:5]))
+
+
+def test_seeded_generator_matches_reference_draw_order():
+    """seed=S reproduces what the reference generates after np.random.seed(S) (fhe_similarity.py:41-58)."""
+    from fhe_icp_b200 import FHESimilarityModel
+    np.random.seed(5)
+    n, d = 50, 16
+    e1 = np.random.randn(n, d).astype(np.float32); e1 /= np.linalg.norm(e1, axis=1, keepdims=True)
+    e2 = np.random.randn(n, d).astype(np.float32); e2 /= np.linalg.norm(e2, axis=1, keepdims=True)
+    mask = np.random.rand(n) > 0.5
+    e2[mask] = e1[mask] + 0.2 * np.random.randn(mask.sum(), d)
+    e2 /= np.linalg.norm(e2, axis=1, keepdims=True)
+    X, y = FHESimilarityModel(input_dim=d, seed=5, verbose=False)._prepare_training_data(n)
+    assert np.array_equal(X, e1 * e2) and np.array_equal(y, np.sum(e1 * e2, axis=1))
+
+
+def test_estimator_members_callers_reach_through():
+    from fhe_icp_b200 import LinearRegression, SGDRegressor
+    rng = np.random.RandomState(0)
+    X = rng.randn(200, 6).astype(np.float32)
+    y = X @ np.array([1, -2, 0.5, 0, 3, 1], dtype=np.float32) + 0.25
+    for est in (LinearRegression(n_bits=8), SGDRegressor(n_bits=8, max_iter=100, random_state=42)):
+        est.fit(X, y)
+        assert est.coef_.shape == (6,) and isinstance(est.intercept_, float)
+        assert est.score(X, y) > 0.98
+        est.compile(X[:20])
+        assert est.fhe_circuit.graph.maximum_integer_bit_width() >= 8
+        assert np.array_equal(est.predict(X[:3]), est.predict(X[:3], fhe="disable"))
+        assert np.array_equal(est.predict(X[:3], fhe="simulate"), est.predict(X[:3]))
+        with pytest.raises(ValueError):
+            est.predict(X[:3], fhe="bogus")
+        with pytest.raises(ValueError):
+            est.predict(X[:3, :5])
+    with pytest.raises(RuntimeError):
+        LinearRegression().predict(X)
+
+
+def test_weight_quantizer_both_regimes_and_two_output_decision():
+    """float32 fits give a huge weight zero-point (two encrypted outputs, client-side
+    correction), float64 fits degenerate to q_W = 1 (one output).  Both stay exact."""
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=42, verbose=False)
+    X, y = m._prepare_training_data(1000)
+    m.train(X.astype(np.float64), y.astype(np.float64))
+    m.compile(X[:10])
+    c = m.model.fhe_circuit
+    assert not c.two_outputs and set(m.model.spec.q_weights.tolist()) == {1} and m.model.spec.weight_q.zero_point == 0
+    assert c.lwe.n < 1100 and (c.lwe.n + 1) % 16 == 0
+    # a hand-made spread of coefficients (asymmetric quantizer, zero-point far from 0)
+    from fhe_icp_b200.quantization import QuantizedLinearSpec
+    coef = 1.0 + 6e-6 * np.linspace(-0.5, 0.5, 128)
+    spec = QuantizedLinearSpec.from_fit(coef, 0.0, X, 8)
+    assert abs(spec.weight_q.zero_point) > 10 ** 6 and spec.q_weights.min() == -128 and spec.q_weights.max() == 127
+    q = spec.input_q.quant(X[:50])
+    ref = (spec.input_q.dequant(q) * spec.weight_q.dequant(spec.q_weights)).sum(axis=1)
+    assert np.abs(spec.predict_clear(X[:50]) - ref).max() < 1e-3   # integer circuit == dequantized algebra
+
+
+def test_parameter_selection_follows_noise_bound():
+    from fhe_icp_b200.params import log2_sigma_for_dimension, select_lwe_params, z_score
+    assert abs(log2_sigma_for_dimension(742) + 17.06) < 0.05 and abs(log2_sigma_for_dimension(2048) + 51.67) < 0.05
+    assert abs(z_score(2 ** -40) - 7.15) < 0.05
+    prev = 0
+    for bits in (12, 16, 20, 24):
+        p = select_lwe_params(bits, 2.0 ** 19)
+        assert (p.n + 1) % 16 == 0 and p.stride % 2 == 0 and p.stride >= p.n + 1 and p.n >= prev
+        prev = p.n
+        # z * sigma * ||w|| < Delta / 2
+        assert np.log2(z_score(p.p_error)) + p.log2_out_noise < p.shift - 1 - 64 + 1e-9
+    with pytest.raises(ValueError, match="NoParametersFound"):
+        select_lwe_params(62, 1.0)
+
+
+def test_signed_bit_width():
+    from fhe_icp_b200.quantization import signed_bit_width
+    assert signed_bit_width(0, 255) == 8 and signed_bit_width(-128, 127) == 8 and signed_bit_width(-129, 0) == 9
+    assert signed_bit_width(0, 0) == 1 and signed_bit_width(-1, 0) == 1 and signed_bit_width(-1, 1) == 2
