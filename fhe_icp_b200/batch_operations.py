@@ -1,0 +1,228 @@
+"""Drop-in for the encrypted-compare callers in the reference's ``batch_operations.py``:
+``BatchConfig``, ``BatchProcessor.{encrypt_documents, compare_encrypted, search_similar,
+get_memory_stats}`` (/root/reference/batch_operations.py:26-40,120-295) with the same argument
+meaning, return types, ordering semantics and error behaviour.
+
+Differences, all on purpose:
+  * ``compare`` / ``search`` really execute FHE (the reference calls the clear model and says
+    "In production, this would run on encrypted data", batch_operations.py:231-233,276); the
+    decrypted scores are bit-identical to that clear quantized model.
+  * ``search_similar`` evaluates all documents in ONE batched encrypt -> dot -> decrypt pass
+    instead of a Python loop with a file read per document (batch_operations.py:268-279).
+  * BERT and the fitted PCA are upstream feature extraction with no weights available offline
+    (out of scope); any object with ``get_embedding / get_embeddings_batch``
+    and ``transform`` can be passed, the default is a deterministic synthetic embedder.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import logging
+from dataclasses import dataclass
+from datetime import datetime
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .fhe_similarity import FHESimilarityModel
+
+logger = logging.getLogger(__name__)
+
+
+@dataclass
+class BatchConfig:
+    """Configuration for batch operations (batch_operations.py:26-40)."""
+    batch_size: int = 10
+    max_memory_mb: int = 4000
+    checkpoint_interval: int = 50
+    show_progress: bool = True
+    force_gc: bool = True
+
+    def __post_init__(self):
+        if self.batch_size < 1:
+            raise ValueError("batch_size must be >= 1")
+        if self.max_memory_mb < 100:
+            raise ValueError("max_memory_mb must be >= 100")
+
+
+class SyntheticEmbedder:
+    """Deterministic stand-in for BertEmbedder + DimensionReducer: a unit-norm Gaussian vector
+    seeded by the SHA-256 of the text, optionally pulled towards a per-topic centre so that
+    related texts score high (texts sharing their first word share a topic)."""
+
+    def __init__(self, dim: int = 128, topic_weight: float = 0.9):
+        self.dim, self.topic_weight = dim, topic_weight
+
+    def _vec(self, key: str) -> np.ndarray:
+        seed = int.from_bytes(hashlib.sha256(key.encode()).digest()[:4], "little")
+        v = np.random.RandomState(seed).randn(self.dim)
+        return v / np.linalg.norm(v)
+
+    def get_embedding(self, text: str) -> np.ndarray:
+        words = text.strip().split()
+        v = self._vec("text:" + text)
+        if words and self.topic_weight > 0:
+            v = self.topic_weight * self._vec("topic:" + words[0].lower()) + (1 - self.topic_weight) * v
+        return (v / np.linalg.norm(v)).astype(np.float32)
+
+    def get_embeddings_batch(self, texts: List[str]) -> np.ndarray:
+        return np.stack([self.get_embedding(t) for t in texts]) if texts else np.zeros((0, self.dim), np.float32)
+
+
+class IdentityReducer:
+    def transform(self, X: np.ndarray) -> np.ndarray:
+        return np.asarray(X)
+
+
+class DocumentStore:
+    """Flat document store: one float32 matrix + a JSON index, insertion-ordered.  Replaces the
+    reference's one-pickle-per-document layout (encrypted_storage.py:40-47,73-108) for the fields
+    the compare path reads: ``load(doc_id).encrypted_embedding`` and ``list_documents()``."""
+
+    @dataclass
+    class Doc:
+        doc_id: str
+        content_hash: str
+        timestamp: str
+        encrypted_embedding: np.ndarray
+        metadata: dict
+
+    def __init__(self, storage_dir: Optional[str] = None, dim: int = 128):
+        self.dim = dim
+        self.dir = Path(storage_dir) if storage_dir else None
+        self.index: Dict[str, dict] = {}
+        self._rows: List[np.ndarray] = []
+        if self.dir is not None and (self.dir / "index.json").exists():
+            meta = json.loads((self.dir / "index.json").read_text())
+            self.dim = meta["dim"]
+            self.index = {d["doc_id"]: d for d in meta["documents"]}
+            mat = np.fromfile(self.dir / "embeddings.f32", dtype=np.float32).reshape(-1, self.dim)
+            self._rows = [mat[i] for i in range(mat.shape[0])]
+
+    def save(self, doc_id: str, embedding: np.ndarray, content_hash: str = "", metadata: Optional[dict] = None):
+        emb = np.asarray(embedding, dtype=np.float32)
+        if emb.ndim != 1:
+            raise ValueError(f"Expected 1D embedding, got shape {emb.shape}")
+        if emb.shape[0] != self.dim:
+            raise ValueError(f"Expected {self.dim}-dim embedding, got {emb.shape}")
+        rec = {"doc_id": doc_id, "row": len(self._rows), "timestamp": datetime.now().isoformat(),
+               "content_hash": content_hash, "size_bytes": int(emb.nbytes), "metadata": metadata or {}}
+        if doc_id in self.index:
+            rec["row"] = self.index[doc_id]["row"]
+            self._rows[rec["row"]] = emb
+        else:
+            self._rows.append(emb)
+        self.index[doc_id] = rec
+        return doc_id
+
+    def flush(self):
+        if self.dir is None:
+            return
+        self.dir.mkdir(parents=True, exist_ok=True)
+        self.matrix().tofile(self.dir / "embeddings.f32")
+        (self.dir / "index.json").write_text(json.dumps({"dim": self.dim, "documents": list(self.index.values())}))
+
+    def load(self, doc_id: str) -> "DocumentStore.Doc":
+        if doc_id not in self.index:
+            raise KeyError(f"Document {doc_id} not found")
+        r = self.index[doc_id]
+        return DocumentStore.Doc(doc_id, r["content_hash"], r["timestamp"], self._rows[r["row"]], r["metadata"])
+
+    def list_documents(self) -> List[dict]:
+        return sorted(self.index.values(), key=lambda r: r["row"])
+
+    def matrix(self) -> np.ndarray:
+        return np.stack(self._rows) if self._rows else np.zeros((0, self.dim), np.float32)
+
+    def __len__(self):
+        return len(self._rows)
+
+
+class BatchProcessor:
+    """Handle batch encryption and comparison operations."""
+
+    def __init__(self, embedder=None, reducer=None, key_manager=None, storage: Optional[DocumentStore] = None,
+                 config: Optional[BatchConfig] = None, fhe_model: Optional[FHESimilarityModel] = None,
+                 fhe: str = "execute", seed: Optional[int] = 0, device: Optional[int] = None, init_model: bool = True):
+        self.embedder = embedder or SyntheticEmbedder(128)
+        self.reducer = reducer or IdentityReducer()
+        self.key_manager = key_manager
+        self.storage = storage if storage is not None else DocumentStore()
+        self.config = config or BatchConfig()
+        self.fhe = fhe
+        self.seed, self.device = seed, device
+        self.fhe_model = fhe_model
+        if self.fhe_model is None and init_model:
+            self._init_model()
+
+    def _init_model(self):
+        """Train + compile the 128-d / 8-bit similarity model (batch_operations.py:78-93)."""
+        self.fhe_model = FHESimilarityModel(input_dim=128, n_bits=8, seed=self.seed, device=self.device, verbose=False)
+        X_train, _ = self.fhe_model.train()
+        self.fhe_model.compile(X_train[:10])
+        logger.info("FHE model initialized and compiled with similarity training data")
+
+    def _require_model(self):
+        if self.fhe_model is None:
+            raise RuntimeError("No FHE model initialized. Generate keys first.")
+
+    def _predict(self, X: np.ndarray) -> np.ndarray:
+        if self.fhe == "execute":
+            return self.fhe_model.predict_encrypted(X)
+        return self.fhe_model.model.predict(X)
+
+    def encrypt_documents(self, texts: List[str], doc_ids: Optional[List[str]] = None,
+                          metadata: Optional[List[Dict]] = None) -> List[str]:
+        self._require_model()
+        n_docs = len(texts)
+        if doc_ids is None:
+            doc_ids = [None] * n_docs
+        stamp = datetime.now().strftime('%Y%m%d_%H%M%S')
+        doc_ids = [d if d is not None else f"doc_{stamp}_{i}" for i, d in enumerate(doc_ids)]
+        if metadata is None:
+            metadata = [{} for _ in range(n_docs)]
+        encrypted_ids = []
+        for i in range(0, n_docs, self.config.batch_size):
+            j = min(i + self.config.batch_size, n_docs)
+            reduced = self.reducer.transform(self.embedder.get_embeddings_batch(texts[i:j]))
+            for text, doc_id, meta, emb in zip(texts[i:j], doc_ids[i:j], metadata[i:j], reduced):
+                self.storage.save(doc_id, emb.astype(np.float32), hashlib.sha256(text.encode()).hexdigest(), meta)
+                encrypted_ids.append(doc_id)
+        self.storage.flush()
+        logger.info(f"Encrypted {len(encrypted_ids)} documents")
+        return encrypted_ids
+
+    def compare_encrypted(self, doc_id1: str, doc_id2: str) -> float:
+        self._require_model()
+        doc1 = self.storage.load(doc_id1)
+        doc2 = self.storage.load(doc_id2)
+        X = (doc1.encrypted_embedding * doc2.encrypted_embedding).reshape(1, -1)
+        return float(self._predict(X)[0])
+
+    def search_similar(self, query_text: str, top_k: int = 5, min_similarity: float = 0.5) -> List[Tuple[str, float]]:
+        self._require_model()
+        query_embedding = self.embedder.get_embedding(query_text)
+        query_reduced = self.reducer.transform(query_embedding.reshape(1, -1))[0]
+        all_docs = self.storage.list_documents()
+        if not all_docs:
+            return []
+        X = (query_reduced[None, :] * self.storage.matrix()).astype(np.float32)
+        scores = self._predict(X)
+        return rank_results([d["doc_id"] for d in all_docs], scores, top_k, min_similarity)
+
+    def get_memory_stats(self) -> Dict[str, float]:
+        try:
+            import psutil
+            current = psutil.Process().memory_info().rss / 1024 / 1024
+        except Exception:
+            current = 0.0
+        return {'current_mb': current, 'max_mb': self.config.max_memory_mb,
+                'usage_percent': (current / self.config.max_memory_mb) * 100}
+
+
+def rank_results(doc_ids: List[str], scores: np.ndarray, top_k: int, min_similarity: float) -> List[Tuple[str, float]]:
+    """Threshold (>=), stable sort by similarity descending, first top_k (batch_operations.py:278-284)."""
+    similarities = [(doc_id, float(s)) for doc_id, s in zip(doc_ids, scores) if s >= min_similarity]
+    similarities.sort(key=lambda x: x[1], reverse=True)
+    return similarities[:top_k]

@@ -1,0 +1,91 @@
+"""compare / search / encrypt-batch on the GPU (fhe="execute") against the clear quantized model the
+reference CLI runs (batch_operations.py:233,276): identical scores, identical ranking."""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def processor(cuda_dev):
+    from fhe_icp_b200.batch_operations import BatchProcessor
+    bp = BatchProcessor(fhe="execute", seed=0)
+    topics = ["quantum", "cooking", "finance", "biology", "sailing"]
+    texts = [f"{topics[i % 5]} document number {i} about things" for i in range(203)]
+    bp.encrypt_documents(texts, [f"d{i}" for i in range(203)])
+    return bp
+
+
+def test_search_equals_clear_model_ranking(processor):
+    from fhe_icp_b200.batch_operations import rank_results
+    bp = processor
+    for query, k, thr in [("quantum entanglement", 3, 0.5), ("cooking dinner", 5, 0.5), ("sailing", 10, -1e9),
+                          ("unrelated words here", 5, 0.5)]:
+        got = bp.search_similar(query, top_k=k, min_similarity=thr)
+        q = bp.reducer.transform(bp.embedder.get_embedding(query).reshape(1, -1))[0]
+        clear = bp.fhe_model.model.predict((q[None, :] * bp.storage.matrix()).astype(np.float32))
+        assert got == rank_results([d["doc_id"] for d in bp.storage.list_documents()], clear, k, thr)
+    assert len(bp.search_similar("quantum entanglement", top_k=3)) == 3
+
+
+def test_compare_equals_clear_model(processor):
+    bp = processor
+    for a, b in [("d0", "d5"), ("d0", "d1"), ("d7", "d7")]:
+        X = (bp.storage.load(a).encrypted_embedding * bp.storage.load(b).encrypted_embedding).reshape(1, -1)
+        assert bp.compare_encrypted(a, b) == float(bp.fhe_model.model.predict(X)[0])
+    assert bp.compare_encrypted("d0", "d5") > 0.7 > bp.compare_encrypted("d0", "d1")
+    with pytest.raises(KeyError):
+        bp.compare_encrypted("d0", "nope")
+
+
+def test_no_model_raises_like_reference():
+    from fhe_icp_b200.batch_operations import BatchProcessor
+    bp = BatchProcessor(init_model=False)
+    for call in (lambda: bp.compare_encrypted("a", "b"), lambda: bp.search_similar("q"), lambda: bp.encrypt_documents(["t"])):
+        with pytest.raises(RuntimeError, match="No FHE model initialized"):
+            call()
+
+
+def test_cli_end_to_end(tmp_path, capsys, cuda_dev):
+    from fhe_icp_b200.fhe_cli import main
+    docs = [{"text": "quantum computing with qubits", "id": "q1", "metadata": {"tag": "physics"}},
+            {"text": "quantum error correction", "id": "q2"}, {"text": "cooking pasta recipes", "id": "c1"}, "cooking garlic"]
+    (tmp_path / "docs.json").write_text(json.dumps(docs))
+    sd = str(tmp_path / "store")
+    assert main(["--storage-dir", sd, "encrypt-batch", str(tmp_path / "docs.json"), "-o", str(tmp_path / "ids.json")]) == 0
+    assert json.loads((tmp_path / "ids.json").read_text())[:3] == ["q1", "q2", "c1"]
+    assert main(["--storage-dir", sd, "compare", "q1", "q2"]) == 0
+    out_exec = capsys.readouterr().out
+    assert "Similarity score:" in out_exec and "Interpretation: Very similar" in out_exec
+    assert main(["--storage-dir", sd, "--fhe", "disable", "compare", "q1", "q2"]) == 0
+    out_clear = capsys.readouterr().out
+    line = [l for l in out_exec.splitlines() if "Similarity score" in l]
+    assert line == [l for l in out_clear.splitlines() if "Similarity score" in l]
+    assert main(["--storage-dir", sd, "search", "quantum supremacy", "--top-k", "3"]) == 0
+    s = capsys.readouterr().out
+    assert "Found 2 similar documents" in s and "1. q" in s and "Metadata: {'tag': 'physics'}" in s
+
+
+def test_sharded_search_single_rank_on_gpu(processor):
+    from fhe_icp_b200.batch_operations import rank_results
+    from fhe_icp_b200.sharded_search import ShardedSearch
+    bp = processor
+    docs = bp.storage.matrix()
+    q = bp.embedder.get_embedding("finance markets")
+    ss = ShardedSearch(bp.fhe_model, docs, [d["doc_id"] for d in bp.storage.list_documents()])
+    got = ss.search(q, top_k=3, min_similarity=0.5)
+    clear = bp.fhe_model.model.predict((q[None, :] * docs).astype(np.float32))
+    assert got == rank_results(ss.doc_ids, clear, 3, 0.5) and len(got) == 3
+
+
+def test_large_batch_chunking_is_exact(cuda_dev):
+    """5000 rows > one 2 GiB ciphertext chunk: predict_host walks chunks, results stay exact."""
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=21, verbose=False)
+    X, _ = m.train(n_samples=500)
+    m.compile(X[:10])
+    rng = np.random.RandomState(1)
+    Xb = X[rng.randint(0, 500, size=5000)] * rng.uniform(0.5, 1.5, size=(5000, 1)).astype(np.float32)
+    assert np.array_equal(m.predict_encrypted(Xb), m.predict_clear(Xb))

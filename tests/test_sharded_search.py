@@ -1,0 +1,110 @@
+"""world_size-2 gloo tests (CPU) of the document-sharded search plumbing: shard bounds, the padded
+all-gather of encrypted scores, client-side decrypt + threshold + stable sort + top-k.  The engine
+behind the plumbing is the CPU oracle here (test infrastructure); on the GPU box the same class runs
+over FHESimilarityModel (tests/test_gpu_search.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+class OracleEngine:
+    """encrypt / run / decrypt of the compiled circuit on CPU tensors, via the oracle."""
+
+    def __init__(self, model, ct_base=0):
+        from oracle import oracle as O
+        self.O, self.m, self.c = O, model, model.model.fhe_circuit
+        self.s = O.secret_key(self.c.key_seed, 2, self.c.lwe.n)
+        self.ct_base = ct_base
+
+    def encrypt(self, X):
+        c, O = self.c, self.O
+        q = self.m.model.quantize_input(X)
+        ct = O.lwe_encrypt(self.s, q, c.lwe.shift, c.lwe.sigma_abs, c.enc_seed, ct_base=self.ct_base, stride=c.lwe.stride)
+        self.ct_base += q.size
+        return torch.from_numpy(ct.reshape(len(X), c.spec.d, -1).view(np.int64))
+
+    def run(self, ct):
+        c = self.c
+        W = np.stack([c.spec.q_weights, np.ones_like(c.spec.q_weights)]) if c.two_outputs else c.spec.q_weights[None]
+        return torch.from_numpy(self.O.lincomb(ct.numpy().view(np.uint64), W, c.lwe.n).view(np.int64))
+
+    def decrypt(self, enc):
+        c = self.c
+        m = self.O.lwe_decrypt(self.s, enc.numpy().view(np.uint64), c.lwe.shift)
+        qy = m[:, 0] - (int(c.spec.weight_q.zero_point) * m[:, 1] if c.two_outputs else 0) + int(c.spec.q_bias)
+        return c.spec.dequantize_output(qy)
+
+
+def _make_problem(n_docs):
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=3, verbose=False)
+    X, _ = m.train(n_samples=300)
+    m.compile(X[:10], bound_mode="inputset")
+    rng = np.random.RandomState(9)
+    q = rng.randn(128).astype(np.float32); q /= np.linalg.norm(q)
+    docs = rng.randn(n_docs, 128).astype(np.float32)
+    docs[::3] = q + 0.3 * rng.randn(len(docs[::3]), 128)
+    docs /= np.linalg.norm(docs, axis=1, keepdims=True)
+    return m, q, docs
+
+
+def _worker(rank, world, port, n_docs, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fhe_icp_b200.sharded_search import ShardedSearch, broadcast_public_material, shard_bounds
+        m, q, docs = _make_problem(n_docs)
+        spec = broadcast_public_material(m.model.spec.to_dict() if rank == 0 else None)
+        assert spec["q_weights"] == m.model.spec.to_dict()["q_weights"]
+        ss = ShardedSearch(OracleEngine(m, ct_base=rank << 40), docs)
+        assert (ss.lo, ss.hi) == shard_bounds(n_docs, world, rank)
+        res = ss.search(q, top_k=4, min_similarity=0.2)
+        if rank == 0:
+            ret["res"] = res
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_docs", [7, 2, 1])
+def test_sharded_search_world2_matches_single_process(n_docs):
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, n_docs, ret), nprocs=world, join=True)
+    from fhe_icp_b200.batch_operations import rank_results
+    m, q, docs = _make_problem(n_docs)
+    ref = rank_results([f"doc_{i}" for i in range(n_docs)], m.predict_clear(q[None, :] * docs), 4, 0.2)
+    assert ret["res"] == ref
+
+
+def test_shard_bounds_cover_everything():
+    from fhe_icp_b200.sharded_search import shard_bounds
+    for n in (0, 1, 5, 8, 1000, 1_000_003):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_rank_results_reference_semantics():
+    """Filter >=, stable sort descending, top-k (batch_operations.py:278-284): ties keep index order."""
+    from fhe_icp_b200.batch_operations import rank_results
+    ids = ["a", "b", "c", "d", "e"]
+    s = np.array([0.5, 0.9, 0.5, 0.49999, 0.9])
+    assert rank_results(ids, s, 5, 0.5) == [("b", 0.9), ("e", 0.9), ("a", 0.5), ("c", 0.5)]
+    assert rank_results(ids, s, 1, 0.5) == [("b", 0.9)]
+    assert rank_results(ids, s, 3, 2.0) == []
+    assert rank_results([], np.zeros(0), 3, 0.0) == []
