@@ -109,6 +109,8 @@ SIGNATURES = {
     "fhe_b200_lincomb": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _vp, C.c_int32,
                                    C.POINTER(C.c_int64), C.c_int32, _vp, _vp]),
     "fhe_b200_accumulate": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
+    "fhe_b200_lwe_modswitch32": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
+    "fhe_b200_similarity_decrypt32": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp]),
     "fhe_b200_ksk_gen": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_uint64, _vp, _vp]),
     "fhe_b200_bsk_gen": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_uint64, _vp, _vp]),
     "fhe_b200_ksk_words": (C.c_uint64, [C.POINTER(PBSParams)]),

@@ -229,6 +229,18 @@ int fhe_b200_lincomb(fhe_b200_ctx* ctx, const uint64_t* d_ct, int64_t B, int32_t
     return FHE_B200_OK;
 }
 
+int fhe_b200_lwe_modswitch32(fhe_b200_ctx* ctx, const uint64_t* d_ct, int64_t count, int64_t stride, uint32_t* d_ct32,
+                             void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(count >= 0 && stride > 0, "bad shape");
+    if (count == 0) return FHE_B200_OK;
+    REQUIRE(d_ct && d_ct32, "null device pointer");
+    REQUIRE(((uintptr_t)d_ct & 15) == 0 && ((uintptr_t)d_ct32 & 7) == 0, "buffers must be 16/8-byte aligned");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_modswitch32(d_ct, count * stride, d_ct32, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 int fhe_b200_accumulate(fhe_b200_ctx* ctx, uint64_t* d_acc, const uint64_t* d_x, int64_t words, void* stream) {
     REQUIRE(ctx, "null ctx");
     REQUIRE(words >= 0, "negative size");
@@ -400,6 +412,23 @@ int fhe_b200_similarity_decrypt(fhe_b200_similarity* s, const uint64_t* d_out, i
     cudaStream_t st = (cudaStream_t)stream;
     CU(s->m.reserve(sizeof(int64_t) * (size_t)B * s->M));
     CU(fhe::launch_lwe_phase(s->d_key, sp.n, sp.stride, d_out, B * s->M, sp.shift, true, (uint64_t*)s->m.p, st));
+    CU(fhe::launch_similarity_finalize((const int64_t*)s->m.p, B, s->M, sp.w_zero_point, sp.q_bias, sp.out_scale,
+                                       sp.out_zero_point, d_y, d_q_y, st));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_decrypt32(fhe_b200_similarity* s, const uint32_t* d_out32, int64_t B, double* d_y,
+                                  int64_t* d_q_y, void* stream) {
+    REQUIRE(s, "null model");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_out32 && (d_y || d_q_y), "null device pointer");
+    const auto& sp = s->spec;
+    REQUIRE(sp.shift >= 32, "the 32-bit wire form needs log2(Delta) >= 32");
+    CU(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(s->m.reserve(sizeof(int64_t) * (size_t)B * s->M));
+    CU(fhe::launch_lwe_decrypt32(s->d_key, sp.n, sp.stride, d_out32, B * s->M, sp.shift - 32, (int64_t*)s->m.p, st));
     CU(fhe::launch_similarity_finalize((const int64_t*)s->m.p, B, s->M, sp.w_zero_point, sp.q_bias, sp.out_scale,
                                        sp.out_zero_point, d_y, d_q_y, st));
     return FHE_B200_OK;

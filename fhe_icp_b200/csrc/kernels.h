@@ -18,6 +18,9 @@ cudaError_t launch_lwe_phase(const uint8_t* d_key, int n, int64_t stride, const 
 cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_t stride, const int64_t* d_W, int M,
                            bool second_is_sum, int64_t bias0, int64_t bias1, int shift, uint64_t* d_out,
                            cudaStream_t s);
+cudaError_t launch_lwe_modswitch32(const uint64_t* d_in, int64_t words, uint32_t* d_out, cudaStream_t s);
+cudaError_t launch_lwe_decrypt32(const uint8_t* d_key, int n, int64_t stride, const uint32_t* d_ct, int64_t count,
+                                 int shift32, int64_t* d_out, cudaStream_t s);
 cudaError_t launch_accumulate(uint64_t* d_acc, const uint64_t* d_x, int64_t words, cudaStream_t s);
 cudaError_t launch_quantize(const float* d_X, int64_t count, double scale, int64_t zp, int64_t qmin, int64_t qmax,
                             int64_t* d_q, cudaStream_t s);

@@ -208,6 +208,62 @@ cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_
     return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------- 32-bit wire form
+// Modulus switch 2^64 -> 2^32 of finished ciphertexts (scores on their way to the client): halves
+// the bytes that cross NVLink.  Added noise: sum_i s_i e_i with e_i uniform in +-2^-33 of the torus,
+// std ~ sqrt(n/24) * 2^-32 (2^-29 at n = 1423, against a decoding margin of 2^-23).
+__global__ void lwe_modswitch32_kernel(const uint64_t* __restrict__ in, int64_t words, uint32_t* __restrict__ out) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < words) {
+        u64x2 v = ld_stream_u64x2(in + i);
+        uint2 o;
+        o.x = (uint32_t)((v.x + 0x80000000ULL) >> 32);
+        o.y = (uint32_t)((v.y + 0x80000000ULL) >> 32);
+        *reinterpret_cast<uint2*>(out + i) = o;
+    } else if (i < words) {
+        out[i] = (uint32_t)((in[i] + 0x80000000ULL) >> 32);
+    }
+}
+
+cudaError_t launch_lwe_modswitch32(const uint64_t* d_in, int64_t words, uint32_t* d_out, cudaStream_t s) {
+    if (words <= 0) return cudaSuccess;
+    int64_t vecs = (words + 1) / 2;
+    lwe_modswitch32_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, s>>>(d_in, words, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// decrypt of 32-bit ciphertexts: m = (b - <a,s> + Delta32/2) >> shift32, arithmetic on 32 bits
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+lwe_decrypt32_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, const uint32_t* __restrict__ cts,
+                     int64_t count, int shift32, int64_t* __restrict__ out) {
+    extern __shared__ uint32_t skey[];
+    pack_key_bits(key, n, skey);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
+    if (c >= count) return;
+    const uint32_t* ct = cts + c * stride;
+    uint32_t dot = 0;
+    for (int w = lane; w < n; w += 32) dot += ct[w] & (0u - ((skey[w >> 5] >> (w & 31)) & 1u));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) {
+        uint32_t v = ct[n] - dot + (shift32 > 0 ? (1u << (shift32 - 1)) : 0u);
+        out[c] = (int64_t)((int32_t)v >> shift32);
+    }
+}
+
+cudaError_t launch_lwe_decrypt32(const uint8_t* d_key, int n, int64_t stride, const uint32_t* d_ct, int64_t count,
+                                 int shift32, int64_t* d_out, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
+    lwe_decrypt32_kernel<<<(unsigned)((count + DEC_WARPS - 1) / DEC_WARPS), DEC_WARPS * 32, smem, s>>>(
+        d_key, n, stride, d_ct, count, shift32, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ----------------------------------------------------------------------------- accumulation
 __global__ void accumulate_kernel(uint64_t* __restrict__ acc, const uint64_t* __restrict__ x, int64_t words) {
     int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;

@@ -13,6 +13,7 @@
 //     polynomial and level), exchanged through shared memory between two named barriers.
 // Roofline: FP64 pipe and shared-memory bandwidth bind (about 176 MFLOP per PBS at the stated
 // set); the 48.6 MB Fourier key is L2-resident, so HBM only sees it once per launch.
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -59,6 +60,36 @@ __device__ __forceinline__ uint64_t f64_to_torus(double x) {
     const double y = fma(-r, 0x1p64, x);
     return (uint64_t)__double2ll_rn(y);
 }
+
+// ------------------------------------------------------------------------------- tensor memory
+// TMEM (256 KB per SM, 128 lanes x 512 32-bit columns) is used here as LANE-PRIVATE storage for the
+// accumulator polynomials: lane j1 of a warp owns the 64 coefficients {j1 + 32*j2} U {+1024} of its
+// polynomial in both FFT directions, i.e. 128 columns of its own TMEM lane.  That takes the 16 KB
+// per polynomial out of shared memory (which then fits 4 ciphertexts = 8 warps per SM instead of
+// 2 = 4 warps) and moves the accumulator read-modify-write off the shared-memory pipe.
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 32 consecutive 32-bit columns of this thread's own TMEM lane <-> 32 registers
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 :
+                 : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------- key -> Fourier
 // One warp per key polynomial: u64 torus coefficients (as signed) -> 1024 complex bins,
@@ -331,6 +362,197 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
     }
 }
 
+// ------------------------------------------------------------------------------- blind rotation, TMEM accumulators
+// K = 1, L = 1.  Shared memory per CTA: tw 16 KB, BSK stage 64 KB, per ciphertext two 16 KB tiles
+// (+ a_tilde): 4 ciphertexts = 8 warps per SM.  The accumulators live in TMEM; a tile carries a
+// coefficient-ordered copy of its polynomial from the end of one CMux (ACC update) to the digit
+// extraction of the next, where the rotation X^a needs other lanes' coefficients.
+struct PbsTmemSmem {
+    static constexpr size_t tw_bytes = (size_t)PBS_M * 16;
+    static constexpr size_t stage_bytes = (size_t)4 * PBS_M * 16;
+    static constexpr size_t bar_bytes = 128;
+    static constexpr size_t head_bytes = tw_bytes + stage_bytes + bar_bytes;
+    static constexpr size_t tile_bytes = (size_t)2 * PBS_M * 16;
+    __host__ __device__ static size_t per_ct(int n) { return tile_bytes + (((size_t)(n + 1) * 2 + 127) & ~(size_t)127); }
+    static size_t total(int n, int nct) { return head_bytes + (size_t)nct * per_ct(n); }
+};
+
+template <int NCT>
+__global__ void __launch_bounds__(NCT * 64, 1)
+pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
+                const uint64_t* __restrict__ luts, const int32_t* __restrict__ lut_index,
+                const cplx* __restrict__ g_tw, uint64_t* __restrict__ out) {
+    using S = PbsTmemSmem;
+    constexpr int POLYS = 2;
+    constexpr uint32_t TMEM_COLS = NCT <= 2 ? 128 : 256;  // 128 columns per warp, two warps per lane quarter
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* tw = reinterpret_cast<cplx*>(smem_raw);
+    cplx* stage = reinterpret_cast<cplx*>(smem_raw + S::tw_bytes);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + S::tw_bytes + S::stage_bytes);
+    uint64_t* bar_empty = bar_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2);
+    for (int i = threadIdx.x; i < PBS_M; i += blockDim.x) tw[i] = g_tw[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_full, 1);
+        mbar_init(bar_empty, NCT * POLYS);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    // this warp's TMEM window: its lane quarter (warp % 4), columns (warp / 4) * 128 ..
+    const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+    constexpr uint32_t STAGE_BYTES = (uint32_t)S::stage_bytes;
+    constexpr size_t bsk_elems = (size_t)4 * PBS_M;
+
+    const int ctl = warp / POLYS, t = warp - ctl * POLYS;
+    const int64_t b = (int64_t)blockIdx.x * NCT + ctl;
+    unsigned char* base = smem_raw + S::head_bytes + (size_t)ctl * S::per_ct(n);
+    cplx* tile_all = reinterpret_cast<cplx*>(base);
+    uint16_t* a_tilde = reinterpret_cast<uint16_t*>(base + S::tile_bytes);
+    cplx* tile = tile_all + (size_t)t * PBS_M;
+    uint64_t* tacc_copy = reinterpret_cast<uint64_t*>(tile);  // coefficient-ordered ACC_t between CMuxes
+    const bool live = b < B;
+    const int bar_id = 1 + ctl, bar_n = POLYS * 32;
+
+    // ---- prologue: mod-switch the mask, ACC = X^(-b~) * (0, LUT) into TMEM and the tile
+    const uint64_t* ct = in + (size_t)(live ? b : 0) * (n + 1);
+    for (int i = t * 32 + lane; i <= n; i += POLYS * 32)
+        a_tilde[i] = (uint16_t)((((ct[i] >> 51) + 1) >> 1) & 4095);
+    named_bar_sync(bar_id, bar_n);
+    {
+        const uint64_t* lut = luts + (size_t)(lut_index && live ? lut_index[b] : 0) * PBS_N;
+        const int rot = (4096 - (int)a_tilde[n]) & 4095;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t r[32];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int x = lane + 32 * ((q & 1) * 16 + u) + (q >= 2 ? PBS_M : 0);
+                uint64_t v = 0;
+                if (t == 1) {
+                    const int src = (x - rot) & 4095;
+                    v = lut[src & 2047];
+                    if (src & 2048) v = 0 - v;
+                }
+                tacc_copy[x] = v;
+                r[2 * u] = (uint32_t)v;
+                r[2 * u + 1] = (uint32_t)(v >> 32);
+            }
+            tmem_st_x32(tacc + q * 32, r);
+        }
+        tmem_wait_st();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar_full, STAGE_BYTES);
+        tma_load_1d(stage, bskf, STAGE_BYTES, bar_full);
+    }
+
+    const uint64_t Bm = (1ULL << beta) - 1, half = 1ULL << (beta - 1);
+    const uint64_t rnd = 1ULL << (63 - beta);
+    double re[32], im[32];
+    for (int i = 0; i < n; ++i) {
+        const int at = a_tilde[i];
+        // ---- digits of (X^at - 1) * ACC_t from the coefficient-ordered copy
+#pragma unroll
+        for (int j2 = 0; j2 < 32; ++j2) {
+            const int x = lane + 32 * j2;
+            const int s0 = (x - at) & 4095, s1 = (x + PBS_M - at) & 4095;
+            uint64_t r0 = tacc_copy[s0 & 2047], r1 = tacc_copy[s1 & 2047];
+            if (s0 & 2048) r0 = 0 - r0;
+            if (s1 & 2048) r1 = 0 - r1;
+            const uint64_t d0 = r0 - tacc_copy[x], d1 = r1 - tacc_copy[x + PBS_M];
+            const uint64_t u0 = ((d0 + rnd) >> (64 - beta)) + half, u1 = ((d1 + rnd) >> (64 - beta)) + half;
+            re[j2] = (double)((int32_t)(u0 & Bm) - (int32_t)half);
+            im[j2] = (double)((int32_t)(u1 & Bm) - (int32_t)half);
+        }
+        __syncwarp();  // every lane has read the ACC copy before the tile becomes the transpose buffer
+        nfft::fwd_phase1(re, im, tw, tile, lane);
+        __syncwarp();
+        nfft::fwd_phase2(re, im, tile, lane);
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            cplx v;
+            v.x = re[p];
+            v.y = im[p];
+            tile[nfft::brev5(p) * 32 + lane] = v;
+        }
+        named_bar_sync(bar_id, bar_n);                 // (A) both polynomials' Fourier digits are visible
+        mbar_wait(bar_full, (uint32_t)(i & 1));        // BSK_i has landed in shared memory
+        {
+            const cplx* bown = stage + ((size_t)t * POLYS + t) * PBS_M;
+            const cplx* f = tile_all + (size_t)(1 - t) * PBS_M;
+            const cplx* bo = stage + ((size_t)(1 - t) * POLYS + t) * PBS_M;
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const int bin = nfft::brev5(p) * 32 + lane;
+                const cplx g = bown[bin], v = f[bin], h = bo[bin];
+                const double a = re[p], c = im[p];
+                re[p] = a * g.x - c * g.y + (v.x * h.x - v.y * h.y);
+                im[p] = a * g.y + c * g.x + (v.x * h.y + v.y * h.x);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty);         // this warp is done with BSK_i
+        named_bar_sync(bar_id, bar_n);                 // (B) nobody reads the published digits any more
+        nfft::inv_phase1(re, im, tw, tile, lane);
+        if (threadIdx.x == 0 && i + 1 < n) {
+            mbar_wait(bar_empty, (uint32_t)(i & 1));
+            mbar_expect_tx(bar_full, STAGE_BYTES);
+            tma_load_1d(stage, bskf + (size_t)(i + 1) * bsk_elems, STAGE_BYTES, bar_full);
+        }
+        __syncwarp();
+        nfft::inv_phase2(re, im, tile, lane);
+        __syncwarp();  // the tile is free again: it receives the updated accumulator
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t r[32];
+            tmem_ld_x32(tacc + q * 32, r);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int j2 = (q & 1) * 16 + u;
+                const uint64_t v = (((uint64_t)r[2 * u + 1] << 32) | r[2 * u]) + f64_to_torus(q < 2 ? re[j2] : im[j2]);
+                r[2 * u] = (uint32_t)v;
+                r[2 * u + 1] = (uint32_t)(v >> 32);
+                tacc_copy[lane + 32 * j2 + (q >= 2 ? PBS_M : 0)] = v;
+            }
+            tmem_st_x32(tacc + q * 32, r);
+        }
+        tmem_wait_st();
+        __syncwarp();
+    }
+    // ---- sample extract coefficient 0 from the coefficient-ordered copy
+    if (live) {
+        uint64_t* o = out + (size_t)b * ((size_t)PBS_N + 1);
+        if (t == 0) {
+            for (int x = lane; x < PBS_N; x += 32) o[x] = x == 0 ? tacc_copy[0] : 0 - tacc_copy[PBS_N - x];
+        } else if (lane == 0) {
+            o[PBS_N] = tacc_copy[0];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int NCT>
+static cudaError_t launch_pbs_tmem_t(const fhe_b200_pbs_params& p, const cplx* bskf, const uint64_t* d_in, int64_t B,
+                                     const uint64_t* d_luts, const int32_t* d_lut_index, const cplx* tw,
+                                     uint64_t* d_out, cudaStream_t s) {
+    const size_t smem = PbsTmemSmem::total(p.n, NCT);
+    cudaError_t e = cudaFuncSetAttribute(pbs_kernel_tmem<NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((B + NCT - 1) / NCT);
+    pbs_kernel_tmem<NCT><<<grid, NCT * 64, smem, s>>>(bskf, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tw, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why) {
     *why = "";
     if (p.N != PBS_N) { *why = "polynomial size N must be 2048"; return false; }
@@ -356,6 +578,12 @@ static cudaError_t launch_pbs_t(const fhe_b200_pbs_params& p, const cplx* bskf, 
     return cudaGetLastError();
 }
 
+// 0 = TMEM accumulators (default), 1 = shared-memory accumulators; FHE_B200_PBS_VARIANT overrides
+static int g_pbs_variant = [] {
+    const char* v = getenv("FHE_B200_PBS_VARIANT");
+    return v ? atoi(v) : 0;
+}();
+
 cudaError_t launch_pbs(const fhe_b200_pbs_params& p, const double* d_bskf, const uint64_t* d_in, int64_t B,
                        const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
                        cudaStream_t s) {
@@ -366,8 +594,12 @@ cudaError_t launch_pbs(const fhe_b200_pbs_params& p, const double* d_bskf, const
     const bool wide = B > (int64_t)sm_count;  // more ciphertexts than SMs: share the staged BSK_i inside a CTA
     switch (p.l_pbs) {
         case 1:
-            return wide ? launch_pbs_t<1, 1, 2>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s)
-                        : launch_pbs_t<1, 1, 1>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+            if (g_pbs_variant == 1)  // shared-memory accumulators (kept for A/B measurements)
+                return wide ? launch_pbs_t<1, 1, 2>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s)
+                            : launch_pbs_t<1, 1, 1>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+            if (B <= (int64_t)sm_count) return launch_pbs_tmem_t<1>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+            if (B <= 2 * (int64_t)sm_count) return launch_pbs_tmem_t<2>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+            return launch_pbs_tmem_t<4>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s);
         case 2:
             return launch_pbs_t<1, 2, 1>(p, bskf, d_in, B, d_luts, d_lut_index, tw, d_out, s);
         case 3:

@@ -185,6 +185,35 @@ class FHESimilarityModel:
         y_np = y.cpu().numpy()
         return (y_np, qy.cpu().numpy()) if return_q else y_np
 
+    def compress_scores(self, out, out32=None):
+        """Server: encrypted scores [B,M,stride] u64 -> 32-bit wire form [B,M,stride] (int32 view of u32)."""
+        import ctypes as C
+        import torch
+        from . import _native as N
+        c = self.keygen().model.fhe_circuit
+        if out32 is None:
+            out32 = torch.empty(out.shape, dtype=torch.int32, device=out.device)
+        st = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+        N.check(N.lib().fhe_b200_lwe_modswitch32(N.context(self.device).handle, C.c_void_p(out.data_ptr()),
+                                                 out.shape[0] * out.shape[1], c.lwe.stride, C.c_void_p(out32.data_ptr()), st))
+        return out32
+
+    def decrypt_compressed(self, out32, return_q: bool = False, to_host: bool = True):
+        """Client: scores in the 32-bit wire form -> float64 similarities."""
+        import ctypes as C
+        import torch
+        from . import _native as N
+        c = self.keygen().model.fhe_circuit
+        B = out32.shape[0]
+        y = torch.empty(B, dtype=torch.float64, device=out32.device)
+        qy = torch.empty(B, dtype=torch.int64, device=out32.device)
+        st = C.c_void_p(torch.cuda.current_stream(out32.device).cuda_stream)
+        N.check(N.lib().fhe_b200_similarity_decrypt32(c.handle, C.c_void_p(out32.data_ptr()), B,
+                                                      C.c_void_p(y.data_ptr()), C.c_void_p(qy.data_ptr()), st))
+        if not to_host:
+            return (y, qy) if return_q else y
+        return (y.cpu().numpy(), qy.cpu().numpy()) if return_q else y.cpu().numpy()
+
     # ---------------------------------------------------------------- misc (fhe_similarity.py:169-224)
     def _get_memory_usage(self) -> float:
         try:

@@ -114,6 +114,10 @@ int fhe_b200_lwe_decrypt(fhe_b200_ctx *ctx, const uint8_t *d_key, int32_t n, int
 int fhe_b200_lincomb(fhe_b200_ctx *ctx, const uint64_t *d_ct, int64_t B, int32_t d, int32_t n,
                      int64_t stride, const int64_t *d_W, int32_t M, const int64_t *h_bias,
                      int32_t shift, uint64_t *d_out, void *stream);
+/* 32-bit wire form of finished ciphertexts (modulus switch 2^64 -> 2^32, same row stride in words):
+ * halves the bytes gathered to the decrypting client; the added noise is stated in DESIGN.md. */
+int fhe_b200_lwe_modswitch32(fhe_b200_ctx *ctx, const uint64_t *d_ct, int64_t count, int64_t stride,
+                             uint32_t *d_ct32, void *stream);
 /* ciphertext accumulation: d_acc[i] += d_x[i] over `words` u64 words (wrapping) */
 int fhe_b200_accumulate(fhe_b200_ctx *ctx, uint64_t *d_acc, const uint64_t *d_x, int64_t words,
                         void *stream);
@@ -151,6 +155,9 @@ int fhe_b200_similarity_run(fhe_b200_similarity *sim, const uint64_t *d_ct, int6
                             uint64_t *d_out, void *stream);
 int fhe_b200_similarity_decrypt(fhe_b200_similarity *sim, const uint64_t *d_out, int64_t B,
                                 double *d_y, int64_t *d_q_y, void *stream);
+/* same, for scores received in the 32-bit wire form */
+int fhe_b200_similarity_decrypt32(fhe_b200_similarity *sim, const uint32_t *d_out32, int64_t B,
+                                  double *d_y, int64_t *d_q_y, void *stream);
 
 #ifdef __cplusplus
 }

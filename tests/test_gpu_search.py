@@ -89,3 +89,18 @@ def test_large_batch_chunking_is_exact(cuda_dev):
     rng = np.random.RandomState(1)
     Xb = X[rng.randint(0, 500, size=5000)] * rng.uniform(0.5, 1.5, size=(5000, 1)).astype(np.float32)
     assert np.array_equal(m.predict_encrypted(Xb), m.predict_clear(Xb))
+
+
+def test_32bit_wire_form_decrypts_identically(cuda_dev):
+    """Modulus-switched scores (2^64 -> 2^32, what crosses NVLink in the sharded search) decrypt to the
+    same integers; the extra noise (std ~2^-29) is far below the 2^-23 decoding margin."""
+    from fhe_icp_b200 import FHESimilarityModel
+    for dt in (np.float32, np.float64):
+        m = FHESimilarityModel(input_dim=128, n_bits=8, seed=5, verbose=False)
+        X, y = m._prepare_training_data(800)
+        m.train(X.astype(dt), y.astype(dt))
+        m.compile(X[:10])
+        out = m.run(m.encrypt(X))
+        y64, q64 = m.decrypt(out, return_q=True)
+        y32, q32 = m.decrypt_compressed(m.compress_scores(out), return_q=True)
+        assert np.array_equal(q64, q32) and np.array_equal(y64, y32) and np.array_equal(y64, m.predict_clear(X))
