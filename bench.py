@@ -226,7 +226,11 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL's stream (and the post stream below) run at high priority: the dot-product kernel keeps
+        # thousands of CTAs queued, and equal-priority kernels only start once those are all dispatched
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
     model, _ = build_model(device=local_rank)
     c = model.model.fhe_circuit
@@ -249,9 +253,10 @@ def run_b200_arm(args):
     # scores travel in the 32-bit wire form (modulus switch 2^64 -> 2^32) and only to the client rank:
     # at 8 GPUs the client's inbound NVLink would otherwise carry 160 MB per 0.22 ms step
     outs32 = [torch.empty(o.shape, dtype=torch.int32, device=dev) for o in outs] if world > 1 else None
+    allg = args.gather_mode == "all_gather"
     gathered = [torch.empty((world * B, M, c.lwe.stride), dtype=torch.int32, device=dev) for _ in outs] \
-        if (world > 1 and rank == 0) else None
-    post = torch.cuda.Stream(device=dev) if world > 1 else None
+        if (world > 1 and (rank == 0 or allg)) else None
+    post = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     done = [None, None]
 
     def step(i, ev=None):
@@ -272,7 +277,10 @@ def run_b200_arm(args):
         with torch.cuda.stream(post):
             post.wait_event(ready)
             model.compress_scores(outs[k], outs32[k])
-            dist.gather(outs32[k], list(gathered[k].chunk(world)) if rank == 0 else None, dst=0)
+            if allg:
+                dist.all_gather_into_tensor(gathered[k], outs32[k])
+            else:
+                dist.gather(outs32[k], list(gathered[k].chunk(world)) if rank == 0 else None, dst=0)
             if rank == 0:
                 _decrypt_device(model, gathered[k], wire32=True)   # client: decrypt every shard's scores
             done[k] = torch.cuda.Event()
@@ -399,6 +407,8 @@ def main():
     ap.add_argument("--docs", type=int, default=1000, help="documents per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-mode", default="all_gather", choices=["gather", "all_gather"],
+                    help="how encrypted scores reach the client rank (N>1)")
     ap.add_argument("--pbs-batch", type=int, default=0, help="PBS microbench batch (0 = default sweep)")
     args = ap.parse_args()
     if args.impl == "reference":
