@@ -91,9 +91,13 @@ FHE_HD constexpr int brev5(int v) {
     return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
 }
 
-// swizzled slot of element (row, col) of the 32x32 transpose tile of 16-byte elements:
-// a warp writing one row, or reading one column, touches every bank group exactly once.
-FHE_HD constexpr int slot(int row, int col) { return row * 32 + (col ^ row); }
+// slot of element (row, col) of the 32x32 transpose tile of 16-byte elements.  Rows are padded to
+// 33 elements: a warp writing one row or reading one column touches every bank group exactly once,
+// and -- unlike an XOR swizzle -- the address is base(lane) + compile-time offset, so the unrolled
+// code needs no per-element address registers (the XOR version spilled them, ncu r1_ncu_pbs_v3).
+constexpr int TILE_PITCH = 33;
+constexpr int TILE_ELEMS = 32 * TILE_PITCH;  // 1056 elements = 16,896 bytes
+FHE_HD constexpr int slot(int row, int col) { return row * TILE_PITCH + col; }
 
 // 32-point DFT, radix-2 decimation in frequency: natural-order input, frequency f ends at
 // register brev5(f).  SIGN=+1: exp(+2*pi*i*jf/32).
@@ -163,7 +167,7 @@ FHE_HD void dit32(double (&re)[32], double (&im)[32]) {
 
 // One 16 KB twiddle table serves both directions: tw[slot(k2, j1)] = W^(j1*k2) * omega^j1.
 // The forward pass reads row k2 across lanes j1, the inverse pass reads, per lane k2, the
-// conjugates along j1; the XOR swizzle makes both patterns bank-conflict free.
+// conjugates along j1; the row padding makes both patterns bank-conflict free.
 //
 // ---- forward: registers hold z[j2] = (c[j] + i*c[j+1024]) for j = lane + 32*j2 (the caller
 // has NOT applied any twist).  After phase 2 register brev5(k1) holds bin k = lane + 32*k1.

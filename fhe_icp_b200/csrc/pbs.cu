@@ -26,9 +26,10 @@ using nfft::cplx;
 
 constexpr int PBS_N = nfft::NPOLY;
 constexpr int PBS_M = nfft::M;
+constexpr int PBS_TILE = nfft::TILE_ELEMS;  // padded transpose tile / twiddle table, in complex elements
 
 // ------------------------------------------------------------------------------- twiddle tables
-static cplx* g_tw = nullptr;  // [1024] swizzled inter-pass twiddles (per device)
+static cplx* g_tw = nullptr;  // [PBS_TILE] row-padded inter-pass twiddles (per device)
 static int g_tw_device = -1;
 static std::mutex g_tw_mu;
 
@@ -38,7 +39,7 @@ static cudaError_t get_tables(const cplx** tw) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (g_tw == nullptr || g_tw_device != dev) {
-        static cplx h[PBS_M];
+        static cplx h[PBS_TILE];
         nfft::fill_twiddle_table(h);
         cplx* d = nullptr;
         if ((e = cudaMalloc(&d, sizeof(h))) != cudaSuccess) return e;
@@ -89,6 +90,20 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[
                  : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
                  : "memory");
 }
+// 16-column variants (8 u64 coefficients per call): smaller register footprint per chunk
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :
+                 : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------- key -> Fourier
@@ -101,13 +116,13 @@ bsk_to_fourier_kernel(const uint64_t* __restrict__ bsk, int64_t polys, const cpl
                       double* __restrict__ bskf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* twf = reinterpret_cast<cplx*>(smem_raw);
-    cplx* bufs = twf + PBS_M;
-    for (int i = threadIdx.x; i < PBS_M; i += blockDim.x) twf[i] = g_twf[i];
+    cplx* bufs = twf + PBS_TILE;
+    for (int i = threadIdx.x; i < PBS_TILE; i += blockDim.x) twf[i] = g_twf[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * B2F_WARPS + warp;
     if (q >= polys) return;
-    cplx* buf = bufs + warp * PBS_M;
+    cplx* buf = bufs + warp * PBS_TILE;
     const uint64_t* src = bsk + (size_t)q * PBS_N;
     double re[32], im[32];
 #pragma unroll
@@ -134,7 +149,7 @@ cudaError_t launch_bsk_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* 
     cudaError_t e = get_tables(&twf);
     if (e != cudaSuccess) return e;
     const int64_t polys = (int64_t)p.n * (p.k + 1) * p.l_pbs * (p.k + 1);
-    const size_t smem = sizeof(cplx) * PBS_M * (1 + B2F_WARPS);
+    const size_t smem = sizeof(cplx) * PBS_TILE * (1 + B2F_WARPS);
     e = cudaFuncSetAttribute(bsk_to_fourier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     bsk_to_fourier_kernel<<<(unsigned)((polys + B2F_WARPS - 1) / B2F_WARPS), B2F_WARPS * 32, smem, s>>>(
@@ -157,12 +172,12 @@ template <int K, int L>
 struct PbsSmem {
     static constexpr int POLYS = K + 1;
     static constexpr bool STAGE = (L == 1);
-    static constexpr size_t tw_bytes = (size_t)PBS_M * 16;
+    static constexpr size_t tw_bytes = (size_t)PBS_TILE * 16;
     static constexpr size_t stage_bytes = STAGE ? (size_t)POLYS * L * POLYS * PBS_M * 16 : 0;
     static constexpr size_t bar_bytes = 128;
     static constexpr size_t head_bytes = tw_bytes + stage_bytes + bar_bytes;
     static constexpr size_t acc_bytes = (size_t)POLYS * PBS_N * 8;
-    static constexpr size_t tile_bytes = (size_t)POLYS * PBS_M * 16;
+    static constexpr size_t tile_bytes = (size_t)POLYS * PBS_TILE * 16;
     static constexpr size_t f_bytes = L > 1 ? (size_t)POLYS * L * PBS_M * 16 : 0;
     __host__ __device__ static size_t per_ct(int n) {
         return acc_bytes + tile_bytes + f_bytes + (((size_t)(n + 1) * 2 + 127) & ~(size_t)127);
@@ -184,7 +199,7 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
     cplx* stage = reinterpret_cast<cplx*>(smem_raw + S::tw_bytes);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + S::tw_bytes + S::stage_bytes);
     uint64_t* bar_empty = bar_full + 1;
-    for (int i = threadIdx.x; i < PBS_M; i += blockDim.x) tw[i] = g_tw[i];
+    for (int i = threadIdx.x; i < PBS_TILE; i += blockDim.x) tw[i] = g_tw[i];
     if (STAGE && threadIdx.x == 0) {
         mbar_init(bar_full, 1);
         mbar_init(bar_empty, NCT * POLYS);
@@ -204,7 +219,7 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
     cplx* f_all = reinterpret_cast<cplx*>(base + S::acc_bytes + S::tile_bytes);
     uint16_t* a_tilde = reinterpret_cast<uint16_t*>(base + S::acc_bytes + S::tile_bytes + S::f_bytes);
     uint64_t* acc = acc_all + (size_t)t * PBS_N;
-    cplx* tile = tile_all + (size_t)t * PBS_M;
+    cplx* tile = tile_all + (size_t)t * PBS_TILE;
     const bool live = b < B;  // dead slots still take part in every barrier
     const int bar_id = 1 + ctl, bar_n = POLYS * 32;
 
@@ -302,7 +317,7 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
 #pragma unroll 1
             for (int tp = 0; tp < POLYS; ++tp) {
                 if (tp == t) continue;
-                const cplx* f = tile_all + (size_t)tp * PBS_M;
+                const cplx* f = tile_all + (size_t)tp * PBS_TILE;
                 const cplx* bo = bk + ((size_t)(tp * L) * POLYS + t) * PBS_M;
 #pragma unroll
                 for (int p = 0; p < 32; ++p) {
@@ -368,11 +383,11 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
 // coefficient-ordered copy of its polynomial from the end of one CMux (ACC update) to the digit
 // extraction of the next, where the rotation X^a needs other lanes' coefficients.
 struct PbsTmemSmem {
-    static constexpr size_t tw_bytes = (size_t)PBS_M * 16;
+    static constexpr size_t tw_bytes = (size_t)PBS_TILE * 16;
     static constexpr size_t stage_bytes = (size_t)4 * PBS_M * 16;
     static constexpr size_t bar_bytes = 128;
     static constexpr size_t head_bytes = tw_bytes + stage_bytes + bar_bytes;
-    static constexpr size_t tile_bytes = (size_t)2 * PBS_M * 16;
+    static constexpr size_t tile_bytes = (size_t)2 * PBS_TILE * 16;
     __host__ __device__ static size_t per_ct(int n) { return tile_bytes + (((size_t)(n + 1) * 2 + 127) & ~(size_t)127); }
     static size_t total(int n, int nct) { return head_bytes + (size_t)nct * per_ct(n); }
 };
@@ -391,7 +406,7 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + S::tw_bytes + S::stage_bytes);
     uint64_t* bar_empty = bar_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2);
-    for (int i = threadIdx.x; i < PBS_M; i += blockDim.x) tw[i] = g_tw[i];
+    for (int i = threadIdx.x; i < PBS_TILE; i += blockDim.x) tw[i] = g_tw[i];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(bar_full, 1);
@@ -413,7 +428,7 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
     unsigned char* base = smem_raw + S::head_bytes + (size_t)ctl * S::per_ct(n);
     cplx* tile_all = reinterpret_cast<cplx*>(base);
     uint16_t* a_tilde = reinterpret_cast<uint16_t*>(base + S::tile_bytes);
-    cplx* tile = tile_all + (size_t)t * PBS_M;
+    cplx* tile = tile_all + (size_t)t * PBS_TILE;
     uint64_t* tacc_copy = reinterpret_cast<uint64_t*>(tile);  // coefficient-ordered ACC_t between CMuxes
     const bool live = b < B;
     const int bar_id = 1 + ctl, bar_n = POLYS * 32;
@@ -427,11 +442,11 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
         const uint64_t* lut = luts + (size_t)(lut_index && live ? lut_index[b] : 0) * PBS_N;
         const int rot = (4096 - (int)a_tilde[n]) & 4095;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t r[32];
+        for (int q = 0; q < 8; ++q) {
+            uint32_t r[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int x = lane + 32 * ((q & 1) * 16 + u) + (q >= 2 ? PBS_M : 0);
+            for (int u = 0; u < 8; ++u) {
+                const int x = lane + 32 * ((q & 3) * 8 + u) + (q >= 4 ? PBS_M : 0);
                 uint64_t v = 0;
                 if (t == 1) {
                     const int src = (x - rot) & 4095;
@@ -442,7 +457,7 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
                 r[2 * u] = (uint32_t)v;
                 r[2 * u + 1] = (uint32_t)(v >> 32);
             }
-            tmem_st_x32(tacc + q * 32, r);
+            tmem_st_x16(tacc + q * 16, r);
         }
         tmem_wait_st();
     }
@@ -459,16 +474,27 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
         const int at = a_tilde[i];
         // ---- digits of (X^at - 1) * ACC_t from the coefficient-ordered copy
 #pragma unroll
-        for (int j2 = 0; j2 < 32; ++j2) {
-            const int x = lane + 32 * j2;
-            const int s0 = (x - at) & 4095, s1 = (x + PBS_M - at) & 4095;
-            uint64_t r0 = tacc_copy[s0 & 2047], r1 = tacc_copy[s1 & 2047];
-            if (s0 & 2048) r0 = 0 - r0;
-            if (s1 & 2048) r1 = 0 - r1;
-            const uint64_t d0 = r0 - tacc_copy[x], d1 = r1 - tacc_copy[x + PBS_M];
-            const uint64_t u0 = ((d0 + rnd) >> (64 - beta)) + half, u1 = ((d1 + rnd) >> (64 - beta)) + half;
-            re[j2] = (double)((int32_t)(u0 & Bm) - (int32_t)half);
-            im[j2] = (double)((int32_t)(u1 & Bm) - (int32_t)half);
+        for (int c8 = 0; c8 < 4; ++c8) {
+            // own (unrotated) coefficients come from this lane's TMEM columns, the rotated ones from
+            // the coefficient-ordered copy in the tile
+            uint32_t lo[16], hi[16];
+            tmem_ld_x16(tacc + c8 * 16, lo);
+            tmem_ld_x16(tacc + 64 + c8 * 16, hi);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j2 = c8 * 8 + u;
+                const int x = lane + 32 * j2;
+                const int s0 = (x - at) & 4095, s1 = (x + PBS_M - at) & 4095;
+                uint64_t r0 = tacc_copy[s0 & 2047], r1 = tacc_copy[s1 & 2047];
+                if (s0 & 2048) r0 = 0 - r0;
+                if (s1 & 2048) r1 = 0 - r1;
+                const uint64_t own0 = ((uint64_t)lo[2 * u + 1] << 32) | lo[2 * u];
+                const uint64_t own1 = ((uint64_t)hi[2 * u + 1] << 32) | hi[2 * u];
+                const uint64_t d0 = r0 - own0, d1 = r1 - own1;
+                const uint64_t u0 = ((d0 + rnd) >> (64 - beta)) + half, u1 = ((d1 + rnd) >> (64 - beta)) + half;
+                re[j2] = (double)((int32_t)(u0 & Bm) - (int32_t)half);
+                im[j2] = (double)((int32_t)(u1 & Bm) - (int32_t)half);
+            }
         }
         __syncwarp();  // every lane has read the ACC copy before the tile becomes the transpose buffer
         nfft::fwd_phase1(re, im, tw, tile, lane);
@@ -486,15 +512,21 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
         mbar_wait(bar_full, (uint32_t)(i & 1));        // BSK_i has landed in shared memory
         {
             const cplx* bown = stage + ((size_t)t * POLYS + t) * PBS_M;
-            const cplx* f = tile_all + (size_t)(1 - t) * PBS_M;
+            const cplx* f = tile_all + (size_t)(1 - t) * PBS_TILE;
             const cplx* bo = stage + ((size_t)(1 - t) * POLYS + t) * PBS_M;
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
-                const int bin = nfft::brev5(p) * 32 + lane;
-                const cplx g = bown[bin], v = f[bin], h = bo[bin];
+                const cplx g = bown[nfft::brev5(p) * 32 + lane];
                 const double a = re[p], c = im[p];
-                re[p] = a * g.x - c * g.y + (v.x * h.x - v.y * h.y);
-                im[p] = a * g.y + c * g.x + (v.x * h.y + v.y * h.x);
+                re[p] = a * g.x - c * g.y;
+                im[p] = a * g.y + c * g.x;
+            }
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const cplx v = f[nfft::brev5(p) * 32 + lane];
+                const cplx h = bo[nfft::brev5(p) * 32 + lane];
+                re[p] += v.x * h.x - v.y * h.y;
+                im[p] += v.x * h.y + v.y * h.x;
             }
         }
         __syncwarp();
@@ -510,18 +542,18 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
         nfft::inv_phase2(re, im, tile, lane);
         __syncwarp();  // the tile is free again: it receives the updated accumulator
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t r[32];
-            tmem_ld_x32(tacc + q * 32, r);
+        for (int q = 0; q < 8; ++q) {
+            uint32_t r[16];
+            tmem_ld_x16(tacc + q * 16, r);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int j2 = (q & 1) * 16 + u;
-                const uint64_t v = (((uint64_t)r[2 * u + 1] << 32) | r[2 * u]) + f64_to_torus(q < 2 ? re[j2] : im[j2]);
+            for (int u = 0; u < 8; ++u) {
+                const int j2 = (q & 3) * 8 + u;
+                const uint64_t v = (((uint64_t)r[2 * u + 1] << 32) | r[2 * u]) + f64_to_torus(q < 4 ? re[j2] : im[j2]);
                 r[2 * u] = (uint32_t)v;
                 r[2 * u + 1] = (uint32_t)(v >> 32);
-                tacc_copy[lane + 32 * j2 + (q >= 2 ? PBS_M : 0)] = v;
+                tacc_copy[lane + 32 * j2 + (q >= 4 ? PBS_M : 0)] = v;
             }
-            tmem_st_x32(tacc + q * 32, r);
+            tmem_st_x16(tacc + q * 16, r);
         }
         tmem_wait_st();
         __syncwarp();

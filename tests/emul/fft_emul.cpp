@@ -7,7 +7,7 @@ using namespace fhe::nfft;
 extern "C" {
 // coef: 2048 doubles -> bins: 1024 complex (re,im interleaved), natural order
 void emul_forward(const double* coef, double* bins) {
-    std::vector<cplx> tw(1024), buf(1024);
+    std::vector<cplx> tw(TILE_ELEMS), buf(TILE_ELEMS);
     fill_twiddle_table(tw.data());
     static double re[32][32], im[32][32];
     for (int lane = 0; lane < 32; ++lane) {
@@ -23,7 +23,7 @@ void emul_forward(const double* coef, double* bins) {
     }
 }
 void emul_inverse(const double* bins, double* coef) {
-    std::vector<cplx> tw(1024), buf(1024);
+    std::vector<cplx> tw(TILE_ELEMS), buf(TILE_ELEMS);
     fill_twiddle_table(tw.data());
     static double re[32][32], im[32][32];
     for (int lane = 0; lane < 32; ++lane) {
