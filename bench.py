@@ -64,9 +64,10 @@ def synthetic_docs(n_docs: int, seed: int):
 
 def top_k(scores: np.ndarray, k: int, min_similarity: float):
     """Reference semantics (batch_operations.py:278-284): filter >=, stable sort descending, [:k]."""
-    sims = [(i, float(s)) for i, s in enumerate(scores) if s >= min_similarity]
-    sims.sort(key=lambda x: x[1], reverse=True)
-    return sims[:k]
+    scores = np.asarray(scores, dtype=np.float64)
+    keep = np.flatnonzero(scores >= min_similarity)
+    order = keep[np.argsort(-scores[keep], kind="stable")][:k]   # == stable sort with reverse=True
+    return [(int(i), float(scores[i])) for i in order]
 
 
 class ClockSampler:

@@ -223,6 +223,8 @@ class BatchProcessor:
 
 def rank_results(doc_ids: List[str], scores: np.ndarray, top_k: int, min_similarity: float) -> List[Tuple[str, float]]:
     """Threshold (>=), stable sort by similarity descending, first top_k (batch_operations.py:278-284)."""
-    similarities = [(doc_id, float(s)) for doc_id, s in zip(doc_ids, scores) if s >= min_similarity]
-    similarities.sort(key=lambda x: x[1], reverse=True)
-    return similarities[:top_k]
+    scores = np.asarray(scores, dtype=np.float64)
+    keep = np.flatnonzero(scores >= min_similarity)
+    # stable sort on the negated scores == Python's stable sort with reverse=True: ties keep index order
+    order = keep[np.argsort(-scores[keep], kind="stable")][:max(int(top_k), 0)]
+    return [(doc_ids[i], float(scores[i])) for i in order]
