@@ -180,13 +180,20 @@ FHE_HD void fwd_phase1(double (&re)[32], double (&im)[32], const cplx* tw, cplx*
         im[j2] = a * ci + b * cr;
     }
     dif32<+1>(re, im);
+    // twiddle loads run PF elements ahead of their use (explicit software prefetch: with one or two
+    // warps per scheduler the shared-memory latency is otherwise exposed at every multiply)
+    constexpr int PF = 4;
+    cplx w[PF];
+#pragma unroll
+    for (int p = 0; p < PF; ++p) w[p] = tw[slot(brev5(p), lane)];
 #pragma unroll
     for (int p = 0; p < 32; ++p) {
         const int k2 = brev5(p);
-        const cplx w = tw[slot(k2, lane)];
+        const cplx wc = w[p % PF];
+        if (p + PF < 32) w[p % PF] = tw[slot(brev5(p + PF), lane)];
         cplx v;
-        v.x = re[p] * w.x - im[p] * w.y;
-        v.y = re[p] * w.y + im[p] * w.x;
+        v.x = re[p] * wc.x - im[p] * wc.y;
+        v.y = re[p] * wc.y + im[p] * wc.x;
         buf[slot(k2, lane)] = v;
     }
 }
@@ -204,12 +211,17 @@ FHE_HD void fwd_phase2(double (&re)[32], double (&im)[32], const cplx* buf, int 
 // (c[j] + i*c[j+1024]) for j = lane + 32*j2, fully untwisted and scaled by 1/1024.
 FHE_HD void inv_phase1(double (&re)[32], double (&im)[32], const cplx* tw, cplx* buf, int lane) {
     dit32<-1>(re, im);
+    constexpr int PF = 4;
+    cplx w[PF];
+#pragma unroll
+    for (int j1 = 0; j1 < PF; ++j1) w[j1] = tw[slot(lane, j1)];
 #pragma unroll
     for (int j1 = 0; j1 < 32; ++j1) {
-        const cplx w = tw[slot(lane, j1)];  // multiply by conj(w)
+        const cplx wc = w[j1 % PF];  // multiply by conj(w)
+        if (j1 + PF < 32) w[j1 % PF] = tw[slot(lane, j1 + PF)];
         cplx v;
-        v.x = re[j1] * w.x + im[j1] * w.y;
-        v.y = im[j1] * w.x - re[j1] * w.y;
+        v.x = re[j1] * wc.x + im[j1] * wc.y;
+        v.y = im[j1] * wc.x - re[j1] * wc.y;
         buf[slot(j1, lane)] = v;
     }
 }

@@ -514,19 +514,23 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
             const cplx* bown = stage + ((size_t)t * POLYS + t) * PBS_M;
             const cplx* f = tile_all + (size_t)(1 - t) * PBS_TILE;
             const cplx* bo = stage + ((size_t)(1 - t) * POLYS + t) * PBS_M;
+            constexpr int PF = 4;
+            cplx g[PF], v[PF], h[PF];
 #pragma unroll
-            for (int p = 0; p < 32; ++p) {
-                const cplx g = bown[nfft::brev5(p) * 32 + lane];
-                const double a = re[p], c = im[p];
-                re[p] = a * g.x - c * g.y;
-                im[p] = a * g.y + c * g.x;
+            for (int p = 0; p < PF; ++p) {
+                const int bin = nfft::brev5(p) * 32 + lane;
+                g[p] = bown[bin]; v[p] = f[bin]; h[p] = bo[bin];
             }
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
-                const cplx v = f[nfft::brev5(p) * 32 + lane];
-                const cplx h = bo[nfft::brev5(p) * 32 + lane];
-                re[p] += v.x * h.x - v.y * h.y;
-                im[p] += v.x * h.y + v.y * h.x;
+                const cplx gc = g[p % PF], vc = v[p % PF], hc = h[p % PF];
+                if (p + PF < 32) {
+                    const int bin = nfft::brev5(p + PF) * 32 + lane;
+                    g[p % PF] = bown[bin]; v[p % PF] = f[bin]; h[p % PF] = bo[bin];
+                }
+                const double a = re[p], c = im[p];
+                re[p] = a * gc.x - c * gc.y + (vc.x * hc.x - vc.y * hc.y);
+                im[p] = a * gc.y + c * gc.x + (vc.x * hc.y + vc.y * hc.x);
             }
         }
         __syncwarp();
