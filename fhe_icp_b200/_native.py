@@ -117,6 +117,8 @@ SIGNATURES = {
     "fhe_b200_bsk_words": (C.c_uint64, [C.POINTER(PBSParams)]),
     "fhe_b200_bsk_to_fourier": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, _vp]),
     "fhe_b200_keyswitch": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp]),
+    "fhe_b200_ksk_to_32": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, _vp]),
+    "fhe_b200_keyswitch32": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp]),
     "fhe_b200_pbs": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "fhe_b200_similarity_create": (C.c_int, [_vp, C.POINTER(SimilaritySpec), C.POINTER(C.c_int64), C.POINTER(_vp)]),
     "fhe_b200_similarity_destroy": (C.c_int, [_vp]),
@@ -132,7 +134,7 @@ def lib() -> C.CDLL:
     """Load libfhe_b200.so (building it if the sources are newer).  Raises if unavailable."""
     global _LIB
     if _LIB is None:
-        so = build()
+        so = os.environ.get("FHE_B200_LIB") or build()   # FHE_B200_LIB: A/B-test an alternative build
         L = C.CDLL(str(so))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol

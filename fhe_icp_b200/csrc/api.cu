@@ -306,6 +306,27 @@ int fhe_b200_keyswitch(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const ui
     return FHE_B200_OK;
 }
 
+int fhe_b200_ksk_to_32(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint64_t* d_ksk, uint32_t* d_ksk32,
+                       void* stream) {
+    REQUIRE(ctx && d_ksk && d_ksk32, "null argument");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_ksk_to_32(*p, d_ksk, d_ksk32, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_keyswitch32(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint32_t* d_ksk32, const uint64_t* d_in,
+                         int64_t B, uint32_t* d_scratch32, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_ksk32 && d_in && d_scratch32 && d_out, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_keyswitch32(*p, d_ksk32, d_in, B, d_scratch32, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 int fhe_b200_pbs(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_bskf, const uint64_t* d_in,
                  int64_t B, const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, void* stream) {
     REQUIRE(ctx, "null ctx");

@@ -25,6 +25,10 @@
 #define FHE_HD inline
 #endif
 
+#ifndef FHE_FFT_PREFETCH
+#define FHE_FFT_PREFETCH 4  // twiddle loads run this many elements ahead of their use
+#endif
+
 namespace fhe {
 namespace nfft {
 
@@ -182,7 +186,7 @@ FHE_HD void fwd_phase1(double (&re)[32], double (&im)[32], const cplx* tw, cplx*
     dif32<+1>(re, im);
     // twiddle loads run PF elements ahead of their use (explicit software prefetch: with one or two
     // warps per scheduler the shared-memory latency is otherwise exposed at every multiply)
-    constexpr int PF = 4;
+    constexpr int PF = FHE_FFT_PREFETCH;
     cplx w[PF];
 #pragma unroll
     for (int p = 0; p < PF; ++p) w[p] = tw[slot(brev5(p), lane)];
@@ -211,7 +215,7 @@ FHE_HD void fwd_phase2(double (&re)[32], double (&im)[32], const cplx* buf, int 
 // (c[j] + i*c[j+1024]) for j = lane + 32*j2, fully untwisted and scaled by 1/1024.
 FHE_HD void inv_phase1(double (&re)[32], double (&im)[32], const cplx* tw, cplx* buf, int lane) {
     dit32<-1>(re, im);
-    constexpr int PF = 4;
+    constexpr int PF = FHE_FFT_PREFETCH;
     cplx w[PF];
 #pragma unroll
     for (int j1 = 0; j1 < PF; ++j1) w[j1] = tw[slot(lane, j1)];

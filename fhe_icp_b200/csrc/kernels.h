@@ -38,6 +38,10 @@ cudaError_t launch_bsk_gen(const fhe_b200_pbs_params& p, const uint8_t* d_s_smal
 cudaError_t launch_keyswitch(const fhe_b200_pbs_params& p, const uint64_t* d_ksk, const uint64_t* d_in, int64_t B,
                              uint64_t* d_out, cudaStream_t s);
 
+cudaError_t launch_ksk_to_32(const fhe_b200_pbs_params& p, const uint64_t* d_ksk, uint32_t* d_ksk32, cudaStream_t s);
+cudaError_t launch_keyswitch32(const fhe_b200_pbs_params& p, const uint32_t* d_ksk32, const uint64_t* d_in, int64_t B,
+                               uint32_t* d_acc32, uint64_t* d_out, cudaStream_t s);
+
 // pbs.cu
 cudaError_t launch_bsk_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* d_bsk, double* d_bskf,
                                   cudaStream_t s);

@@ -23,16 +23,22 @@ __global__ void ks_init_kernel(const uint64_t* __restrict__ in, int64_t B, int64
     out[i] = (w == n) ? in[b * (kN + 1) + kN] : 0;
 }
 
+__device__ __forceinline__ void ks_atomic_add(uint64_t* p, uint64_t v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+__device__ __forceinline__ void ks_atomic_add(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
+
+template <typename W>
 __global__ void __launch_bounds__(KS_COLS)
-keyswitch_kernel(const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ in, int64_t B, int64_t kN, int n,
-                 int l, int beta, int j_per_split, uint64_t* __restrict__ out) {
+keyswitch_kernel(const W* __restrict__ ksk, const uint64_t* __restrict__ in, int64_t B, int64_t kN, int n,
+                 int l, int beta, int j_per_split, W* __restrict__ out) {
     __shared__ int32_t dig[KS_JC][KS_MAXL][KS_TB];
     const int col = blockIdx.x * KS_COLS + threadIdx.x;
     const int64_t b0 = (int64_t)blockIdx.y * KS_TB;
     const int64_t j0 = (int64_t)blockIdx.z * j_per_split;
     const int64_t j1 = min(j0 + (int64_t)j_per_split, kN);
     const int nb = (int)min((int64_t)KS_TB, B - b0);
-    uint64_t acc[KS_TB];
+    W acc[KS_TB];
 #pragma unroll
     for (int t = 0; t < KS_TB; ++t) acc[t] = 0;
     const int tot = l * beta;
@@ -56,19 +62,18 @@ keyswitch_kernel(const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ 
         if (col <= n) {
             const int jn = (int)min((int64_t)KS_JC, j1 - jc);
             for (int jj = 0; jj < jn; ++jj) {
-                const uint64_t* kr = ksk + ((size_t)(jc + jj) * l) * (n + 1) + col;
+                const W* kr = ksk + ((size_t)(jc + jj) * l) * (n + 1) + col;
                 for (int lev = 0; lev < l; ++lev) {
-                    const uint64_t kv = kr[(size_t)lev * (n + 1)];
+                    const W kv = kr[(size_t)lev * (n + 1)];
 #pragma unroll
-                    for (int t = 0; t < KS_TB; ++t) acc[t] -= (uint64_t)(int64_t)dig[jj][lev][t] * kv;
+                    for (int t = 0; t < KS_TB; ++t) acc[t] -= (W)(int64_t)dig[jj][lev][t] * kv;
                 }
             }
         }
     }
     if (col <= n) {
         for (int t = 0; t < nb; ++t)
-            if (acc[t]) atomicAdd(reinterpret_cast<unsigned long long*>(out + (b0 + t) * (n + 1) + col),
-                                  (unsigned long long)acc[t]);
+            if (acc[t]) ks_atomic_add(out + (b0 + t) * (n + 1) + col, acc[t]);
     }
 }
 
@@ -87,7 +92,56 @@ cudaError_t launch_keyswitch(const fhe_b200_pbs_params& p, const uint64_t* d_ksk
     while (splits < 64 && (int64_t)col_tiles * b_tiles * splits < 600 && (kN / (splits * 2)) >= KS_JC) splits *= 2;
     const int j_per_split = (int)((kN + splits - 1) / splits);
     dim3 grid(col_tiles, (unsigned)b_tiles, splits);
-    keyswitch_kernel<<<grid, KS_COLS, 0, s>>>(d_ksk, d_in, B, kN, p.n, p.l_ks, p.beta_ks, j_per_split, d_out);
+    keyswitch_kernel<uint64_t><<<grid, KS_COLS, 0, s>>>(d_ksk, d_in, B, kN, p.n, p.l_ks, p.beta_ks, j_per_split, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---- 32-bit keyswitch ("KS32"): key and accumulation on the top 32 bits of the torus.  The output
+// only has to be accurate to the small key's noise (2^-17 at the stated set); rounding the key to
+// 32 bits adds ~2^-26.  One IMAD per MAC instead of three, half the key bytes.
+__global__ void ksk_to_32_kernel(const uint64_t* __restrict__ ksk, int64_t words, uint32_t* __restrict__ ksk32) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < words) ksk32[i] = (uint32_t)((ksk[i] + 0x80000000ULL) >> 32);
+}
+
+cudaError_t launch_ksk_to_32(const fhe_b200_pbs_params& p, const uint64_t* d_ksk, uint32_t* d_ksk32, cudaStream_t s) {
+    const int64_t words = (int64_t)p.k * p.N * p.l_ks * (p.n + 1);
+    ksk_to_32_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(d_ksk, words, d_ksk32);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void ks32_init_kernel(const uint64_t* __restrict__ in, int64_t B, int64_t kN, int n, uint32_t* __restrict__ acc) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * (n + 1)) return;
+    int64_t b = i / (n + 1);
+    int w = (int)(i - b * (n + 1));
+    acc[i] = (w == n) ? (uint32_t)((in[b * (kN + 1) + kN] + 0x80000000ULL) >> 32) : 0u;
+}
+
+__global__ void ks32_widen_kernel(const uint32_t* __restrict__ acc, int64_t words, uint64_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < words) out[i] = (uint64_t)acc[i] << 32;
+}
+
+cudaError_t launch_keyswitch32(const fhe_b200_pbs_params& p, const uint32_t* d_ksk32, const uint64_t* d_in, int64_t B,
+                               uint32_t* d_acc32, uint64_t* d_out, cudaStream_t s) {
+    if (p.l_ks > KS_MAXL || p.l_ks * p.beta_ks > 62) return cudaErrorInvalidValue;
+    const int64_t kN = (int64_t)p.k * p.N;
+    const int64_t tot = B * (p.n + 1);
+    ks32_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_in, B, kN, p.n, d_acc32);
+    count_launch();
+    const int col_tiles = (p.n + 1 + KS_COLS - 1) / KS_COLS;
+    const int64_t b_tiles = (B + KS_TB - 1) / KS_TB;
+    if (b_tiles > 65535) return cudaErrorInvalidValue;
+    int splits = 1;
+    while (splits < 64 && (int64_t)col_tiles * b_tiles * splits < 600 && (kN / (splits * 2)) >= KS_JC) splits *= 2;
+    const int j_per_split = (int)((kN + splits - 1) / splits);
+    dim3 grid(col_tiles, (unsigned)b_tiles, splits);
+    keyswitch_kernel<uint32_t><<<grid, KS_COLS, 0, s>>>(d_ksk32, d_in, B, kN, p.n, p.l_ks, p.beta_ks, j_per_split, d_acc32);
+    count_launch();
+    ks32_widen_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_acc32, tot, d_out);
     count_launch();
     return cudaGetLastError();
 }

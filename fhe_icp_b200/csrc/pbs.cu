@@ -26,6 +26,9 @@ using nfft::cplx;
 
 constexpr int PBS_N = nfft::NPOLY;
 constexpr int PBS_M = nfft::M;
+#ifndef PBS_PREFETCH
+#define PBS_PREFETCH 4
+#endif
 constexpr int PBS_TILE = nfft::TILE_ELEMS;  // padded transpose tile / twiddle table, in complex elements
 
 // ------------------------------------------------------------------------------- twiddle tables
@@ -114,7 +117,7 @@ constexpr int B2F_WARPS = 4;
 __global__ void __launch_bounds__(B2F_WARPS * 32)
 bsk_to_fourier_kernel(const uint64_t* __restrict__ bsk, int64_t polys, const cplx* __restrict__ g_twf,
                       double* __restrict__ bskf) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* twf = reinterpret_cast<cplx*>(smem_raw);
     cplx* bufs = twf + PBS_TILE;
     for (int i = threadIdx.x; i < PBS_TILE; i += blockDim.x) twf[i] = g_twf[i];
@@ -193,7 +196,6 @@ pbs_kernel(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, int64
     using S = PbsSmem<K, L>;
     constexpr int POLYS = K + 1;
     constexpr bool STAGE = S::STAGE;
-    constexpr int WORKERS = NCT * POLYS * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
     cplx* stage = reinterpret_cast<cplx*>(smem_raw + S::tw_bytes);
@@ -480,12 +482,20 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
             uint32_t lo[16], hi[16];
             tmem_ld_x16(tacc + c8 * 16, lo);
             tmem_ld_x16(tacc + 64 + c8 * 16, hi);
+            uint64_t rot0[8], rot1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {  // all rotated loads of the chunk first, then the arithmetic
+                const int x = lane + 32 * (c8 * 8 + u);
+                const int s0 = (x - at) & 4095, s1 = (x + PBS_M - at) & 4095;
+                rot0[u] = tacc_copy[s0 & 2047];
+                rot1[u] = tacc_copy[s1 & 2047];
+            }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int j2 = c8 * 8 + u;
                 const int x = lane + 32 * j2;
                 const int s0 = (x - at) & 4095, s1 = (x + PBS_M - at) & 4095;
-                uint64_t r0 = tacc_copy[s0 & 2047], r1 = tacc_copy[s1 & 2047];
+                uint64_t r0 = rot0[u], r1 = rot1[u];
                 if (s0 & 2048) r0 = 0 - r0;
                 if (s1 & 2048) r1 = 0 - r1;
                 const uint64_t own0 = ((uint64_t)lo[2 * u + 1] << 32) | lo[2 * u];
@@ -514,7 +524,7 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
             const cplx* bown = stage + ((size_t)t * POLYS + t) * PBS_M;
             const cplx* f = tile_all + (size_t)(1 - t) * PBS_TILE;
             const cplx* bo = stage + ((size_t)(1 - t) * POLYS + t) * PBS_M;
-            constexpr int PF = 4;
+            constexpr int PF = PBS_PREFETCH;
             cplx g[PF], v[PF], h[PF];
 #pragma unroll
             for (int p = 0; p < PF; ++p) {

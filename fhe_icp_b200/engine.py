@@ -152,6 +152,26 @@ def keyswitch(p: N.PBSParams, ksk: torch.Tensor, ct: torch.Tensor) -> torch.Tens
     return out
 
 
+def ksk_to_32(p: N.PBSParams, ksk: torch.Tensor) -> torch.Tensor:
+    """Round the keyswitching key to its top 32 torus bits (int32 view of u32)."""
+    ksk32 = torch.empty(ksk.shape, dtype=torch.int32, device=ksk.device)
+    N.check(N.lib().fhe_b200_ksk_to_32(_ctx(ksk.device).handle, C.byref(p), _ptr(ksk), _ptr(ksk32), _stream(ksk.device)))
+    return ksk32
+
+
+def keyswitch32(p: N.PBSParams, ksk32: torch.Tensor, ct: torch.Tensor) -> torch.Tensor:
+    """32-bit keyswitch: same interface as :func:`keyswitch`, ~3x fewer integer operations."""
+    dev = ct.device
+    ct = ct.contiguous()
+    B = ct.shape[0]
+    assert ct.shape[1] == p.k * p.N + 1
+    scratch = torch.empty((B, p.n + 1), dtype=torch.int32, device=dev)
+    out = torch.empty((B, p.n + 1), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_keyswitch32(_ctx(dev).handle, C.byref(p), _ptr(ksk32), _ptr(ct), B, _ptr(scratch),
+                                         _ptr(out), _stream(dev)))
+    return out
+
+
 def pbs(p: N.PBSParams, bskf: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor,
         lut_index: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     dev = ct.device

@@ -134,6 +134,13 @@ int fhe_b200_bsk_to_fourier(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p,
                             const uint64_t *d_bsk, double *d_bskf, void *stream);
 int fhe_b200_keyswitch(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_ksk,
                        const uint64_t *d_in, int64_t B, uint64_t *d_out, void *stream);
+/* 32-bit keyswitch ("KS32"): key rounded to the top 32 torus bits, u32 accumulation; d_scratch32 holds
+ * B*(n+1) u32 words; the result is written as u64 words with the low half zero. */
+int fhe_b200_ksk_to_32(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_ksk,
+                       uint32_t *d_ksk32, void *stream);
+int fhe_b200_keyswitch32(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint32_t *d_ksk32,
+                         const uint64_t *d_in, int64_t B, uint32_t *d_scratch32, uint64_t *d_out,
+                         void *stream);
 int fhe_b200_pbs(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf,
                  const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
                  const int32_t *d_lut_index, uint64_t *d_out, void *stream);

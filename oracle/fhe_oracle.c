@@ -271,6 +271,39 @@ void orc_keyswitch_batch(const orc_pbs_params *p, const uint64_t *ksk, const uin
     }
 }
 
+/* 32-bit keyswitch ("KS32"): the keyswitch output only has to be accurate to the small key's noise
+ * (2^-17), so key and accumulation are carried on the top 32 bits of the torus.
+ * ksk32 = round(ksk / 2^32); out = ((round(b_in / 2^32) - sum digit * ksk32) mod 2^32) << 32. */
+void orc_ksk_to_32(const orc_pbs_params *p, const uint64_t *ksk, uint32_t *ksk32) {
+    int64_t words = (int64_t)p->k * p->N * p->l_ks * (p->n + 1);
+    for (int64_t i = 0; i < words; ++i) ksk32[i] = (uint32_t)((ksk[i] + 0x80000000ULL) >> 32);
+}
+
+void orc_keyswitch32_batch(const orc_pbs_params *p, const uint32_t *ksk32, const uint64_t *in,
+                           int64_t B, uint64_t *out) {
+    int64_t kN = (int64_t)p->k * p->N;
+    int n = p->n, l = p->l_ks, beta = p->beta_ks;
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < B; ++b) {
+        const uint64_t *x = in + (size_t)b * (kN + 1);
+        uint64_t *o = out + (size_t)b * (n + 1);
+        uint32_t acc[4097];
+        for (int w = 0; w < n; ++w) acc[w] = 0;
+        acc[n] = (uint32_t)((x[kN] + 0x80000000ULL) >> 32);
+        int64_t dig[16];
+        for (int64_t j = 0; j < kN; ++j) {
+            decompose(x[j], l, beta, dig);
+            for (int lev = 0; lev < l; ++lev) {
+                if (!dig[lev]) continue;
+                const uint32_t *kr = ksk32 + ((size_t)j * l + lev) * (n + 1);
+                uint32_t dv = (uint32_t)(int32_t)dig[lev];
+                for (int w = 0; w <= n; ++w) acc[w] -= dv * kr[w];
+            }
+        }
+        for (int w = 0; w <= n; ++w) o[w] = (uint64_t)acc[w] << 32;
+    }
+}
+
 /* ------------------------------------------------------------------ */
 /* Negacyclic FFT (size N/2 complex, folding + twisting)                */
 /* ------------------------------------------------------------------ */

@@ -71,6 +71,9 @@ void orc_bsk_gen(const orc_pbs_params *p, const uint8_t *s_small, const uint8_t 
 void orc_bsk_to_fourier(const orc_pbs_params *p, const uint64_t *bsk, double *bskf);
 void orc_keyswitch_batch(const orc_pbs_params *p, const uint64_t *ksk, const uint64_t *in,
                          int64_t B, uint64_t *out);
+void orc_ksk_to_32(const orc_pbs_params *p, const uint64_t *ksk, uint32_t *ksk32);
+void orc_keyswitch32_batch(const orc_pbs_params *p, const uint32_t *ksk32, const uint64_t *in,
+                           int64_t B, uint64_t *out);
 void orc_modswitch_batch(const orc_pbs_params *p, const uint64_t *in, int64_t B, int32_t *out);
 void orc_pbs_batch(const orc_pbs_params *p, const double *bskf, const uint64_t *in, int64_t B,
                    const uint64_t *luts, const int32_t *lut_index, uint64_t *out);

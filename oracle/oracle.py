@@ -68,6 +68,8 @@ def lib() -> C.CDLL:
         L.orc_bsk_gen.argtypes = [pp, u8p, u8p, C.c_uint64, u64p]
         L.orc_bsk_to_fourier.argtypes = [pp, u64p, f64p]
         L.orc_keyswitch_batch.argtypes = [pp, u64p, u64p, C.c_int64, u64p]
+        L.orc_ksk_to_32.argtypes = [pp, u64p, u32p]
+        L.orc_keyswitch32_batch.argtypes = [pp, u32p, u64p, C.c_int64, u64p]
         L.orc_modswitch_batch.argtypes = [pp, u64p, C.c_int64, i32p]
         L.orc_pbs_batch.argtypes = [pp, f64p, u64p, C.c_int64, u64p, i32p, u64p]
         L.orc_negacyclic_mul_fft.argtypes = [C.c_int32, i64p, u64p, u64p]
@@ -182,6 +184,21 @@ def keyswitch(p: PBSParams, ksk, ct) -> np.ndarray:
     B = ct.shape[0]
     out = np.zeros((B, p.n + 1), dtype=np.uint64)
     lib().orc_keyswitch_batch(C.byref(p), _p(ksk, C.c_uint64), _p(ct, C.c_uint64), B, _p(out, C.c_uint64))
+    return out
+
+
+def ksk_to_32(p: PBSParams, ksk) -> np.ndarray:
+    ksk = np.ascontiguousarray(ksk, dtype=np.uint64)
+    out = np.zeros(ksk.shape, dtype=np.uint32)
+    lib().orc_ksk_to_32(C.byref(p), _p(ksk, C.c_uint64), _p(out, C.c_uint32))
+    return out
+
+
+def keyswitch32(p: PBSParams, ksk32, ct) -> np.ndarray:
+    ct = np.ascontiguousarray(ct, dtype=np.uint64); ksk32 = np.ascontiguousarray(ksk32, dtype=np.uint32)
+    B = ct.shape[0]
+    out = np.zeros((B, p.n + 1), dtype=np.uint64)
+    lib().orc_keyswitch32_batch(C.byref(p), _p(ksk32, C.c_uint32), _p(ct, C.c_uint64), B, _p(out, C.c_uint64))
     return out
 
 

@@ -156,3 +156,25 @@ def test_pbs_per_ciphertext_lut_index(O, toy, cuda_dev):
     out = E.pbs(K.p, K.bskf, ct, E.from_u64_numpy(luts, cuda_dev), torch.as_tensor(idx.astype(np.int32)))
     exp = np.where(idx == 0, t0[msgs], t1[msgs])
     assert np.array_equal(O.lwe_decrypt(K.oS, _u64(out), 59) & 15, exp)
+
+
+@pytest.mark.parametrize("which,B", [("toy", 5), ("p4", 1), ("p4", 40)])
+def test_keyswitch32_bit_exact_and_correct(O, request, cuda_dev, which, B):
+    """32-bit keyswitch (key rounded to 32 torus bits): bit-exact vs the oracle's KS32, decrypts to the
+    message, and its output differs from the 64-bit keyswitch by ~2^-21.6 (std) of the torus -- the
+    rounded key's error over kN*l*(n/2) terms -- against a small-key noise of 2^-17.1."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    K = request.getfixturevalue(which)
+    msgs = np.random.RandomState(B).randint(0, 16, size=B)
+    ct = E.lwe_encrypt(K.S, torch.as_tensor(msgs), 59, K.op.sigma_glwe_abs, enc_seed=5, ct_base=70,
+                       stride=K.p.k * K.p.N + 2)[:, : K.p.k * K.p.N + 1].contiguous()
+    ksk32 = E.ksk_to_32(K.p, K.ksk)
+    oksk32 = O.ksk_to_32(K.op, _u64(K.ksk))
+    assert np.array_equal(ksk32.cpu().numpy().view(np.uint32), oksk32)
+    out = E.keyswitch32(K.p, ksk32, ct)
+    ref = O.keyswitch32(K.op, oksk32, _u64(ct))
+    assert np.array_equal(_u64(out), ref)
+    assert np.array_equal(O.lwe_decrypt(K.os, ref, 59), msgs)
+    d = (O.lwe_phase(K.os, ref) - O.lwe_phase(K.os, O.keyswitch(K.op, _u64(K.ksk), _u64(ct)))).view(np.int64)
+    assert np.log2(np.abs(d).max() + 1) - 64 < -19
