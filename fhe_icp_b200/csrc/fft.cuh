@@ -7,9 +7,10 @@
 //   transpose through a 16 KB XOR-swizzled shared-memory tile (the only exchange)
 //   pass 2  lane k2 : 32-point DFT over j1 held in registers           -> index k1
 //
-// Forward passes are radix-2 DIF (natural in, bit-reversed out), inverse passes are DIT
-// (bit-reversed in, natural out), so no permutation is ever executed: "bit reversal" is a
-// compile-time renaming of registers.  Bins come out in natural order k = lane + 32*k1,
+// All passes are radix-2 DIT butterflies (fused with their twiddle product); the forward passes
+// run them on a bit-reversed view of the registers (natural in, bit-reversed out), the inverse
+// passes directly (bit-reversed in, natural out), so no permutation is ever executed: "bit
+// reversal" is a compile-time renaming of registers.  Bins come out in natural order k = lane + 32*k1,
 // which is also the layout of the Fourier-domain bootstrapping key.
 //
 // The per-lane code is __host__ __device__ so that tests/ can emulate a warp on the CPU
@@ -103,41 +104,14 @@ constexpr int TILE_PITCH = 33;
 constexpr int TILE_ELEMS = 32 * TILE_PITCH;  // 1056 elements = 16,896 bytes
 FHE_HD constexpr int slot(int row, int col) { return row * TILE_PITCH + col; }
 
-// 32-point DFT, radix-2 decimation in frequency: natural-order input, frequency f ends at
-// register brev5(f).  SIGN=+1: exp(+2*pi*i*jf/32).
-template <int SIGN>
-FHE_HD void dif32(double (&re)[32], double (&im)[32]) {
-#pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-#pragma unroll
-        for (int base = 0; base < 32; base += 2 * half) {
-#pragma unroll
-            for (int j = 0; j < half; ++j) {
-                const int a = base + j, b = a + half;
-                const double ar = re[a], ai = im[a], br = re[b], bi = im[b];
-                re[a] = ar + br;
-                im[a] = ai + bi;
-                const double dr = ar - br, di = ai - bi;
-                const int tw = j * (16 / half);
-                if (tw == 0) {
-                    re[b] = dr;
-                    im[b] = di;
-                } else if (tw == 8) {
-                    re[b] = SIGN > 0 ? -di : di;
-                    im[b] = SIGN > 0 ? dr : -dr;
-                } else {
-                    const double wr = FHE_W32_RE(tw), wi = SIGN > 0 ? FHE_W32_IM(tw) : -FHE_W32_IM(tw);
-                    re[b] = dr * wr - di * wi;
-                    im[b] = dr * wi + di * wr;
-                }
-            }
-        }
-    }
-}
-
-// 32-point DFT, radix-2 decimation in time: input for index q sits at register brev5(q),
-// output in natural order.
-template <int SIGN>
+// 32-point DFT, radix-2 decimation in time, fully unrolled in registers.  The input for index q
+// sits at LOGICAL position brev5(q), the output for index f at logical position f.  With
+// PERM = true logical position i lives in register brev5(i): natural-order input registers, output
+// f in register brev5(f) (what a decimation-in-frequency pass would leave) -- so both transform
+// directions use DIT butterflies and "bit reversal" stays a compile-time renaming of registers.
+// DIT is chosen because its butterfly fuses with the twiddle product: y0 = a + w*b costs 4 FMAs and
+// y1 = 2a - y0 two more (6 FP64 instructions instead of 8 for multiply-then-add/sub).
+template <int SIGN, bool PERM>
 FHE_HD void dit32(double (&re)[32], double (&im)[32]) {
 #pragma unroll
     for (int half = 1; half <= 16; half <<= 1) {
@@ -145,25 +119,32 @@ FHE_HD void dit32(double (&re)[32], double (&im)[32]) {
         for (int base = 0; base < 32; base += 2 * half) {
 #pragma unroll
             for (int j = 0; j < half; ++j) {
-                const int a = base + j, b = a + half;
+                const int a = PERM ? brev5(base + j) : base + j;
+                const int b = PERM ? brev5(base + j + half) : base + j + half;
                 const int tw = j * (16 / half);
-                double tr, ti;
+                const double ar = re[a], ai = im[a], br = re[b], bi = im[b];
                 if (tw == 0) {
-                    tr = re[b];
-                    ti = im[b];
-                } else if (tw == 8) {
-                    tr = SIGN > 0 ? -im[b] : im[b];
-                    ti = SIGN > 0 ? re[b] : -re[b];
+                    re[a] = ar + br;
+                    im[a] = ai + bi;
+                    re[b] = ar - br;
+                    im[b] = ai - bi;
+                } else if (tw == 8) {  // w = +-i
+                    if (SIGN > 0) {
+                        re[a] = ar - bi; im[a] = ai + br;
+                        re[b] = ar + bi; im[b] = ai - br;
+                    } else {
+                        re[a] = ar + bi; im[a] = ai - br;
+                        re[b] = ar - bi; im[b] = ai + br;
+                    }
                 } else {
                     const double wr = FHE_W32_RE(tw), wi = SIGN > 0 ? FHE_W32_IM(tw) : -FHE_W32_IM(tw);
-                    tr = re[b] * wr - im[b] * wi;
-                    ti = re[b] * wi + im[b] * wr;
+                    const double y0r = fma(-bi, wi, fma(br, wr, ar));
+                    const double y0i = fma(bi, wr, fma(br, wi, ai));
+                    re[a] = y0r;
+                    im[a] = y0i;
+                    re[b] = fma(2.0, ar, -y0r);
+                    im[b] = fma(2.0, ai, -y0i);
                 }
-                const double ar = re[a], ai = im[a];
-                re[a] = ar + tr;
-                im[a] = ai + ti;
-                re[b] = ar - tr;
-                im[b] = ai - ti;
             }
         }
     }
@@ -183,7 +164,7 @@ FHE_HD void fwd_phase1(double (&re)[32], double (&im)[32], const cplx* tw, cplx*
         re[j2] = a * cr - b * ci;
         im[j2] = a * ci + b * cr;
     }
-    dif32<+1>(re, im);
+    dit32<+1, true>(re, im);
     // twiddle loads run PF elements ahead of their use (explicit software prefetch: with one or two
     // warps per scheduler the shared-memory latency is otherwise exposed at every multiply)
     constexpr int PF = FHE_FFT_PREFETCH;
@@ -208,13 +189,13 @@ FHE_HD void fwd_phase2(double (&re)[32], double (&im)[32], const cplx* buf, int 
         re[j1] = v.x;
         im[j1] = v.y;
     }
-    dif32<+1>(re, im);
+    dit32<+1, true>(re, im);
 }
 
 // ---- inverse: register brev5(k1) holds bin k = lane + 32*k1.  After phase 2 register j2 holds
 // (c[j] + i*c[j+1024]) for j = lane + 32*j2, fully untwisted and scaled by 1/1024.
 FHE_HD void inv_phase1(double (&re)[32], double (&im)[32], const cplx* tw, cplx* buf, int lane) {
-    dit32<-1>(re, im);
+    dit32<-1, false>(re, im);
     constexpr int PF = FHE_FFT_PREFETCH;
     cplx w[PF];
 #pragma unroll
@@ -236,7 +217,7 @@ FHE_HD void inv_phase2(double (&re)[32], double (&im)[32], const cplx* buf, int 
         re[p] = v.x;
         im[p] = v.y;
     }
-    dit32<-1>(re, im);
+    dit32<-1, false>(re, im);
     re[0] *= 0x1p-10;
     im[0] *= 0x1p-10;
 #pragma unroll
