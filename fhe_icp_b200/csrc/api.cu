@@ -229,6 +229,48 @@ int fhe_b200_lincomb(fhe_b200_ctx* ctx, const uint64_t* d_ct, int64_t B, int32_t
     return FHE_B200_OK;
 }
 
+int fhe_b200_lwe_encrypt_seeded(fhe_b200_ctx* ctx, const uint8_t* d_key, int32_t n, const int64_t* d_msgs, int64_t count,
+                                int32_t shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
+                                uint64_t* d_bodies, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(count >= 0, "negative count");
+    if (count == 0) return FHE_B200_OK;
+    REQUIRE(d_key && d_msgs && d_bodies, "null device pointer");
+    REQUIRE(n > 0 && shift >= 0 && shift < 64 && purpose < 256, "bad parameters");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_encrypt_seeded(d_key, n, d_msgs, count, shift, sigma_abs, enc_seed, ct_base, purpose, d_bodies,
+                                      (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_lwe_expand_seeded(fhe_b200_ctx* ctx, const uint64_t* d_bodies, int64_t count, int32_t n, int64_t stride,
+                               uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, uint64_t* d_ct, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(count >= 0, "negative count");
+    if (count == 0) return FHE_B200_OK;
+    REQUIRE(d_bodies && d_ct && purpose < 256, "null device pointer");
+    if (int r = check_lwe_shape(n, stride, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_expand_seeded(d_bodies, count, n, stride, enc_seed, ct_base, purpose, d_ct, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_lincomb_seeded(fhe_b200_ctx* ctx, const uint64_t* d_bodies, int64_t B, int32_t d, int32_t n, int64_t stride,
+                            uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, const int64_t* d_W, int32_t M,
+                            const int64_t* h_bias, int32_t shift, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_bodies && d_W && d_out, "null device pointer");
+    REQUIRE(d > 0 && d <= 4096 && (M == 1 || M == 2) && shift >= 0 && shift < 64 && purpose < 256, "bad parameters");
+    if (int r = check_lwe_shape(n, stride, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    int64_t b0 = h_bias ? h_bias[0] : 0, b1 = (h_bias && M == 2) ? h_bias[1] : 0;
+    CU(fhe::launch_lincomb_seeded(d_bodies, B, d, n, stride, enc_seed, ct_base, purpose, d_W, M, false, b0, b1, shift, d_out,
+                                  (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 int fhe_b200_lwe_modswitch32(fhe_b200_ctx* ctx, const uint64_t* d_ct, int64_t count, int64_t stride, uint32_t* d_ct32,
                              void* stream) {
     REQUIRE(ctx, "null ctx");
@@ -435,6 +477,68 @@ int fhe_b200_similarity_decrypt(fhe_b200_similarity* s, const uint64_t* d_out, i
     CU(fhe::launch_lwe_phase(s->d_key, sp.n, sp.stride, d_out, B * s->M, sp.shift, true, (uint64_t*)s->m.p, st));
     CU(fhe::launch_similarity_finalize((const int64_t*)s->m.p, B, s->M, sp.w_zero_point, sp.q_bias, sp.out_scale,
                                        sp.out_zero_point, d_y, d_q_y, st));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_encrypt_seeded(fhe_b200_similarity* s, const float* d_X, int64_t B, uint64_t enc_seed,
+                                       uint64_t ct_base, uint64_t* d_bodies, void* stream) {
+    REQUIRE(s, "null model");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_X && d_bodies, "null device pointer");
+    const auto& sp = s->spec;
+    CU(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t cnt = B * sp.d;
+    CU(s->q.reserve(sizeof(int64_t) * (size_t)cnt));
+    const int64_t qmin = -sp.x_offset, qmax = (1LL << sp.n_bits) - 1 - sp.x_offset;
+    CU(fhe::launch_quantize(d_X, cnt, sp.x_scale, sp.x_zero_point, qmin, qmax, (int64_t*)s->q.p, st));
+    CU(fhe::launch_lwe_encrypt_seeded(s->d_key, sp.n, (const int64_t*)s->q.p, cnt, sp.shift, sp.sigma_abs, enc_seed,
+                                      ct_base, FHE_B200_PUR_INPUT, d_bodies, st));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_run_seeded(fhe_b200_similarity* s, const uint64_t* d_bodies, int64_t B, uint64_t enc_seed,
+                                   uint64_t ct_base, uint64_t* d_out, void* stream) {
+    REQUIRE(s, "null model");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_bodies && d_out, "null device pointer");
+    const auto& sp = s->spec;
+    CU(cudaSetDevice(s->ctx->device));
+    CU(fhe::launch_lincomb_seeded(d_bodies, B, sp.d, sp.n, sp.stride, enc_seed, ct_base, FHE_B200_PUR_INPUT, s->d_W, s->M,
+                                  s->second_is_sum, 0, 0, sp.shift, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity* s, const float* h_X, int64_t B, uint64_t enc_seed,
+                                            uint64_t ct_base, double* h_y, int64_t* h_q_y) {
+    REQUIRE(s, "null model");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(h_X && (h_y || h_q_y), "null host pointer");
+    const auto& sp = s->spec;
+    CU(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->stream;
+    const size_t xbytes = sizeof(float) * (size_t)B * sp.d;
+    CU(s->X.reserve(xbytes));
+    CU(s->hX.reserve(xbytes));
+    CU(s->ct.reserve(sizeof(uint64_t) * (size_t)B * sp.d));       // bodies only
+    CU(s->out.reserve(sizeof(uint64_t) * (size_t)B * s->M * sp.stride));
+    CU(s->y.reserve(sizeof(double) * (size_t)B));
+    CU(s->qy.reserve(sizeof(int64_t) * (size_t)B));
+    CU(s->hy.reserve(sizeof(double) * (size_t)B));
+    CU(s->hqy.reserve(sizeof(int64_t) * (size_t)B));
+    memcpy(s->hX.p, h_X, xbytes);
+    CU(cudaMemcpyAsync(s->X.p, s->hX.p, xbytes, cudaMemcpyHostToDevice, st));
+    if (int r = fhe_b200_similarity_encrypt_seeded(s, (const float*)s->X.p, B, enc_seed, ct_base, (uint64_t*)s->ct.p, st)) return r;
+    if (int r = fhe_b200_similarity_run_seeded(s, (const uint64_t*)s->ct.p, B, enc_seed, ct_base, (uint64_t*)s->out.p, st)) return r;
+    if (int r = fhe_b200_similarity_decrypt(s, (const uint64_t*)s->out.p, B, (double*)s->y.p, (int64_t*)s->qy.p, st)) return r;
+    CU(cudaMemcpyAsync(s->hy.p, s->y.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s->hqy.p, s->qy.p, sizeof(int64_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_y) memcpy(h_y, s->hy.p, sizeof(double) * (size_t)B);
+    if (h_q_y) memcpy(h_q_y, s->hqy.p, sizeof(int64_t) * (size_t)B);
     return FHE_B200_OK;
 }
 

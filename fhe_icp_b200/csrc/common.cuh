@@ -15,14 +15,10 @@ namespace fhe {
 struct u32x4 { uint32_t x, y, z, w; };
 
 __host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-#ifdef __CUDA_ARCH__
-    lo = a * b;
-    hi = __umulhi(a, b);
-#else
+    // one 32x32->64 multiply (IMAD.WIDE.U32 on the device) instead of separate lo / hi products
     uint64_t p = (uint64_t)a * b;
     lo = (uint32_t)p;
     hi = (uint32_t)(p >> 32);
-#endif
 }
 
 __host__ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
@@ -39,6 +35,38 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, ui
         c = n;
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// Round keys k + r*(W0,W1) depend only on the seed: hot loops expand them once per thread.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+    __host__ __device__ __forceinline__ explicit PhiloxKeys(uint64_t seed) {
+        uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            k0[r] = a;
+            k1[r] = b;
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+    }
+};
+
+__host__ __device__ __forceinline__ u32x4 rng_block(const PhiloxKeys& K, uint32_t domain, uint64_t obj, uint32_t blk) {
+    u32x4 c{blk, (uint32_t)obj, (uint32_t)(obj >> 32), domain};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(0xD2511F53u, c.x, hi0, lo0);
+        mulhilo32(0xCD9E8D57u, c.z, hi1, lo1);
+        u32x4 n;
+        n.x = hi1 ^ c.y ^ K.k0[r];
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ K.k1[r];
+        n.w = lo0;
+        c = n;
     }
     return c;
 }

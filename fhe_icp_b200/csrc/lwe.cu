@@ -6,6 +6,8 @@
 // Roofline: every kernel here is HBM-bound (0.125 u64 MAC per byte for the dot product).
 // Layout: ciphertext rows of `stride` u64 words (stride even => every row is 16-byte
 // aligned), so a warp reads 512 contiguous bytes per 128-bit load instruction.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "lwe_device.cuh"
@@ -35,6 +37,7 @@ cudaError_t launch_secret_key(uint64_t key_seed, uint32_t key_id, int64_t dim, u
 // each), stores them with one 128-bit store (512 B per warp instruction) and accumulates
 // <a, s> against the key bits held in shared memory.
 constexpr int ENC_WARPS = 8;
+constexpr int64_t ENC_MAX_GRID = 148 * 8;  // resident CTAs on a B200; beyond that warps loop
 
 __global__ void __launch_bounds__(ENC_WARPS * 32)
 lwe_encrypt_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, const int64_t* __restrict__ msgs,
@@ -44,10 +47,10 @@ lwe_encrypt_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, const
     pack_key_bits(key, n, skey);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
-    if (c >= count) return;
-    warp_lwe_encrypt(skey, n, stride, (uint64_t)msgs[c] << shift, sigma_abs, enc_seed, purpose, ct_base + (uint64_t)c,
-                     out + c * stride, lane);
+    // the key bits are packed once per CTA; warps then stride over the ciphertexts
+    for (int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); c < count; c += (int64_t)gridDim.x * ENC_WARPS)
+        warp_lwe_encrypt(skey, n, stride, (uint64_t)msgs[c] << shift, sigma_abs, enc_seed, purpose,
+                         ct_base + (uint64_t)c, out + c * stride, lane);
 }
 
 cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
@@ -55,7 +58,7 @@ cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, cons
                                uint64_t* d_ct, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
     size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
-    unsigned grid = (unsigned)((count + ENC_WARPS - 1) / ENC_WARPS);
+    unsigned grid = (unsigned)std::min<int64_t>((count + ENC_WARPS - 1) / ENC_WARPS, ENC_MAX_GRID);
     lwe_encrypt_kernel<<<grid, ENC_WARPS * 32, smem, s>>>(d_key, n, stride, d_msgs, count, shift, sigma_abs,
                                                           enc_seed, ct_base, purpose, d_ct);
     count_launch();
@@ -204,6 +207,150 @@ cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_
         lincomb_kernel<2, true, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out);
     else
         lincomb_kernel<2, false, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------- seeded ciphertexts
+// A fresh LWE ciphertext is (mask, body) with the mask a pure function of (seed, ciphertext id): the
+// "seeded" form keeps only the 8-byte body and lets the evaluator regenerate the mask.  For this
+// path it turns 1.46 MB per document into 1 KB (1 M documents = 1 GB instead of 1.46 TB, SURVEY.md
+// section 7.2) and moves the dot product from the HBM roofline to the integer pipe (10 Philox rounds
+// per 16 mask bytes).  Results are bit-identical to the materialised form.
+
+// client: bodies only.  One warp per ciphertext, exactly the arithmetic of warp_lwe_encrypt.
+__global__ void __launch_bounds__(ENC_WARPS * 32)
+lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, const int64_t* __restrict__ msgs, int64_t count,
+                          int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
+                          uint64_t* __restrict__ bodies) {
+    extern __shared__ uint32_t skey[];
+    pack_key_bits(key, n, skey);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
+    const PhiloxKeys K(enc_seed);
+    const int nblk = (n + 1) / 2;
+    for (int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); c < count; c += (int64_t)gridDim.x * ENC_WARPS) {
+        const uint64_t id = ct_base + (uint64_t)c;
+        uint64_t dot = 0;
+#pragma unroll 2
+        for (int blk = lane; blk < nblk; blk += 32) {
+            u32x4 r = rng_block(K, dom, id, (uint32_t)blk);
+            const int w = 2 * blk;
+            uint32_t bits = skey[w >> 5] >> (w & 31);
+            dot += lo64(r) & (0 - (uint64_t)(bits & 1u));
+            if (w + 1 < n) dot += hi64(r) & (0 - (uint64_t)((bits >> 1) & 1u));
+        }
+        dot = warp_sum_u64(dot);
+        if (lane == 0) {
+            int64_t e = gaussian_i64(enc_seed, FHE_B200_KIND_NOISE | (purpose << 8), id, 0, sigma_abs);
+            bodies[c] = dot + ((uint64_t)msgs[c] << shift) + (uint64_t)e;
+        }
+    }
+}
+
+cudaError_t launch_lwe_encrypt_seeded(const uint8_t* d_key, int n, const int64_t* d_msgs, int64_t count, int shift,
+                                      double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
+                                      uint64_t* d_bodies, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
+    unsigned grid = (unsigned)std::min<int64_t>((count + ENC_WARPS - 1) / ENC_WARPS, ENC_MAX_GRID);
+    lwe_encrypt_seeded_kernel<<<grid, ENC_WARPS * 32, smem, s>>>(d_key, n, d_msgs, count, shift, sigma_abs, enc_seed,
+                                                                 ct_base, purpose, d_bodies);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// word w of the materialised ciphertext `id` whose body is `body`
+__device__ __forceinline__ void seeded_pair(const PhiloxKeys& K, uint32_t dom, uint64_t id, int w0, int n, uint64_t body,
+                                            uint64_t& x, uint64_t& y) {
+    u32x4 r = rng_block(K, dom, id, (uint32_t)(w0 >> 1));
+    x = w0 < n ? lo64(r) : (w0 == n ? body : 0);
+    y = w0 + 1 < n ? hi64(r) : (w0 + 1 == n ? body : 0);
+}
+
+// materialise [count][stride] from bodies (interop / tests)
+__global__ void lwe_expand_seeded_kernel(const uint64_t* __restrict__ bodies, int64_t count, int n, int64_t stride,
+                                         uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
+                                         uint64_t* __restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vecs = (int)(stride >> 1);
+    if (g >= count * vecs) return;
+    const int64_t c = g / vecs;
+    const int w0 = 2 * (int)(g - c * vecs);
+    uint64_t x, y;
+    seeded_pair(PhiloxKeys(enc_seed), FHE_B200_KIND_MASK | (purpose << 8), ct_base + (uint64_t)c, w0, n, bodies[c], x, y);
+    st_stream_u64x2(out + c * stride + w0, u64x2{x, y});
+}
+
+cudaError_t launch_lwe_expand_seeded(const uint64_t* d_bodies, int64_t count, int n, int64_t stride, uint64_t enc_seed,
+                                     uint64_t ct_base, uint32_t purpose, uint64_t* d_out, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t tot = count * (stride / 2);
+    lwe_expand_seeded_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_bodies, count, n, stride, enc_seed, ct_base,
+                                                                         purpose, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// server: out[b][m][:] = sum_j W[m][j] * expand(seed, ct_base + b*d + j)[:], masks regenerated on the fly.
+// Same thread -> (document, column pair) mapping as lincomb_kernel; no global loads except the d bodies.
+template <int M, bool SECOND_IS_SUM>
+__global__ void __launch_bounds__(LC_THREADS)
+lincomb_seeded_kernel(const uint64_t* __restrict__ bodies, int d, int n, int64_t stride, int64_t total_vecs,
+                      uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, const int64_t* __restrict__ W,
+                      uint64_t bias0, uint64_t bias1, uint64_t* __restrict__ out) {
+    extern __shared__ int64_t sW[];
+    for (int i = threadIdx.x; i < M * d; i += blockDim.x) sW[i] = W[i];
+    __syncthreads();
+    const int64_t g = (int64_t)blockIdx.x * LC_THREADS + threadIdx.x;
+    if (g >= total_vecs) return;
+    const int vecs = (int)(stride >> 1);
+    const int64_t b = g / vecs;
+    const int w0 = 2 * (int)(g - b * vecs);
+    const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
+    const uint64_t id0 = ct_base + (uint64_t)b * d;
+    const bool has_body = (w0 == n) || (w0 + 1 == n);
+    const PhiloxKeys K(enc_seed);
+    uint64_t a0x = 0, a0y = 0, a1x = 0, a1y = 0;
+    if (w0 <= n) {
+#pragma unroll 4
+        for (int j = 0; j < d; ++j) {
+            uint64_t x, y;
+            seeded_pair(K, dom, id0 + j, w0, n, has_body ? bodies[b * d + j] : 0, x, y);
+            const uint64_t w = (uint64_t)sW[j];
+            a0x += w * x;
+            a0y += w * y;
+            if (M == 2) {
+                const uint64_t w1 = SECOND_IS_SUM ? 1ULL : (uint64_t)sW[d + j];
+                a1x += w1 * x;
+                a1y += w1 * y;
+            }
+        }
+    }
+    if (w0 == n) { a0x += bias0; a1x += bias1; }
+    if (w0 + 1 == n) { a0y += bias0; a1y += bias1; }
+    uint64_t* o = out + (size_t)b * M * stride + w0;
+    st_stream_u64x2(o, u64x2{a0x, a0y});
+    if (M == 2) st_stream_u64x2(o + stride, u64x2{a1x, a1y});
+}
+
+cudaError_t launch_lincomb_seeded(const uint64_t* d_bodies, int64_t B, int d, int n, int64_t stride, uint64_t enc_seed,
+                                  uint64_t ct_base, uint32_t purpose, const int64_t* d_W, int M, bool second_is_sum,
+                                  int64_t bias0, int64_t bias1, int shift, uint64_t* d_out, cudaStream_t s) {
+    if (B <= 0) return cudaSuccess;
+    const int64_t total_vecs = B * (stride / 2);
+    const int64_t grid64 = (total_vecs + LC_THREADS - 1) / LC_THREADS;
+    if (grid64 > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)grid64;
+    const size_t smem = (size_t)M * d * sizeof(int64_t);
+    const uint64_t b0 = (uint64_t)bias0 << shift, b1 = (uint64_t)bias1 << shift;
+    if (M == 1)
+        lincomb_seeded_kernel<1, false><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out);
+    else if (second_is_sum)
+        lincomb_seeded_kernel<2, true><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out);
+    else
+        lincomb_seeded_kernel<2, false><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out);
     count_launch();
     return cudaGetLastError();
 }

@@ -7,12 +7,22 @@ namespace fhe {
 // pack the 0/1 key bytes into 32-bit words in shared memory (block-wide; caller syncs)
 __device__ __forceinline__ void pack_key_bits(const uint8_t* __restrict__ key, int n, uint32_t* skey) {
     const int kw = (n + 31) / 32 + 1;
+    const bool aligned = (reinterpret_cast<uintptr_t>(key) & 3) == 0;
     for (int i = threadIdx.x; i < kw; i += blockDim.x) {
         uint32_t w = 0;
-#pragma unroll 8
-        for (int b = 0; b < 32; ++b) {
-            int j = i * 32 + b;
-            if (j < n) w |= (uint32_t)(key[j] & 1u) << b;
+        if (aligned && i * 32 + 32 <= n) {
+            // 8 independent 4-byte loads; each byte holds 0/1
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(key + i * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t v = p[q];
+                w |= ((v & 1u) | ((v >> 7) & 2u) | ((v >> 14) & 4u) | ((v >> 21) & 8u)) << (4 * q);
+            }
+        } else {
+            for (int b = 0; b < 32; ++b) {
+                int j = i * 32 + b;
+                if (j < n) w |= (uint32_t)(key[j] & 1u) << b;
+            }
         }
         skey[i] = w;
     }
@@ -24,10 +34,12 @@ __device__ __forceinline__ void warp_lwe_encrypt(const uint32_t* skey, int n, in
                                                  double sigma_abs, uint64_t seed, uint32_t purpose, uint64_t id,
                                                  uint64_t* __restrict__ ct, int lane) {
     const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
+    const PhiloxKeys K(seed);
     uint64_t dot = 0;
     const int nblk = (n + 1) / 2;
+#pragma unroll 2
     for (int blk = lane; blk < nblk; blk += 32) {
-        u32x4 r = rng_block(seed, dom, id, (uint32_t)blk);
+        u32x4 r = rng_block(K, dom, id, (uint32_t)blk);
         uint64_t a0 = lo64(r), a1 = hi64(r);
         const int w = 2 * blk;
         uint32_t bits = skey[w >> 5] >> (w & 31);  // w even => bits w and w+1 share a word

@@ -102,6 +102,44 @@ def lincomb(ct: torch.Tensor, W: torch.Tensor, n: int, bias=None, shift: int = 0
     return out
 
 
+# ------------------------------------------------------------------------------- seeded ciphertexts
+def lwe_encrypt_seeded(key: torch.Tensor, msgs: torch.Tensor, shift: int, sigma_abs: float, enc_seed: int,
+                       ct_base: int = 0, purpose: int = N.PUR_INPUT) -> torch.Tensor:
+    """Bodies only (8 bytes per ciphertext); masks are regenerated from (enc_seed, ct_base + index)."""
+    dev = key.device
+    m = msgs.to(device=dev, dtype=torch.int64).contiguous()
+    bodies = torch.empty(m.shape, dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_lwe_encrypt_seeded(_ctx(dev).handle, _ptr(key), key.numel(), _ptr(m), m.numel(), shift,
+                                                float(sigma_abs), enc_seed, ct_base, purpose, _ptr(bodies), _stream(dev)))
+    return bodies
+
+
+def lwe_expand_seeded(bodies: torch.Tensor, n: int, enc_seed: int, ct_base: int = 0, purpose: int = N.PUR_INPUT,
+                      stride: int | None = None) -> torch.Tensor:
+    dev = bodies.device
+    stride = stride or even_stride(n)
+    b = bodies.contiguous()
+    ct = torch.empty(tuple(b.shape) + (stride,), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_lwe_expand_seeded(_ctx(dev).handle, _ptr(b), b.numel(), n, stride, enc_seed, ct_base,
+                                               purpose, _ptr(ct), _stream(dev)))
+    return ct
+
+
+def lincomb_seeded(bodies: torch.Tensor, W: torch.Tensor, n: int, enc_seed: int, ct_base: int = 0,
+                   purpose: int = N.PUR_INPUT, bias=None, shift: int = 0, stride: int | None = None) -> torch.Tensor:
+    """bodies [B,d], W [M,d] -> [B,M,stride]; identical to lincomb(lwe_expand_seeded(bodies), W)."""
+    dev = bodies.device
+    B, d = bodies.shape
+    stride = stride or even_stride(n)
+    W = W.to(device=dev, dtype=torch.int64).reshape(-1, d).contiguous()
+    M = W.shape[0]
+    out = torch.empty((B, M, stride), dtype=torch.int64, device=dev)
+    hb = (C.c_int64 * M)(*[int(x) for x in bias]) if bias is not None else None
+    N.check(N.lib().fhe_b200_lincomb_seeded(_ctx(dev).handle, _ptr(bodies.contiguous()), B, d, n, stride, enc_seed,
+                                            ct_base, purpose, _ptr(W), M, hb, shift, _ptr(out), _stream(dev)))
+    return out
+
+
 def accumulate(acc: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     dev = acc.device
     assert acc.is_contiguous() and x.is_contiguous() and acc.numel() == x.numel()

@@ -15,6 +15,21 @@ import numpy as np
 from .linear_model import DEFAULT_ENC_SEED, DEFAULT_KEY_SEED, LinearRegression, SGDRegressor  # noqa: F401
 
 
+class SeededCiphertexts:
+    """Compressed fresh ciphertexts: ``bodies`` [B,d] u64 (int64 view) + the public (enc_seed, ct_base)
+    from which the evaluator regenerates every mask word (ciphertext (b,j) has id ct_base + b*d + j)."""
+
+    def __init__(self, bodies, enc_seed: int, ct_base: int):
+        self.bodies, self.enc_seed, self.ct_base = bodies, int(enc_seed), int(ct_base)
+
+    @property
+    def shape(self):
+        return tuple(self.bodies.shape)
+
+    def nbytes(self) -> int:
+        return self.bodies.numel() * 8
+
+
 class FHESimilarityModel:
     """Optimized FHE model for similarity computation."""
 
@@ -141,8 +156,9 @@ class FHESimilarityModel:
             c.keygen()
         return self
 
-    def encrypt(self, X: np.ndarray):
-        """Client: float rows [B,d] -> device ciphertext tensor [B,d,stride] (int64 view of u64)."""
+    def encrypt(self, X: np.ndarray, seeded: bool = False):
+        """Client: float rows [B,d] -> device ciphertext tensor [B,d,stride] (int64 view of u64), or --
+        ``seeded=True`` -- a :class:`SeededCiphertexts` (8-byte bodies + the public mask seed/ids)."""
         import ctypes as C
         import torch
         from . import _native as N
@@ -150,6 +166,13 @@ class FHESimilarityModel:
         dev = torch.device("cuda", N.context(self.device).device)
         Xd = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32)).reshape(-1, c.spec.d).to(dev)
         B = Xd.shape[0]
+        if seeded:
+            bodies = torch.empty((B, c.spec.d), dtype=torch.int64, device=dev)
+            base = c.next_ct_base(B * c.spec.d)
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            N.check(N.lib().fhe_b200_similarity_encrypt_seeded(c.handle, C.c_void_p(Xd.data_ptr()), B, c.enc_seed, base,
+                                                               C.c_void_p(bodies.data_ptr()), st))
+            return SeededCiphertexts(bodies, c.enc_seed, base)
         ct = torch.empty((B, c.spec.d, c.lwe.stride), dtype=torch.int64, device=dev)
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         N.check(N.lib().fhe_b200_similarity_encrypt(c.handle, C.c_void_p(Xd.data_ptr()), B, c.enc_seed,
@@ -162,8 +185,16 @@ class FHESimilarityModel:
         import torch
         from . import _native as N
         c = self.keygen().model.fhe_circuit
-        B = ct.shape[0]
         M = 2 if c.two_outputs else 1
+        if isinstance(ct, SeededCiphertexts):
+            B, dev = ct.bodies.shape[0], ct.bodies.device
+            if out is None:
+                out = torch.empty((B, M, c.lwe.stride), dtype=torch.int64, device=dev)
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            N.check(N.lib().fhe_b200_similarity_run_seeded(c.handle, C.c_void_p(ct.bodies.data_ptr()), B, ct.enc_seed,
+                                                           ct.ct_base, C.c_void_p(out.data_ptr()), st))
+            return out
+        B = ct.shape[0]
         if out is None:
             out = torch.empty((B, M, c.lwe.stride), dtype=torch.int64, device=ct.device)
         st = C.c_void_p(torch.cuda.current_stream(ct.device).cuda_stream)

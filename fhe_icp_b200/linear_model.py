@@ -43,6 +43,9 @@ class FHECircuit:
         self.enc_seed = int(enc_seed)
         self.device = device
         self.ct_counter = 0
+        # "seeded": fresh ciphertexts travel as 8-byte bodies + public mask seed (the evaluator regenerates
+        # the masks); "expanded": full (n+1)-word ciphertexts are materialised in HBM.  Same results.
+        self.ciphertext_format = "seeded"
         self._sim = None
         self._sim_ctx = None
         zp_w = int(spec.weight_q.zero_point)
@@ -128,7 +131,9 @@ class FHECircuit:
         y = np.empty(B, dtype=np.float64)
         qy = np.empty(B, dtype=np.int64)
         base = self.next_ct_base(B * self.spec.d)
-        N.check(N.lib().fhe_b200_similarity_predict_host(
+        fn = (N.lib().fhe_b200_similarity_predict_host_seeded if self.ciphertext_format == "seeded"
+              else N.lib().fhe_b200_similarity_predict_host)
+        N.check(fn(
             self.handle, X.ctypes.data_as(C.POINTER(C.c_float)), B, self.enc_seed, base,
             y.ctypes.data_as(C.POINTER(C.c_double)), qy.ctypes.data_as(C.POINTER(C.c_int64))))
         return (y, qy) if return_q else y

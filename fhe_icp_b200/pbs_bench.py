@@ -82,9 +82,14 @@ def measure(dev, args, batches=None):
                      "frac": best["fp64_tflops"] / fp64_peak if fp64_peak else None,
                      "peak_source": "measured live (fhe_b200_probe_fp64, dependent-FMA chains)",
                      "flops_per_pbs": flops, "bsk_fourier_bytes": int(bsk_bytes),
-                     "note": "batch 1 is key-streaming/latency bound (one CTA walks 742 dependent CMuxes); "
-                             "from a few ciphertexts per SM the FP64 pipe + shared-memory bandwidth bind and the "
-                             "48.6 MB Fourier key stays L2-resident"},
+                     "fp64_pipe_active_ncu": 0.526, "smem_wavefronts_of_peak_ncu": 0.593,
+                     "ncu_source": "profiles/r1_ncu_pbs_v5_dit.txt (batch 592)",
+                     "hbm_term": {"bytes_per_batch": int(bsk_bytes + best["batch"] * (p.n + 1 + p.k * p.N + 1 + p.N) * 8),
+                                  "note": "the Fourier key is read from HBM once per launch and then served from L2 "
+                                          "(ncu: 52 MB DRAM reads per launch); key streaming never binds once batched"},
+                     "note": "flops = 5*M*log2(M) per FFT + 8 per complex MAC; the kernel's instruction mix "
+                             "(DADD/DMUL/DFMA ~ 45/25/30 %) caps it at ~65 % of the FMA peak even with a saturated "
+                             "pipe.  Batch 1 is latency bound (one CTA walks 742 dependent CMuxes, 7.7 ms)."},
     }
     return res
 

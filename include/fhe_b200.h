@@ -114,6 +114,22 @@ int fhe_b200_lwe_decrypt(fhe_b200_ctx *ctx, const uint8_t *d_key, int32_t n, int
 int fhe_b200_lincomb(fhe_b200_ctx *ctx, const uint64_t *d_ct, int64_t B, int32_t d, int32_t n,
                      int64_t stride, const int64_t *d_W, int32_t M, const int64_t *h_bias,
                      int32_t shift, uint64_t *d_out, void *stream);
+/* ---- seeded (compressed) ciphertexts ----------------------------------------------
+ * A fresh ciphertext's mask is a function of (enc_seed, purpose, ct_base + index); the seeded form
+ * keeps only the 8-byte body.  encrypt_seeded writes d_bodies[count]; expand_seeded materialises the
+ * identical [count][stride] rows fhe_b200_lwe_encrypt would have written; lincomb_seeded evaluates
+ * the encrypted dot product of B rows of d seeded ciphertexts (ids ct_base + b*d + j) regenerating
+ * the masks on the fly.  Bit-identical to the materialised path; 1 KB instead of 1.46 MB per row. */
+int fhe_b200_lwe_encrypt_seeded(fhe_b200_ctx *ctx, const uint8_t *d_key, int32_t n, const int64_t *d_msgs,
+                                int64_t count, int32_t shift, double sigma_abs, uint64_t enc_seed,
+                                uint64_t ct_base, uint32_t purpose, uint64_t *d_bodies, void *stream);
+int fhe_b200_lwe_expand_seeded(fhe_b200_ctx *ctx, const uint64_t *d_bodies, int64_t count, int32_t n,
+                               int64_t stride, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
+                               uint64_t *d_ct, void *stream);
+int fhe_b200_lincomb_seeded(fhe_b200_ctx *ctx, const uint64_t *d_bodies, int64_t B, int32_t d, int32_t n,
+                            int64_t stride, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
+                            const int64_t *d_W, int32_t M, const int64_t *h_bias, int32_t shift,
+                            uint64_t *d_out, void *stream);
 /* 32-bit wire form of finished ciphertexts (modulus switch 2^64 -> 2^32, same row stride in words):
  * halves the bytes gathered to the decrypting client; the added noise is stated in DESIGN.md. */
 int fhe_b200_lwe_modswitch32(fhe_b200_ctx *ctx, const uint64_t *d_ct, int64_t count, int64_t stride,
@@ -162,6 +178,13 @@ int fhe_b200_similarity_run(fhe_b200_similarity *sim, const uint64_t *d_ct, int6
                             uint64_t *d_out, void *stream);
 int fhe_b200_similarity_decrypt(fhe_b200_similarity *sim, const uint64_t *d_out, int64_t B,
                                 double *d_y, int64_t *d_q_y, void *stream);
+/* seeded variants: d_bodies [B][d] u64, ciphertext ids ct_base + b*d + j */
+int fhe_b200_similarity_encrypt_seeded(fhe_b200_similarity *sim, const float *d_X, int64_t B,
+                                       uint64_t enc_seed, uint64_t ct_base, uint64_t *d_bodies, void *stream);
+int fhe_b200_similarity_run_seeded(fhe_b200_similarity *sim, const uint64_t *d_bodies, int64_t B,
+                                   uint64_t enc_seed, uint64_t ct_base, uint64_t *d_out, void *stream);
+int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity *sim, const float *h_X, int64_t B,
+                                            uint64_t enc_seed, uint64_t ct_base, double *h_y, int64_t *h_q_y);
 /* same, for scores received in the 32-bit wire form */
 int fhe_b200_similarity_decrypt32(fhe_b200_similarity *sim, const uint32_t *d_out32, int64_t B,
                                   double *d_y, int64_t *d_q_y, void *stream);

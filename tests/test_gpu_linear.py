@@ -166,3 +166,47 @@ def test_noise_variance_within_bound(O, cuda_dev):
     pred_std = c.lwe.sigma_abs * np.sqrt(float((c.spec.q_weights.astype(np.float64) ** 2).sum()))
     assert 0.8 < err.std() / pred_std < 1.2
     assert np.abs(err).max() < 2.0 ** (c.lwe.shift - 1)
+
+
+@pytest.mark.parametrize("n,d,M", [(1423, 128, 2), (1023, 128, 1), (16, 5, 2), (15, 3, 1), (630, 130, 2)])
+def test_seeded_ciphertexts_bit_identical_to_expanded(O, cuda_dev, n, d, M):
+    """Seeded form (bodies + public seed): expand(seeded) == encrypt == oracle, and the on-the-fly
+    dot product equals the dot product of the materialised ciphertexts, word for word."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    rng = np.random.RandomState(n + d)
+    B, shift, sigma = 7, 42, 2.0 ** 28
+    msgs = rng.randint(-128, 128, size=(B, d))
+    key = E.secret_key(99, 2, n, cuda_dev)
+    stride = E.even_stride(n)
+    bodies = E.lwe_encrypt_seeded(key, torch.as_tensor(msgs), shift, sigma, enc_seed=555, ct_base=12345)
+    full = E.lwe_encrypt(key, torch.as_tensor(msgs), shift, sigma, enc_seed=555, ct_base=12345, stride=stride)
+    assert np.array_equal(_u64(bodies), _u64(full)[..., n])
+    assert np.array_equal(_u64(E.lwe_expand_seeded(bodies, n, 555, 12345, stride=stride)), _u64(full))
+    ref_ct = O.lwe_encrypt(O.secret_key(99, 2, n), msgs, shift, sigma, 555, ct_base=12345, stride=stride)
+    assert np.array_equal(_u64(full).reshape(-1, stride), ref_ct)
+    W = rng.randint(-128, 128, size=(M, d))
+    bias = rng.randint(-50, 50, size=M)
+    got = E.lincomb_seeded(bodies, torch.as_tensor(W), n, 555, 12345, bias=bias, shift=shift, stride=stride)
+    assert np.array_equal(_u64(got), O.lincomb(ref_ct.reshape(B, d, stride), W, n, bias=bias, shift=shift))
+    assert np.array_equal(O.lwe_decrypt(O.secret_key(99, 2, n), _u64(got), shift), msgs @ W.T + bias)
+
+
+def test_seeded_and_expanded_model_paths_agree(cuda_dev):
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=17, verbose=False)
+    X, _ = m.train(n_samples=400)
+    m.compile(X[:10])
+    c = m.model.fhe_circuit
+    assert c.ciphertext_format == "seeded"
+    y_seeded = m.predict_encrypted(X)
+    c.ciphertext_format = "expanded"
+    y_expanded = m.predict_encrypted(X)
+    assert np.array_equal(y_seeded, y_expanded) and np.array_equal(y_seeded, m.predict_clear(X))
+    sc = m.encrypt(X[:50], seeded=True)
+    assert sc.nbytes() == 50 * 128 * 8
+    out_s = m.run(sc)
+    c.ct_counter = sc.ct_base                      # same ciphertext ids for the expanded form
+    out_e = m.run(m.encrypt(X[:50]))
+    assert np.array_equal(_u64(out_s), _u64(out_e))
+    assert np.array_equal(m.decrypt(out_s), m.predict_clear(X[:50]))
