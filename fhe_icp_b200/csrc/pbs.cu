@@ -469,8 +469,8 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
         tma_load_1d(stage, bskf, STAGE_BYTES, bar_full);
     }
 
-    const uint64_t Bm = (1ULL << beta) - 1, half = 1ULL << (beta - 1);
     const uint64_t rnd = 1ULL << (63 - beta);
+    const int dshift = 32 - beta;
     double re[32], im[32];
     for (int i = 0; i < n; ++i) {
         const int at = a_tilde[i];
@@ -500,10 +500,11 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
                 if (s1 & 2048) r1 = 0 - r1;
                 const uint64_t own0 = ((uint64_t)lo[2 * u + 1] << 32) | lo[2 * u];
                 const uint64_t own1 = ((uint64_t)hi[2 * u + 1] << 32) | hi[2 * u];
-                const uint64_t d0 = r0 - own0, d1 = r1 - own1;
-                const uint64_t u0 = ((d0 + rnd) >> (64 - beta)) + half, u1 = ((d1 + rnd) >> (64 - beta)) + half;
-                re[j2] = (double)((int32_t)(u0 & Bm) - (int32_t)half);
-                im[j2] = (double)((int32_t)(u1 & Bm) - (int32_t)half);
+                // one level: the closest multiple of 2^(64-beta), read as a signed beta-bit integer, IS the
+                // balanced digit -- an arithmetic shift of the high word of (d + rounding constant)
+                const uint64_t d0 = r0 - own0 + rnd, d1 = r1 - own1 + rnd;
+                re[j2] = (double)((int32_t)(uint32_t)(d0 >> 32) >> dshift);
+                im[j2] = (double)((int32_t)(uint32_t)(d1 >> 32) >> dshift);
             }
         }
         __syncwarp();  // every lane has read the ACC copy before the tile becomes the transpose buffer
