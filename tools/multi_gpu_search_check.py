@@ -27,8 +27,10 @@ q = rng.randn(128).astype(np.float32); q /= np.linalg.norm(q)
 docs = rng.randn(n_docs, 128).astype(np.float32)
 docs[::3] = q + 0.3 * rng.randn(len(docs[::3]), 128)
 docs /= np.linalg.norm(docs, axis=1, keepdims=True)
-ss = ShardedSearch(m, docs)
+ss = ShardedSearch(m, docs)                       # seeded ciphertexts + 32-bit score gather (defaults)
 res = ss.search(q, top_k=5, min_similarity=0.5)
+res_plain = ShardedSearch(m, docs, seeded=False, wire32=False).search(q, top_k=5, min_similarity=0.5)
+assert res == res_plain
 if rank == 0:
     ref = rank_results(ss.doc_ids, m.predict_clear(q[None, :] * docs), 5, 0.5)
     assert res == ref, (res, ref)
