@@ -431,7 +431,12 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
     cplx* tile_all = reinterpret_cast<cplx*>(base);
     uint16_t* a_tilde = reinterpret_cast<uint16_t*>(base + S::tile_bytes);
     cplx* tile = tile_all + (size_t)t * PBS_TILE;
-    uint64_t* tacc_copy = reinterpret_cast<uint64_t*>(tile);  // coefficient-ordered ACC_t between CMuxes
+    // Between CMuxes the tile carries the HIGH 32-bit words of ACC_t in coefficient order, followed by
+    // their complements (~hi = high word of -A up to one unit of 2^-32): c32[(x - a) mod 4096] is the
+    // rotated coefficient of X^a * ACC_t, sign included, in one 4-byte load.  The digit only needs
+    // torus bits 63..41, so dropping the low words moves a rounding boundary by < 2^-32 of the torus
+    // (noise +0.8 % in variance); the exact 64-bit accumulator stays in TMEM.
+    uint32_t* c32 = reinterpret_cast<uint32_t*>(tile);
     const bool live = b < B;
     const int bar_id = 1 + ctl, bar_n = POLYS * 32;
 
@@ -444,22 +449,25 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
         const uint64_t* lut = luts + (size_t)(lut_index && live ? lut_index[b] : 0) * PBS_N;
         const int rot = (4096 - (int)a_tilde[n]) & 4095;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            uint32_t r[16];
+        for (int c = 0; c < 4; ++c) {  // 16 coefficients per chunk: word q = 16c+u <-> x = lane + 32*(q&31) + 1024*(q>>5)
+            uint32_t rl[16], rh[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int x = lane + 32 * ((q & 3) * 8 + u) + (q >= 4 ? PBS_M : 0);
+            for (int u = 0; u < 16; ++u) {
+                const int q = 16 * c + u;
+                const int x = lane + 32 * (q & 31) + (q >> 5) * PBS_M;
                 uint64_t v = 0;
                 if (t == 1) {
                     const int src = (x - rot) & 4095;
                     v = lut[src & 2047];
                     if (src & 2048) v = 0 - v;
                 }
-                tacc_copy[x] = v;
-                r[2 * u] = (uint32_t)v;
-                r[2 * u + 1] = (uint32_t)(v >> 32);
+                rl[u] = (uint32_t)v;
+                rh[u] = (uint32_t)(v >> 32);
+                c32[x] = rh[u];
+                c32[x + PBS_N] = ~rh[u];
             }
-            tmem_st_x16(tacc + q * 16, r);
+            tmem_st_x16(tacc + 16 * c, rl);
+            tmem_st_x16(tacc + 64 + 16 * c, rh);
         }
         tmem_wait_st();
     }
@@ -469,42 +477,32 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
         tma_load_1d(stage, bskf, STAGE_BYTES, bar_full);
     }
 
-    const uint64_t rnd = 1ULL << (63 - beta);
+    const uint32_t rnd32 = 1u << (31 - beta);
     const int dshift = 32 - beta;
     double re[32], im[32];
     for (int i = 0; i < n; ++i) {
         const int at = a_tilde[i];
         // ---- digits of (X^at - 1) * ACC_t from the coefficient-ordered copy
+        const int base0 = lane - at;  // (x - at) for j2 = 0; the +32*j2 / +1024 offsets are immediates
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-            // own (unrotated) coefficients come from this lane's TMEM columns, the rotated ones from
-            // the coefficient-ordered copy in the tile
-            uint32_t lo[16], hi[16];
-            tmem_ld_x16(tacc + c8 * 16, lo);
-            tmem_ld_x16(tacc + 64 + c8 * 16, hi);
-            uint64_t rot0[8], rot1[8];
+        for (int c = 0; c < 2; ++c) {
+            // own (unrotated) high words come from this lane's TMEM columns, the rotated ones from c32
+            uint32_t own0[16], own1[16], rot0[16], rot1[16];
+            tmem_ld_x16(tacc + 64 + 16 * c, own0);
+            tmem_ld_x16(tacc + 96 + 16 * c, own1);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {  // all rotated loads of the chunk first, then the arithmetic
-                const int x = lane + 32 * (c8 * 8 + u);
-                const int s0 = (x - at) & 4095, s1 = (x + PBS_M - at) & 4095;
-                rot0[u] = tacc_copy[s0 & 2047];
-                rot1[u] = tacc_copy[s1 & 2047];
+            for (int u = 0; u < 16; ++u) {  // all rotated loads of the chunk first, then the arithmetic
+                const int j2 = 16 * c + u;
+                rot0[u] = c32[(base0 + 32 * j2) & 4095];
+                rot1[u] = c32[(base0 + 32 * j2 + PBS_M) & 4095];
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int j2 = c8 * 8 + u;
-                const int x = lane + 32 * j2;
-                const int s0 = (x - at) & 4095, s1 = (x + PBS_M - at) & 4095;
-                uint64_t r0 = rot0[u], r1 = rot1[u];
-                if (s0 & 2048) r0 = 0 - r0;
-                if (s1 & 2048) r1 = 0 - r1;
-                const uint64_t own0 = ((uint64_t)lo[2 * u + 1] << 32) | lo[2 * u];
-                const uint64_t own1 = ((uint64_t)hi[2 * u + 1] << 32) | hi[2 * u];
+            for (int u = 0; u < 16; ++u) {
                 // one level: the closest multiple of 2^(64-beta), read as a signed beta-bit integer, IS the
-                // balanced digit -- an arithmetic shift of the high word of (d + rounding constant)
-                const uint64_t d0 = r0 - own0 + rnd, d1 = r1 - own1 + rnd;
-                re[j2] = (double)((int32_t)(uint32_t)(d0 >> 32) >> dshift);
-                im[j2] = (double)((int32_t)(uint32_t)(d1 >> 32) >> dshift);
+                // balanced digit -- an arithmetic shift of the (rounded) high word of the difference
+                const int j2 = 16 * c + u;
+                re[j2] = (double)((int32_t)(rot0[u] - own0[u] + rnd32) >> dshift);
+                im[j2] = (double)((int32_t)(rot1[u] - own1[u] + rnd32) >> dshift);
             }
         }
         __syncwarp();  // every lane has read the ACC copy before the tile becomes the transpose buffer
@@ -557,29 +555,47 @@ pbs_kernel_tmem(const cplx* __restrict__ bskf, const uint64_t* __restrict__ in, 
         nfft::inv_phase2(re, im, tile, lane);
         __syncwarp();  // the tile is free again: it receives the updated accumulator
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            uint32_t r[16];
-            tmem_ld_x16(tacc + q * 16, r);
+        for (int c = 0; c < 4; ++c) {
+            uint32_t rl[16], rh[16];
+            tmem_ld_x16(tacc + 16 * c, rl);
+            tmem_ld_x16(tacc + 64 + 16 * c, rh);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int j2 = (q & 3) * 8 + u;
-                const uint64_t v = (((uint64_t)r[2 * u + 1] << 32) | r[2 * u]) + f64_to_torus(q < 4 ? re[j2] : im[j2]);
-                r[2 * u] = (uint32_t)v;
-                r[2 * u + 1] = (uint32_t)(v >> 32);
-                tacc_copy[lane + 32 * j2 + (q >= 4 ? PBS_M : 0)] = v;
+            for (int u = 0; u < 16; ++u) {
+                const int q = 16 * c + u;
+                const uint64_t v = (((uint64_t)rh[u] << 32) | rl[u]) + f64_to_torus(c < 2 ? re[q] : im[q - 32]);
+                rl[u] = (uint32_t)v;
+                rh[u] = (uint32_t)(v >> 32);
+                const int x = lane + 32 * (q & 31) + (q >> 5) * PBS_M;
+                c32[x] = rh[u];
+                c32[x + PBS_N] = ~rh[u];
             }
-            tmem_st_x16(tacc + q * 16, r);
+            tmem_st_x16(tacc + 16 * c, rl);
+            tmem_st_x16(tacc + 64 + 16 * c, rh);
         }
         tmem_wait_st();
         __syncwarp();
     }
-    // ---- sample extract coefficient 0 from the coefficient-ordered copy
+    // ---- sample extract coefficient 0 from the exact accumulators in TMEM:
+    //      o[0] = A_0[0], o[N - x] = -A_0[x] (x >= 1), o[N] = A_1[0]
     if (live) {
         uint64_t* o = out + (size_t)b * ((size_t)PBS_N + 1);
-        if (t == 0) {
-            for (int x = lane; x < PBS_N; x += 32) o[x] = x == 0 ? tacc_copy[0] : 0 - tacc_copy[PBS_N - x];
-        } else if (lane == 0) {
-            o[PBS_N] = tacc_copy[0];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t rl[16], rh[16];
+            tmem_ld_x16(tacc + 16 * c, rl);
+            tmem_ld_x16(tacc + 64 + 16 * c, rh);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int q = 16 * c + u;
+                const int x = lane + 32 * (q & 31) + (q >> 5) * PBS_M;
+                const uint64_t v = ((uint64_t)rh[u] << 32) | rl[u];
+                if (t == 0) {
+                    if (x == 0) o[0] = v;
+                    else o[PBS_N - x] = 0 - v;
+                } else if (x == 0) {
+                    o[PBS_N] = v;
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
