@@ -9,7 +9,10 @@
 
 namespace fhe {
 
-constexpr int KS_TB = 8;      // ciphertexts per CTA
+#ifndef KS_TB_VALUE
+#define KS_TB_VALUE 8
+#endif
+constexpr int KS_TB = KS_TB_VALUE;  // ciphertexts per CTA
 constexpr int KS_COLS = 128;  // output columns per CTA (one per thread)
 constexpr int KS_JC = 32;     // j's decomposed per shared-memory refill
 constexpr int KS_MAXL = 8;
@@ -28,11 +31,14 @@ __device__ __forceinline__ void ks_atomic_add(uint64_t* p, uint64_t v) {
 }
 __device__ __forceinline__ void ks_atomic_add(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
 
-template <typename W>
+// L = number of levels when known at compile time (0 = runtime l): with L fixed the L key words of one
+// input coefficient are loaded back to back (independent loads in flight) before their MACs.
+template <typename W, int L>
 __global__ void __launch_bounds__(KS_COLS)
 keyswitch_kernel(const W* __restrict__ ksk, const uint64_t* __restrict__ in, int64_t B, int64_t kN, int n,
-                 int l, int beta, int j_per_split, W* __restrict__ out) {
+                 int l_rt, int beta, int j_per_split, W* __restrict__ out) {
     __shared__ int32_t dig[KS_JC][KS_MAXL][KS_TB];
+    const int l = L > 0 ? L : l_rt;
     const int col = blockIdx.x * KS_COLS + threadIdx.x;
     const int64_t b0 = (int64_t)blockIdx.y * KS_TB;
     const int64_t j0 = (int64_t)blockIdx.z * j_per_split;
@@ -45,6 +51,7 @@ keyswitch_kernel(const W* __restrict__ ksk, const uint64_t* __restrict__ in, int
     const uint64_t Bm = (1ULL << beta) - 1, half = 1ULL << (beta - 1);
     uint64_t offs = 0;  // sum over digit positions of B/2: turns balanced digits into plain ones
     for (int lev = 0; lev < l; ++lev) offs |= half << (beta * lev);
+    const size_t row = (size_t)(n + 1);
     for (int64_t jc = j0; jc < j1; jc += KS_JC) {
         __syncthreads();
         for (int e = threadIdx.x; e < KS_JC * KS_TB; e += KS_COLS) {
@@ -61,12 +68,31 @@ keyswitch_kernel(const W* __restrict__ ksk, const uint64_t* __restrict__ in, int
         __syncthreads();
         if (col <= n) {
             const int jn = (int)min((int64_t)KS_JC, j1 - jc);
-            for (int jj = 0; jj < jn; ++jj) {
-                const W* kr = ksk + ((size_t)(jc + jj) * l) * (n + 1) + col;
-                for (int lev = 0; lev < l; ++lev) {
-                    const W kv = kr[(size_t)lev * (n + 1)];
+            const W* kr = ksk + ((size_t)jc * l) * row + col;
+            if (L > 0) {
+                W kv[L > 0 ? L : 1], kn[L > 0 ? L : 1];
 #pragma unroll
-                    for (int t = 0; t < KS_TB; ++t) acc[t] -= (W)(int64_t)dig[jj][lev][t] * kv;
+                for (int lev = 0; lev < L; ++lev) kv[lev] = kr[(size_t)lev * row];
+                for (int jj = 0; jj < jn; ++jj) {
+                    if (jj + 1 < jn) {  // next coefficient's key words are in flight behind these MACs
+#pragma unroll
+                        for (int lev = 0; lev < L; ++lev) kn[lev] = kr[((size_t)(jj + 1) * L + lev) * row];
+                    }
+#pragma unroll
+                    for (int lev = 0; lev < L; ++lev) {
+#pragma unroll
+                        for (int t = 0; t < KS_TB; ++t) acc[t] -= (W)(int64_t)dig[jj][lev][t] * kv[lev];
+                    }
+#pragma unroll
+                    for (int lev = 0; lev < L; ++lev) kv[lev] = kn[lev];
+                }
+            } else {
+                for (int jj = 0; jj < jn; ++jj) {
+                    for (int lev = 0; lev < l; ++lev) {
+                        const W kv = kr[((size_t)jj * l + lev) * row];
+#pragma unroll
+                        for (int t = 0; t < KS_TB; ++t) acc[t] -= (W)(int64_t)dig[jj][lev][t] * kv;
+                    }
                 }
             }
         }
@@ -74,6 +100,17 @@ keyswitch_kernel(const W* __restrict__ ksk, const uint64_t* __restrict__ in, int
     if (col <= n) {
         for (int t = 0; t < nb; ++t)
             if (acc[t]) ks_atomic_add(out + (b0 + t) * (n + 1) + col, acc[t]);
+    }
+}
+
+template <typename W>
+static void ks_dispatch(dim3 grid, cudaStream_t s, const W* ksk, const uint64_t* in, int64_t B, int64_t kN, int n, int l,
+                        int beta, int j_per_split, W* out) {
+    switch (l) {
+        case 3: keyswitch_kernel<W, 3><<<grid, KS_COLS, 0, s>>>(ksk, in, B, kN, n, l, beta, j_per_split, out); break;
+        case 4: keyswitch_kernel<W, 4><<<grid, KS_COLS, 0, s>>>(ksk, in, B, kN, n, l, beta, j_per_split, out); break;
+        case 5: keyswitch_kernel<W, 5><<<grid, KS_COLS, 0, s>>>(ksk, in, B, kN, n, l, beta, j_per_split, out); break;
+        default: keyswitch_kernel<W, 0><<<grid, KS_COLS, 0, s>>>(ksk, in, B, kN, n, l, beta, j_per_split, out); break;
     }
 }
 
@@ -92,7 +129,7 @@ cudaError_t launch_keyswitch(const fhe_b200_pbs_params& p, const uint64_t* d_ksk
     while (splits < 64 && (int64_t)col_tiles * b_tiles * splits < 600 && (kN / (splits * 2)) >= KS_JC) splits *= 2;
     const int j_per_split = (int)((kN + splits - 1) / splits);
     dim3 grid(col_tiles, (unsigned)b_tiles, splits);
-    keyswitch_kernel<uint64_t><<<grid, KS_COLS, 0, s>>>(d_ksk, d_in, B, kN, p.n, p.l_ks, p.beta_ks, j_per_split, d_out);
+    ks_dispatch<uint64_t>(grid, s, d_ksk, d_in, B, kN, p.n, p.l_ks, p.beta_ks, j_per_split, d_out);
     count_launch();
     return cudaGetLastError();
 }
@@ -139,7 +176,7 @@ cudaError_t launch_keyswitch32(const fhe_b200_pbs_params& p, const uint32_t* d_k
     while (splits < 64 && (int64_t)col_tiles * b_tiles * splits < 600 && (kN / (splits * 2)) >= KS_JC) splits *= 2;
     const int j_per_split = (int)((kN + splits - 1) / splits);
     dim3 grid(col_tiles, (unsigned)b_tiles, splits);
-    keyswitch_kernel<uint32_t><<<grid, KS_COLS, 0, s>>>(d_ksk32, d_in, B, kN, p.n, p.l_ks, p.beta_ks, j_per_split, d_acc32);
+    ks_dispatch<uint32_t>(grid, s, d_ksk32, d_in, B, kN, p.n, p.l_ks, p.beta_ks, j_per_split, d_acc32);
     count_launch();
     ks32_widen_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_acc32, tot, d_out);
     count_launch();
