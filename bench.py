@@ -82,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -170,7 +170,7 @@ def run_reference_arm(args):
     model, _ = build_model()
     _, _, X = synthetic_docs(args.docs, DATA_SEED + 1)
     vals = []
-    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = min(args.cpu_seconds, max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup))))
     rows = 0
     threads = 0
     for i in range(args.warmup + args.steps):
