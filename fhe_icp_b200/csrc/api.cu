@@ -93,6 +93,8 @@ struct fhe_b200_similarity {
     uint8_t* d_key = nullptr;
     int64_t* d_W = nullptr;  // [M][d]
     cudaStream_t stream = nullptr;
+    cudaStream_t enc_stream = nullptr;       // second stream: encryption of the next chunk
+    cudaEvent_t ev_enc[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_q = nullptr;
     // grow-only workspaces for the host-buffer entry point
     DevBuf X, q, ct, out, m, y, qy;
     PinBuf hX, hy, hqy;
@@ -430,6 +432,12 @@ int fhe_b200_similarity_destroy(fhe_b200_similarity* s) {
     s->X.release(); s->q.release(); s->ct.release(); s->out.release(); s->m.release(); s->y.release(); s->qy.release();
     s->hX.release(); s->hy.release(); s->hqy.release();
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->enc_stream) cudaStreamDestroy(s->enc_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (s->ev_enc[i]) cudaEventDestroy(s->ev_enc[i]);
+        if (s->ev_free[i]) cudaEventDestroy(s->ev_free[i]);
+    }
+    if (s->ev_q) cudaEventDestroy(s->ev_q);
     delete s;
     return FHE_B200_OK;
 }
@@ -568,29 +576,57 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
     const auto& sp = s->spec;
     CU(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->stream;
+    if (!s->enc_stream) {
+        CU(cudaStreamCreateWithFlags(&s->enc_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&s->ev_enc[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&s->ev_q, cudaEventDisableTiming));
+    }
     const size_t xbytes = sizeof(float) * (size_t)B * sp.d;
     CU(s->X.reserve(xbytes));
     CU(s->hX.reserve(xbytes));
-    // ciphertexts are materialised in HBM in chunks of at most ~2 GiB
+    // Full ciphertexts are materialised in HBM in chunks (two buffers of <= 1 GiB).  Encryption is
+    // integer-pipe bound and the dot product HBM bound, so chunk i+1 is encrypted on a second stream
+    // while chunk i is evaluated and decrypted.
     const size_t row_bytes = sizeof(uint64_t) * (size_t)sp.d * sp.stride;
-    int64_t chunk = (int64_t)(((size_t)2 << 30) / row_bytes);
+    int64_t chunk = (int64_t)(((size_t)1 << 30) / row_bytes);
     if (chunk < 1) chunk = 1;
+    if (B >= 2048 && chunk > (B + 3) / 4) chunk = (B + 3) / 4;   // >= 4 chunks so the stages overlap (measured: pays from ~2k rows)
     if (chunk > B) chunk = B;
-    CU(s->ct.reserve(row_bytes * (size_t)chunk));
+    const int64_t cnt = B * sp.d;
+    CU(s->ct.reserve(2 * row_bytes * (size_t)chunk));
     CU(s->out.reserve(sizeof(uint64_t) * (size_t)chunk * s->M * sp.stride));
+    CU(s->q.reserve(sizeof(int64_t) * (size_t)cnt));
+    CU(s->m.reserve(sizeof(int64_t) * (size_t)chunk * s->M));
     CU(s->y.reserve(sizeof(double) * (size_t)B));
     CU(s->qy.reserve(sizeof(int64_t) * (size_t)B));
     CU(s->hy.reserve(sizeof(double) * (size_t)B));
     CU(s->hqy.reserve(sizeof(int64_t) * (size_t)B));
     memcpy(s->hX.p, h_X, xbytes);  // stage through pinned memory so the copy is truly async
     CU(cudaMemcpyAsync(s->X.p, s->hX.p, xbytes, cudaMemcpyHostToDevice, st));
-    for (int64_t r0 = 0; r0 < B; r0 += chunk) {
+    const int64_t qmin = -sp.x_offset, qmax = (1LL << sp.n_bits) - 1 - sp.x_offset;
+    CU(fhe::launch_quantize((const float*)s->X.p, cnt, sp.x_scale, sp.x_zero_point, qmin, qmax, (int64_t*)s->q.p, st));
+    CU(cudaEventRecord(s->ev_q, st));
+    CU(cudaStreamWaitEvent(s->enc_stream, s->ev_q, 0));
+    int k = 0;
+    for (int64_t r0 = 0; r0 < B; r0 += chunk, ++k) {
         const int64_t rows = (B - r0 < chunk) ? (B - r0) : chunk;
-        if (int r = fhe_b200_similarity_encrypt(s, (const float*)s->X.p + r0 * sp.d, rows, enc_seed,
-                                                ct_base + (uint64_t)(r0 * sp.d), (uint64_t*)s->ct.p, st)) return r;
-        if (int r = fhe_b200_similarity_run(s, (const uint64_t*)s->ct.p, rows, (uint64_t*)s->out.p, st)) return r;
-        if (int r = fhe_b200_similarity_decrypt(s, (const uint64_t*)s->out.p, rows, (double*)s->y.p + r0,
-                                                (int64_t*)s->qy.p + r0, st)) return r;
+        uint64_t* ctb = (uint64_t*)s->ct.p + (size_t)(k & 1) * (size_t)chunk * sp.d * sp.stride;
+        if (k >= 2) CU(cudaStreamWaitEvent(s->enc_stream, s->ev_free[k & 1], 0));   // buffer consumed by chunk k-2
+        CU(fhe::launch_lwe_encrypt(s->d_key, sp.n, sp.stride, (const int64_t*)s->q.p + r0 * sp.d, rows * sp.d, sp.shift,
+                                   sp.sigma_abs, enc_seed, ct_base + (uint64_t)(r0 * sp.d), FHE_B200_PUR_INPUT, ctb,
+                                   s->enc_stream));
+        CU(cudaEventRecord(s->ev_enc[k & 1], s->enc_stream));
+        CU(cudaStreamWaitEvent(st, s->ev_enc[k & 1], 0));
+        CU(fhe::launch_lincomb(ctb, rows, sp.d, sp.n, sp.stride, s->d_W, s->M, s->second_is_sum, 0, 0, sp.shift,
+                               (uint64_t*)s->out.p, st));
+        CU(cudaEventRecord(s->ev_free[k & 1], st));
+        CU(fhe::launch_lwe_phase(s->d_key, sp.n, sp.stride, (const uint64_t*)s->out.p, rows * s->M, sp.shift, true,
+                                 (uint64_t*)s->m.p, st));
+        CU(fhe::launch_similarity_finalize((const int64_t*)s->m.p, rows, s->M, sp.w_zero_point, sp.q_bias, sp.out_scale,
+                                           sp.out_zero_point, (double*)s->y.p + r0, (int64_t*)s->qy.p + r0, st));
     }
     CU(cudaMemcpyAsync(s->hy.p, s->y.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(s->hqy.p, s->qy.p, sizeof(int64_t) * (size_t)B, cudaMemcpyDeviceToHost, st));

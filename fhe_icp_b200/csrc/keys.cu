@@ -23,7 +23,9 @@ ksk_gen_kernel(const uint8_t* __restrict__ S_big, const uint8_t* __restrict__ s_
     const int64_t j = c / l;
     const int lev = (int)(c - j * l);
     const uint64_t pt = (uint64_t)(S_big[j] & 1u) << (64 - beta * (lev + 1));
-    warp_lwe_encrypt(skey, n, n + 1, pt, sigma_abs, evk_seed, FHE_B200_PUR_KSK, (uint64_t)c, ksk + c * (n + 1), lane);
+    int64_t e = 0;  // setup kernel: lane 0 evaluates the Gaussian, no batching needed
+    if (lane == 0) e = gaussian_i64(evk_seed, FHE_B200_KIND_NOISE | (FHE_B200_PUR_KSK << 8), (uint64_t)c, 0, sigma_abs);
+    warp_lwe_encrypt(skey, n, n + 1, pt, e, evk_seed, FHE_B200_PUR_KSK, (uint64_t)c, ksk + c * (n + 1), lane);
 }
 
 cudaError_t launch_ksk_gen(const fhe_b200_pbs_params& p, const uint8_t* d_S_big, const uint8_t* d_s_small,

@@ -47,10 +47,22 @@ lwe_encrypt_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, const
     pack_key_bits(key, n, skey);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    // the key bits are packed once per CTA; warps then stride over the ciphertexts
-    for (int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); c < count; c += (int64_t)gridDim.x * ENC_WARPS)
-        warp_lwe_encrypt(skey, n, stride, (uint64_t)msgs[c] << shift, sigma_abs, enc_seed, purpose,
-                         ct_base + (uint64_t)c, out + c * stride, lane);
+    // the key bits are packed once per CTA; each warp then takes groups of 32 consecutive ciphertexts:
+    // the 32 Gaussian errors of a group are computed lane-parallel, then the warp walks the group
+    const uint32_t ndom = FHE_B200_KIND_NOISE | (purpose << 8);
+    const int64_t groups = (count + 31) / 32;
+    for (int64_t g = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); g < groups; g += (int64_t)gridDim.x * ENC_WARPS) {
+        const int64_t c0 = g * 32;
+        const int64_t mine = c0 + lane;
+        const int64_t e_mine = mine < count ? gaussian_i64(enc_seed, ndom, ct_base + (uint64_t)mine, 0, sigma_abs) : 0;
+        const uint64_t pt_mine = mine < count ? (uint64_t)msgs[mine] << shift : 0;
+        const int cnt = (int)min((int64_t)32, count - c0);
+        for (int k = 0; k < cnt; ++k) {
+            const int64_t e = __shfl_sync(0xffffffffu, e_mine, k);
+            const uint64_t pt = __shfl_sync(0xffffffffu, pt_mine, k);
+            warp_lwe_encrypt(skey, n, stride, pt, e, enc_seed, purpose, ct_base + (uint64_t)(c0 + k), out + (c0 + k) * stride, lane);
+        }
+    }
 }
 
 cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
@@ -58,7 +70,8 @@ cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, cons
                                uint64_t* d_ct, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
     size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
-    unsigned grid = (unsigned)std::min<int64_t>((count + ENC_WARPS - 1) / ENC_WARPS, ENC_MAX_GRID);
+    const int64_t groups = (count + 31) / 32;
+    unsigned grid = (unsigned)std::min<int64_t>((groups + ENC_WARPS - 1) / ENC_WARPS, ENC_MAX_GRID);
     lwe_encrypt_kernel<<<grid, ENC_WARPS * 32, smem, s>>>(d_key, n, stride, d_msgs, count, shift, sigma_abs,
                                                           enc_seed, ct_base, purpose, d_ct);
     count_launch();
@@ -230,22 +243,32 @@ lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, const int64_t*
     const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
     const PhiloxKeys K(enc_seed);
     const int nblk = (n + 1) / 2;
-    for (int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); c < count; c += (int64_t)gridDim.x * ENC_WARPS) {
-        const uint64_t id = ct_base + (uint64_t)c;
-        uint64_t dot = 0;
+    const uint32_t ndom = FHE_B200_KIND_NOISE | (purpose << 8);
+    const int64_t groups = (count + 31) / 32;
+    for (int64_t g = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); g < groups; g += (int64_t)gridDim.x * ENC_WARPS) {
+        const int64_t c0 = g * 32;
+        const int64_t mine = c0 + lane;
+        // lane-parallel: error and plaintext of ciphertext c0 + lane; the dot products follow one by one
+        uint64_t body_mine = 0;
+        if (mine < count)
+            body_mine = ((uint64_t)msgs[mine] << shift) +
+                        (uint64_t)gaussian_i64(enc_seed, ndom, ct_base + (uint64_t)mine, 0, sigma_abs);
+        const int cnt = (int)min((int64_t)32, count - c0);
+        for (int k = 0; k < cnt; ++k) {
+            const uint64_t id = ct_base + (uint64_t)(c0 + k);
+            uint64_t dot = 0;
 #pragma unroll 2
-        for (int blk = lane; blk < nblk; blk += 32) {
-            u32x4 r = rng_block(K, dom, id, (uint32_t)blk);
-            const int w = 2 * blk;
-            uint32_t bits = skey[w >> 5] >> (w & 31);
-            dot += lo64(r) & (0 - (uint64_t)(bits & 1u));
-            if (w + 1 < n) dot += hi64(r) & (0 - (uint64_t)((bits >> 1) & 1u));
+            for (int blk = lane; blk < nblk; blk += 32) {
+                u32x4 r = rng_block(K, dom, id, (uint32_t)blk);
+                const int w = 2 * blk;
+                uint32_t bits = skey[w >> 5] >> (w & 31);
+                dot += lo64(r) & (0 - (uint64_t)(bits & 1u));
+                if (w + 1 < n) dot += hi64(r) & (0 - (uint64_t)((bits >> 1) & 1u));
+            }
+            dot = warp_sum_u64(dot);
+            if (lane == k) body_mine += dot;
         }
-        dot = warp_sum_u64(dot);
-        if (lane == 0) {
-            int64_t e = gaussian_i64(enc_seed, FHE_B200_KIND_NOISE | (purpose << 8), id, 0, sigma_abs);
-            bodies[c] = dot + ((uint64_t)msgs[c] << shift) + (uint64_t)e;
-        }
+        if (mine < count) bodies[mine] = body_mine;   // one coalesced store per group
     }
 }
 
@@ -254,7 +277,8 @@ cudaError_t launch_lwe_encrypt_seeded(const uint8_t* d_key, int n, const int64_t
                                       uint64_t* d_bodies, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
     size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
-    unsigned grid = (unsigned)std::min<int64_t>((count + ENC_WARPS - 1) / ENC_WARPS, ENC_MAX_GRID);
+    const int64_t groups = (count + 31) / 32;
+    unsigned grid = (unsigned)std::min<int64_t>((groups + ENC_WARPS - 1) / ENC_WARPS, ENC_MAX_GRID);
     lwe_encrypt_seeded_kernel<<<grid, ENC_WARPS * 32, smem, s>>>(d_key, n, d_msgs, count, shift, sigma_abs, enc_seed,
                                                                  ct_base, purpose, d_bodies);
     count_launch();

@@ -30,8 +30,11 @@ __device__ __forceinline__ void pack_key_bits(const uint8_t* __restrict__ key, i
 
 // One warp writes ciphertext `id`: mask from Philox blocks (two words each, one 128-bit
 // store per lane per block => 512 B per warp instruction), body = <a,s> + plaintext + e.
+// `noise` is the ciphertext's rounded Gaussian error, already computed by the caller: the Box-Muller
+// chain is ~250 dependent FP64 instructions, so callers evaluate it for 32 ciphertexts at once (one
+// per lane) instead of on lane 0 of every ciphertext.
 __device__ __forceinline__ void warp_lwe_encrypt(const uint32_t* skey, int n, int64_t stride, uint64_t plaintext,
-                                                 double sigma_abs, uint64_t seed, uint32_t purpose, uint64_t id,
+                                                 int64_t noise, uint64_t seed, uint32_t purpose, uint64_t id,
                                                  uint64_t* __restrict__ ct, int lane) {
     const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
     const PhiloxKeys K(seed);
@@ -53,10 +56,7 @@ __device__ __forceinline__ void warp_lwe_encrypt(const uint32_t* skey, int n, in
         }
     }
     dot = warp_sum_u64(dot);
-    if (lane == 0) {
-        int64_t e = gaussian_i64(seed, FHE_B200_KIND_NOISE | (purpose << 8), id, 0, sigma_abs);
-        ct[n] = dot + plaintext + (uint64_t)e;
-    }
+    if (lane == 0) ct[n] = dot + plaintext + (uint64_t)noise;
     for (int64_t w = n + 1 + lane; w < stride; w += 32) ct[w] = 0;
 }
 
