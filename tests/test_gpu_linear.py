@@ -210,3 +210,54 @@ def test_seeded_and_expanded_model_paths_agree(cuda_dev):
     out_e = m.run(m.encrypt(X[:50]))
     assert np.array_equal(_u64(out_s), _u64(out_e))
     assert np.array_equal(m.decrypt(out_s), m.predict_clear(X[:50]))
+
+
+def test_edge_shapes_and_empty_batches(O, cuda_dev):
+    """Ragged / degenerate shapes through the C-ABI: empty batches, a single feature, d below the
+    unroll factor, odd word counts in the 32-bit wire form."""
+    import ctypes as C
+    import torch
+    from fhe_icp_b200 import _native as N
+    from fhe_icp_b200 import engine as E
+    n = 33
+    key = E.secret_key(4, 2, n, cuda_dev)
+    stride = E.even_stride(n)
+    empty = torch.empty((0, 3), dtype=torch.int64)
+    assert E.lwe_encrypt(key, empty, 40, 1.0, 1).shape == (0, 3, stride)
+    assert E.lwe_encrypt_seeded(key, empty, 40, 1.0, 1).shape == (0, 3)
+    assert E.lincomb_seeded(torch.empty((0, 3), dtype=torch.int64, device=cuda_dev), torch.ones((1, 3), dtype=torch.int64),
+                            n, 1).shape == (0, 1, stride)
+    assert E.lwe_decrypt(key, torch.empty((0, stride), dtype=torch.int64, device=cuda_dev), 40).shape == (0,)
+    for d in (1, 2, 7, 9):  # below / around the 8-row register pipeline
+        msgs = np.arange(5 * d).reshape(5, d) - 7
+        ct = E.lwe_encrypt(key, torch.as_tensor(msgs), 40, 2.0 ** 10, 3, ct_base=d)
+        W = (np.arange(d) % 5 - 2).reshape(1, d)
+        out = E.lincomb(ct, torch.as_tensor(W), n)
+        ref = O.lincomb(_u64(ct), W, n)
+        assert np.array_equal(_u64(out), ref)
+        assert np.array_equal(E.lwe_decrypt(key, out, 40).cpu().numpy(), msgs @ W.T)
+    # 32-bit wire form on an odd number of words
+    x = torch.as_tensor(np.random.RandomState(0).randint(-2 ** 62, 2 ** 62, size=3 * stride, dtype=np.int64)).to(cuda_dev)
+    y = torch.empty(3 * stride, dtype=torch.int32, device=cuda_dev)
+    ctx = N.context(cuda_dev.index)
+    N.check(N.lib().fhe_b200_lwe_modswitch32(ctx.handle, C.c_void_p(x.data_ptr()), 3, stride, C.c_void_p(y.data_ptr()), None))
+    exp = ((x.cpu().numpy().view(np.uint64) + np.uint64(1 << 31)) >> np.uint64(32)).astype(np.uint32)
+    assert np.array_equal(y.cpu().numpy().view(np.uint32), exp)
+
+
+def test_invalid_arguments_on_device(cuda_dev):
+    import ctypes as C
+    import torch
+    from fhe_icp_b200 import _native as N
+    from fhe_icp_b200 import engine as E
+    ctx = N.context(cuda_dev.index)
+    key = E.secret_key(4, 2, 16, cuda_dev)
+    ct = torch.zeros((1, 2, 17), dtype=torch.int64, device=cuda_dev)  # odd stride is rejected, not mis-read
+    rc = N.lib().fhe_b200_lincomb(ctx.handle, C.c_void_p(ct.data_ptr()), 1, 2, 16, 17, C.c_void_p(ct.data_ptr()), 1, None, 0,
+                                  C.c_void_p(ct.data_ptr()), None)
+    assert rc == N.ERR_INVALID and b"stride" in N.lib().fhe_b200_last_error()
+    with pytest.raises(N.FheB200Error):
+        E.lincomb(torch.zeros((1, 2, 18), dtype=torch.int64, device=cuda_dev), torch.ones((3, 2), dtype=torch.int64), 16)  # M=3
+    p = E.make_pbs_params(n=16, N_poly=1024)
+    with pytest.raises(N.FheB200Error, match="N must be 2048"):
+        E.ksk_gen(p, key, key, 1)

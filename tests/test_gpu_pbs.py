@@ -178,3 +178,29 @@ def test_keyswitch32_bit_exact_and_correct(O, request, cuda_dev, which, B):
     assert np.array_equal(O.lwe_decrypt(K.os, ref, 59), msgs)
     d = (O.lwe_phase(K.os, ref) - O.lwe_phase(K.os, O.keyswitch(K.op, _u64(K.ksk), _u64(ct)))).view(np.int64)
     assert np.log2(np.abs(d).max() + 1) - 64 < -19
+
+
+def test_keyswitch_generic_level_count(O, cuda_dev):
+    """l_ks outside the compile-time specialisations (3,4,5) takes the runtime-level kernel."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    d = dict(TOY, l_ks=6, beta_ks=2)
+    K = Keys(O, cuda_dev, d)
+    msgs = np.arange(12) % 8
+    ct = E.lwe_encrypt(K.S, torch.as_tensor(msgs), 60, K.op.sigma_glwe_abs, enc_seed=8, stride=K.p.N + 2)[:, : K.p.N + 1].contiguous()
+    assert np.array_equal(_u64(E.keyswitch(K.p, K.ksk, ct)), O.keyswitch(K.op, _u64(K.ksk), _u64(ct)))
+    k32 = E.ksk_to_32(K.p, K.ksk)
+    assert np.array_equal(_u64(E.keyswitch32(K.p, k32, ct)), O.keyswitch32(K.op, O.ksk_to_32(K.op, _u64(K.ksk)), _u64(ct)))
+
+
+def test_pbs_large_batch_wide_kernel(O, p4, cuda_dev):
+    """Batch > 2 x SM count takes the 4-ciphertexts-per-CTA kernel (incl. dead slots in the last CTA)."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    K = p4
+    B = 2 * 148 + 3
+    msgs = np.random.RandomState(3).randint(0, 16, size=B)
+    ct = E.lwe_encrypt(K.s, torch.as_tensor(msgs), 59, K.op.sigma_lwe_abs, enc_seed=12, stride=K.p.n + 2)[:, : K.p.n + 1].contiguous()
+    table = (np.arange(16) * 11 + 5) % 16
+    out = E.pbs(K.p, K.bskf, ct, E.from_u64_numpy(E.make_lut_poly(table, 4, K.p.N, 59), cuda_dev))
+    assert np.array_equal(O.lwe_decrypt(K.oS, _u64(out), 59) & 15, table[msgs])
