@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE = 0, 1, 2, 3, 4
 KIND_SK, KIND_MASK, KIND_NOISE = 1, 2, 3
-PUR_INPUT, PUR_KSK, PUR_BSK = 0, 1, 2
+PUR_INPUT, PUR_KSK, PUR_BSK, PUR_BSK2 = 0, 1, 2, 3
 
 
 class FheB200Error(RuntimeError):
@@ -127,6 +127,10 @@ SIGNATURES = {
     "fhe_b200_bsk_words": (C.c_uint64, [C.POINTER(PBSParams)]),
     "fhe_b200_bsk_to_fourier": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, _vp]),
     "fhe_b200_keyswitch": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp]),
+    "fhe_b200_bsk2_words": (C.c_uint64, [C.POINTER(PBSParams)]),
+    "fhe_b200_bsk2_gen": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_uint64, _vp, _vp]),
+    "fhe_b200_bsk2_to_fourier": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, _vp]),
+    "fhe_b200_pbs_mb2": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "fhe_b200_ksk_to_32": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, _vp]),
     "fhe_b200_keyswitch32": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp]),
     "fhe_b200_pbs": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),

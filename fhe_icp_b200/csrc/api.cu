@@ -350,6 +350,48 @@ int fhe_b200_keyswitch(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const ui
     return FHE_B200_OK;
 }
 
+uint64_t fhe_b200_bsk2_words(const fhe_b200_pbs_params* p) {
+    return p ? (uint64_t)(p->n / 2) * 3 * (p->k + 1) * p->l_pbs * (uint64_t)(p->k + 1) * p->N : 0;
+}
+
+static int check_mb2_params(const fhe_b200_pbs_params* p, const char* fn) {
+    if (int r = check_pbs_params(p, fn)) return r;
+    if (p->l_pbs != 1 || (p->n & 1))
+        return fail(FHE_B200_ERR_INVALID, "%s: the multi-bit path needs l_pbs == 1 and an even n", fn);
+    return FHE_B200_OK;
+}
+
+int fhe_b200_bsk2_gen(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint8_t* d_s_small, const uint8_t* d_S_big,
+                      uint64_t evk_seed, uint64_t* d_bsk2, void* stream) {
+    REQUIRE(ctx && d_S_big && d_s_small && d_bsk2, "null argument");
+    if (int r = check_mb2_params(p, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_bsk2_gen(*p, d_s_small, d_S_big, evk_seed, d_bsk2, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_bsk2_to_fourier(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint64_t* d_bsk2, double* d_bskf2,
+                             void* stream) {
+    REQUIRE(ctx && d_bsk2 && d_bskf2, "null argument");
+    if (int r = check_mb2_params(p, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_bsk2_to_fourier(*p, d_bsk2, d_bskf2, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_pbs_mb2(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_bskf2, const uint64_t* d_in,
+                     int64_t B, const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_bskf2 && d_in && d_luts && d_out, "null device pointer");
+    if (int r = check_mb2_params(p, __func__)) return r;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_pbs_mb2(*p, d_bskf2, d_in, B, d_luts, d_lut_index, d_out, ctx->prop.multiProcessorCount,
+                           (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 int fhe_b200_ksk_to_32(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint64_t* d_ksk, uint32_t* d_ksk32,
                        void* stream) {
     REQUIRE(ctx && d_ksk && d_ksk32, "null argument");

@@ -42,6 +42,9 @@ cudaError_t launch_ksk_gen(const fhe_b200_pbs_params& p, const uint8_t* d_S_big,
 cudaError_t launch_bsk_gen(const fhe_b200_pbs_params& p, const uint8_t* d_s_small, const uint8_t* d_S_big,
                            uint64_t evk_seed, uint64_t* d_bsk, cudaStream_t s);
 
+cudaError_t launch_bsk2_gen(const fhe_b200_pbs_params& p, const uint8_t* d_s_small, const uint8_t* d_S_big,
+                            uint64_t evk_seed, uint64_t* d_bsk2, cudaStream_t s);
+
 // keyswitch.cu
 cudaError_t launch_keyswitch(const fhe_b200_pbs_params& p, const uint64_t* d_ksk, const uint64_t* d_in, int64_t B,
                              uint64_t* d_out, cudaStream_t s);
@@ -56,6 +59,10 @@ cudaError_t launch_bsk_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* 
 cudaError_t launch_pbs(const fhe_b200_pbs_params& p, const double* d_bskf, const uint64_t* d_in, int64_t B,
                        const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
                        cudaStream_t s);
+cudaError_t launch_bsk2_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* d_bsk2, double* d_bskf2, cudaStream_t s);
+cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
+                           const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
+                           cudaStream_t s);
 bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why);
 
 // probe.cu

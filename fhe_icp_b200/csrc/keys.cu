@@ -46,28 +46,39 @@ constexpr int BSK_THREADS = 256;
 
 __global__ void __launch_bounds__(BSK_THREADS)
 bsk_gen_kernel(const uint8_t* __restrict__ s_small, const uint8_t* __restrict__ S_big, int k, int N, int l, int beta,
-               double sigma_abs, uint64_t evk_seed, uint64_t* __restrict__ bsk) {
+               double sigma_abs, uint64_t evk_seed, int group, uint32_t purpose, uint64_t* __restrict__ bsk) {
     extern __shared__ uint64_t sm[];  // A[N] then S bits [N/32 words]
     uint64_t* A = sm;
     uint32_t* Sb = reinterpret_cast<uint32_t*>(sm + N);
+    // group == 1: row R = (i*(k+1)+t)*l+lev encrypts s_i.  group == 3 (multi-bit, pairs of key bits):
+    // R = ((i*3+g)*(k+1)+t)*l+lev encrypts s_2i*s_2i+1, s_2i*(1-s_2i+1), (1-s_2i)*s_2i+1 for g = 0,1,2.
     const int64_t R = blockIdx.x;
     const int lev = (int)(R % l);
     const int t = (int)((R / l) % (k + 1));
-    const int i = (int)(R / ((int64_t)l * (k + 1)));
+    const int64_t ig = R / ((int64_t)l * (k + 1));
+    const int g = (int)(ig % group);
+    const int i = (int)(ig / group);
+    int bit;
+    if (group == 1) {
+        bit = s_small[i] & 1;
+    } else {
+        const int sa = s_small[2 * i] & 1, sb = s_small[2 * i + 1] & 1;
+        bit = g == 0 ? (sa & sb) : (g == 1 ? (sa & (1 - sb)) : ((1 - sa) & sb));
+    }
     uint64_t* row = bsk + (size_t)R * (k + 1) * N;
     constexpr int PER = 16;  // coefficients per thread, N <= BSK_THREADS * PER
     uint64_t body[PER];
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int x = threadIdx.x + u * BSK_THREADS;
-        body[u] = x < N ? (uint64_t)gaussian_i64(evk_seed, FHE_B200_KIND_NOISE | (FHE_B200_PUR_BSK << 8), (uint64_t)R,
+        body[u] = x < N ? (uint64_t)gaussian_i64(evk_seed, FHE_B200_KIND_NOISE | (purpose << 8), (uint64_t)R,
                                                  (uint32_t)x, sigma_abs)
                         : 0;
     }
     for (int c = 0; c < k; ++c) {
         __syncthreads();
         for (int x = threadIdx.x; x < N; x += BSK_THREADS) {
-            uint64_t a = mask_word(evk_seed, FHE_B200_PUR_BSK, (uint64_t)R, (int64_t)c * N + x);
+            uint64_t a = mask_word(evk_seed, purpose, (uint64_t)R, (int64_t)c * N + x);
             A[x] = a;
             row[(size_t)c * N + x] = a;
         }
@@ -91,19 +102,19 @@ bsk_gen_kernel(const uint8_t* __restrict__ s_small, const uint8_t* __restrict__ 
             }
         }
     }
-    const uint64_t g = (uint64_t)(s_small[i] & 1u) << (64 - beta * (lev + 1));
+    const uint64_t gd = (uint64_t)bit << (64 - beta * (lev + 1));
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int x = threadIdx.x + u * BSK_THREADS;
         if (x < N) {
             uint64_t v = body[u];
-            if (t == k && x == 0) v += g;
+            if (t == k && x == 0) v += gd;
             row[(size_t)k * N + x] = v;
         }
     }
     if (t < k) {
         __syncthreads();  // mask polynomials of this row are all written by this block
-        if (threadIdx.x == 0) row[(size_t)t * N] += g;
+        if (threadIdx.x == 0) row[(size_t)t * N] += gd;
     }
 }
 
@@ -113,7 +124,18 @@ cudaError_t launch_bsk_gen(const fhe_b200_pbs_params& p, const uint8_t* d_s_smal
     const int64_t rows = (int64_t)p.n * (p.k + 1) * p.l_pbs;
     size_t smem = (size_t)p.N * 8 + (size_t)p.N / 8;
     bsk_gen_kernel<<<(unsigned)rows, BSK_THREADS, smem, s>>>(d_s_small, d_S_big, p.k, p.N, p.l_pbs, p.beta_pbs,
-                                                            p.sigma_glwe_abs, evk_seed, d_bsk);
+                                                            p.sigma_glwe_abs, evk_seed, 1, FHE_B200_PUR_BSK, d_bsk);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bsk2_gen(const fhe_b200_pbs_params& p, const uint8_t* d_s_small, const uint8_t* d_S_big,
+                            uint64_t evk_seed, uint64_t* d_bsk2, cudaStream_t s) {
+    if (p.N > BSK_THREADS * 16 || (p.n & 1)) return cudaErrorInvalidValue;
+    const int64_t rows = (int64_t)(p.n / 2) * 3 * (p.k + 1) * p.l_pbs;
+    size_t smem = (size_t)p.N * 8 + (size_t)p.N / 8;
+    bsk_gen_kernel<<<(unsigned)rows, BSK_THREADS, smem, s>>>(d_s_small, d_S_big, p.k, p.N, p.l_pbs, p.beta_pbs,
+                                                            p.sigma_glwe_abs, evk_seed, 3, FHE_B200_PUR_BSK2, d_bsk2);
     count_launch();
     return cudaGetLastError();
 }

@@ -32,7 +32,8 @@ constexpr int PBS_M = nfft::M;
 constexpr int PBS_TILE = nfft::TILE_ELEMS;  // padded transpose tile / twiddle table, in complex elements
 
 // ------------------------------------------------------------------------------- twiddle tables
-static cplx* g_tw = nullptr;  // [PBS_TILE] row-padded inter-pass twiddles (per device)
+constexpr int PBS_OMEGA = 128;  // two-level table of omega = exp(2*pi*i/4096): [0,64) omega^x, [64,128) omega^(64*y)
+static cplx* g_tw = nullptr;  // [PBS_TILE] row-padded inter-pass twiddles + [PBS_OMEGA] (per device)
 static int g_tw_device = -1;
 static std::mutex g_tw_mu;
 
@@ -42,8 +43,15 @@ static cudaError_t get_tables(const cplx** tw) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (g_tw == nullptr || g_tw_device != dev) {
-        static cplx h[PBS_TILE];
+        static cplx h[PBS_TILE + PBS_OMEGA];
         nfft::fill_twiddle_table(h);
+        for (int x = 0; x < 64; ++x) {
+            const long double two_pi = 6.283185307179586476925286766559005768L;
+            h[PBS_TILE + x].x = (double)cosl(two_pi * x / 4096.0L);
+            h[PBS_TILE + x].y = (double)sinl(two_pi * x / 4096.0L);
+            h[PBS_TILE + 64 + x].x = (double)cosl(two_pi * (64 * x) / 4096.0L);
+            h[PBS_TILE + 64 + x].y = (double)sinl(two_pi * (64 * x) / 4096.0L);
+        }
         cplx* d = nullptr;
         if ((e = cudaMalloc(&d, sizeof(h))) != cudaSuccess) return e;
         if ((e = cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
@@ -614,6 +622,316 @@ static cudaError_t launch_pbs_tmem_t(const fhe_b200_pbs_params& p, const cplx* b
     pbs_kernel_tmem<NCT><<<grid, NCT * 64, smem, s>>>(bskf, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tw, d_out);
     count_launch();
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------- multi-bit blind rotation (grouping 2)
+// One CMux consumes TWO key bits: ACC += sum_g (X^{e_g} - 1) * (G_g [.] ACC), g = 1..3, with
+// G1 = GGSW(s_a s_b), G2 = GGSW(s_a(1-s_b)), G3 = GGSW((1-s_a)s_b) and e = (a~_a + a~_b, a~_a, a~_b).
+// ACC is decomposed and transformed once per pair and the monomials are applied in the Fourier domain
+// (X^e at bin k is rho_k^e = omega^((4k+1)e)), so a pair costs one forward and one inverse FFT per
+// polynomial instead of two of each, at the price of 3 key elements per pair (73 MB key, L2-resident).
+// The key is stored sliced by frequency block k1 (6 KB per slice: [g][t'][c][32 bins]) and streamed
+// through an 8-slice shared-memory ring by TMA while the warps walk k1 = 0..31.
+constexpr int MB2_SLICES = 8;
+constexpr int MB2_LAG = 2;                       // refill a ring slot this many slices after warp 0 left it
+constexpr int MB2_SLICE_ELEMS = 3 * 2 * 2 * 32;  // complex elements per slice
+struct PbsMb2Smem {
+    static constexpr size_t tw_bytes = (size_t)PBS_TILE * 16;
+    static constexpr size_t ring_bytes = (size_t)MB2_SLICES * MB2_SLICE_ELEMS * 16;
+    static constexpr size_t omega_bytes = (size_t)PBS_OMEGA * 16;
+    static constexpr size_t bar_bytes = 256;
+    static constexpr size_t head_bytes = tw_bytes + ring_bytes + omega_bytes + bar_bytes;
+    static constexpr size_t tile_bytes = (size_t)2 * PBS_TILE * 16;
+    __host__ __device__ static size_t per_ct(int n) { return tile_bytes + (((size_t)(n + 1) * 2 + 127) & ~(size_t)127); }
+    static size_t total(int n, int nct) { return head_bytes + (size_t)nct * per_ct(n); }
+};
+
+template <int NCT>
+__global__ void __launch_bounds__(NCT * 64, 1)
+pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
+               const uint64_t* __restrict__ luts, const int32_t* __restrict__ lut_index,
+               const cplx* __restrict__ g_tw, uint64_t* __restrict__ out) {
+    using S = PbsMb2Smem;
+    constexpr int POLYS = 2;
+    constexpr uint32_t TMEM_COLS = NCT <= 2 ? 128 : 256;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* tw = reinterpret_cast<cplx*>(smem_raw);
+    cplx* ring = reinterpret_cast<cplx*>(smem_raw + S::tw_bytes);
+    cplx* omega = reinterpret_cast<cplx*>(smem_raw + S::tw_bytes + S::ring_bytes);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + S::tw_bytes + S::ring_bytes + S::omega_bytes);
+    uint64_t* bar_empty = bar_full + MB2_SLICES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_empty + MB2_SLICES);
+    for (int i = threadIdx.x; i < PBS_TILE; i += blockDim.x) tw[i] = g_tw[i];
+    for (int i = threadIdx.x; i < PBS_OMEGA; i += blockDim.x) omega[i] = g_tw[PBS_TILE + i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < MB2_SLICES; ++q) { mbar_init(&bar_full[q], 1); mbar_init(&bar_empty[q], NCT * POLYS); }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+    constexpr uint32_t SLICE_BYTES = (uint32_t)(MB2_SLICE_ELEMS * 16);
+    const int pairs = n >> 1;
+    const int total_slices = pairs * 32;
+
+    const int ctl = warp / POLYS, t = warp - ctl * POLYS;
+    const int64_t b = (int64_t)blockIdx.x * NCT + ctl;
+    unsigned char* base = smem_raw + S::head_bytes + (size_t)ctl * S::per_ct(n);
+    cplx* tile_all = reinterpret_cast<cplx*>(base);
+    uint16_t* a_tilde = reinterpret_cast<uint16_t*>(base + S::tile_bytes);
+    cplx* tile = tile_all + (size_t)t * PBS_TILE;
+    const cplx* tile_other = tile_all + (size_t)(1 - t) * PBS_TILE;
+    const bool live = b < B;
+    const int bar_id = 1 + ctl, bar_n = POLYS * 32;
+
+    // ---- prologue: mod-switch the mask, ACC = X^(-b~) * (0, LUT) into TMEM (lo words | hi words)
+    const uint64_t* ct = in + (size_t)(live ? b : 0) * (n + 1);
+    for (int i = t * 32 + lane; i <= n; i += POLYS * 32)
+        a_tilde[i] = (uint16_t)((((ct[i] >> 51) + 1) >> 1) & 4095);
+    named_bar_sync(bar_id, bar_n);
+    {
+        const uint64_t* lut = luts + (size_t)(lut_index && live ? lut_index[b] : 0) * PBS_N;
+        const int rot = (4096 - (int)a_tilde[n]) & 4095;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t rl[16], rh[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int q = 16 * c + u;
+                const int x = lane + 32 * (q & 31) + (q >> 5) * PBS_M;
+                uint64_t v = 0;
+                if (t == 1) {
+                    const int src = (x - rot) & 4095;
+                    v = lut[src & 2047];
+                    if (src & 2048) v = 0 - v;
+                }
+                rl[u] = (uint32_t)v;
+                rh[u] = (uint32_t)(v >> 32);
+            }
+            tmem_st_x16(tacc + 16 * c, rl);
+            tmem_st_x16(tacc + 64 + 16 * c, rh);
+        }
+        tmem_wait_st();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // fill the ring
+        for (int q = 0; q < MB2_SLICES && q < total_slices; ++q) {
+            mbar_expect_tx(&bar_full[q], SLICE_BYTES);
+            tma_load_1d(ring + (size_t)q * MB2_SLICE_ELEMS, bskf2 + (size_t)q * MB2_SLICE_ELEMS, SLICE_BYTES, &bar_full[q]);
+        }
+    }
+
+    const uint32_t rnd32 = 1u << (31 - beta);
+    const int dshift = 32 - beta;
+    double re[32], im[32];
+    for (int i = 0; i < pairs; ++i) {
+        // ---- digits of ACC_t itself (no rotation in the coefficient domain): high words from TMEM
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t h0[16], h1[16];
+            tmem_ld_x16(tacc + 64 + 16 * c, h0);
+            tmem_ld_x16(tacc + 96 + 16 * c, h1);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                re[16 * c + u] = (double)((int32_t)(h0[u] + rnd32) >> dshift);
+                im[16 * c + u] = (double)((int32_t)(h1[u] + rnd32) >> dshift);
+            }
+        }
+        nfft::fwd_phase1(re, im, tw, tile, lane);
+        __syncwarp();
+        nfft::fwd_phase2(re, im, tile, lane);
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            cplx v;
+            v.x = re[p];
+            v.y = im[p];
+            tile[nfft::brev5(p) * 32 + lane] = v;
+        }
+        // ---- monomials at this lane's bins: rho_k^e = omega^((4*lane+1)*e) * (omega^(128*e))^k1
+        const int ea = a_tilde[2 * i], eb = a_tilde[2 * i + 1];
+        double mx[3], my[3], rx[3], ry[3];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            const int e = g == 0 ? ((ea + eb) & 4095) : (g == 1 ? ea : eb);
+            const int E = (e * (4 * lane + 1)) & 4095;
+            const cplx hi = omega[64 + (E >> 6)], lo = omega[E & 63];
+            mx[g] = hi.x * lo.x - hi.y * lo.y;
+            my[g] = hi.x * lo.y + hi.y * lo.x;
+            const cplx r = omega[64 + (((128 * e) & 4095) >> 6)];
+            rx[g] = r.x;
+            ry[g] = r.y;
+        }
+        named_bar_sync(bar_id, bar_n);  // (A) both polynomials' Fourier digits are visible
+        // ---- walk the frequency blocks: out[bin] = sum_g (rho^e_g - 1) * (F_t * G_g[t][t] + F_t' * G_g[t'][t])
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) {
+            const int sidx = i * 32 + k1;
+            const int slot = sidx % MB2_SLICES;
+            mbar_wait(&bar_full[slot], (uint32_t)((sidx / MB2_SLICES) & 1));
+            const cplx* sl = ring + (size_t)slot * MB2_SLICE_ELEMS;
+            const int p = nfft::brev5(k1);
+            const cplx fo = tile_other[k1 * 32 + lane];
+            const double ax = re[p], ay = im[p];
+            double ox = 0.0, oy = 0.0;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const cplx bt = sl[((g * 2 + t) * 2 + t) * 32 + lane];
+                const cplx bo = sl[((g * 2 + (1 - t)) * 2 + t) * 32 + lane];
+                const double ix = ax * bt.x - ay * bt.y + (fo.x * bo.x - fo.y * bo.y);
+                const double iy = ax * bt.y + ay * bt.x + (fo.x * bo.y + fo.y * bo.x);
+                const double cx = mx[g] - 1.0, cy = my[g];
+                ox += cx * ix - cy * iy;
+                oy += cx * iy + cy * ix;
+                const double nx = mx[g] * rx[g] - my[g] * ry[g];
+                my[g] = mx[g] * ry[g] + my[g] * rx[g];
+                mx[g] = nx;
+            }
+            re[p] = ox;
+            im[p] = oy;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[slot]);
+            if (threadIdx.x == 0) {  // keep the ring full: refill the slot warp 0 left MB2_LAG slices ago
+                const int done = sidx - MB2_LAG;
+                const int next = done + MB2_SLICES;
+                if (done >= 0 && next < total_slices) {
+                    const int ds = done % MB2_SLICES;
+                    mbar_wait(&bar_empty[ds], (uint32_t)((done / MB2_SLICES) & 1));
+                    mbar_expect_tx(&bar_full[ds], SLICE_BYTES);
+                    tma_load_1d(ring + (size_t)ds * MB2_SLICE_ELEMS, bskf2 + (size_t)next * MB2_SLICE_ELEMS, SLICE_BYTES,
+                                &bar_full[ds]);
+                }
+            }
+        }
+        named_bar_sync(bar_id, bar_n);  // (B) nobody reads the published digits any more
+        nfft::inv_phase1(re, im, tw, tile, lane);
+        __syncwarp();
+        nfft::inv_phase2(re, im, tile, lane);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t rl[16], rh[16];
+            tmem_ld_x16(tacc + 16 * c, rl);
+            tmem_ld_x16(tacc + 64 + 16 * c, rh);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int q = 16 * c + u;
+                const uint64_t v = (((uint64_t)rh[u] << 32) | rl[u]) + f64_to_torus(c < 2 ? re[q] : im[q - 32]);
+                rl[u] = (uint32_t)v;
+                rh[u] = (uint32_t)(v >> 32);
+            }
+            tmem_st_x16(tacc + 16 * c, rl);
+            tmem_st_x16(tacc + 64 + 16 * c, rh);
+        }
+        tmem_wait_st();
+        __syncwarp();
+    }
+    // the tail slices (done > total - LAG) were never waited for by the producer; nothing is pending
+    if (live) {
+        uint64_t* o = out + (size_t)b * ((size_t)PBS_N + 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t rl[16], rh[16];
+            tmem_ld_x16(tacc + 16 * c, rl);
+            tmem_ld_x16(tacc + 64 + 16 * c, rh);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int q = 16 * c + u;
+                const int x = lane + 32 * (q & 31) + (q >> 5) * PBS_M;
+                const uint64_t v = ((uint64_t)rh[u] << 32) | rl[u];
+                if (t == 0) {
+                    if (x == 0) o[0] = v;
+                    else o[PBS_N - x] = 0 - v;
+                } else if (x == 0) {
+                    o[PBS_N] = v;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// standard-domain bsk2 [pairs][3][2][1][2][N] -> Fourier, sliced: [pairs][32][3][2][2][32]
+__global__ void __launch_bounds__(B2F_WARPS * 32)
+bsk2_to_fourier_kernel(const uint64_t* __restrict__ bsk2, int64_t polys, const cplx* __restrict__ g_twf,
+                       cplx* __restrict__ bskf2) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* twf = reinterpret_cast<cplx*>(smem_raw);
+    cplx* bufs = twf + PBS_TILE;
+    for (int i = threadIdx.x; i < PBS_TILE; i += blockDim.x) twf[i] = g_twf[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * B2F_WARPS + warp;   // q = ((i*3+g)*2+t)*2+c
+    if (q >= polys) return;
+    cplx* buf = bufs + warp * PBS_TILE;
+    const uint64_t* src = bsk2 + (size_t)q * PBS_N;
+    double re[32], im[32];
+#pragma unroll
+    for (int j2 = 0; j2 < 32; ++j2) {
+        re[j2] = (double)(int64_t)src[lane + 32 * j2];
+        im[j2] = (double)(int64_t)src[lane + 32 * j2 + PBS_M];
+    }
+    nfft::fwd_phase1(re, im, twf, buf, lane);
+    __syncwarp();
+    nfft::fwd_phase2(re, im, buf, lane);
+    const int c = (int)(q & 1), tt = (int)((q >> 1) & 1);
+    const int64_t ig = q >> 2;
+    const int g = (int)(ig % 3);
+    const int64_t i = ig / 3;
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        const int k1 = nfft::brev5(p);
+        cplx v;
+        v.x = re[p];
+        v.y = im[p];
+        bskf2[((size_t)(i * 32 + k1) * 12 + (size_t)((g * 2 + tt) * 2 + c)) * 32 + lane] = v;
+    }
+}
+
+cudaError_t launch_bsk2_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* d_bsk2, double* d_bskf2, cudaStream_t s) {
+    const cplx* twf;
+    cudaError_t e = get_tables(&twf);
+    if (e != cudaSuccess) return e;
+    if (p.k != 1 || p.l_pbs != 1 || (p.n & 1)) return cudaErrorInvalidValue;
+    const int64_t polys = (int64_t)(p.n / 2) * 3 * 2 * 2;
+    const size_t smem = sizeof(cplx) * PBS_TILE * (1 + B2F_WARPS);
+    e = cudaFuncSetAttribute(bsk2_to_fourier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bsk2_to_fourier_kernel<<<(unsigned)((polys + B2F_WARPS - 1) / B2F_WARPS), B2F_WARPS * 32, smem, s>>>(
+        d_bsk2, polys, twf, reinterpret_cast<cplx*>(d_bskf2));
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int NCT>
+static cudaError_t launch_pbs_mb2_t(const fhe_b200_pbs_params& p, const cplx* bskf2, const uint64_t* d_in, int64_t B,
+                                    const uint64_t* d_luts, const int32_t* d_lut_index, const cplx* tw, uint64_t* d_out,
+                                    cudaStream_t s) {
+    const size_t smem = PbsMb2Smem::total(p.n, NCT);
+    cudaError_t e = cudaFuncSetAttribute(pbs_kernel_mb2<NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((B + NCT - 1) / NCT);
+    pbs_kernel_mb2<NCT><<<grid, NCT * 64, smem, s>>>(bskf2, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tw, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
+                           const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
+                           cudaStream_t s) {
+    if (p.k != 1 || p.l_pbs != 1 || (p.n & 1) || p.N != PBS_N) return cudaErrorInvalidValue;
+    const cplx* tw;
+    cudaError_t e = get_tables(&tw);
+    if (e != cudaSuccess) return e;
+    const cplx* bskf2 = reinterpret_cast<const cplx*>(d_bskf2);
+    if (B <= (int64_t)sm_count) return launch_pbs_mb2_t<1>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    if (B <= 2 * (int64_t)sm_count) return launch_pbs_mb2_t<2>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    return launch_pbs_mb2_t<4>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
 }
 
 bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why) {

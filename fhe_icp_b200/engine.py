@@ -228,6 +228,42 @@ def pbs(p: N.PBSParams, bskf: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor
     return out
 
 
+# ---- multi-bit blind rotation (two key bits per CMux)
+def bsk2_gen(p: N.PBSParams, s_small: torch.Tensor, S_big: torch.Tensor, evk_seed: int) -> torch.Tensor:
+    dev = S_big.device
+    bsk2 = torch.empty((p.n // 2, 3, p.k + 1, p.l_pbs, p.k + 1, p.N), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_bsk2_gen(_ctx(dev).handle, C.byref(p), _ptr(s_small), _ptr(S_big), evk_seed,
+                                      _ptr(bsk2), _stream(dev)))
+    return bsk2
+
+
+def bsk2_to_fourier(p: N.PBSParams, bsk2: torch.Tensor) -> torch.Tensor:
+    """-> [n/2][32 frequency blocks][3][k+1][k+1][32][2] f64 (the sliced layout the kernel streams)."""
+    dev = bsk2.device
+    bskf2 = torch.empty((p.n // 2, 32, 3, p.k + 1, p.k + 1, 32, 2), dtype=torch.float64, device=dev)
+    N.check(N.lib().fhe_b200_bsk2_to_fourier(_ctx(dev).handle, C.byref(p), _ptr(bsk2.contiguous()), _ptr(bskf2),
+                                             _stream(dev)))
+    return bskf2
+
+
+def pbs_mb2(p: N.PBSParams, bskf2: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor,
+            lut_index: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    dev = ct.device
+    ct = ct.contiguous()
+    B = ct.shape[0]
+    assert ct.shape[1] == p.n + 1
+    luts = luts.to(device=dev, dtype=torch.int64).reshape(-1, p.N).contiguous()
+    if out is None:
+        out = torch.empty((B, p.k * p.N + 1), dtype=torch.int64, device=dev)
+    li = None
+    if lut_index is not None:
+        lut_index = lut_index.to(device=dev, dtype=torch.int32).contiguous()
+        li = _ptr(lut_index)
+    N.check(N.lib().fhe_b200_pbs_mb2(_ctx(dev).handle, C.byref(p), _ptr(bskf2), _ptr(ct), B, _ptr(luts), li, _ptr(out),
+                                     _stream(dev)))
+    return out
+
+
 def make_lut_poly(table, p_bits: int, N_poly: int, delta_out_log2: int) -> np.ndarray:
     """Accumulator polynomial of a p-bit table lookup (message + 1 padding bit): box m holds
     table[m] << delta_out_log2 and the polynomial is multiplied by X^(-box/2)."""

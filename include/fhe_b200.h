@@ -38,7 +38,7 @@ enum {
 
 /* RNG stream tags (DESIGN.md "Deterministic randomness") */
 enum { FHE_B200_KIND_SK = 1, FHE_B200_KIND_MASK = 2, FHE_B200_KIND_NOISE = 3 };
-enum { FHE_B200_PUR_INPUT = 0, FHE_B200_PUR_KSK = 1, FHE_B200_PUR_BSK = 2 };
+enum { FHE_B200_PUR_INPUT = 0, FHE_B200_PUR_KSK = 1, FHE_B200_PUR_BSK = 2, FHE_B200_PUR_BSK2 = 3 };
 
 typedef struct fhe_b200_ctx fhe_b200_ctx;
 typedef struct fhe_b200_similarity fhe_b200_similarity;
@@ -150,6 +150,18 @@ int fhe_b200_bsk_to_fourier(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p,
                             const uint64_t *d_bsk, double *d_bskf, void *stream);
 int fhe_b200_keyswitch(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_ksk,
                        const uint64_t *d_in, int64_t B, uint64_t *d_out, void *stream);
+/* Multi-bit blind rotation, grouping factor 2 (two key bits per CMux, one gadget decomposition and one
+ * FFT round trip per pair; n even, k = 1, l_pbs = 1).  bsk2 standard domain: [n/2][3][k+1][l][k+1][N] u64;
+ * Fourier domain: [n/2][32 slices][3][k+1][k+1][32] complex f64 (sliced by frequency block so that the
+ * kernel streams it through a small shared-memory ring).  Same inputs / outputs as fhe_b200_pbs. */
+uint64_t fhe_b200_bsk2_words(const fhe_b200_pbs_params *p);
+int fhe_b200_bsk2_gen(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_s_small,
+                      const uint8_t *d_S_big, uint64_t evk_seed, uint64_t *d_bsk2, void *stream);
+int fhe_b200_bsk2_to_fourier(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_bsk2,
+                             double *d_bskf2, void *stream);
+int fhe_b200_pbs_mb2(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
+                     const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
+                     const int32_t *d_lut_index, uint64_t *d_out, void *stream);
 /* 32-bit keyswitch ("KS32"): key rounded to the top 32 torus bits, u32 accumulation; d_scratch32 holds
  * B*(n+1) u32 words; the result is written as u64 words with the low half zero. */
 int fhe_b200_ksk_to_32(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_ksk,

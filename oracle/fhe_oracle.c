@@ -570,6 +570,131 @@ void orc_pbs_batch(const orc_pbs_params *p, const double *bskf, const uint64_t *
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* Multi-bit blind rotation, grouping factor 2                          */
+/* (Bourse, Minelli, Minihold, Paillier 2018; TFHE-rs "multi-bit PBS").  */
+/* For the key-bit pair (s_a, s_b) = (s_{2i}, s_{2i+1}) the key holds    */
+/* G1 = GGSW(s_a s_b), G2 = GGSW(s_a (1-s_b)), G3 = GGSW((1-s_a) s_b)   */
+/* and one step is  ACC += sum_g (X^{e_g} - 1) * (G_g [.] ACC) with      */
+/* e1 = a~_a + a~_b, e2 = a~_a, e3 = a~_b  (exactly one G_g encrypts 1,  */
+/* or none): one gadget decomposition of ACC serves two key bits.        */
+/* bsk2[i][g][t][lev][c][N], rows drawn from purpose ORC_PUR_BSK2.       */
+/* ------------------------------------------------------------------ */
+void orc_bsk2_gen(const orc_pbs_params *p, const uint8_t *s_small, const uint8_t *S_big,
+                  uint64_t evk_seed, uint64_t *bsk2) {
+    int n = p->n, k = p->k, N = p->N, l = p->l_pbs, beta = p->beta_pbs;
+    int64_t rows = (int64_t)(n / 2) * 3 * (k + 1) * l;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t R = 0; R < rows; ++R) {
+        int lev = (int)(R % l);
+        int t = (int)((R / l) % (k + 1));
+        int g = (int)((R / ((int64_t)l * (k + 1))) % 3);
+        int i = (int)(R / ((int64_t)l * (k + 1) * 3));
+        int sa = s_small[2 * i], sb = s_small[2 * i + 1];
+        int bit = g == 0 ? (sa & sb) : (g == 1 ? (sa & (1 - sb)) : ((1 - sa) & sb));
+        uint64_t *row = bsk2 + (size_t)R * (k + 1) * N;
+        uint64_t *body = row + (size_t)k * N;
+        for (int x = 0; x < N; ++x)
+            body[x] = (uint64_t)orc_gaussian(evk_seed, ORC_KIND_NOISE | (ORC_PUR_BSK2 << 8),
+                                             (uint64_t)R, (uint32_t)x, p->sigma_glwe_abs);
+        for (int c = 0; c < k; ++c) {
+            uint64_t *A = row + (size_t)c * N;
+            for (int x = 0; x < N; ++x)
+                A[x] = mask_word(evk_seed, ORC_PUR_BSK2, (uint64_t)R, (int64_t)c * N + x);
+            const uint8_t *S = S_big + (size_t)c * N;
+            for (int y = 0; y < N; ++y) {
+                if (!S[y]) continue;
+                for (int x = 0; x < N - y; ++x) body[x + y] += A[x];
+                for (int x = N - y; x < N; ++x) body[x + y - N] -= A[x];
+            }
+        }
+        if (bit) row[(size_t)t * N] += 1ULL << (64 - beta * (lev + 1));
+    }
+}
+
+/* bskf2[i][g][t][lev][c][M] complex, natural bins (oracle layout; the GPU re-slices it) */
+void orc_bsk2_to_fourier(const orc_pbs_params *p, const uint64_t *bsk2, double *bskf2) {
+    orc_pbs_params q = *p;
+    q.n = (p->n / 2) * 3;  /* same per-polynomial transform, 3 GGSWs per pair */
+    orc_bsk_to_fourier(&q, bsk2, bskf2);
+}
+
+void orc_pbs_mb2_batch(const orc_pbs_params *p, const double *bskf2, const uint64_t *in, int64_t B,
+                       const uint64_t *luts, const int32_t *lut_index, uint64_t *out) {
+    int n = p->n, k = p->k, N = p->N, M = N / 2, l = p->l_pbs, beta = p->beta_pbs;
+    const fft_plan *pl = get_plan(N);
+    int log2N2 = 0;
+    while ((1 << log2N2) < 2 * N) ++log2N2;
+#pragma omp parallel
+    {
+        uint64_t *acc = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(k + 1) * N);
+        uint64_t *prod = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)N);
+        uint64_t *rot = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)N);
+        uint64_t *delta = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(k + 1) * N);
+        double *co = (double *)malloc(sizeof(double) * (size_t)N);
+        double *F = (double *)malloc(sizeof(double) * (size_t)(k + 1) * l * N);
+        double *O = (double *)malloc(sizeof(double) * (size_t)N);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t b = 0; b < B; ++b) {
+            const uint64_t *ct = in + (size_t)b * (n + 1);
+            const uint64_t *lut = luts + (size_t)(lut_index ? lut_index[b] : 0) * N;
+            int bt = (int)((((ct[n] >> (64 - log2N2 - 1)) + 1) >> 1) & (uint64_t)(2 * N - 1));
+            for (int c = 0; c < k; ++c) memset(acc + (size_t)c * N, 0, sizeof(uint64_t) * N);
+            rotate_poly(N, lut, (2 * N - bt) % (2 * N), acc + (size_t)k * N);
+            for (int i = 0; i < n / 2; ++i) {
+                int ea = (int)((((ct[2 * i] >> (64 - log2N2 - 1)) + 1) >> 1) & (uint64_t)(2 * N - 1));
+                int eb = (int)((((ct[2 * i + 1] >> (64 - log2N2 - 1)) + 1) >> 1) & (uint64_t)(2 * N - 1));
+                int e[3] = {(ea + eb) % (2 * N), ea, eb};
+                /* one decomposition of ACC for the pair */
+                for (int t = 0; t <= k; ++t) {
+                    const uint64_t *a = acc + (size_t)t * N;
+                    for (int lev = 0; lev < l; ++lev) {
+                        for (int x = 0; x < N; ++x) {
+                            int64_t dg[16];
+                            decompose(a[x], l, beta, dg);
+                            co[x] = (double)dg[lev];
+                        }
+                        double *f = F + ((size_t)t * l + lev) * N;
+                        nega_forward(pl, co, f, f + M);
+                    }
+                }
+                memset(delta, 0, sizeof(uint64_t) * (size_t)(k + 1) * N);
+                for (int g = 0; g < 3; ++g) {
+                    if (e[g] == 0) continue; /* X^0 - 1 = 0 */
+                    for (int c = 0; c <= k; ++c) {
+                        double *ore = O, *oim = O + M;
+                        for (int j = 0; j < M; ++j) { ore[j] = 0.0; oim[j] = 0.0; }
+                        for (int t = 0; t <= k; ++t)
+                            for (int lev = 0; lev < l; ++lev) {
+                                const double *f = F + ((size_t)t * l + lev) * N;
+                                const double *gk = bskf2 + (((((size_t)i * 3 + g) * (k + 1) + t) * l + lev) * (k + 1) + c) * N;
+                                for (int j = 0; j < M; ++j) {
+                                    double gr = gk[2 * j], gi = gk[2 * j + 1];
+                                    ore[j] += f[j] * gr - f[j + M] * gi;
+                                    oim[j] += f[j] * gi + f[j + M] * gr;
+                                }
+                            }
+                        memset(prod, 0, sizeof(uint64_t) * N);
+                        nega_inverse_add(pl, ore, oim, prod);          /* prod = (G_g [.] ACC)_c           */
+                        rotate_poly(N, prod, e[g], rot);                /* rot  = X^{e_g} * prod            */
+                        uint64_t *dl = delta + (size_t)c * N;
+                        for (int x = 0; x < N; ++x) dl[x] += rot[x] - prod[x];
+                    }
+                }
+                for (size_t x = 0; x < (size_t)(k + 1) * N; ++x) acc[x] += delta[x];
+            }
+            uint64_t *o = out + (size_t)b * ((size_t)k * N + 1);
+            for (int c = 0; c < k; ++c) {
+                const uint64_t *A = acc + (size_t)c * N;
+                o[(size_t)c * N] = A[0];
+                for (int x = 1; x < N; ++x) o[(size_t)c * N + x] = (uint64_t)0 - A[N - x];
+            }
+            o[(size_t)k * N] = acc[(size_t)k * N];
+        }
+        free(acc); free(prod); free(rot); free(delta); free(co); free(F); free(O);
+    }
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

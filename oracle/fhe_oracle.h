@@ -27,7 +27,7 @@ extern "C" {
 
 /* RNG domain tags (counter word c3 = kind | purpose << 8) -- the spec is in DESIGN.md */
 enum { ORC_KIND_SK = 1, ORC_KIND_MASK = 2, ORC_KIND_NOISE = 3 };
-enum { ORC_PUR_INPUT = 0, ORC_PUR_KSK = 1, ORC_PUR_BSK = 2 };
+enum { ORC_PUR_INPUT = 0, ORC_PUR_KSK = 1, ORC_PUR_BSK = 2, ORC_PUR_BSK2 = 3 };
 
 typedef struct {
     int32_t n;        /* small LWE dimension */
@@ -77,6 +77,11 @@ void orc_keyswitch32_batch(const orc_pbs_params *p, const uint32_t *ksk32, const
 void orc_modswitch_batch(const orc_pbs_params *p, const uint64_t *in, int64_t B, int32_t *out);
 void orc_pbs_batch(const orc_pbs_params *p, const double *bskf, const uint64_t *in, int64_t B,
                    const uint64_t *luts, const int32_t *lut_index, uint64_t *out);
+void orc_bsk2_gen(const orc_pbs_params *p, const uint8_t *s_small, const uint8_t *S_big,
+                  uint64_t evk_seed, uint64_t *bsk2);
+void orc_bsk2_to_fourier(const orc_pbs_params *p, const uint64_t *bsk2, double *bskf2);
+void orc_pbs_mb2_batch(const orc_pbs_params *p, const double *bskf2, const uint64_t *in, int64_t B,
+                       const uint64_t *luts, const int32_t *lut_index, uint64_t *out);
 void orc_negacyclic_mul_fft(int32_t N, const int64_t *a, const uint64_t *b, uint64_t *out);
 int orc_num_threads(void);
 void orc_set_num_threads(int t);

@@ -23,7 +23,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB = None
 
 KIND_SK, KIND_MASK, KIND_NOISE = 1, 2, 3
-PUR_INPUT, PUR_KSK, PUR_BSK = 0, 1, 2
+PUR_INPUT, PUR_KSK, PUR_BSK, PUR_BSK2 = 0, 1, 2, 3
 
 
 class PBSParams(C.Structure):
@@ -72,6 +72,9 @@ def lib() -> C.CDLL:
         L.orc_keyswitch32_batch.argtypes = [pp, u32p, u64p, C.c_int64, u64p]
         L.orc_modswitch_batch.argtypes = [pp, u64p, C.c_int64, i32p]
         L.orc_pbs_batch.argtypes = [pp, f64p, u64p, C.c_int64, u64p, i32p, u64p]
+        L.orc_bsk2_gen.argtypes = [pp, u8p, u8p, C.c_uint64, u64p]
+        L.orc_bsk2_to_fourier.argtypes = [pp, u64p, f64p]
+        L.orc_pbs_mb2_batch.argtypes = [pp, f64p, u64p, C.c_int64, u64p, i32p, u64p]
         L.orc_negacyclic_mul_fft.argtypes = [C.c_int32, i64p, u64p, u64p]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
@@ -221,6 +224,35 @@ def pbs(p: PBSParams, bskf, ct, luts, lut_index=None) -> np.ndarray:
         li = _p(lut_index, C.c_int32)
     lib().orc_pbs_batch(C.byref(p), _p(bskf, C.c_double), _p(ct, C.c_uint64), B, _p(luts, C.c_uint64), li,
                         _p(out, C.c_uint64))
+    return out
+
+
+def bsk2_gen(p: PBSParams, s_small, S_big, evk_seed: int) -> np.ndarray:
+    """Multi-bit (grouping factor 2) bootstrapping key: [n/2][3][k+1][l][k+1][N] u64."""
+    S_big = np.ascontiguousarray(S_big, dtype=np.uint8); s_small = np.ascontiguousarray(s_small, dtype=np.uint8)
+    out = np.zeros((p.n // 2, 3, p.k + 1, p.l_pbs, p.k + 1, p.N), dtype=np.uint64)
+    lib().orc_bsk2_gen(C.byref(p), _p(s_small, C.c_uint8), _p(S_big, C.c_uint8), evk_seed, _p(out, C.c_uint64))
+    return out
+
+
+def bsk2_to_fourier(p: PBSParams, bsk2) -> np.ndarray:
+    bsk2 = np.ascontiguousarray(bsk2, dtype=np.uint64)
+    out = np.zeros((p.n // 2, 3, p.k + 1, p.l_pbs, p.k + 1, p.N // 2, 2), dtype=np.float64)
+    lib().orc_bsk2_to_fourier(C.byref(p), _p(bsk2, C.c_uint64), _p(out, C.c_double))
+    return out
+
+
+def pbs_mb2(p: PBSParams, bskf2, ct, luts, lut_index=None) -> np.ndarray:
+    ct = np.ascontiguousarray(ct, dtype=np.uint64); bskf2 = np.ascontiguousarray(bskf2, dtype=np.float64)
+    luts = np.ascontiguousarray(np.atleast_2d(luts), dtype=np.uint64)
+    B = ct.shape[0]
+    out = np.zeros((B, p.k * p.N + 1), dtype=np.uint64)
+    li = None
+    if lut_index is not None:
+        lut_index = np.ascontiguousarray(lut_index, dtype=np.int32)
+        li = _p(lut_index, C.c_int32)
+    lib().orc_pbs_mb2_batch(C.byref(p), _p(bskf2, C.c_double), _p(ct, C.c_uint64), B, _p(luts, C.c_uint64), li,
+                            _p(out, C.c_uint64))
     return out
 
 

@@ -204,3 +204,47 @@ def test_pbs_large_batch_wide_kernel(O, p4, cuda_dev):
     table = (np.arange(16) * 11 + 5) % 16
     out = E.pbs(K.p, K.bskf, ct, E.from_u64_numpy(E.make_lut_poly(table, 4, K.p.N, 59), cuda_dev))
     assert np.array_equal(O.lwe_decrypt(K.oS, _u64(out), 59) & 15, table[msgs])
+
+
+class KeysMB2:
+    def __init__(self, O, dev, d, key_seed=11, evk_seed=22):
+        from fhe_icp_b200 import engine as E
+        self.p = E.make_pbs_params(**d)
+        self.op = _oparams(O, d)
+        self.s = E.secret_key(key_seed, 0, d["n"], dev)
+        self.S = E.secret_key(key_seed, 1, d["N_poly"], dev)
+        self.os, self.oS = O.secret_key(key_seed, 0, d["n"]), O.secret_key(key_seed, 1, d["N_poly"])
+        self.bsk2 = E.bsk2_gen(self.p, self.s, self.S, evk_seed)
+        self.bskf2 = E.bsk2_to_fourier(self.p, self.bsk2)
+        self.evk_seed = evk_seed
+
+
+@pytest.mark.parametrize("which,B", [("toy", 16), ("toy", 3), ("p4", 16), ("p4", 2 * 148 + 5)])
+def test_multibit_pbs(O, cuda_dev, which, B):
+    """Multi-bit blind rotation (two key bits per CMux): key bit-exact vs the oracle, every message
+    maps to LUT[m], phases agree with the oracle's multi-bit evaluation within the PBS noise bound."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    d = TOY if which == "toy" else P4
+    K = KeysMB2(O, cuda_dev, d)
+    obsk2 = O.bsk2_gen(K.op, K.os, K.oS, K.evk_seed)
+    assert np.array_equal(_u64(K.bsk2), obsk2)
+    of = O.bsk2_to_fourier(K.op, obsk2)                     # [i][g][t][l][c][M][2]
+    gf = K.bskf2.cpu().numpy()                              # [i][k1][g][t][c][32][2]
+    ref_sliced = of[:, :, :, 0].reshape(of.shape[0], 3, 2, 2, 32, 32, 2).transpose(0, 4, 1, 2, 3, 5, 6)
+    assert np.abs(gf - ref_sliced).max() / np.abs(of).max() < 1e-13
+    rng = np.random.RandomState(B)
+    msgs = rng.randint(0, 16, size=B)
+    msgs[: min(B, 16)] = np.arange(16)[: min(B, 16)]
+    ct = E.lwe_encrypt(K.s, torch.as_tensor(msgs), 59, K.op.sigma_lwe_abs, enc_seed=B, ct_base=100,
+                       stride=K.p.n + 2 - (K.p.n % 2))[:, : K.p.n + 1].contiguous()
+    table = (np.arange(16) * 5 + 2) % 16
+    lut = E.make_lut_poly(table, 4, K.p.N, 59)
+    out = E.pbs_mb2(K.p, K.bskf2, ct, E.from_u64_numpy(lut, cuda_dev))
+    got = _u64(out)
+    assert np.array_equal(O.lwe_decrypt(K.oS, got, 59) & 15, table[msgs])
+    ref = O.pbs_mb2(K.op, of, _u64(ct)[: min(B, 32)], lut)
+    diff = (O.lwe_phase(K.oS, got[: min(B, 32)]) - O.lwe_phase(K.oS, ref)).view(np.int64).astype(np.float64)
+    assert np.log2(np.abs(diff).max() + 1) - 64 < -12
+    err = (O.lwe_phase(K.oS, got) - (table[msgs].astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
+    assert np.log2(err.std() + 1) - 64 < -13.5

@@ -20,10 +20,19 @@ msgs = np.random.RandomState(0).randint(0, 16, size=B)
 ct_big = E.lwe_encrypt(S, torch.as_tensor(msgs), 59, p.sigma_glwe_abs, enc_seed=303, stride=p.N + 2)[:, : p.N + 1].contiguous()
 ct = E.keyswitch(p, ksk, ct_big)
 out = torch.empty((B, p.N + 1), dtype=torch.int64, device=dev)
+import os
+MB2 = os.environ.get("PBS_MB2", "0") == "1"
+if MB2:
+    bskf2 = E.bsk2_to_fourier(p, E.bsk2_gen(p, s, S, 202))
 for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); E.pbs(p, bskf, ct, lut, out=out); e1.record(); torch.cuda.synchronize()
-    print(f"B={B} pbs {e0.elapsed_time(e1):.3f} ms -> {B / e0.elapsed_time(e1) * 1e3:.0f} PBS/s")
+    e0.record()
+    if MB2:
+        E.pbs_mb2(p, bskf2, ct, lut, out=out)
+    else:
+        E.pbs(p, bskf, ct, lut, out=out)
+    e1.record(); torch.cuda.synchronize()
+    print(f"B={B} {'mb2' if MB2 else 'pbs'} {e0.elapsed_time(e1):.3f} ms -> {B / e0.elapsed_time(e1) * 1e3:.0f} PBS/s")
 z = torch.zeros((B, p.N + 2), dtype=torch.int64, device=dev); z[:, : p.N + 1] = out
 dec = E.lwe_decrypt(S, z, 59).cpu().numpy() & 15
 print("correct:", bool(np.array_equal(dec, table[msgs])))
