@@ -630,11 +630,13 @@ static cudaError_t launch_pbs_tmem_t(const fhe_b200_pbs_params& p, const cplx* b
 // ACC is decomposed and transformed once per pair and the monomials are applied in the Fourier domain
 // (X^e at bin k is rho_k^e = omega^((4k+1)e)), so a pair costs one forward and one inverse FFT per
 // polynomial instead of two of each, at the price of 3 key elements per pair (73 MB key, L2-resident).
-// The key is stored sliced by frequency block k1 (6 KB per slice: [g][t'][c][32 bins]) and streamed
-// through an 8-slice shared-memory ring by TMA while the warps walk k1 = 0..31.
-constexpr int MB2_SLICES = 8;
-constexpr int MB2_LAG = 2;                       // refill a ring slot this many slices after warp 0 left it
-constexpr int MB2_SLICE_ELEMS = 3 * 2 * 2 * 32;  // complex elements per slice
+// The key is stored by frequency block k1 (6 KB per block: [g][t'][c][32 bins]) and streamed through a
+// shared-memory ring of 4 two-block slices by TMA while the warps walk k1 = 0..31.
+constexpr int MB2_K1 = 2;                        // frequency blocks (k1 values) per slice
+constexpr int MB2_SLICES = 4;                    // ring slots
+constexpr int MB2_LAG = 1;                       // refill a ring slot this many slices after warp 0 left it
+constexpr int MB2_BLOCK_ELEMS = 3 * 2 * 2 * 32;  // complex elements per frequency block: [g][t'][c][32 bins]
+constexpr int MB2_SLICE_ELEMS = MB2_K1 * MB2_BLOCK_ELEMS;
 struct PbsMb2Smem {
     static constexpr size_t tw_bytes = (size_t)PBS_TILE * 16;
     static constexpr size_t ring_bytes = (size_t)MB2_SLICES * MB2_SLICE_ELEMS * 16;
@@ -676,7 +678,8 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
     const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
     constexpr uint32_t SLICE_BYTES = (uint32_t)(MB2_SLICE_ELEMS * 16);
     const int pairs = n >> 1;
-    const int total_slices = pairs * 32;
+    constexpr int SPI = 32 / MB2_K1;  // slices per blind-rotation step
+    const int total_slices = pairs * SPI;
 
     const int ctl = warp / POLYS, t = warp - ctl * POLYS;
     const int64_t b = (int64_t)blockIdx.x * NCT + ctl;
@@ -769,30 +772,36 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
         named_bar_sync(bar_id, bar_n);  // (A) both polynomials' Fourier digits are visible
         // ---- walk the frequency blocks: out[bin] = sum_g (rho^e_g - 1) * (F_t * G_g[t][t] + F_t' * G_g[t'][t])
 #pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) {
-            const int sidx = i * 32 + k1;
+        for (int sl_i = 0; sl_i < SPI; ++sl_i) {
+            const int sidx = i * SPI + sl_i;
             const int slot = sidx % MB2_SLICES;
             mbar_wait(&bar_full[slot], (uint32_t)((sidx / MB2_SLICES) & 1));
             const cplx* sl = ring + (size_t)slot * MB2_SLICE_ELEMS;
-            const int p = nfft::brev5(k1);
-            const cplx fo = tile_other[k1 * 32 + lane];
-            const double ax = re[p], ay = im[p];
-            double ox = 0.0, oy = 0.0;
 #pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                const cplx bt = sl[((g * 2 + t) * 2 + t) * 32 + lane];
-                const cplx bo = sl[((g * 2 + (1 - t)) * 2 + t) * 32 + lane];
-                const double ix = ax * bt.x - ay * bt.y + (fo.x * bo.x - fo.y * bo.y);
-                const double iy = ax * bt.y + ay * bt.x + (fo.x * bo.y + fo.y * bo.x);
-                const double cx = mx[g] - 1.0, cy = my[g];
-                ox += cx * ix - cy * iy;
-                oy += cx * iy + cy * ix;
-                const double nx = mx[g] * rx[g] - my[g] * ry[g];
-                my[g] = mx[g] * ry[g] + my[g] * rx[g];
-                mx[g] = nx;
+            for (int kk = 0; kk < MB2_K1; ++kk) {
+                const int k1 = sl_i * MB2_K1 + kk;
+                const cplx* blk = sl + kk * MB2_BLOCK_ELEMS;
+                const int p = nfft::brev5(k1);
+                const cplx fo = tile_other[k1 * 32 + lane];
+                const double ax = re[p], ay = im[p];
+                // K_own = sum_g (rho^e_g - 1) * G_g[t][t],  K_oth = sum_g (rho^e_g - 1) * G_g[t'][t]
+                double kox = 0.0, koy = 0.0, ktx = 0.0, kty = 0.0;
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    const cplx bt = blk[((g * 2 + t) * 2 + t) * 32 + lane];
+                    const cplx bo = blk[((g * 2 + (1 - t)) * 2 + t) * 32 + lane];
+                    const double cx = mx[g] - 1.0, cy = my[g];
+                    kox += cx * bt.x - cy * bt.y;
+                    koy += cx * bt.y + cy * bt.x;
+                    ktx += cx * bo.x - cy * bo.y;
+                    kty += cx * bo.y + cy * bo.x;
+                    const double nx = mx[g] * rx[g] - my[g] * ry[g];
+                    my[g] = mx[g] * ry[g] + my[g] * rx[g];
+                    mx[g] = nx;
+                }
+                re[p] = ax * kox - ay * koy + (fo.x * ktx - fo.y * kty);
+                im[p] = ax * koy + ay * kox + (fo.x * kty + fo.y * ktx);
             }
-            re[p] = ox;
-            im[p] = oy;
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[slot]);
             if (threadIdx.x == 0) {  // keep the ring full: refill the slot warp 0 left MB2_LAG slices ago
