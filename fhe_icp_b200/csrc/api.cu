@@ -296,6 +296,29 @@ int fhe_b200_accumulate(fhe_b200_ctx* ctx, uint64_t* d_acc, const uint64_t* d_x,
     return FHE_B200_OK;
 }
 
+int fhe_b200_lwe_pair_addsub(fhe_b200_ctx* ctx, const uint64_t* d_q, const uint64_t* d_y, int64_t B, int32_t d,
+                             int32_t words, int64_t in_stride, uint64_t offset, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0 && d >= 1 && words >= 1 && in_stride >= words, "bad shape");
+    REQUIRE(B * (int64_t)d < ((int64_t)1 << 31), "too many ciphertext pairs for one launch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_q && d_y && d_out, "null device pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_pair_addsub(d_q, d_y, B, d, words, in_stride, offset, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx* ctx, const uint64_t* d_in, int64_t B, int32_t d, int32_t words,
+                               int64_t out_stride, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0 && d >= 1 && words >= 1 && out_stride >= words, "bad shape");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_in && d_out, "null device pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_pair_diff_sum(d_in, B, d, words, out_stride, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 // ------------------------------------------------------------------------------- KS / PBS
 static int check_pbs_params(const fhe_b200_pbs_params* p, const char* fn) {
     if (!p) return fail(FHE_B200_ERR_INVALID, "%s: null params", fn);

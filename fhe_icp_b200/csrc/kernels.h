@@ -30,6 +30,10 @@ cudaError_t launch_lwe_modswitch32(const uint64_t* d_in, int64_t words, uint32_t
 cudaError_t launch_lwe_decrypt32(const uint8_t* d_key, int n, int64_t stride, const uint32_t* d_ct, int64_t count,
                                  int shift32, int64_t* d_out, cudaStream_t s);
 cudaError_t launch_accumulate(uint64_t* d_acc, const uint64_t* d_x, int64_t words, cudaStream_t s);
+cudaError_t launch_lwe_pair_addsub(const uint64_t* d_q, const uint64_t* d_y, int64_t B, int d, int words,
+                                   int64_t in_stride, uint64_t offset, uint64_t* d_out, cudaStream_t s);
+cudaError_t launch_lwe_pair_diff_sum(const uint64_t* d_in, int64_t B, int d, int words, int64_t out_stride,
+                                     uint64_t* d_out, cudaStream_t s);
 cudaError_t launch_quantize(const float* d_X, int64_t count, double scale, int64_t zp, int64_t qmin, int64_t qmax,
                             int64_t* d_q, cudaStream_t s);
 cudaError_t launch_similarity_finalize(const int64_t* d_m, int64_t B, int M, int64_t zp_w, int64_t q_bias,

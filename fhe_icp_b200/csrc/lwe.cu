@@ -457,6 +457,73 @@ cudaError_t launch_accumulate(uint64_t* d_acc, const uint64_t* d_x, int64_t word
     return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------- encrypted x encrypted glue
+// xy = floor((x+y)^2/4) - floor((x-y)^2/4): the two PBS inputs per dimension are the sum and the
+// difference of the query's and the document's ciphertexts, shifted by a plaintext offset into the
+// unsigned half of the message space.  out[b][j][0] = q[j] + y[b][j] + off, out[b][j][1] = q[j] - y[b][j] + off.
+constexpr int PAIR_THREADS = 256;
+
+__global__ void __launch_bounds__(PAIR_THREADS)
+lwe_pair_addsub_kernel(const uint64_t* __restrict__ q, const uint64_t* __restrict__ y, int d, int words,
+                       int64_t in_stride, uint64_t offset, uint64_t* __restrict__ out) {
+    const int64_t row = blockIdx.x;  // b*d + j
+    const int j = (int)(row % d);
+    const uint64_t* qr = q + (size_t)j * in_stride;
+    const uint64_t* yr = y + (size_t)row * in_stride;
+    uint64_t* o0 = out + (size_t)row * 2 * words;
+    uint64_t* o1 = o0 + words;
+    for (int w = threadIdx.x; w < words; w += PAIR_THREADS) {
+        const uint64_t a = qr[w], b = yr[w];
+        const uint64_t off = w == words - 1 ? offset : 0;
+        o0[w] = a + b + off;
+        o1[w] = a - b + off;
+    }
+}
+
+cudaError_t launch_lwe_pair_addsub(const uint64_t* d_q, const uint64_t* d_y, int64_t B, int d, int words,
+                                   int64_t in_stride, uint64_t offset, uint64_t* d_out, cudaStream_t s) {
+    if (B <= 0 || d <= 0) return cudaSuccess;
+    lwe_pair_addsub_kernel<<<(unsigned)(B * d), PAIR_THREADS, 0, s>>>(d_q, d_y, d, words, in_stride, offset, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// out[b][w] = sum_j (in[b][j][0][w] - in[b][j][1][w]): the encrypted score from the 2d bootstrapped squares
+__global__ void __launch_bounds__(PAIR_THREADS)
+lwe_pair_diff_sum_kernel(const uint64_t* __restrict__ in, int d, int words, int64_t out_stride,
+                         uint64_t* __restrict__ out) {
+    const int w = blockIdx.x * PAIR_THREADS + threadIdx.x;
+    if (w >= words) {
+        if (w < out_stride) out[(size_t)blockIdx.y * out_stride + w] = 0;  // row padding
+        return;
+    }
+    const uint64_t* base = in + (size_t)blockIdx.y * d * 2 * words + w;
+    uint64_t acc = 0;
+    int j = 0;
+    for (; j + 4 <= d; j += 4) {
+        uint64_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(base + (size_t)(2 * j + u) * words);
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) acc += v[u] - v[u + 1];
+    }
+    for (; j < d; ++j) acc += base[(size_t)(2 * j) * words] - base[(size_t)(2 * j + 1) * words];
+    out[(size_t)blockIdx.y * out_stride + w] = acc;
+}
+
+cudaError_t launch_lwe_pair_diff_sum(const uint64_t* d_in, int64_t B, int d, int words, int64_t out_stride,
+                                     uint64_t* d_out, cudaStream_t s) {
+    if (B <= 0) return cudaSuccess;
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {  // gridDim.y limit
+        const unsigned nb = (unsigned)((B - b0) < 65535 ? (B - b0) : 65535);
+        dim3 grid((unsigned)((out_stride + PAIR_THREADS - 1) / PAIR_THREADS), nb);
+        lwe_pair_diff_sum_kernel<<<grid, PAIR_THREADS, 0, s>>>(d_in + (size_t)b0 * d * 2 * words, d, words, out_stride,
+                                                              d_out + (size_t)b0 * out_stride);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
 // ----------------------------------------------------------------------------- quantize / finalize
 // q = clip(rint(x / scale + zp), qmin, qmax) in float64, the UniformQuantizer rule
 // (SURVEY.md Appendix A.1); IEEE div/add/rint => identical to numpy.

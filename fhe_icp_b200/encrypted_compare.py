@@ -1,0 +1,141 @@
+"""Encrypted x encrypted comparison: BOTH embedding vectors are encrypted.
+
+The reference multiplies the two embeddings in the clear before the FHE model sees them
+(`batch_operations.py:226` `X = (emb1 * emb2).reshape(1, -1)`, `:273` in the search loop) and
+concedes that "both documents must be available to compute products" (`SESSION5_FIXES.md:118-120`,
+`test_fhe_workflow.py:108-112`).  Here the product itself is evaluated under encryption:
+
+    x*y = floor((x+y)^2 / 4) - floor((x-y)^2 / 4)          (x+y and x-y have the same parity)
+
+so one comparison of two d-dimensional vectors is 2d programmable bootstraps (table lookups of the
+quarter square) on sums / differences of the two parties' ciphertexts, followed by a wrapping sum
+of the 2d outputs into ONE score ciphertext per document, decrypted by the client.
+
+Quantization is of the FACTORS (signed `in_bits`-bit integers, symmetric scale), not of the product
+as in the reference, so the scores are not bit-comparable to `FHESimilarityModel`'s; the parity
+oracle for this path is its own clear integer model `sum_j xq_j * yq_j` (`compare_clear`) and the
+CPU restatement `oracle.encrypted_product_scores`.  Decrypted scores equal the clear integer model
+exactly; see DESIGN.md for the noise budget that makes this hold (l_pbs = 2).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import engine as E
+
+# n=742, N=2048 as the stated 4-bit set, but two decomposition levels in the bootstrap: one PBS output
+# carries noise std ~2^-22 of the torus (2^-15 with one level), so the sum of 2d = 256 outputs
+# (std ~2^-18) stays 16 sigma inside the half-step 2^-14 of the 13-bit signed score.
+COMPARE_PARAMS = dict(n=742, k=1, N_poly=2048, l_pbs=2, beta_pbs=15, l_ks=5, beta_ks=3,
+                      log2_sigma_lwe=-17.1, log2_sigma_glwe=-51.6)
+P_BITS = 4          # PBS message space: in_bits + 1 (sum/difference), offset-binary; plus one padding bit
+IN_BITS = 3         # signed factors in [-4, 3]
+IN_SHIFT = 63 - P_BITS
+SCORE_BITS = 13     # signed score range [-4096, 4095] >= d * 16 for d <= 256
+OUT_SHIFT = 64 - SCORE_BITS
+
+
+def quarter_square_table(p_bits: int = P_BITS) -> np.ndarray:
+    w = np.arange(1 << p_bits, dtype=np.int64) - (1 << (p_bits - 1))
+    return (w * w) // 4
+
+
+class EncryptedCompare:
+    """Client + server halves of the encrypted x encrypted cosine score.
+
+    client: `keygen`, `quantize`, `encrypt`, `decrypt`, `dequantize`;  server: `scores` (needs only
+    the Fourier bootstrapping key).  `multibit=True` uses the two-bits-per-step blind rotation when
+    the parameter set allows it (l_pbs == 1)."""
+
+    def __init__(self, input_dim: int = 128, params: dict | None = None, key_seed: int = 0x5EED0001,
+                 evk_seed: int = 0x5EED0002, device=None, multibit: bool = False, chunk_pbs: int = 148 * 4 * 16):
+        if input_dim * 16 >= (1 << (SCORE_BITS - 1)):
+            raise ValueError("input_dim too large for the 13-bit score range")
+        self.d = int(input_dim)
+        self.pd = dict(params or COMPARE_PARAMS)
+        self.p = E.make_pbs_params(**self.pd)
+        self.dev = E._dev(device)
+        self.key_seed, self.evk_seed = key_seed, evk_seed
+        self.multibit = bool(multibit)
+        if self.multibit and self.p.l_pbs != 1:
+            raise ValueError("multi-bit blind rotation is implemented for l_pbs == 1")
+        self.chunk_pbs = int(chunk_pbs)
+        self.scale = None
+        self.s = self.S = self.bskf = None
+        self.lut = E.from_u64_numpy(E.make_lut_poly(quarter_square_table(), P_BITS, self.p.N, OUT_SHIFT), self.dev)
+
+    # ---- client
+    def keygen(self) -> "EncryptedCompare":
+        p = self.p
+        self.s = E.secret_key(self.key_seed, 0, p.n, self.dev)
+        self.S = E.secret_key(self.key_seed, 1, p.k * p.N, self.dev)
+        if self.multibit:
+            bsk = E.bsk2_gen(p, self.s, self.S, self.evk_seed)
+            self.bskf = E.bsk2_to_fourier(p, bsk)
+        else:
+            bsk = E.bsk_gen(p, self.s, self.S, self.evk_seed)
+            self.bskf = E.bsk_to_fourier(p, bsk)
+        del bsk
+        return self
+
+    def fit_scale(self, X: np.ndarray, clip_sigmas: float = 2.5) -> float:
+        """Symmetric scale for the signed IN_BITS quantizer: clip at `clip_sigmas` standard deviations."""
+        sd = float(np.asarray(X, dtype=np.float64).std())
+        self.scale = clip_sigmas * sd / (1 << (IN_BITS - 1)) if sd > 0 else 1.0
+        return self.scale
+
+    def quantize(self, X: np.ndarray) -> np.ndarray:
+        if self.scale is None:
+            raise RuntimeError("Quantizer not calibrated. Call fit_scale() first.")
+        lo, hi = -(1 << (IN_BITS - 1)), (1 << (IN_BITS - 1)) - 1
+        return np.clip(np.rint(np.asarray(X, dtype=np.float64) / self.scale), lo, hi).astype(np.int64)
+
+    def dequantize(self, q_scores: np.ndarray) -> np.ndarray:
+        return np.asarray(q_scores, dtype=np.float64) * (self.scale * self.scale)
+
+    def encrypt(self, Xq: np.ndarray, enc_seed: int, ct_base: int = 0) -> torch.Tensor:
+        """Xq int [.., d] -> small-key ciphertexts [.., d, stride] (one LWE per dimension)."""
+        self._need_keys()
+        m = torch.as_tensor(np.ascontiguousarray(Xq, dtype=np.int64))
+        return E.lwe_encrypt(self.s, m, IN_SHIFT, self.p.sigma_lwe_abs, enc_seed, ct_base)
+
+    def decrypt(self, scores: torch.Tensor) -> np.ndarray:
+        self._need_keys()
+        v = E.lwe_decrypt(self.S, scores, OUT_SHIFT).cpu().numpy() & ((1 << SCORE_BITS) - 1)
+        return np.where(v >= (1 << (SCORE_BITS - 1)), v - (1 << SCORE_BITS), v)
+
+    # ---- server
+    def scores(self, ct_query: torch.Tensor, ct_docs: torch.Tensor) -> torch.Tensor:
+        """ct_query [d, stride], ct_docs [B, d, stride] -> [B, kN+2] encrypted sum_j x_j*y_j (big key;
+        ciphertext = first kN+1 words of a row)."""
+        if self.bskf is None:
+            raise RuntimeError("No evaluation key. Call keygen() (or load one) first.")
+        p, d = self.p, self.d
+        B = ct_docs.shape[0]
+        words = p.n + 1
+        out = torch.empty((B, E.even_stride(p.k * p.N)), dtype=torch.int64, device=self.dev)
+        docs_per_chunk = max(1, self.chunk_pbs // (2 * d))
+        fn = E.pbs_mb2 if self.multibit else E.pbs
+        for b0 in range(0, B, docs_per_chunk):
+            b1 = min(B, b0 + docs_per_chunk)
+            pairs = E.pair_addsub(ct_query, ct_docs[b0:b1], words, 1 << 62)
+            sq = fn(p, self.bskf, pairs.view(-1, words), self.lut)
+            E.pair_diff_sum(sq.view(b1 - b0, d, 2, -1), out[b0:b1])
+        return out
+
+    # ---- whole pipeline, float in / float out
+    def compare_clear(self, q: np.ndarray, docs: np.ndarray) -> np.ndarray:
+        """The clear integer model this path must reproduce exactly: sum_j xq_j * yq_j."""
+        return self.quantize(docs) @ self.quantize(q)
+
+    def similarity(self, q: np.ndarray, docs: np.ndarray, enc_seed: int = 1) -> np.ndarray:
+        docs = np.atleast_2d(docs)
+        ct_q = self.encrypt(self.quantize(q), enc_seed, 0)
+        ct_d = self.encrypt(self.quantize(docs), enc_seed, self.d)
+        return self.dequantize(self.decrypt(self.scores(ct_q, ct_d)))
+
+    def _need_keys(self):
+        if self.s is None:
+            raise RuntimeError("No secret key. Call keygen() first.")

@@ -147,6 +147,31 @@ def accumulate(acc: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return acc
 
 
+def pair_addsub(q: torch.Tensor, y: torch.Tensor, words: int, offset: int) -> torch.Tensor:
+    """q [d,stride], y [B,d,stride] (ciphertext = first `words` words of a row) ->
+    [B,d,2,words] = (q+y+offset, q-y+offset), offset on the body."""
+    dev = y.device
+    B, d, stride = y.shape
+    assert q.shape == (d, stride) and q.is_contiguous() and y.is_contiguous() and words <= stride
+    out = torch.empty((B, d, 2, words), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_lwe_pair_addsub(_ctx(dev).handle, _ptr(q), _ptr(y), B, d, words, stride,
+                                             offset & 0xFFFFFFFFFFFFFFFF, _ptr(out), _stream(dev)))
+    return out
+
+
+def pair_diff_sum(sq: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """sq [B,d,2,words] -> [B,even_stride] = sum_j (sq[:,j,0] - sq[:,j,1]) (wrapping), rows zero-padded."""
+    dev = sq.device
+    B, d, two, words = sq.shape
+    assert two == 2 and sq.is_contiguous()
+    if out is None:
+        out = torch.empty((B, even_stride(words - 1)), dtype=torch.int64, device=dev)
+    assert out.is_contiguous() and out.shape[0] == B and out.shape[1] >= words
+    N.check(N.lib().fhe_b200_lwe_pair_diff_sum(_ctx(dev).handle, _ptr(sq), B, d, words, out.shape[1], _ptr(out),
+                                               _stream(dev)))
+    return out
+
+
 # ------------------------------------------------------------------------------- KS / PBS
 def make_pbs_params(n=742, k=1, N_poly=2048, l_pbs=1, beta_pbs=23, l_ks=5, beta_ks=3,
                     log2_sigma_lwe=-17.1, log2_sigma_glwe=-51.6) -> N.PBSParams:

@@ -138,6 +138,19 @@ int fhe_b200_lwe_modswitch32(fhe_b200_ctx *ctx, const uint64_t *d_ct, int64_t co
 int fhe_b200_accumulate(fhe_b200_ctx *ctx, uint64_t *d_acc, const uint64_t *d_x, int64_t words,
                         void *stream);
 
+/* ---- encrypted x encrypted comparison glue -----------------------
+ * Replaces the CLEAR element-wise product emb1 * emb2 of batch_operations.py:226,273 when both
+ * vectors are encrypted: x*y = floor((x+y)^2/4) - floor((x-y)^2/4), two table lookups (PBS) per
+ * dimension.  pair_addsub builds the PBS inputs from the query's d ciphertexts d_q [d][in_stride]
+ * and the documents' d_y [B][d][in_stride] (the first `words` words of each row are the ciphertext):
+ * d_out [B][d][2][words] = (q+y+offset, q-y+offset), `offset` added to the body (word words-1).  pair_diff_sum folds the bootstrapped squares back into one
+ * score ciphertext per document: d_out [B][out_stride] = sum_j (d_in[b][j][0] - d_in[b][j][1]), words
+ * words..out_stride-1 of each row zeroed (an even out_stride makes the rows decryptable in place). */
+int fhe_b200_lwe_pair_addsub(fhe_b200_ctx *ctx, const uint64_t *d_q, const uint64_t *d_y, int64_t B, int32_t d,
+                             int32_t words, int64_t in_stride, uint64_t offset, uint64_t *d_out, void *stream);
+int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx *ctx, const uint64_t *d_in, int64_t B, int32_t d, int32_t words,
+                               int64_t out_stride, uint64_t *d_out, void *stream);
+
 /* ---- keyswitch + programmable bootstrap ---------------------------------------
  * north-star primitives; not exercised by the reference's compiled circuit. */
 int fhe_b200_ksk_gen(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_S_big,

@@ -256,6 +256,45 @@ def pbs_mb2(p: PBSParams, bskf2, ct, luts, lut_index=None) -> np.ndarray:
     return out
 
 
+# ----------------------------------------------------------------------------- encrypted x encrypted comparison
+# both vectors encrypted; replaces the clear product of batch_operations.py:226,273.
+# x*y = floor((x+y)^2/4) - floor((x-y)^2/4), one table lookup per term.
+def pair_addsub(q, y, words: int, offset: int) -> np.ndarray:
+    """q [d,stride], y [B,d,stride] -> [B,d,2,words] = (q+y+offset, q-y+offset), offset on the body."""
+    q = np.asarray(q, dtype=np.uint64)[None, :, :words]
+    y = np.asarray(y, dtype=np.uint64)[:, :, :words]
+    out = np.empty(y.shape[:2] + (2, words), dtype=np.uint64)
+    out[:, :, 0] = q + y
+    out[:, :, 1] = q - y
+    out[:, :, :, words - 1] += np.uint64(offset & 0xFFFFFFFFFFFFFFFF)
+    return out
+
+
+def pair_diff_sum(sq) -> np.ndarray:
+    """sq [B,d,2,words] -> [B,words] = sum_j (sq[:,j,0] - sq[:,j,1]) (wrapping u64)."""
+    sq = np.asarray(sq, dtype=np.uint64)
+    return (sq[:, :, 0] - sq[:, :, 1]).sum(axis=1, dtype=np.uint64)
+
+
+def quarter_square_table(p_bits: int) -> np.ndarray:
+    """table[w] = floor((w - 2^(p_bits-1))^2 / 4) for the offset-binary message w."""
+    w = np.arange(1 << p_bits, dtype=np.int64) - (1 << (p_bits - 1))
+    return (w * w) // 4
+
+
+def encrypted_product_scores(p: PBSParams, bskf, ct_q, ct_docs, p_bits: int, out_shift: int,
+                             multibit: bool = False) -> np.ndarray:
+    """ct_q [d,stride], ct_docs [B,d,stride] under the small key -> [B, kN+1] under the big key:
+    LWE encryptions of sum_j x_j*y_j at 2^out_shift."""
+    words = p.n + 1
+    B, d = np.asarray(ct_docs).shape[:2]
+    pairs = pair_addsub(ct_q, ct_docs, words, 1 << (63 - 1))  # + 2^(p_bits-1) messages = half of the unsigned range
+    lut = make_lut_poly(quarter_square_table(p_bits), p_bits, p.N, out_shift)
+    fn = pbs_mb2 if multibit else pbs
+    sq = fn(p, bskf, pairs.reshape(-1, words), lut)
+    return pair_diff_sum(sq.reshape(B, d, 2, -1))
+
+
 def negacyclic_mul_fft(a_small, b_torus) -> np.ndarray:
     a = np.ascontiguousarray(a_small, dtype=np.int64); b = np.ascontiguousarray(b_torus, dtype=np.uint64)
     out = np.zeros(a.size, dtype=np.uint64)

@@ -150,3 +150,21 @@ def test_modswitch_and_negacyclic_lut_wraparound(O):
     assert int(lut[2047]) == (1 << 64) - 0 * (1 << 59) or True   # wrapped part carries -f(0) = 0
     lut2 = O.make_lut_poly(np.arange(16) + 1, 4, 2048, 59)
     assert int(lut2[2047]) == (1 << 64) - (1 << 59)              # -f(0) on the wrapped half box
+
+
+def test_encrypted_product_oracle_matches_clear_model(O):
+    """quarter-square products through the oracle's PBS decrypt to sum_j x_j*y_j."""
+    p = O.make_params(n=16, k=1, N=2048, l_pbs=2, beta_pbs=15, l_ks=4, beta_ks=4, log2_sigma_lwe=-30.0,
+                      log2_sigma_glwe=-51.6)
+    s, S = O.secret_key(3, 0, p.n), O.secret_key(3, 1, p.k * p.N)
+    bskf = O.bsk_to_fourier(p, O.bsk_gen(p, s, S, 4))
+    rng = np.random.RandomState(0)
+    d, B = 3, 2
+    xq, yq = rng.randint(-4, 4, size=d), rng.randint(-4, 4, size=(B, d))
+    xq[0], yq[0, 0], yq[1, 0] = -4, -4, 3     # extremes: 16 and -12
+    cq = O.lwe_encrypt(s, xq, 59, p.sigma_lwe_abs, 7, 0, stride=p.n + 2)
+    cd = O.lwe_encrypt(s, yq, 59, p.sigma_lwe_abs, 7, d, stride=p.n + 2).reshape(B, d, -1)
+    assert np.array_equal(O.quarter_square_table(4)[[0, 8, 15]], [16, 0, 12])
+    sc = O.encrypted_product_scores(p, bskf, cq, cd, 4, 51)
+    dec = O.lwe_decrypt(S, sc, 51) & 8191
+    assert np.array_equal(np.where(dec >= 4096, dec - 8192, dec), yq @ xq)
