@@ -379,8 +379,10 @@ uint64_t fhe_b200_bsk2_words(const fhe_b200_pbs_params* p) {
 
 static int check_mb2_params(const fhe_b200_pbs_params* p, const char* fn) {
     if (int r = check_pbs_params(p, fn)) return r;
-    if (p->l_pbs != 1 || (p->n & 1))
-        return fail(FHE_B200_ERR_INVALID, "%s: the multi-bit path needs l_pbs == 1 and an even n", fn);
+    if (p->l_pbs > 2 || (p->n & 1))
+        return fail(FHE_B200_ERR_INVALID, "%s: the multi-bit path needs l_pbs <= 2 and an even n", fn);
+    if (p->l_pbs == 2 && 2 * p->beta_pbs > 31)
+        return fail(FHE_B200_ERR_INVALID, "%s: two-level multi-bit path needs 2*beta_pbs <= 31", fn);
     return FHE_B200_OK;
 }
 

@@ -629,45 +629,54 @@ static cudaError_t launch_pbs_tmem_t(const fhe_b200_pbs_params& p, const cplx* b
 // G1 = GGSW(s_a s_b), G2 = GGSW(s_a(1-s_b)), G3 = GGSW((1-s_a)s_b) and e = (a~_a + a~_b, a~_a, a~_b).
 // ACC is decomposed and transformed once per pair and the monomials are applied in the Fourier domain
 // (X^e at bin k is rho_k^e = omega^((4k+1)e)), so a pair costs one forward and one inverse FFT per
-// polynomial instead of two of each, at the price of 3 key elements per pair (73 MB key, L2-resident).
-// The key is stored by frequency block k1 (6 KB per block: [g][t'][c][32 bins]) and streamed through a
-// shared-memory ring of 4 two-block slices by TMA while the warps walk k1 = 0..31.
+// polynomial and level instead of two of each, at the price of 3 key elements per pair (L2-resident).
+// The key is stored by frequency block k1 ([g][t'][lev][c][32 bins], 6*L KB per block) and streamed
+// through a shared-memory ring of two-block slices by TMA while the warps walk k1 = 0..31.
+//
+// L decomposition levels: the external product is L independent single-level products whose outputs
+// add, so a ciphertext is served by 2L warps.  Warp (t, lev) transforms the level-lev digits of ACC_t,
+// accumulates sum_t' F[t'][lev] * G[t'][lev][t] and adds its inverse transform into its OWN partial
+// accumulator A[t][lev] in TMEM (ACC_t = sum_lev A[t][lev]); the partials of one polynomial sit in the
+// same TMEM lane quadrant (warps w and w+4), so every warp can read the full ACC_t for its digits.
 constexpr int MB2_K1 = 2;                        // frequency blocks (k1 values) per slice
-constexpr int MB2_SLICES = 4;                    // ring slots
 constexpr int MB2_LAG = 1;                       // refill a ring slot this many slices after warp 0 left it
-constexpr int MB2_BLOCK_ELEMS = 3 * 2 * 2 * 32;  // complex elements per frequency block: [g][t'][c][32 bins]
-constexpr int MB2_SLICE_ELEMS = MB2_K1 * MB2_BLOCK_ELEMS;
+template <int L>
 struct PbsMb2Smem {
+    static constexpr int slices = L == 1 ? 4 : 3;                       // ring slots
+    static constexpr int block_elems = 3 * 2 * L * 2 * 32;              // complex elements per frequency block
+    static constexpr int slice_elems = MB2_K1 * block_elems;
     static constexpr size_t tw_bytes = (size_t)PBS_TILE * 16;
-    static constexpr size_t ring_bytes = (size_t)MB2_SLICES * MB2_SLICE_ELEMS * 16;
+    static constexpr size_t ring_bytes = (size_t)slices * slice_elems * 16;
     static constexpr size_t omega_bytes = (size_t)PBS_OMEGA * 16;
     static constexpr size_t bar_bytes = 256;
     static constexpr size_t head_bytes = tw_bytes + ring_bytes + omega_bytes + bar_bytes;
-    static constexpr size_t tile_bytes = (size_t)2 * PBS_TILE * 16;
+    static constexpr size_t tile_bytes = (size_t)2 * L * PBS_TILE * 16;  // one per warp (t, lev)
     __host__ __device__ static size_t per_ct(int n) { return tile_bytes + (((size_t)(n + 1) * 2 + 127) & ~(size_t)127); }
     static size_t total(int n, int nct) { return head_bytes + (size_t)nct * per_ct(n); }
 };
 
-template <int NCT>
-__global__ void __launch_bounds__(NCT * 64, 1)
+template <int L, int NCT>
+__global__ void __launch_bounds__(NCT * 64 * L, 1)
 pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
                const uint64_t* __restrict__ luts, const int32_t* __restrict__ lut_index,
                const cplx* __restrict__ g_tw, uint64_t* __restrict__ out) {
-    using S = PbsMb2Smem;
-    constexpr int POLYS = 2;
-    constexpr uint32_t TMEM_COLS = NCT <= 2 ? 128 : 256;
+    using S = PbsMb2Smem<L>;
+    static_assert(L == 1 || (L == 2 && NCT == 2), "two levels: 2 ciphertexts x 4 warps, partials paired by TMEM quadrant");
+    constexpr int WARPS = NCT * 2 * L;
+    constexpr int SLICES = S::slices;
+    constexpr uint32_t TMEM_COLS = WARPS <= 4 ? 128 : 256;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
     cplx* ring = reinterpret_cast<cplx*>(smem_raw + S::tw_bytes);
     cplx* omega = reinterpret_cast<cplx*>(smem_raw + S::tw_bytes + S::ring_bytes);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + S::tw_bytes + S::ring_bytes + S::omega_bytes);
-    uint64_t* bar_empty = bar_full + MB2_SLICES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_empty + MB2_SLICES);
+    uint64_t* bar_empty = bar_full + SLICES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_empty + SLICES);
     for (int i = threadIdx.x; i < PBS_TILE; i += blockDim.x) tw[i] = g_tw[i];
     for (int i = threadIdx.x; i < PBS_OMEGA; i += blockDim.x) omega[i] = g_tw[PBS_TILE + i];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int q = 0; q < MB2_SLICES; ++q) { mbar_init(&bar_full[q], 1); mbar_init(&bar_empty[q], NCT * POLYS); }
+        for (int q = 0; q < SLICES; ++q) { mbar_init(&bar_full[q], 1); mbar_init(&bar_empty[q], WARPS); }
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -675,25 +684,29 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
-    constexpr uint32_t SLICE_BYTES = (uint32_t)(MB2_SLICE_ELEMS * 16);
-    const int pairs = n >> 1;
+    // warp -> (ciphertext, polynomial t, level); its TMEM lane quadrant is warp & 3, column half warp >> 2
+    const int ctl = L == 1 ? warp / 2 : (warp & 3) / 2;
+    const int t = warp & 1;
+    const int lev = L == 1 ? 0 : warp >> 2;
+    const uint32_t tquad = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tacc = tquad + (uint32_t)((warp >> 2) * 128);   // this warp's (partial) accumulator
+    constexpr uint32_t SLICE_BYTES = (uint32_t)(S::slice_elems * 16);
     constexpr int SPI = 32 / MB2_K1;  // slices per blind-rotation step
+    const int pairs = n >> 1;
     const int total_slices = pairs * SPI;
 
-    const int ctl = warp / POLYS, t = warp - ctl * POLYS;
     const int64_t b = (int64_t)blockIdx.x * NCT + ctl;
     unsigned char* base = smem_raw + S::head_bytes + (size_t)ctl * S::per_ct(n);
     cplx* tile_all = reinterpret_cast<cplx*>(base);
     uint16_t* a_tilde = reinterpret_cast<uint16_t*>(base + S::tile_bytes);
-    cplx* tile = tile_all + (size_t)t * PBS_TILE;
-    const cplx* tile_other = tile_all + (size_t)(1 - t) * PBS_TILE;
+    cplx* tile = tile_all + (size_t)(t * L + lev) * PBS_TILE;
+    const cplx* tile_other = tile_all + (size_t)((1 - t) * L + lev) * PBS_TILE;
     const bool live = b < B;
-    const int bar_id = 1 + ctl, bar_n = POLYS * 32;
+    const int bar_id = 1 + ctl, bar_n = 2 * L * 32;
 
     // ---- prologue: mod-switch the mask, ACC = X^(-b~) * (0, LUT) into TMEM (lo words | hi words)
     const uint64_t* ct = in + (size_t)(live ? b : 0) * (n + 1);
-    for (int i = t * 32 + lane; i <= n; i += POLYS * 32)
+    for (int i = (t * L + lev) * 32 + lane; i <= n; i += 2 * L * 32)
         a_tilde[i] = (uint16_t)((((ct[i] >> 51) + 1) >> 1) & 4095);
     named_bar_sync(bar_id, bar_n);
     {
@@ -707,7 +720,7 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
                 const int q = 16 * c + u;
                 const int x = lane + 32 * (q & 31) + (q >> 5) * PBS_M;
                 uint64_t v = 0;
-                if (t == 1) {
+                if (t == 1 && lev == 0) {
                     const int src = (x - rot) & 4095;
                     v = lut[src & 2047];
                     if (src & 2048) v = 0 - v;
@@ -720,11 +733,13 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
         }
         tmem_wait_st();
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (threadIdx.x == 0) {  // fill the ring
-        for (int q = 0; q < MB2_SLICES && q < total_slices; ++q) {
+        for (int q = 0; q < SLICES && q < total_slices; ++q) {
             mbar_expect_tx(&bar_full[q], SLICE_BYTES);
-            tma_load_1d(ring + (size_t)q * MB2_SLICE_ELEMS, bskf2 + (size_t)q * MB2_SLICE_ELEMS, SLICE_BYTES, &bar_full[q]);
+            tma_load_1d(ring + (size_t)q * S::slice_elems, bskf2 + (size_t)q * S::slice_elems, SLICE_BYTES, &bar_full[q]);
         }
     }
 
@@ -732,16 +747,39 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
     const int dshift = 32 - beta;
     double re[32], im[32];
     for (int i = 0; i < pairs; ++i) {
-        // ---- digits of ACC_t itself (no rotation in the coefficient domain): high words from TMEM
+        // ---- digits of ACC_t itself (no rotation in the coefficient domain)
+        if constexpr (L == 1) {  // high words of the accumulator from TMEM
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t h0[16], h1[16];
-            tmem_ld_x16(tacc + 64 + 16 * c, h0);
-            tmem_ld_x16(tacc + 96 + 16 * c, h1);
+            for (int c = 0; c < 2; ++c) {
+                uint32_t h0[16], h1[16];
+                tmem_ld_x16(tacc + 64 + 16 * c, h0);
+                tmem_ld_x16(tacc + 96 + 16 * c, h1);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                re[16 * c + u] = (double)((int32_t)(h0[u] + rnd32) >> dshift);
-                im[16 * c + u] = (double)((int32_t)(h1[u] + rnd32) >> dshift);
+                for (int u = 0; u < 16; ++u) {
+                    re[16 * c + u] = (double)((int32_t)(h0[u] + rnd32) >> dshift);
+                    im[16 * c + u] = (double)((int32_t)(h1[u] + rnd32) >> dshift);
+                }
+            }
+        } else {  // ACC_t = A[t][0] + A[t][1] (64-bit sum of the two partials), then the level's balanced digit:
+            // round to 2*beta bits, lev 1 = low beta bits sign-extended, lev 0 = the rest after the carry
+            const uint32_t r_lo = 1u << (31 - 2 * beta);                            // rounding to 2*beta bits
+            const uint32_t r_hi = r_lo + (1u << (31 - beta));                       // ... plus the carry out of digit 1
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t l0[16], h0[16], l1[16], h1[16];
+                tmem_ld_x16(tquad + 16 * c, l0);
+                tmem_ld_x16(tquad + 64 + 16 * c, h0);
+                tmem_ld_x16(tquad + 128 + 16 * c, l1);
+                tmem_ld_x16(tquad + 192 + 16 * c, h1);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const uint32_t lo = l0[u] + l1[u];
+                    const uint32_t hi = h0[u] + h1[u] + (lo < l0[u] ? 1u : 0u);
+                    const int32_t dg = lev == 0 ? (int32_t)(hi + r_hi) >> dshift
+                                                : (int32_t)((hi + r_lo) << beta) >> dshift;
+                    if (c < 2) re[16 * c + u] = (double)dg;
+                    else im[16 * (c - 2) + u] = (double)dg;
+                }
             }
         }
         nfft::fwd_phase1(re, im, tw, tile, lane);
@@ -769,27 +807,27 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
             rx[g] = r.x;
             ry[g] = r.y;
         }
-        named_bar_sync(bar_id, bar_n);  // (A) both polynomials' Fourier digits are visible
-        // ---- walk the frequency blocks: out[bin] = sum_g (rho^e_g - 1) * (F_t * G_g[t][t] + F_t' * G_g[t'][t])
+        named_bar_sync(bar_id, bar_n);  // (A) every warp's Fourier digits are visible
+        // ---- walk the frequency blocks: out[bin] = F_t * sum_g c_g G_g[t][lev][t] + F_t' * sum_g c_g G_g[t'][lev][t],
+        //      c_g = rho^e_g - 1
 #pragma unroll
         for (int sl_i = 0; sl_i < SPI; ++sl_i) {
             const int sidx = i * SPI + sl_i;
-            const int slot = sidx % MB2_SLICES;
-            mbar_wait(&bar_full[slot], (uint32_t)((sidx / MB2_SLICES) & 1));
-            const cplx* sl = ring + (size_t)slot * MB2_SLICE_ELEMS;
+            const int slot = sidx % SLICES;
+            mbar_wait(&bar_full[slot], (uint32_t)((sidx / SLICES) & 1));
+            const cplx* sl = ring + (size_t)slot * S::slice_elems;
 #pragma unroll
             for (int kk = 0; kk < MB2_K1; ++kk) {
                 const int k1 = sl_i * MB2_K1 + kk;
-                const cplx* blk = sl + kk * MB2_BLOCK_ELEMS;
+                const cplx* blk = sl + kk * S::block_elems;
                 const int p = nfft::brev5(k1);
                 const cplx fo = tile_other[k1 * 32 + lane];
                 const double ax = re[p], ay = im[p];
-                // K_own = sum_g (rho^e_g - 1) * G_g[t][t],  K_oth = sum_g (rho^e_g - 1) * G_g[t'][t]
                 double kox = 0.0, koy = 0.0, ktx = 0.0, kty = 0.0;
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                    const cplx bt = blk[((g * 2 + t) * 2 + t) * 32 + lane];
-                    const cplx bo = blk[((g * 2 + (1 - t)) * 2 + t) * 32 + lane];
+                    const cplx bt = blk[(((g * 2 + t) * L + lev) * 2 + t) * 32 + lane];
+                    const cplx bo = blk[(((g * 2 + (1 - t)) * L + lev) * 2 + t) * 32 + lane];
                     const double cx = mx[g] - 1.0, cy = my[g];
                     kox += cx * bt.x - cy * bt.y;
                     koy += cx * bt.y + cy * bt.x;
@@ -806,12 +844,12 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
             if (lane == 0) mbar_arrive(&bar_empty[slot]);
             if (threadIdx.x == 0) {  // keep the ring full: refill the slot warp 0 left MB2_LAG slices ago
                 const int done = sidx - MB2_LAG;
-                const int next = done + MB2_SLICES;
+                const int next = done + SLICES;
                 if (done >= 0 && next < total_slices) {
-                    const int ds = done % MB2_SLICES;
-                    mbar_wait(&bar_empty[ds], (uint32_t)((done / MB2_SLICES) & 1));
+                    const int ds = done % SLICES;
+                    mbar_wait(&bar_empty[ds], (uint32_t)((done / SLICES) & 1));
                     mbar_expect_tx(&bar_full[ds], SLICE_BYTES);
-                    tma_load_1d(ring + (size_t)ds * MB2_SLICE_ELEMS, bskf2 + (size_t)next * MB2_SLICE_ELEMS, SLICE_BYTES,
+                    tma_load_1d(ring + (size_t)ds * S::slice_elems, bskf2 + (size_t)next * S::slice_elems, SLICE_BYTES,
                                 &bar_full[ds]);
                 }
             }
@@ -836,21 +874,33 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
             tmem_st_x16(tacc + 64 + 16 * c, rh);
         }
         tmem_wait_st();
-        __syncwarp();
+        if constexpr (L > 1) {  // (C) the partner's partial accumulator is complete before anyone sums it
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            named_bar_sync(bar_id, bar_n);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        } else {
+            __syncwarp();
+        }
     }
     // the tail slices (done > total - LAG) were never waited for by the producer; nothing is pending
-    if (live) {
+    if (live && lev == 0) {
         uint64_t* o = out + (size_t)b * ((size_t)PBS_N + 1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             uint32_t rl[16], rh[16];
             tmem_ld_x16(tacc + 16 * c, rl);
             tmem_ld_x16(tacc + 64 + 16 * c, rh);
+            uint32_t sl[16], sh[16];
+            if constexpr (L > 1) {
+                tmem_ld_x16(tquad + 128 + 16 * c, sl);
+                tmem_ld_x16(tquad + 192 + 16 * c, sh);
+            }
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
                 const int q = 16 * c + u;
                 const int x = lane + 32 * (q & 31) + (q >> 5) * PBS_M;
-                const uint64_t v = ((uint64_t)rh[u] << 32) | rl[u];
+                uint64_t v = ((uint64_t)rh[u] << 32) | rl[u];
+                if constexpr (L > 1) v += ((uint64_t)sh[u] << 32) | sl[u];
                 if (t == 0) {
                     if (x == 0) o[0] = v;
                     else o[PBS_N - x] = 0 - v;
@@ -865,9 +915,9 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
     if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// standard-domain bsk2 [pairs][3][2][1][2][N] -> Fourier, sliced: [pairs][32][3][2][2][32]
+// standard-domain bsk2 [pairs][3][2][L][2][N] -> Fourier, by frequency block: [pairs][32][3][2][L][2][32]
 __global__ void __launch_bounds__(B2F_WARPS * 32)
-bsk2_to_fourier_kernel(const uint64_t* __restrict__ bsk2, int64_t polys, const cplx* __restrict__ g_twf,
+bsk2_to_fourier_kernel(const uint64_t* __restrict__ bsk2, int64_t polys, int L, const cplx* __restrict__ g_twf,
                        cplx* __restrict__ bskf2) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* twf = reinterpret_cast<cplx*>(smem_raw);
@@ -875,7 +925,7 @@ bsk2_to_fourier_kernel(const uint64_t* __restrict__ bsk2, int64_t polys, const c
     for (int i = threadIdx.x; i < PBS_TILE; i += blockDim.x) twf[i] = g_twf[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * B2F_WARPS + warp;   // q = ((i*3+g)*2+t)*2+c
+    const int64_t q = (int64_t)blockIdx.x * B2F_WARPS + warp;   // q = (((i*3+g)*2+t)*L+lev)*2+c
     if (q >= polys) return;
     cplx* buf = bufs + warp * PBS_TILE;
     const uint64_t* src = bsk2 + (size_t)q * PBS_N;
@@ -888,17 +938,16 @@ bsk2_to_fourier_kernel(const uint64_t* __restrict__ bsk2, int64_t polys, const c
     nfft::fwd_phase1(re, im, twf, buf, lane);
     __syncwarp();
     nfft::fwd_phase2(re, im, buf, lane);
-    const int c = (int)(q & 1), tt = (int)((q >> 1) & 1);
-    const int64_t ig = q >> 2;
-    const int g = (int)(ig % 3);
-    const int64_t i = ig / 3;
+    const int per_pair = 3 * 2 * L * 2;          // polynomials per key-bit pair = entries per frequency block
+    const int64_t i = q / per_pair;
+    const int within = (int)(q - i * per_pair);  // ((g*2+t)*L+lev)*2+c
 #pragma unroll
     for (int p = 0; p < 32; ++p) {
         const int k1 = nfft::brev5(p);
         cplx v;
         v.x = re[p];
         v.y = im[p];
-        bskf2[((size_t)(i * 32 + k1) * 12 + (size_t)((g * 2 + tt) * 2 + c)) * 32 + lane] = v;
+        bskf2[((size_t)(i * 32 + k1) * per_pair + (size_t)within) * 32 + lane] = v;
     }
 }
 
@@ -906,26 +955,26 @@ cudaError_t launch_bsk2_to_fourier(const fhe_b200_pbs_params& p, const uint64_t*
     const cplx* twf;
     cudaError_t e = get_tables(&twf);
     if (e != cudaSuccess) return e;
-    if (p.k != 1 || p.l_pbs != 1 || (p.n & 1)) return cudaErrorInvalidValue;
-    const int64_t polys = (int64_t)(p.n / 2) * 3 * 2 * 2;
+    if (p.k != 1 || p.l_pbs < 1 || p.l_pbs > 2 || (p.n & 1) || p.N != PBS_N) return cudaErrorInvalidValue;
+    const int64_t polys = (int64_t)(p.n / 2) * 3 * 2 * p.l_pbs * 2;
     const size_t smem = sizeof(cplx) * PBS_TILE * (1 + B2F_WARPS);
     e = cudaFuncSetAttribute(bsk2_to_fourier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     bsk2_to_fourier_kernel<<<(unsigned)((polys + B2F_WARPS - 1) / B2F_WARPS), B2F_WARPS * 32, smem, s>>>(
-        d_bsk2, polys, twf, reinterpret_cast<cplx*>(d_bskf2));
+        d_bsk2, polys, p.l_pbs, twf, reinterpret_cast<cplx*>(d_bskf2));
     count_launch();
     return cudaGetLastError();
 }
 
-template <int NCT>
+template <int L, int NCT>
 static cudaError_t launch_pbs_mb2_t(const fhe_b200_pbs_params& p, const cplx* bskf2, const uint64_t* d_in, int64_t B,
                                     const uint64_t* d_luts, const int32_t* d_lut_index, const cplx* tw, uint64_t* d_out,
                                     cudaStream_t s) {
-    const size_t smem = PbsMb2Smem::total(p.n, NCT);
-    cudaError_t e = cudaFuncSetAttribute(pbs_kernel_mb2<NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = PbsMb2Smem<L>::total(p.n, NCT);
+    cudaError_t e = cudaFuncSetAttribute(pbs_kernel_mb2<L, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((B + NCT - 1) / NCT);
-    pbs_kernel_mb2<NCT><<<grid, NCT * 64, smem, s>>>(bskf2, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tw, d_out);
+    pbs_kernel_mb2<L, NCT><<<grid, NCT * 64 * L, smem, s>>>(bskf2, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tw, d_out);
     count_launch();
     return cudaGetLastError();
 }
@@ -933,14 +982,16 @@ static cudaError_t launch_pbs_mb2_t(const fhe_b200_pbs_params& p, const cplx* bs
 cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
                            const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
                            cudaStream_t s) {
-    if (p.k != 1 || p.l_pbs != 1 || (p.n & 1) || p.N != PBS_N) return cudaErrorInvalidValue;
+    if (p.k != 1 || p.l_pbs < 1 || p.l_pbs > 2 || (p.n & 1) || p.N != PBS_N) return cudaErrorInvalidValue;
+    if (p.l_pbs == 2 && (2 * p.beta_pbs > 31)) return cudaErrorInvalidValue;  // digits come from the high word
     const cplx* tw;
     cudaError_t e = get_tables(&tw);
     if (e != cudaSuccess) return e;
     const cplx* bskf2 = reinterpret_cast<const cplx*>(d_bskf2);
-    if (B <= (int64_t)sm_count) return launch_pbs_mb2_t<1>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
-    if (B <= 2 * (int64_t)sm_count) return launch_pbs_mb2_t<2>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
-    return launch_pbs_mb2_t<4>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    if (p.l_pbs == 2) return launch_pbs_mb2_t<2, 2>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    if (B <= (int64_t)sm_count) return launch_pbs_mb2_t<1, 1>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    if (B <= 2 * (int64_t)sm_count) return launch_pbs_mb2_t<1, 2>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    return launch_pbs_mb2_t<1, 4>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
 }
 
 bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why) {

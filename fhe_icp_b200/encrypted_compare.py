@@ -46,11 +46,11 @@ class EncryptedCompare:
     """Client + server halves of the encrypted x encrypted cosine score.
 
     client: `keygen`, `quantize`, `encrypt`, `decrypt`, `dequantize`;  server: `scores` (needs only
-    the Fourier bootstrapping key).  `multibit=True` uses the two-bits-per-step blind rotation when
-    the parameter set allows it (l_pbs == 1)."""
+    the Fourier bootstrapping key).  `multibit=True` uses the two-bits-per-step blind rotation
+    (l_pbs <= 2)."""
 
     def __init__(self, input_dim: int = 128, params: dict | None = None, key_seed: int = 0x5EED0001,
-                 evk_seed: int = 0x5EED0002, device=None, multibit: bool = False, chunk_pbs: int = 148 * 4 * 16):
+                 evk_seed: int = 0x5EED0002, device=None, multibit: bool = True, chunk_pbs: int = 148 * 2 * 32):
         if input_dim * 16 >= (1 << (SCORE_BITS - 1)):
             raise ValueError("input_dim too large for the 13-bit score range")
         self.d = int(input_dim)
@@ -59,8 +59,8 @@ class EncryptedCompare:
         self.dev = E._dev(device)
         self.key_seed, self.evk_seed = key_seed, evk_seed
         self.multibit = bool(multibit)
-        if self.multibit and self.p.l_pbs != 1:
-            raise ValueError("multi-bit blind rotation is implemented for l_pbs == 1")
+        if self.multibit and self.p.l_pbs > 2:
+            raise ValueError("multi-bit blind rotation is implemented for l_pbs <= 2")
         self.chunk_pbs = int(chunk_pbs)
         self.scale = None
         self.s = self.S = self.bskf = None

@@ -263,9 +263,9 @@ def bsk2_gen(p: N.PBSParams, s_small: torch.Tensor, S_big: torch.Tensor, evk_see
 
 
 def bsk2_to_fourier(p: N.PBSParams, bsk2: torch.Tensor) -> torch.Tensor:
-    """-> [n/2][32 frequency blocks][3][k+1][k+1][32][2] f64 (the sliced layout the kernel streams)."""
+    """-> [n/2][32 frequency blocks][3][k+1][l][k+1][32][2] f64 (the layout the kernel streams)."""
     dev = bsk2.device
-    bskf2 = torch.empty((p.n // 2, 32, 3, p.k + 1, p.k + 1, 32, 2), dtype=torch.float64, device=dev)
+    bskf2 = torch.empty((p.n // 2, 32, 3, p.k + 1, p.l_pbs, p.k + 1, 32, 2), dtype=torch.float64, device=dev)
     N.check(N.lib().fhe_b200_bsk2_to_fourier(_ctx(dev).handle, C.byref(p), _ptr(bsk2.contiguous()), _ptr(bskf2),
                                              _stream(dev)))
     return bskf2

@@ -164,9 +164,9 @@ int fhe_b200_bsk_to_fourier(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p,
 int fhe_b200_keyswitch(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_ksk,
                        const uint64_t *d_in, int64_t B, uint64_t *d_out, void *stream);
 /* Multi-bit blind rotation, grouping factor 2 (two key bits per CMux, one gadget decomposition and one
- * FFT round trip per pair; n even, k = 1, l_pbs = 1).  bsk2 standard domain: [n/2][3][k+1][l][k+1][N] u64;
- * Fourier domain: [n/2][32 slices][3][k+1][k+1][32] complex f64 (sliced by frequency block so that the
- * kernel streams it through a small shared-memory ring).  Same inputs / outputs as fhe_b200_pbs. */
+ * FFT round trip per pair; n even, k = 1, l_pbs <= 2, and 2*beta_pbs <= 31 when l_pbs = 2).  bsk2 standard
+ * domain: [n/2][3][k+1][l][k+1][N] u64; Fourier domain: [n/2][32 blocks][3][k+1][l][k+1][32] complex f64
+ * (by frequency block so that the kernel streams it through a small shared-memory ring).  Same inputs / outputs as fhe_b200_pbs. */
 uint64_t fhe_b200_bsk2_words(const fhe_b200_pbs_params *p);
 int fhe_b200_bsk2_gen(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_s_small,
                       const uint8_t *d_S_big, uint64_t evk_seed, uint64_t *d_bsk2, void *stream);

@@ -87,6 +87,16 @@ def test_toy_multibit_single_level(O, cuda_dev):
     assert _pipeline(O, cuda_dev, TOY_L1, 4, 2, seed=5, multibit=True, tol_log2=-13) < -15
 
 
+def test_toy_multibit_two_levels(O, cuda_dev):
+    assert _pipeline(O, cuda_dev, TOY_L2, 6, 3, seed=8, multibit=True) < -15
+
+
+def test_full_parameter_set_d128_multibit(O, cuda_dev):
+    """The production configuration: two-level multi-bit blind rotation."""
+    from fhe_icp_b200.encrypted_compare import COMPARE_PARAMS
+    assert _pipeline(O, cuda_dev, COMPARE_PARAMS, 128, 37, seed=21, multibit=True, with_oracle=False) < -15.5
+
+
 def test_full_parameter_set_d128(O, cuda_dev):
     """n=742, N=2048, l=2, d=128: 256 bootstraps per document; one document also through the oracle."""
     from fhe_icp_b200.encrypted_compare import COMPARE_PARAMS
