@@ -172,6 +172,16 @@ class BatchProcessor:
             return self.fhe_model.predict_encrypted(X)
         return self.fhe_model.model.predict(X)
 
+    def _pair_engine(self):
+        """fhe="both": the product itself is evaluated under encryption (both vectors encrypted; the
+        reference multiplies them in the clear, batch_operations.py:226,273).  Built on first use."""
+        if getattr(self, "_pair", None) is None:
+            from .encrypted_compare import EncryptedCompare
+            d = 128
+            self._pair = EncryptedCompare(input_dim=d, device=self.device).keygen()
+            self._pair.fit_scale(np.array([-1.0, 1.0]) / np.sqrt(d))  # unit-norm embeddings: std 1/sqrt(d)
+        return self._pair
+
     def encrypt_documents(self, texts: List[str], doc_ids: Optional[List[str]] = None,
                           metadata: Optional[List[Dict]] = None) -> List[str]:
         self._require_model()
@@ -197,6 +207,8 @@ class BatchProcessor:
         self._require_model()
         doc1 = self.storage.load(doc_id1)
         doc2 = self.storage.load(doc_id2)
+        if self.fhe == "both":
+            return float(self._pair_engine().similarity(doc1.encrypted_embedding, doc2.encrypted_embedding[None, :])[0])
         X = (doc1.encrypted_embedding * doc2.encrypted_embedding).reshape(1, -1)
         return float(self._predict(X)[0])
 
@@ -207,8 +219,11 @@ class BatchProcessor:
         all_docs = self.storage.list_documents()
         if not all_docs:
             return []
-        X = (query_reduced[None, :] * self.storage.matrix()).astype(np.float32)
-        scores = self._predict(X)
+        if self.fhe == "both":
+            scores = self._pair_engine().similarity(query_reduced, self.storage.matrix())
+        else:
+            X = (query_reduced[None, :] * self.storage.matrix()).astype(np.float32)
+            scores = self._predict(X)
         return rank_results([d["doc_id"] for d in all_docs], scores, top_k, min_similarity)
 
     def get_memory_stats(self) -> Dict[str, float]:

@@ -84,8 +84,9 @@ class FHEDocumentCLI:
 def build_parser() -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser(description="FHE Document Encryption and Comparison CLI (B200 engine)")
     parser.add_argument('--storage-dir', default='./encrypted_docs')
-    parser.add_argument('--fhe', default='execute', choices=['execute', 'disable'],
-                        help="execute = encrypted evaluation on the GPU (default); disable = the reference's clear path")
+    parser.add_argument('--fhe', default='execute', choices=['execute', 'disable', 'both'],
+                        help="execute = encrypted evaluation on the GPU (default); disable = the reference's clear path; "
+                             "both = both vectors encrypted, products evaluated by programmable bootstraps")
     parser.add_argument('--seed', type=int, default=0)
     subparsers = parser.add_subparsers(dest='command', help='Available commands')
     batch_parser = subparsers.add_parser('encrypt-batch', help='Encrypt multiple documents')

@@ -104,3 +104,22 @@ def test_32bit_wire_form_decrypts_identically(cuda_dev):
         y64, q64 = m.decrypt(out, return_q=True)
         y32, q32 = m.decrypt_compressed(m.compress_scores(out), return_q=True)
         assert np.array_equal(q64, q32) and np.array_equal(y64, y32) and np.array_equal(y64, m.predict_clear(X))
+
+
+def test_both_encrypted_mode_search_and_compare(processor):
+    """fhe="both": query and documents both encrypted.  Scores equal the clear
+    integer model of that path exactly and rank the topic's documents first."""
+    from fhe_icp_b200.batch_operations import BatchProcessor, rank_results
+    bp = BatchProcessor(fhe="both", seed=0, init_model=False, fhe_model=processor.fhe_model, storage=processor.storage)
+    eng = bp._pair_engine()
+    q = bp.reducer.transform(bp.embedder.get_embedding("quantum entanglement").reshape(1, -1))[0]
+    M = bp.storage.matrix()[:60]
+    sim = eng.similarity(q, M)
+    assert np.array_equal(sim, eng.dequantize(eng.compare_clear(q, M)))
+    cos = M @ q
+    top = set(np.argsort(-cos)[:12])
+    assert top == set(np.argsort(-sim, kind="stable")[:12])       # the 12 "quantum" documents of the first 60
+    a, b = bp.storage.load("d0").encrypted_embedding, bp.storage.load("d5").encrypted_embedding
+    got = bp.compare_encrypted("d0", "d5")
+    assert got == float(eng.dequantize(eng.compare_clear(a, b[None, :]))[0])
+    assert abs(got - float(a @ b)) < 0.12 and got > bp.compare_encrypted("d0", "d1")
