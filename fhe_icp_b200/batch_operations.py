@@ -226,6 +226,25 @@ class BatchProcessor:
             scores = self._predict(X)
         return rank_results([d["doc_id"] for d in all_docs], scores, top_k, min_similarity)
 
+    def filter_similar(self, query_text: str, min_similarity: float = 0.5) -> List[str]:
+        """fhe="both" only: the test `similarity >= min_similarity` (batch_operations.py:278) itself runs under
+        encryption; the client decrypts one bit per document and never sees the scores."""
+        if self.fhe != "both":
+            raise RuntimeError("filter_similar needs fhe='both'")
+        self._require_model()
+        all_docs = self.storage.list_documents()
+        if not all_docs:
+            return []
+        from .encrypted_compare import EncryptedThreshold
+        eng = self._pair_engine()
+        if getattr(self, "_thr", None) is None:
+            self._thr = EncryptedThreshold(eng)
+        q = self.reducer.transform(self.embedder.get_embedding(query_text).reshape(1, -1))[0]
+        ct_q = eng.encrypt(eng.quantize(q), enc_seed=1, ct_base=0)
+        ct_d = eng.encrypt(eng.quantize(self.storage.matrix()), enc_seed=1, ct_base=eng.d)
+        bits = self._thr.decrypt(self._thr.ge(eng.scores(ct_q, ct_d), self._thr.threshold_to_int(min_similarity)))
+        return [d["doc_id"] for d, b in zip(all_docs, bits) if b]
+
     def get_memory_stats(self) -> Dict[str, float]:
         try:
             import psutil

@@ -319,6 +319,29 @@ int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx* ctx, const uint64_t* d_in, int64_t 
     return FHE_B200_OK;
 }
 
+int fhe_b200_lwe_shl_add(fhe_b200_ctx* ctx, const uint64_t* d_in, int64_t in_stride, int64_t count, int32_t words,
+                         int32_t shift, uint64_t offset, uint64_t* d_out, int64_t out_stride, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(count >= 0 && words >= 1 && in_stride >= words && out_stride >= words && shift >= 0 && shift < 64,
+            "bad shape");
+    if (count == 0) return FHE_B200_OK;
+    REQUIRE(d_in && d_out, "null device pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_shl_add(d_in, in_stride, count, words, shift, offset, d_out, out_stride, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_lwe_sub_plain(fhe_b200_ctx* ctx, uint64_t* d_acc, int64_t acc_stride, const uint64_t* d_x, int64_t count,
+                           int32_t words, uint64_t plain, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(count >= 0 && words >= 1 && acc_stride >= words, "bad shape");
+    if (count == 0) return FHE_B200_OK;
+    REQUIRE(d_acc && d_x, "null device pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_sub_plain(d_acc, acc_stride, d_x, count, words, plain, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 // ------------------------------------------------------------------------------- KS / PBS
 static int check_pbs_params(const fhe_b200_pbs_params* p, const char* fn) {
     if (!p) return fail(FHE_B200_ERR_INVALID, "%s: null params", fn);

@@ -524,6 +524,51 @@ cudaError_t launch_lwe_pair_diff_sum(const uint64_t* d_in, int64_t B, int d, int
     return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------- bit-extraction glue
+// Exact encrypted threshold (sign of a wide message by LSB-first bit extraction): per step the
+// ciphertext is scaled by a power of two (the wanted bit moves to the top of the torus, higher bits
+// wrap away) and a plaintext offset is added to the body; the bootstrapped bit is then subtracted.
+__global__ void __launch_bounds__(PAIR_THREADS)
+lwe_shl_add_kernel(const uint64_t* __restrict__ in, int64_t in_stride, int64_t count, int words, int shift,
+                   uint64_t offset, uint64_t* __restrict__ out, int64_t out_stride) {
+    const int64_t idx = (int64_t)blockIdx.x * PAIR_THREADS + threadIdx.x;
+    if (idx >= count * out_stride) return;
+    const int64_t row = idx / out_stride;
+    const int w = (int)(idx - row * out_stride);
+    out[idx] = w < words ? (in[row * in_stride + w] << shift) + (w == words - 1 ? offset : 0) : 0;
+}
+
+cudaError_t launch_lwe_shl_add(const uint64_t* d_in, int64_t in_stride, int64_t count, int words, int shift,
+                               uint64_t offset, uint64_t* d_out, int64_t out_stride, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t total = count * out_stride;
+    lwe_shl_add_kernel<<<(unsigned)((total + PAIR_THREADS - 1) / PAIR_THREADS), PAIR_THREADS, 0, s>>>(
+        d_in, in_stride, count, words, shift, offset, d_out, out_stride);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// acc[row][w] -= x[row][w] (+ plain on the body), acc rows acc_stride apart, x rows `words` apart
+__global__ void __launch_bounds__(PAIR_THREADS)
+lwe_sub_plain_kernel(uint64_t* __restrict__ acc, int64_t acc_stride, const uint64_t* __restrict__ x, int64_t count,
+                     int words, uint64_t plain) {
+    const int64_t idx = (int64_t)blockIdx.x * PAIR_THREADS + threadIdx.x;
+    if (idx >= count * words) return;
+    const int64_t row = idx / words;
+    const int w = (int)(idx - row * words);
+    acc[row * acc_stride + w] -= x[idx] + (w == words - 1 ? plain : 0);
+}
+
+cudaError_t launch_lwe_sub_plain(uint64_t* d_acc, int64_t acc_stride, const uint64_t* d_x, int64_t count, int words,
+                                 uint64_t plain, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t total = count * words;
+    lwe_sub_plain_kernel<<<(unsigned)((total + PAIR_THREADS - 1) / PAIR_THREADS), PAIR_THREADS, 0, s>>>(
+        d_acc, acc_stride, d_x, count, words, plain);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ----------------------------------------------------------------------------- quantize / finalize
 // q = clip(rint(x / scale + zp), qmin, qmax) in float64, the UniformQuantizer rule
 // (SURVEY.md Appendix A.1); IEEE div/add/rint => identical to numpy.

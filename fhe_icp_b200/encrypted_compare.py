@@ -139,3 +139,60 @@ class EncryptedCompare:
     def _need_keys(self):
         if self.s is None:
             raise RuntimeError("No secret key. Call keygen() first.")
+
+
+BIT_SHIFT = 60      # threshold results: one bit at 2^60, so up to 7 of them can be added (score buckets)
+
+
+class EncryptedThreshold:
+    """`score >= T` evaluated under encryption, exactly.
+
+    The reference thresholds decrypted scores in the clear (`batch_operations.py:278`
+    `if similarity >= min_similarity`) and buckets them at 0.9 / 0.7 / 0.5 (`fhe_cli.py:169-176`).  Here
+    the server returns only the encrypted outcome.  A single N=2048 bootstrap resolves ~5 message
+    bits, the score has 13, so the sign of v = score - T is taken by LSB-first bit extraction: for
+    i = 0..11 the ciphertext is scaled by 2^(12-i) (bit i moves to the top of the torus, the bits above
+    wrap away, the bits below are already cleared), offset by 1/4, keyswitched to the small key and
+    bootstrapped with a constant (sign) test polynomial, which returns bit i at its own weight with
+    fresh noise; that is subtracted.  What remains is the sign bit; a 13th bootstrap maps it to
+    (score >= T) * 2^60.  Every step has a decision margin of 1/4 of the torus against keyswitch +
+    mod-switch noise of ~2^-8.6, so the result is exact for every score and threshold."""
+
+    def __init__(self, ec: EncryptedCompare):
+        self.ec = ec
+        p = ec.p
+        ec._need_keys()
+        self.ksk32 = E.ksk_to_32(p, E.ksk_gen(p, ec.S, ec.s, ec.evk_seed))
+        mask = (1 << 64) - 1
+        consts = [(-(1 << (OUT_SHIFT - 1 + i))) & mask for i in range(SCORE_BITS - 1)] + [1 << (BIT_SHIFT - 1)]
+        self.luts = E.from_u64_numpy(np.repeat(np.array(consts, dtype=np.uint64)[:, None], p.N, axis=1), ec.dev)
+
+    def threshold_to_int(self, min_similarity: float) -> int:
+        """Smallest integer score whose dequantized value is >= min_similarity."""
+        lim = 1 << (SCORE_BITS - 1)
+        return int(np.clip(np.ceil(min_similarity / (self.ec.scale ** 2) - 1e-9), -lim // 2, lim // 2 - 1))
+
+    def ge(self, scores: torch.Tensor, T: int) -> torch.Tensor:
+        """scores [B, stride] (big key) -> [B, kN+2] encrypting (score >= T) * 2^BIT_SHIFT."""
+        ec, p = self.ec, self.ec.p
+        words = p.k * p.N + 1
+        fn = E.pbs_mb2 if ec.multibit else E.pbs
+        acc = E.shl_add(scores.contiguous(), words, 0, -(int(T) << OUT_SHIFT))          # v = score - T
+        for i in range(SCORE_BITS):
+            last = i == SCORE_BITS - 1
+            tmp = E.shl_add(acc, words, SCORE_BITS - 1 - i, 1 << 62)                       # bit i on top, + 1/4
+            pb = fn(p, ec.bskf, E.keyswitch32(p, self.ksk32, tmp), self.luts[i])
+            if last:   # -/+ 2^59 for sign bit 0/1 -> (1 - sign) * 2^60
+                return E.shl_add(pb, words, 0, 1 << (BIT_SHIFT - 1), out_stride=E.even_stride(words - 1))
+            E.sub_plain(acc, pb, 1 << (OUT_SHIFT - 1 + i))                                 # clear bit i
+
+    def buckets(self, scores: torch.Tensor, thresholds) -> torch.Tensor:
+        """Number of thresholds each score reaches (e.g. 0.5 / 0.7 / 0.9 -> 0..3), one ciphertext per score."""
+        out = None
+        for T in thresholds:
+            g = self.ge(scores, T)
+            out = g if out is None else E.accumulate(out, g)
+        return out
+
+    def decrypt(self, bits: torch.Tensor) -> np.ndarray:
+        return E.lwe_decrypt(self.ec.S, bits, BIT_SHIFT).cpu().numpy() & 15

@@ -172,6 +172,29 @@ def pair_diff_sum(sq: torch.Tensor, out: torch.Tensor | None = None) -> torch.Te
     return out
 
 
+def shl_add(ct: torch.Tensor, words: int, shift: int, offset: int, out_stride: int | None = None) -> torch.Tensor:
+    """ct [count, stride] -> [count, out_stride or words] = (row << shift), offset added to the body,
+    words beyond the ciphertext zeroed."""
+    dev = ct.device
+    count, stride = ct.shape
+    out_stride = out_stride or words
+    assert ct.is_contiguous() and words <= stride and out_stride >= words
+    out = torch.empty((count, out_stride), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_lwe_shl_add(_ctx(dev).handle, _ptr(ct), stride, count, words, shift,
+                                         offset & 0xFFFFFFFFFFFFFFFF, _ptr(out), out_stride, _stream(dev)))
+    return out
+
+
+def sub_plain(acc: torch.Tensor, x: torch.Tensor, plain: int) -> torch.Tensor:
+    """acc [count, stride] -= x [count, words] (first `words` words of each row), body -= plain."""
+    dev = acc.device
+    count, words = x.shape
+    assert acc.is_contiguous() and x.is_contiguous() and acc.shape[0] == count and acc.shape[1] >= words
+    N.check(N.lib().fhe_b200_lwe_sub_plain(_ctx(dev).handle, _ptr(acc), acc.shape[1], _ptr(x), count, words,
+                                           plain & 0xFFFFFFFFFFFFFFFF, _stream(dev)))
+    return acc
+
+
 # ------------------------------------------------------------------------------- KS / PBS
 def make_pbs_params(n=742, k=1, N_poly=2048, l_pbs=1, beta_pbs=23, l_ks=5, beta_ks=3,
                     log2_sigma_lwe=-17.1, log2_sigma_glwe=-51.6) -> N.PBSParams:

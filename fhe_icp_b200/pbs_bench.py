@@ -120,6 +120,7 @@ def measure_pair(dev, args, docs: int = 74):
     bootstraps per document at d = 128 (n=742, N=2048, l_pbs=2, two-level multi-bit blind rotation)."""
     import time
     import torch
+    from . import engine as E_
     from .encrypted_compare import COMPARE_PARAMS, EncryptedCompare, IN_SHIFT, OUT_SHIFT, P_BITS
     d = 128
     ec = EncryptedCompare(input_dim=d, device=dev).keygen()
@@ -145,6 +146,23 @@ def measure_pair(dev, args, docs: int = 74):
            "e2e": {"value": docs / e2e_s, "unit": "comparisons/s"},
            "pbs_per_sec": 2 * d * docs / (ms * 1e-3), "docs": docs, "d": d, "pbs_per_comparison": 2 * d,
            "params": dict(COMPARE_PARAMS), "kernel": "pbs_kernel_mb2<2,2>", "exact_vs_clear_integer_model": exact}
+    # exact encrypted threshold (13 keyswitch + PBS per score) on a batch of score ciphertexts
+    from .encrypted_compare import EncryptedThreshold
+    th = EncryptedThreshold(ec)
+    nthr = 592
+    vals = rng.randint(-1536, 2049, size=nthr)
+    sct = E_.lwe_encrypt(ec.S, torch.as_tensor(vals), OUT_SHIFT, 2.0 ** (64 - 18), enc_seed=5, ct_base=0)
+    T = th.threshold_to_int(0.5)
+    th.ge(sct[:8], T)
+    torch.cuda.synchronize()
+    e0.record()
+    bits = th.ge(sct, T)
+    e1.record()
+    torch.cuda.synchronize()
+    thr_ms = e0.elapsed_time(e1)
+    res["threshold"] = {"metric": "encrypted_thresholds_per_sec", "value": nthr / (thr_ms * 1e-3), "batch": nthr,
+                        "ks_pbs_per_threshold": 13,
+                        "exact": bool(np.array_equal(th.decrypt(bits), (vals >= T).astype(np.int64)))}
     # bench.py's CPU-baseline leg re-evaluates this sample with the oracle (the product never imports it)
     res["_sample"] = {"xq": xq, "yq": yq[:1], "expect": int((yq @ xq)[0]), "key_seed": ec.key_seed,
                       "evk_seed": ec.evk_seed, "stride": int(ct_q.shape[-1]), "in_shift": IN_SHIFT,

@@ -151,6 +151,16 @@ int fhe_b200_lwe_pair_addsub(fhe_b200_ctx *ctx, const uint64_t *d_q, const uint6
 int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx *ctx, const uint64_t *d_in, int64_t B, int32_t d, int32_t words,
                                int64_t out_stride, uint64_t *d_out, void *stream);
 
+/* ---- exact encrypted threshold glue -------------------------------
+ * Replaces the CLEAR test `similarity >= min_similarity` of batch_operations.py:278 (and the score
+ * buckets of fhe_cli.py:169-176) by the sign of (score - T) computed under encryption: LSB-first bit
+ * extraction, one keyswitch + PBS per bit.  shl_add: d_out [count][out_stride] = (row << shift) with
+ * `offset` added to the body (word words-1), words beyond zeroed; sub_plain: d_acc row -= d_x row, body additionally -= plain. */
+int fhe_b200_lwe_shl_add(fhe_b200_ctx *ctx, const uint64_t *d_in, int64_t in_stride, int64_t count, int32_t words,
+                         int32_t shift, uint64_t offset, uint64_t *d_out, int64_t out_stride, void *stream);
+int fhe_b200_lwe_sub_plain(fhe_b200_ctx *ctx, uint64_t *d_acc, int64_t acc_stride, const uint64_t *d_x,
+                           int64_t count, int32_t words, uint64_t plain, void *stream);
+
 /* ---- keyswitch + programmable bootstrap ---------------------------------------
  * north-star primitives; not exercised by the reference's compiled circuit. */
 int fhe_b200_ksk_gen(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_S_big,

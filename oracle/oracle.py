@@ -295,6 +295,29 @@ def encrypted_product_scores(p: PBSParams, bskf, ct_q, ct_docs, p_bits: int, out
     return pair_diff_sum(sq.reshape(B, d, 2, -1))
 
 
+def encrypted_ge(p: PBSParams, ksk32, bskf, scores, T: int, score_bits: int, out_shift: int, bit_shift: int,
+                 multibit: bool = False) -> np.ndarray:
+    """SURVEY.md 8f N3 (replaces the clear test of batch_operations.py:278): scores [B, >=kN+1] big-key
+    LWE of a signed score_bits-bit value at 2^out_shift -> [B, kN+1] LWE of (score >= T) * 2^bit_shift,
+    by LSB-first bit extraction (one 32-bit keyswitch + sign bootstrap per bit)."""
+    words = p.k * p.N + 1
+    M64 = 0xFFFFFFFFFFFFFFFF
+    acc = np.array(np.asarray(scores, dtype=np.uint64)[:, :words])
+    acc[:, -1] -= np.uint64((int(T) << out_shift) & M64)
+    fn = pbs_mb2 if multibit else pbs
+    for i in range(score_bits):
+        last = i == score_bits - 1
+        tmp = acc << np.uint64(score_bits - 1 - i)
+        tmp[:, -1] += np.uint64(1 << 62)
+        c = (1 << (bit_shift - 1)) if last else (-(1 << (out_shift - 1 + i))) & M64
+        pb = fn(p, bskf, keyswitch32(p, ksk32, tmp), np.full(p.N, c, dtype=np.uint64))
+        if last:
+            pb[:, -1] += np.uint64(1 << (bit_shift - 1))
+            return pb
+        acc -= pb
+        acc[:, -1] -= np.uint64(1 << (out_shift - 1 + i))
+
+
 def negacyclic_mul_fft(a_small, b_torus) -> np.ndarray:
     a = np.ascontiguousarray(a_small, dtype=np.int64); b = np.ascontiguousarray(b_torus, dtype=np.uint64)
     out = np.zeros(a.size, dtype=np.uint64)

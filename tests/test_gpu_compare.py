@@ -120,3 +120,62 @@ def test_float_pipeline_tracks_cosine(cuda_dev):
     cos = docs @ q
     assert np.abs(sim - cos).max() < 0.12          # 3-bit factors: coarse but unbiased enough to rank
     assert set(np.argsort(-sim)[: B // 2]) == set(range(B // 2))
+
+
+# ---------------------------------------------------------------------------------------------- encrypted threshold (N3)
+def _score_cts(ec, values):
+    """Big-key encryptions of given integer scores at the score encoding (test fixture: stands in for
+    the output of EncryptedCompare.scores, with the PBS-sum noise level 2^-18)."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    from fhe_icp_b200.encrypted_compare import OUT_SHIFT
+    return E.lwe_encrypt(ec.S, torch.as_tensor(np.asarray(values, dtype=np.int64)), OUT_SHIFT, 2.0 ** (64 - 18),
+                         enc_seed=77, ct_base=0)
+
+
+@pytest.mark.parametrize("params_name,multibit", [("toy", False), ("toy", True), ("full", True)])
+def test_encrypted_threshold_exact(O, cuda_dev, params_name, multibit):
+    """(score >= T) under encryption equals the clear comparison for every score around every
+    threshold, including score == T and the extremes of the 13-bit range; GPU == oracle."""
+    from fhe_icp_b200 import engine as E
+    from fhe_icp_b200.encrypted_compare import (BIT_SHIFT, COMPARE_PARAMS, OUT_SHIFT, SCORE_BITS, EncryptedCompare,
+                                                EncryptedThreshold)
+    params = TOY_L2 if params_name == "toy" else COMPARE_PARAMS
+    ec = EncryptedCompare(input_dim=128, params=params, device=cuda_dev, multibit=multibit).keygen()
+    th = EncryptedThreshold(ec)
+    vals = np.array([-1536, -1, 0, 1, 2, 165, 166, 167, 255, 256, 257, 1023, 1024, 2047, 2048, -300, 777])
+    cts = _score_cts(ec, vals)
+    for T in ([166, 0] if params_name == "full" else [166, 0, -1536, 2047, 1, 256, -299]):
+        got = th.decrypt(th.ge(cts, T))
+        assert np.array_equal(got, (vals >= T).astype(np.int64)), (T, got)
+    if params_name == "toy":
+        op = _oparams(O, params)
+        os_, oS = O.secret_key(ec.key_seed, 0, op.n), O.secret_key(ec.key_seed, 1, op.k * op.N)
+        ksk32 = O.ksk_to_32(op, O.ksk_gen(op, oS, os_, ec.evk_seed))
+        assert np.array_equal(th.ksk32.cpu().numpy().view(np.uint32).reshape(ksk32.shape), ksk32)
+        bskf = (O.bsk2_to_fourier(op, O.bsk2_gen(op, os_, oS, ec.evk_seed)) if multibit
+                else O.bsk_to_fourier(op, O.bsk_gen(op, os_, oS, ec.evk_seed)))
+        ref = O.encrypted_ge(op, ksk32, bskf, _u64(cts), 166, SCORE_BITS, OUT_SHIFT, BIT_SHIFT, multibit=multibit)
+        assert np.array_equal(O.lwe_decrypt(oS, ref, BIT_SHIFT) & 15, (vals >= 166).astype(np.int64))
+    b = th.decrypt(th.buckets(cts, [166, 256, 1024]))
+    assert np.array_equal(b, (vals >= 166).astype(int) + (vals >= 256) + (vals >= 1024))
+
+
+def test_encrypted_threshold_on_real_scores(cuda_dev):
+    """End to end: both vectors encrypted -> encrypted scores -> encrypted (score >= min_similarity)."""
+    from fhe_icp_b200.encrypted_compare import EncryptedCompare, EncryptedThreshold
+    rng = np.random.RandomState(4)
+    d, B = 128, 12
+    q = rng.randn(d); q /= np.linalg.norm(q)
+    docs = rng.randn(B, d)
+    docs[:5] = 0.85 * q + 0.5 * docs[:5] / np.sqrt(d)
+    docs /= np.linalg.norm(docs, axis=1, keepdims=True)
+    ec = EncryptedCompare(input_dim=d, device=cuda_dev).keygen()
+    ec.fit_scale(np.array([-1.0, 1.0]) / np.sqrt(d))
+    sc = ec.scores(ec.encrypt(ec.quantize(q), 3, 0), ec.encrypt(ec.quantize(docs), 3, d))
+    ints = ec.decrypt(sc)
+    th = EncryptedThreshold(ec)
+    T = th.threshold_to_int(0.5)
+    hit = th.decrypt(th.ge(sc, T))
+    assert np.array_equal(hit, (ints >= T).astype(np.int64))
+    assert np.array_equal(hit.astype(bool), ec.dequantize(ints) >= 0.5) and hit[:5].all() and not hit[5:].any()

@@ -123,3 +123,12 @@ def test_both_encrypted_mode_search_and_compare(processor):
     got = bp.compare_encrypted("d0", "d5")
     assert got == float(eng.dequantize(eng.compare_clear(a, b[None, :]))[0])
     assert abs(got - float(a @ b)) < 0.12 and got > bp.compare_encrypted("d0", "d1")
+    # encrypted threshold: same documents as thresholding the decrypted scores of the same path
+    small = BatchProcessor(fhe="both", seed=0, init_model=False, fhe_model=processor.fhe_model)
+    small._pair, small.embedder = eng, bp.embedder
+    small.encrypt_documents([f"{t} document number {i} about things" for i, t in
+                             enumerate(["quantum", "cooking", "finance", "quantum", "biology", "sailing", "quantum"])],
+                            [f"s{i}" for i in range(7)])
+    hits = small.filter_similar("quantum entanglement", 0.5)
+    want = [i for i, _ in small.search_similar("quantum entanglement", top_k=10, min_similarity=0.5)]
+    assert sorted(hits) == sorted(want) == ["s0", "s3", "s6"]

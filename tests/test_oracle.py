@@ -168,3 +168,17 @@ def test_encrypted_product_oracle_matches_clear_model(O):
     sc = O.encrypted_product_scores(p, bskf, cq, cd, 4, 51)
     dec = O.lwe_decrypt(S, sc, 51) & 8191
     assert np.array_equal(np.where(dec >= 4096, dec - 8192, dec), yq @ xq)
+
+
+def test_encrypted_threshold_oracle_exact(O):
+    """LSB-first bit extraction of (score - T) decides score >= T exactly."""
+    p = O.make_params(n=16, k=1, N=2048, l_pbs=2, beta_pbs=15, l_ks=4, beta_ks=4, log2_sigma_lwe=-30.0,
+                      log2_sigma_glwe=-51.6)
+    s, S = O.secret_key(3, 0, p.n), O.secret_key(3, 1, p.k * p.N)
+    bskf = O.bsk_to_fourier(p, O.bsk_gen(p, s, S, 4))
+    ksk32 = O.ksk_to_32(p, O.ksk_gen(p, S, s, 4))
+    vals = np.array([-1536, -1, 0, 41, 42, 43, 2048])
+    cts = O.lwe_encrypt(S, vals, 51, 2.0 ** (64 - 18), 9, 0)
+    for T in (42, 0, -1536):
+        out = O.encrypted_ge(p, ksk32, bskf, cts, T, 13, 51, 60)
+        assert np.array_equal(O.lwe_decrypt(S, out, 60) & 15, (vals >= T).astype(np.int64))
