@@ -240,9 +240,10 @@ class BatchProcessor:
         if getattr(self, "_thr", None) is None:
             self._thr = EncryptedThreshold(eng)
         q = self.reducer.transform(self.embedder.get_embedding(query_text).reshape(1, -1))[0]
-        ct_q = eng.encrypt(eng.quantize(q), enc_seed=1, ct_base=0)
-        ct_d = eng.encrypt(eng.quantize(self.storage.matrix()), enc_seed=1, ct_base=eng.d)
-        bits = self._thr.decrypt(self._thr.ge(eng.scores(ct_q, ct_d), self._thr.threshold_to_int(min_similarity)))
+        xq, yq = eng.quantize(q), eng.quantize(self.storage.matrix())
+        ct_q, ct_d = eng.encrypt(xq, enc_seed=1, ct_base=0), eng.encrypt(yq, enc_seed=1, ct_base=eng.d)
+        scores = eng.scores(ct_q, ct_d, eng.encrypt_norms(xq, 1, 0), eng.encrypt_norms(yq, 1, 1))
+        bits = self._thr.decrypt(self._thr.ge(scores, self._thr.threshold_to_int(min_similarity)))
         return [d["doc_id"] for d, b in zip(all_docs, bits) if b]
 
     def get_memory_stats(self) -> Dict[str, float]:

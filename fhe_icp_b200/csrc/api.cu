@@ -319,6 +319,31 @@ int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx* ctx, const uint64_t* d_in, int64_t 
     return FHE_B200_OK;
 }
 
+int fhe_b200_lwe_pair_add(fhe_b200_ctx* ctx, const uint64_t* d_q, const uint64_t* d_y, int64_t B, int32_t d,
+                          int32_t words, int64_t in_stride, uint64_t offset, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0 && d >= 1 && words >= 1 && in_stride >= words, "bad shape");
+    REQUIRE(B * (int64_t)d < ((int64_t)1 << 31), "too many ciphertext pairs for one launch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_q && d_y && d_out, "null device pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_pair_add(d_q, d_y, B, d, words, in_stride, offset, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_lwe_square_sum(fhe_b200_ctx* ctx, const uint64_t* d_sq, int64_t B, int32_t d, int32_t words,
+                            const uint64_t* d_norm_q, const uint64_t* d_norm_y, int64_t norm_stride,
+                            int64_t out_stride, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0 && d >= 1 && words >= 1 && out_stride >= words && norm_stride >= words, "bad shape");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_sq && d_norm_q && d_norm_y && d_out, "null device pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_lwe_square_sum(d_sq, B, d, words, d_norm_q, d_norm_y, norm_stride, out_stride, d_out,
+                                  (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 int fhe_b200_lwe_shl_add(fhe_b200_ctx* ctx, const uint64_t* d_in, int64_t in_stride, int64_t count, int32_t words,
                          int32_t shift, uint64_t offset, uint64_t* d_out, int64_t out_stride, void* stream) {
     REQUIRE(ctx, "null ctx");

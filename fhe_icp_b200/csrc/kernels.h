@@ -32,6 +32,11 @@ cudaError_t launch_lwe_decrypt32(const uint8_t* d_key, int n, int64_t stride, co
 cudaError_t launch_accumulate(uint64_t* d_acc, const uint64_t* d_x, int64_t words, cudaStream_t s);
 cudaError_t launch_lwe_pair_addsub(const uint64_t* d_q, const uint64_t* d_y, int64_t B, int d, int words,
                                    int64_t in_stride, uint64_t offset, uint64_t* d_out, cudaStream_t s);
+cudaError_t launch_lwe_pair_add(const uint64_t* d_q, const uint64_t* d_y, int64_t B, int d, int words,
+                                int64_t in_stride, uint64_t offset, uint64_t* d_out, cudaStream_t s);
+cudaError_t launch_lwe_square_sum(const uint64_t* d_sq, int64_t B, int d, int words, const uint64_t* d_norm_q,
+                                  const uint64_t* d_norm_y, int64_t norm_stride, int64_t out_stride, uint64_t* d_out,
+                                  cudaStream_t s);
 cudaError_t launch_lwe_shl_add(const uint64_t* d_in, int64_t in_stride, int64_t count, int words, int shift,
                                uint64_t offset, uint64_t* d_out, int64_t out_stride, cudaStream_t s);
 cudaError_t launch_lwe_sub_plain(uint64_t* d_acc, int64_t acc_stride, const uint64_t* d_x, int64_t count, int words,

@@ -524,6 +524,67 @@ cudaError_t launch_lwe_pair_diff_sum(const uint64_t* d_in, int64_t B, int d, int
     return cudaGetLastError();
 }
 
+// One bootstrap per dimension when each party also supplies an encryption of its own squared norm:
+// 2*sum_j x_j*y_j = sum_j (x_j+y_j)^2 - sum_j x_j^2 - sum_j y_j^2.  pair_add builds the d sums,
+// square_sum folds the d bootstrapped squares and subtracts the two norm ciphertexts.
+__global__ void __launch_bounds__(PAIR_THREADS)
+lwe_pair_add_kernel(const uint64_t* __restrict__ q, const uint64_t* __restrict__ y, int d, int words,
+                    int64_t in_stride, uint64_t offset, uint64_t* __restrict__ out) {
+    const int64_t row = blockIdx.x;  // b*d + j
+    const int j = (int)(row % d);
+    const uint64_t* qr = q + (size_t)j * in_stride;
+    const uint64_t* yr = y + (size_t)row * in_stride;
+    uint64_t* o = out + (size_t)row * words;
+    for (int w = threadIdx.x; w < words; w += PAIR_THREADS) o[w] = qr[w] + yr[w] + (w == words - 1 ? offset : 0);
+}
+
+cudaError_t launch_lwe_pair_add(const uint64_t* d_q, const uint64_t* d_y, int64_t B, int d, int words,
+                                int64_t in_stride, uint64_t offset, uint64_t* d_out, cudaStream_t s) {
+    if (B <= 0 || d <= 0) return cudaSuccess;
+    lwe_pair_add_kernel<<<(unsigned)(B * d), PAIR_THREADS, 0, s>>>(d_q, d_y, d, words, in_stride, offset, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// out[b][w] = sum_j sq[b][j][w] - norm_q[w] - norm_y[b][w]
+__global__ void __launch_bounds__(PAIR_THREADS)
+lwe_square_sum_kernel(const uint64_t* __restrict__ sq, int d, int words, const uint64_t* __restrict__ norm_q,
+                      const uint64_t* __restrict__ norm_y, int64_t norm_stride, int64_t out_stride,
+                      uint64_t* __restrict__ out) {
+    const int w = blockIdx.x * PAIR_THREADS + threadIdx.x;
+    if (w >= words) {
+        if (w < out_stride) out[(size_t)blockIdx.y * out_stride + w] = 0;  // row padding
+        return;
+    }
+    const uint64_t* base = sq + (size_t)blockIdx.y * d * words + w;
+    uint64_t acc = 0 - norm_q[w] - norm_y[(size_t)blockIdx.y * norm_stride + w];
+    int j = 0;
+    for (; j + 8 <= d; j += 8) {
+        uint64_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(base + (size_t)(j + u) * words);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; j < d; ++j) acc += base[(size_t)j * words];
+    out[(size_t)blockIdx.y * out_stride + w] = acc;
+}
+
+cudaError_t launch_lwe_square_sum(const uint64_t* d_sq, int64_t B, int d, int words, const uint64_t* d_norm_q,
+                                  const uint64_t* d_norm_y, int64_t norm_stride, int64_t out_stride, uint64_t* d_out,
+                                  cudaStream_t s) {
+    if (B <= 0) return cudaSuccess;
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {  // gridDim.y limit
+        const unsigned nb = (unsigned)((B - b0) < 65535 ? (B - b0) : 65535);
+        dim3 grid((unsigned)((out_stride + PAIR_THREADS - 1) / PAIR_THREADS), nb);
+        lwe_square_sum_kernel<<<grid, PAIR_THREADS, 0, s>>>(d_sq + (size_t)b0 * d * words, d, words, d_norm_q,
+                                                           d_norm_y + (size_t)b0 * norm_stride, norm_stride, out_stride,
+                                                           d_out + (size_t)b0 * out_stride);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
 // ----------------------------------------------------------------------------- bit-extraction glue
 // Exact encrypted threshold (sign of a wide message by LSB-first bit extraction): per step the
 // ciphertext is scaled by a power of two (the wanted bit moves to the top of the torus, higher bits

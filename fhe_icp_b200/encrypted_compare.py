@@ -11,6 +11,13 @@ so one comparison of two d-dimensional vectors is 2d programmable bootstraps (ta
 quarter square) on sums / differences of the two parties' ciphertexts, followed by a wrapping sum
 of the 2d outputs into ONE score ciphertext per document, decrypted by the client.
 
+Each party knows its own vector, so it can also send an encryption of its own squared norm; then
+
+    2 * sum_j x_j*y_j = sum_j (x_j+y_j)^2 - sum_j x_j^2 - sum_j y_j^2
+
+needs only d bootstraps (of the square table) per comparison.  That is the default protocol
+(`encrypt_norms`, `scores(..., norm_q, norm_docs)`); both produce the same score encoding.
+
 Quantization is of the FACTORS (signed `in_bits`-bit integers, symmetric scale), not of the product
 as in the reference, so the scores are not bit-comparable to `FHESimilarityModel`'s; the parity
 oracle for this path is its own clear integer model `sum_j xq_j * yq_j` (`compare_clear`) and the
@@ -42,6 +49,14 @@ def quarter_square_table(p_bits: int = P_BITS) -> np.ndarray:
     return (w * w) // 4
 
 
+def square_table(p_bits: int = P_BITS) -> np.ndarray:
+    w = np.arange(1 << p_bits, dtype=np.int64) - (1 << (p_bits - 1))
+    return w * w
+
+
+NORM_CT_BASE = 1 << 40   # ciphertext ids of the squared-norm encryptions (disjoint from the vectors')
+
+
 class EncryptedCompare:
     """Client + server halves of the encrypted x encrypted cosine score.
 
@@ -65,6 +80,8 @@ class EncryptedCompare:
         self.scale = None
         self.s = self.S = self.bskf = None
         self.lut = E.from_u64_numpy(E.make_lut_poly(quarter_square_table(), P_BITS, self.p.N, OUT_SHIFT), self.dev)
+        # one-bootstrap protocol: (w-8)^2 at half the score unit, so that sum - norms = 2*sum(xy) * 2^(OUT_SHIFT-1)
+        self.lut_sq = E.from_u64_numpy(E.make_lut_poly(square_table(), P_BITS, self.p.N, OUT_SHIFT - 1), self.dev)
 
     # ---- client
     def keygen(self) -> "EncryptedCompare":
@@ -101,15 +118,24 @@ class EncryptedCompare:
         m = torch.as_tensor(np.ascontiguousarray(Xq, dtype=np.int64))
         return E.lwe_encrypt(self.s, m, IN_SHIFT, self.p.sigma_lwe_abs, enc_seed, ct_base)
 
+    def encrypt_norms(self, Xq: np.ndarray, enc_seed: int, ct_base: int = 0) -> torch.Tensor:
+        """Xq int [.., d] -> big-key ciphertexts [.., kN+2] of sum_j xq_j^2 at 2^(OUT_SHIFT-1)."""
+        self._need_keys()
+        Xq = np.asarray(Xq, dtype=np.int64)
+        m = torch.as_tensor(np.ascontiguousarray((Xq * Xq).sum(axis=-1)))
+        return E.lwe_encrypt(self.S, m, OUT_SHIFT - 1, self.p.sigma_glwe_abs, enc_seed, NORM_CT_BASE + ct_base)
+
     def decrypt(self, scores: torch.Tensor) -> np.ndarray:
         self._need_keys()
         v = E.lwe_decrypt(self.S, scores, OUT_SHIFT).cpu().numpy() & ((1 << SCORE_BITS) - 1)
         return np.where(v >= (1 << (SCORE_BITS - 1)), v - (1 << SCORE_BITS), v)
 
     # ---- server
-    def scores(self, ct_query: torch.Tensor, ct_docs: torch.Tensor) -> torch.Tensor:
+    def scores(self, ct_query: torch.Tensor, ct_docs: torch.Tensor, norm_query: torch.Tensor | None = None,
+               norm_docs: torch.Tensor | None = None) -> torch.Tensor:
         """ct_query [d, stride], ct_docs [B, d, stride] -> [B, kN+2] encrypted sum_j x_j*y_j (big key;
-        ciphertext = first kN+1 words of a row)."""
+        ciphertext = first kN+1 words of a row).  With the two parties' encrypted squared norms
+        (norm_query [kN+2], norm_docs [B, kN+2]) one bootstrap per dimension, otherwise two."""
         if self.bskf is None:
             raise RuntimeError("No evaluation key. Call keygen() (or load one) first.")
         p, d = self.p, self.d
@@ -118,11 +144,21 @@ class EncryptedCompare:
         out = torch.empty((B, E.even_stride(p.k * p.N)), dtype=torch.int64, device=self.dev)
         docs_per_chunk = max(1, self.chunk_pbs // (2 * d))
         fn = E.pbs_mb2 if self.multibit else E.pbs
+        if (norm_query is None) != (norm_docs is None):
+            raise ValueError("give both squared-norm ciphertexts or neither")
+        if norm_query is not None:
+            docs_per_chunk *= 2
+            nq = norm_query.reshape(-1).contiguous()
         for b0 in range(0, B, docs_per_chunk):
             b1 = min(B, b0 + docs_per_chunk)
-            pairs = E.pair_addsub(ct_query, ct_docs[b0:b1], words, 1 << 62)
-            sq = fn(p, self.bskf, pairs.view(-1, words), self.lut)
-            E.pair_diff_sum(sq.view(b1 - b0, d, 2, -1), out[b0:b1])
+            if norm_query is None:
+                pairs = E.pair_addsub(ct_query, ct_docs[b0:b1], words, 1 << 62)
+                sq = fn(p, self.bskf, pairs.view(-1, words), self.lut)
+                E.pair_diff_sum(sq.view(b1 - b0, d, 2, -1), out[b0:b1])
+            else:
+                sums = E.pair_add(ct_query, ct_docs[b0:b1], words, 1 << 62)
+                sq = fn(p, self.bskf, sums.view(-1, words), self.lut_sq)
+                E.square_sum(sq.view(b1 - b0, d, -1), nq, norm_docs[b0:b1], out[b0:b1])
         return out
 
     # ---- whole pipeline, float in / float out
@@ -130,11 +166,15 @@ class EncryptedCompare:
         """The clear integer model this path must reproduce exactly: sum_j xq_j * yq_j."""
         return self.quantize(docs) @ self.quantize(q)
 
-    def similarity(self, q: np.ndarray, docs: np.ndarray, enc_seed: int = 1) -> np.ndarray:
+    def similarity(self, q: np.ndarray, docs: np.ndarray, enc_seed: int = 1, norms: bool = True) -> np.ndarray:
         docs = np.atleast_2d(docs)
-        ct_q = self.encrypt(self.quantize(q), enc_seed, 0)
-        ct_d = self.encrypt(self.quantize(docs), enc_seed, self.d)
-        return self.dequantize(self.decrypt(self.scores(ct_q, ct_d)))
+        xq, yq = self.quantize(q), self.quantize(docs)
+        ct_q = self.encrypt(xq, enc_seed, 0)
+        ct_d = self.encrypt(yq, enc_seed, self.d)
+        if not norms:
+            return self.dequantize(self.decrypt(self.scores(ct_q, ct_d)))
+        nq, nd = self.encrypt_norms(xq, enc_seed, 0), self.encrypt_norms(yq, enc_seed, 1)
+        return self.dequantize(self.decrypt(self.scores(ct_q, ct_d, nq, nd)))
 
     def _need_keys(self):
         if self.s is None:

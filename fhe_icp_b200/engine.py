@@ -172,6 +172,31 @@ def pair_diff_sum(sq: torch.Tensor, out: torch.Tensor | None = None) -> torch.Te
     return out
 
 
+def pair_add(q: torch.Tensor, y: torch.Tensor, words: int, offset: int) -> torch.Tensor:
+    """q [d,stride], y [B,d,stride] -> [B,d,words] = q + y + offset (offset on the body)."""
+    dev = y.device
+    B, d, stride = y.shape
+    assert q.shape == (d, stride) and q.is_contiguous() and y.is_contiguous() and words <= stride
+    out = torch.empty((B, d, words), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_lwe_pair_add(_ctx(dev).handle, _ptr(q), _ptr(y), B, d, words, stride,
+                                          offset & 0xFFFFFFFFFFFFFFFF, _ptr(out), _stream(dev)))
+    return out
+
+
+def square_sum(sq: torch.Tensor, norm_q: torch.Tensor, norm_y: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """sq [B,d,words], norm_q [>=words], norm_y [B,norm_stride] -> [B,even_stride] = sum_j sq[:,j] - norm_q - norm_y."""
+    dev = sq.device
+    B, d, words = sq.shape
+    assert sq.is_contiguous() and norm_q.is_contiguous() and norm_y.is_contiguous()
+    assert norm_q.numel() >= words and norm_y.shape[0] == B and norm_y.shape[1] >= words
+    if out is None:
+        out = torch.empty((B, even_stride(words - 1)), dtype=torch.int64, device=dev)
+    assert out.is_contiguous() and out.shape[0] == B and out.shape[1] >= words
+    N.check(N.lib().fhe_b200_lwe_square_sum(_ctx(dev).handle, _ptr(sq), B, d, words, _ptr(norm_q), _ptr(norm_y),
+                                            norm_y.shape[1], out.shape[1], _ptr(out), _stream(dev)))
+    return out
+
+
 def shl_add(ct: torch.Tensor, words: int, shift: int, offset: int, out_stride: int | None = None) -> torch.Tensor:
     """ct [count, stride] -> [count, out_stride or words] = (row << shift), offset added to the body,
     words beyond the ciphertext zeroed."""

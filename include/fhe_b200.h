@@ -151,6 +151,17 @@ int fhe_b200_lwe_pair_addsub(fhe_b200_ctx *ctx, const uint64_t *d_q, const uint6
 int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx *ctx, const uint64_t *d_in, int64_t B, int32_t d, int32_t words,
                                int64_t out_stride, uint64_t *d_out, void *stream);
 
+/* One bootstrap per dimension instead of two when each party also sends an encryption of its own
+ * squared norm (big key, same scale as the bootstrapped squares):
+ *   2 * sum_j x_j*y_j = sum_j (x_j+y_j)^2 - sum_j x_j^2 - sum_j y_j^2.
+ * pair_add: d_out [B][d][words] = q + y + offset.  square_sum: d_out [B][out_stride] =
+ * sum_j d_sq[b][j] - d_norm_q - d_norm_y[b] (norm rows norm_stride words apart), padding zeroed. */
+int fhe_b200_lwe_pair_add(fhe_b200_ctx *ctx, const uint64_t *d_q, const uint64_t *d_y, int64_t B, int32_t d,
+                          int32_t words, int64_t in_stride, uint64_t offset, uint64_t *d_out, void *stream);
+int fhe_b200_lwe_square_sum(fhe_b200_ctx *ctx, const uint64_t *d_sq, int64_t B, int32_t d, int32_t words,
+                            const uint64_t *d_norm_q, const uint64_t *d_norm_y, int64_t norm_stride,
+                            int64_t out_stride, uint64_t *d_out, void *stream);
+
 /* ---- exact encrypted threshold glue -------------------------------
  * Replaces the CLEAR test `similarity >= min_similarity` of batch_operations.py:278 (and the score
  * buckets of fhe_cli.py:169-176) by the sign of (score - T) computed under encryption: LSB-first bit

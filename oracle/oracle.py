@@ -295,6 +295,28 @@ def encrypted_product_scores(p: PBSParams, bskf, ct_q, ct_docs, p_bits: int, out
     return pair_diff_sum(sq.reshape(B, d, 2, -1))
 
 
+def square_table(p_bits: int) -> np.ndarray:
+    w = np.arange(1 << p_bits, dtype=np.int64) - (1 << (p_bits - 1))
+    return w * w
+
+
+def encrypted_product_scores_norms(p: PBSParams, bskf, ct_q, ct_docs, norm_q, norm_docs, p_bits: int,
+                                   out_shift: int, multibit: bool = False) -> np.ndarray:
+    """One bootstrap per dimension: sum_j (x_j+y_j)^2 - |x|^2 - |y|^2 = 2 sum_j x_j*y_j, squares and norms at
+    2^(out_shift-1) so that the result encodes sum_j x_j*y_j at 2^out_shift.  norm_q [>=kN+1], norm_docs [B, >=kN+1]."""
+    words = p.n + 1
+    big = p.k * p.N + 1
+    ct_docs = np.asarray(ct_docs, dtype=np.uint64)
+    B, d = ct_docs.shape[:2]
+    sums = np.asarray(ct_q, dtype=np.uint64)[None, :, :words] + ct_docs[:, :, :words]
+    sums[:, :, words - 1] += np.uint64(1 << 62)
+    lut = make_lut_poly(square_table(p_bits), p_bits, p.N, out_shift - 1)
+    fn = pbs_mb2 if multibit else pbs
+    sq = fn(p, bskf, sums.reshape(-1, words), lut).reshape(B, d, big)
+    return (sq.sum(axis=1, dtype=np.uint64) - np.asarray(norm_q, dtype=np.uint64).reshape(-1)[None, :big]
+            - np.asarray(norm_docs, dtype=np.uint64)[:, :big])
+
+
 def encrypted_ge(p: PBSParams, ksk32, bskf, scores, T: int, score_bits: int, out_shift: int, bit_shift: int,
                  multibit: bool = False) -> np.ndarray:
     """SURVEY.md 8f N3 (replaces the clear test of batch_operations.py:278): scores [B, >=kN+1] big-key

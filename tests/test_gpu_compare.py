@@ -39,7 +39,7 @@ def test_pair_glue_bit_exact(O, cuda_dev, B, d, words, stride):
         assert not _u64(s)[:, words:].any()
 
 
-def _pipeline(O, cuda_dev, params, d, B, seed, multibit, with_oracle=True, tol_log2=-16):
+def _pipeline(O, cuda_dev, params, d, B, seed, multibit, with_oracle=True, tol_log2=-16, norms=False):
     from fhe_icp_b200.encrypted_compare import EncryptedCompare, IN_SHIFT, OUT_SHIFT, P_BITS
     rng = np.random.RandomState(seed)
     ec = EncryptedCompare(input_dim=d, params=params, device=cuda_dev, multibit=multibit).keygen()
@@ -51,7 +51,11 @@ def _pipeline(O, cuda_dev, params, d, B, seed, multibit, with_oracle=True, tol_l
     assert xq.min() >= -4 and xq.max() <= 3
     ct_q = ec.encrypt(xq, enc_seed=seed, ct_base=0)
     ct_d = ec.encrypt(yq, enc_seed=seed, ct_base=d)
-    scores = ec.scores(ct_q, ct_d)
+    if norms:
+        n_q, n_d = ec.encrypt_norms(xq, seed, 0), ec.encrypt_norms(yq, seed, 1)
+        scores = ec.scores(ct_q, ct_d, n_q, n_d)
+    else:
+        scores = ec.scores(ct_q, ct_d)
     got = ec.decrypt(scores)
     assert np.array_equal(got, yq @ xq)                      # exact: the clear integer model
     assert np.array_equal(got, ec.compare_clear(q, docs))
@@ -65,7 +69,15 @@ def _pipeline(O, cuda_dev, params, d, B, seed, multibit, with_oracle=True, tol_l
             obskf = O.bsk2_to_fourier(op, O.bsk2_gen(op, os_, oS, ec.evk_seed))
         else:
             obskf = O.bsk_to_fourier(op, O.bsk_gen(op, os_, oS, ec.evk_seed))
-        ref = O.encrypted_product_scores(op, obskf, oq, od, P_BITS, OUT_SHIFT, multibit=multibit)
+        if norms:
+            from fhe_icp_b200.encrypted_compare import NORM_CT_BASE
+            onq = O.lwe_encrypt(oS, (xq * xq).sum(), OUT_SHIFT - 1, op.sigma_glwe_abs, seed, NORM_CT_BASE, stride=n_q.shape[-1])
+            ond = O.lwe_encrypt(oS, (yq * yq).sum(axis=1), OUT_SHIFT - 1, op.sigma_glwe_abs, seed, NORM_CT_BASE + 1,
+                                stride=n_q.shape[-1])
+            assert np.array_equal(_u64(n_q).reshape(onq.shape), onq) and np.array_equal(_u64(n_d), ond)
+            ref = O.encrypted_product_scores_norms(op, obskf, oq, od, onq, ond, P_BITS, OUT_SHIFT, multibit=multibit)
+        else:
+            ref = O.encrypted_product_scores(op, obskf, oq, od, P_BITS, OUT_SHIFT, multibit=multibit)
         words = op.k * op.N + 1
         dec = O.lwe_decrypt(oS, ref, OUT_SHIFT) & 8191
         assert np.array_equal(np.where(dec >= 4096, dec - 8192, dec), got)
@@ -85,6 +97,18 @@ def test_toy_two_levels(O, cuda_dev, B, d):
 def test_toy_multibit_single_level(O, cuda_dev):
     # l_pbs = 1 (23-bit digits): the per-PBS noise is ~2^-18 at n=24, small sums still decode
     assert _pipeline(O, cuda_dev, TOY_L1, 4, 2, seed=5, multibit=True, tol_log2=-13) < -15
+
+
+@pytest.mark.parametrize("B,d,multibit", [(1, 1, False), (3, 7, True), (2, 16, True)])
+def test_toy_one_bootstrap_per_dimension(O, cuda_dev, B, d, multibit):
+    assert _pipeline(O, cuda_dev, TOY_L2, d, B, seed=B + d, multibit=multibit, norms=True) < -15
+
+
+def test_full_parameter_set_d128_norm_protocol(O, cuda_dev):
+    """Default protocol at the production set: d = 128 bootstraps per document, one document via the oracle."""
+    from fhe_icp_b200.encrypted_compare import COMPARE_PARAMS
+    assert _pipeline(O, cuda_dev, COMPARE_PARAMS, 128, 1, seed=31, multibit=True, tol_log2=-15, norms=True) < -15.5
+    assert _pipeline(O, cuda_dev, COMPARE_PARAMS, 128, 50, seed=32, multibit=True, with_oracle=False, norms=True) < -15.5
 
 
 def test_toy_multibit_two_levels(O, cuda_dev):

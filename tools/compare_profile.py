@@ -25,16 +25,20 @@ docs = rng.randn(B, d) / np.sqrt(d)
 ec.fit_scale(docs)
 ct_q = ec.encrypt(ec.quantize(q), 1, 0)
 ct_d = ec.encrypt(ec.quantize(docs), 1, d)
-ec.scores(ct_q, ct_d)
+NORMS = len(sys.argv) > 5 and sys.argv[5] == "norms"
+nq = nd = None
+if NORMS:
+    nq, nd = ec.encrypt_norms(ec.quantize(q), 1, 0), ec.encrypt_norms(ec.quantize(docs), 1, 1)
+ec.scores(ct_q, ct_d, nq, nd)
 torch.cuda.synchronize()
 for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    sc = ec.scores(ct_q, ct_d)
+    sc = ec.scores(ct_q, ct_d, nq, nd)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     print(f"docs={B} l_pbs={params['l_pbs']} multibit={mb}: {ms:.2f} ms -> {B / ms * 1e3:.1f} comparisons/s, "
-          f"{2 * d * B / ms * 1e3:.0f} PBS/s")
+          f"{(1 if NORMS else 2) * d * B / ms * 1e3:.0f} PBS/s")
 got = ec.decrypt(sc)
 print("exact:", bool(np.array_equal(got, ec.compare_clear(q, docs))))

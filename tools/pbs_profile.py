@@ -10,7 +10,11 @@ from fhe_icp_b200.params import PBS_PARAMS_4BIT
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dev = torch.device("cuda", 0)
-p = E.make_pbs_params(**PBS_PARAMS_4BIT)
+import os
+PD = dict(PBS_PARAMS_4BIT)
+if os.environ.get("PBS_L", "1") == "2":   # the two-level set of the encrypted x encrypted comparison
+    PD.update(l_pbs=2, beta_pbs=15)
+p = E.make_pbs_params(**PD)
 s, S = E.secret_key(101, 0, p.n, dev), E.secret_key(101, 1, p.k * p.N, dev)
 ksk, bsk = E.ksk_gen(p, S, s, 202), E.bsk_gen(p, s, S, 202)
 bskf = E.bsk_to_fourier(p, bsk)
