@@ -108,3 +108,88 @@ def test_rank_results_reference_semantics():
     assert rank_results(ids, s, 1, 0.5) == [("b", 0.9)]
     assert rank_results(ids, s, 3, 2.0) == []
     assert rank_results([], np.zeros(0), 3, 0.0) == []
+
+
+# ------------------------------------------------------------------ both vectors encrypted (ShardedPairSearch)
+class OraclePairEngine:
+    """CPU stand-in for EncryptedCompare (same method names) over the oracle, toy parameters."""
+    IN_SHIFT, OUT_SHIFT, P_BITS = 59, 51, 4
+
+    def __init__(self, d, client):
+        from oracle import oracle as O
+        self.O, self.d, self.dev = O, d, torch.device("cpu")
+        self.p = O.make_params(n=16, k=1, N=2048, l_pbs=2, beta_pbs=15, l_ks=4, beta_ks=4, log2_sigma_lwe=-30.0,
+                               log2_sigma_glwe=-51.6)
+        self.scale = 0.25
+        self.bskf = None
+        if client:   # only the client rank ever holds secret keys
+            self.s, self.S = O.secret_key(5, 0, self.p.n), O.secret_key(5, 1, self.p.N)
+            self.bskf = torch.from_numpy(O.bsk_to_fourier(self.p, O.bsk_gen(self.p, self.s, self.S, 6)))
+
+    def quantize(self, X):
+        return np.clip(np.rint(np.asarray(X, dtype=np.float64) / self.scale), -4, 3).astype(np.int64)
+
+    def dequantize(self, q):
+        return np.asarray(q, dtype=np.float64) * self.scale ** 2
+
+    def encrypt(self, Xq, enc_seed, ct_base=0):
+        Xq = np.asarray(Xq)
+        ct = self.O.lwe_encrypt(self.s, Xq, self.IN_SHIFT, self.p.sigma_lwe_abs, enc_seed, ct_base, stride=self.p.n + 2)
+        return torch.from_numpy(ct.reshape(Xq.shape + (-1,)).view(np.int64))
+
+    def encrypt_norms(self, Xq, enc_seed, ct_base=0):
+        Xq = np.asarray(Xq)
+        m = (Xq * Xq).sum(axis=-1)
+        ct = self.O.lwe_encrypt(self.S, m, self.OUT_SHIFT - 1, self.p.sigma_glwe_abs, enc_seed, (1 << 40) + ct_base,
+                                stride=self.p.N + 2)
+        return torch.from_numpy(ct.reshape(np.shape(m) + (-1,)).view(np.int64))
+
+    def scores(self, ct_q, ct_docs, n_q, n_docs):
+        out = self.O.encrypted_product_scores_norms(self.p, self.bskf.numpy(), ct_q.numpy().view(np.uint64),
+                                                    ct_docs.numpy().view(np.uint64), n_q.numpy().view(np.uint64),
+                                                    n_docs.numpy().view(np.uint64), self.P_BITS, self.OUT_SHIFT)
+        pad = np.zeros((out.shape[0], self.p.N + 2), dtype=np.uint64)
+        pad[:, : out.shape[1]] = out
+        return torch.from_numpy(pad.view(np.int64))
+
+    def decrypt(self, sc):
+        v = self.O.lwe_decrypt(self.S, sc.numpy().view(np.uint64), self.OUT_SHIFT) & 8191
+        return np.where(v >= 4096, v - 8192, v)
+
+
+def _pair_problem(n_docs, d=6):
+    rng = np.random.RandomState(n_docs)
+    return rng.uniform(-1, 1, size=d), rng.uniform(-1, 1, size=(n_docs, d))
+
+
+def _pair_worker(rank, world, port, n_docs, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fhe_icp_b200.sharded_search import ShardedPairSearch
+        q, docs = _pair_problem(n_docs)
+        eng = OraclePairEngine(6, client=rank == 0)
+        sp = ShardedPairSearch(eng, docs if rank == 0 else None)       # servers never see the documents in clear
+        assert (rank == 0) or not hasattr(eng, "s")
+        ints = sp.search_scores(q if rank == 0 else None)
+        res = sp.search(q if rank == 0 else None, top_k=3, min_similarity=-10.0)
+        if rank == 0:
+            ret["ints"], ret["res"] = ints.tolist(), res
+        else:
+            assert ints is None and res is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_docs", [5, 2, 1])
+def test_sharded_pair_search_world2(n_docs):
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_pair_worker, args=(world, port, n_docs, ret), nprocs=world, join=True)
+    from fhe_icp_b200.batch_operations import rank_results
+    q, docs = _pair_problem(n_docs)
+    eng = OraclePairEngine(6, client=True)
+    clear = eng.quantize(docs) @ eng.quantize(q)
+    assert ret["ints"] == clear.tolist()
+    assert ret["res"] == rank_results([f"doc_{i}" for i in range(n_docs)], eng.dequantize(clear), 3, -10.0)
