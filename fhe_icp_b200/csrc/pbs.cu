@@ -795,17 +795,19 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
         }
         // ---- monomials at this lane's bins: rho_k^e = omega^((4*lane+1)*e) * (omega^(128*e))^k1
         const int ea = a_tilde[2 * i], eb = a_tilde[2 * i + 1];
-        double mx[3], my[3], rx[3], ry[3];
+        // c_g = rho^e_g - 1 is carried directly: c' = c*r + (r - 1), all FMA chains
+        double cx[3], cy[3], rx[3], ry[3], qx[3];
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
             const int e = g == 0 ? ((ea + eb) & 4095) : (g == 1 ? ea : eb);
             const int E = (e * (4 * lane + 1)) & 4095;
             const cplx hi = omega[64 + (E >> 6)], lo = omega[E & 63];
-            mx[g] = hi.x * lo.x - hi.y * lo.y;
-            my[g] = hi.x * lo.y + hi.y * lo.x;
+            cx[g] = fma(hi.x, lo.x, fma(-hi.y, lo.y, -1.0));
+            cy[g] = fma(hi.x, lo.y, hi.y * lo.x);
             const cplx r = omega[64 + (((128 * e) & 4095) >> 6)];
             rx[g] = r.x;
             ry[g] = r.y;
+            qx[g] = r.x - 1.0;
         }
         named_bar_sync(bar_id, bar_n);  // (A) every warp's Fourier digits are visible
         // ---- walk the frequency blocks: out[bin] = F_t * sum_g c_g G_g[t][lev][t] + F_t' * sum_g c_g G_g[t'][lev][t],
@@ -823,22 +825,28 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
                 const int p = nfft::brev5(k1);
                 const cplx fo = tile_other[k1 * 32 + lane];
                 const double ax = re[p], ay = im[p];
-                double kox = 0.0, koy = 0.0, ktx = 0.0, kty = 0.0;
+                double kox, koy, ktx, kty;
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
                     const cplx bt = blk[(((g * 2 + t) * L + lev) * 2 + t) * 32 + lane];
                     const cplx bo = blk[(((g * 2 + (1 - t)) * L + lev) * 2 + t) * 32 + lane];
-                    const double cx = mx[g] - 1.0, cy = my[g];
-                    kox += cx * bt.x - cy * bt.y;
-                    koy += cx * bt.y + cy * bt.x;
-                    ktx += cx * bo.x - cy * bo.y;
-                    kty += cx * bo.y + cy * bo.x;
-                    const double nx = mx[g] * rx[g] - my[g] * ry[g];
-                    my[g] = mx[g] * ry[g] + my[g] * rx[g];
-                    mx[g] = nx;
+                    if (g == 0) {
+                        kox = fma(cx[g], bt.x, -(cy[g] * bt.y));
+                        koy = fma(cx[g], bt.y, cy[g] * bt.x);
+                        ktx = fma(cx[g], bo.x, -(cy[g] * bo.y));
+                        kty = fma(cx[g], bo.y, cy[g] * bo.x);
+                    } else {
+                        kox = fma(cx[g], bt.x, fma(-cy[g], bt.y, kox));
+                        koy = fma(cx[g], bt.y, fma(cy[g], bt.x, koy));
+                        ktx = fma(cx[g], bo.x, fma(-cy[g], bo.y, ktx));
+                        kty = fma(cx[g], bo.y, fma(cy[g], bo.x, kty));
+                    }
+                    const double nx = fma(cx[g], rx[g], fma(-cy[g], ry[g], qx[g]));
+                    cy[g] = fma(cx[g], ry[g], fma(cy[g], rx[g], ry[g]));
+                    cx[g] = nx;
                 }
-                re[p] = ax * kox - ay * koy + (fo.x * ktx - fo.y * kty);
-                im[p] = ax * koy + ay * kox + (fo.x * kty + fo.y * ktx);
+                re[p] = fma(ax, kox, fma(-ay, koy, fma(fo.x, ktx, -(fo.y * kty))));
+                im[p] = fma(ax, koy, fma(ay, kox, fma(fo.x, kty, fo.y * ktx)));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[slot]);
