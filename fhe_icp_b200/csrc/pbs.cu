@@ -638,13 +638,21 @@ static cudaError_t launch_pbs_tmem_t(const fhe_b200_pbs_params& p, const cplx* b
 // accumulates sum_t' F[t'][lev] * G[t'][lev][t] and adds its inverse transform into its OWN partial
 // accumulator A[t][lev] in TMEM (ACC_t = sum_lev A[t][lev]); the partials of one polynomial sit in the
 // same TMEM lane quadrant (warps w and w+4), so every warp can read the full ACC_t for its digits.
-constexpr int MB2_K1 = 2;                        // frequency blocks (k1 values) per slice
+#ifndef MB2_L2_K1
+#define MB2_L2_K1 2
+#endif
+#ifndef MB2_L2_SLICES
+#define MB2_L2_SLICES 3
+#endif
+#define MB2_SLICE_K1(L) ((L) == 1 ? 2 : MB2_L2_K1)
+#define MB2_SLICE_COUNT(L) ((L) == 1 ? 4 : MB2_L2_SLICES)
 constexpr int MB2_LAG = 1;                       // refill a ring slot this many slices after warp 0 left it
 template <int L>
 struct PbsMb2Smem {
-    static constexpr int slices = L == 1 ? 4 : 3;                       // ring slots
+    static constexpr int k1 = MB2_SLICE_K1(L);                           // frequency blocks per slice
+    static constexpr int slices = MB2_SLICE_COUNT(L);                    // ring slots
     static constexpr int block_elems = 3 * 2 * L * 2 * 32;              // complex elements per frequency block
-    static constexpr int slice_elems = MB2_K1 * block_elems;
+    static constexpr int slice_elems = k1 * block_elems;
     static constexpr size_t tw_bytes = (size_t)PBS_TILE * 16;
     static constexpr size_t ring_bytes = (size_t)slices * slice_elems * 16;
     static constexpr size_t omega_bytes = (size_t)PBS_OMEGA * 16;
@@ -691,7 +699,8 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
     const uint32_t tquad = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t tacc = tquad + (uint32_t)((warp >> 2) * 128);   // this warp's (partial) accumulator
     constexpr uint32_t SLICE_BYTES = (uint32_t)(S::slice_elems * 16);
-    constexpr int SPI = 32 / MB2_K1;  // slices per blind-rotation step
+    constexpr int K1 = S::k1;
+    constexpr int SPI = 32 / K1;  // slices per blind-rotation step
     const int pairs = n >> 1;
     const int total_slices = pairs * SPI;
 
@@ -819,8 +828,8 @@ pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, 
             mbar_wait(&bar_full[slot], (uint32_t)((sidx / SLICES) & 1));
             const cplx* sl = ring + (size_t)slot * S::slice_elems;
 #pragma unroll
-            for (int kk = 0; kk < MB2_K1; ++kk) {
-                const int k1 = sl_i * MB2_K1 + kk;
+            for (int kk = 0; kk < K1; ++kk) {
+                const int k1 = sl_i * K1 + kk;
                 const cplx* blk = sl + kk * S::block_elems;
                 const int p = nfft::brev5(k1);
                 const cplx fo = tile_other[k1 * 32 + lane];
