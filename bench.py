@@ -394,6 +394,8 @@ def run_b200_arm(args):
                                 "sample": f"{rows} documents (the {B}-document workload tiled), quantize+encrypt+dot+decrypt in {t:.1f} s, "
                                           "oracle/fhe_oracle.c (OpenMP)"}
     try:
+        if args.no_extras:
+            raise ImportError
         from fhe_icp_b200 import pbs_bench
         line["pbs"] = pbs_bench.measure(dev, args)
         if world == 1:
@@ -468,6 +470,8 @@ def main():
     ap.add_argument("--gather-mode", default="all_gather", choices=["gather", "all_gather"],
                     help="how encrypted scores reach the client rank (N>1)")
     ap.add_argument("--pbs-batch", type=int, default=0, help="PBS microbench batch (0 = default sweep)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the PBS / encrypted-pair sections that follow the timed loop (for a clean ncu launch list)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
