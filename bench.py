@@ -397,6 +397,7 @@ def run_b200_arm(args):
         if args.no_extras:
             raise ImportError
         from fhe_icp_b200 import pbs_bench
+        args._hbm_peak = peak
         line["pbs"] = pbs_bench.measure(dev, args)
         if world == 1:
             pair = pbs_bench.measure_pair(dev, args)
