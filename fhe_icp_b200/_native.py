@@ -109,6 +109,13 @@ SIGNATURES = {
     "fhe_b200_lincomb": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _vp, C.c_int32,
                                    C.POINTER(C.c_int64), C.c_int32, _vp, _vp]),
     "fhe_b200_accumulate": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
+    "fhe_b200_glwe_encrypt_rows": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
+                                             C.c_uint64, _vp, _vp]),
+    "fhe_b200_glwe_ggsw_dot": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _vp, _vp]),
+    "fhe_b200_glwe_decrypt_coeffs": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_int32, _vp, _vp]),
+    "fhe_b200_glwe_sample_extract": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                               _vp, _vp]),
     "fhe_b200_lwe_pair_add": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_uint64, _vp, _vp]),
     "fhe_b200_lwe_square_sum": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
     "fhe_b200_lwe_shl_add": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _vp, C.c_int64, _vp]),

@@ -319,6 +319,68 @@ int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx* ctx, const uint64_t* d_in, int64_t 
     return FHE_B200_OK;
 }
 
+// ------------------------------------------------------------------------------- packed inner products (GLWE x GGSW)
+static int check_pbs_params(const fhe_b200_pbs_params* p, const char* fn);
+int fhe_b200_glwe_encrypt_rows(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint8_t* d_S_big,
+                               const int64_t* d_msgs, int64_t rows, int64_t msg_stride, int32_t mode, int32_t shift,
+                               uint64_t seed, uint64_t id_base, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx && p && d_S_big && d_msgs && d_out, "null argument");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    REQUIRE(mode == 0 || mode == 1, "mode must be 0 (vectors) or 1 (GGSW of one polynomial)");
+    REQUIRE(rows >= 0 && shift >= 0 && shift < 64, "bad shape");
+    REQUIRE(mode == 0 ? msg_stride >= p->N : rows == (int64_t)(p->k + 1) * p->l_pbs,
+            "mode 0 needs msg_stride >= N; mode 1 needs rows == (k+1)*l_pbs");
+    if (rows == 0) return FHE_B200_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_glwe_encrypt_rows(*p, d_S_big, d_msgs, rows, msg_stride, mode, shift, seed, id_base, d_out,
+                                     (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_glwe_ggsw_dot(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_ggswf, const uint64_t* d_in,
+                           int64_t G, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx && p, "null argument");
+    REQUIRE(G >= 0, "negative batch");
+    if (G == 0) return FHE_B200_OK;
+    REQUIRE(d_ggswf && d_in && d_out, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    REQUIRE(p->l_pbs == 2, "the packed inner-product kernel needs l_pbs == 2");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_glwe_dot(*p, d_ggswf, d_in, G, d_out, ctx->prop.multiProcessorCount, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_glwe_decrypt_coeffs(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint8_t* d_S_big,
+                                 const uint64_t* d_glwe, int64_t G, int32_t first, int32_t step, int32_t count,
+                                 int32_t shift, int64_t* d_msgs, void* stream) {
+    REQUIRE(ctx && p, "null argument");
+    REQUIRE(G >= 0 && count >= 0, "negative size");
+    if (G == 0 || count == 0) return FHE_B200_OK;
+    REQUIRE(d_S_big && d_glwe && d_msgs, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    REQUIRE(first >= 0 && step >= 0 && (int64_t)first + (int64_t)(count - 1) * step < p->N && shift >= 0 && shift < 64,
+            "coefficient indices out of range");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_glwe_decrypt_coeffs(d_S_big, d_glwe, G, p->N, first, step, count, shift, d_msgs, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_glwe_sample_extract(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint64_t* d_glwe, int64_t G,
+                                 int32_t first, int32_t step, int32_t count, int64_t out_stride, uint64_t* d_out,
+                                 void* stream) {
+    REQUIRE(ctx && p, "null argument");
+    REQUIRE(G >= 0 && count >= 0, "negative size");
+    if (G == 0 || count == 0) return FHE_B200_OK;
+    REQUIRE(d_glwe && d_out, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    REQUIRE(first >= 0 && step >= 0 && (int64_t)first + (int64_t)(count - 1) * step < p->N && out_stride >= p->N + 1,
+            "coefficient indices / stride out of range");
+    REQUIRE(G * (int64_t)count < ((int64_t)1 << 31), "too many rows for one launch");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_glwe_sample_extract(d_glwe, G, p->N, first, step, count, out_stride, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 int fhe_b200_lwe_pair_add(fhe_b200_ctx* ctx, const uint64_t* d_q, const uint64_t* d_y, int64_t B, int32_t d,
                           int32_t words, int64_t in_stride, uint64_t offset, uint64_t* d_out, void* stream) {
     REQUIRE(ctx, "null ctx");

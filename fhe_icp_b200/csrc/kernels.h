@@ -32,6 +32,15 @@ cudaError_t launch_lwe_decrypt32(const uint8_t* d_key, int n, int64_t stride, co
 cudaError_t launch_accumulate(uint64_t* d_acc, const uint64_t* d_x, int64_t words, cudaStream_t s);
 cudaError_t launch_lwe_pair_addsub(const uint64_t* d_q, const uint64_t* d_y, int64_t B, int d, int words,
                                    int64_t in_stride, uint64_t offset, uint64_t* d_out, cudaStream_t s);
+cudaError_t launch_glwe_encrypt_rows(const fhe_b200_pbs_params& p, const uint8_t* d_S_big, const int64_t* d_msgs,
+                                     int64_t rows, int64_t msg_stride, int mode, int shift, uint64_t seed,
+                                     uint64_t id_base, uint64_t* d_out, cudaStream_t s);
+cudaError_t launch_glwe_dot(const fhe_b200_pbs_params& p, const double* d_ggswf, const uint64_t* d_in, int64_t G,
+                            uint64_t* d_out, int sm_count, cudaStream_t s);
+cudaError_t launch_glwe_decrypt_coeffs(const uint8_t* d_S_big, const uint64_t* d_glwe, int64_t G, int N, int first,
+                                       int step, int count, int shift, int64_t* d_out, cudaStream_t s);
+cudaError_t launch_glwe_sample_extract(const uint64_t* d_glwe, int64_t G, int N, int first, int step, int count,
+                                       int64_t out_stride, uint64_t* d_out, cudaStream_t s);
 cudaError_t launch_lwe_pair_add(const uint64_t* d_q, const uint64_t* d_y, int64_t B, int d, int words,
                                 int64_t in_stride, uint64_t offset, uint64_t* d_out, cudaStream_t s);
 cudaError_t launch_lwe_square_sum(const uint64_t* d_sq, int64_t B, int d, int words, const uint64_t* d_norm_q,

@@ -118,6 +118,79 @@ bsk_gen_kernel(const uint8_t* __restrict__ s_small, const uint8_t* __restrict__ 
     }
 }
 
+// Generic GLWE row encryption for the packed inner-product path: row R of out [rows][k+1][N] is
+// GLWE_S(0) + (msg_R(X) << shift_R) on component comp_R.  mode 0 (document vectors): msg_R = msgs +
+// R*msg_stride, shift_R = shift, comp_R = k (body).  mode 1 (GGSW of one polynomial): R = t*l + lev,
+// msg_R = msgs, shift_R = 64 - beta*(lev+1), comp_R = t.  Randomness of row R: object id_base + R,
+// purpose GLWE.  Same structure as bsk_gen_kernel (body = sum_c A_c * S_c + E by sparse negacyclic adds).
+__global__ void __launch_bounds__(BSK_THREADS)
+glwe_encrypt_rows_kernel(const uint8_t* __restrict__ S_big, const int64_t* __restrict__ msgs, int64_t msg_stride,
+                         int mode, int shift, int k, int N, int l, int beta, double sigma_abs, uint64_t seed,
+                         uint64_t id_base, uint64_t* __restrict__ out) {
+    extern __shared__ uint64_t sm[];  // A[N] then S bits [N/32 words]
+    uint64_t* A = sm;
+    uint32_t* Sb = reinterpret_cast<uint32_t*>(sm + N);
+    const int64_t R = blockIdx.x;
+    const uint64_t id = id_base + (uint64_t)R;
+    uint64_t* row = out + (size_t)R * (k + 1) * N;
+    const int64_t* m = mode == 0 ? msgs + (size_t)R * msg_stride : msgs;
+    const int sh = mode == 0 ? shift : 64 - beta * ((int)(R % l) + 1);
+    const int comp = mode == 0 ? k : (int)(R / l);
+    constexpr int PER = 16;
+    uint64_t body[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int x = threadIdx.x + u * BSK_THREADS;
+        body[u] = x < N ? (uint64_t)gaussian_i64(seed, FHE_B200_KIND_NOISE | (FHE_B200_PUR_GLWE << 8), id, (uint32_t)x,
+                                                 sigma_abs)
+                        : 0;
+    }
+    for (int c = 0; c < k; ++c) {
+        __syncthreads();
+        for (int x = threadIdx.x; x < N; x += BSK_THREADS) {
+            const uint64_t a = mask_word(seed, FHE_B200_PUR_GLWE, id, (int64_t)c * N + x);
+            A[x] = a;
+            row[(size_t)c * N + x] = a + (c == comp ? (uint64_t)m[x] << sh : 0);
+        }
+        for (int w = threadIdx.x; w < N / 32; w += BSK_THREADS) {
+            uint32_t bits = 0;
+            for (int b = 0; b < 32; ++b) bits |= (uint32_t)(S_big[(size_t)c * N + w * 32 + b] & 1u) << b;
+            Sb[w] = bits;
+        }
+        __syncthreads();
+        for (int w = 0; w < N / 32; ++w) {
+            uint32_t bits = Sb[w];
+            while (bits) {
+                const int y = w * 32 + (__ffs(bits) - 1);
+                bits &= bits - 1;
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int x = threadIdx.x + u * BSK_THREADS;
+                    if (x < N) body[u] += (x >= y) ? A[x - y] : (uint64_t)0 - A[x - y + N];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int x = threadIdx.x + u * BSK_THREADS;
+        if (x < N) row[(size_t)k * N + x] = body[u] + (comp == k ? (uint64_t)m[x] << sh : 0);
+    }
+}
+
+cudaError_t launch_glwe_encrypt_rows(const fhe_b200_pbs_params& p, const uint8_t* d_S_big, const int64_t* d_msgs,
+                                     int64_t rows, int64_t msg_stride, int mode, int shift, uint64_t seed,
+                                     uint64_t id_base, uint64_t* d_out, cudaStream_t s) {
+    if (p.N > BSK_THREADS * 16) return cudaErrorInvalidValue;
+    if (rows <= 0) return cudaSuccess;
+    size_t smem = (size_t)p.N * 8 + (size_t)p.N / 8;
+    glwe_encrypt_rows_kernel<<<(unsigned)rows, BSK_THREADS, smem, s>>>(d_S_big, d_msgs, msg_stride, mode, shift, p.k, p.N,
+                                                                      p.l_pbs, p.beta_pbs, p.sigma_glwe_abs, seed, id_base,
+                                                                      d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_bsk_gen(const fhe_b200_pbs_params& p, const uint8_t* d_s_small, const uint8_t* d_S_big,
                            uint64_t evk_seed, uint64_t* d_bsk, cudaStream_t s) {
     if (p.N > BSK_THREADS * 16) return cudaErrorInvalidValue;

@@ -585,6 +585,90 @@ cudaError_t launch_lwe_square_sum(const uint64_t* d_sq, int64_t B, int d, int wo
     return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------- packed GLWE results
+// A GLWE ciphertext (A, B) under S carries N coefficients; the packed inner-product path needs `count`
+// of them (first, first+step, ...).  Client: phase_q = B[idx] - sum_i S_i * a_i(idx), with the sample-
+// extraction mask a_i(idx) = A[idx-i] (i <= idx), -A[N+idx-i] (i > idx), decoded as round(phase / 2^shift).
+constexpr int GDEC_THREADS = 256;
+
+__global__ void __launch_bounds__(GDEC_THREADS)
+glwe_decrypt_coeffs_kernel(const uint8_t* __restrict__ S_big, const uint64_t* __restrict__ glwe, int N, int first,
+                           int step, int count, int shift, int64_t* __restrict__ out) {
+    extern __shared__ uint64_t gsm[];  // A[N], then S bits, then per-warp partials
+    uint64_t* A = gsm;
+    uint32_t* Sb = reinterpret_cast<uint32_t*>(gsm + N);
+    uint64_t* part = gsm + N + N / 64 + 1;
+    const uint64_t* g = glwe + (size_t)blockIdx.x * 2 * N;
+    for (int x = threadIdx.x; x < N; x += GDEC_THREADS) A[x] = g[x];
+    for (int w = threadIdx.x; w < N / 32; w += GDEC_THREADS) {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; ++b) bits |= (uint32_t)(S_big[w * 32 + b] & 1u) << b;
+        Sb[w] = bits;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < count; ++q) {
+        const int idx = first + q * step;
+        uint64_t acc = 0;
+        for (int i = threadIdx.x; i < N; i += GDEC_THREADS) {
+            const uint64_t sel = 0 - (uint64_t)((Sb[i >> 5] >> (i & 31)) & 1u);
+            const int m = idx - i;
+            const uint64_t a = m >= 0 ? A[m] : (uint64_t)0 - A[m + N];
+            acc += a & sel;
+        }
+        acc = warp_sum_u64(acc);
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t dot = 0;
+            for (int w = 0; w < GDEC_THREADS / 32; ++w) dot += part[w];
+            const uint64_t phase = g[(size_t)N + idx] - dot;
+            out[(size_t)blockIdx.x * count + q] = (int64_t)((phase + (shift ? (1ull << (shift - 1)) : 0)) >> shift);
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_glwe_decrypt_coeffs(const uint8_t* d_S_big, const uint64_t* d_glwe, int64_t G, int N, int first,
+                                       int step, int count, int shift, int64_t* d_out, cudaStream_t s) {
+    if (G <= 0 || count <= 0) return cudaSuccess;
+    const size_t smem = (size_t)N * 8 + ((size_t)N / 64 + 1) * 8 + (GDEC_THREADS / 32) * 8;
+    glwe_decrypt_coeffs_kernel<<<(unsigned)G, GDEC_THREADS, smem, s>>>(d_S_big, d_glwe, N, first, step, count, shift, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// Server-side sample extraction (when a score has to continue as an LWE ciphertext, e.g. into the
+// encrypted threshold): out[(g*count + q)][0..N] = extract(glwe[g], first + q*step), rows out_stride apart.
+__global__ void __launch_bounds__(PAIR_THREADS)
+glwe_sample_extract_kernel(const uint64_t* __restrict__ glwe, int N, int first, int step, int count,
+                           int64_t out_stride, uint64_t* __restrict__ out) {
+    const int64_t row = blockIdx.x;  // g*count + q
+    const int64_t gi = row / count;
+    const int idx = first + (int)(row - gi * count) * step;
+    const uint64_t* A = glwe + (size_t)gi * 2 * N;
+    uint64_t* o = out + (size_t)row * out_stride;
+    for (int i = threadIdx.x; i < out_stride; i += PAIR_THREADS) {
+        uint64_t v = 0;
+        if (i < N) {
+            const int m = idx - i;
+            v = m >= 0 ? A[m] : (uint64_t)0 - A[m + N];
+        } else if (i == N) {
+            v = A[(size_t)N + idx];
+        }
+        o[i] = v;
+    }
+}
+
+cudaError_t launch_glwe_sample_extract(const uint64_t* d_glwe, int64_t G, int N, int first, int step, int count,
+                                       int64_t out_stride, uint64_t* d_out, cudaStream_t s) {
+    if (G <= 0 || count <= 0) return cudaSuccess;
+    glwe_sample_extract_kernel<<<(unsigned)(G * count), PAIR_THREADS, 0, s>>>(d_glwe, N, first, step, count, out_stride,
+                                                                             d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ----------------------------------------------------------------------------- bit-extraction glue
 // Exact encrypted threshold (sign of a wide message by LSB-first bit extraction): per step the
 // ciphertext is scaled by a power of two (the wanted bit moves to the top of the torus, higher bits

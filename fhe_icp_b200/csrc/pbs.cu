@@ -1011,6 +1011,172 @@ cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, 
     return launch_pbs_mb2_t<1, 4>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
 }
 
+// ------------------------------------------------------------------------------- packed encrypted inner products
+// out[g] = GGSW(Q) [.] GLWE_g for a whole collection of GLWE ciphertexts and ONE GGSW (the query):
+// the leveled form of the both-encrypted comparison.  Each GLWE packs N/slot document vectors, Q(X) =
+// sum_j x_j X^(-j), so coefficient slot*b of the product is the inner product with document b.
+//
+// The Fourier GGSW (2 x L x 2 polynomials, 128 KB at L = 2) is the only operand every ciphertext
+// shares.  It lives in TENSOR MEMORY for the whole launch: column c of it is exactly 64 KB = one TMEM
+// lane quadrant (32 lanes x 512 columns), lane k2 holding its 32 bins x 2L rows as (re, im) f64 pairs;
+// warps of even quadrants produce output polynomial 0 (mask), odd quadrants polynomial 1 (body), so every
+// warp finds the column it needs in its own quadrant and shared memory is left to the transforms.
+// Persistent CTAs (one per SM) stream the GLWE ciphertexts from HBM: 32 KB in, 32 KB out per ciphertext.
+// Warp t of a ciphertext: digits of polynomial t at both levels -> two forward FFTs, published in shared
+// memory; after a named barrier, out_t = sum_{t',lev} F[t'][lev] * G[t'][lev][t] with G read from TMEM;
+// inverse FFT; coefficients written back.
+struct GlweDotSmem {
+    static constexpr size_t tw_bytes = (size_t)PBS_TILE * 16;
+    static constexpr size_t bar_bytes = 128;
+    static constexpr size_t head_bytes = tw_bytes + bar_bytes;
+    static constexpr size_t per_ct = (size_t)4 * PBS_TILE * 16;   // tiles (t, lev)
+    static size_t total(int nct) { return head_bytes + (size_t)nct * per_ct; }
+};
+
+template <int NCT>
+__global__ void __launch_bounds__(NCT * 64, 1)
+glwe_dot_kernel(const cplx* __restrict__ ggswf, const uint64_t* __restrict__ in, int64_t G, int beta,
+                const cplx* __restrict__ g_tw, uint64_t* __restrict__ out) {
+    using S = GlweDotSmem;
+    constexpr int L = 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* tw = reinterpret_cast<cplx*>(smem_raw);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + S::tw_bytes);
+    for (int i = threadIdx.x; i < PBS_TILE; i += blockDim.x) tw[i] = g_tw[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int t = warp & 1;                      // polynomial this warp decomposes AND the output column it produces
+    const uint32_t tq = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    // ---- GGSW column t -> this quadrant: column ((tl*32 + p)*4 + w), p = register index of bin lane + 32*brev5(p)
+    if (warp < 4 && warp < NCT * 2) {
+#pragma unroll 1
+        for (int tl = 0; tl < 2 * L; ++tl) {
+            const cplx* src = ggswf + (size_t)(tl * 2 + t) * PBS_M;
+#pragma unroll
+            for (int pc = 0; pc < 8; ++pc) {
+                uint32_t w[16];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const cplx v = src[lane + 32 * nfft::brev5(pc * 4 + u)];
+                    const unsigned long long xr = (unsigned long long)__double_as_longlong(v.x);
+                    const unsigned long long xi = (unsigned long long)__double_as_longlong(v.y);
+                    w[4 * u + 0] = (uint32_t)xr;
+                    w[4 * u + 1] = (uint32_t)(xr >> 32);
+                    w[4 * u + 2] = (uint32_t)xi;
+                    w[4 * u + 3] = (uint32_t)(xi >> 32);
+                }
+                tmem_st_x16(tq + (uint32_t)((tl * 32 + pc * 4) * 4), w);
+            }
+        }
+        tmem_wait_st();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const int ctl = warp >> 1;
+    cplx* tiles = reinterpret_cast<cplx*>(smem_raw + S::head_bytes + (size_t)ctl * S::per_ct);
+    const int bar_id = 1 + ctl;
+    // balanced digits of the value rounded to 2*beta bits: lev 1 = low beta bits sign-extended,
+    // lev 0 = the rest after the carry out of lev 1 (same digits as the oracle's decompose())
+    const uint64_t rnd = 1ull << (63 - 2 * beta);
+    const int s1 = 64 - 2 * beta, sx = 32 - beta;
+    const uint32_t carry = 1u << (31 - beta);
+    auto digit = [&](uint64_t v, int lev) -> double {
+        const uint64_t r = v + rnd;   // bits [64-2*beta, 64) are the rounded value; digits are taken with 32-bit ops
+        const int32_t dg = lev == 0 ? (int32_t)((uint32_t)(r >> 32) + carry) >> sx
+                                    : (int32_t)((uint32_t)(r >> s1) << sx) >> sx;
+        return (double)dg;
+    };
+    double re[32], im[32];
+    for (int64_t grp = blockIdx.x; grp * NCT < G; grp += gridDim.x) {
+        const int64_t g = grp * NCT + ctl;
+        if (g >= G) continue;   // whole ciphertext slot idle: both of its warps skip together
+        const uint64_t* src = in + ((size_t)g * 2 + t) * PBS_N;
+#pragma unroll
+        for (int lev = 0; lev < L; ++lev) {
+            cplx* tile = tiles + (size_t)(t * L + lev) * PBS_TILE;
+#pragma unroll
+            for (int j2 = 0; j2 < 32; ++j2) {
+                re[j2] = digit(src[lane + 32 * j2], lev);
+                im[j2] = digit(src[lane + 32 * j2 + PBS_M], lev);
+            }
+            nfft::fwd_phase1(re, im, tw, tile, lane);
+            __syncwarp();
+            nfft::fwd_phase2(re, im, tile, lane);
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                cplx v;
+                v.x = re[p];
+                v.y = im[p];
+                tile[nfft::brev5(p) * 32 + lane] = v;
+            }
+        }
+        named_bar_sync(bar_id, 64);  // (A) all four spectra of this ciphertext are visible
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc) {
+            double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int tl = 0; tl < 2 * L; ++tl) {
+                uint32_t w[16];
+                tmem_ld_x16(tq + (uint32_t)((tl * 32 + pc * 4) * 4), w);
+                const cplx* f = tiles + (size_t)tl * PBS_TILE;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const cplx fv = f[nfft::brev5(pc * 4 + u) * 32 + lane];
+                    const double gx = __longlong_as_double((long long)(((unsigned long long)w[4 * u + 1] << 32) | w[4 * u + 0]));
+                    const double gy = __longlong_as_double((long long)(((unsigned long long)w[4 * u + 3] << 32) | w[4 * u + 2]));
+                    ax[u] = fma(fv.x, gx, fma(-fv.y, gy, ax[u]));
+                    ay[u] = fma(fv.x, gy, fma(fv.y, gx, ay[u]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                re[pc * 4 + u] = ax[u];
+                im[pc * 4 + u] = ay[u];
+            }
+        }
+        named_bar_sync(bar_id, 64);  // (B) nobody reads the published spectra any more
+        cplx* tile = tiles + (size_t)(t * L) * PBS_TILE;
+        nfft::inv_phase1(re, im, tw, tile, lane);
+        __syncwarp();
+        nfft::inv_phase2(re, im, tile, lane);
+        uint64_t* dst = out + ((size_t)g * 2 + t) * PBS_N;
+#pragma unroll
+        for (int j2 = 0; j2 < 32; ++j2) {
+            dst[lane + 32 * j2] = f64_to_torus(re[j2]);
+            dst[lane + 32 * j2 + PBS_M] = f64_to_torus(im[j2]);
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+cudaError_t launch_glwe_dot(const fhe_b200_pbs_params& p, const double* d_ggswf, const uint64_t* d_in, int64_t G,
+                            uint64_t* d_out, int sm_count, cudaStream_t s) {
+    if (p.k != 1 || p.l_pbs != 2 || p.N != PBS_N || 2 * p.beta_pbs > 62) return cudaErrorInvalidValue;
+    if (G <= 0) return cudaSuccess;
+    const cplx* tw;
+    cudaError_t e = get_tables(&tw);
+    if (e != cudaSuccess) return e;
+    constexpr int NCT = 3;
+    const size_t smem = GlweDotSmem::total(NCT);
+    e = cudaFuncSetAttribute(glwe_dot_kernel<NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t groups = (G + NCT - 1) / NCT;
+    const unsigned grid = (unsigned)(groups < sm_count ? groups : sm_count);
+    glwe_dot_kernel<NCT><<<grid, NCT * 64, smem, s>>>(reinterpret_cast<const cplx*>(d_ggswf), d_in, G, p.beta_pbs, tw, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why) {
     *why = "";
     if (p.N != PBS_N) { *why = "polynomial size N must be 2048"; return false; }

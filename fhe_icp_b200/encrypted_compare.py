@@ -198,18 +198,21 @@ class EncryptedThreshold:
     (score >= T) * 2^60.  Every step has a decision margin of 1/4 of the torus against keyswitch +
     mod-switch noise of ~2^-8.6, so the result is exact for every score and threshold."""
 
-    def __init__(self, ec: EncryptedCompare):
+    def __init__(self, ec: EncryptedCompare, score_bits: int = SCORE_BITS, out_shift: int = OUT_SHIFT):
         self.ec = ec
+        self.score_bits, self.out_shift = int(score_bits), int(out_shift)
+        if self.score_bits + self.out_shift != 64:
+            raise ValueError("the score must fill the torus: score_bits + out_shift == 64")
         p = ec.p
         ec._need_keys()
         self.ksk32 = E.ksk_to_32(p, E.ksk_gen(p, ec.S, ec.s, ec.evk_seed))
         mask = (1 << 64) - 1
-        consts = [(-(1 << (OUT_SHIFT - 1 + i))) & mask for i in range(SCORE_BITS - 1)] + [1 << (BIT_SHIFT - 1)]
+        consts = [(-(1 << (self.out_shift - 1 + i))) & mask for i in range(self.score_bits - 1)] + [1 << (BIT_SHIFT - 1)]
         self.luts = E.from_u64_numpy(np.repeat(np.array(consts, dtype=np.uint64)[:, None], p.N, axis=1), ec.dev)
 
     def threshold_to_int(self, min_similarity: float) -> int:
         """Smallest integer score whose dequantized value is >= min_similarity."""
-        lim = 1 << (SCORE_BITS - 1)
+        lim = 1 << (self.score_bits - 1)
         return int(np.clip(np.ceil(min_similarity / (self.ec.scale ** 2) - 1e-9), -lim // 2, lim // 2 - 1))
 
     def ge(self, scores: torch.Tensor, T: int) -> torch.Tensor:
@@ -217,14 +220,14 @@ class EncryptedThreshold:
         ec, p = self.ec, self.ec.p
         words = p.k * p.N + 1
         fn = E.pbs_mb2 if ec.multibit else E.pbs
-        acc = E.shl_add(scores.contiguous(), words, 0, -(int(T) << OUT_SHIFT))          # v = score - T
-        for i in range(SCORE_BITS):
-            last = i == SCORE_BITS - 1
-            tmp = E.shl_add(acc, words, SCORE_BITS - 1 - i, 1 << 62)                       # bit i on top, + 1/4
+        acc = E.shl_add(scores.contiguous(), words, 0, -(int(T) << self.out_shift))     # v = score - T
+        for i in range(self.score_bits):
+            last = i == self.score_bits - 1
+            tmp = E.shl_add(acc, words, self.score_bits - 1 - i, 1 << 62)                  # bit i on top, + 1/4
             pb = fn(p, ec.bskf, E.keyswitch32(p, self.ksk32, tmp), self.luts[i])
             if last:   # -/+ 2^59 for sign bit 0/1 -> (1 - sign) * 2^60
                 return E.shl_add(pb, words, 0, 1 << (BIT_SHIFT - 1), out_stride=E.even_stride(words - 1))
-            E.sub_plain(acc, pb, 1 << (OUT_SHIFT - 1 + i))                                 # clear bit i
+            E.sub_plain(acc, pb, 1 << (self.out_shift - 1 + i))                            # clear bit i
 
     def buckets(self, scores: torch.Tensor, thresholds) -> torch.Tensor:
         """Number of thresholds each score reaches (e.g. 0.5 / 0.7 / 0.9 -> 0..3), one ciphertext per score."""
@@ -236,3 +239,124 @@ class EncryptedThreshold:
 
     def decrypt(self, bits: torch.Tensor) -> np.ndarray:
         return E.lwe_decrypt(self.ec.S, bits, BIT_SHIFT).cpu().numpy() & 15
+
+
+# ================================================================================================ packed (leveled) variant
+# GLWE side as above (k=1, N=2048) but 2 x 18-bit decomposition levels.  The dominant noise of an external
+# product with a BINARY key is (N/4) * (2^-2*l*beta / 12) * (sum_j Q_j)^2: the key's non-zero mean correlates
+# the rounding errors of all coefficients, so a constant-sign query is the worst case ((sum Q)^2 = d^2 * 2^8
+# at 5-bit factors).  With 36 decomposed bits that worst case is std 2^-22.4 of the torus (measured, oracle and
+# GPU) against a decoding margin of 2^-18: exact for EVERY input, not just zero-mean embeddings.  (At 2 x 15
+# bits the worst case reaches 2^-17.4, inside the margin of a 15-bit score -- rejected.)
+PACKED_PARAMS = dict(COMPARE_PARAMS, beta_pbs=18)
+PACKED_IN_BITS = 5                     # signed factors in [-16, 15]
+PACKED_SCORE_BITS = 17                 # |sum_j x_j*y_j| <= 128 * 256 = 2^15
+PACKED_OUT_SHIFT = 64 - PACKED_SCORE_BITS
+
+
+def pack_documents(Yq: np.ndarray, N_poly: int, slot: int) -> np.ndarray:
+    """int [B, d] -> message polynomials int64 [ceil(B / (N/slot)), N]: document b of a group occupies
+    coefficients slot*b .. slot*b + d - 1."""
+    Yq = np.asarray(Yq, dtype=np.int64)
+    B, d = Yq.shape
+    per = N_poly // slot
+    G = (B + per - 1) // per
+    out = np.zeros((G * per, slot), dtype=np.int64)
+    out[:B, :d] = Yq
+    return out.reshape(G, N_poly)
+
+
+def query_polynomial(xq: np.ndarray, N_poly: int) -> np.ndarray:
+    """Q(X) = sum_j x_j X^(-j) = x_0 - sum_{j>=1} x_j X^(N-j): coefficient m of Q*D is sum_j x_j D_{m+j}."""
+    xq = np.asarray(xq, dtype=np.int64)
+    Q = np.zeros(N_poly, dtype=np.int64)
+    Q[0] = xq[0]
+    Q[N_poly - np.arange(1, xq.size)] = -xq[1:]
+    return Q
+
+
+class PackedEncryptedCompare:
+    """Both vectors encrypted, no bootstrap: documents packed N/slot per GLWE ciphertext, the query a GGSW
+    encryption of Q(X) = sum_j x_j X^(-j); ONE external product per GLWE yields N/slot inner products
+    (coefficient slot*b of the product).  At d = 128: 16 comparisons per external product, 2 KB of
+    ciphertext per document.  The noise of an external product grows with |Q|_2 instead of being reset,
+    which 5-bit factors and two 18-bit decomposition levels absorb (worst case std 2^-22.4 against a
+    decoding margin of 2^-18, see PACKED_PARAMS), so decrypted scores equal sum_j xq_j*yq_j exactly.
+
+    client: keygen / fit_scale / quantize / encrypt_documents / encrypt_query / decrypt / dequantize;
+    server: scores (needs no key material at all -- the GGSW IS the query)."""
+
+    def __init__(self, input_dim: int = 128, params: dict | None = None, key_seed: int = 0x5EED0001, device=None):
+        self.d = int(input_dim)
+        self.pd = dict(params or PACKED_PARAMS)
+        self.p = E.make_pbs_params(**self.pd)
+        self.slot = 1 << max(0, (self.d - 1).bit_length())
+        if self.slot > self.p.N:
+            raise ValueError("input_dim exceeds the polynomial size")
+        if self.d * (1 << (2 * PACKED_IN_BITS - 2)) >= (1 << (PACKED_SCORE_BITS - 1)):
+            raise ValueError("input_dim too large for the 17-bit score range")
+        self.per = self.p.N // self.slot
+        self.dev = E._dev(device)
+        self.key_seed = key_seed
+        self.scale = None
+        self.S = None
+
+    # ---- client
+    def keygen(self) -> "PackedEncryptedCompare":
+        self.S = E.secret_key(self.key_seed, 1, self.p.k * self.p.N, self.dev)
+        return self
+
+    def fit_scale(self, X: np.ndarray, clip_sigmas: float = 2.5) -> float:
+        sd = float(np.asarray(X, dtype=np.float64).std())
+        self.scale = clip_sigmas * sd / (1 << (PACKED_IN_BITS - 1)) if sd > 0 else 1.0
+        return self.scale
+
+    def quantize(self, X: np.ndarray) -> np.ndarray:
+        if self.scale is None:
+            raise RuntimeError("Quantizer not calibrated. Call fit_scale() first.")
+        lo, hi = -(1 << (PACKED_IN_BITS - 1)), (1 << (PACKED_IN_BITS - 1)) - 1
+        return np.clip(np.rint(np.asarray(X, dtype=np.float64) / self.scale), lo, hi).astype(np.int64)
+
+    def dequantize(self, q_scores: np.ndarray) -> np.ndarray:
+        return np.asarray(q_scores, dtype=np.float64) * (self.scale * self.scale)
+
+    def encrypt_documents(self, Yq: np.ndarray, enc_seed: int, id_base: int = 1 << 20) -> torch.Tensor:
+        """int [B, d] -> GLWE [ceil(B/per), 2, N] (documents packed `per` to a ciphertext)."""
+        self._need_keys()
+        polys = torch.as_tensor(pack_documents(Yq, self.p.N, self.slot))
+        return E.glwe_encrypt_vectors(self.p, self.S, polys, PACKED_OUT_SHIFT, enc_seed, id_base)
+
+    def encrypt_query(self, xq: np.ndarray, enc_seed: int, id_base: int = 0) -> torch.Tensor:
+        """int [d] -> Fourier GGSW of Q(X) (the only thing the server needs for this query)."""
+        self._need_keys()
+        ggsw = E.ggsw_encrypt_poly(self.p, self.S, torch.as_tensor(query_polynomial(xq, self.p.N)), enc_seed, id_base)
+        return E.ggsw_to_fourier(self.p, ggsw)
+
+    def decrypt(self, products: torch.Tensor, n_docs: int) -> np.ndarray:
+        self._need_keys()
+        v = E.glwe_decrypt_coeffs(self.p, self.S, products, 0, self.slot, self.per, PACKED_OUT_SHIFT).cpu().numpy()
+        v = v.reshape(-1)[:n_docs] & ((1 << PACKED_SCORE_BITS) - 1)
+        return np.where(v >= (1 << (PACKED_SCORE_BITS - 1)), v - (1 << PACKED_SCORE_BITS), v)
+
+    # ---- server
+    def scores(self, query_ggsw_fourier: torch.Tensor, docs_glwe: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """-> GLWE [G, 2, N]; coefficient slot*b of ciphertext g encrypts the score of document g*per + b."""
+        return E.glwe_ggsw_dot(self.p, query_ggsw_fourier, docs_glwe, out)
+
+    def scores_as_lwe(self, products: torch.Tensor) -> torch.Tensor:
+        """Sample-extract every packed score into its own big-key LWE ciphertext [G*per, kN+2]."""
+        return E.glwe_sample_extract(self.p, products, 0, self.slot, self.per)
+
+    # ---- whole pipeline
+    def compare_clear(self, q: np.ndarray, docs: np.ndarray) -> np.ndarray:
+        return self.quantize(docs) @ self.quantize(q)
+
+    def similarity(self, q: np.ndarray, docs: np.ndarray, enc_seed: int = 1) -> np.ndarray:
+        docs = np.atleast_2d(docs)
+        gq = self.encrypt_query(self.quantize(q), enc_seed)
+        gd = self.encrypt_documents(self.quantize(docs), enc_seed)
+        return self.dequantize(self.decrypt(self.scores(gq, gd), docs.shape[0]))
+
+    def _need_keys(self):
+        if self.S is None:
+            raise RuntimeError("No secret key. Call keygen() first.")

@@ -350,3 +350,67 @@ def make_lut_poly(table, p_bits: int, N_poly: int, delta_out_log2: int) -> np.nd
     out[: N_poly - half] = p0[half:]
     out[N_poly - half:] = np.uint64(0) - p0[:half]
     return out
+
+
+# ------------------------------------------------------------------------------- packed inner products (GLWE x GGSW)
+def glwe_encrypt_vectors(p: N.PBSParams, S_big: torch.Tensor, polys: torch.Tensor, shift: int, seed: int,
+                         id_base: int = 0) -> torch.Tensor:
+    """polys int64 [rows, N] (message polynomials) -> GLWE(poly << shift) [rows, k+1, N]."""
+    dev = S_big.device
+    polys = polys.to(device=dev, dtype=torch.int64).contiguous()
+    rows = polys.shape[0]
+    assert polys.shape[1] == p.N
+    out = torch.empty((rows, p.k + 1, p.N), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_glwe_encrypt_rows(_ctx(dev).handle, C.byref(p), _ptr(S_big), _ptr(polys), rows, p.N, 0, shift,
+                                               seed, id_base, _ptr(out), _stream(dev)))
+    return out
+
+
+def ggsw_encrypt_poly(p: N.PBSParams, S_big: torch.Tensor, poly: torch.Tensor, seed: int, id_base: int = 0) -> torch.Tensor:
+    """poly int64 [N] -> GGSW rows [(k+1)*l, k+1, N] (row t*l+lev carries poly << (64 - beta*(lev+1)) on component t)."""
+    dev = S_big.device
+    poly = poly.to(device=dev, dtype=torch.int64).contiguous()
+    assert poly.numel() == p.N
+    rows = (p.k + 1) * p.l_pbs
+    out = torch.empty((rows, p.k + 1, p.N), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_glwe_encrypt_rows(_ctx(dev).handle, C.byref(p), _ptr(S_big), _ptr(poly), rows, 0, 1, 0, seed,
+                                               id_base, _ptr(out), _stream(dev)))
+    return out
+
+
+def ggsw_to_fourier(p: N.PBSParams, ggsw: torch.Tensor) -> torch.Tensor:
+    """GGSW rows -> Fourier [1][k+1][l][k+1][N/2][2] f64 (the bootstrapping-key transform with n = 1)."""
+    p1 = N.PBSParams(1, p.k, p.N, p.l_pbs, p.beta_pbs, p.l_ks, p.beta_ks, 0, p.sigma_lwe_abs, p.sigma_glwe_abs)
+    return bsk_to_fourier(p1, ggsw.contiguous())
+
+
+def glwe_ggsw_dot(p: N.PBSParams, ggswf: torch.Tensor, glwe: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """GGSW (Fourier) external product with every GLWE of the batch: [G, k+1, N] -> [G, k+1, N]."""
+    dev = glwe.device
+    assert glwe.is_contiguous() and glwe.shape[1:] == (p.k + 1, p.N)
+    if out is None:
+        out = torch.empty_like(glwe)
+    N.check(N.lib().fhe_b200_glwe_ggsw_dot(_ctx(dev).handle, C.byref(p), _ptr(ggswf), _ptr(glwe), glwe.shape[0],
+                                           _ptr(out), _stream(dev)))
+    return out
+
+
+def glwe_decrypt_coeffs(p: N.PBSParams, S_big: torch.Tensor, glwe: torch.Tensor, first: int, step: int, count: int,
+                        shift: int) -> torch.Tensor:
+    dev = glwe.device
+    assert glwe.is_contiguous()
+    out = torch.empty((glwe.shape[0], count), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_glwe_decrypt_coeffs(_ctx(dev).handle, C.byref(p), _ptr(S_big), _ptr(glwe), glwe.shape[0],
+                                                 first, step, count, shift, _ptr(out), _stream(dev)))
+    return out
+
+
+def glwe_sample_extract(p: N.PBSParams, glwe: torch.Tensor, first: int, step: int, count: int) -> torch.Tensor:
+    """-> LWE rows [G*count, even_stride(kN)] under the big key."""
+    dev = glwe.device
+    assert glwe.is_contiguous()
+    stride = even_stride(p.k * p.N)
+    out = torch.empty((glwe.shape[0] * count, stride), dtype=torch.int64, device=dev)
+    N.check(N.lib().fhe_b200_glwe_sample_extract(_ctx(dev).handle, C.byref(p), _ptr(glwe), glwe.shape[0], first, step,
+                                                 count, stride, _ptr(out), _stream(dev)))
+    return out

@@ -38,7 +38,7 @@ enum {
 
 /* RNG stream tags (DESIGN.md "Deterministic randomness") */
 enum { FHE_B200_KIND_SK = 1, FHE_B200_KIND_MASK = 2, FHE_B200_KIND_NOISE = 3 };
-enum { FHE_B200_PUR_INPUT = 0, FHE_B200_PUR_KSK = 1, FHE_B200_PUR_BSK = 2, FHE_B200_PUR_BSK2 = 3 };
+enum { FHE_B200_PUR_INPUT = 0, FHE_B200_PUR_KSK = 1, FHE_B200_PUR_BSK = 2, FHE_B200_PUR_BSK2 = 3, FHE_B200_PUR_GLWE = 4 };
 
 typedef struct fhe_b200_ctx fhe_b200_ctx;
 typedef struct fhe_b200_similarity fhe_b200_similarity;
@@ -150,6 +150,32 @@ int fhe_b200_lwe_pair_addsub(fhe_b200_ctx *ctx, const uint64_t *d_q, const uint6
                              int32_t words, int64_t in_stride, uint64_t offset, uint64_t *d_out, void *stream);
 int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx *ctx, const uint64_t *d_in, int64_t B, int32_t d, int32_t words,
                                int64_t out_stride, uint64_t *d_out, void *stream);
+
+/* ---- packed encrypted inner products: GLWE x GGSW (leveled; no bootstrap) ------------
+ * The fast form of the both-encrypted comparison (same reference anchor: the clear product of
+ * batch_operations.py:226,273).  Documents are packed N/slot per GLWE ciphertext (document b of a
+ * group in coefficients slot*b ..), the query is a GGSW encryption of Q(X) = sum_j x_j X^(-j);
+ * coefficient slot*b of GGSW(Q) [.] GLWE is sum_j x_j*y_{b,j}.  One external product per GLWE.
+ *  glwe_encrypt_rows: row R of d_out [rows][k+1][N] = GLWE_S(0) + (msg_R << shift_R) on component comp_R;
+ *    mode 0: msg_R = d_msgs + R*msg_stride (N coefficients), shift_R = shift, comp_R = k;
+ *    mode 1 (GGSW of one polynomial, rows = (k+1)*l): R = t*l+lev, msg_R = d_msgs, shift_R = 64-beta*(lev+1),
+ *    comp_R = t.  Row R draws mask / noise from object id_base + R, purpose FHE_B200_PUR_GLWE.
+ *  The GGSW goes to the Fourier domain with fhe_b200_bsk_to_fourier and a parameter copy with n = 1
+ *    (layout [t][lev][c][N/2] complex).
+ *  glwe_ggsw_dot: d_out [G][k+1][N] = GGSW [.] d_in[g] for all g (k = 1, l_pbs = 2).
+ *  glwe_decrypt_coeffs (client): d_msgs [G][count] = round(phase of coefficient first+q*step / 2^shift).
+ *  glwe_sample_extract: d_out [(g*count+q)][out_stride] = LWE (big key) of coefficient first+q*step. */
+int fhe_b200_glwe_encrypt_rows(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_S_big,
+                               const int64_t *d_msgs, int64_t rows, int64_t msg_stride, int32_t mode,
+                               int32_t shift, uint64_t seed, uint64_t id_base, uint64_t *d_out, void *stream);
+int fhe_b200_glwe_ggsw_dot(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_ggswf,
+                           const uint64_t *d_in, int64_t G, uint64_t *d_out, void *stream);
+int fhe_b200_glwe_decrypt_coeffs(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_S_big,
+                                 const uint64_t *d_glwe, int64_t G, int32_t first, int32_t step, int32_t count,
+                                 int32_t shift, int64_t *d_msgs, void *stream);
+int fhe_b200_glwe_sample_extract(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_glwe,
+                                 int64_t G, int32_t first, int32_t step, int32_t count, int64_t out_stride,
+                                 uint64_t *d_out, void *stream);
 
 /* One bootstrap per dimension instead of two when each party also sends an encryption of its own
  * squared norm (big key, same scale as the bootstrapped squares):

@@ -458,6 +458,108 @@ void orc_bsk_gen(const orc_pbs_params *p, const uint8_t *s_small, const uint8_t 
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* Packed encrypted inner products (leveled variant): documents are GLWE          */
+/* encryptions of polynomials, the query is a GGSW of a polynomial, one external product per GLWE. */
+/* Row R of `out` ([rows][k+1][N]) = GLWE_S(0) + msg_R(X) << shift_R on component comp_R, where     */
+/*   mode 0 (vectors): msg_R = msgs + R*msg_stride, shift_R = shift, comp_R = k (body);            */
+/*   mode 1 (GGSW of one polynomial): R = t*l + lev, msg_R = msgs, shift_R = 64 - beta*(lev+1),     */
+/*                                    comp_R = t.                                                  */
+/* Randomness: mask words / noise of row R come from object id (id_base + R), purpose ORC_PUR_GLWE. */
+/* ------------------------------------------------------------------ */
+void orc_glwe_encrypt_rows(const orc_pbs_params *p, const uint8_t *S_big, const int64_t *msgs, int64_t rows,
+                           int64_t msg_stride, int32_t mode, int32_t shift, uint64_t seed, uint64_t id_base,
+                           uint64_t *out) {
+    int k = p->k, N = p->N, l = p->l_pbs, beta = p->beta_pbs;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t R = 0; R < rows; ++R) {
+        uint64_t id = id_base + (uint64_t)R;
+        uint64_t *row = out + (size_t)R * (k + 1) * N;
+        uint64_t *body = row + (size_t)k * N;
+        for (int x = 0; x < N; ++x)
+            body[x] = (uint64_t)orc_gaussian(seed, ORC_KIND_NOISE | (ORC_PUR_GLWE << 8), id, (uint32_t)x,
+                                             p->sigma_glwe_abs);
+        for (int c = 0; c < k; ++c) {
+            uint64_t *A = row + (size_t)c * N;
+            for (int x = 0; x < N; ++x) A[x] = mask_word(seed, ORC_PUR_GLWE, id, (int64_t)c * N + x);
+            const uint8_t *S = S_big + (size_t)c * N;
+            for (int y = 0; y < N; ++y) {
+                if (!S[y]) continue;
+                for (int x = 0; x < N - y; ++x) body[x + y] += A[x];
+                for (int x = N - y; x < N; ++x) body[x + y - N] -= A[x];
+            }
+        }
+        const int64_t *m = mode == 0 ? msgs + (size_t)R * msg_stride : msgs;
+        int sh = mode == 0 ? shift : 64 - beta * ((int)(R % l) + 1);
+        int comp = mode == 0 ? k : (int)(R / l);
+        uint64_t *dst = row + (size_t)comp * N;
+        for (int x = 0; x < N; ++x) dst[x] += (uint64_t)m[x] << sh;
+    }
+}
+
+/* out[b] = GGSW (Fourier, [t][lev][c][M] interleaved complex) external-product GLWE in[b]; [B][k+1][N] */
+void orc_glwe_external_product_batch(const orc_pbs_params *p, const double *ggswf, const uint64_t *in, int64_t B,
+                                     uint64_t *out) {
+    int k = p->k, N = p->N, M = N / 2, l = p->l_pbs, beta = p->beta_pbs;
+    const fft_plan *pl = get_plan(N);
+#pragma omp parallel
+    {
+        double *co = (double *)malloc(sizeof(double) * (size_t)N);
+        double *F = (double *)malloc(sizeof(double) * (size_t)(k + 1) * l * N);
+        double *O = (double *)malloc(sizeof(double) * (size_t)N);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t b = 0; b < B; ++b) {
+            const uint64_t *g = in + (size_t)b * (k + 1) * N;
+            uint64_t *o = out + (size_t)b * (k + 1) * N;
+            for (int t = 0; t <= k; ++t)
+                for (int lev = 0; lev < l; ++lev) {
+                    for (int x = 0; x < N; ++x) {
+                        int64_t dg[16];
+                        decompose(g[(size_t)t * N + x], l, beta, dg);
+                        co[x] = (double)dg[lev];
+                    }
+                    double *f = F + ((size_t)t * l + lev) * N;
+                    nega_forward(pl, co, f, f + M);
+                }
+            for (int c = 0; c <= k; ++c) {
+                double *ore = O, *oim = O + M;
+                for (int j = 0; j < M; ++j) { ore[j] = 0.0; oim[j] = 0.0; }
+                for (int t = 0; t <= k; ++t)
+                    for (int lev = 0; lev < l; ++lev) {
+                        const double *f = F + ((size_t)t * l + lev) * N;
+                        const double *gk = ggswf + ((((size_t)t) * l + lev) * (k + 1) + c) * N;
+                        for (int j = 0; j < M; ++j) {
+                            double gr = gk[2 * j], gi = gk[2 * j + 1];
+                            ore[j] += f[j] * gr - f[j + M] * gi;
+                            oim[j] += f[j] * gi + f[j + M] * gr;
+                        }
+                    }
+                memset(o + (size_t)c * N, 0, sizeof(uint64_t) * N);
+                nega_inverse_add(pl, ore, oim, o + (size_t)c * N);
+            }
+        }
+        free(co); free(F); free(O);
+    }
+}
+
+/* LWE sample extraction of coefficient `idx` of each GLWE: out [B][count][kN+1],
+   out[b][q] = extract(in[b], first + q*step).  a_i = A_{idx-i} (i <= idx), -A_{N+idx-i} (i > idx). */
+void orc_glwe_sample_extract(const orc_pbs_params *p, const uint64_t *in, int64_t B, int32_t first, int32_t step,
+                             int32_t count, int64_t out_stride, uint64_t *out) {
+    int k = p->k, N = p->N;
+    for (int64_t b = 0; b < B; ++b)
+        for (int q = 0; q < count; ++q) {
+            int idx = first + q * step;
+            const uint64_t *g = in + (size_t)b * (k + 1) * N;
+            uint64_t *o = out + ((size_t)b * count + q) * out_stride;
+            for (int c = 0; c < k; ++c)
+                for (int i = 0; i < N; ++i)
+                    o[(size_t)c * N + i] = i <= idx ? g[(size_t)c * N + idx - i] : (uint64_t)0 - g[(size_t)c * N + N + idx - i];
+            o[(size_t)k * N] = g[(size_t)k * N + idx];
+            for (int64_t w = (int64_t)k * N + 1; w < out_stride; ++w) o[w] = 0;
+        }
+}
+
 /* bskf[i][t][lev][c][M] complex interleaved (re,im), natural bin order */
 void orc_bsk_to_fourier(const orc_pbs_params *p, const uint64_t *bsk, double *bskf) {
     int N = p->N, M = N / 2;

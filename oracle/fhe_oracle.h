@@ -27,7 +27,7 @@ extern "C" {
 
 /* RNG domain tags (counter word c3 = kind | purpose << 8) -- the spec is in DESIGN.md */
 enum { ORC_KIND_SK = 1, ORC_KIND_MASK = 2, ORC_KIND_NOISE = 3 };
-enum { ORC_PUR_INPUT = 0, ORC_PUR_KSK = 1, ORC_PUR_BSK = 2, ORC_PUR_BSK2 = 3 };
+enum { ORC_PUR_INPUT = 0, ORC_PUR_KSK = 1, ORC_PUR_BSK = 2, ORC_PUR_BSK2 = 3, ORC_PUR_GLWE = 4 };
 
 typedef struct {
     int32_t n;        /* small LWE dimension */
@@ -82,6 +82,13 @@ void orc_bsk2_gen(const orc_pbs_params *p, const uint8_t *s_small, const uint8_t
 void orc_bsk2_to_fourier(const orc_pbs_params *p, const uint64_t *bsk2, double *bskf2);
 void orc_pbs_mb2_batch(const orc_pbs_params *p, const double *bskf2, const uint64_t *in, int64_t B,
                        const uint64_t *luts, const int32_t *lut_index, uint64_t *out);
+void orc_glwe_encrypt_rows(const orc_pbs_params *p, const uint8_t *S_big, const int64_t *msgs, int64_t rows,
+                           int64_t msg_stride, int32_t mode, int32_t shift, uint64_t seed, uint64_t id_base,
+                           uint64_t *out);
+void orc_glwe_external_product_batch(const orc_pbs_params *p, const double *ggswf, const uint64_t *in, int64_t B,
+                                     uint64_t *out);
+void orc_glwe_sample_extract(const orc_pbs_params *p, const uint64_t *in, int64_t B, int32_t first, int32_t step,
+                             int32_t count, int64_t out_stride, uint64_t *out);
 void orc_negacyclic_mul_fft(int32_t N, const int64_t *a, const uint64_t *b, uint64_t *out);
 int orc_num_threads(void);
 void orc_set_num_threads(int t);

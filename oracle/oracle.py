@@ -75,6 +75,10 @@ def lib() -> C.CDLL:
         L.orc_bsk2_gen.argtypes = [pp, u8p, u8p, C.c_uint64, u64p]
         L.orc_bsk2_to_fourier.argtypes = [pp, u64p, f64p]
         L.orc_pbs_mb2_batch.argtypes = [pp, f64p, u64p, C.c_int64, u64p, i32p, u64p]
+        L.orc_glwe_encrypt_rows.argtypes = [pp, u8p, i64p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
+                                            C.c_uint64, u64p]
+        L.orc_glwe_external_product_batch.argtypes = [pp, f64p, u64p, C.c_int64, u64p]
+        L.orc_glwe_sample_extract.argtypes = [pp, u64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, u64p]
         L.orc_negacyclic_mul_fft.argtypes = [C.c_int32, i64p, u64p, u64p]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
@@ -338,6 +342,62 @@ def encrypted_ge(p: PBSParams, ksk32, bskf, scores, T: int, score_bits: int, out
             return pb
         acc -= pb
         acc[:, -1] -= np.uint64(1 << (out_shift - 1 + i))
+
+
+# ----------------------------------------------------------------------------- packed encrypted inner products
+# Leveled variant of the both-encrypted comparison: P = N/slot documents per GLWE ciphertext
+# (document b of a group occupies coefficients slot*b .. slot*b+d-1), the query as a GGSW of
+# Q(X) = sum_j x_j X^(-j); coefficient slot*b of GGSW(Q) [.] GLWE(D) is sum_j x_j * y_{b,j}.
+def pack_documents(Yq, N: int, slot: int) -> np.ndarray:
+    Yq = np.asarray(Yq, dtype=np.int64)
+    B, d = Yq.shape
+    per = N // slot
+    G = (B + per - 1) // per
+    out = np.zeros((G * per, slot), dtype=np.int64)
+    out[:B, :d] = Yq
+    return out.reshape(G, N)
+
+
+def query_polynomial(xq, N: int) -> np.ndarray:
+    xq = np.asarray(xq, dtype=np.int64)
+    Q = np.zeros(N, dtype=np.int64)
+    Q[0] = xq[0]
+    Q[N - np.arange(1, xq.size)] = -xq[1:]
+    return Q
+
+
+def glwe_encrypt_rows(p: PBSParams, S_big, msgs, mode: int, shift: int, seed: int, id_base: int = 0) -> np.ndarray:
+    """mode 0: msgs [rows][N] -> GLWE(msg << shift) [rows][k+1][N]; mode 1: msgs [N] -> GGSW rows [(k+1)*l][k+1][N]."""
+    S_big = np.ascontiguousarray(S_big, dtype=np.uint8)
+    msgs = np.ascontiguousarray(msgs, dtype=np.int64)
+    rows = msgs.shape[0] if mode == 0 else (p.k + 1) * p.l_pbs
+    out = np.zeros((rows, p.k + 1, p.N), dtype=np.uint64)
+    lib().orc_glwe_encrypt_rows(C.byref(p), _p(S_big, C.c_uint8), _p(msgs, C.c_int64), rows, p.N if mode == 0 else 0,
+                                mode, shift, seed, id_base, _p(out, C.c_uint64))
+    return out
+
+
+def ggsw_to_fourier(p: PBSParams, ggsw) -> np.ndarray:
+    p1 = PBSParams(1, p.k, p.N, p.l_pbs, p.beta_pbs, p.l_ks, p.beta_ks, 0, p.sigma_lwe_abs, p.sigma_glwe_abs)
+    return bsk_to_fourier(p1, np.ascontiguousarray(ggsw, dtype=np.uint64))
+
+
+def glwe_external_product(p: PBSParams, ggswf, glwe) -> np.ndarray:
+    glwe = np.ascontiguousarray(glwe, dtype=np.uint64)
+    ggswf = np.ascontiguousarray(ggswf, dtype=np.float64)
+    out = np.zeros_like(glwe)
+    lib().orc_glwe_external_product_batch(C.byref(p), _p(ggswf, C.c_double), _p(glwe, C.c_uint64), glwe.shape[0],
+                                          _p(out, C.c_uint64))
+    return out
+
+
+def glwe_sample_extract(p: PBSParams, glwe, first: int, step: int, count: int, out_stride: int | None = None) -> np.ndarray:
+    glwe = np.ascontiguousarray(glwe, dtype=np.uint64)
+    out_stride = out_stride or p.k * p.N + 1
+    out = np.zeros((glwe.shape[0] * count, out_stride), dtype=np.uint64)
+    lib().orc_glwe_sample_extract(C.byref(p), _p(glwe, C.c_uint64), glwe.shape[0], first, step, count, out_stride,
+                                  _p(out, C.c_uint64))
+    return out
 
 
 def negacyclic_mul_fft(a_small, b_torus) -> np.ndarray:
