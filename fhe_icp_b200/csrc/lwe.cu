@@ -594,45 +594,51 @@ constexpr int GDEC_THREADS = 256;
 __global__ void __launch_bounds__(GDEC_THREADS)
 glwe_decrypt_coeffs_kernel(const uint8_t* __restrict__ S_big, const uint64_t* __restrict__ glwe, int N, int first,
                            int step, int count, int shift, int64_t* __restrict__ out) {
-    extern __shared__ uint64_t gsm[];  // A[N], then S bits, then per-warp partials
+    extern __shared__ uint64_t gsm[];  // A[N], then the key bits
     uint64_t* A = gsm;
     uint32_t* Sb = reinterpret_cast<uint32_t*>(gsm + N);
-    uint64_t* part = gsm + N + N / 64 + 1;
     const uint64_t* g = glwe + (size_t)blockIdx.x * 2 * N;
-    for (int x = threadIdx.x; x < N; x += GDEC_THREADS) A[x] = g[x];
+    for (int x = threadIdx.x; x < N; x += GDEC_THREADS) A[x] = __ldcs(g + x);
     for (int w = threadIdx.x; w < N / 32; w += GDEC_THREADS) {
+        const uint4* sp = reinterpret_cast<const uint4*>(S_big + w * 32);
         uint32_t bits = 0;
-        for (int b = 0; b < 32; ++b) bits |= (uint32_t)(S_big[w * 32 + b] & 1u) << b;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {   // 32 key bytes -> 32 bits
+            const uint4 q4 = sp[v];
+            const uint32_t ws[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) bits |= ((ws[c] >> (8 * bb)) & 1u) << (v * 16 + c * 4 + bb);
+        }
         Sb[w] = bits;
     }
     __syncthreads();
+    // one warp per requested coefficient: no block-wide reduction
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = 0; q < count; ++q) {
+    for (int q = warp; q < count; q += GDEC_THREADS / 32) {
         const int idx = first + q * step;
         uint64_t acc = 0;
-        for (int i = threadIdx.x; i < N; i += GDEC_THREADS) {
-            const uint64_t sel = 0 - (uint64_t)((Sb[i >> 5] >> (i & 31)) & 1u);
+#pragma unroll 4
+        for (int w = 0; w < N / 32; ++w) {
+            const int i = w * 32 + lane;
+            const uint64_t sel = 0 - (uint64_t)((Sb[w] >> lane) & 1u);
             const int m = idx - i;
             const uint64_t a = m >= 0 ? A[m] : (uint64_t)0 - A[m + N];
             acc += a & sel;
         }
         acc = warp_sum_u64(acc);
-        if (lane == 0) part[warp] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint64_t dot = 0;
-            for (int w = 0; w < GDEC_THREADS / 32; ++w) dot += part[w];
-            const uint64_t phase = g[(size_t)N + idx] - dot;
+        if (lane == 0) {
+            const uint64_t phase = g[(size_t)N + idx] - acc;
             out[(size_t)blockIdx.x * count + q] = (int64_t)((phase + (shift ? (1ull << (shift - 1)) : 0)) >> shift);
         }
-        __syncthreads();
     }
 }
 
 cudaError_t launch_glwe_decrypt_coeffs(const uint8_t* d_S_big, const uint64_t* d_glwe, int64_t G, int N, int first,
                                        int step, int count, int shift, int64_t* d_out, cudaStream_t s) {
     if (G <= 0 || count <= 0) return cudaSuccess;
-    const size_t smem = (size_t)N * 8 + ((size_t)N / 64 + 1) * 8 + (GDEC_THREADS / 32) * 8;
+    const size_t smem = (size_t)N * 8 + ((size_t)N / 64 + 1) * 8;
     glwe_decrypt_coeffs_kernel<<<(unsigned)G, GDEC_THREADS, smem, s>>>(d_S_big, d_glwe, N, first, step, count, shift, d_out);
     count_launch();
     return cudaGetLastError();

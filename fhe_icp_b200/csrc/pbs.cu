@@ -1097,7 +1097,15 @@ glwe_dot_kernel(const cplx* __restrict__ ggswf, const uint64_t* __restrict__ in,
         const int64_t g = grp * NCT + ctl;
         if (g >= G) continue;   // whole ciphertext slot idle: both of its warps skip together
         const uint64_t* src = in + ((size_t)g * 2 + t) * PBS_N;
+        {   // pull the polynomial this warp will need in the NEXT iteration into L2 while this one is processed
+            const int64_t gn = g + (int64_t)gridDim.x * NCT;
+            if (gn < G) {
+                const char* nx = reinterpret_cast<const char*>(in + ((size_t)gn * 2 + t) * PBS_N);
 #pragma unroll
+                for (int u = 0; u < 4; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)(lane + 32 * u) * 128));
+            }
+        }
+#pragma unroll 1   // one copy of the forward transform in the instruction cache (ncu: no_instruction stalls)
         for (int lev = 0; lev < L; ++lev) {
             cplx* tile = tiles + (size_t)(t * L + lev) * PBS_TILE;
 #pragma unroll

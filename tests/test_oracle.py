@@ -182,3 +182,24 @@ def test_encrypted_threshold_oracle_exact(O):
     for T in (42, 0, -1536):
         out = O.encrypted_ge(p, ksk32, bskf, cts, T, 13, 51, 60)
         assert np.array_equal(O.lwe_decrypt(S, out, 60) & 15, (vals >= T).astype(np.int64))
+
+
+def test_packed_inner_product_oracle_exact_and_worst_case_noise(O):
+    """Leveled both-encrypted comparison: GGSW(Q) [.] GLWE(packed documents), coefficient slot*b = <x, y_b>.
+    A constant-sign query is the worst case for the noise (binary key, see encrypted_compare.PACKED_PARAMS)."""
+    p = O.make_params(n=742, k=1, N=2048, l_pbs=2, beta_pbs=18)
+    S = O.secret_key(5, 1, 2048)
+    rng = np.random.RandomState(3)
+    d, B, sh = 128, 35, 47
+    for xq in (rng.randint(-16, 16, size=d), np.full(d, -16)):
+        yq = rng.randint(-16, 16, size=(B, d))
+        yq[0] = -16
+        docs = O.glwe_encrypt_rows(p, S, O.pack_documents(yq, 2048, 128), 0, sh, seed=7, id_base=100)
+        assert docs.shape == (3, 2, 2048)
+        gf = O.ggsw_to_fourier(p, O.glwe_encrypt_rows(p, S, O.query_polynomial(xq, 2048), 1, 0, seed=7))
+        lwe = O.glwe_sample_extract(p, O.glwe_external_product(p, gf, docs), 0, 128, 16, 2050)[:B]
+        dec = O.lwe_decrypt(S, lwe, sh) & 131071
+        want = yq @ xq
+        assert np.array_equal(np.where(dec >= 65536, dec - 131072, dec), want)
+        err = (O.lwe_phase(S, lwe) - (want.astype(np.int64).astype(np.uint64) << np.uint64(sh))).view(np.int64)
+        assert np.log2(np.abs(err.astype(np.float64)).max() + 1) - 64 < -19.5      # decoding margin 2^-18
