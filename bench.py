@@ -405,6 +405,11 @@ def run_b200_arm(args):
             if not args.no_cpu_baseline:
                 pair["cpu_baseline"] = cpu_pair_reference(pair["params"], sample)
             line["encrypted_pair"] = pair
+            packed = pbs_bench.measure_packed(dev, args)
+            sample = packed.pop("_sample")
+            if not args.no_cpu_baseline:
+                packed["cpu_baseline"] = cpu_packed_reference(packed["params"], sample)
+            line["encrypted_pair_packed"] = packed
     except ImportError:
         pass
     print(json.dumps(line))
@@ -437,6 +442,32 @@ def cpu_pair_reference(params, sm):
     return {"value": nd / cpu_s, "unit": "comparisons/s", "cores": O.num_threads(), "kind": "port",
             "sample": f"{nd} documents ({nd * d} PBS) in {cpu_s:.1f} s, oracle/fhe_oracle.c (OpenMP)",
             "agrees_with_gpu": bool(np.array_equal(dec, np.asarray(sm["expect"])))}
+
+
+def cpu_packed_reference(params, sm):
+    """CPU baseline of the packed both-encrypted comparison: the oracle's external product (OpenMP over the
+    host cores) on 64 ciphertexts = 1024 documents."""
+    import numpy as np
+    from oracle import oracle as O
+    op = O.make_params(n=params["n"], k=params["k"], N=params["N_poly"], l_pbs=params["l_pbs"],
+                       beta_pbs=params["beta_pbs"], l_ks=params["l_ks"], beta_ks=params["beta_ks"],
+                       log2_sigma_lwe=params["log2_sigma_lwe"], log2_sigma_glwe=params["log2_sigma_glwe"])
+    oS = O.secret_key(sm["key_seed"], 1, op.k * op.N)
+    docs = O.glwe_encrypt_rows(op, oS, O.pack_documents(sm["yq"], op.N, sm["slot"]), 0, sm["out_shift"], 1, 1 << 20)
+    gf = O.ggsw_to_fourier(op, O.glwe_encrypt_rows(op, oS, O.query_polynomial(sm["xq"], op.N), 1, 0, 2, 0))
+    O.glwe_external_product(op, gf, docs[:2])
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        prod = O.glwe_external_product(op, gf, docs)
+    cpu_s = (time.perf_counter() - t0) / reps
+    lwe = O.glwe_sample_extract(op, prod, 0, sm["slot"], sm["per"], op.N + 2)
+    dec = O.lwe_decrypt(oS, lwe, sm["out_shift"]) & 131071
+    dec = np.where(dec >= 65536, dec - 131072, dec)
+    n = len(sm["yq"])
+    return {"value": n / cpu_s, "unit": "comparisons/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"{n} documents ({docs.shape[0]} external products) in {cpu_s * 1e3:.1f} ms, oracle/fhe_oracle.c (OpenMP)",
+            "agrees_with_gpu": bool(np.array_equal(dec[:n], np.asarray(sm["expect"])))}
 
 
 def _decrypt_device(model, out, wire32=False):

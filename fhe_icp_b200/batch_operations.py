@@ -174,11 +174,12 @@ class BatchProcessor:
 
     def _pair_engine(self):
         """fhe="both": the product itself is evaluated under encryption (both vectors encrypted; the
-        reference multiplies them in the clear, batch_operations.py:226,273).  Built on first use."""
+        reference multiplies them in the clear, batch_operations.py:226,273).  Built on first use: the
+        packed GLWE x GGSW engine (16 documents per ciphertext, no bootstrap)."""
         if getattr(self, "_pair", None) is None:
-            from .encrypted_compare import EncryptedCompare
+            from .encrypted_compare import PackedEncryptedCompare
             d = 128
-            self._pair = EncryptedCompare(input_dim=d, device=self.device).keygen()
+            self._pair = PackedEncryptedCompare(input_dim=d, device=self.device).keygen()
             self._pair.fit_scale(np.array([-1.0, 1.0]) / np.sqrt(d))  # unit-norm embeddings: std 1/sqrt(d)
         return self._pair
 
@@ -235,14 +236,17 @@ class BatchProcessor:
         all_docs = self.storage.list_documents()
         if not all_docs:
             return []
-        from .encrypted_compare import EncryptedThreshold
+        from .encrypted_compare import (PACKED_OUT_SHIFT, PACKED_SCORE_BITS, EncryptedCompare, EncryptedThreshold)
         eng = self._pair_engine()
-        if getattr(self, "_thr", None) is None:
-            self._thr = EncryptedThreshold(eng)
+        if getattr(self, "_thr", None) is None:   # bootstrapping + keyswitching keys under the same big key
+            pbs_side = EncryptedCompare(input_dim=eng.d, key_seed=eng.key_seed, device=self.device).keygen()
+            self._thr = EncryptedThreshold(pbs_side, score_bits=PACKED_SCORE_BITS, out_shift=PACKED_OUT_SHIFT,
+                                           scale=eng.scale)
         q = self.reducer.transform(self.embedder.get_embedding(query_text).reshape(1, -1))[0]
-        xq, yq = eng.quantize(q), eng.quantize(self.storage.matrix())
-        ct_q, ct_d = eng.encrypt(xq, enc_seed=1, ct_base=0), eng.encrypt(yq, enc_seed=1, ct_base=eng.d)
-        scores = eng.scores(ct_q, ct_d, eng.encrypt_norms(xq, 1, 0), eng.encrypt_norms(yq, 1, 1))
+        n_docs = len(all_docs)
+        products = eng.scores(eng.encrypt_query(eng.quantize(q), enc_seed=2),
+                              eng.encrypt_documents(eng.quantize(self.storage.matrix()), enc_seed=1))
+        scores = eng.scores_as_lwe(products)[:n_docs].contiguous()
         bits = self._thr.decrypt(self._thr.ge(scores, self._thr.threshold_to_int(min_similarity)))
         return [d["doc_id"] for d, b in zip(all_docs, bits) if b]
 

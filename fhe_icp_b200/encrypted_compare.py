@@ -198,8 +198,10 @@ class EncryptedThreshold:
     (score >= T) * 2^60.  Every step has a decision margin of 1/4 of the torus against keyswitch +
     mod-switch noise of ~2^-8.6, so the result is exact for every score and threshold."""
 
-    def __init__(self, ec: EncryptedCompare, score_bits: int = SCORE_BITS, out_shift: int = OUT_SHIFT):
+    def __init__(self, ec: EncryptedCompare, score_bits: int = SCORE_BITS, out_shift: int = OUT_SHIFT,
+                 scale: float | None = None):
         self.ec = ec
+        self.scale = scale          # quantizer scale of the scores' producer (defaults to ec.scale)
         self.score_bits, self.out_shift = int(score_bits), int(out_shift)
         if self.score_bits + self.out_shift != 64:
             raise ValueError("the score must fill the torus: score_bits + out_shift == 64")
@@ -213,7 +215,8 @@ class EncryptedThreshold:
     def threshold_to_int(self, min_similarity: float) -> int:
         """Smallest integer score whose dequantized value is >= min_similarity."""
         lim = 1 << (self.score_bits - 1)
-        return int(np.clip(np.ceil(min_similarity / (self.ec.scale ** 2) - 1e-9), -lim // 2, lim // 2 - 1))
+        scale = self.scale if self.scale is not None else self.ec.scale
+        return int(np.clip(np.ceil(min_similarity / (scale ** 2) - 1e-9), -lim // 2, lim // 2 - 1))
 
     def ge(self, scores: torch.Tensor, T: int) -> torch.Tensor:
         """scores [B, stride] (big key) -> [B, kN+2] encrypting (score >= T) * 2^BIT_SHIFT."""

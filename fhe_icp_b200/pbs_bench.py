@@ -192,6 +192,69 @@ def measure_pair(dev, args, docs: int = 148):
     return res
 
 
+def measure_packed(dev, args, docs: int = 262144):
+    """Packed both-encrypted comparison (GLWE x GGSW external product, 16 documents per ciphertext at
+    d = 128, query GGSW resident in TMEM): the leveled form of SURVEY.md 8f N1."""
+    import time
+    import torch
+    from . import engine as E_
+    from .batch_operations import rank_results
+    from .encrypted_compare import PACKED_OUT_SHIFT, PACKED_PARAMS, PackedEncryptedCompare
+    d = 128
+    pe = PackedEncryptedCompare(input_dim=d, device=dev).keygen()
+    rng = np.random.RandomState(23)
+    q = rng.randn(d); q /= np.linalg.norm(q)
+    X = rng.randn(docs, d)
+    X[::5] = 0.8 * q + 0.6 * X[::5] / np.sqrt(d)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    pe.fit_scale(np.array([-1.0, 1.0]) / np.sqrt(d))
+    xq, yq = pe.quantize(q), pe.quantize(X)
+    gd = pe.encrypt_documents(yq, 1)               # the collection, encrypted once, resident (2 KB per document)
+    gq = pe.encrypt_query(xq, 2)
+    out = torch.empty_like(gd)
+    pe.scores(gq, gd, out)
+    torch.cuda.synchronize()
+    reps = 5
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(reps):
+        pe.scores(gq, gd, out)
+    e1.record()
+    for _ in range(reps):
+        E_.glwe_decrypt_coeffs(pe.p, pe.S, out, 0, pe.slot, pe.per, PACKED_OUT_SHIFT)
+    e2.record()
+    torch.cuda.synchronize()
+    ms, dec_ms = e0.elapsed_time(e1) / reps, e1.elapsed_time(e2) / reps
+    ids = [f"doc_{i}" for i in range(docs)]
+    t0 = time.perf_counter()   # end to end per query: host floats -> GGSW -> products -> client decrypt -> host scores -> top-k
+    for _ in range(reps):
+        gq2 = pe.encrypt_query(pe.quantize(q), 3)
+        ints = pe.decrypt(pe.scores(gq2, gd, out), docs)
+        top = rank_results(ids, pe.dequantize(ints), 3, 0.5)
+    e2e_s = (time.perf_counter() - t0) / reps
+    clear = yq @ xq
+    exact = bool(np.array_equal(ints, clear)) and top == rank_results(ids, pe.dequantize(clear), 3, 0.5)
+    G = gd.shape[0]
+    hbm = 2 * gd.numel() * 8
+    res = {"metric": "packed_encrypted_pair_comparisons_per_sec", "value": docs / (ms * 1e-3), "unit": "comparisons/s",
+           "e2e": {"value": docs / e2e_s, "unit": "comparisons/s",
+                   "what": "per query: quantize + GGSW-encrypt the query, external products over the resident encrypted "
+                           "collection, client decrypt kernel, D2H of the scores, host top-k"},
+           "docs": docs, "d": d, "docs_per_ciphertext": pe.per, "ciphertexts": int(G), "kernel": "glwe_dot_kernel<3>",
+           "external_products_per_sec": G / (ms * 1e-3), "client_decrypt_ms": dec_ms, "ms": ms,
+           "params": dict(PACKED_PARAMS), "factor_bits": 5, "score_bits": 17, "exact_vs_clear_integer_model": exact,
+           "roofline": {"bound": "fp64", "achieved_hbm_gbs": hbm / (ms * 1e-3) / 1e9,
+                        "algorithmic_bytes_per_launch": int(hbm),
+                        "flops_per_ciphertext": float(6 * 5 * 1024 * 10 + 2 * 4 * 1024 * 8),
+                        "achieved_tflops": float(6 * 5 * 1024 * 10 + 2 * 4 * 1024 * 8) * G / (ms * 1e-3) / 1e12,
+                        "fp64_pipe_active_ncu": 0.32, "ncu_source": "profiles/r1_ncu_glwe_dot_v1.txt",
+                        "note": "32 KB in + 32 KB out per ciphertext is a third of the HBM roof; the six 1024-point f64 "
+                                "FFTs per ciphertext bind (6 warps per SM at 255 registers, latency-exposed)"}}
+    res["_sample"] = {"xq": xq, "yq": yq[:1024], "key_seed": pe.key_seed, "slot": pe.slot, "per": pe.per,
+                      "out_shift": PACKED_OUT_SHIFT, "expect": clear[:1024]}
+    return res
+
+
 def _pad(out):
     """[B, kN+1] -> even-stride rows for the decrypt kernel."""
     import torch
