@@ -193,3 +193,77 @@ def test_sharded_pair_search_world2(n_docs):
     clear = eng.quantize(docs) @ eng.quantize(q)
     assert ret["ints"] == clear.tolist()
     assert ret["res"] == rank_results([f"doc_{i}" for i in range(n_docs)], eng.dequantize(clear), 3, -10.0)
+
+
+# ------------------------------------------------------------------ packed both-encrypted search (ShardedPackedSearch)
+class OraclePackedEngine:
+    """CPU stand-in for PackedEncryptedCompare (same method names) over the oracle."""
+    OUT_SHIFT = 47
+
+    def __init__(self, d, client):
+        from oracle import oracle as O
+        self.O, self.d, self.dev = O, d, torch.device("cpu")
+        self.p = O.make_params(n=742, k=1, N=2048, l_pbs=2, beta_pbs=18)
+        self.slot = 1 << (d - 1).bit_length()
+        self.per = 2048 // self.slot
+        self.scale = 1.0 / 16
+        self.S = O.secret_key(5, 1, 2048) if client else None      # only the client rank holds the key
+
+    def quantize(self, X):
+        return np.clip(np.rint(np.asarray(X, dtype=np.float64) / self.scale), -16, 15).astype(np.int64)
+
+    def dequantize(self, q):
+        return np.asarray(q, dtype=np.float64) * self.scale ** 2
+
+    def encrypt_documents(self, Yq, enc_seed, id_base=1 << 20):
+        ct = self.O.glwe_encrypt_rows(self.p, self.S, self.O.pack_documents(Yq, 2048, self.slot), 0, self.OUT_SHIFT,
+                                      enc_seed, id_base)
+        return torch.from_numpy(ct.view(np.int64))
+
+    def encrypt_query(self, xq, enc_seed, id_base=0):
+        gg = self.O.glwe_encrypt_rows(self.p, self.S, self.O.query_polynomial(xq, 2048), 1, 0, enc_seed, id_base)
+        return torch.from_numpy(self.O.ggsw_to_fourier(self.p, gg))
+
+    def scores(self, gq, glwe):
+        return torch.from_numpy(self.O.glwe_external_product(self.p, gq.numpy(), glwe.numpy().view(np.uint64)).view(np.int64))
+
+    def decrypt(self, prod, n_docs):
+        lwe = self.O.glwe_sample_extract(self.p, prod.numpy().view(np.uint64), 0, self.slot, self.per, 2050)
+        v = self.O.lwe_decrypt(self.S, lwe, self.OUT_SHIFT)[:n_docs] & 131071
+        return np.where(v >= 65536, v - 131072, v)
+
+
+def _packed_worker(rank, world, port, n_docs, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fhe_icp_b200.sharded_search import ShardedPackedSearch
+        rng = np.random.RandomState(n_docs)
+        q, docs = rng.uniform(-1, 1, size=100), rng.uniform(-1, 1, size=(n_docs, 100))
+        eng = OraclePackedEngine(100, client=rank == 0)
+        sp = ShardedPackedSearch(eng, docs if rank == 0 else None, chunk_groups=1)
+        assert rank == 0 or eng.S is None
+        ints = sp.search_scores(q if rank == 0 else None)
+        res = sp.search(q if rank == 0 else None, top_k=4, min_similarity=-100.0)
+        if rank == 0:
+            ret["ints"], ret["res"] = ints.tolist(), res
+        else:
+            assert ints is None and res is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_docs", [53, 16, 3])
+def test_sharded_packed_search_world2(n_docs):
+    """53 documents = 4 ciphertexts (2 per rank, last one ragged); 16 = one ciphertext (rank 1 idle); 3 = partial."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_packed_worker, args=(world, port, n_docs, ret), nprocs=world, join=True)
+    from fhe_icp_b200.batch_operations import rank_results
+    rng = np.random.RandomState(n_docs)
+    q, docs = rng.uniform(-1, 1, size=100), rng.uniform(-1, 1, size=(n_docs, 100))
+    eng = OraclePackedEngine(100, client=True)
+    clear = eng.quantize(docs) @ eng.quantize(q)
+    assert ret["ints"] == clear.tolist()
+    assert ret["res"] == rank_results([f"doc_{i}" for i in range(n_docs)], eng.dequantize(clear), 4, -100.0)
