@@ -202,8 +202,15 @@ def workload_config(args, c):
             "ciphertext_words": c.lwe.stride, "log2_delta": c.lwe.shift, "log2_sigma": round(c.lwe.log2_sigma, 2),
             "outputs_per_comparison": 2 if c.two_outputs else 1,
             "bytes_per_comparison": comparison_bytes(c),
-            "multi_gpu": "contiguous document shards; encrypted scores (32-bit wire form) gathered to the client rank "
-                         "over NCCL and decrypted there, overlapped with the next step",
+            "multi_gpu": {
+                "push": "contiguous document shards; the dot-product kernel of every rank stores its encrypted scores "
+                        "(32-bit wire form) into the client GPU's score board over NVLink (cudaIpc peer memory) and flags "
+                        "their arrival; the client decrypts them under the next step's dot products; no collective",
+                "local": "single GPU: scores decrypted in place",
+            }.get(getattr(args, "_gather_mode", "local"),
+                  "contiguous document shards; encrypted scores (32-bit wire form) gathered to the client rank "
+                  "over NCCL and decrypted there, overlapped with the next step"),
+            "gather_mode": getattr(args, "_gather_mode", "local"),
             "l2_policy": "inputs larger than L2 (ciphertext set per step >= 1 GB vs 126 MB L2), no flush",
             "seeds": {"data": DATA_SEED, "key": KEY_SEED, "enc": ENC_SEED}}
 
@@ -228,6 +235,7 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
         # NCCL's stream (and the post stream below) run at high priority: the dot-product kernel keeps
         # thousands of CTAs queued, and equal-priority kernels only start once those are all dispatched
         opts = dist.ProcessGroupNCCL.Options()
@@ -249,21 +257,54 @@ def run_b200_arm(args):
     out = torch.empty((B, M, c.lwe.stride), dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
 
-    # Multi-GPU step: every rank evaluates its shard (server), the encrypted scores are all-gathered to
-    # the client rank over NCCL, and rank 0 decrypts all of them.  The gather + decrypt of step i run on
-    # a second stream, overlapped with the dot products of step i+1 (double-buffered outputs).
-    outs = [out, torch.empty_like(out)] if world > 1 else [out]
+    # Multi-GPU step: every rank evaluates its shard (server) and the encrypted scores reach the client
+    # rank, which decrypts all of them.
+    #   push (default): the dot-product kernel itself stores the scores, in the 32-bit wire form, into the
+    #     client GPU's score board over NVLink and flags their arrival (fhe_icp_b200/score_board.py); the
+    #     client's wait + decrypt + credit kernels of step i run on a second stream under the dot products
+    #     of step i+1.  No collective, no extra pass over the scores.
+    #   all_gather / gather: scores written locally, compressed (modulus switch to 32 bits) and moved by
+    #     NCCL on a high-priority stream, overlapped with step i+1 (double-buffered outputs).
+    mode = args.gather_mode if world > 1 else "local"
+    board = None
+    if mode == "push":
+        from fhe_icp_b200.score_board import PeerScoreBoard
+        try:
+            board = PeerScoreBoard(model, B, client_rank=0)
+        except Exception as e:  # e.g. no peer access between the GPUs of this box: NCCL path instead
+            print(f"bench.py: rank {rank}: peer score board unavailable ({e}); using all_gather", file=sys.stderr)
+            mode = "all_gather"
+        flag = torch.tensor([1 if mode == "push" else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # every rank takes the same path
+        if int(flag.item()) == 0 and mode == "push":
+            board.close()
+            board, mode = None, "all_gather"
+    nccl = mode in ("gather", "all_gather")
+    outs = [out, torch.empty_like(out)] if nccl else [out]
     # scores travel in the 32-bit wire form (modulus switch 2^64 -> 2^32) and only to the client rank:
     # at 8 GPUs the client's inbound NVLink would otherwise carry 160 MB per 0.22 ms step
-    outs32 = [torch.empty(o.shape, dtype=torch.int32, device=dev) for o in outs] if world > 1 else None
-    allg = args.gather_mode == "all_gather"
+    outs32 = [torch.empty(o.shape, dtype=torch.int32, device=dev) for o in outs] if nccl else None
+    allg = mode == "all_gather"
     gathered = [torch.empty((world * B, M, c.lwe.stride), dtype=torch.int32, device=dev) for _ in outs] \
-        if (world > 1 and (rank == 0 or allg)) else None
+        if (nccl and (rank == 0 or allg)) else None
     post = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     done = [None, None]
+    last_board = [None]
 
     def step(i, ev=None):
         cur = torch.cuda.current_stream(dev)
+        if mode == "push":
+            if ev:
+                ev[0].record()
+            board.push(ct)                               # server: dot products, scores pushed to the client
+            if ev:
+                ev[1].record()
+            if rank == 0:
+                with torch.cuda.stream(post):
+                    last_board[0] = board.collect()      # client: wait for every shard's arrival flag,
+                    _decrypt_device(model, last_board[0], wire32=True)   # decrypt every shard's scores,
+                    board.release()                      # hand the slot back
+            return
         k = i % len(outs)
         if world > 1 and done[k] is not None:
             cur.wait_event(done[k])                      # buffer k was consumed by the post stream
@@ -292,12 +333,23 @@ def run_b200_arm(args):
     for i in range(max(args.warmup, 3)):
         step(i)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     ref = model.predict_clear(X)
-    y_dev = model.decrypt(outs[0])
-    assert np.array_equal(y_dev, ref), "GPU scores differ from the clear quantized circuit"
-    if world > 1 and rank == 0:   # the gathered scores of every shard decrypt to each shard's clear result
-        y_all = model.decrypt_compressed(gathered[0])
-        assert np.array_equal(y_all[:B], ref)
+    if mode == "push":
+        board.check()
+        if rank == 0:   # the pushed scores of every shard decrypt to each shard's clear result
+            y_all = model.decrypt_compressed(last_board[0])
+            assert np.array_equal(y_all[:B], ref), "pushed scores differ from the clear quantized circuit"
+            refs = [model.predict_clear(synthetic_docs(args.docs, DATA_SEED + 1 + r)[2]) for r in range(1, world)]
+            for r, rr in enumerate(refs, start=1):
+                assert np.array_equal(y_all[r * B:(r + 1) * B], rr), f"rank {r}'s pushed scores differ from its clear result"
+    else:
+        y_dev = model.decrypt(outs[0])
+        assert np.array_equal(y_dev, ref), "GPU scores differ from the clear quantized circuit"
+        if world > 1 and rank == 0:   # the gathered scores of every shard decrypt to each shard's clear result
+            y_all = model.decrypt_compressed(gathered[0])
+            assert np.array_equal(y_all[:B], ref)
 
     # --- timed region: K steps, device-resident inputs
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -352,6 +404,10 @@ def run_b200_arm(args):
     e2e_expanded, _ = e2e_run("expanded")     # full ciphertexts materialised in HBM between the stages
     e2e_value, hits = e2e_run("seeded")       # the default: fresh ciphertexts as 8-byte bodies + public mask seed
     clocks = sampler.stop() if rank == 0 else None  # sampled over the timed region and the e2e region
+    if board is not None:
+        board.check()      # no in-stream wait timed out
+        board.close()
+    args._gather_mode = mode
     assert [i for i, _ in hits] == [i for i, _ in top_k(ref, 3, -np.inf)], "top-k ranking differs from the clear circuit"
 
     if rank != 0:
@@ -499,8 +555,9 @@ def main():
                     help="resident ciphertext format for the device-timed step: expanded = full (n+1)-word ciphertexts "
                          "(HBM-bound dot product, the headline); seeded = 8-byte bodies, masks regenerated on the fly "
                          "(integer-bound; what makes the 1M-document configuration fit)")
-    ap.add_argument("--gather-mode", default="all_gather", choices=["gather", "all_gather"],
-                    help="how encrypted scores reach the client rank (N>1)")
+    ap.add_argument("--gather-mode", default="push", choices=["push", "gather", "all_gather"],
+                    help="how encrypted scores reach the client rank (N>1): push = stored by the dot-product kernel "
+                         "into the client's memory over NVLink (peer score board); gather / all_gather = NCCL")
     ap.add_argument("--pbs-batch", type=int, default=0, help="PBS microbench batch (0 = default sweep)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the PBS / encrypted-pair sections that follow the timed loop (for a clean ncu launch list)")

@@ -56,6 +56,14 @@ class SimilaritySpec(C.Structure):
     ]
 
 
+class Push(C.Structure):
+    """``fhe_b200_push``: destination of one evaluation pushed to the client's score board."""
+    _fields_ = [("d_board32", C.c_void_p), ("d_arrive", C.c_void_p), ("step", C.c_uint64), ("d_counter", C.c_void_p)]
+
+
+IPC_HANDLE_BYTES = 64
+
+
 def _stale() -> bool:
     if not _SO.exists():
         return True
@@ -154,6 +162,14 @@ SIGNATURES = {
     "fhe_b200_similarity_encrypt": (C.c_int, [_vp, _vp, C.c_int64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "fhe_b200_similarity_run": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
     "fhe_b200_similarity_decrypt": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp]),
+    "fhe_b200_peer_alloc": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp), _u8p]),
+    "fhe_b200_peer_open": (C.c_int, [_vp, _u8p, C.POINTER(_vp)]),
+    "fhe_b200_peer_close": (C.c_int, [_vp, _vp]),
+    "fhe_b200_peer_free": (C.c_int, [_vp, _vp]),
+    "fhe_b200_similarity_run_push": (C.c_int, [_vp, _vp, C.c_int64, C.POINTER(Push), _vp]),
+    "fhe_b200_similarity_run_seeded_push": (C.c_int, [_vp, _vp, C.c_int64, C.c_uint64, C.c_uint64, C.POINTER(Push), _vp]),
+    "fhe_b200_peer_wait": (C.c_int, [_vp, _vp, C.c_int32, C.c_uint64, C.c_uint32, _vp, _vp]),
+    "fhe_b200_peer_signal": (C.c_int, [_vp, _vp, C.c_int32, C.c_uint64, _vp]),
 }
 
 

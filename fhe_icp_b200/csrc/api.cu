@@ -744,6 +744,113 @@ int fhe_b200_similarity_decrypt32(fhe_b200_similarity* s, const uint32_t* d_out3
     return FHE_B200_OK;
 }
 
+// ---- multi-GPU search: peer score board ---------------------------------------------------------------
+int fhe_b200_peer_alloc(fhe_b200_ctx* ctx, uint64_t bytes, void** d_ptr, uint8_t* handle) {
+    REQUIRE(ctx && d_ptr && handle, "peer_alloc: null argument");
+    REQUIRE(bytes > 0, "peer_alloc: empty allocation");
+    *d_ptr = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(FHE_B200_ERR_CUDA, "peer_alloc: %s", cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == FHE_B200_IPC_HANDLE_BYTES, "ipc handle size");
+    memcpy(handle, &h, sizeof(h));
+    *d_ptr = p;
+    return FHE_B200_OK;
+}
+
+int fhe_b200_peer_open(fhe_b200_ctx* ctx, const uint8_t* handle, void** d_ptr) {
+    REQUIRE(ctx && d_ptr && handle, "peer_open: null argument");
+    *d_ptr = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = p;
+    return FHE_B200_OK;
+}
+
+int fhe_b200_peer_close(fhe_b200_ctx* ctx, void* d_ptr) {
+    REQUIRE(ctx, "peer_close: null context");
+    if (!d_ptr) return FHE_B200_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_peer_free(fhe_b200_ctx* ctx, void* d_ptr) {
+    REQUIRE(ctx, "peer_free: null context");
+    if (!d_ptr) return FHE_B200_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFree(d_ptr));
+    return FHE_B200_OK;
+}
+
+static int check_push(const fhe_b200_push* p) {
+    REQUIRE(p, "null push descriptor");
+    REQUIRE(p->d_board32 && p->d_arrive && p->d_counter, "push: null device pointer");
+    REQUIRE(p->step > 0, "push: step must be positive");
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_run_push(fhe_b200_similarity* s, const uint64_t* d_ct, int64_t B, const fhe_b200_push* push,
+                                 void* stream) {
+    REQUIRE(s, "null model");
+    REQUIRE(B > 0, "run_push: empty batch (signal the arrival flag with fhe_b200_peer_signal instead)");
+    REQUIRE(d_ct, "null device pointer");
+    if (int r = check_push(push)) return r;
+    const auto& sp = s->spec;
+    REQUIRE(sp.shift >= 32, "the 32-bit wire form needs log2(Delta) >= 32");
+    CU(cudaSetDevice(s->ctx->device));
+    CU(fhe::launch_lincomb_push(d_ct, B, sp.d, sp.n, sp.stride, s->d_W, s->M, s->second_is_sum, 0, 0, sp.shift, *push,
+                                (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_run_seeded_push(fhe_b200_similarity* s, const uint64_t* d_bodies, int64_t B, uint64_t enc_seed,
+                                        uint64_t ct_base, const fhe_b200_push* push, void* stream) {
+    REQUIRE(s, "null model");
+    REQUIRE(B > 0, "run_seeded_push: empty batch (signal the arrival flag with fhe_b200_peer_signal instead)");
+    REQUIRE(d_bodies, "null device pointer");
+    if (int r = check_push(push)) return r;
+    const auto& sp = s->spec;
+    REQUIRE(sp.shift >= 32, "the 32-bit wire form needs log2(Delta) >= 32");
+    CU(cudaSetDevice(s->ctx->device));
+    CU(fhe::launch_lincomb_seeded_push(d_bodies, B, sp.d, sp.n, sp.stride, enc_seed, ct_base, FHE_B200_PUR_INPUT, s->d_W,
+                                       s->M, s->second_is_sum, 0, 0, sp.shift, *push, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_peer_wait(fhe_b200_ctx* ctx, const uint64_t* d_flags, int32_t count, uint64_t value, uint32_t timeout_ms,
+                       uint32_t* d_status, void* stream) {
+    REQUIRE(ctx, "peer_wait: null context");
+    REQUIRE(count >= 0, "peer_wait: negative count");
+    if (count == 0) return FHE_B200_OK;
+    REQUIRE(d_flags && d_status, "peer_wait: null device pointer");
+    REQUIRE(timeout_ms > 0, "peer_wait: timeout_ms must be positive");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_peer_wait(d_flags, count, value, timeout_ms, d_status, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_peer_signal(fhe_b200_ctx* ctx, uint64_t* const* d_flag_ptrs, int32_t count, uint64_t value, void* stream) {
+    REQUIRE(ctx, "peer_signal: null context");
+    REQUIRE(count >= 0, "peer_signal: negative count");
+    if (count == 0) return FHE_B200_OK;
+    REQUIRE(d_flag_ptrs, "peer_signal: null device pointer");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_peer_signal(d_flag_ptrs, count, value, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, int64_t B, uint64_t enc_seed,
                                      uint64_t ct_base, double* h_y, int64_t* h_q_y) {
     REQUIRE(s, "null model");

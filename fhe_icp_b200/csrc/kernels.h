@@ -26,6 +26,16 @@ cudaError_t launch_lwe_expand_seeded(const uint64_t* d_bodies, int64_t count, in
 cudaError_t launch_lincomb_seeded(const uint64_t* d_bodies, int64_t B, int d, int n, int64_t stride, uint64_t enc_seed,
                                   uint64_t ct_base, uint32_t purpose, const int64_t* d_W, int M, bool second_is_sum,
                                   int64_t bias0, int64_t bias1, int shift, uint64_t* d_out, cudaStream_t s);
+cudaError_t launch_lincomb_push(const uint64_t* d_ct, int64_t B, int d, int n, int64_t stride, const int64_t* d_W, int M,
+                                bool second_is_sum, int64_t bias0, int64_t bias1, int shift, const fhe_b200_push& push,
+                                cudaStream_t s);
+cudaError_t launch_lincomb_seeded_push(const uint64_t* d_bodies, int64_t B, int d, int n, int64_t stride,
+                                       uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, const int64_t* d_W, int M,
+                                       bool second_is_sum, int64_t bias0, int64_t bias1, int shift,
+                                       const fhe_b200_push& push, cudaStream_t s);
+cudaError_t launch_peer_wait(const uint64_t* d_flags, int count, uint64_t value, uint32_t timeout_ms,
+                             uint32_t* d_status, cudaStream_t s);
+cudaError_t launch_peer_signal(uint64_t* const* d_flag_ptrs, int count, uint64_t value, cudaStream_t s);
 cudaError_t launch_lwe_modswitch32(const uint64_t* d_in, int64_t words, uint32_t* d_out, cudaStream_t s);
 cudaError_t launch_lwe_decrypt32(const uint8_t* d_key, int n, int64_t stride, const uint32_t* d_ct, int64_t count,
                                  int shift32, int64_t* d_out, cudaStream_t s);

@@ -138,6 +138,66 @@ cudaError_t launch_lwe_phase(const uint8_t* d_key, int n, int64_t stride, const 
 constexpr int LC_THREADS = 256;
 constexpr int LC_UNROLL = 8;
 
+// ---- pushed scores (multi-GPU search) ---------------------------------------------------------------
+// With a PushArgs destination the dot-product kernels do the gather themselves: every thread writes its
+// two finished score words in the 32-bit wire form (modulus switch 2^64 -> 2^32, exactly
+// lwe_modswitch32_kernel) straight into the CLIENT GPU's score board -- a peer mapping of the client's
+// memory, so the stores travel over NVLink while the other CTAs are still streaming ciphertexts -- and
+// the last CTA to finish publishes `step` in the client's arrival flag (release at system scope).
+// Flow control: the board has two slots; the caller orders the launch behind a one-warp wait
+// (peer_wait_kernel) on the credit flag the client bumps once it has decrypted the slot's previous
+// contents.  The wait is NOT done inside this kernel: spinning CTAs would hold their SM slots and could
+// lock the client's own decrypt kernels out of the GPU that has to produce the credit.
+struct PushArgs {
+    uint32_t* board;         // peer: this rank's rows of the slot, [B][M][stride] u32
+    uint64_t* arrive;        // peer: arrival flag of (slot, rank) in the client's memory
+    uint64_t step;           // value published on arrival (monotonic, > 0)
+    uint32_t* counter;       // local: finished-CTA counter, left at zero
+};
+
+__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// bounded spin: false on time-out (never hangs the GPU if a peer died)
+__device__ __noinline__ bool spin_until_ge(const uint64_t* flag, uint64_t need, uint64_t timeout_ns) {
+    if (ld_acquire_sys_u64(flag) >= need) return true;
+    const uint64_t t0 = global_timer_ns();
+    while (ld_acquire_sys_u64(flag) < need) {
+        if (global_timer_ns() - t0 > timeout_ns) return false;
+        __nanosleep(256);
+    }
+    return true;
+}
+__device__ __forceinline__ void push_store(uint32_t* o, uint64_t x, uint64_t y) {
+    uint2 v;
+    v.x = (uint32_t)((x + 0x80000000ULL) >> 32);
+    v.y = (uint32_t)((y + 0x80000000ULL) >> 32);
+    *reinterpret_cast<uint2*>(o) = v;
+}
+// every thread of the CTA calls this after its stores
+__device__ __forceinline__ void push_arrive(const PushArgs& p) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(p.counter, 1u);
+        if (prev == gridDim.x - 1) {
+            atomicExch(p.counter, 0u);
+            __threadfence_system();
+            st_release_sys_u64(p.arrive, p.step);
+        }
+    }
+}
+
 template <int M, bool SECOND_IS_SUM, int UNROLL>
 __device__ __forceinline__ void lc_mac(const u64x2 (&x)[UNROLL], const int64_t* sW, int d, int j, uint64_t& a0x,
                                        uint64_t& a0y, uint64_t& a1x, uint64_t& a1y) {
@@ -159,15 +219,10 @@ __device__ __forceinline__ void lc_mac(const u64x2 (&x)[UNROLL], const int64_t* 
     }
 }
 
-template <int M, bool SECOND_IS_SUM, int UNROLL>
-__global__ void __launch_bounds__(LC_THREADS)
-lincomb_kernel(const uint64_t* __restrict__ ct, int d, int n_words, int64_t stride, int64_t total_vecs,
-               const int64_t* __restrict__ W, uint64_t bias0, uint64_t bias1, uint64_t* __restrict__ out) {
-    extern __shared__ int64_t sW[];  // [M][d]
-    for (int i = threadIdx.x; i < M * d; i += blockDim.x) sW[i] = W[i];
-    __syncthreads();
-    const int64_t g = (int64_t)blockIdx.x * LC_THREADS + threadIdx.x;
-    if (g >= total_vecs) return;
+template <int M, bool SECOND_IS_SUM, int UNROLL, bool PUSH>
+__device__ __forceinline__ void lincomb_thread(const uint64_t* __restrict__ ct, int d, int n_words, int64_t stride,
+                                               int64_t g, const int64_t* sW, uint64_t bias0, uint64_t bias1,
+                                               uint64_t* __restrict__ out, const PushArgs& push) {
     const int vecs = (int)(stride >> 1);
     const int64_t b = g / vecs;
     const int w0 = 2 * (int)(g - b * vecs);
@@ -198,14 +253,35 @@ lincomb_kernel(const uint64_t* __restrict__ ct, int d, int n_words, int64_t stri
     if (w0 + 1 == nb) { a0y += bias0; a1y += bias1; }
     if (w0 >= n_words) { a0x = 0; a1x = 0; }
     if (w0 + 1 >= n_words) { a0y = 0; a1y = 0; }
-    uint64_t* o = out + (size_t)b * M * stride + w0;
-    st_stream_u64x2(o, u64x2{a0x, a0y});
-    if (M == 2) st_stream_u64x2(o + stride, u64x2{a1x, a1y});
+    if (PUSH) {
+        uint32_t* o = push.board + (size_t)b * M * stride + w0;
+        push_store(o, a0x, a0y);
+        if (M == 2) push_store(o + stride, a1x, a1y);
+    } else {
+        uint64_t* o = out + (size_t)b * M * stride + w0;
+        st_stream_u64x2(o, u64x2{a0x, a0y});
+        if (M == 2) st_stream_u64x2(o + stride, u64x2{a1x, a1y});
+    }
 }
 
-cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_t stride, const int64_t* d_W, int M,
-                           bool second_is_sum, int64_t bias0, int64_t bias1, int shift, uint64_t* d_out,
-                           cudaStream_t s) {
+template <int M, bool SECOND_IS_SUM, int UNROLL, bool PUSH>
+__global__ void __launch_bounds__(LC_THREADS)
+lincomb_kernel(const uint64_t* __restrict__ ct, int d, int n_words, int64_t stride, int64_t total_vecs,
+               const int64_t* __restrict__ W, uint64_t bias0, uint64_t bias1, uint64_t* __restrict__ out,
+               const PushArgs push) {
+    extern __shared__ int64_t sW[];  // [M][d]
+    for (int i = threadIdx.x; i < M * d; i += blockDim.x) sW[i] = W[i];
+    __syncthreads();
+    const int64_t g = (int64_t)blockIdx.x * LC_THREADS + threadIdx.x;
+    if (g < total_vecs)
+        lincomb_thread<M, SECOND_IS_SUM, UNROLL, PUSH>(ct, d, n_words, stride, g, sW, bias0, bias1, out, push);
+    if (PUSH) push_arrive(push);  // one call site: every thread of the CTA reaches the same barrier
+}
+
+template <bool PUSH>
+static cudaError_t launch_lincomb_impl(const uint64_t* d_ct, int64_t B, int d, int n, int64_t stride, const int64_t* d_W,
+                                       int M, bool second_is_sum, int64_t bias0, int64_t bias1, int shift,
+                                       uint64_t* d_out, const PushArgs& push, cudaStream_t s) {
     if (B <= 0) return cudaSuccess;
     const int64_t total_vecs = B * (stride / 2);
     const int64_t grid64 = (total_vecs + LC_THREADS - 1) / LC_THREADS;
@@ -215,13 +291,36 @@ cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_
     const uint64_t b0 = (uint64_t)bias0 << shift, b1 = (uint64_t)bias1 << shift;
     constexpr int U = LC_UNROLL;
     if (M == 1)
-        lincomb_kernel<1, false, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out);
+        lincomb_kernel<1, false, U, PUSH><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out, push);
     else if (second_is_sum)
-        lincomb_kernel<2, true, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out);
+        lincomb_kernel<2, true, U, PUSH><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out, push);
     else
-        lincomb_kernel<2, false, U><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out);
+        lincomb_kernel<2, false, U, PUSH><<<grid, LC_THREADS, smem, s>>>(d_ct, d, n + 1, stride, total_vecs, d_W, b0, b1, d_out, push);
     count_launch();
     return cudaGetLastError();
+}
+
+cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_t stride, const int64_t* d_W, int M,
+                           bool second_is_sum, int64_t bias0, int64_t bias1, int shift, uint64_t* d_out,
+                           cudaStream_t s) {
+    return launch_lincomb_impl<false>(d_ct, B, d, n, stride, d_W, M, second_is_sum, bias0, bias1, shift, d_out,
+                                      PushArgs{}, s);
+}
+
+static PushArgs make_push(const fhe_b200_push& p) {
+    PushArgs a;
+    a.board = p.d_board32;
+    a.arrive = p.d_arrive;
+    a.step = p.step;
+    a.counter = p.d_counter;
+    return a;
+}
+
+cudaError_t launch_lincomb_push(const uint64_t* d_ct, int64_t B, int d, int n, int64_t stride, const int64_t* d_W, int M,
+                                bool second_is_sum, int64_t bias0, int64_t bias1, int shift, const fhe_b200_push& push,
+                                cudaStream_t s) {
+    return launch_lincomb_impl<true>(d_ct, B, d, n, stride, d_W, M, second_is_sum, bias0, bias1, shift, nullptr,
+                                     make_push(push), s);
 }
 
 // ----------------------------------------------------------------------------- seeded ciphertexts
@@ -319,49 +418,59 @@ cudaError_t launch_lwe_expand_seeded(const uint64_t* d_bodies, int64_t count, in
 
 // server: out[b][m][:] = sum_j W[m][j] * expand(seed, ct_base + b*d + j)[:], masks regenerated on the fly.
 // Same thread -> (document, column pair) mapping as lincomb_kernel; no global loads except the d bodies.
-template <int M, bool SECOND_IS_SUM>
+template <int M, bool SECOND_IS_SUM, bool PUSH>
 __global__ void __launch_bounds__(LC_THREADS)
 lincomb_seeded_kernel(const uint64_t* __restrict__ bodies, int d, int n, int64_t stride, int64_t total_vecs,
                       uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, const int64_t* __restrict__ W,
-                      uint64_t bias0, uint64_t bias1, uint64_t* __restrict__ out) {
+                      uint64_t bias0, uint64_t bias1, uint64_t* __restrict__ out, const PushArgs push) {
     extern __shared__ int64_t sW[];
     for (int i = threadIdx.x; i < M * d; i += blockDim.x) sW[i] = W[i];
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * LC_THREADS + threadIdx.x;
-    if (g >= total_vecs) return;
-    const int vecs = (int)(stride >> 1);
-    const int64_t b = g / vecs;
-    const int w0 = 2 * (int)(g - b * vecs);
-    const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
-    const uint64_t id0 = ct_base + (uint64_t)b * d;
-    const bool has_body = (w0 == n) || (w0 + 1 == n);
-    const PhiloxKeys K(enc_seed);
-    uint64_t a0x = 0, a0y = 0, a1x = 0, a1y = 0;
-    if (w0 <= n) {
+    if (g < total_vecs) {
+        const int vecs = (int)(stride >> 1);
+        const int64_t b = g / vecs;
+        const int w0 = 2 * (int)(g - b * vecs);
+        const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
+        const uint64_t id0 = ct_base + (uint64_t)b * d;
+        const bool has_body = (w0 == n) || (w0 + 1 == n);
+        const PhiloxKeys K(enc_seed);
+        uint64_t a0x = 0, a0y = 0, a1x = 0, a1y = 0;
+        if (w0 <= n) {
 #pragma unroll 4
-        for (int j = 0; j < d; ++j) {
-            uint64_t x, y;
-            seeded_pair(K, dom, id0 + j, w0, n, has_body ? bodies[b * d + j] : 0, x, y);
-            const uint64_t w = (uint64_t)sW[j];
-            a0x += w * x;
-            a0y += w * y;
-            if (M == 2) {
-                const uint64_t w1 = SECOND_IS_SUM ? 1ULL : (uint64_t)sW[d + j];
-                a1x += w1 * x;
-                a1y += w1 * y;
+            for (int j = 0; j < d; ++j) {
+                uint64_t x, y;
+                seeded_pair(K, dom, id0 + j, w0, n, has_body ? bodies[b * d + j] : 0, x, y);
+                const uint64_t w = (uint64_t)sW[j];
+                a0x += w * x;
+                a0y += w * y;
+                if (M == 2) {
+                    const uint64_t w1 = SECOND_IS_SUM ? 1ULL : (uint64_t)sW[d + j];
+                    a1x += w1 * x;
+                    a1y += w1 * y;
+                }
             }
         }
+        if (w0 == n) { a0x += bias0; a1x += bias1; }
+        if (w0 + 1 == n) { a0y += bias0; a1y += bias1; }
+        if (PUSH) {
+            uint32_t* o = push.board + (size_t)b * M * stride + w0;
+            push_store(o, a0x, a0y);
+            if (M == 2) push_store(o + stride, a1x, a1y);
+        } else {
+            uint64_t* o = out + (size_t)b * M * stride + w0;
+            st_stream_u64x2(o, u64x2{a0x, a0y});
+            if (M == 2) st_stream_u64x2(o + stride, u64x2{a1x, a1y});
+        }
     }
-    if (w0 == n) { a0x += bias0; a1x += bias1; }
-    if (w0 + 1 == n) { a0y += bias0; a1y += bias1; }
-    uint64_t* o = out + (size_t)b * M * stride + w0;
-    st_stream_u64x2(o, u64x2{a0x, a0y});
-    if (M == 2) st_stream_u64x2(o + stride, u64x2{a1x, a1y});
+    if (PUSH) push_arrive(push);
 }
 
-cudaError_t launch_lincomb_seeded(const uint64_t* d_bodies, int64_t B, int d, int n, int64_t stride, uint64_t enc_seed,
-                                  uint64_t ct_base, uint32_t purpose, const int64_t* d_W, int M, bool second_is_sum,
-                                  int64_t bias0, int64_t bias1, int shift, uint64_t* d_out, cudaStream_t s) {
+template <bool PUSH>
+static cudaError_t launch_lincomb_seeded_impl(const uint64_t* d_bodies, int64_t B, int d, int n, int64_t stride,
+                                              uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, const int64_t* d_W,
+                                              int M, bool second_is_sum, int64_t bias0, int64_t bias1, int shift,
+                                              uint64_t* d_out, const PushArgs& push, cudaStream_t s) {
     if (B <= 0) return cudaSuccess;
     const int64_t total_vecs = B * (stride / 2);
     const int64_t grid64 = (total_vecs + LC_THREADS - 1) / LC_THREADS;
@@ -370,11 +479,56 @@ cudaError_t launch_lincomb_seeded(const uint64_t* d_bodies, int64_t B, int d, in
     const size_t smem = (size_t)M * d * sizeof(int64_t);
     const uint64_t b0 = (uint64_t)bias0 << shift, b1 = (uint64_t)bias1 << shift;
     if (M == 1)
-        lincomb_seeded_kernel<1, false><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out);
+        lincomb_seeded_kernel<1, false, PUSH><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out, push);
     else if (second_is_sum)
-        lincomb_seeded_kernel<2, true><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out);
+        lincomb_seeded_kernel<2, true, PUSH><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out, push);
     else
-        lincomb_seeded_kernel<2, false><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out);
+        lincomb_seeded_kernel<2, false, PUSH><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out, push);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lincomb_seeded(const uint64_t* d_bodies, int64_t B, int d, int n, int64_t stride, uint64_t enc_seed,
+                                  uint64_t ct_base, uint32_t purpose, const int64_t* d_W, int M, bool second_is_sum,
+                                  int64_t bias0, int64_t bias1, int shift, uint64_t* d_out, cudaStream_t s) {
+    return launch_lincomb_seeded_impl<false>(d_bodies, B, d, n, stride, enc_seed, ct_base, purpose, d_W, M, second_is_sum,
+                                             bias0, bias1, shift, d_out, PushArgs{}, s);
+}
+
+cudaError_t launch_lincomb_seeded_push(const uint64_t* d_bodies, int64_t B, int d, int n, int64_t stride,
+                                       uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, const int64_t* d_W, int M,
+                                       bool second_is_sum, int64_t bias0, int64_t bias1, int shift,
+                                       const fhe_b200_push& push, cudaStream_t s) {
+    return launch_lincomb_seeded_impl<true>(d_bodies, B, d, n, stride, enc_seed, ct_base, purpose, d_W, M, second_is_sum,
+                                            bias0, bias1, shift, nullptr, make_push(push), s);
+}
+
+// ----------------------------------------------------------------------------- score board flags
+// client: the stream continues once every listed arrival flag has reached `value`
+__global__ void peer_wait_kernel(const uint64_t* __restrict__ flags, int count, uint64_t value, uint64_t timeout_ns,
+                                 uint32_t* __restrict__ status) {
+    for (int i = threadIdx.x; i < count; i += blockDim.x)
+        if (!spin_until_ge(flags + i, value, timeout_ns)) atomicExch(status, 1u);
+}
+// stream-ordered release store to (peer) flags: everything before it on the stream is visible first
+__global__ void peer_signal_kernel(uint64_t* const* __restrict__ ptrs, int count, uint64_t value) {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        __threadfence_system();
+        st_release_sys_u64(ptrs[i], value);
+    }
+}
+
+cudaError_t launch_peer_wait(const uint64_t* d_flags, int count, uint64_t value, uint32_t timeout_ms,
+                             uint32_t* d_status, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    peer_wait_kernel<<<1, 32, 0, s>>>(d_flags, count, value, (uint64_t)timeout_ms * 1000000ULL, d_status);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_signal(uint64_t* const* d_flag_ptrs, int count, uint64_t value, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    peer_signal_kernel<<<1, 32, 0, s>>>(d_flag_ptrs, count, value);
     count_launch();
     return cudaGetLastError();
 }

@@ -261,6 +261,50 @@ int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity *sim, const floa
 int fhe_b200_similarity_decrypt32(fhe_b200_similarity *sim, const uint32_t *d_out32, int64_t B,
                                   double *d_y, int64_t *d_q_y, void *stream);
 
+/* ---- multi-GPU search: scores pushed into the client GPU's memory ---------------------------------
+ * replaces the per-document result collection of BatchProcessor.search_similar
+ * (batch_operations.py:264-284) when the collection is sharded over the GPUs of one box: instead of
+ * writing its encrypted scores locally and handing them to a collective, the dot-product kernel of
+ * every rank stores them, in the 32-bit wire form, directly into the CLIENT rank's "score board" over
+ * NVLink (a cudaIpc peer mapping) and publishes an arrival flag; the client waits for the flags,
+ * decrypts the board and returns a credit per slot.  No host synchronisation, no collective call.
+ * Every in-stream wait is bounded (timeout_ms): a dead peer sets a status word, it never hangs the GPU.
+ *
+ * peer_alloc: zero-filled device allocation that other processes of the box may map; `handle` receives
+ * the 64-byte cudaIpcMemHandle to pass to them (any byte transport).  peer_open maps another process's
+ * allocation (peer access is enabled on demand); peer_close unmaps; peer_free releases an allocation. */
+#define FHE_B200_IPC_HANDLE_BYTES 64
+int fhe_b200_peer_alloc(fhe_b200_ctx *ctx, uint64_t bytes, void **d_ptr, uint8_t *handle);
+int fhe_b200_peer_open(fhe_b200_ctx *ctx, const uint8_t *handle, void **d_ptr);
+int fhe_b200_peer_close(fhe_b200_ctx *ctx, void *d_ptr);
+int fhe_b200_peer_free(fhe_b200_ctx *ctx, void *d_ptr);
+
+/* Destination of one pushed evaluation.  d_board32 / d_arrive point into the client's allocation
+ * (mapped with peer_open, or local on the client rank itself); d_counter is local to the caller.
+ * Flow control is the caller's: before a slot is overwritten, order the launch behind
+ * fhe_b200_peer_wait on the credit flag the client signals after decrypting the slot. */
+typedef struct {
+    uint32_t *d_board32; /* this rank's rows of the slot: [B][M][stride] u32 */
+    uint64_t *d_arrive;  /* arrival flag of (slot, rank): set to `step` when every row is written */
+    uint64_t step;       /* monotonic, > 0 */
+    uint32_t *d_counter; /* local u32, zero before the first call; the kernel leaves it zero */
+} fhe_b200_push;
+
+/* fhe_b200_similarity_run / _run_seeded with the result pushed to the client's score board */
+int fhe_b200_similarity_run_push(fhe_b200_similarity *sim, const uint64_t *d_ct, int64_t B,
+                                 const fhe_b200_push *push, void *stream);
+int fhe_b200_similarity_run_seeded_push(fhe_b200_similarity *sim, const uint64_t *d_bodies, int64_t B,
+                                        uint64_t enc_seed, uint64_t ct_base, const fhe_b200_push *push,
+                                        void *stream);
+/* client: block the stream until d_flags[i] >= value for every i < count (bounded by timeout_ms;
+ * on time-out *d_status is set to 1 and the stream continues) */
+int fhe_b200_peer_wait(fhe_b200_ctx *ctx, const uint64_t *d_flags, int32_t count, uint64_t value,
+                       uint32_t timeout_ms, uint32_t *d_status, void *stream);
+/* stream-ordered release store of `value` to each of the `count` flags whose (peer or local) addresses
+ * are listed in the DEVICE array d_flag_ptrs: the client's credits, or the arrival of an empty shard */
+int fhe_b200_peer_signal(fhe_b200_ctx *ctx, uint64_t *const *d_flag_ptrs, int32_t count, uint64_t value,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,3 +132,89 @@ def test_both_encrypted_mode_search_and_compare(processor):
     hits = small.filter_similar("quantum entanglement", 0.5)
     want = [i for i, _ in small.search_similar("quantum entanglement", top_k=10, min_similarity=0.5)]
     assert sorted(hits) == sorted(want) == ["s0", "s3", "s6"]
+
+
+def _board_model(seed=11, rows=300):
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=seed, verbose=False)
+    X, _ = m.train(n_samples=max(rows, 200))
+    m.compile(X[:10])
+    return m, X[:rows]
+
+
+def test_score_board_push_is_bit_exact(cuda_dev):
+    """Scores pushed by the dot-product kernel into the (here: local) score board equal the 32-bit wire form
+    of the plain path word for word, for expanded and seeded ciphertexts, across more steps than slots."""
+    import torch
+    from fhe_icp_b200.score_board import PeerScoreBoard
+    m, X = _board_model()
+    B = X.shape[0]
+    board = PeerScoreBoard(m, rows_max=B + 7)          # board rows need not equal the shard size
+    try:
+        for seeded in (False, True):
+            ct = m.encrypt(X, seeded=seeded)
+            want = m.compress_scores(m.run(ct))
+            for _ in range(5):
+                step = board.push(ct)
+                slot = board.collect()
+                assert slot.shape == (board.rows_max, board.M, board.stride)
+                assert torch.equal(slot[:B], want), f"step {step}: pushed words differ from modswitch32(run())"
+                assert np.array_equal(m.decrypt_compressed(slot[:B]), m.predict_clear(X))
+                board.release()
+        # an empty shard only flags its arrival
+        board.push(None)
+        board.collect()
+        board.release()
+        board.check()
+    finally:
+        board.close()
+
+
+def test_score_board_waits_are_bounded(cuda_dev):
+    """A credit that never comes (dead client) must not hang the GPU: the wait times out and check() raises."""
+    from fhe_icp_b200.score_board import PeerScoreBoard
+    m, X = _board_model(rows=64)
+    board = PeerScoreBoard(m, rows_max=64, timeout_ms=30)
+    try:
+        ct = m.encrypt(X, seeded=True)
+        for _ in range(3):          # the third step needs the credit of the first, which nobody released
+            board.push(ct)
+        with pytest.raises(RuntimeError, match="timed out"):
+            board.check()
+    finally:
+        board.close()
+
+
+def test_score_board_rejects_bad_arguments(cuda_dev):
+    import ctypes as C
+    from fhe_icp_b200 import _native as N
+    m, X = _board_model(rows=8)
+    c = m.keygen().model.fhe_circuit
+    ct = m.encrypt(X)
+    lib = N.lib()
+    push = N.Push(0, 0, 1, 0)
+    assert lib.fhe_b200_similarity_run_push(c.handle, C.c_void_p(ct.data_ptr()), 8, C.byref(push), None) == N.ERR_INVALID
+    assert b"null device pointer" in lib.fhe_b200_last_error()
+    push = N.Push(ct.data_ptr(), ct.data_ptr(), 0, ct.data_ptr())
+    assert lib.fhe_b200_similarity_run_push(c.handle, C.c_void_p(ct.data_ptr()), 8, C.byref(push), None) == N.ERR_INVALID
+    push = N.Push(ct.data_ptr(), ct.data_ptr(), 1, ct.data_ptr())
+    assert lib.fhe_b200_similarity_run_push(c.handle, C.c_void_p(ct.data_ptr()), 0, C.byref(push), None) == N.ERR_INVALID
+    assert lib.fhe_b200_peer_wait(N.context().handle, None, 1, 1, 10, None, None) == N.ERR_INVALID
+    with pytest.raises(ValueError):
+        from fhe_icp_b200.sharded_search import ShardedSearch
+        ShardedSearch(m, X, gather="carrier-pigeon")
+
+
+def test_sharded_search_push_mode_equals_nccl_mode(processor):
+    from fhe_icp_b200.sharded_search import ShardedSearch
+    bp = processor
+    docs = bp.storage.matrix()
+    ids = [d["doc_id"] for d in bp.storage.list_documents()]
+    q = bp.embedder.get_embedding("biology cells")
+    want = ShardedSearch(bp.fhe_model, docs, ids).search(q, top_k=4, min_similarity=0.5)
+    sp = ShardedSearch(bp.fhe_model, docs, ids, gather="push")
+    try:
+        for _ in range(4):
+            assert sp.search(q, top_k=4, min_similarity=0.5) == want
+    finally:
+        sp.close()

@@ -267,3 +267,25 @@ def test_sharded_packed_search_world2(n_docs):
     clear = eng.quantize(docs) @ eng.quantize(q)
     assert ret["ints"] == clear.tolist()
     assert ret["res"] == rank_results([f"doc_{i}" for i in range(n_docs)], eng.dequantize(clear), 4, -100.0)
+
+
+def test_score_board_layout_and_credits():
+    """Host logic of the peer score board (no GPU): slots alternate, a slot is reused only after the step
+    two back was consumed, and the (slot, rank) regions of the client allocation tile it without overlap."""
+    from fhe_icp_b200 import score_board as sb
+    assert [sb.slot_of(s) for s in (1, 2, 3, 4)] == [1, 0, 1, 0]
+    assert [sb.credit_needed(s) for s in (1, 2, 3, 4, 9)] == [0, 0, 1, 2, 7]
+    for s in range(3, 50):
+        assert sb.slot_of(sb.credit_needed(s)) == sb.slot_of(s)
+    world, rows, M, stride = 8, 1000, 2, 1424
+    spans, flags = [], set()
+    for slot in range(sb.SLOTS):
+        for r in range(world):
+            a, off = sb.board_offsets(world, rows, M, stride, slot, r)
+            assert a % 8 == 0 and a + 8 <= sb.HEADER_BYTES and off % 16 == 0
+            flags.add(a)
+            spans.append((off, off + 4 * rows * M * stride))
+    assert len(flags) == sb.SLOTS * world
+    spans.sort()
+    assert spans[0][0] == sb.HEADER_BYTES and spans[-1][1] == sb.board_bytes(world, rows, M, stride)
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))

@@ -31,6 +31,13 @@ ss = ShardedSearch(m, docs)                       # seeded ciphertexts + 32-bit 
 res = ss.search(q, top_k=5, min_similarity=0.5)
 res_plain = ShardedSearch(m, docs, seeded=False, wire32=False).search(q, top_k=5, min_similarity=0.5)
 assert res == res_plain
+# fused gather: scores pushed by the dot-product kernels into the client's score board (no collective)
+for seeded in (True, False):
+    sp = ShardedSearch(m, docs, seeded=seeded, gather="push")
+    for rep in range(5):                            # > 2 steps: exercises the slot credits
+        res_push = sp.search(q, top_k=5, min_similarity=0.5)
+        assert res_push == res, (rank, seeded, rep, res_push, res)
+    sp.close()
 if rank == 0:
     ref = rank_results(ss.doc_ids, m.predict_clear(q[None, :] * docs), 5, 0.5)
     assert res == ref, (res, ref)
