@@ -64,19 +64,23 @@ class Push(C.Structure):
 IPC_HANDLE_BYTES = 64
 
 
-def _stale() -> bool:
-    if not _SO.exists():
+_OBJ_DIR = _PKG / "build"
+
+
+def _newer_than(target: Path, deps) -> bool:
+    if not target.exists():
         return True
-    t = _SO.stat().st_mtime
-    for f in _SOURCES + _HEADERS:
-        p = (_CSRC / f)
-        if p.exists() and p.stat().st_mtime > t:
-            return True
-    return False
+    t = target.stat().st_mtime
+    return any(p.exists() and p.stat().st_mtime > t for p in deps)
+
+
+def _stale() -> bool:
+    return _newer_than(_SO, [_CSRC / f for f in _SOURCES + _HEADERS])
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a into ``libfhe_b200.so`` (in-tree)."""
+    """Compile every CUDA source for sm_100a into ``libfhe_b200.so`` (in-tree).  One object per source
+    (compiled in parallel, rebuilt only when the source or a header is newer), then one link."""
     if not force and not _stale():
         return _SO
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -84,14 +88,34 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if _SO.exists():
             return _SO  # GPU box without a toolchain: use the prebuilt library
         raise RuntimeError("nvcc not found and libfhe_b200.so is not built")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(_SO)] + [str(_CSRC / s) for s in _SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    _OBJ_DIR.mkdir(exist_ok=True)
+    headers = [_CSRC / h for h in _HEADERS]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    procs = []
+    for src in _SOURCES:
+        obj = _OBJ_DIR / (Path(src).stem + ".o")
+        if not force and not _newer_than(obj, [_CSRC / src] + headers):
+            continue
+        cmd = [nvcc, *compile_flags, "-c", "-o", str(obj), str(_CSRC / src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        log.append(out)
+        if pr.returncode != 0:
+            for _, other in procs:
+                if other.poll() is None:
+                    other.kill()
+            raise RuntimeError(f"nvcc failed on {src}:\n" + out)
+    objs = [str(_OBJ_DIR / (Path(s).stem + ".o")) for s in _SOURCES]
+    r = subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-o", str(_SO)] + objs, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     if verbose:
-        print(r.stderr)
+        print("".join(log))
     return _SO
 
 

@@ -91,12 +91,13 @@ struct fhe_b200_similarity {
     int M;
     bool second_is_sum;
     uint8_t* d_key = nullptr;
+    uint32_t* d_key_bits = nullptr;  // the same key, 32 bits per word (fused decrypt kernel)
     int64_t* d_W = nullptr;  // [M][d]
     cudaStream_t stream = nullptr;
     cudaStream_t enc_stream = nullptr;       // second stream: encryption of the next chunk
     cudaEvent_t ev_enc[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_q = nullptr;
     // grow-only workspaces for the host-buffer entry point
-    DevBuf X, q, ct, out, m, y, qy;
+    DevBuf X, q, ct, out, y, qy;
     PinBuf hX, hy, hqy;
 };
 
@@ -592,6 +593,8 @@ int fhe_b200_similarity_create(fhe_b200_ctx* ctx, const fhe_b200_similarity_spec
         if (e != cudaSuccess) goto bad;
     }
     if ((e = fhe::launch_secret_key(spec->key_seed, 2, spec->n, s->d_key, s->stream)) != cudaSuccess) goto bad;
+    if ((e = cudaMalloc(&s->d_key_bits, sizeof(uint32_t) * ((size_t)spec->n / 32 + 1))) != cudaSuccess) goto bad;
+    if ((e = fhe::launch_pack_key(s->d_key, spec->n, s->d_key_bits, s->stream)) != cudaSuccess) goto bad;
     if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) goto bad;
     *sim = s;
     return FHE_B200_OK;
@@ -605,8 +608,9 @@ int fhe_b200_similarity_destroy(fhe_b200_similarity* s) {
     cudaSetDevice(s->ctx->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->d_key) cudaFree(s->d_key);
+    if (s->d_key_bits) cudaFree(s->d_key_bits);
     if (s->d_W) cudaFree(s->d_W);
-    s->X.release(); s->q.release(); s->ct.release(); s->out.release(); s->m.release(); s->y.release(); s->qy.release();
+    s->X.release(); s->q.release(); s->ct.release(); s->out.release(); s->y.release(); s->qy.release();
     s->hX.release(); s->hy.release(); s->hqy.release();
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->enc_stream) cudaStreamDestroy(s->enc_stream);
@@ -658,10 +662,8 @@ int fhe_b200_similarity_decrypt(fhe_b200_similarity* s, const uint64_t* d_out, i
     const auto& sp = s->spec;
     CU(cudaSetDevice(s->ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CU(s->m.reserve(sizeof(int64_t) * (size_t)B * s->M));
-    CU(fhe::launch_lwe_phase(s->d_key, sp.n, sp.stride, d_out, B * s->M, sp.shift, true, (uint64_t*)s->m.p, st));
-    CU(fhe::launch_similarity_finalize((const int64_t*)s->m.p, B, s->M, sp.w_zero_point, sp.q_bias, sp.out_scale,
-                                       sp.out_zero_point, d_y, d_q_y, st));
+    CU(fhe::launch_similarity_decrypt(s->d_key_bits, sp.n, sp.stride, d_out, false, B, s->M, sp.shift, sp.w_zero_point,
+                                      sp.q_bias, sp.out_scale, sp.out_zero_point, d_y, d_q_y, st));
     return FHE_B200_OK;
 }
 
@@ -737,10 +739,8 @@ int fhe_b200_similarity_decrypt32(fhe_b200_similarity* s, const uint32_t* d_out3
     REQUIRE(sp.shift >= 32, "the 32-bit wire form needs log2(Delta) >= 32");
     CU(cudaSetDevice(s->ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CU(s->m.reserve(sizeof(int64_t) * (size_t)B * s->M));
-    CU(fhe::launch_lwe_decrypt32(s->d_key, sp.n, sp.stride, d_out32, B * s->M, sp.shift - 32, (int64_t*)s->m.p, st));
-    CU(fhe::launch_similarity_finalize((const int64_t*)s->m.p, B, s->M, sp.w_zero_point, sp.q_bias, sp.out_scale,
-                                       sp.out_zero_point, d_y, d_q_y, st));
+    CU(fhe::launch_similarity_decrypt(s->d_key_bits, sp.n, sp.stride, d_out32, true, B, s->M, sp.shift - 32,
+                                      sp.w_zero_point, sp.q_bias, sp.out_scale, sp.out_zero_point, d_y, d_q_y, st));
     return FHE_B200_OK;
 }
 
@@ -883,7 +883,6 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
     CU(s->ct.reserve(2 * row_bytes * (size_t)chunk));
     CU(s->out.reserve(sizeof(uint64_t) * (size_t)chunk * s->M * sp.stride));
     CU(s->q.reserve(sizeof(int64_t) * (size_t)cnt));
-    CU(s->m.reserve(sizeof(int64_t) * (size_t)chunk * s->M));
     CU(s->y.reserve(sizeof(double) * (size_t)B));
     CU(s->qy.reserve(sizeof(int64_t) * (size_t)B));
     CU(s->hy.reserve(sizeof(double) * (size_t)B));
@@ -907,10 +906,9 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
         CU(fhe::launch_lincomb(ctb, rows, sp.d, sp.n, sp.stride, s->d_W, s->M, s->second_is_sum, 0, 0, sp.shift,
                                (uint64_t*)s->out.p, st));
         CU(cudaEventRecord(s->ev_free[k & 1], st));
-        CU(fhe::launch_lwe_phase(s->d_key, sp.n, sp.stride, (const uint64_t*)s->out.p, rows * s->M, sp.shift, true,
-                                 (uint64_t*)s->m.p, st));
-        CU(fhe::launch_similarity_finalize((const int64_t*)s->m.p, rows, s->M, sp.w_zero_point, sp.q_bias, sp.out_scale,
-                                           sp.out_zero_point, (double*)s->y.p + r0, (int64_t*)s->qy.p + r0, st));
+        CU(fhe::launch_similarity_decrypt(s->d_key_bits, sp.n, sp.stride, s->out.p, false, rows, s->M, sp.shift,
+                                          sp.w_zero_point, sp.q_bias, sp.out_scale, sp.out_zero_point,
+                                          (double*)s->y.p + r0, (int64_t*)s->qy.p + r0, st));
     }
     CU(cudaMemcpyAsync(s->hy.p, s->y.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(s->hqy.p, s->qy.p, sizeof(int64_t) * (size_t)B, cudaMemcpyDeviceToHost, st));

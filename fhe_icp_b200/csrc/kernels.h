@@ -64,9 +64,10 @@ cudaError_t launch_lwe_pair_diff_sum(const uint64_t* d_in, int64_t B, int d, int
                                      uint64_t* d_out, cudaStream_t s);
 cudaError_t launch_quantize(const float* d_X, int64_t count, double scale, int64_t zp, int64_t qmin, int64_t qmax,
                             int64_t* d_q, cudaStream_t s);
-cudaError_t launch_similarity_finalize(const int64_t* d_m, int64_t B, int M, int64_t zp_w, int64_t q_bias,
-                                       double out_scale, int64_t out_zp, double* d_y, int64_t* d_q_y,
-                                       cudaStream_t s);
+cudaError_t launch_pack_key(const uint8_t* d_key, int n, uint32_t* d_bits, cudaStream_t s);
+cudaError_t launch_similarity_decrypt(const uint32_t* d_kbits, int n, int64_t stride, const void* d_cts, bool wire32,
+                                      int64_t B, int M, int shift, int64_t zp_w, int64_t q_bias, double out_scale,
+                                      int64_t out_zp, double* d_y, int64_t* d_q_y, cudaStream_t s);
 
 // keys.cu
 cudaError_t launch_ksk_gen(const fhe_b200_pbs_params& p, const uint8_t* d_S_big, const uint8_t* d_s_small,

@@ -261,3 +261,53 @@ def test_invalid_arguments_on_device(cuda_dev):
     p = E.make_pbs_params(n=16, N_poly=1024)
     with pytest.raises(N.FheB200Error, match="N must be 2048"):
         E.ksk_gen(p, key, key, 1)
+
+
+@pytest.mark.parametrize("n,stride,two", [(1, 2, 1), (5, 6, 1), (30, 32, 0), (33, 34, 1), (64, 66, 1), (127, 128, 0),
+                                          (743, 744, 1), (742, 746, 1), (1423, 1424, 1)])
+def test_fused_similarity_decrypt_all_row_shapes(cuda_dev, n, stride, two):
+    """The fused client kernel (decrypt + decode + dequantize, one CTA per document) on row shapes that hit
+    every vector width / tail case, in the native 64-bit and the 32-bit wire form: the integers equal
+    m0 - zp_w*m1 + q_bias computed in numpy and the floats equal out_scale*(q - zp_out) exactly."""
+    import ctypes as C
+    import torch
+    from fhe_icp_b200 import _native as N
+    from fhe_icp_b200 import engine as E
+    M = 2 if two else 1
+    shift, key_seed = 44, 77 + n
+    zp_w, q_bias, out_scale, out_zp = -31337, 12345, 3.25e-7, -99
+    spec = N.SimilaritySpec(d=3, n_bits=8, n=n, stride=stride, shift=shift, two_outputs=two, sigma_abs=2.0 ** 20,
+                            x_scale=1.0, x_zero_point=0, x_offset=128, w_zero_point=zp_w if two else 0, q_bias=q_bias,
+                            out_scale=out_scale, out_zero_point=out_zp, key_seed=key_seed)
+    ctx = N.context(cuda_dev.index)
+    h = C.c_void_p()
+    qw = (C.c_int64 * 3)(1, 2, 3)
+    N.check(N.lib().fhe_b200_similarity_create(ctx.handle, C.byref(spec), qw, C.byref(h)))
+    try:
+        B = 37
+        rng = np.random.RandomState(n)
+        msgs = rng.randint(-2 ** 17, 2 ** 17, size=(B, M)).astype(np.int64)
+        key = E.secret_key(key_seed, 2, n, cuda_dev)           # the model's client key (key id 2)
+        ct = E.lwe_encrypt(key, torch.as_tensor(msgs), shift, 2.0 ** 20, 5, stride=stride)
+        q_want = msgs[:, 0] - (zp_w * msgs[:, 1] if two else 0) + q_bias
+        y_want = out_scale * (q_want - out_zp).astype(np.float64)
+        y = torch.empty(B, dtype=torch.float64, device=cuda_dev)
+        qy = torch.empty(B, dtype=torch.int64, device=cuda_dev)
+        N.check(N.lib().fhe_b200_similarity_decrypt(h, C.c_void_p(ct.data_ptr()), B, C.c_void_p(y.data_ptr()),
+                                                    C.c_void_p(qy.data_ptr()), None))
+        assert np.array_equal(qy.cpu().numpy(), q_want) and np.array_equal(y.cpu().numpy(), y_want)
+        ct32 = torch.empty(ct.shape, dtype=torch.int32, device=cuda_dev)
+        N.check(N.lib().fhe_b200_lwe_modswitch32(ctx.handle, C.c_void_p(ct.data_ptr()), B * M, stride,
+                                                 C.c_void_p(ct32.data_ptr()), None))
+        y.zero_(); qy.zero_()
+        N.check(N.lib().fhe_b200_similarity_decrypt32(h, C.c_void_p(ct32.data_ptr()), B, None, C.c_void_p(qy.data_ptr()), None))
+        assert np.array_equal(qy.cpu().numpy(), q_want)
+        # a view that starts 8 bytes into a 16-byte line exercises the unaligned wire-form path
+        if stride % 4 == 2:
+            sub = ct32[1:]
+            N.check(N.lib().fhe_b200_similarity_decrypt32(h, C.c_void_p(sub.data_ptr()), B - 1, C.c_void_p(y.data_ptr()),
+                                                          C.c_void_p(qy.data_ptr()), None))
+            assert np.array_equal(qy.cpu().numpy()[:B - 1], q_want[1:])
+            assert np.array_equal(y.cpu().numpy()[:B - 1], y_want[1:])
+    finally:
+        N.lib().fhe_b200_similarity_destroy(h)
