@@ -549,6 +549,39 @@ int fhe_b200_keyswitch32(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const 
     return FHE_B200_OK;
 }
 
+// ---- tensor-core keyswitch (ks_mma.cu)
+uint64_t fhe_b200_ksk_mma_bytes(const fhe_b200_pbs_params* p) {
+    return (p && fhe::keyswitch_mma_supported(*p)) ? (uint64_t)fhe::keyswitch_mma_key_bytes(*p) : 0;
+}
+uint64_t fhe_b200_keyswitch_mma_workspace_bytes(const fhe_b200_pbs_params* p, int64_t B) {
+    return (p && B > 0 && fhe::keyswitch_mma_supported(*p)) ? (uint64_t)fhe::keyswitch_mma_workspace_bytes(*p, B) : 0;
+}
+
+int fhe_b200_ksk_to_mma(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint32_t* d_ksk32, uint8_t* d_key_mma,
+                        void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(d_ksk32 && d_key_mma, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    REQUIRE(fhe::keyswitch_mma_supported(*p), "parameters outside the tensor-core keyswitch (kN % 128, beta_ks <= 8, s32 range)");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_ksk32_to_mma(*p, d_ksk32, d_key_mma, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_keyswitch_mma(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint8_t* d_key_mma, const uint64_t* d_in,
+                           int64_t B, int8_t* d_work, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_key_mma && d_in && d_work && d_out, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    REQUIRE(fhe::keyswitch_mma_supported(*p), "parameters outside the tensor-core keyswitch (kN % 128, beta_ks <= 8, s32 range)");
+    REQUIRE(ctx->prop.major == 10, "tcgen05 needs an sm_100 device");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_keyswitch_mma(*p, d_key_mma, d_in, B, d_work, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 int fhe_b200_pbs(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_bskf, const uint64_t* d_in,
                  int64_t B, const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, void* stream) {
     REQUIRE(ctx, "null ctx");

@@ -86,6 +86,14 @@ cudaError_t launch_ksk_to_32(const fhe_b200_pbs_params& p, const uint64_t* d_ksk
 cudaError_t launch_keyswitch32(const fhe_b200_pbs_params& p, const uint32_t* d_ksk32, const uint64_t* d_in, int64_t B,
                                uint32_t* d_acc32, uint64_t* d_out, cudaStream_t s);
 
+// ks_mma.cu -- the 32-bit keyswitch as an int8 tensor-core contraction (tcgen05.mma.kind::i8)
+bool keyswitch_mma_supported(const fhe_b200_pbs_params& p);
+size_t keyswitch_mma_key_bytes(const fhe_b200_pbs_params& p);
+size_t keyswitch_mma_workspace_bytes(const fhe_b200_pbs_params& p, int64_t B);
+cudaError_t launch_ksk32_to_mma(const fhe_b200_pbs_params& p, const uint32_t* d_ksk32, uint8_t* d_tiles, cudaStream_t s);
+cudaError_t launch_keyswitch_mma(const fhe_b200_pbs_params& p, const uint8_t* d_tiles, const uint64_t* d_in, int64_t B,
+                                 int8_t* d_work, uint64_t* d_out, cudaStream_t s);
+
 // pbs.cu
 cudaError_t launch_bsk_to_fourier(const fhe_b200_pbs_params& p, const uint64_t* d_bsk, double* d_bskf,
                                   cudaStream_t s);

@@ -283,6 +283,33 @@ def keyswitch32(p: N.PBSParams, ksk32: torch.Tensor, ct: torch.Tensor) -> torch.
     return out
 
 
+def ksk_to_mma(p: N.PBSParams, ksk32: torch.Tensor) -> torch.Tensor:
+    """Lay the 32-bit keyswitching key out as the byte blocks the tensor-core keyswitch reads (once per key)."""
+    nbytes = int(N.lib().fhe_b200_ksk_mma_bytes(C.byref(p)))
+    if nbytes == 0:
+        raise ValueError("parameter set outside the tensor-core keyswitch")
+    tiles = torch.empty(nbytes, dtype=torch.uint8, device=ksk32.device)
+    N.check(N.lib().fhe_b200_ksk_to_mma(_ctx(ksk32.device).handle, C.byref(p), _ptr(ksk32), _ptr(tiles), _stream(ksk32.device)))
+    return tiles
+
+
+def keyswitch_mma(p: N.PBSParams, key_mma: torch.Tensor, ct: torch.Tensor, work: torch.Tensor | None = None) -> torch.Tensor:
+    """32-bit keyswitch on the tensor cores (tcgen05 int8 contraction); bit-identical to :func:`keyswitch32`."""
+    dev = ct.device
+    ct = ct.contiguous()
+    B = ct.shape[0]
+    assert ct.shape[1] == p.k * p.N + 1
+    out = torch.empty((B, p.n + 1), dtype=torch.int64, device=dev)
+    if B == 0:
+        return out
+    need = int(N.lib().fhe_b200_keyswitch_mma_workspace_bytes(C.byref(p), B))
+    if work is None or work.numel() < need:
+        work = torch.empty(need, dtype=torch.int8, device=dev)
+    N.check(N.lib().fhe_b200_keyswitch_mma(_ctx(dev).handle, C.byref(p), _ptr(key_mma), _ptr(ct), B, _ptr(work), _ptr(out),
+                                           _stream(dev)))
+    return out
+
+
 def pbs(p: N.PBSParams, bskf: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor,
         lut_index: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     dev = ct.device

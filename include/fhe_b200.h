@@ -229,6 +229,17 @@ int fhe_b200_ksk_to_32(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const ui
 int fhe_b200_keyswitch32(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint32_t *d_ksk32,
                          const uint64_t *d_in, int64_t B, uint32_t *d_scratch32, uint64_t *d_out,
                          void *stream);
+/* The same 32-bit keyswitch as a dense int8 contraction on the tensor cores (tcgen05.mma.kind::i8, s8 digits x
+ * u8 key bytes -> s32 in tensor memory; ks_mma.cu).  Bit-identical to fhe_b200_keyswitch32.  ksk_to_mma lays
+ * the 32-bit key out in MMA blocks (ksk_mma_bytes bytes, once per key); keyswitch_mma needs a per-call
+ * workspace of keyswitch_mma_workspace_bytes(B) for the digit matrix.  Both sizes are 0 for parameter sets the
+ * kernel does not cover (kN % 128 != 0, beta_ks > 8, or l_ks*kN*1020 >= 2^31). */
+uint64_t fhe_b200_ksk_mma_bytes(const fhe_b200_pbs_params *p);
+uint64_t fhe_b200_keyswitch_mma_workspace_bytes(const fhe_b200_pbs_params *p, int64_t B);
+int fhe_b200_ksk_to_mma(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint32_t *d_ksk32,
+                        uint8_t *d_key_mma, void *stream);
+int fhe_b200_keyswitch_mma(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_key_mma,
+                           const uint64_t *d_in, int64_t B, int8_t *d_work, uint64_t *d_out, void *stream);
 int fhe_b200_pbs(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf,
                  const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
                  const int32_t *d_lut_index, uint64_t *d_out, void *stream);

@@ -254,3 +254,29 @@ def test_multibit_pbs(O, cuda_dev, which, B):
     assert np.log2(np.abs(diff).max() + 1) - 64 < (-19 if two else -12)
     err = (O.lwe_phase(K.oS, got) - (table[msgs].astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
     assert np.log2(err.std() + 1) - 64 < (-20.5 if two else -13.5)
+
+
+@pytest.mark.parametrize("which,B", [("toy", 5), ("toy", 130), ("p4", 1), ("p4", 40), ("p4", 300)])
+def test_keyswitch_tensor_core_bit_exact(O, request, cuda_dev, which, B):
+    """The keyswitch as an int8 contraction on the tensor cores (tcgen05.mma.kind::i8: signed digits x unsigned
+    key bytes -> s32 in tensor memory, byte planes recombined in the epilogue) equals the integer-pipe KS32
+    kernel -- and therefore the oracle -- word for word, including ragged row tiles and the padded last
+    column tile; random torus inputs also cover every digit value."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    K = request.getfixturevalue(which)
+    kN = K.p.k * K.p.N
+    msgs = np.random.RandomState(B).randint(0, 16, size=B)
+    ct = E.lwe_encrypt(K.S, torch.as_tensor(msgs), 59, K.op.sigma_glwe_abs, enc_seed=6, ct_base=9,
+                       stride=kN + 2)[:, : kN + 1].contiguous()
+    ksk32 = E.ksk_to_32(K.p, K.ksk)
+    key_mma = E.ksk_to_mma(K.p, ksk32)
+    out = E.keyswitch_mma(K.p, key_mma, ct)
+    want = E.keyswitch32(K.p, ksk32, ct)
+    assert np.array_equal(_u64(out), _u64(want))
+    if B <= 40:
+        assert np.array_equal(_u64(out), O.keyswitch32(K.op, O.ksk_to_32(K.op, _u64(K.ksk)), _u64(ct)))
+    assert np.array_equal(O.lwe_decrypt(K.os, _u64(out), 59), msgs)
+    rnd = torch.as_tensor(np.random.RandomState(B + 1).randint(-2 ** 63, 2 ** 63 - 1, size=(B, kN + 1), dtype=np.int64)).to(cuda_dev)
+    assert np.array_equal(_u64(E.keyswitch_mma(K.p, key_mma, rnd)), _u64(E.keyswitch32(K.p, ksk32, rnd)))
+    assert E.keyswitch_mma(K.p, key_mma, rnd[:0]).shape == (0, K.p.n + 1)
