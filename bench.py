@@ -454,6 +454,10 @@ def run_b200_arm(args):
             raise ImportError
         from fhe_icp_b200 import pbs_bench
         args._hbm_peak = peak
+        try:   # dense bf16 burst rate measured on this pool (denominator of the tensor-core keyswitch roofline)
+            args._bf16_peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["bf16_tflops"])
+        except Exception:
+            args._bf16_peak = None
         line["pbs"] = pbs_bench.measure(dev, args)
         if world == 1:
             pair = pbs_bench.measure_pair(dev, args)

@@ -26,6 +26,8 @@ exactly; see DESIGN.md for the noise budget that makes this hold (l_pbs = 2).
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -207,7 +209,9 @@ class EncryptedThreshold:
             raise ValueError("the score must fill the torus: score_bits + out_shift == 64")
         p = ec.p
         ec._need_keys()
-        self.ksk32 = E.ksk_to_32(p, E.ksk_gen(p, ec.S, ec.s, ec.evk_seed))
+        # keyswitching key laid out for the tensor-core contraction (ks_mma.cu); bit-identical to KS32
+        self.key_mma = E.ksk_to_mma(p, E.ksk_to_32(p, E.ksk_gen(p, ec.S, ec.s, ec.evk_seed)))
+        self._ks_work = None
         mask = (1 << 64) - 1
         consts = [(-(1 << (self.out_shift - 1 + i))) & mask for i in range(self.score_bits - 1)] + [1 << (BIT_SHIFT - 1)]
         self.luts = E.from_u64_numpy(np.repeat(np.array(consts, dtype=np.uint64)[:, None], p.N, axis=1), ec.dev)
@@ -227,10 +231,16 @@ class EncryptedThreshold:
         for i in range(self.score_bits):
             last = i == self.score_bits - 1
             tmp = E.shl_add(acc, words, self.score_bits - 1 - i, 1 << 62)                  # bit i on top, + 1/4
-            pb = fn(p, ec.bskf, E.keyswitch32(p, self.ksk32, tmp), self.luts[i])
+            pb = fn(p, ec.bskf, self._keyswitch(tmp), self.luts[i])
             if last:   # -/+ 2^59 for sign bit 0/1 -> (1 - sign) * 2^60
                 return E.shl_add(pb, words, 0, 1 << (BIT_SHIFT - 1), out_stride=E.even_stride(words - 1))
             E.sub_plain(acc, pb, 1 << (self.out_shift - 1 + i))                            # clear bit i
+
+    def _keyswitch(self, ct: torch.Tensor) -> torch.Tensor:
+        need = int(N.lib().fhe_b200_keyswitch_mma_workspace_bytes(C.byref(self.ec.p), ct.shape[0]))
+        if self._ks_work is None or self._ks_work.numel() < need:
+            self._ks_work = torch.empty(need, dtype=torch.int8, device=ct.device)
+        return E.keyswitch_mma(self.ec.p, self.key_mma, ct, work=self._ks_work)
 
     def buckets(self, scores: torch.Tensor, thresholds) -> torch.Tensor:
         """Number of thresholds each score reaches (e.g. 0.5 / 0.7 / 0.9 -> 0..3), one ciphertext per score."""

@@ -15,6 +15,7 @@ def flops_per_pbs(n, k, N, l):
 
 
 def measure(dev, args, batches=None):
+    import ctypes as C
     import torch
     from . import _native as N_
     from . import engine as E
@@ -28,6 +29,7 @@ def measure(dev, args, batches=None):
     bskf2 = E.bsk2_to_fourier(p, bsk2)
     del bsk2
     ksk32 = E.ksk_to_32(p, ksk)
+    key_mma = E.ksk_to_mma(p, ksk32)    # the same key as int8 MMA blocks (tensor-core keyswitch)
     table = (np.arange(16) * 7 + 3) % 16
     lut = E.from_u64_numpy(E.make_lut_poly(table, 4, p.N, 59), dev)
     ctx = N_.context(dev.index)
@@ -75,7 +77,10 @@ def measure(dev, args, batches=None):
             torch.cuda.synchronize()
             return k0.elapsed_time(k1) / reps
         ks64_ms = time_ks(lambda: E.keyswitch(p, ksk, ct_big))
-        ks_ms = time_ks(lambda: E.keyswitch32(p, ksk32, ct_big))   # the 32-bit keyswitch is the one used
+        ks32_ms = time_ks(lambda: E.keyswitch32(p, ksk32, ct_big))   # 32-bit keyswitch on the integer pipe
+        ks_work = torch.empty(int(N_.lib().fhe_b200_keyswitch_mma_workspace_bytes(C.byref(p), B)), dtype=torch.int8, device=dev)
+        ks_ms = time_ks(lambda: E.keyswitch_mma(p, key_mma, ct_big, work=ks_work))   # the same on the tensor cores: the one used
+        ks_same = bool(torch.equal(E.keyswitch_mma(p, key_mma, ct_big, work=ks_work), E.keyswitch32(p, ksk32, ct_big)))
         dec = E.lwe_decrypt(S, _pad(out), 59)
         ok = bool(np.array_equal(dec.cpu().numpy() & 15, table[msgs]))
         ok2 = bool(np.array_equal(E.lwe_decrypt(S, _pad(out2), 59).cpu().numpy() & 15, table[msgs]))
@@ -84,9 +89,10 @@ def measure(dev, args, batches=None):
                "kernel": "pbs_kernel_mb2 (two key bits per step)" if mb2_ms < ms else "pbs_kernel_tmem (one key bit per step)",
                "single_bit_ms": ms, "single_bit_per_sec": B / (ms * 1e-3),
                "multi_bit_ms": mb2_ms, "multi_bit_per_sec": B / (mb2_ms * 1e-3),
-               "ks_ms": ks_ms, "ks64_ms": ks64_ms,
+               "ks_ms": ks_ms, "ks32_int_pipe_ms": ks32_ms, "ks64_ms": ks64_ms,
                "ks_per_sec": B / (ks_ms * 1e-3), "ks_pbs_per_sec": B / ((fastest + ks_ms) * 1e-3),
-               "fp64_tflops": flops * B / (fastest * 1e-3) / 1e12, "correct": ok and ok2}
+               "ks_int8_tops": 2.0 * B * p.k * p.N * p.l_ks * 4 * (p.n + 1) / (ks_ms * 1e-3) / 1e12,
+               "fp64_tflops": flops * B / (fastest * 1e-3) / 1e12, "correct": ok and ok2 and ks_same}
         # both roofline terms: key streamed once per launch + ciphertext I/O over HBM, and the
         # algorithmic FP64 work; whichever is larger is the roofline time for this batch
         key_bytes = bsk_bytes * (3 / 2 if mb2_ms < ms else 1)
@@ -103,6 +109,7 @@ def measure(dev, args, batches=None):
         "metric": "pbs_per_sec", "value": best["pbs_per_sec"], "unit": "PBS/s", "batch": best["batch"],
         "kernel": best["kernel"],
         "ks_pbs_per_sec": best["ks_pbs_per_sec"], "all_correct": all(r["correct"] for r in rows),
+        "keyswitch": _keyswitch_summary(rows, p, getattr(args, "_bf16_peak", None)),
         "params": {k: d[k] for k in ("n", "k", "N_poly", "l_pbs", "beta_pbs", "l_ks", "beta_ks", "log2_sigma_lwe",
                                      "log2_sigma_glwe")},
         "by_batch": rows,
@@ -125,6 +132,27 @@ def measure(dev, args, batches=None):
                              "(by_batch[].roofline_terms gives both terms per batch)."},
     }
     return res
+
+
+def _keyswitch_summary(rows, p, bf16_peak_tflops):
+    """Keyswitch section of the bench line: the tensor-core contraction against an int8 roofline."""
+    best = max(rows, key=lambda r: r["ks_per_sec"])
+    # int8 dense peak: twice the dense bf16 rate (same tensor pipe, half the operand width); the bf16 figure is the
+    # measured cuBLAS burst number of MEASURED_PEAKS.json when present, else the nominal 2250 TFLOP/s
+    bf16 = float(bf16_peak_tflops) if bf16_peak_tflops else 2250.0
+    peak = 2.0 * bf16
+    return {"metric": "keyswitches_per_sec", "value": best["ks_per_sec"], "unit": "keyswitch/s", "batch": best["batch"],
+            "kernel": "ks_mma_kernel (tcgen05.mma.kind::i8, s8 digits x u8 key bytes -> s32 in TMEM) + ks_digits_kernel",
+            "integer_pipe_ks32_per_sec": best["batch"] / (best["ks32_int_pipe_ms"] * 1e-3),
+            "bit_identical_to_integer_kernel": all(r["correct"] for r in rows),
+            "roofline": {"bound": "tensor", "achieved": best["ks_int8_tops"], "peak": peak, "unit": "TOP/s",
+                         "frac": best["ks_int8_tops"] / peak,
+                         "peak_source": ("2 x measured dense bf16 burst (MEASURED_PEAKS.json)" if bf16_peak_tflops
+                                         else "2 x nominal dense bf16 (2250 TFLOP/s)"),
+                         "ops_per_keyswitch": 2.0 * p.k * p.N * p.l_ks * 4 * (p.n + 1),
+                         "note": "achieved counts the int8 MACs of the byte-plane contraction (4 planes per 32-bit key word) over the "
+                                 "time of digit extraction + contraction; 128x256 tiles read 48 KB of operands per 1 M MACs, so the "
+                                 "kernel is bounded by L2->SM operand bandwidth before the tensor pipe"}}
 
 
 def measure_pair(dev, args, docs: int = 148):

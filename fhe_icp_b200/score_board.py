@@ -16,7 +16,9 @@ Layout (client allocation): ``arrive[2][world]`` u64 flags in a 4 KiB header, th
 Flow control: step ``s`` (1, 2, ...) uses slot ``s % 2``; rank r may overwrite the slot only after the
 client consumed step ``s - 2``, which it learns from ``credit[s % 2] >= s - 2`` (a bounded one-warp
 wait on a side stream, joined to the compute stream by an event, so it costs no bubble).  All waits
-time out (status word -> RuntimeError at the next :meth:`check`), they never hang the GPU.
+time out (status word -> RuntimeError at the next :meth:`check`), they never hang the GPU, and a
+kernel only ever spins on a flag that ANOTHER GPU writes: dependencies between streams of the client's
+own GPU (its own shard's arrival, its own credit) are CUDA events.
 """
 from __future__ import annotations
 
@@ -146,7 +148,15 @@ class PeerScoreBoard:
         step, slot = self.step, slot_of(self.step)
         main, st = self._st()
         need = credit_needed(step)
-        if need:   # bounded wait for the client's credit on a side stream; joins the compute stream by event
+        if need and self.rank == self.client_rank:
+            # the client's own shard: the slot was released by this process, on this GPU -- an event orders it
+            # (kernels that spin on a flag are only ever used ACROSS GPUs, never between streams of one GPU)
+            ev = self._events.get(("consumed", slot))
+            if ev is None:
+                self.step -= 1
+                raise RuntimeError(f"score board: step {step} would overwrite slot {slot} before release() of step {need}")
+            main.wait_event(ev)
+        elif need:  # bounded wait for the client's credit on a side stream; joins the compute stream by event
             ev = self._events.setdefault(("credit", slot), torch.cuda.Event())
             with torch.cuda.stream(self.credit_stream):
                 N.check(self._lib.fhe_b200_peer_wait(self.ctx.handle, C.c_void_p(self.ctrl + 8 * slot), 1, need,
@@ -169,6 +179,7 @@ class PeerScoreBoard:
                      for s in range(SLOTS)], dtype=torch.int64))
             N.check(self._lib.fhe_b200_peer_signal(self.ctx.handle, C.c_void_p(self._own_arrive_tab.data_ptr() + 8 * slot),
                                                    1, step, st))
+            self._mark_pushed(main)
             return step
         push = N.Push(self.board_base + rows_off, self.board_base + arrive, step, self.ctrl + _CTRL_COUNTER)
         h = self.circuit.handle
@@ -177,7 +188,13 @@ class PeerScoreBoard:
                                                                   ct.ct_base, C.byref(push), st))
         else:
             N.check(self._lib.fhe_b200_similarity_run_push(h, C.c_void_p(ct.data_ptr()), B, C.byref(push), st))
+        self._mark_pushed(main)
         return step
+
+    def _mark_pushed(self, main) -> None:
+        if self.rank == self.client_rank:   # collect() orders itself behind the client's own shard by this event
+            ev = self._events.setdefault("pushed", torch.cuda.Event())
+            ev.record(main)
 
     # ---- client side
     def collect(self, stream=None) -> torch.Tensor:
@@ -185,7 +202,9 @@ class PeerScoreBoard:
         the slot as an int32 tensor [world * rows_max, M, stride] (rank r's rows start at r * rows_max)."""
         assert self.rank == self.client_rank, "collect() is a client-rank call"
         step, slot = self.step, slot_of(self.step)
-        _, st = self._st(stream)
+        s, st = self._st(stream)
+        if "pushed" in self._events:
+            s.wait_event(self._events["pushed"])     # own shard: stream order; the kernel below waits for the peers
         N.check(self._lib.fhe_b200_peer_wait(self.ctx.handle, C.c_void_p(self.board_base + 8 * slot * self.world),
                                              self.world, step, self.timeout_ms, C.c_void_p(self.ctrl + _CTRL_STATUS), st))
         return self._slots[slot]
@@ -195,9 +214,10 @@ class PeerScoreBoard:
         back to every rank (stream-ordered release store of the step into their credit flags)."""
         assert self.rank == self.client_rank, "release() is a client-rank call"
         slot = slot_of(self.step)
-        _, st = self._st(stream)
+        s, st = self._st(stream)
         N.check(self._lib.fhe_b200_peer_signal(self.ctx.handle, C.c_void_p(self.ctrl + _CTRL_PTRS + 8 * slot * self.world),
                                                self.world, self.step, st))
+        self._events.setdefault(("consumed", slot), torch.cuda.Event()).record(s)
 
     def check(self) -> None:
         """Host check of the time-out status word (synchronises the device)."""

@@ -171,16 +171,35 @@ def test_score_board_push_is_bit_exact(cuda_dev):
 
 
 def test_score_board_waits_are_bounded(cuda_dev):
-    """A credit that never comes (dead client) must not hang the GPU: the wait times out and check() raises."""
+    """A flag that never comes (dead peer) must not hang the GPU: the in-stream wait times out and sets the
+    status word; a flag that is already there lets the stream through.  On the client's own GPU the slot
+    credit is an event, and overwriting an unreleased slot is a host-side error."""
+    import ctypes as C
+    import torch
+    from fhe_icp_b200 import _native as N
     from fhe_icp_b200.score_board import PeerScoreBoard
+    ctx = N.context(cuda_dev.index)
+    flags = torch.tensor([7, 7, 3], dtype=torch.int64, device=cuda_dev)
+    status = torch.zeros(1, dtype=torch.int32, device=cuda_dev)
+    N.check(N.lib().fhe_b200_peer_wait(ctx.handle, C.c_void_p(flags.data_ptr()), 2, 7, 30, C.c_void_p(status.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    N.check(N.lib().fhe_b200_peer_wait(ctx.handle, C.c_void_p(flags.data_ptr()), 3, 7, 30, C.c_void_p(status.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert int(status.item()) == 1                      # flags[2] = 3 never reaches 7: timed out after 30 ms
+    ptrs = torch.tensor([flags.data_ptr() + 16], dtype=torch.int64, device=cuda_dev)
+    N.check(N.lib().fhe_b200_peer_signal(ctx.handle, C.c_void_p(ptrs.data_ptr()), 1, 9, None))
+    torch.cuda.synchronize()
+    assert flags.tolist() == [7, 7, 9]
     m, X = _board_model(rows=64)
     board = PeerScoreBoard(m, rows_max=64, timeout_ms=30)
     try:
         ct = m.encrypt(X, seeded=True)
-        for _ in range(3):          # the third step needs the credit of the first, which nobody released
-            board.push(ct)
-        with pytest.raises(RuntimeError, match="timed out"):
-            board.check()
+        board.push(ct)
+        board.push(ct)
+        with pytest.raises(RuntimeError, match="before release"):
+            board.push(ct)          # the third step needs the slot of the first, which nobody released
+        board.check()
     finally:
         board.close()
 
