@@ -33,35 +33,45 @@ cudaError_t launch_secret_key(uint64_t key_seed, uint32_t key_id, int64_t dim, u
 }
 
 // ----------------------------------------------------------------------------- encrypt
-// One warp per ciphertext.  Lane L generates Philox blocks L, L+32, ... (two mask words
-// each), stores them with one 128-bit store (512 B per warp instruction) and accumulates
-// <a, s> against the key bits held in shared memory.
+// Two kernels.  (1) lwe_body_noise_kernel, one THREAD per ciphertext: plaintext + rounded Gaussian error into the
+// body slot (the Box-Muller chain is ~250 dependent FP64 instructions, so it runs lane-parallel).  (2) one WARP
+// per ciphertext: lane L generates Philox blocks L, L+32, ... (two mask words each), stores them with one 128-bit
+// store (512 B per warp instruction), accumulates <a, s> against the key bits held in shared memory and adds it
+// to the body.  The unit of work is ONE ciphertext and the grid is the number of resident warps, so the static
+// round-robin is balanced to a few percent (with 32-ciphertext units, 128 k ciphertexts filled only 4000 of
+// 4736 resident warps and the kernel ran at the pace of the fullest SMs: 15 % lost).
 constexpr int ENC_WARPS = 8;
-constexpr int64_t ENC_MAX_GRID = 148 * 8;  // resident CTAs on a B200; beyond that warps loop
+
+__global__ void lwe_body_noise_kernel(const int64_t* __restrict__ msgs, int64_t count, int shift, double sigma_abs,
+                                      uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, uint64_t* __restrict__ dst,
+                                      int64_t dst_stride) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t ndom = FHE_B200_KIND_NOISE | (purpose << 8);
+    dst[i * dst_stride] = ((uint64_t)msgs[i] << shift) + (uint64_t)gaussian_i64(enc_seed, ndom, ct_base + (uint64_t)i, 0, sigma_abs);
+}
+
+template <typename Kernel>
+static unsigned enc_grid(Kernel kernel, size_t smem, int64_t count) {
+    int dev = 0, sms = 148, per_sm = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ENC_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 4;
+    const int64_t resident = (int64_t)sms * per_sm;
+    return (unsigned)std::min<int64_t>((count + ENC_WARPS - 1) / ENC_WARPS, resident);
+}
 
 __global__ void __launch_bounds__(ENC_WARPS * 32)
-lwe_encrypt_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, const int64_t* __restrict__ msgs,
-                   int64_t count, int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base,
-                   uint32_t purpose, uint64_t* __restrict__ out) {
+lwe_encrypt_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, int64_t count, uint64_t enc_seed,
+                   uint64_t ct_base, uint32_t purpose, uint64_t* __restrict__ out) {
     extern __shared__ uint32_t skey[];  // packed key bits, ceil(n/32) words (+1 pad)
     pack_key_bits(key, n, skey);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    // the key bits are packed once per CTA; each warp then takes groups of 32 consecutive ciphertexts:
-    // the 32 Gaussian errors of a group are computed lane-parallel, then the warp walks the group
-    const uint32_t ndom = FHE_B200_KIND_NOISE | (purpose << 8);
-    const int64_t groups = (count + 31) / 32;
-    for (int64_t g = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); g < groups; g += (int64_t)gridDim.x * ENC_WARPS) {
-        const int64_t c0 = g * 32;
-        const int64_t mine = c0 + lane;
-        const int64_t e_mine = mine < count ? gaussian_i64(enc_seed, ndom, ct_base + (uint64_t)mine, 0, sigma_abs) : 0;
-        const uint64_t pt_mine = mine < count ? (uint64_t)msgs[mine] << shift : 0;
-        const int cnt = (int)min((int64_t)32, count - c0);
-        for (int k = 0; k < cnt; ++k) {
-            const int64_t e = __shfl_sync(0xffffffffu, e_mine, k);
-            const uint64_t pt = __shfl_sync(0xffffffffu, pt_mine, k);
-            warp_lwe_encrypt(skey, n, stride, pt, e, enc_seed, purpose, ct_base + (uint64_t)(c0 + k), out + (c0 + k) * stride, lane);
-        }
+    for (int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); c < count; c += (int64_t)gridDim.x * ENC_WARPS) {
+        uint64_t* ct = out + c * stride;
+        const uint64_t pre = lane == 0 ? ct[n] : 0;   // plaintext + error, written by lwe_body_noise_kernel
+        warp_lwe_encrypt(skey, n, stride, pre, 0, enc_seed, purpose, ct_base + (uint64_t)c, ct, lane);
     }
 }
 
@@ -69,11 +79,12 @@ cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, cons
                                int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
                                uint64_t* d_ct, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
+    lwe_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_msgs, count, shift, sigma_abs, enc_seed, ct_base,
+                                                                        purpose, d_ct + n, stride);
+    count_launch();
     size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
-    const int64_t groups = (count + 31) / 32;
-    unsigned grid = (unsigned)std::min<int64_t>((groups + ENC_WARPS - 1) / ENC_WARPS, ENC_MAX_GRID);
-    lwe_encrypt_kernel<<<grid, ENC_WARPS * 32, smem, s>>>(d_key, n, stride, d_msgs, count, shift, sigma_abs,
-                                                          enc_seed, ct_base, purpose, d_ct);
+    lwe_encrypt_kernel<<<enc_grid(lwe_encrypt_kernel, smem, count), ENC_WARPS * 32, smem, s>>>(d_key, n, stride, count, enc_seed,
+                                                                                              ct_base, purpose, d_ct);
     count_launch();
     return cudaGetLastError();
 }
@@ -330,11 +341,11 @@ cudaError_t launch_lincomb_push(const uint64_t* d_ct, int64_t B, int d, int n, i
 // section 7.2) and moves the dot product from the HBM roofline to the integer pipe (10 Philox rounds
 // per 16 mask bytes).  Results are bit-identical to the materialised form.
 
-// client: bodies only.  One warp per ciphertext, exactly the arithmetic of warp_lwe_encrypt.
+// client: bodies only.  lwe_body_noise_kernel writes plaintext + error, then one warp per ciphertext adds <a, s>
+// (exactly the arithmetic of warp_lwe_encrypt, nothing stored but the 8-byte body).
 __global__ void __launch_bounds__(ENC_WARPS * 32)
-lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, const int64_t* __restrict__ msgs, int64_t count,
-                          int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
-                          uint64_t* __restrict__ bodies) {
+lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, int64_t count, uint64_t enc_seed, uint64_t ct_base,
+                          uint32_t purpose, uint64_t* __restrict__ bodies) {
     extern __shared__ uint32_t skey[];
     pack_key_bits(key, n, skey);
     __syncthreads();
@@ -342,32 +353,20 @@ lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, const int64_t*
     const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
     const PhiloxKeys K(enc_seed);
     const int nblk = (n + 1) / 2;
-    const uint32_t ndom = FHE_B200_KIND_NOISE | (purpose << 8);
-    const int64_t groups = (count + 31) / 32;
-    for (int64_t g = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); g < groups; g += (int64_t)gridDim.x * ENC_WARPS) {
-        const int64_t c0 = g * 32;
-        const int64_t mine = c0 + lane;
-        // lane-parallel: error and plaintext of ciphertext c0 + lane; the dot products follow one by one
-        uint64_t body_mine = 0;
-        if (mine < count)
-            body_mine = ((uint64_t)msgs[mine] << shift) +
-                        (uint64_t)gaussian_i64(enc_seed, ndom, ct_base + (uint64_t)mine, 0, sigma_abs);
-        const int cnt = (int)min((int64_t)32, count - c0);
-        for (int k = 0; k < cnt; ++k) {
-            const uint64_t id = ct_base + (uint64_t)(c0 + k);
-            uint64_t dot = 0;
+    for (int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); c < count; c += (int64_t)gridDim.x * ENC_WARPS) {
+        const uint64_t id = ct_base + (uint64_t)c;
+        const uint64_t pre = lane == 0 ? bodies[c] : 0;
+        uint64_t dot = 0;
 #pragma unroll 2
-            for (int blk = lane; blk < nblk; blk += 32) {
-                u32x4 r = rng_block(K, dom, id, (uint32_t)blk);
-                const int w = 2 * blk;
-                uint32_t bits = skey[w >> 5] >> (w & 31);
-                dot += lo64(r) & (0 - (uint64_t)(bits & 1u));
-                if (w + 1 < n) dot += hi64(r) & (0 - (uint64_t)((bits >> 1) & 1u));
-            }
-            dot = warp_sum_u64(dot);
-            if (lane == k) body_mine += dot;
+        for (int blk = lane; blk < nblk; blk += 32) {
+            u32x4 r = rng_block(K, dom, id, (uint32_t)blk);
+            const int w = 2 * blk;
+            uint32_t bits = skey[w >> 5] >> (w & 31);
+            dot += lo64(r) & (0 - (uint64_t)(bits & 1u));
+            if (w + 1 < n) dot += hi64(r) & (0 - (uint64_t)((bits >> 1) & 1u));
         }
-        if (mine < count) bodies[mine] = body_mine;   // one coalesced store per group
+        dot = warp_sum_u64(dot);
+        if (lane == 0) bodies[c] = pre + dot;
     }
 }
 
@@ -375,11 +374,12 @@ cudaError_t launch_lwe_encrypt_seeded(const uint8_t* d_key, int n, const int64_t
                                       double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
                                       uint64_t* d_bodies, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
+    lwe_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_msgs, count, shift, sigma_abs, enc_seed, ct_base,
+                                                                        purpose, d_bodies, 1);
+    count_launch();
     size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
-    const int64_t groups = (count + 31) / 32;
-    unsigned grid = (unsigned)std::min<int64_t>((groups + ENC_WARPS - 1) / ENC_WARPS, ENC_MAX_GRID);
-    lwe_encrypt_seeded_kernel<<<grid, ENC_WARPS * 32, smem, s>>>(d_key, n, d_msgs, count, shift, sigma_abs, enc_seed,
-                                                                 ct_base, purpose, d_bodies);
+    lwe_encrypt_seeded_kernel<<<enc_grid(lwe_encrypt_seeded_kernel, smem, count), ENC_WARPS * 32, smem, s>>>(
+        d_key, n, count, enc_seed, ct_base, purpose, d_bodies);
     count_launch();
     return cudaGetLastError();
 }
@@ -960,6 +960,11 @@ similarity_decrypt_kernel(const uint32_t* __restrict__ kbits, int n, int64_t str
     const int t = (warp - m * wpc) * 32 + lane, T = wpc * 32;
     const WORD* ct = cts + ((size_t)blockIdx.x * M + m) * stride;
     const int nvec = n / VW;
+    WORD body[2] = {0, 0};
+    if (threadIdx.x == 0) {   // in flight behind the mask loads, instead of a second round trip after the barrier
+        body[0] = cts[((size_t)blockIdx.x * M) * stride + n];
+        if (M == 2) body[1] = cts[((size_t)blockIdx.x * M + 1) * stride + n];
+    }
     WORD dot = 0;
     for (int v0 = t; v0 < nvec; v0 += T * SD_DEPTH) {
         RowVec<WORD, VW> x[SD_DEPTH];
@@ -993,7 +998,7 @@ similarity_decrypt_kernel(const uint32_t* __restrict__ kbits, int n, int64_t str
             if (mm >= M) break;
             WORD d = 0;
             for (int w = 0; w < wpc; ++w) d += part[mm * wpc + w];
-            const WORD mu = cts[((size_t)blockIdx.x * M + mm) * stride + n] - d;
+            const WORD mu = body[mm] - d;
             const WORD v = mu + (shift > 0 ? ((WORD)1 << (shift - 1)) : (WORD)0);
             if (sizeof(WORD) == 8) msg[mm] = (int64_t)v >> shift;
             else msg[mm] = (int64_t)((int32_t)v >> shift);

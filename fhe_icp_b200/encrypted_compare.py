@@ -210,7 +210,8 @@ class EncryptedThreshold:
         p = ec.p
         ec._need_keys()
         # keyswitching key laid out for the tensor-core contraction (ks_mma.cu); bit-identical to KS32
-        self.key_mma = E.ksk_to_mma(p, E.ksk_to_32(p, E.ksk_gen(p, ec.S, ec.s, ec.evk_seed)))
+        self.ksk32 = E.ksk_to_32(p, E.ksk_gen(p, ec.S, ec.s, ec.evk_seed))
+        self.key_mma = E.ksk_to_mma(p, self.ksk32)
         self._ks_work = None
         mask = (1 << 64) - 1
         consts = [(-(1 << (self.out_shift - 1 + i))) & mask for i in range(self.score_bits - 1)] + [1 << (BIT_SHIFT - 1)]
