@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -612,7 +613,12 @@ int fhe_b200_similarity_create(fhe_b200_ctx* ctx, const fhe_b200_similarity_spec
     s->M = spec->two_outputs ? 2 : 1;
     s->second_is_sum = spec->two_outputs != 0;
     cudaError_t e;
-    if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) goto bad;
+    {   // the model's stream carries the dot products and the client kernels: highest priority, so that they are
+        // scheduled ahead of the encryption of the next chunk (enc_stream, lowest priority) when the two overlap
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((e = cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, hi)) != cudaSuccess) goto bad;
+    }
     if ((e = cudaMalloc(&s->d_key, (size_t)spec->n)) != cudaSuccess) goto bad;
     if ((e = cudaMalloc(&s->d_W, sizeof(int64_t) * (size_t)s->M * spec->d)) != cudaSuccess) goto bad;
     if ((e = cudaMemcpyAsync(s->d_W, h_q_w, sizeof(int64_t) * spec->d, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess) goto bad;
@@ -894,7 +900,9 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
     CU(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->stream;
     if (!s->enc_stream) {
-        CU(cudaStreamCreateWithFlags(&s->enc_stream, cudaStreamNonBlocking));
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&s->enc_stream, cudaStreamNonBlocking, lo));
         for (int i = 0; i < 2; ++i) {
             CU(cudaEventCreateWithFlags(&s->ev_enc[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming));
@@ -910,7 +918,16 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
     const size_t row_bytes = sizeof(uint64_t) * (size_t)sp.d * sp.stride;
     int64_t chunk = (int64_t)(((size_t)1 << 30) / row_bytes);
     if (chunk < 1) chunk = 1;
-    if (B >= 2048 && chunk > (B + 3) / 4) chunk = (B + 3) / 4;   // >= 4 chunks so the stages overlap (measured: pays from ~2k rows)
+    static const int64_t overlap_from = [] {   // FHE_B200_OVERLAP_FROM: batch size from which the stages are overlapped
+        const char* e = getenv("FHE_B200_OVERLAP_FROM");
+        return e ? (int64_t)atoll(e) : (int64_t)512;
+    }();
+    static const int64_t overlap_chunks = [] {
+        const char* e = getenv("FHE_B200_OVERLAP_CHUNKS");
+        return e ? (int64_t)atoll(e) : (int64_t)8;   // measured at 1000 rows: 4 -> 0.70 ms, 8 -> 0.65 ms, 16 -> 0.78 ms
+    }();
+    const bool overlap = B >= overlap_from;
+    if (overlap && chunk > (B + overlap_chunks - 1) / overlap_chunks) chunk = (B + overlap_chunks - 1) / overlap_chunks;
     if (chunk > B) chunk = B;
     const int64_t cnt = B * sp.d;
     CU(s->ct.reserve(2 * row_bytes * (size_t)chunk));
@@ -931,9 +948,14 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
         const int64_t rows = (B - r0 < chunk) ? (B - r0) : chunk;
         uint64_t* ctb = (uint64_t*)s->ct.p + (size_t)(k & 1) * (size_t)chunk * sp.d * sp.stride;
         if (k >= 2) CU(cudaStreamWaitEvent(s->enc_stream, s->ev_free[k & 1], 0));   // buffer consumed by chunk k-2
-        CU(fhe::launch_lwe_encrypt(s->d_key, sp.n, sp.stride, (const int64_t*)s->q.p + r0 * sp.d, rows * sp.d, sp.shift,
-                                   sp.sigma_abs, enc_seed, ct_base + (uint64_t)(r0 * sp.d), FHE_B200_PUR_INPUT, ctb,
-                                   s->enc_stream));
+        if (overlap)   // short-lived CTAs: the dot product of chunk k-1 shares the SMs with this
+            CU(fhe::launch_lwe_encrypt_packed(s->d_key_bits, sp.n, sp.stride, (const int64_t*)s->q.p + r0 * sp.d, rows * sp.d,
+                                              sp.shift, sp.sigma_abs, enc_seed, ct_base + (uint64_t)(r0 * sp.d),
+                                              FHE_B200_PUR_INPUT, ctb, s->enc_stream));
+        else
+            CU(fhe::launch_lwe_encrypt(s->d_key, sp.n, sp.stride, (const int64_t*)s->q.p + r0 * sp.d, rows * sp.d, sp.shift,
+                                       sp.sigma_abs, enc_seed, ct_base + (uint64_t)(r0 * sp.d), FHE_B200_PUR_INPUT, ctb,
+                                       s->enc_stream));
         CU(cudaEventRecord(s->ev_enc[k & 1], s->enc_stream));
         CU(cudaStreamWaitEvent(st, s->ev_enc[k & 1], 0));
         CU(fhe::launch_lincomb(ctb, rows, sp.d, sp.n, sp.stride, s->d_W, s->M, s->second_is_sum, 0, 0, sp.shift,

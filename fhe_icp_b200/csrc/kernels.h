@@ -13,6 +13,9 @@ cudaError_t launch_secret_key(uint64_t key_seed, uint32_t key_id, int64_t dim, u
 cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
                                int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
                                uint64_t* d_ct, cudaStream_t s);
+cudaError_t launch_lwe_encrypt_packed(const uint32_t* d_kbits, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
+                                      int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
+                                      uint64_t* d_ct, cudaStream_t s);
 cudaError_t launch_lwe_phase(const uint8_t* d_key, int n, int64_t stride, const uint64_t* d_ct, int64_t count,
                              int shift, bool decode, uint64_t* d_out, cudaStream_t s);
 cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_t stride, const int64_t* d_W, int M,

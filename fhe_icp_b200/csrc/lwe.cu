@@ -75,6 +75,35 @@ lwe_encrypt_kernel(const uint8_t* __restrict__ key, int n, int64_t stride, int64
     }
 }
 
+// Variant for a pipeline stage that runs NEXT TO the HBM-bound dot product of the previous chunk: key bits come
+// pre-packed from global memory (no per-CTA prologue) and a CTA encrypts ENC_WARPS ciphertexts and exits, so SM
+// slots keep turning over and the higher-priority dot-product CTAs get the share they need (a persistent grid
+// would hold every slot until the whole chunk is encrypted).
+__global__ void __launch_bounds__(ENC_WARPS * 32)
+lwe_encrypt_packed_kernel(const uint32_t* __restrict__ kbits, int n, int64_t stride, int64_t count, uint64_t enc_seed,
+                          uint64_t ct_base, uint32_t purpose, uint64_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
+    if (c >= count) return;
+    uint64_t* ct = out + c * stride;
+    const uint64_t pre = lane == 0 ? ct[n] : 0;
+    warp_lwe_encrypt(kbits, n, stride, pre, 0, enc_seed, purpose, ct_base + (uint64_t)c, ct, lane);
+}
+
+cudaError_t launch_lwe_encrypt_packed(const uint32_t* d_kbits, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
+                                      int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
+                                      uint64_t* d_ct, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t grid = (count + ENC_WARPS - 1) / ENC_WARPS;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+    lwe_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_msgs, count, shift, sigma_abs, enc_seed, ct_base,
+                                                                        purpose, d_ct + n, stride);
+    count_launch();
+    lwe_encrypt_packed_kernel<<<(unsigned)grid, ENC_WARPS * 32, 0, s>>>(d_kbits, n, stride, count, enc_seed, ct_base, purpose, d_ct);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
                                int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
                                uint64_t* d_ct, cudaStream_t s) {
@@ -948,22 +977,28 @@ struct RowVec<uint32_t, 2> {
 constexpr int SD_THREADS = 256;
 constexpr int SD_DEPTH = 6;   // loads in flight per lane
 
-template <typename WORD, int VW>
+// DPC = documents per CTA: the 8 warps are shared by the DPC * M ciphertexts of DPC consecutive documents.  The
+// 32-bit wire form has half as many 16-byte vectors per row, so it takes two documents per CTA to keep ~6 loads
+// in flight per lane -- and half the CTA slot-time, which matters on the client GPU of a multi-GPU search where
+// this kernel runs next to the HBM-bound dot product of the next step.
+template <typename WORD, int VW, int DPC>
 __global__ void __launch_bounds__(SD_THREADS)
-similarity_decrypt_kernel(const uint32_t* __restrict__ kbits, int n, int64_t stride, const WORD* __restrict__ cts,
+similarity_decrypt_kernel(const uint32_t* __restrict__ kbits, int n, int64_t stride, const WORD* __restrict__ cts, int64_t B,
                           int M, int shift, int64_t zp_w, int64_t q_bias, double out_scale, int64_t out_zp,
                           double* __restrict__ y, int64_t* __restrict__ q_y) {
     __shared__ WORD part[SD_THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpc = (SD_THREADS / 32) / M;                 // warps per ciphertext (M = 1 or 2)
-    const int m = warp / wpc;
-    const int t = (warp - m * wpc) * 32 + lane, T = wpc * 32;
-    const WORD* ct = cts + ((size_t)blockIdx.x * M + m) * stride;
-    const int nvec = n / VW;
+    const int wpc = (SD_THREADS / 32) / (M * DPC);         // warps per ciphertext (M = 1 or 2)
+    const int ci = warp / wpc;                             // ciphertext of this CTA: document ci / M, output ci % M
+    const int t = (warp - ci * wpc) * 32 + lane, T = wpc * 32;
+    const int64_t doc0 = (int64_t)blockIdx.x * DPC;
+    const bool live = doc0 + ci / M < B;
+    const WORD* ct = cts + ((size_t)doc0 * M + ci) * stride;
+    const int nvec = live ? n / VW : 0;
     WORD body[2] = {0, 0};
-    if (threadIdx.x == 0) {   // in flight behind the mask loads, instead of a second round trip after the barrier
-        body[0] = cts[((size_t)blockIdx.x * M) * stride + n];
-        if (M == 2) body[1] = cts[((size_t)blockIdx.x * M + 1) * stride + n];
+    if (threadIdx.x < DPC && doc0 + threadIdx.x < B) {   // thread dd finalises document dd: its bodies are in flight
+        body[0] = cts[((size_t)(doc0 + threadIdx.x) * M) * stride + n];   // behind the mask loads
+        if (M == 2) body[1] = cts[((size_t)(doc0 + threadIdx.x) * M + 1) * stride + n];
     }
     WORD dot = 0;
     for (int v0 = t; v0 < nvec; v0 += T * SD_DEPTH) {
@@ -983,7 +1018,7 @@ similarity_decrypt_kernel(const uint32_t* __restrict__ kbits, int n, int64_t str
             }
         }
     }
-    if (t < n - nvec * VW) {   // mask words past the last full vector
+    if (live && t < n - nvec * VW) {   // mask words past the last full vector
         const int w = nvec * VW + t;
         dot += ct[w] & (WORD)(0 - (WORD)((__ldg(kbits + (w >> 5)) >> (w & 31)) & 1u));
     }
@@ -991,13 +1026,14 @@ similarity_decrypt_kernel(const uint32_t* __restrict__ kbits, int n, int64_t str
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
     if (lane == 0) part[warp] = dot;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < DPC && doc0 + threadIdx.x < B) {
+        const int dd = threadIdx.x;
         int64_t msg[2] = {0, 0};
 #pragma unroll
         for (int mm = 0; mm < 2; ++mm) {
             if (mm >= M) break;
             WORD d = 0;
-            for (int w = 0; w < wpc; ++w) d += part[mm * wpc + w];
+            for (int w = 0; w < wpc; ++w) d += part[(dd * M + mm) * wpc + w];
             const WORD mu = body[mm] - d;
             const WORD v = mu + (shift > 0 ? ((WORD)1 << (shift - 1)) : (WORD)0);
             if (sizeof(WORD) == 8) msg[mm] = (int64_t)v >> shift;
@@ -1005,8 +1041,8 @@ similarity_decrypt_kernel(const uint32_t* __restrict__ kbits, int n, int64_t str
         }
         // q_y = m0 - zp_w * m1 + q_bias;  y = out_scale * (q_y - out_zp)   
         const int64_t q = msg[0] - zp_w * msg[1] + q_bias;
-        if (q_y) q_y[blockIdx.x] = q;
-        if (y) y[blockIdx.x] = __dmul_rn(out_scale, (double)(q - out_zp));
+        if (q_y) q_y[doc0 + dd] = q;
+        if (y) y[doc0 + dd] = __dmul_rn(out_scale, (double)(q - out_zp));
     }
 }
 
@@ -1015,16 +1051,15 @@ cudaError_t launch_similarity_decrypt(const uint32_t* d_kbits, int n, int64_t st
                                       int64_t out_zp, double* d_y, int64_t* d_q_y, cudaStream_t s) {
     if (B <= 0) return cudaSuccess;
     if (B > 0x7fffffffLL || (M != 1 && M != 2)) return cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)B;
     if (!wire32)
-        similarity_decrypt_kernel<uint64_t, 2><<<grid, SD_THREADS, 0, s>>>(
-            d_kbits, n, stride, (const uint64_t*)d_cts, M, shift, zp_w, q_bias, out_scale, out_zp, d_y, d_q_y);
+        similarity_decrypt_kernel<uint64_t, 2, 1><<<(unsigned)B, SD_THREADS, 0, s>>>(
+            d_kbits, n, stride, (const uint64_t*)d_cts, B, M, shift, zp_w, q_bias, out_scale, out_zp, d_y, d_q_y);
     else if (stride % 4 == 0 && (reinterpret_cast<uintptr_t>(d_cts) & 15) == 0)
-        similarity_decrypt_kernel<uint32_t, 4><<<grid, SD_THREADS, 0, s>>>(
-            d_kbits, n, stride, (const uint32_t*)d_cts, M, shift, zp_w, q_bias, out_scale, out_zp, d_y, d_q_y);
+        similarity_decrypt_kernel<uint32_t, 4, 2><<<(unsigned)((B + 1) / 2), SD_THREADS, 0, s>>>(
+            d_kbits, n, stride, (const uint32_t*)d_cts, B, M, shift, zp_w, q_bias, out_scale, out_zp, d_y, d_q_y);
     else
-        similarity_decrypt_kernel<uint32_t, 2><<<grid, SD_THREADS, 0, s>>>(
-            d_kbits, n, stride, (const uint32_t*)d_cts, M, shift, zp_w, q_bias, out_scale, out_zp, d_y, d_q_y);
+        similarity_decrypt_kernel<uint32_t, 2, 1><<<(unsigned)B, SD_THREADS, 0, s>>>(
+            d_kbits, n, stride, (const uint32_t*)d_cts, B, M, shift, zp_w, q_bias, out_scale, out_zp, d_y, d_q_y);
     count_launch();
     return cudaGetLastError();
 }
