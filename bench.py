@@ -235,7 +235,7 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
+        os.environ["NCCL_DEBUG"] = os.environ.get("FHE_B200_NCCL_DEBUG", "NONE")   # VERSION and WARN both print a banner on stdout; the contract is ONE JSON line
         # NCCL's stream (and the post stream below) run at high priority: the dot-product kernel keeps
         # thousands of CTAs queued, and equal-priority kernels only start once those are all dispatched
         opts = dist.ProcessGroupNCCL.Options()

@@ -224,11 +224,12 @@ __device__ __forceinline__ void push_store(uint32_t* o, uint64_t x, uint64_t y) 
     v.y = (uint32_t)((y + 0x80000000ULL) >> 32);
     *reinterpret_cast<uint2*>(o) = v;
 }
-// every thread of the CTA calls this after its stores
+// every thread of the CTA calls this after its stores.  The barrier orders the CTA's stores before thread 0,
+// whose system-scope fence is cumulative over them (the grid-sync pattern): one fence per CTA, not one per thread.
 __device__ __forceinline__ void push_arrive(const PushArgs& p) {
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned prev = atomicAdd(p.counter, 1u);
         if (prev == gridDim.x - 1) {
             atomicExch(p.counter, 0u);
