@@ -33,7 +33,7 @@ sys.path.insert(0, str(ROOT))
 D_FEATURES = 128
 N_BITS = 8
 DATA_SEED, KEY_SEED, ENC_SEED, EVK_SEED = 20261018, 0x5EED0001, 0x5EED0002, 0x5EED0003
-NCU_DRAM_BYTES_PER_DOC = 1475339  # (1.458192 GB + 17.147 MB) / 1000 documents, profiles/r1_ncu_lincomb_v2.txt
+NCU_DRAM_BYTES_PER_DOC = 1475986  # (1.458192 GB read + 17.794 MB written) / 1000 documents, profiles/r1_ncu_lincomb_decrypt_v3.txt
 METRIC = "encrypted_comparisons_per_sec"
 UNIT = "comparisons/s"
 
@@ -436,7 +436,7 @@ def run_b200_arm(args):
         "roofline": {"bound": "hbm", "kernel": "lincomb_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_DOC * B if c.lwe.n == 1423 and M == 2 else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
-                                       "profiles/r1_ncu_lincomb_v2.txt (1000 documents, n=1423)",
+                                       "profiles/r1_ncu_lincomb_decrypt_v3.txt (1000 documents, n=1423)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms": kern_ms},
         "clocks": clocks,

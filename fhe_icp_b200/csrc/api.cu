@@ -716,11 +716,9 @@ int fhe_b200_similarity_encrypt_seeded(fhe_b200_similarity* s, const float* d_X,
     CU(cudaSetDevice(s->ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t cnt = B * sp.d;
-    CU(s->q.reserve(sizeof(int64_t) * (size_t)cnt));
     const int64_t qmin = -sp.x_offset, qmax = (1LL << sp.n_bits) - 1 - sp.x_offset;
-    CU(fhe::launch_quantize(d_X, cnt, sp.x_scale, sp.x_zero_point, qmin, qmax, (int64_t*)s->q.p, st));
-    CU(fhe::launch_lwe_encrypt_seeded(s->d_key, sp.n, (const int64_t*)s->q.p, cnt, sp.shift, sp.sigma_abs, enc_seed,
-                                      ct_base, FHE_B200_PUR_INPUT, d_bodies, st));
+    CU(fhe::launch_lwe_encrypt_seeded_float(s->d_key, sp.n, d_X, cnt, sp.x_scale, sp.x_zero_point, qmin, qmax, sp.shift,
+                                            sp.sigma_abs, enc_seed, ct_base, FHE_B200_PUR_INPUT, d_bodies, st));
     return FHE_B200_OK;
 }
 
@@ -751,20 +749,20 @@ int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity* s, const float*
     CU(s->hX.reserve(xbytes));
     CU(s->ct.reserve(sizeof(uint64_t) * (size_t)B * sp.d));       // bodies only
     CU(s->out.reserve(sizeof(uint64_t) * (size_t)B * s->M * sp.stride));
-    CU(s->y.reserve(sizeof(double) * (size_t)B));
-    CU(s->qy.reserve(sizeof(int64_t) * (size_t)B));
-    CU(s->hy.reserve(sizeof(double) * (size_t)B));
-    CU(s->hqy.reserve(sizeof(int64_t) * (size_t)B));
-    memcpy(s->hX.p, h_X, xbytes);
+    // scores and integers share one device / one pinned buffer: a single device->host copy
+    CU(s->y.reserve(16 * (size_t)B));
+    CU(s->hy.reserve(16 * (size_t)B));
+    double* d_y = (double*)s->y.p;
+    int64_t* d_qy = (int64_t*)((char*)s->y.p + 8 * (size_t)B);
+    memcpy(s->hX.p, h_X, xbytes);   // staged through pinned memory so the copy is truly asynchronous
     CU(cudaMemcpyAsync(s->X.p, s->hX.p, xbytes, cudaMemcpyHostToDevice, st));
     if (int r = fhe_b200_similarity_encrypt_seeded(s, (const float*)s->X.p, B, enc_seed, ct_base, (uint64_t*)s->ct.p, st)) return r;
     if (int r = fhe_b200_similarity_run_seeded(s, (const uint64_t*)s->ct.p, B, enc_seed, ct_base, (uint64_t*)s->out.p, st)) return r;
-    if (int r = fhe_b200_similarity_decrypt(s, (const uint64_t*)s->out.p, B, (double*)s->y.p, (int64_t*)s->qy.p, st)) return r;
-    CU(cudaMemcpyAsync(s->hy.p, s->y.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(s->hqy.p, s->qy.p, sizeof(int64_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (int r = fhe_b200_similarity_decrypt(s, (const uint64_t*)s->out.p, B, d_y, d_qy, st)) return r;
+    CU(cudaMemcpyAsync(s->hy.p, s->y.p, 16 * (size_t)B, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (h_y) memcpy(h_y, s->hy.p, sizeof(double) * (size_t)B);
-    if (h_q_y) memcpy(h_q_y, s->hqy.p, sizeof(int64_t) * (size_t)B);
+    if (h_q_y) memcpy(h_q_y, (char*)s->hy.p + 8 * (size_t)B, sizeof(int64_t) * (size_t)B);
     return FHE_B200_OK;
 }
 

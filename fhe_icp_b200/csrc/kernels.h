@@ -24,6 +24,10 @@ cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_
 cudaError_t launch_lwe_encrypt_seeded(const uint8_t* d_key, int n, const int64_t* d_msgs, int64_t count, int shift,
                                       double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
                                       uint64_t* d_bodies, cudaStream_t s);
+cudaError_t launch_lwe_encrypt_seeded_float(const uint8_t* d_key, int n, const float* d_X, int64_t count, double scale,
+                                            int64_t zp, int64_t qmin, int64_t qmax, int shift, double sigma_abs,
+                                            uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, uint64_t* d_bodies,
+                                            cudaStream_t s);
 cudaError_t launch_lwe_expand_seeded(const uint64_t* d_bodies, int64_t count, int n, int64_t stride, uint64_t enc_seed,
                                      uint64_t ct_base, uint32_t purpose, uint64_t* d_out, cudaStream_t s);
 cudaError_t launch_lincomb_seeded(const uint64_t* d_bodies, int64_t B, int d, int n, int64_t stride, uint64_t enc_seed,

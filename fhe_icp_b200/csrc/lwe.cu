@@ -400,6 +400,35 @@ lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, int64_t count,
     }
 }
 
+// quantize (the UniformQuantizer rule of quantize_kernel) + plaintext + error in one pass:
+// the client path from float features to seeded ciphertexts needs no integer staging buffer
+__global__ void quantize_body_noise_kernel(const float* __restrict__ X, int64_t count, double scale, double zp, double qmin,
+                                           double qmax, int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base,
+                                           uint32_t purpose, uint64_t* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double v = rint(__dadd_rn(__ddiv_rn((double)X[i], scale), zp));
+    v = fmin(fmax(v, qmin), qmax);
+    const uint32_t ndom = FHE_B200_KIND_NOISE | (purpose << 8);
+    dst[i] = ((uint64_t)(int64_t)v << shift) + (uint64_t)gaussian_i64(enc_seed, ndom, ct_base + (uint64_t)i, 0, sigma_abs);
+}
+
+cudaError_t launch_lwe_encrypt_seeded_float(const uint8_t* d_key, int n, const float* d_X, int64_t count, double scale,
+                                            int64_t zp, int64_t qmin, int64_t qmax, int shift, double sigma_abs,
+                                            uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, uint64_t* d_bodies,
+                                            cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    quantize_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_X, count, scale, (double)zp, (double)qmin,
+                                                                             (double)qmax, shift, sigma_abs, enc_seed, ct_base,
+                                                                             purpose, d_bodies);
+    count_launch();
+    size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
+    lwe_encrypt_seeded_kernel<<<enc_grid(lwe_encrypt_seeded_kernel, smem, count), ENC_WARPS * 32, smem, s>>>(
+        d_key, n, count, enc_seed, ct_base, purpose, d_bodies);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lwe_encrypt_seeded(const uint8_t* d_key, int n, const int64_t* d_msgs, int64_t count, int shift,
                                       double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
                                       uint64_t* d_bodies, cudaStream_t s) {

@@ -19,3 +19,14 @@ def run(O):
     out = E.pbs(p, bskf, E.keyswitch(p, ksk, ct), lut)
     dec = O.lwe_decrypt(O.secret_key(1, 1, p.k * p.N), E.to_u64_numpy(out), 59) & 15
     assert np.array_equal(dec, table), "decrypt(PBS(KS(enc(m)))) != LUT[m]"
+    # the same atomic pattern with the keyswitch on the tensor cores (tcgen05 int8 contraction): bit-identical
+    # to the integer-pipe 32-bit keyswitch and to the oracle's, and the bootstrap behind it still evaluates the table
+    ksk32 = E.ksk_to_32(p, ksk)
+    ks_tc = E.keyswitch_mma(p, E.ksk_to_mma(p, ksk32), ct)
+    assert torch.equal(ks_tc, E.keyswitch32(p, ksk32, ct)), "tensor-core keyswitch != integer keyswitch"
+    op = O.make_params(n=d["n"], k=d["k"], N=d["N_poly"], l_pbs=d["l_pbs"], beta_pbs=d["beta_pbs"], l_ks=d["l_ks"],
+                       beta_ks=d["beta_ks"], log2_sigma_lwe=d["log2_sigma_lwe"], log2_sigma_glwe=d["log2_sigma_glwe"])
+    assert np.array_equal(E.to_u64_numpy(ks_tc), O.keyswitch32(op, O.ksk_to_32(op, E.to_u64_numpy(ksk)), E.to_u64_numpy(ct))), \
+        "tensor-core keyswitch != oracle"
+    dec = O.lwe_decrypt(O.secret_key(1, 1, p.k * p.N), E.to_u64_numpy(E.pbs(p, bskf, ks_tc, lut)), 59) & 15
+    assert np.array_equal(dec, table), "decrypt(PBS(KS_mma(enc(m)))) != LUT[m]"
