@@ -17,7 +17,7 @@ _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 _SO = _PKG / "libfhe_b200.so"
 _SOURCES = ["api.cu", "lwe.cu", "keys.cu", "keyswitch.cu", "ks_mma.cu", "pbs.cu", "probe.cu"]
-_HEADERS = ["common.cuh", "kernels.h", "fft.cuh", "lwe_device.cuh", "../../include/fhe_b200.h"]
+_HEADERS = ["common.cuh", "kernels.h", "fft.cuh", "lwe_device.cuh", "ks_mma_layout.cuh", "../../include/fhe_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

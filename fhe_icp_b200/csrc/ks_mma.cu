@@ -25,22 +25,23 @@
 // ciphertext words).  4-stage full/empty mbarrier ring; `tcgen05.commit` releases a stage when its MMAs retire.
 #include "common.cuh"
 #include "kernels.h"
+#include "ks_mma_layout.cuh"
 
 namespace fhe {
 namespace {
 
-constexpr int KM_M = 128;                       // ciphertext rows per tile (UMMA M)
-constexpr int KM_N = 256;                       // byte columns per tile (UMMA N) = 64 output words
-constexpr int KM_KB = 128;                      // k per pipeline stage
-constexpr int KM_UMMA_K = 32;                   // k per tcgen05.mma.kind::i8
+constexpr int KM_M = kml::M_TILE;               // ciphertext rows per tile (UMMA M)
+constexpr int KM_N = kml::N_TILE;               // byte columns per tile (UMMA N) = 64 output words
+constexpr int KM_KB = kml::K_BLOCK;             // k per pipeline stage
+constexpr int KM_UMMA_K = kml::UMMA_K;          // k per tcgen05.mma.kind::i8
 constexpr int KM_STAGES = 4;
-constexpr int KM_A_BYTES = KM_M * KM_KB;        // 16 KB
-constexpr int KM_B_BYTES = KM_N * KM_KB;        // 32 KB
+constexpr int KM_A_BYTES = kml::A_BYTES;        // 16 KB
+constexpr int KM_B_BYTES = kml::B_BYTES;        // 32 KB
 constexpr int KM_THREADS = 192;
 constexpr uint32_t KM_TMEM_COLS = 256;
-constexpr uint32_t KM_A_LBO = (KM_M / 8) * 128;  // bytes between 16-byte k chunks of A (2048)
-constexpr uint32_t KM_B_LBO = (KM_N / 8) * 128;  // ... of B (4096)
-constexpr uint32_t KM_SBO = 128;                 // bytes between 8-row groups
+constexpr uint32_t KM_A_LBO = kml::A_LBO;       // bytes between 16-byte k chunks of A (2048)
+constexpr uint32_t KM_B_LBO = kml::B_LBO;       // ... of B (4096)
+constexpr uint32_t KM_SBO = kml::SBO;           // bytes between 8-row groups
 constexpr size_t KM_SMEM = (size_t)KM_STAGES * (KM_A_BYTES + KM_B_BYTES) + 256;
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (Blackwell)
@@ -82,78 +83,18 @@ __device__ __forceinline__ void km_tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]
 
 }  // namespace
 
-// ---- key bytes in MMA block layout (once per key)
-// One thread per 16-byte chunk: (nt, kb, k16, n8, r) -> 16 consecutive k of byte-column cc = n8*8 + r.
-__global__ void ksk32_to_mma_kernel(const uint32_t* __restrict__ ksk32, int kN, int l, int n, int n_tiles,
+// ---- key bytes in MMA block layout (once per key) and digits in MMA block layout (per batch): one thread per
+// 16-byte chunk / per (row, 16 coefficients); the builders live in ks_mma_layout.cuh (shared with the CPU emulation)
+__global__ void ksk32_to_mma_kernel(const uint32_t* __restrict__ ksk32, int kN, int l, int n, int64_t chunks,
                                     uint8_t* __restrict__ tiles) {
-    const int kblocks = l * (kN / KM_KB);
-    const int64_t chunks = (int64_t)n_tiles * kblocks * (KM_KB / 16) * KM_N;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= chunks) return;
-    const int r = (int)(g & 7);
-    const int n8 = (int)((g >> 3) % (KM_N / 8));
-    int64_t rest = (g >> 3) / (KM_N / 8);
-    const int k16 = (int)(rest % (KM_KB / 16));
-    rest /= (KM_KB / 16);
-    const int kb = (int)(rest % kblocks);
-    const int nt = (int)(rest / kblocks);
-    const int cc = n8 * 8 + r;
-    const int c = nt * (KM_N / 4) + (cc >> 2), q = cc & 3;
-    const int lev = kb / (kN / KM_KB);
-    const int j0 = (kb % (kN / KM_KB)) * KM_KB + k16 * 16;
-    uint32_t w[4] = {0, 0, 0, 0};
-    if (c <= n) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint32_t v = ksk32[((size_t)(j0 + i) * l + lev) * (size_t)(n + 1) + c];
-            w[i >> 2] |= ((v >> (8 * q)) & 0xFFu) << (8 * (i & 3));
-        }
-    }
-    *reinterpret_cast<uint4*>(tiles + g * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (g < chunks) kml::build_b_chunk(g, ksk32, kN, l, n, tiles);
 }
 
-// ---- digits in MMA block layout (per batch)
-// One thread per (row, 16 consecutive coefficients): l chunks of 16 digit bytes, one per level.
-__global__ void ks_digits_kernel(const uint64_t* __restrict__ in, int64_t B, int kN, int l, int beta,
+__global__ void ks_digits_kernel(const uint64_t* __restrict__ in, int64_t B, int kN, int l, int beta, int64_t items,
                                  int8_t* __restrict__ a_tiles) {
-    const int chunks_per_row = kN / 16;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t rows = (B + KM_M - 1) / KM_M * KM_M;
-    if (g >= rows * chunks_per_row) return;
-    // consecutive threads walk the rows of one 8-row group, then the groups: stores are 128-byte contiguous
-    const int r = (int)(g % KM_M);
-    int64_t rest = g / KM_M;
-    const int ch = (int)(rest % chunks_per_row);
-    const int64_t mt = rest / chunks_per_row;
-    const int64_t b = mt * KM_M + r;
-    const int kblocks = l * (kN / KM_KB);
-    const int jb = ch / (KM_KB / 16), k16 = ch % (KM_KB / 16);
-    const int tot = l * beta;
-    const uint64_t Bm = (1ULL << beta) - 1, half = 1ULL << (beta - 1);
-    uint64_t offs = 0;
-    for (int lev = 0; lev < l; ++lev) offs |= half << (beta * lev);
-    uint64_t st[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const uint64_t a = b < B ? in[b * (int64_t)(kN + 1) + ch * 16 + i] : 0;
-        // closest representative on tot bits, then balanced base-2^beta digits (keyswitch_kernel's arithmetic)
-        st[i] = ((a + (1ULL << (63 - tot))) >> (64 - tot)) + offs;
-    }
-    for (int lev = 0; lev < l; ++lev) {
-        const int sh = beta * (l - 1 - lev);
-        uint32_t w[4] = {0, 0, 0, 0};
-        if (b < B) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int dgt = (int)((st[i] >> sh) & Bm) - (int)half;
-                w[i >> 2] |= ((uint32_t)dgt & 0xFFu) << (8 * (i & 3));
-            }
-        }
-        const int kb = lev * (kN / KM_KB) + jb;
-        int8_t* dst = a_tiles + ((size_t)(mt * kblocks + kb)) * KM_A_BYTES + (size_t)k16 * KM_A_LBO + (size_t)(r >> 3) * KM_SBO +
-                      (size_t)(r & 7) * 16;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+    if (g < items) kml::build_a_chunks(g, in, B, kN, l, beta, a_tiles);
 }
 
 // ---- the contraction
@@ -227,8 +168,8 @@ ks_mma_kernel(const int8_t* __restrict__ a_tiles, const uint8_t* __restrict__ b_
             km_tmem_ld_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ch * 16), r);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int c = nt * (KM_N / 4) + ch * 4 + i;
-                const uint32_t v = r[4 * i] + (r[4 * i + 1] << 8) + (r[4 * i + 2] << 16) + (r[4 * i + 3] << 24);
+                const int c = kml::word_of(nt, ch * 16 + 4 * i);
+                const uint32_t v = kml::recombine(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
                 if (b < B && c <= n) orow[c] = (uint64_t)((c == n ? body : 0u) - v) << 32;
             }
         }
@@ -238,12 +179,12 @@ ks_mma_kernel(const int8_t* __restrict__ a_tiles, const uint8_t* __restrict__ b_
     if (warp == 1) km_tmem_dealloc(tmem_base, KM_TMEM_COLS);
 }
 
-static int km_col_tiles(int n) { return (4 * (n + 1) + KM_N - 1) / KM_N; }
+static int km_col_tiles(int n) { return kml::col_tiles(n); }
 
 bool keyswitch_mma_supported(const fhe_b200_pbs_params& p) {
     const int64_t kN = (int64_t)p.k * p.N;
     return kN % KM_KB == 0 && p.beta_ks >= 1 && p.beta_ks <= 8 && p.l_ks >= 1 && p.l_ks * p.beta_ks <= 62 &&
-           (int64_t)p.l_ks * kN * 4 * 255 < (1LL << 31);
+           (int64_t)p.l_ks * kN * (1LL << (p.beta_ks - 1)) * 255 < (1LL << 31);   // |digit| <= 2^(beta-1), byte <= 255: s32 never wraps
 }
 
 size_t keyswitch_mma_key_bytes(const fhe_b200_pbs_params& p) {
@@ -260,7 +201,7 @@ cudaError_t launch_ksk32_to_mma(const fhe_b200_pbs_params& p, const uint32_t* d_
     if (!keyswitch_mma_supported(p)) return cudaErrorInvalidValue;
     const int kN = p.k * p.N;
     const int64_t chunks = (int64_t)(keyswitch_mma_key_bytes(p) / 16);
-    ksk32_to_mma_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(d_ksk32, kN, p.l_ks, p.n, km_col_tiles(p.n), d_tiles);
+    ksk32_to_mma_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(d_ksk32, kN, p.l_ks, p.n, chunks, d_tiles);
     count_launch();
     return cudaGetLastError();
 }
@@ -273,7 +214,7 @@ cudaError_t launch_keyswitch_mma(const fhe_b200_pbs_params& p, const uint8_t* d_
     const int64_t m_tiles = (B + KM_M - 1) / KM_M;
     if (m_tiles > 65535) return cudaErrorInvalidValue;
     const int64_t dthreads = m_tiles * KM_M * (kN / 16);
-    ks_digits_kernel<<<(unsigned)((dthreads + 255) / 256), 256, 0, s>>>(d_in, B, kN, p.l_ks, p.beta_ks, d_work);
+    ks_digits_kernel<<<(unsigned)((dthreads + 255) / 256), 256, 0, s>>>(d_in, B, kN, p.l_ks, p.beta_ks, dthreads, d_work);
     count_launch();
     cudaError_t e = cudaFuncSetAttribute(ks_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KM_SMEM);
     if (e != cudaSuccess) return e;

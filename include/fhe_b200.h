@@ -233,7 +233,7 @@ int fhe_b200_keyswitch32(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const 
  * u8 key bytes -> s32 in tensor memory; ks_mma.cu).  Bit-identical to fhe_b200_keyswitch32.  ksk_to_mma lays
  * the 32-bit key out in MMA blocks (ksk_mma_bytes bytes, once per key); keyswitch_mma needs a per-call
  * workspace of keyswitch_mma_workspace_bytes(B) for the digit matrix.  Both sizes are 0 for parameter sets the
- * kernel does not cover (kN % 128 != 0, beta_ks > 8, or l_ks*kN*1020 >= 2^31). */
+ * kernel does not cover (kN % 128 != 0, beta_ks > 8, or l_ks*kN*2^(beta_ks-1)*255 >= 2^31). */
 uint64_t fhe_b200_ksk_mma_bytes(const fhe_b200_pbs_params *p);
 uint64_t fhe_b200_keyswitch_mma_workspace_bytes(const fhe_b200_pbs_params *p, int64_t B);
 int fhe_b200_ksk_to_mma(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint32_t *d_ksk32,

@@ -280,3 +280,17 @@ def test_keyswitch_tensor_core_bit_exact(O, request, cuda_dev, which, B):
     rnd = torch.as_tensor(np.random.RandomState(B + 1).randint(-2 ** 63, 2 ** 63 - 1, size=(B, kN + 1), dtype=np.int64)).to(cuda_dev)
     assert np.array_equal(_u64(E.keyswitch_mma(K.p, key_mma, rnd)), _u64(E.keyswitch32(K.p, ksk32, rnd)))
     assert E.keyswitch_mma(K.p, key_mma, rnd[:0]).shape == (0, K.p.n + 1)
+
+
+def test_keyswitch_tensor_core_other_gadgets(O, cuda_dev):
+    """Gadgets other than the stated 5 x 3 bits: 3 x 4 and 2 x 8 bits (digits down to -128 fill the whole s8 range)."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    for l_ks, beta_ks in [(3, 4), (2, 8)]:
+        K = Keys(O, cuda_dev, dict(TOY, l_ks=l_ks, beta_ks=beta_ks))
+        kN = K.p.k * K.p.N
+        rnd = torch.as_tensor(np.random.RandomState(l_ks).randint(-2 ** 63, 2 ** 63 - 1, size=(37, kN + 1), dtype=np.int64)).to(cuda_dev)
+        ksk32 = E.ksk_to_32(K.p, K.ksk)
+        out = E.keyswitch_mma(K.p, E.ksk_to_mma(K.p, ksk32), rnd)
+        assert np.array_equal(_u64(out), _u64(E.keyswitch32(K.p, ksk32, rnd)))
+        assert np.array_equal(_u64(out), O.keyswitch32(K.op, O.ksk_to_32(K.op, _u64(K.ksk)), _u64(rnd)))
