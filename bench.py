@@ -64,10 +64,9 @@ def synthetic_docs(n_docs: int, seed: int):
 
 def top_k(scores: np.ndarray, k: int, min_similarity: float):
     """Reference semantics (batch_operations.py:278-284): filter >=, stable sort descending, [:k]."""
+    from fhe_icp_b200.batch_operations import top_indices
     scores = np.asarray(scores, dtype=np.float64)
-    keep = np.flatnonzero(scores >= min_similarity)
-    order = keep[np.argsort(-scores[keep], kind="stable")][:k]   # == stable sort with reverse=True
-    return [(int(i), float(scores[i])) for i in order]
+    return [(int(i), float(scores[i])) for i in top_indices(scores, k, min_similarity)]
 
 
 class ClockSampler:

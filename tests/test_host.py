@@ -169,3 +169,21 @@ def test_signed_bit_width():
     from fhe_icp_b200.quantization import signed_bit_width
     assert signed_bit_width(0, 255) == 8 and signed_bit_width(-128, 127) == 8 and signed_bit_width(-129, 0) == 9
     assert signed_bit_width(0, 0) == 1 and signed_bit_width(-1, 0) == 1 and signed_bit_width(-1, 1) == 2
+
+
+def test_top_indices_equals_full_stable_sort():
+    """The selection-based ranking equals the reference's 'filter, stable sort descending, [:k]' on ties, NaN-free
+    ragged inputs, thresholds that empty the list and k larger than the collection."""
+    from fhe_icp_b200.batch_operations import rank_results, top_indices
+    rng = np.random.RandomState(0)
+    for n in (0, 1, 5, 300, 5000):
+        for trial in range(6):
+            s = np.round(rng.randn(n), 1 if trial % 2 else 6)          # 1 decimal: many exact ties
+            for k in (0, 1, 3, 10, n + 5):
+                for thr in (-np.inf, -0.5, 0.5, 10.0):
+                    keep = [i for i in range(n) if s[i] >= thr]
+                    want = sorted(keep, key=lambda i: s[i], reverse=True)[:k]     # Python's stable sort, like the reference
+                    assert top_indices(s, k, thr).tolist() == want
+    ids = [f"d{i}" for i in range(7)]
+    sc = np.array([0.5, 0.9, 0.5, 0.9, 0.1, 0.7, 0.5])
+    assert rank_results(ids, sc, 4, 0.5) == [("d1", 0.9), ("d3", 0.9), ("d5", 0.7), ("d0", 0.5)]

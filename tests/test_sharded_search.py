@@ -289,3 +289,46 @@ def test_score_board_layout_and_credits():
     spans.sort()
     assert spans[0][0] == sb.HEADER_BYTES and spans[-1][1] == sb.board_bytes(world, rows, M, stride)
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_score_board_protocol_is_safe_and_live_under_any_schedule():
+    """Model of the flag protocol built on score_board.slot_of / credit_needed: `world` servers push steps
+    1..K (a push may start only when credit[slot] >= credit_needed(step)), the client consumes a step once every
+    arrival flag of its slot carries that step and then writes the step into every rank's credit flag.  Under
+    randomly interleaved schedules the run always finishes (no deadlock), a slot is never overwritten before the
+    client consumed it, and the client reads exactly the step it waited for."""
+    from fhe_icp_b200 import score_board as sb
+    rng = np.random.RandomState(7)
+    for world in (1, 2, 3, 8):
+        for trial in range(40):
+            K = 9
+            nxt = [1] * world                                   # next step each server will push
+            arrive = [[0] * world for _ in range(sb.SLOTS)]     # client memory
+            content = [[0] * world for _ in range(sb.SLOTS)]    # which step's scores sit in (slot, rank)
+            credit = [[0] * sb.SLOTS for _ in range(world)]     # each rank's memory
+            consumed = 0
+            for _ in range(20000):
+                if consumed == K:
+                    break
+                actor = rng.randint(0, world + 1)
+                if actor < world:                               # server `actor` tries to push its next step
+                    s = nxt[actor]
+                    if s > K:
+                        continue
+                    k = sb.slot_of(s)
+                    if credit[actor][k] < sb.credit_needed(s):
+                        continue                                # bounded wait: not yet
+                    assert content[k][actor] <= consumed, "slot overwritten before the client consumed it"
+                    content[k][actor] = s
+                    arrive[k][actor] = s
+                    nxt[actor] = s + 1
+                else:                                           # client tries to consume step consumed + 1
+                    s = consumed + 1
+                    k = sb.slot_of(s)
+                    if min(arrive[k]) < s:
+                        continue
+                    assert content[k] == [s] * world, "client read a slot holding another step's scores"
+                    consumed = s
+                    for r in range(world):
+                        credit[r][k] = s
+            assert consumed == K, f"deadlock: world={world}, consumed={consumed}, next={nxt}"
