@@ -41,6 +41,10 @@ cudaError_t launch_secret_key(uint64_t key_seed, uint32_t key_id, int64_t dim, u
 // round-robin is balanced to a few percent (with 32-ciphertext units, 128 k ciphertexts filled only 4000 of
 // 4736 resident warps and the kernel ran at the pace of the fullest SMs: 15 % lost).
 constexpr int ENC_WARPS = 8;
+#ifndef LCS_UNROLL
+#define LCS_UNROLL 4
+#endif
+constexpr int LCS_UNROLL_N = LCS_UNROLL;   // independent Philox blocks in flight per thread (seeded dot product)
 
 __global__ void lwe_body_noise_kernel(const int64_t* __restrict__ msgs, int64_t count, int shift, double sigma_abs,
                                       uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, uint64_t* __restrict__ dst,
@@ -387,7 +391,7 @@ lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, int64_t count,
         const uint64_t id = ct_base + (uint64_t)c;
         const uint64_t pre = lane == 0 ? bodies[c] : 0;
         uint64_t dot = 0;
-#pragma unroll 2
+#pragma unroll ENC_UNROLL_N
         for (int blk = lane; blk < nblk; blk += 32) {
             u32x4 r = rng_block(K, dom, id, (uint32_t)blk);
             const int w = 2 * blk;
@@ -496,7 +500,7 @@ lincomb_seeded_kernel(const uint64_t* __restrict__ bodies, int d, int n, int64_t
         const PhiloxKeys K(enc_seed);
         uint64_t a0x = 0, a0y = 0, a1x = 0, a1y = 0;
         if (w0 <= n) {
-#pragma unroll 4
+#pragma unroll LCS_UNROLL_N
             for (int j = 0; j < d; ++j) {
                 uint64_t x, y;
                 seeded_pair(K, dom, id0 + j, w0, n, has_body ? bodies[b * d + j] : 0, x, y);

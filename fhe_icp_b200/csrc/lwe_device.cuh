@@ -4,6 +4,11 @@
 
 namespace fhe {
 
+#ifndef ENC_UNROLL
+#define ENC_UNROLL 2
+#endif
+constexpr int ENC_UNROLL_N = ENC_UNROLL;   // independent Philox blocks in flight per lane (encryption)
+
 // pack the 0/1 key bytes into 32-bit words in shared memory (block-wide; caller syncs)
 __device__ __forceinline__ void pack_key_bits(const uint8_t* __restrict__ key, int n, uint32_t* skey) {
     const int kw = (n + 31) / 32 + 1;
@@ -40,7 +45,7 @@ __device__ __forceinline__ void warp_lwe_encrypt(const uint32_t* skey, int n, in
     const PhiloxKeys K(seed);
     uint64_t dot = 0;
     const int nblk = (n + 1) / 2;
-#pragma unroll 2
+#pragma unroll ENC_UNROLL_N
     for (int blk = lane; blk < nblk; blk += 32) {
         u32x4 r = rng_block(K, dom, id, (uint32_t)blk);
         uint64_t a0 = lo64(r), a1 = hi64(r);
