@@ -268,15 +268,10 @@ def run_b200_arm(args):
     board = None
     if mode == "push":
         from fhe_icp_b200.score_board import PeerScoreBoard
-        try:
+        try:   # setup is collective and fails on every rank together (score_board.py), so all ranks take the same path
             board = PeerScoreBoard(model, B, client_rank=0)
         except Exception as e:  # e.g. no peer access between the GPUs of this box: NCCL path instead
             print(f"bench.py: rank {rank}: peer score board unavailable ({e}); using all_gather", file=sys.stderr)
-            mode = "all_gather"
-        flag = torch.tensor([1 if mode == "push" else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # every rank takes the same path
-        if int(flag.item()) == 0 and mode == "push":
-            board.close()
             board, mode = None, "all_gather"
     nccl = mode in ("gather", "all_gather")
     outs = [out, torch.empty_like(out)] if nccl else [out]

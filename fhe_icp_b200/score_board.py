@@ -93,33 +93,67 @@ class PeerScoreBoard:
         self._events = {}
         self.credit_stream = torch.cuda.Stream(device=self.dev, priority=-1)
 
-        # every rank: control block; client: board
-        self.ctrl, ctrl_handle = self._alloc(CTRL_BYTES)
+        # Every rank: control block; client: board.  Setup is collective, so a rank whose allocation or mapping
+        # fails (no peer access between two GPUs, out of memory) must not leave the others waiting in a
+        # collective: errors are held back until every rank has gone through the same sequence of collectives,
+        # then all ranks raise together.
         is_client = self.rank == self.client_rank
-        board_handle = None
-        if is_client:
-            self.board_base, board_handle = self._alloc(board_bytes(self.world, self.rows_max, self.M, self.stride))
+        err: Optional[BaseException] = None
+        ctrl_handle = board_handle = None
+        self.ctrl = self.board_base = 0
+        self._slots = None
+        self._own_arrive_tab = None
+        try:
+            self.ctrl, ctrl_handle = self._alloc(CTRL_BYTES)
+            if is_client:
+                self.board_base, board_handle = self._alloc(board_bytes(self.world, self.rows_max, self.M, self.stride))
+        except Exception as e:   # noqa: BLE001 -- re-raised below, after the collectives
+            err = e
+        ctrl_ptrs = [self.ctrl]
         if self.world > 1:
             handles = [None] * self.world
             dist.all_gather_object(handles, (ctrl_handle, board_handle))
-            if is_client:
-                ctrl_ptrs = [self.ctrl if r == self.rank else self._open(handles[r][0]) for r in range(self.world)]
-            else:
-                self.board_base = self._open(handles[self.client_rank][1])
-        else:
-            ctrl_ptrs = [self.ctrl]
-        if is_client:
-            # device tables of the credit-flag addresses of every rank, one table per slot
-            tab = _view(self.ctrl + _CTRL_PTRS, (SLOTS, self.world), "<i8", torch.int64, self.dev)
-            tab.copy_(torch.tensor([[p + 8 * s for p in ctrl_ptrs] for s in range(SLOTS)], dtype=torch.int64))
-            self._slots = [
-                _view(self.board_base + board_offsets(self.world, self.rows_max, self.M, self.stride, s, 0)[1],
-                      (self.world * self.rows_max, self.M, self.stride), "<i4", torch.int32, self.dev)
-                for s in range(SLOTS)]
-        self._own_arrive_tab = None
-        torch.cuda.synchronize(self.dev)
-        if self.world > 1:
-            dist.barrier()
+            try:
+                if err is None and any(h is None or h[0] is None for h in handles):
+                    raise RuntimeError("a peer failed to allocate its control block")
+                if err is None and is_client:
+                    ctrl_ptrs = [self.ctrl if r == self.rank else self._open(handles[r][0]) for r in range(self.world)]
+                elif err is None:
+                    if handles[self.client_rank][1] is None:
+                        raise RuntimeError("the client rank failed to allocate the score board")
+                    self.board_base = self._open(handles[self.client_rank][1])
+            except Exception as e:   # noqa: BLE001
+                err = e
+        try:
+            if err is None and is_client:
+                # device tables of the credit-flag addresses of every rank, one table per slot
+                tab = _view(self.ctrl + _CTRL_PTRS, (SLOTS, self.world), "<i8", torch.int64, self.dev)
+                tab.copy_(torch.tensor([[p + 8 * s for p in ctrl_ptrs] for s in range(SLOTS)], dtype=torch.int64))
+                self._slots = [
+                    _view(self.board_base + board_offsets(self.world, self.rows_max, self.M, self.stride, s, 0)[1],
+                          (self.world * self.rows_max, self.M, self.stride), "<i4", torch.int32, self.dev)
+                    for s in range(SLOTS)]
+            torch.cuda.synchronize(self.dev)
+        except Exception as e:   # noqa: BLE001
+            err = err or e
+        if self.world > 1:   # agreement doubles as the barrier: nobody pushes before every mapping exists
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                self._release_local()
+                raise RuntimeError(f"peer score board: setup failed on at least one rank (this rank: {err!r})")
+        elif err is not None:
+            self._release_local()
+            raise err
+
+    def _release_local(self) -> None:
+        """Undo this rank's share of a failed setup (no collective)."""
+        self._slots = None
+        for p in self._peer_ptrs:
+            self._lib.fhe_b200_peer_close(self.ctx.handle, C.c_void_p(p))
+        for p in self._own:
+            self._lib.fhe_b200_peer_free(self.ctx.handle, C.c_void_p(p))
+        self._peer_ptrs, self._own = [], []
 
     # ---- allocation helpers
     def _alloc(self, nbytes: int):
