@@ -91,6 +91,7 @@ class PeerScoreBoard:
         self._peer_ptrs = []          # mappings to close
         self._own = []                # allocations to free
         self._events = {}
+        self._released = [0] * SLOTS    # client: last step released per slot
         self.credit_stream = torch.cuda.Stream(device=self.dev, priority=-1)
 
         # Every rank: control block; client: board.  Setup is collective, so a rank whose allocation or mapping
@@ -185,11 +186,10 @@ class PeerScoreBoard:
         if need and self.rank == self.client_rank:
             # the client's own shard: the slot was released by this process, on this GPU -- an event orders it
             # (kernels that spin on a flag are only ever used ACROSS GPUs, never between streams of one GPU)
-            ev = self._events.get(("consumed", slot))
-            if ev is None:
+            if self._released[slot] < need:
                 self.step -= 1
                 raise RuntimeError(f"score board: step {step} would overwrite slot {slot} before release() of step {need}")
-            main.wait_event(ev)
+            main.wait_event(self._events[("consumed", slot)])
         elif need:  # bounded wait for the client's credit on a side stream; joins the compute stream by event
             ev = self._events.setdefault(("credit", slot), torch.cuda.Event())
             with torch.cuda.stream(self.credit_stream):
@@ -252,6 +252,7 @@ class PeerScoreBoard:
         N.check(self._lib.fhe_b200_peer_signal(self.ctx.handle, C.c_void_p(self.ctrl + _CTRL_PTRS + 8 * slot * self.world),
                                                self.world, self.step, st))
         self._events.setdefault(("consumed", slot), torch.cuda.Event()).record(s)
+        self._released[slot] = self.step
 
     def check(self) -> None:
         """Host check of the time-out status word (synchronises the device)."""

@@ -199,6 +199,18 @@ def test_score_board_waits_are_bounded(cuda_dev):
         board.push(ct)
         with pytest.raises(RuntimeError, match="before release"):
             board.push(ct)          # the third step needs the slot of the first, which nobody released
+        # ... and an OLDER release of the same slot does not count: steps 1..4 released, 5 not, 7 must be refused
+        board2 = PeerScoreBoard(m, rows_max=64, timeout_ms=30)
+        try:
+            for step in range(1, 7):
+                assert board2.push(ct) == step
+                if step != 5:
+                    board2.collect()
+                    board2.release()
+            with pytest.raises(RuntimeError, match="before release"):
+                board2.push(ct)
+        finally:
+            board2.close()
         board.check()
     finally:
         board.close()
