@@ -308,7 +308,9 @@ int fhe_b200_similarity_run_seeded_push(fhe_b200_similarity *sim, const uint64_t
                                         uint64_t enc_seed, uint64_t ct_base, const fhe_b200_push *push,
                                         void *stream);
 /* client: block the stream until d_flags[i] >= value for every i < count (bounded by timeout_ms;
- * on time-out *d_status is set to 1 and the stream continues) */
+ * on time-out *d_status is set to 1 and the stream continues).  Use it for flags that ANOTHER GPU
+ * writes; order work of the same GPU with events -- two kernels of one GPU are not guaranteed to run
+ * concurrently, so a kernel must not spin on a flag a later launch of the same GPU would set. */
 int fhe_b200_peer_wait(fhe_b200_ctx *ctx, const uint64_t *d_flags, int32_t count, uint64_t value,
                        uint32_t timeout_ms, uint32_t *d_status, void *stream);
 /* stream-ordered release store of `value` to each of the `count` flags whose (peer or local) addresses
