@@ -311,3 +311,30 @@ def test_fused_similarity_decrypt_all_row_shapes(cuda_dev, n, stride, two):
             assert np.array_equal(y.cpu().numpy()[:B - 1], y_want[1:])
     finally:
         N.lib().fhe_b200_similarity_destroy(h)
+
+
+@pytest.mark.parametrize("n_bits", [4, 8, 12])
+def test_quantization_strategy_sweep_fhe_equals_clear(cuda_dev, n_bits):
+    """The reference's quantization benchmark (quantization_strategy.py:28-90,134-160): SGDRegressor(n_bits,
+    max_iter=20, random_state=42) on the seed-42 dataset of CONCATENATED 256-d pairs, compiled on the training
+    set, then five rows predicted one at a time with fhe="execute" and compared with the clear prediction.  The
+    reference records `clear_vs_fhe_mae`; here it is exactly zero, for every bit width it sweeps."""
+    from fhe_icp_b200 import SGDRegressor
+    np.random.seed(42)
+    n_samples, dim = 500, 128
+    emb1 = np.random.randn(n_samples, dim).astype(np.float32)
+    emb1 = emb1 / np.linalg.norm(emb1, axis=1, keepdims=True)
+    emb2 = np.zeros_like(emb1)
+    for i in range(n_samples):
+        emb2[i] = emb1[i] + 0.1 * np.random.randn(dim) if i % 2 == 0 else np.random.randn(dim)
+    emb2 = emb2 / np.linalg.norm(emb2, axis=1, keepdims=True)
+    X, y = np.hstack([emb1, emb2]), np.sum(emb1 * emb2, axis=1)
+    X_train, X_test, y_train = X[:400], X[400:], y[:400]
+    model = SGDRegressor(n_bits=n_bits, max_iter=20, random_state=42)
+    model.fit(X_train, y_train)
+    model.compile(X_train)
+    assert model.fhe_circuit.graph.maximum_integer_bit_width() >= n_bits
+    clear = model.predict(X_test[:5])
+    fhe = np.array([model.predict(X_test[i:i + 1], fhe="execute")[0] for i in range(5)])
+    assert np.mean(np.abs(clear - fhe)) == 0.0
+    assert np.array_equal(model.predict(X_test, fhe="execute"), model.predict(X_test))
