@@ -113,8 +113,10 @@ FHE_HD void fwd_split_pass1(int h, double (&re)[16], double (&im)[16], cplx* til
 // ---- forward pass 2.  Warp h2, lane k2 = q + 16s: deferred butterfly, inter-pass twiddle tw[slot(k2, j1)] =
 // W^(j1*k2) * omega^j1 (fft.cuh's table, read along the lane's own row), 16-point DFT over the j1 of parity h2.
 // Publishes P0[p][k2] = Z_0[p] (h2 = 0) or P1[p][k2] = w32^p * Z_1[p] (h2 = 1).
-FHE_HD void fwd_split_pass2(int h2, double (&re)[16], double (&im)[16], const cplx* tile_e, const cplx* tile_o,
-                            const cplx* tw, cplx* pub0, cplx* pub1, int lane) {
+// compute part: results stay in registers (index p in register brev4(p), w32^p already applied for h2 = 1) so that
+// a kernel can put a barrier between the last read of the E / O tiles and the store over the same bytes.
+FHE_HD void fwd_split_pass2_compute(int h2, double (&re)[16], double (&im)[16], const cplx* tile_e, const cplx* tile_o,
+                                    const cplx* tw, int lane) {
     const int q = lane & 15;
     const double sg = lane >= 16 ? -1.0 : 1.0;   // the deferred butterfly as one FMA: X[q + 16s] = E + (-1)^s O
 #pragma unroll
@@ -128,20 +130,30 @@ FHE_HD void fwd_split_pass2(int h2, double (&re)[16], double (&im)[16], const cp
         im[m] = xr * w.y + xi * w.x;
     }
     dit16<+1, true>(re, im);
+    if (h2) {
+#pragma unroll
+        for (int p = 1; p < 16; ++p) {
+            const double wr = FHE_W32_RE(p), wi = FHE_W32_IM(p);
+            const double a = re[brev4(p)], b = im[brev4(p)];
+            re[brev4(p)] = a * wr - b * wi;
+            im[brev4(p)] = a * wi + b * wr;
+        }
+    }
+}
+FHE_HD void fwd_split_pass2_store(int h2, const double (&re)[16], const double (&im)[16], cplx* pub0, cplx* pub1, int lane) {
     cplx* dst = h2 ? pub1 : pub0;
 #pragma unroll
     for (int p = 0; p < 16; ++p) {
         cplx v;
         v.x = re[brev4(p)];
         v.y = im[brev4(p)];
-        if (h2 && p) {
-            const double wr = FHE_W32_RE(p), wi = FHE_W32_IM(p);
-            const double a = v.x, b = v.y;
-            v.x = a * wr - b * wi;
-            v.y = a * wi + b * wr;
-        }
         dst[hslot(p, lane)] = v;
     }
+}
+FHE_HD void fwd_split_pass2(int h2, double (&re)[16], double (&im)[16], const cplx* tile_e, const cplx* tile_o,
+                            const cplx* tw, cplx* pub0, cplx* pub1, int lane) {
+    fwd_split_pass2_compute(h2, re, im, tile_e, tile_o, tw, lane);
+    fwd_split_pass2_store(h2, re, im, pub0, pub1, lane);
 }
 
 // bin k = k2 + 32*k1 from the published half-spectra (what the pointwise stage reads)
@@ -177,6 +189,44 @@ FHE_HD void inv_split_pass1(int h, const cplx (&g_lo)[16], const cplx (&g_hi)[16
     for (int m = 0; m < 16; ++m) {
         const int j1 = 2 * m + h;
         const cplx w = tw[slot(lane, j1)];  // multiply by conj(w)
+        cplx v;
+        v.x = re[m] * w.x + im[m] * w.y;
+        v.y = im[m] * w.x - re[m] * w.y;
+        tile[slot(j1, lane)] = v;
+    }
+}
+// The same in three parts, for a kernel whose warp holds its OWN half of the pointwise output in registers (index p in
+// register p: G[k2 + 32(16h + p)]) and finds its partner's half in shared memory as exch[hslot(p, lane)]:
+//   combine  : S_p from own registers and the partner's half, in place (own registers become the DFT input)
+//   (barrier : the partner has read this warp's half, the bytes may be overwritten by the tile)
+//   finish   : 16-point DFT, conj twiddle, tile rows of parity h
+FHE_HD void inv_split_pass1_combine(int h, double (&re)[16], double (&im)[16], const cplx* partner_half, int lane) {
+    double sr[16], si[16];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+        const cplx o = partner_half[hslot(p, lane)];
+        // h = 0: own = G[p] (low half), partner = G[p+16];  h = 1: own = G[p+16], partner = G[p]:  S = G_lo + (-1)^h G_hi
+        sr[p] = h ? o.x - re[p] : re[p] + o.x;
+        si[p] = h ? o.y - im[p] : im[p] + o.y;
+        if (h && p) {
+            const double wr = FHE_W32_RE(p), wi = -FHE_W32_IM(p);
+            const double a = sr[p], b = si[p];
+            sr[p] = a * wr - b * wi;
+            si[p] = a * wi + b * wr;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+        re[brev4(p)] = sr[p];
+        im[brev4(p)] = si[p];
+    }
+}
+FHE_HD void inv_split_pass1_finish(int h, double (&re)[16], double (&im)[16], const cplx* tw, cplx* tile, int lane) {
+    dit16<-1, false>(re, im);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int j1 = 2 * m + h;
+        const cplx w = tw[slot(lane, j1)];
         cplx v;
         v.x = re[m] * w.x + im[m] * w.y;
         v.y = im[m] * w.x - re[m] * w.y;

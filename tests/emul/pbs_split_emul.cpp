@@ -48,7 +48,10 @@ extern "C" int emul_pbs_mb2_split(const double* key_blocks /* [pairs][32][3][2][
         for (int t = 0; t < 2; ++t)
             for (int h = 0; h < 2; ++h)
                 for (int lane = 0; lane < 32; ++lane)
-                    fwd_split_pass2(h, re, im, te[t].data(), to[t].data(), tw.data(), p0[t].data(), p1[t].data(), lane);
+                {   // compute, (barrier), store -- the kernel's order
+                    fwd_split_pass2_compute(h, re, im, te[t].data(), to[t].data(), tw.data(), lane);
+                    fwd_split_pass2_store(h, re, im, p0[t].data(), p1[t].data(), lane);
+                }
         for (int t = 0; t < 2; ++t)
             for (int h = 0; h < 2; ++h)
                 for (int lane = 0; lane < 32; ++lane) {   // pointwise on half-spectra
@@ -57,16 +60,24 @@ extern "C" int emul_pbs_mb2_split(const double* key_blocks /* [pairs][32][3][2][
                     split_pointwise(t, h, lane, p0[t].data(), p1[t].data(), p0[1 - t].data(), p1[1 - t].data(), key_pair, mo,
                                     g_re[t][h][lane], g_im[t][h][lane]);
                 }
+        // exchange of the halves as the kernel will do it: every warp stores its own half where the half-spectra were
+        // (after the barrier that ends the pointwise stage), the partner combines it with the half it holds in registers
+        static cplx exch[2][2][HALF_TILE_ELEMS];
         for (int t = 0; t < 2; ++t)
             for (int h = 0; h < 2; ++h)
-                for (int lane = 0; lane < 32; ++lane) {   // exchange of the halves -> inverse pass 1
-                    cplx lo[16], hi[16];
-                    for (int p = 0; p < 16; ++p) {
-                        lo[p].x = g_re[t][0][lane][p]; lo[p].y = g_im[t][0][lane][p];
-                        hi[p].x = g_re[t][1][lane][p]; hi[p].y = g_im[t][1][lane][p];
-                    }
-                    inv_split_pass1(h, lo, hi, re, im, tw.data(), tile[t].data(), lane);
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int p = 0; p < 16; ++p) { exch[t][h][hslot(p, lane)].x = g_re[t][h][lane][p]; exch[t][h][hslot(p, lane)].y = g_im[t][h][lane][p]; }
+        static double s_re[2][2][32][16], s_im[2][2][32][16];
+        for (int t = 0; t < 2; ++t)
+            for (int h = 0; h < 2; ++h)
+                for (int lane = 0; lane < 32; ++lane) {
+                    std::memcpy(s_re[t][h][lane], g_re[t][h][lane], sizeof(double) * 16);
+                    std::memcpy(s_im[t][h][lane], g_im[t][h][lane], sizeof(double) * 16);
+                    inv_split_pass1_combine(h, s_re[t][h][lane], s_im[t][h][lane], exch[t][1 - h], lane);
                 }
+        for (int t = 0; t < 2; ++t)      // (barrier) then the tile overwrites the exchange area
+            for (int h = 0; h < 2; ++h)
+                for (int lane = 0; lane < 32; ++lane) inv_split_pass1_finish(h, s_re[t][h][lane], s_im[t][h][lane], tw.data(), tile[t].data(), lane);
         for (int t = 0; t < 2; ++t)
             for (int h = 0; h < 2; ++h)
                 for (int lane = 0; lane < 32; ++lane) {   // inverse pass 2 -> accumulator update
