@@ -550,6 +550,31 @@ int fhe_b200_keyswitch32(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const 
     return FHE_B200_OK;
 }
 
+// ---- EXPERIMENTAL two-warps-per-polynomial multi-bit blind rotation (pbs_split.cu; not validated on a GPU yet)
+int fhe_b200_bsk2_fourier_split(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_bskf2, double* d_bskf2_split,
+                                void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(d_bskf2 && d_bskf2_split, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    REQUIRE(p->l_pbs == 1 && p->k == 1 && (p->n & 1) == 0, "the split kernel covers k = 1, l_pbs = 1, even n");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_bsk2_fourier_split(*p, d_bskf2, d_bskf2_split, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_pbs_mb2_split(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_bskf2_split, const uint64_t* d_in,
+                           int64_t B, const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_bskf2_split && d_in && d_luts && d_out, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    REQUIRE(p->l_pbs == 1 && p->k == 1 && (p->n & 1) == 0, "the split kernel covers k = 1, l_pbs = 1, even n");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_pbs_mb2_split(*p, d_bskf2_split, d_in, B, d_luts, d_lut_index, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 // ---- tensor-core keyswitch (ks_mma.cu)
 uint64_t fhe_b200_ksk_mma_bytes(const fhe_b200_pbs_params* p) {
     return (p && fhe::keyswitch_mma_supported(*p)) ? (uint64_t)fhe::keyswitch_mma_key_bytes(*p) : 0;

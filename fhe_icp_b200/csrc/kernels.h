@@ -112,6 +112,12 @@ cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, 
                            const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
                            cudaStream_t s);
 bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why);
+cudaError_t pbs_tables(const void** tables);
+
+// pbs_split.cu -- EXPERIMENTAL two-warps-per-polynomial multi-bit blind rotation (not validated on a GPU yet)
+cudaError_t launch_bsk2_fourier_split(const fhe_b200_pbs_params& p, const double* d_bskf2, double* d_bskf2_split, cudaStream_t s);
+cudaError_t launch_pbs_mb2_split(const fhe_b200_pbs_params& p, const double* d_bskf2_split, const uint64_t* d_in, int64_t B,
+                                 const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, cudaStream_t s);
 
 // probe.cu
 cudaError_t probe_fp64(int sm_count, double* tflops, cudaStream_t s);

@@ -1241,4 +1241,12 @@ cudaError_t launch_pbs(const fhe_b200_pbs_params& p, const double* d_bskf, const
     }
 }
 
+// the per-device twiddle + omega table, for kernels in other translation units (pbs_split.cu)
+cudaError_t pbs_tables(const void** tables) {
+    const cplx* tw = nullptr;
+    cudaError_t e = get_tables(&tw);
+    *tables = tw;
+    return e;
+}
+
 }  // namespace fhe

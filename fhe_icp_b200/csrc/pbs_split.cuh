@@ -58,31 +58,36 @@ FHE_HD void split_monomials_init(SplitMonomials& mo, const cplx* omega, int ea, 
     }
 }
 
-// pointwise stage of warp (t, h): out[kk] = G[lane + 32*(16h + kk)] of output polynomial t,
-//   G = F_t * sum_g c_g K_g[t][t] + F_t' * sum_g c_g K_g[t'][t],   F from the published half-spectra of both polynomials.
-// key_pair: the 32 frequency blocks of this pair of key bits.
+// one bin of the pointwise stage: G = F_t * sum_g c_g K_g[t][t] + F_t' * sum_g c_g K_g[t'][t] with the key block `blk`
+// of this bin's frequency block; advances the monomial factors to the next frequency block.
+FHE_HD void split_pointwise_bin(int t, int lane, const cplx fa, const cplx fo, const cplx* blk, SplitMonomials& mo,
+                                double& out_re, double& out_im) {
+    double kox = 0, koy = 0, ktx = 0, kty = 0;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        const cplx bt = blk[((g * 2 + t) * 2 + t) * 32 + lane];
+        const cplx bo = blk[((g * 2 + (1 - t)) * 2 + t) * 32 + lane];
+        kox = fma(mo.cx[g], bt.x, fma(-mo.cy[g], bt.y, kox));
+        koy = fma(mo.cx[g], bt.y, fma(mo.cy[g], bt.x, koy));
+        ktx = fma(mo.cx[g], bo.x, fma(-mo.cy[g], bo.y, ktx));
+        kty = fma(mo.cx[g], bo.y, fma(mo.cy[g], bo.x, kty));
+        const double nx = fma(mo.cx[g], mo.rx[g], fma(-mo.cy[g], mo.ry[g], mo.qx[g]));
+        mo.cy[g] = fma(mo.cx[g], mo.ry[g], fma(mo.cy[g], mo.rx[g], mo.ry[g]));
+        mo.cx[g] = nx;
+    }
+    out_re = fma(fa.x, kox, fma(-fa.y, koy, fma(fo.x, ktx, -(fo.y * kty))));
+    out_im = fma(fa.x, koy, fma(fa.y, kox, fma(fo.x, kty, fo.y * ktx)));
+}
+
+// pointwise stage of warp (t, h): out[kk] = G[lane + 32*(16h + kk)] of output polynomial t, F from the published
+// half-spectra of both polynomials.  key_pair: the 32 frequency blocks of this pair of key bits, in k1 order.
 FHE_HD void split_pointwise(int t, int h, int lane, const cplx* own0, const cplx* own1, const cplx* oth0, const cplx* oth1,
                             const cplx* key_pair, SplitMonomials& mo, double (&re)[16], double (&im)[16]) {
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
         const int k1 = 16 * h + kk;
-        const cplx* blk = key_pair + (size_t)k1 * MB2_BLOCK_ELEMS;
-        const cplx fa = split_bin(own0, own1, lane, k1), fo = split_bin(oth0, oth1, lane, k1);
-        double kox = 0, koy = 0, ktx = 0, kty = 0;
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
-            const cplx bt = blk[((g * 2 + t) * 2 + t) * 32 + lane];
-            const cplx bo = blk[((g * 2 + (1 - t)) * 2 + t) * 32 + lane];
-            kox = fma(mo.cx[g], bt.x, fma(-mo.cy[g], bt.y, kox));
-            koy = fma(mo.cx[g], bt.y, fma(mo.cy[g], bt.x, koy));
-            ktx = fma(mo.cx[g], bo.x, fma(-mo.cy[g], bo.y, ktx));
-            kty = fma(mo.cx[g], bo.y, fma(mo.cy[g], bo.x, kty));
-            const double nx = fma(mo.cx[g], mo.rx[g], fma(-mo.cy[g], mo.ry[g], mo.qx[g]));
-            mo.cy[g] = fma(mo.cx[g], mo.ry[g], fma(mo.cy[g], mo.rx[g], mo.ry[g]));
-            mo.cx[g] = nx;
-        }
-        re[kk] = fma(fa.x, kox, fma(-fa.y, koy, fma(fo.x, ktx, -(fo.y * kty))));
-        im[kk] = fma(fa.x, koy, fma(fa.y, kox, fma(fo.x, kty, fo.y * ktx)));
+        split_pointwise_bin(t, lane, split_bin(own0, own1, lane, k1), split_bin(oth0, oth1, lane, k1),
+                            key_pair + (size_t)k1 * MB2_BLOCK_ELEMS, mo, re[kk], im[kk]);
     }
 }
 

@@ -364,6 +364,33 @@ def pbs_mb2(p: N.PBSParams, bskf2: torch.Tensor, ct: torch.Tensor, luts: torch.T
     return out
 
 
+# ---- EXPERIMENTAL: two warps per polynomial (csrc/pbs_split.cu); not validated on a GPU yet, nothing dispatches to it
+def bsk2_fourier_split(p: N.PBSParams, bskf2: torch.Tensor) -> torch.Tensor:
+    """Re-slice the Fourier key of :func:`bsk2_to_fourier` into the order the split kernel streams (same size)."""
+    out = torch.empty_like(bskf2)
+    N.check(N.lib().fhe_b200_bsk2_fourier_split(_ctx(bskf2.device).handle, C.byref(p), _ptr(bskf2.contiguous()), _ptr(out),
+                                                _stream(bskf2.device)))
+    return out
+
+
+def pbs_mb2_split(p: N.PBSParams, bskf2_split: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor,
+                  lut_index: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    dev = ct.device
+    ct = ct.contiguous()
+    B = ct.shape[0]
+    assert ct.shape[1] == p.n + 1
+    luts = luts.to(device=dev, dtype=torch.int64).reshape(-1, p.N).contiguous()
+    if out is None:
+        out = torch.empty((B, p.k * p.N + 1), dtype=torch.int64, device=dev)
+    li = None
+    if lut_index is not None:
+        lut_index = lut_index.to(device=dev, dtype=torch.int32).contiguous()
+        li = _ptr(lut_index)
+    N.check(N.lib().fhe_b200_pbs_mb2_split(_ctx(dev).handle, C.byref(p), _ptr(bskf2_split), _ptr(ct), B, _ptr(luts), li,
+                                           _ptr(out), _stream(dev)))
+    return out
+
+
 def make_lut_poly(table, p_bits: int, N_poly: int, delta_out_log2: int) -> np.ndarray:
     """Accumulator polynomial of a p-bit table lookup (message + 1 padding bit): box m holds
     table[m] << delta_out_log2 and the polynomial is multiplied by X^(-box/2)."""

@@ -222,6 +222,15 @@ int fhe_b200_bsk2_to_fourier(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, co
 int fhe_b200_pbs_mb2(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
                      const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
                      const int32_t *d_lut_index, uint64_t *d_out, void *stream);
+/* EXPERIMENTAL -- not validated on a GPU yet: the same multi-bit blind rotation with two warps per
+ * polynomial (16 points per lane, 128 registers, 16 warps per SM).  Its arithmetic is checked by CPU emulation
+ * (tests/test_pbs_split_emul.py); nothing in the engine dispatches to it.  bsk2_fourier_split re-slices the Fourier
+ * key of fhe_b200_bsk2_to_fourier (same size) into the order this kernel streams; l_pbs = 1 only. */
+int fhe_b200_bsk2_fourier_split(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
+                                double *d_bskf2_split, void *stream);
+int fhe_b200_pbs_mb2_split(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2_split,
+                           const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
+                           const int32_t *d_lut_index, uint64_t *d_out, void *stream);
 /* 32-bit keyswitch ("KS32"): key rounded to the top 32 torus bits, u32 accumulation; d_scratch32 holds
  * B*(n+1) u32 words; the result is written as u64 words with the low half zero. */
 int fhe_b200_ksk_to_32(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_ksk,
