@@ -20,6 +20,8 @@ def emul(tmp_path_factory):
     lib = C.CDLL(str(so))
     lib.emul_pbs_mb2_split.restype = C.c_int
     lib.emul_pbs_mb2_split.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.emul_pbs_mb2_split_aliased.restype = C.c_int
+    lib.emul_pbs_mb2_split_aliased.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     return lib
 
 
@@ -43,3 +45,28 @@ def test_split_blind_rotation_equals_oracle_multibit_pbs(emul, O):
     assert np.log2(np.abs(diff).max() + 1) - 64 < -12
     err = (O.lwe_phase(S, got) - (table[msgs].astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
     assert np.log2(err.std() + 1) - 64 < -13.5
+
+
+def test_kernel_memory_plan_is_order_independent(emul, O):
+    """The kernel's shared-memory plan (csrc/pbs_split.cu): ONE region per polynomial reused as E|O tiles, half-spectra,
+    exchanged pointwise halves and inverse tile, with phase boundaries exactly where the kernel has its named barriers.
+    Whatever order the warps and lanes of a phase run in, the output is bit-identical to the un-aliased emulation --
+    a hand-over without a barrier would make it depend on the order."""
+    n = 8
+    p = O.make_params(n=n, k=1, N=2048, l_pbs=1, beta_pbs=23, log2_sigma_lwe=-30.0, log2_sigma_glwe=-51.6)
+    s, S = O.secret_key(3, 0, n), O.secret_key(3, 1, 2048)
+    of = O.bsk2_to_fourier(p, O.bsk2_gen(p, s, S, 4))
+    blocks = np.ascontiguousarray(of.reshape(of.shape[0], 3, 2, 1, 2, 32, 32, 2).transpose(0, 5, 1, 2, 3, 4, 6, 7))
+    msgs = np.array([0, 5, 9, 15])
+    ct = O.lwe_encrypt(s, msgs, 59, p.sigma_lwe_abs, enc_seed=6, ct_base=7, stride=n + 2)[:, : n + 1].copy()
+    table = (np.arange(16) * 3 + 1) % 16
+    lut = O.make_lut_poly(table, 4, 2048, 59)
+    for b in range(len(msgs)):
+        row = np.ascontiguousarray(ct[b])
+        want = np.zeros(2049, dtype=np.uint64)
+        assert emul.emul_pbs_mb2_split(blocks.ctypes.data, row.ctypes.data, n, 23, lut.ctypes.data, want.ctypes.data) == 0
+        for order in (0, 1, 2):
+            got = np.full(2049, 0xDEAD, dtype=np.uint64)
+            assert emul.emul_pbs_mb2_split_aliased(blocks.ctypes.data, row.ctypes.data, n, 23, lut.ctypes.data, order, got.ctypes.data) == 0
+            assert np.array_equal(got, want), (b, order)
+        assert (O.lwe_decrypt(S, want[None, :], 59) & 15)[0] == table[msgs[b]]
