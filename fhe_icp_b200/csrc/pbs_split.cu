@@ -86,7 +86,7 @@ __global__ void bsk2_split_reslice_kernel(const cplx* __restrict__ src, int64_t 
     const int64_t i = g / per_pair;
     const int r = (int)(g - i * per_pair);
     const int pos = r / nfft::MB2_BLOCK_ELEMS, e = r - pos * nfft::MB2_BLOCK_ELEMS;   // pos = 2*s + hh
-    const int k1 = 16 * (pos & 1) + (pos >> 1);
+    const int k1 = nfft::split_ring_block(pos);
     dst[g] = src[i * per_pair + (int64_t)k1 * nfft::MB2_BLOCK_ELEMS + e];
 }
 

@@ -20,6 +20,10 @@ namespace nfft {
 
 constexpr int MB2_BLOCK_ELEMS = 3 * 2 * 1 * 2 * 32;   // complex elements per frequency block (l_pbs = 1)
 
+// Ring order of the key: position pos = 2*s + hh of a pair (slice s = 0..15, block hh = 0..1 of the slice) holds
+// frequency block k1 = 16*hh + s, so that half h of every polynomial finds ITS block of step s in slice s.
+FHE_HD constexpr int split_ring_block(int pos) { return 16 * (pos & 1) + (pos >> 1); }
+
 // x mod 2^64, rounded to the nearest integer (pbs.cu's f64_to_torus)
 FHE_HD uint64_t split_f64_to_torus(double x) {
     const double r = rint(x * 0x1p-64);

@@ -181,3 +181,6 @@ extern "C" int emul_pbs_mb2_split_aliased(const double* key_blocks, const uint64
         }
     return 0;
 }
+
+// ring position -> frequency block (the re-slicing of fhe_b200_bsk2_fourier_split)
+extern "C" int emul_split_ring_block(int pos) { return split_ring_block(pos); }

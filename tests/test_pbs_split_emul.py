@@ -70,3 +70,13 @@ def test_kernel_memory_plan_is_order_independent(emul, O):
             assert emul.emul_pbs_mb2_split_aliased(blocks.ctypes.data, row.ctypes.data, n, 23, lut.ctypes.data, order, got.ctypes.data) == 0
             assert np.array_equal(got, want), (b, order)
         assert (O.lwe_decrypt(S, want[None, :], 59) & 15)[0] == table[msgs[b]]
+
+
+def test_ring_order_gives_each_half_its_block(emul):
+    """Slice s of a pair holds frequency blocks {s, 16 + s}: in step s half h reads block h of the slice and must find
+    k1 = 16h + s there; the 32 positions are a permutation of the 32 blocks."""
+    got = [emul.emul_split_ring_block(pos) for pos in range(32)]
+    assert sorted(got) == list(range(32))
+    for s in range(16):
+        for h in range(2):
+            assert got[2 * s + h] == 16 * h + s
