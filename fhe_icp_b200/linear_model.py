@@ -71,7 +71,20 @@ class FHECircuit:
         full = spec.circuit(inputset_q)
         self.clear_postprocess_bits = signed_bit_width(min(full.min(), -abs(zp_w) * amax * spec.d),
                                                        max(full.max(), abs(zp_w) * amax * spec.d))
-        self.graph = _Graph(self.inputset_bits)
+        # --- what graph.maximum_integer_bit_width() reports: the widest node of the FULL integer circuit
+        # q_X @ q_W - zp_W * sum(q_X) + q_bias over the inputset -- inputs, constants and every intermediate,
+        # as Concrete's graph does [EXT].  The bias constant is the wide node on the reference's configurations:
+        # it reproduces the published 12 / 20 / 28 bits of /root/reference/SESSION_REPORT.md:66-71
+        # (tests/test_host.py::test_published_circuit_bit_widths).  Crypto parameters are NOT sized from this
+        # number: the client adds zp_W * (.) and q_bias after decryption, so only `inputset_bits` /
+        # `guaranteed_bits` (the encrypted values) enter the parameter selection.
+        zsum = zp_w * ssum
+        nodes = [(inputset_q.min(), inputset_q.max()), (spec.q_weights.min(), spec.q_weights.max()),
+                 (dot.min(), dot.max()), (ssum.min(), ssum.max()), (zp_w, zp_w), (zsum.min(), zsum.max()),
+                 ((dot - zsum).min(), (dot - zsum).max()), (int(spec.q_bias), int(spec.q_bias)),
+                 (full.min(), full.max())]
+        self.circuit_bits = max(signed_bit_width(lo, hi) for lo, hi in nodes)
+        self.graph = _Graph(self.circuit_bits)
 
     # ------------------------------------------------------------------ device model
     def native_spec(self):
@@ -254,6 +267,21 @@ class SGDRegressor(LinearRegression):
         self.alpha, self.eta0, self.power_t, self.tol = alpha, eta0, power_t, tol
 
     def _fit_float(self, X, y):
+        # Concrete-ML's SGDRegressor is a wrapper around sklearn's: use that very fit when sklearn is importable
+        # (same coefficients as the reference for a given random_state); the plain SGD below is the stand-in.
+        try:
+            from sklearn.linear_model import SGDRegressor as _SkSGD
+        except ImportError:  # pragma: no cover
+            _SkSGD = None
+        if _SkSGD is not None:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")   # ConvergenceWarning at the reference's max_iter=20
+                sk = _SkSGD(max_iter=self.max_iter, random_state=self.random_state, alpha=self.alpha, eta0=self.eta0,
+                            power_t=self.power_t, tol=self.tol, fit_intercept=self.fit_intercept).fit(X, y)
+            self.solver_ = "sklearn.linear_model.SGDRegressor"
+            return np.asarray(sk.coef_, dtype=np.float64), float(np.ravel(sk.intercept_)[0])
+        self.solver_ = "builtin-sgd"
         rng = np.random.RandomState(self.random_state)
         X = X.astype(np.float64)
         y = y.astype(np.float64)

@@ -187,3 +187,31 @@ def test_top_indices_equals_full_stable_sort():
     ids = [f"d{i}" for i in range(7)]
     sc = np.array([0.5, 0.9, 0.5, 0.9, 0.1, 0.7, 0.5])
     assert rank_results(ids, sc, 4, 0.5) == [("d1", 0.9), ("d3", 0.9), ("d5", 0.7), ("d0", 0.5)]
+
+
+def _reference_quantization_dataset(n_samples=500, dim=128):
+    """The seeded generator of /root/reference/quantization_strategy.py:134-160 (seed 42, 256-d concatenation)."""
+    np.random.seed(42)
+    emb1 = np.random.randn(n_samples, dim).astype(np.float32)
+    emb1 = emb1 / np.linalg.norm(emb1, axis=1, keepdims=True)
+    emb2 = np.zeros_like(emb1)
+    for i in range(n_samples):
+        emb2[i] = emb1[i] + 0.1 * np.random.randn(dim) if i % 2 == 0 else np.random.randn(dim)
+    emb2 = emb2 / np.linalg.norm(emb2, axis=1, keepdims=True)
+    return np.hstack([emb1, emb2]), np.sum(emb1 * emb2, axis=1)
+
+
+@pytest.mark.parametrize("n_bits,published", [(4, 12), (8, 20), (12, 28)])
+def test_published_circuit_bit_widths(n_bits, published):
+    """The one numeric fixture the reference publishes for this path: `Circuit Max Bits` 12 / 20 / 28 at 4 / 8 / 12-bit
+    quantization (/root/reference/SESSION_REPORT.md:66-71), produced by quantization_strategy.py:34-59 on its seed-42
+    dataset (SGDRegressor(max_iter=20, random_state=42), compile(X_train), graph.maximum_integer_bit_width())."""
+    from fhe_icp_b200 import SGDRegressor
+    X, y = _reference_quantization_dataset()
+    X_train, y_train = X[:400], y[:400]
+    model = SGDRegressor(n_bits=n_bits, max_iter=20, random_state=42)
+    model.fit(X_train, y_train)
+    circuit = model.compile(X_train)
+    assert model.fhe_circuit.graph.maximum_integer_bit_width() == published
+    # the sizing input stays separate: only encrypted values enter the parameter selection
+    assert circuit.inputset_bits == published - 2 and circuit.guaranteed_bits >= circuit.inputset_bits

@@ -26,17 +26,22 @@ ct = E.keyswitch(p, ksk, ct_big)
 out = torch.empty((B, p.N + 1), dtype=torch.int64, device=dev)
 import os
 MB2 = os.environ.get("PBS_MB2", "0") == "1"
-if MB2:
+SPLIT = os.environ.get("PBS_SPLIT", "0") == "1"
+if MB2 or SPLIT:
     bskf2 = E.bsk2_to_fourier(p, E.bsk2_gen(p, s, S, 202))
+if SPLIT:
+    bskf2s = E.bsk2_fourier_split(p, bskf2)
 for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    if MB2:
+    if SPLIT:
+        E.pbs_mb2_split(p, bskf2s, ct, lut, out=out)
+    elif MB2:
         E.pbs_mb2(p, bskf2, ct, lut, out=out)
     else:
         E.pbs(p, bskf, ct, lut, out=out)
     e1.record(); torch.cuda.synchronize()
-    print(f"B={B} {'mb2' if MB2 else 'pbs'} {e0.elapsed_time(e1):.3f} ms -> {B / e0.elapsed_time(e1) * 1e3:.0f} PBS/s")
+    print(f"B={B} {'split' if SPLIT else 'mb2' if MB2 else 'pbs'} {e0.elapsed_time(e1):.3f} ms -> {B / e0.elapsed_time(e1) * 1e3:.0f} PBS/s")
 z = torch.zeros((B, p.N + 2), dtype=torch.int64, device=dev); z[:, : p.N + 1] = out
 dec = E.lwe_decrypt(S, z, 59).cpu().numpy() & 15
 print("correct:", bool(np.array_equal(dec, table[msgs])))
