@@ -2,9 +2,8 @@
 // step between TWO warps, so that a polynomial is transformed by 64 lanes holding 16 complex points each
 // (~64 data registers per thread instead of 128: four warps per scheduler instead of two).
 //
-// STATUS: index algebra only.  No kernel uses this header yet ("plan for the next round"); it is
-// __host__ __device__ and tests/test_fft_split_emul.py emulates the two warps on the CPU against numpy and against
-// the one-warp transform, so the redesign of the blind-rotation kernel can start from checked arithmetic.
+// Used by pbs_kernel_mb2_split (pbs_split.cu).  __host__ __device__: tests/test_fft_split_emul.py emulates the two
+// warps on the CPU against numpy and against the one-warp transform.
 //
 //   j = j1 + 32*j2 (time),  k = k2 + 32*k1 (frequency),  W = exp(2*pi*i/1024), w32 = W^32, omega = exp(2*pi*i/4096)
 //

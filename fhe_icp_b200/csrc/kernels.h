@@ -114,10 +114,11 @@ cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, 
 bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why);
 cudaError_t pbs_tables(const void** tables);
 
-// pbs_split.cu -- EXPERIMENTAL two-warps-per-polynomial multi-bit blind rotation (not validated on a GPU yet)
-cudaError_t launch_bsk2_fourier_split(const fhe_b200_pbs_params& p, const double* d_bskf2, double* d_bskf2_split, cudaStream_t s);
-cudaError_t launch_pbs_mb2_split(const fhe_b200_pbs_params& p, const double* d_bskf2_split, const uint64_t* d_in, int64_t B,
-                                 const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, cudaStream_t s);
+// pbs_split.cu -- two-warps-per-polynomial multi-bit blind rotation: the small-batch kernel (launch_pbs_mb2 dispatches
+// it for B <= 2 x SMs).  cts_per_cta: 1, 2, 4, or 0 = best measured form for the batch.
+cudaError_t launch_pbs_mb2_split(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
+                                 const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
+                                 int cts_per_cta, cudaStream_t s);
 
 // probe.cu
 cudaError_t probe_fp64(int sm_count, double* tflops, cudaStream_t s);

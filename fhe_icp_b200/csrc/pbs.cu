@@ -1006,8 +1006,11 @@ cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, 
     if (e != cudaSuccess) return e;
     const cplx* bskf2 = reinterpret_cast<const cplx*>(d_bskf2);
     if (p.l_pbs == 2) return launch_pbs_mb2_t<2, 2>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
-    if (B <= (int64_t)sm_count) return launch_pbs_mb2_t<1, 1>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
-    if (B <= 2 * (int64_t)sm_count) return launch_pbs_mb2_t<1, 2>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    // up to two ciphertexts per SM the two-warps-per-polynomial kernel (pbs_split.cu: four warps per ciphertext, one
+    // ciphertext per CTA) is 1.3-1.7x faster -- a lone ciphertext's step is latency-bound, so more warps per
+    // ciphertext win; from four ciphertexts per SM on, two fat warps per ciphertext are ahead (107 k vs 102 k PBS/s)
+    if (B <= 2 * (int64_t)sm_count && p.beta_pbs <= 31)
+        return launch_pbs_mb2_split(p, d_bskf2, d_in, B, d_luts, d_lut_index, d_out, sm_count, 1, s);
     return launch_pbs_mb2_t<1, 4>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
 }
 

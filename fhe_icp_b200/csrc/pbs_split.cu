@@ -1,13 +1,13 @@
-// pbs_split.cu -- multi-bit blind rotation with TWO WARPS PER POLYNOMIAL (16 complex points per lane, <= 128
-// registers per thread: four ciphertexts = 16 warps per SM, four warps per scheduler instead of two).
+// pbs_split.cu -- multi-bit blind rotation with TWO WARPS PER POLYNOMIAL (16 complex points per lane, 128 registers per
+// thread, no spills): four warps per ciphertext instead of the two of pbs_kernel_mb2 (pbs.cu).
 //
-// STATUS: EXPERIMENTAL, NOT VALIDATED ON A GPU.  The per-lane arithmetic (fft_split.cuh, pbs_split.cuh) is checked on
-// the CPU -- tests/test_fft_split_emul.py, tests/test_pbs_split_emul.py run a complete blind rotation through the same
-// functions and match the oracle's multi-bit PBS -- but the plumbing below (named barriers, the aliasing of the
-// shared-memory regions, tensor-memory offsets, the TMA ring) was written after this round's GPU budget was spent.
-// Nothing dispatches to it: it is reachable only through fhe_b200_pbs_mb2_split, its test is skipped unless
-// FHE_B200_EXPERIMENTAL=1, and DESIGN.md 6 lists it as the next round's first job.  pbs_kernel_mb2 (pbs.cu) remains
-// the product path.
+// Validated on a B200 (tests/test_gpu_pbs.py::test_multibit_pbs_split_kernel; same acceptance as pbs_kernel_mb2) and
+// measured (profiles/r2_ncu_pbs_split_v1.txt, profiles/r2_pbs_split_times.txt): with twice the warps per ciphertext it
+// is the SMALL-BATCH kernel -- one ciphertext per CTA, one or two CTAs per SM: batch 1 in 2.56 ms (pbs_kernel_mb2: 4.25),
+// batch 148 at 52 k PBS/s (31 k), batch 296 at 83 k (66 k) -- and launch_pbs_mb2 dispatches it for B <= 2 x SMs.  With
+// four ciphertexts per SM (16 warps) it reaches 102 k PBS/s against 107 k for pbs_kernel_mb2: the extra shared-memory
+// wavefronts of the split transposes (76 % of the pipe's peak) and 30 % more issued instructions eat what the
+// occupancy gains, so large batches stay on pbs_kernel_mb2.
 //
 // Warp w of a CTA: ciphertext w >> 2, polynomial t = (w >> 1) & 1, half h = w & 1.  Warp (t, h) owns the accumulator
 // coefficients j = lane + 32(2m + h) and j + 1024 (m = 0..15; tensor memory, 64 columns of its lane quadrant) and, in
@@ -18,8 +18,9 @@
 // with a 64-thread named barrier (the two warps of the polynomial) at every hand-over and the two 128-thread barriers
 // of the ciphertext around the pointwise stage, where the warps of one polynomial read the other's half-spectra.
 //
-// Key stream: the Fourier key is re-sliced so that ring slice s of a pair holds frequency blocks {s, 16 + s}
-// (fhe_b200_bsk2_fourier_split); all 16 warps walk the 16 slices of a step in lock step, half h using block h of each.
+// Key stream: the Fourier key of fhe_b200_bsk2_to_fourier is read as it is ([pair][32 frequency blocks][384 complex]);
+// ring slice s of a pair is two 6 KB bulk copies, frequency blocks s and 16 + s, so that all warps walk the 16 slices
+// of a step in lock step, half h using block h of each slice.
 #include "common.cuh"
 #include "kernels.h"
 #include "pbs_split.cuh"
@@ -77,22 +78,9 @@ __device__ __forceinline__ void ps_tmem_wait_st() { asm volatile("tcgen05.wait::
 
 }  // namespace
 
-// Fourier key by frequency block [pairs][32 blocks][384] -> ring order [pairs][16 slices][2 blocks][384]:
-// slice s = {block s, block 16 + s}
-__global__ void bsk2_split_reslice_kernel(const cplx* __restrict__ src, int64_t pairs, cplx* __restrict__ dst) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t per_pair = 32 * nfft::MB2_BLOCK_ELEMS;
-    if (g >= pairs * per_pair) return;
-    const int64_t i = g / per_pair;
-    const int r = (int)(g - i * per_pair);
-    const int pos = r / nfft::MB2_BLOCK_ELEMS, e = r - pos * nfft::MB2_BLOCK_ELEMS;   // pos = 2*s + hh
-    const int k1 = nfft::split_ring_block(pos);
-    dst[g] = src[i * per_pair + (int64_t)k1 * nfft::MB2_BLOCK_ELEMS + e];
-}
-
 template <int NCT>
 __global__ void __launch_bounds__(NCT * 128, 1)
-pbs_kernel_mb2_split(const cplx* __restrict__ bskf2s, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
+pbs_kernel_mb2_split(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
                      const uint64_t* __restrict__ luts, const int32_t* __restrict__ lut_index,
                      const cplx* __restrict__ g_tw, uint64_t* __restrict__ out) {
     using S = PsSmem;
@@ -124,6 +112,17 @@ pbs_kernel_mb2_split(const cplx* __restrict__ bskf2s, const uint64_t* __restrict
     constexpr uint32_t SLICE_BYTES = (uint32_t)(PS_SLICE_ELEMS * 16);
     const int pairs = n >> 1;
     const int total_slices = pairs * PS_SPI;
+    // ring slot <- slice q of the whole key walk: frequency blocks s and 16 + s of pair q / 16 (s = q % 16)
+    auto load_slice = [&](int slot, int q) {
+        const cplx* pair = bskf2 + (size_t)(q >> 4) * 32 * nfft::MB2_BLOCK_ELEMS;
+        cplx* dst = ring + (size_t)slot * PS_SLICE_ELEMS;
+        mbar_expect_tx(&bar_full[slot], SLICE_BYTES);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+            tma_load_1d(dst + (size_t)hh * nfft::MB2_BLOCK_ELEMS,
+                        pair + (size_t)nfft::split_ring_block(2 * (q & 15) + hh) * nfft::MB2_BLOCK_ELEMS, SLICE_BYTES / 2,
+                        &bar_full[slot]);
+    };
 
     const int64_t b = (int64_t)blockIdx.x * NCT + ctl;
     unsigned char* base = smem_raw + S::head_bytes + (size_t)ctl * S::per_ct(n);
@@ -170,10 +169,7 @@ pbs_kernel_mb2_split(const cplx* __restrict__ bskf2s, const uint64_t* __restrict
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (threadIdx.x == 0) {  // fill the ring
-        for (int q = 0; q < PS_SLICES && q < total_slices; ++q) {
-            mbar_expect_tx(&bar_full[q], SLICE_BYTES);
-            tma_load_1d(ring + (size_t)q * PS_SLICE_ELEMS, bskf2s + (size_t)q * PS_SLICE_ELEMS, SLICE_BYTES, &bar_full[q]);
-        }
+        for (int q = 0; q < PS_SLICES && q < total_slices; ++q) load_slice(q, q);
     }
 
     double re[16], im[16];
@@ -215,9 +211,7 @@ pbs_kernel_mb2_split(const cplx* __restrict__ bskf2s, const uint64_t* __restrict
                 if (done >= 0 && next < total_slices) {
                     const int ds = done % PS_SLICES;
                     mbar_wait(&bar_empty[ds], (uint32_t)((done / PS_SLICES) & 1));
-                    mbar_expect_tx(&bar_full[ds], SLICE_BYTES);
-                    tma_load_1d(ring + (size_t)ds * PS_SLICE_ELEMS, bskf2s + (size_t)next * PS_SLICE_ELEMS, SLICE_BYTES,
-                                &bar_full[ds]);
+                    load_slice(ds, next);
                 }
             }
         }
@@ -289,32 +283,35 @@ pbs_kernel_mb2_split(const cplx* __restrict__ bskf2s, const uint64_t* __restrict
     if (warp == 0) ps_tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-cudaError_t launch_bsk2_fourier_split(const fhe_b200_pbs_params& p, const double* d_bskf2, double* d_bskf2_split, cudaStream_t s) {
-    if (p.k != 1 || p.l_pbs != 1 || (p.n & 1) || p.N != PS_N) return cudaErrorInvalidValue;
-    const int64_t pairs = p.n / 2;
-    const int64_t total = pairs * 32 * nfft::MB2_BLOCK_ELEMS;
-    bsk2_split_reslice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const cplx*>(d_bskf2), pairs,
-                                                                            reinterpret_cast<cplx*>(d_bskf2_split));
+template <int NCT>
+static cudaError_t launch_split_t(const fhe_b200_pbs_params& p, const cplx* bskf2, const uint64_t* d_in, int64_t B,
+                                  const uint64_t* d_luts, const int32_t* d_lut_index, const cplx* tables, uint64_t* d_out,
+                                  cudaStream_t s) {
+    const size_t smem = PsSmem::total(p.n, NCT);
+    cudaError_t e = cudaFuncSetAttribute(pbs_kernel_mb2_split<NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((B + NCT - 1) / NCT);
+    pbs_kernel_mb2_split<NCT><<<grid, NCT * 128, smem, s>>>(bskf2, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tables, d_out);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_pbs_mb2_split(const fhe_b200_pbs_params& p, const double* d_bskf2_split, const uint64_t* d_in, int64_t B,
-                                 const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, cudaStream_t s) {
+// cts_per_cta: 1, 2 or 4; 0 = the best measured form for the batch (one ciphertext per CTA up to 2 x SMs, else four)
+cudaError_t launch_pbs_mb2_split(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
+                                 const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
+                                 int cts_per_cta, cudaStream_t s) {
     if (B <= 0) return cudaSuccess;
     if (p.k != 1 || p.l_pbs != 1 || (p.n & 1) || p.N != PS_N || p.beta_pbs < 1 || p.beta_pbs > 31) return cudaErrorInvalidValue;
     const void* tables = nullptr;
     cudaError_t e = pbs_tables(&tables);
     if (e != cudaSuccess) return e;
-    constexpr int NCT = 4;
-    const size_t smem = PsSmem::total(p.n, NCT);
-    e = cudaFuncSetAttribute(pbs_kernel_mb2_split<NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((B + NCT - 1) / NCT);
-    pbs_kernel_mb2_split<NCT><<<grid, NCT * 128, smem, s>>>(reinterpret_cast<const cplx*>(d_bskf2_split), d_in, B, p.n, p.beta_pbs,
-                                                           d_luts, d_lut_index, reinterpret_cast<const cplx*>(tables), d_out);
-    count_launch();
-    return cudaGetLastError();
+    const cplx* key = reinterpret_cast<const cplx*>(d_bskf2);
+    const cplx* tw = reinterpret_cast<const cplx*>(tables);
+    if (cts_per_cta == 0) cts_per_cta = B <= 2 * (int64_t)sm_count ? 1 : 4;
+    if (cts_per_cta == 1) return launch_split_t<1>(p, key, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    if (cts_per_cta == 2) return launch_split_t<2>(p, key, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    if (cts_per_cta == 4) return launch_split_t<4>(p, key, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace fhe

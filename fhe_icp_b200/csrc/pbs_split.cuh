@@ -2,9 +2,9 @@
 // (fft_split.cuh): digit extraction for the coefficients a warp owns, the pointwise stage on half-spectra, and the
 // accumulator update.  One decomposition level (l_pbs = 1), k = 1, N = 2048 -- the stated 4-bit set.
 //
-// STATUS: arithmetic only, used by no kernel yet (plan for the next round).  Everything here is
-// __host__ __device__; tests/test_pbs_split_emul.py runs a complete blind rotation through these functions on the CPU
-// (four emulated warps per ciphertext) and checks it against the oracle's multi-bit PBS.
+// Used by pbs_kernel_mb2_split (pbs_split.cu).  Everything here is __host__ __device__; tests/test_pbs_split_emul.py
+// runs a complete blind rotation through these functions on the CPU (four emulated warps per ciphertext) and checks it
+// against the oracle's multi-bit PBS.
 //
 // Ownership.  Warp (t, h) of a ciphertext: polynomial t of the accumulator, coefficients j = lane + 32*(2m + h)
 // and j + 1024 for m = 0..15 (register m of re / im).  In the pointwise stage the same warp produces the bins

@@ -364,17 +364,11 @@ def pbs_mb2(p: N.PBSParams, bskf2: torch.Tensor, ct: torch.Tensor, luts: torch.T
     return out
 
 
-# ---- EXPERIMENTAL: two warps per polynomial (csrc/pbs_split.cu); not validated on a GPU yet, nothing dispatches to it
-def bsk2_fourier_split(p: N.PBSParams, bskf2: torch.Tensor) -> torch.Tensor:
-    """Re-slice the Fourier key of :func:`bsk2_to_fourier` into the order the split kernel streams (same size)."""
-    out = torch.empty_like(bskf2)
-    N.check(N.lib().fhe_b200_bsk2_fourier_split(_ctx(bskf2.device).handle, C.byref(p), _ptr(bskf2.contiguous()), _ptr(out),
-                                                _stream(bskf2.device)))
-    return out
-
-
-def pbs_mb2_split(p: N.PBSParams, bskf2_split: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor,
-                  lut_index: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+# ---- two warps per polynomial (csrc/pbs_split.cu): the small-batch kernel pbs_mb2 dispatches for B <= 2 x SMs
+def pbs_mb2_split(p: N.PBSParams, bskf2: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor,
+                  lut_index: torch.Tensor | None = None, out: torch.Tensor | None = None, cts_per_cta: int = 0) -> torch.Tensor:
+    """:func:`pbs_mb2` through the two-warps-per-polynomial kernel with an explicit number of ciphertexts per CTA
+    (1, 2, 4; 0 = the dispatcher's choice).  Same key layout as :func:`pbs_mb2`."""
     dev = ct.device
     ct = ct.contiguous()
     B = ct.shape[0]
@@ -386,8 +380,8 @@ def pbs_mb2_split(p: N.PBSParams, bskf2_split: torch.Tensor, ct: torch.Tensor, l
     if lut_index is not None:
         lut_index = lut_index.to(device=dev, dtype=torch.int32).contiguous()
         li = _ptr(lut_index)
-    N.check(N.lib().fhe_b200_pbs_mb2_split(_ctx(dev).handle, C.byref(p), _ptr(bskf2_split), _ptr(ct), B, _ptr(luts), li,
-                                           _ptr(out), _stream(dev)))
+    N.check(N.lib().fhe_b200_pbs_mb2_split(_ctx(dev).handle, C.byref(p), _ptr(bskf2), _ptr(ct), B, _ptr(luts), li,
+                                           int(cts_per_cta), _ptr(out), _stream(dev)))
     return out
 
 

@@ -222,15 +222,14 @@ int fhe_b200_bsk2_to_fourier(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, co
 int fhe_b200_pbs_mb2(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
                      const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
                      const int32_t *d_lut_index, uint64_t *d_out, void *stream);
-/* EXPERIMENTAL -- not validated on a GPU yet: the same multi-bit blind rotation with two warps per
- * polynomial (16 points per lane, 128 registers, 16 warps per SM).  Its arithmetic is checked by CPU emulation
- * (tests/test_pbs_split_emul.py); nothing in the engine dispatches to it.  bsk2_fourier_split re-slices the Fourier
- * key of fhe_b200_bsk2_to_fourier (same size) into the order this kernel streams; l_pbs = 1 only. */
-int fhe_b200_bsk2_fourier_split(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
-                                double *d_bskf2_split, void *stream);
-int fhe_b200_pbs_mb2_split(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2_split,
+/* The same multi-bit blind rotation with two warps per polynomial (16 points per lane, 128 registers; pbs_split.cu):
+ * four warps per ciphertext make it the small-batch kernel -- fhe_b200_pbs_mb2 itself runs it for B <= 2 x SMs (batch 1:
+ * 2.6 ms instead of 4.2 ms; batch 148: 52 k instead of 31 k PBS/s).  This entry point exposes the choice of
+ * ciphertexts per CTA (1, 2 or 4; 0 = the dispatcher's choice) for the tests and the benchmark's batch sweep.  Same key
+ * (fhe_b200_bsk2_to_fourier), inputs and outputs as fhe_b200_pbs_mb2; k = 1, l_pbs = 1, n even. */
+int fhe_b200_pbs_mb2_split(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
                            const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
-                           const int32_t *d_lut_index, uint64_t *d_out, void *stream);
+                           const int32_t *d_lut_index, int32_t cts_per_cta, uint64_t *d_out, void *stream);
 /* 32-bit keyswitch ("KS32"): key rounded to the top 32 torus bits, u32 accumulation; d_scratch32 holds
  * B*(n+1) u32 words; the result is written as u64 words with the low half zero. */
 int fhe_b200_ksk_to_32(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_ksk,

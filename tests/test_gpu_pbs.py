@@ -298,18 +298,17 @@ def test_keyswitch_tensor_core_other_gadgets(O, cuda_dev):
         assert np.array_equal(_u64(out), O.keyswitch32(K.op, O.ksk_to_32(K.op, _u64(K.ksk)), _u64(rnd)))
 
 
-@pytest.mark.skipif(os.environ.get("FHE_B200_EXPERIMENTAL") != "1",
-                    reason="pbs_split.cu has not been validated on a GPU yet (DESIGN.md 6); set FHE_B200_EXPERIMENTAL=1 to run it")
-@pytest.mark.parametrize("which,B", [("toy", 16), ("toy", 3), ("p4", 16), ("p4", 2 * 148 + 5)])
-def test_multibit_pbs_split_kernel_experimental(O, cuda_dev, which, B):
-    """Same acceptance as test_multibit_pbs for the two-warps-per-polynomial kernel: every message maps to LUT[m],
-    phases agree with the oracle's multi-bit PBS within the noise bound.  The kernel's arithmetic already passes this
-    bar in CPU emulation (tests/test_pbs_split_emul.py)."""
+@pytest.mark.parametrize("which,B,nct", [("toy", 16, 4), ("toy", 3, 1), ("toy", 5, 2), ("p4", 16, 1), ("p4", 2 * 148 + 5, 4),
+                                         ("p4", 149, 2), ("p4", 7, 0)])
+def test_multibit_pbs_split_kernel(O, cuda_dev, which, B, nct):
+    """Same acceptance as test_multibit_pbs for the two-warps-per-polynomial kernel (pbs_split.cu), at every
+    ciphertexts-per-CTA form and with ragged last CTAs: every message maps to LUT[m], phases agree with the oracle-checked
+    pbs_kernel_mb2 within the noise bound.  nct = 0 is the dispatcher's choice; pbs_mb2 itself runs this kernel for
+    B <= 2 x SMs (covered by test_multibit_pbs' small batches)."""
     import torch
     from fhe_icp_b200 import engine as E
     d = {"toy": TOY, "p4": P4}[which]
     K = KeysMB2(O, cuda_dev, d)
-    split_key = E.bsk2_fourier_split(K.p, K.bskf2)
     rng = np.random.RandomState(B)
     msgs = rng.randint(0, 16, size=B)
     msgs[: min(B, 16)] = np.arange(16)[: min(B, 16)]
@@ -317,8 +316,13 @@ def test_multibit_pbs_split_kernel_experimental(O, cuda_dev, which, B):
                        stride=K.p.n + 2 - (K.p.n % 2))[:, : K.p.n + 1].contiguous()
     table = (np.arange(16) * 5 + 2) % 16
     lut = E.make_lut_poly(table, 4, K.p.N, 59)
-    got = _u64(E.pbs_mb2_split(K.p, split_key, ct, E.from_u64_numpy(lut, cuda_dev)))
+    lut_d = E.from_u64_numpy(lut, cuda_dev)
+    got = _u64(E.pbs_mb2_split(K.p, K.bskf2, ct, lut_d, cts_per_cta=nct))
     assert np.array_equal(O.lwe_decrypt(K.oS, got, 59) & 15, table[msgs])
-    want = _u64(E.pbs_mb2(K.p, K.bskf2, ct, E.from_u64_numpy(lut, cuda_dev)))
-    diff = (O.lwe_phase(K.oS, got) - O.lwe_phase(K.oS, want)).view(np.int64).astype(np.float64)
+    of = O.bsk2_to_fourier(K.op, O.bsk2_gen(K.op, K.os, K.oS, K.evk_seed))
+    ref = O.pbs_mb2(K.op, of, _u64(ct)[: min(B, 32)], lut)
+    diff = (O.lwe_phase(K.oS, got[: min(B, 32)]) - O.lwe_phase(K.oS, ref)).view(np.int64).astype(np.float64)
     assert np.log2(np.abs(diff).max() + 1) - 64 < -12
+    err = (O.lwe_phase(K.oS, got) - (table[msgs].astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
+    assert np.log2(err.std() + 1) - 64 < -13.5
+    assert E.pbs_mb2_split(K.p, K.bskf2, ct[:0], lut_d, cts_per_cta=nct).shape == (0, K.p.N + 1)

@@ -29,13 +29,12 @@ MB2 = os.environ.get("PBS_MB2", "0") == "1"
 SPLIT = os.environ.get("PBS_SPLIT", "0") == "1"
 if MB2 or SPLIT:
     bskf2 = E.bsk2_to_fourier(p, E.bsk2_gen(p, s, S, 202))
-if SPLIT:
-    bskf2s = E.bsk2_fourier_split(p, bskf2)
+NCT = int(os.environ.get("PBS_SPLIT_NCT", "0"))
 for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if SPLIT:
-        E.pbs_mb2_split(p, bskf2s, ct, lut, out=out)
+        E.pbs_mb2_split(p, bskf2, ct, lut, out=out, cts_per_cta=NCT)
     elif MB2:
         E.pbs_mb2(p, bskf2, ct, lut, out=out)
     else:
