@@ -32,7 +32,8 @@ sys.path.insert(0, str(ROOT))
 
 D_FEATURES = 128
 N_BITS = 8
-DATA_SEED, KEY_SEED, ENC_SEED, EVK_SEED = 20261018, 0x5EED0001, 0x5EED0002, 0x5EED0003
+# fixed seeds are an explicit opt-in for a reproducible benchmark; the library's defaults come from the OS CSPRNG
+DATA_SEED, KEY_SEED, ENC_SEED, EVK_SEED, NOISE_SEED = 20261018, 0x5EED0001, 0x5EED0002, 0x5EED0003, 0x5EED0004
 NCU_DRAM_BYTES_PER_DOC = 1475986  # (1.458192 GB read + 17.794 MB written) / 1000 documents, profiles/r1_ncu_lincomb_decrypt_v3.txt
 METRIC = "encrypted_comparisons_per_sec"
 UNIT = "comparisons/s"
@@ -41,7 +42,7 @@ UNIT = "comparisons/s"
 def build_model(device=None):
     from fhe_icp_b200 import FHESimilarityModel
     m = FHESimilarityModel(input_dim=D_FEATURES, n_bits=N_BITS, seed=DATA_SEED, key_seed=KEY_SEED, enc_seed=ENC_SEED,
-                           device=device, verbose=False)
+                           noise_seed=NOISE_SEED, ct_start=0, device=device, verbose=False)
     X, _ = m.train()
     m.compile(X[:10])
     return m, X
@@ -125,12 +126,20 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
 # ------------------------------------------------------------------------------------- CPU arm
 def cpu_reference(model, X, target_seconds: float, threads=None):
     """Oracle port of predict_encrypted on the host cores: quantize -> encrypt -> dot -> decrypt."""
     from oracle import oracle as O
-    if threads:
-        O.lib().orc_set_num_threads(int(threads))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm sets its own thread count (all host cores this
+    # process may run on) instead of inheriting that
+    O.lib().orc_set_num_threads(int(threads) if threads else host_cores())
     c = model.model.fhe_circuit
     spec = c.spec
     s = O.secret_key(c.key_seed, 2, c.lwe.n)
@@ -141,7 +150,8 @@ def cpu_reference(model, X, target_seconds: float, threads=None):
         Xr = np.tile(X, (reps, 1))[:rows] if reps > 1 else X[:rows]
         t0 = time.perf_counter()
         q = O.quantize(Xr, spec.input_q.scale, spec.input_q.zero_point, spec.input_q.offset, spec.input_q.n_bits)
-        ct = O.lwe_encrypt(s, q, c.lwe.shift, c.lwe.sigma_abs, c.enc_seed, ct_base=0, stride=c.lwe.stride)
+        ct = O.lwe_encrypt(s, q, c.lwe.shift, c.lwe.sigma_abs, c.enc_seed, ct_base=0, stride=c.lwe.stride,
+                           noise_seed=c.noise_seed)
         out = O.lincomb(ct.reshape(rows, spec.d, -1), W, c.lwe.n)
         m = O.lwe_decrypt(s, out, c.lwe.shift)
         qy = m[:, 0] - (int(spec.weight_q.zero_point) * m[:, 1] if c.two_outputs else 0) + int(spec.q_bias)
@@ -234,7 +244,10 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("FHE_B200_NCCL_DEBUG", "NONE")   # VERSION and WARN both print a banner on stdout; the contract is ONE JSON line
+        # the contract is ONE JSON line on stdout, and NCCL logs to stdout by default: its log (INFO unless the caller
+        # chose a level) goes to stderr instead, where a driver can still read the communicator / rank lines
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         # NCCL's stream (and the post stream below) run at high priority: the dot-product kernel keeps
         # thousands of CTAs queued, and equal-priority kernels only start once those are all dispatched
         opts = dist.ProcessGroupNCCL.Options()

@@ -52,7 +52,7 @@ class SimilaritySpec(C.Structure):
         ("x_zero_point", C.c_int64), ("x_offset", C.c_int64),
         ("w_zero_point", C.c_int64), ("q_bias", C.c_int64),
         ("out_scale", C.c_double), ("out_zero_point", C.c_int64),
-        ("key_seed", C.c_uint64),
+        ("key_seed", C.c_uint64), ("noise_seed", C.c_uint64),
     ]
 
 
@@ -135,14 +135,14 @@ SIGNATURES = {
     "fhe_b200_probe_fp64": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "fhe_b200_secret_key": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_int64, _vp, _vp]),
     "fhe_b200_lwe_encrypt": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, C.c_int32, C.c_double,
-                                       C.c_uint64, C.c_uint64, C.c_uint32, _vp, _vp]),
+                                       C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, _vp, _vp]),
     "fhe_b200_lwe_phase": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp]),
     "fhe_b200_lwe_decrypt": (C.c_int, [_vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, C.c_int32, _vp, _vp]),
     "fhe_b200_lincomb": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _vp, C.c_int32,
                                    C.POINTER(C.c_int64), C.c_int32, _vp, _vp]),
     "fhe_b200_accumulate": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
     "fhe_b200_glwe_encrypt_rows": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
-                                             C.c_uint64, _vp, _vp]),
+                                             C.c_uint64, C.c_uint64, _vp, _vp]),
     "fhe_b200_glwe_ggsw_dot": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, _vp, _vp]),
     "fhe_b200_glwe_decrypt_coeffs": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                                C.c_int32, _vp, _vp]),
@@ -155,7 +155,7 @@ SIGNATURES = {
     "fhe_b200_lwe_pair_addsub": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_uint64, _vp, _vp]),
     "fhe_b200_lwe_pair_diff_sum": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _vp, _vp]),
     "fhe_b200_lwe_encrypt_seeded": (C.c_int, [_vp, _vp, C.c_int32, _vp, C.c_int64, C.c_int32, C.c_double, C.c_uint64,
-                                              C.c_uint64, C.c_uint32, _vp, _vp]),
+                                              C.c_uint64, C.c_uint64, C.c_uint32, _vp, _vp]),
     "fhe_b200_lwe_expand_seeded": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64,
                                              C.c_uint32, _vp, _vp]),
     "fhe_b200_lincomb_seeded": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64,
@@ -185,6 +185,8 @@ SIGNATURES = {
     "fhe_b200_keyswitch_mma": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp]),
     "fhe_b200_pbs": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "fhe_b200_similarity_create": (C.c_int, [_vp, C.POINTER(SimilaritySpec), C.POINTER(C.c_int64), C.POINTER(_vp)]),
+    "fhe_b200_similarity_create_evaluator": (C.c_int, [_vp, C.POINTER(SimilaritySpec), C.POINTER(C.c_int64), C.POINTER(_vp)]),
+    "fhe_b200_similarity_wire32_supported": (C.c_int, [_vp]),
     "fhe_b200_similarity_destroy": (C.c_int, [_vp]),
     "fhe_b200_similarity_predict_host": (C.c_int, [_vp, C.POINTER(C.c_float), C.c_int64, C.c_uint64, C.c_uint64,
                                                    C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -212,7 +214,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.fhe_b200_abi_version() != 1:
+        if L.fhe_b200_abi_version() != 2:
             raise RuntimeError("libfhe_b200.so ABI version mismatch")
         _LIB = L
     return _LIB

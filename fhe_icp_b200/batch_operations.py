@@ -223,7 +223,7 @@ class BatchProcessor:
         if self.fhe == "both":
             scores = self._pair_engine().similarity(query_reduced, self.storage.matrix())
         else:
-            X = (query_reduced[None, :] * self.storage.matrix()).astype(np.float32)
+            X = query_reduced[None, :] * self.storage.matrix()    # dtype as in the reference (batch_operations.py:273)
             scores = self._predict(X)
         return rank_results([d["doc_id"] for d in all_docs], scores, top_k, min_similarity)
 
@@ -239,13 +239,15 @@ class BatchProcessor:
         from .encrypted_compare import (PACKED_OUT_SHIFT, PACKED_SCORE_BITS, EncryptedCompare, EncryptedThreshold)
         eng = self._pair_engine()
         if getattr(self, "_thr", None) is None:   # bootstrapping + keyswitching keys under the same big key
-            pbs_side = EncryptedCompare(input_dim=eng.d, key_seed=eng.key_seed, device=self.device).keygen()
+            pbs_side = EncryptedCompare(input_dim=eng.d, key_seed=eng.key_seed, noise_seed=eng.noise_seed,
+                                        enc_seed=eng.enc_seed, device=self.device).keygen()
+            pbs_side.ids = eng.ids          # one id allocator per key set: ids never repeat across the engines
             self._thr = EncryptedThreshold(pbs_side, score_bits=PACKED_SCORE_BITS, out_shift=PACKED_OUT_SHIFT,
                                            scale=eng.scale)
         q = self.reducer.transform(self.embedder.get_embedding(query_text).reshape(1, -1))[0]
         n_docs = len(all_docs)
-        products = eng.scores(eng.encrypt_query(eng.quantize(q), enc_seed=2),
-                              eng.encrypt_documents(eng.quantize(self.storage.matrix()), enc_seed=1))
+        products = eng.scores(eng.encrypt_query(eng.quantize(q)),           # fresh ciphertext ids on every call
+                              eng.encrypt_documents(eng.quantize(self.storage.matrix())))
         scores = eng.scores_as_lwe(products)[:n_docs].contiguous()
         bits = self._thr.decrypt(self._thr.ge(scores, self._thr.threshold_to_int(min_similarity)))
         return [d["doc_id"] for d, b in zip(all_docs, bits) if b]

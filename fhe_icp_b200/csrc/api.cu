@@ -10,6 +10,7 @@
 #include <new>
 #include <string>
 
+#include <cmath>
 #include "kernels.h"
 
 namespace {
@@ -91,6 +92,8 @@ struct fhe_b200_similarity {
     fhe_b200_similarity_spec spec;
     int M;
     bool second_is_sum;
+    bool has_key = false;            // false: evaluator-only handle (server side), no secret material at all
+    bool wire32_ok = false;          // the 2^64 -> 2^32 modulus switch of the scores keeps p_error (see create)
     uint8_t* d_key = nullptr;
     uint32_t* d_key_bits = nullptr;  // the same key, 32 bits per word (fused decrypt kernel)
     int64_t* d_W = nullptr;  // [M][d]
@@ -176,8 +179,8 @@ static int check_lwe_shape(int32_t n, int64_t stride, const char* fn) {
 }
 
 int fhe_b200_lwe_encrypt(fhe_b200_ctx* ctx, const uint8_t* d_key, int32_t n, int64_t stride, const int64_t* d_msgs,
-                         int64_t count, int32_t shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base,
-                         uint32_t purpose, uint64_t* d_ct, void* stream) {
+                         int64_t count, int32_t shift, double sigma_abs, uint64_t enc_seed, uint64_t noise_seed,
+                         uint64_t ct_base, uint32_t purpose, uint64_t* d_ct, void* stream) {
     REQUIRE(ctx, "null ctx");
     REQUIRE(count >= 0, "negative count");
     if (count == 0) return FHE_B200_OK;
@@ -185,7 +188,7 @@ int fhe_b200_lwe_encrypt(fhe_b200_ctx* ctx, const uint8_t* d_key, int32_t n, int
     REQUIRE(shift >= 0 && shift < 64 && purpose < 256, "shift must be in [0,64), purpose < 256");
     if (int r = check_lwe_shape(n, stride, __func__)) return r;
     CU(cudaSetDevice(ctx->device));
-    CU(fhe::launch_lwe_encrypt(d_key, n, stride, d_msgs, count, shift, sigma_abs, enc_seed, ct_base, purpose, d_ct,
+    CU(fhe::launch_lwe_encrypt(d_key, n, stride, d_msgs, count, shift, sigma_abs, enc_seed, noise_seed, ct_base, purpose, d_ct,
                                (cudaStream_t)stream));
     return FHE_B200_OK;
 }
@@ -234,15 +237,15 @@ int fhe_b200_lincomb(fhe_b200_ctx* ctx, const uint64_t* d_ct, int64_t B, int32_t
 }
 
 int fhe_b200_lwe_encrypt_seeded(fhe_b200_ctx* ctx, const uint8_t* d_key, int32_t n, const int64_t* d_msgs, int64_t count,
-                                int32_t shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
-                                uint64_t* d_bodies, void* stream) {
+                                int32_t shift, double sigma_abs, uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base,
+                                uint32_t purpose, uint64_t* d_bodies, void* stream) {
     REQUIRE(ctx, "null ctx");
     REQUIRE(count >= 0, "negative count");
     if (count == 0) return FHE_B200_OK;
     REQUIRE(d_key && d_msgs && d_bodies, "null device pointer");
     REQUIRE(n > 0 && shift >= 0 && shift < 64 && purpose < 256, "bad parameters");
     CU(cudaSetDevice(ctx->device));
-    CU(fhe::launch_lwe_encrypt_seeded(d_key, n, d_msgs, count, shift, sigma_abs, enc_seed, ct_base, purpose, d_bodies,
+    CU(fhe::launch_lwe_encrypt_seeded(d_key, n, d_msgs, count, shift, sigma_abs, enc_seed, noise_seed, ct_base, purpose, d_bodies,
                                       (cudaStream_t)stream));
     return FHE_B200_OK;
 }
@@ -325,7 +328,7 @@ int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx* ctx, const uint64_t* d_in, int64_t 
 static int check_pbs_params(const fhe_b200_pbs_params* p, const char* fn);
 int fhe_b200_glwe_encrypt_rows(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const uint8_t* d_S_big,
                                const int64_t* d_msgs, int64_t rows, int64_t msg_stride, int32_t mode, int32_t shift,
-                               uint64_t seed, uint64_t id_base, uint64_t* d_out, void* stream) {
+                               uint64_t seed, uint64_t noise_seed, uint64_t id_base, uint64_t* d_out, void* stream) {
     REQUIRE(ctx && p && d_S_big && d_msgs && d_out, "null argument");
     if (int r = check_pbs_params(p, __func__)) return r;
     REQUIRE(mode == 0 || mode == 1, "mode must be 0 (vectors) or 1 (GGSW of one polynomial)");
@@ -334,7 +337,7 @@ int fhe_b200_glwe_encrypt_rows(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, 
             "mode 0 needs msg_stride >= N; mode 1 needs rows == (k+1)*l_pbs");
     if (rows == 0) return FHE_B200_OK;
     CU(cudaSetDevice(ctx->device));
-    CU(fhe::launch_glwe_encrypt_rows(*p, d_S_big, d_msgs, rows, msg_stride, mode, shift, seed, id_base, d_out,
+    CU(fhe::launch_glwe_encrypt_rows(*p, d_S_big, d_msgs, rows, msg_stride, mode, shift, seed, noise_seed, id_base, d_out,
                                      (cudaStream_t)stream));
     return FHE_B200_OK;
 }
@@ -615,8 +618,11 @@ int fhe_b200_pbs(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* 
 }
 
 // ------------------------------------------------------------------------------- similarity model
-int fhe_b200_similarity_create(fhe_b200_ctx* ctx, const fhe_b200_similarity_spec* spec, const int64_t* h_q_w,
-                               fhe_b200_similarity** sim) {
+#define REQUIRE_CLIENT(s) \
+    REQUIRE((s)->has_key, "evaluator-only handle: it holds no secret key, so it cannot encrypt or decrypt")
+
+static int similarity_create_impl(fhe_b200_ctx* ctx, const fhe_b200_similarity_spec* spec, const int64_t* h_q_w,
+                                  bool with_key, fhe_b200_similarity** sim) {
     REQUIRE(ctx && spec && h_q_w && sim, "null argument");
     *sim = nullptr;
     REQUIRE(spec->d > 0 && spec->d <= 4096, "d must be in [1,4096]");
@@ -637,7 +643,19 @@ int fhe_b200_similarity_create(fhe_b200_ctx* ctx, const fhe_b200_similarity_spec
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if ((e = cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, hi)) != cudaSuccess) goto bad;
     }
-    if ((e = cudaMalloc(&s->d_key, (size_t)spec->n)) != cudaSuccess) goto bad;
+    s->has_key = with_key;
+    {   // 32-bit wire form: the modulus switch adds sum_i s_i r_i + r_b with r uniform in +-2^31 (variance 2^64/12 each,
+        // ~n/2 key bits set) to the output noise sigma^2 * max(||q_W||^2, d).  It is allowed only while the total still
+        // decodes with the compile-time failure probability 2^-40 (z = 7.15):  z * sqrt(var) < Delta / 2.
+        long double w2 = 0;
+        for (int i = 0; i < spec->d; ++i) w2 += (long double)h_q_w[i] * (long double)h_q_w[i];
+        if (spec->two_outputs && w2 < spec->d) w2 = spec->d;
+        const long double var = (long double)spec->sigma_abs * spec->sigma_abs * w2 +
+                                ((long double)spec->n / 2 + 1) * 18446744073709551616.0L / 12.0L;
+        s->wire32_ok = spec->shift >= 32 && spec->shift <= 63 &&
+                       7.15L * sqrtl(var) < ldexpl(1.0L, spec->shift - 1);
+    }
+    if (!with_key) { s->spec.key_seed = 0; s->spec.noise_seed = 0; }   // an evaluator never stores client secrets
     if ((e = cudaMalloc(&s->d_W, sizeof(int64_t) * (size_t)s->M * spec->d)) != cudaSuccess) goto bad;
     if ((e = cudaMemcpyAsync(s->d_W, h_q_w, sizeof(int64_t) * spec->d, cudaMemcpyHostToDevice, s->stream)) != cudaSuccess) goto bad;
     if (s->M == 2) {
@@ -649,9 +667,12 @@ int fhe_b200_similarity_create(fhe_b200_ctx* ctx, const fhe_b200_similarity_spec
         delete[] ones;
         if (e != cudaSuccess) goto bad;
     }
-    if ((e = fhe::launch_secret_key(spec->key_seed, 2, spec->n, s->d_key, s->stream)) != cudaSuccess) goto bad;
-    if ((e = cudaMalloc(&s->d_key_bits, sizeof(uint32_t) * ((size_t)spec->n / 32 + 1))) != cudaSuccess) goto bad;
-    if ((e = fhe::launch_pack_key(s->d_key, spec->n, s->d_key_bits, s->stream)) != cudaSuccess) goto bad;
+    if (with_key) {
+        if ((e = cudaMalloc(&s->d_key, (size_t)spec->n)) != cudaSuccess) goto bad;
+        if ((e = fhe::launch_secret_key(spec->key_seed, 2, spec->n, s->d_key, s->stream)) != cudaSuccess) goto bad;
+        if ((e = cudaMalloc(&s->d_key_bits, sizeof(uint32_t) * ((size_t)spec->n / 32 + 1))) != cudaSuccess) goto bad;
+        if ((e = fhe::launch_pack_key(s->d_key, spec->n, s->d_key_bits, s->stream)) != cudaSuccess) goto bad;
+    }
     if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) goto bad;
     *sim = s;
     return FHE_B200_OK;
@@ -659,6 +680,18 @@ bad:
     fhe_b200_similarity_destroy(s);
     return cuda_fail(e, "similarity_create");
 }
+
+int fhe_b200_similarity_create(fhe_b200_ctx* ctx, const fhe_b200_similarity_spec* spec, const int64_t* h_q_w,
+                               fhe_b200_similarity** sim) {
+    return similarity_create_impl(ctx, spec, h_q_w, true, sim);
+}
+
+int fhe_b200_similarity_create_evaluator(fhe_b200_ctx* ctx, const fhe_b200_similarity_spec* spec, const int64_t* h_q_w,
+                                         fhe_b200_similarity** sim) {
+    return similarity_create_impl(ctx, spec, h_q_w, false, sim);
+}
+
+int fhe_b200_similarity_wire32_supported(const fhe_b200_similarity* s) { return s && s->wire32_ok ? 1 : 0; }
 
 int fhe_b200_similarity_destroy(fhe_b200_similarity* s) {
     if (!s) return FHE_B200_OK;
@@ -683,6 +716,7 @@ int fhe_b200_similarity_destroy(fhe_b200_similarity* s) {
 int fhe_b200_similarity_encrypt(fhe_b200_similarity* s, const float* d_X, int64_t B, uint64_t enc_seed,
                                 uint64_t ct_base, uint64_t* d_ct, void* stream) {
     REQUIRE(s, "null model");
+    REQUIRE_CLIENT(s);
     REQUIRE(B >= 0, "negative batch");
     if (B == 0) return FHE_B200_OK;
     REQUIRE(d_X && d_ct, "null device pointer");
@@ -694,7 +728,7 @@ int fhe_b200_similarity_encrypt(fhe_b200_similarity* s, const float* d_X, int64_
     const int64_t qmin = -sp.x_offset, qmax = (1LL << sp.n_bits) - 1 - sp.x_offset;
     CU(fhe::launch_quantize(d_X, cnt, sp.x_scale, sp.x_zero_point, qmin, qmax, (int64_t*)s->q.p, st));
     CU(fhe::launch_lwe_encrypt(s->d_key, sp.n, sp.stride, (const int64_t*)s->q.p, cnt, sp.shift, sp.sigma_abs,
-                               enc_seed, ct_base, FHE_B200_PUR_INPUT, d_ct, st));
+                               enc_seed, sp.noise_seed, ct_base, FHE_B200_PUR_INPUT, d_ct, st));
     return FHE_B200_OK;
 }
 
@@ -713,6 +747,7 @@ int fhe_b200_similarity_run(fhe_b200_similarity* s, const uint64_t* d_ct, int64_
 int fhe_b200_similarity_decrypt(fhe_b200_similarity* s, const uint64_t* d_out, int64_t B, double* d_y,
                                 int64_t* d_q_y, void* stream) {
     REQUIRE(s, "null model");
+    REQUIRE_CLIENT(s);
     REQUIRE(B >= 0, "negative batch");
     if (B == 0) return FHE_B200_OK;
     REQUIRE(d_out && (d_y || d_q_y), "null device pointer");
@@ -727,6 +762,7 @@ int fhe_b200_similarity_decrypt(fhe_b200_similarity* s, const uint64_t* d_out, i
 int fhe_b200_similarity_encrypt_seeded(fhe_b200_similarity* s, const float* d_X, int64_t B, uint64_t enc_seed,
                                        uint64_t ct_base, uint64_t* d_bodies, void* stream) {
     REQUIRE(s, "null model");
+    REQUIRE_CLIENT(s);
     REQUIRE(B >= 0, "negative batch");
     if (B == 0) return FHE_B200_OK;
     REQUIRE(d_X && d_bodies, "null device pointer");
@@ -736,7 +772,7 @@ int fhe_b200_similarity_encrypt_seeded(fhe_b200_similarity* s, const float* d_X,
     const int64_t cnt = B * sp.d;
     const int64_t qmin = -sp.x_offset, qmax = (1LL << sp.n_bits) - 1 - sp.x_offset;
     CU(fhe::launch_lwe_encrypt_seeded_float(s->d_key, sp.n, d_X, cnt, sp.x_scale, sp.x_zero_point, qmin, qmax, sp.shift,
-                                            sp.sigma_abs, enc_seed, ct_base, FHE_B200_PUR_INPUT, d_bodies, st));
+                                            sp.sigma_abs, enc_seed, sp.noise_seed, ct_base, FHE_B200_PUR_INPUT, d_bodies, st));
     return FHE_B200_OK;
 }
 
@@ -756,6 +792,7 @@ int fhe_b200_similarity_run_seeded(fhe_b200_similarity* s, const uint64_t* d_bod
 int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity* s, const float* h_X, int64_t B, uint64_t enc_seed,
                                             uint64_t ct_base, double* h_y, int64_t* h_q_y) {
     REQUIRE(s, "null model");
+    REQUIRE_CLIENT(s);
     REQUIRE(B >= 0, "negative batch");
     if (B == 0) return FHE_B200_OK;
     REQUIRE(h_X && (h_y || h_q_y), "null host pointer");
@@ -787,11 +824,13 @@ int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity* s, const float*
 int fhe_b200_similarity_decrypt32(fhe_b200_similarity* s, const uint32_t* d_out32, int64_t B, double* d_y,
                                   int64_t* d_q_y, void* stream) {
     REQUIRE(s, "null model");
+    REQUIRE_CLIENT(s);
     REQUIRE(B >= 0, "negative batch");
     if (B == 0) return FHE_B200_OK;
     REQUIRE(d_out32 && (d_y || d_q_y), "null device pointer");
     const auto& sp = s->spec;
-    REQUIRE(sp.shift >= 32, "the 32-bit wire form needs log2(Delta) >= 32");
+    REQUIRE(s->wire32_ok, "the 32-bit wire form would push the decoding failure probability above 2^-40 at these "
+                          "parameters (log2(Delta) too small for the modulus-switch noise): use the 64-bit scores");
     CU(cudaSetDevice(s->ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     CU(fhe::launch_similarity_decrypt(s->d_key_bits, sp.n, sp.stride, d_out32, true, B, s->M, sp.shift - 32,
@@ -863,7 +902,8 @@ int fhe_b200_similarity_run_push(fhe_b200_similarity* s, const uint64_t* d_ct, i
     REQUIRE(d_ct, "null device pointer");
     if (int r = check_push(push)) return r;
     const auto& sp = s->spec;
-    REQUIRE(sp.shift >= 32, "the 32-bit wire form needs log2(Delta) >= 32");
+    REQUIRE(s->wire32_ok, "the 32-bit wire form would push the decoding failure probability above 2^-40 at these "
+                          "parameters (log2(Delta) too small for the modulus-switch noise): use the 64-bit scores");
     CU(cudaSetDevice(s->ctx->device));
     CU(fhe::launch_lincomb_push(d_ct, B, sp.d, sp.n, sp.stride, s->d_W, s->M, s->second_is_sum, 0, 0, sp.shift, *push,
                                 (cudaStream_t)stream));
@@ -877,7 +917,8 @@ int fhe_b200_similarity_run_seeded_push(fhe_b200_similarity* s, const uint64_t* 
     REQUIRE(d_bodies, "null device pointer");
     if (int r = check_push(push)) return r;
     const auto& sp = s->spec;
-    REQUIRE(sp.shift >= 32, "the 32-bit wire form needs log2(Delta) >= 32");
+    REQUIRE(s->wire32_ok, "the 32-bit wire form would push the decoding failure probability above 2^-40 at these "
+                          "parameters (log2(Delta) too small for the modulus-switch noise): use the 64-bit scores");
     CU(cudaSetDevice(s->ctx->device));
     CU(fhe::launch_lincomb_seeded_push(d_bodies, B, sp.d, sp.n, sp.stride, enc_seed, ct_base, FHE_B200_PUR_INPUT, s->d_W,
                                        s->M, s->second_is_sum, 0, 0, sp.shift, *push, (cudaStream_t)stream));
@@ -909,6 +950,7 @@ int fhe_b200_peer_signal(fhe_b200_ctx* ctx, uint64_t* const* d_flag_ptrs, int32_
 int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, int64_t B, uint64_t enc_seed,
                                      uint64_t ct_base, double* h_y, int64_t* h_q_y) {
     REQUIRE(s, "null model");
+    REQUIRE_CLIENT(s);
     REQUIRE(B >= 0, "negative batch");
     if (B == 0) return FHE_B200_OK;
     REQUIRE(h_X && (h_y || h_q_y), "null host pointer");
@@ -966,12 +1008,12 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
         if (k >= 2) CU(cudaStreamWaitEvent(s->enc_stream, s->ev_free[k & 1], 0));   // buffer consumed by chunk k-2
         if (overlap)   // short-lived CTAs: the dot product of chunk k-1 shares the SMs with this
             CU(fhe::launch_lwe_encrypt_packed(s->d_key_bits, sp.n, sp.stride, (const int64_t*)s->q.p + r0 * sp.d, rows * sp.d,
-                                              sp.shift, sp.sigma_abs, enc_seed, ct_base + (uint64_t)(r0 * sp.d),
-                                              FHE_B200_PUR_INPUT, ctb, s->enc_stream));
+                                              sp.shift, sp.sigma_abs, enc_seed, sp.noise_seed,
+                                              ct_base + (uint64_t)(r0 * sp.d), FHE_B200_PUR_INPUT, ctb, s->enc_stream));
         else
             CU(fhe::launch_lwe_encrypt(s->d_key, sp.n, sp.stride, (const int64_t*)s->q.p + r0 * sp.d, rows * sp.d, sp.shift,
-                                       sp.sigma_abs, enc_seed, ct_base + (uint64_t)(r0 * sp.d), FHE_B200_PUR_INPUT, ctb,
-                                       s->enc_stream));
+                                       sp.sigma_abs, enc_seed, sp.noise_seed, ct_base + (uint64_t)(r0 * sp.d),
+                                       FHE_B200_PUR_INPUT, ctb, s->enc_stream));
         CU(cudaEventRecord(s->ev_enc[k & 1], s->enc_stream));
         CU(cudaStreamWaitEvent(st, s->ev_enc[k & 1], 0));
         CU(fhe::launch_lincomb(ctb, rows, sp.d, sp.n, sp.stride, s->d_W, s->M, s->second_is_sum, 0, 0, sp.shift,

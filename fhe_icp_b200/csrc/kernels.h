@@ -11,23 +11,23 @@ void count_launch(int n = 1);  // api.cu: bumps the per-process launch counter
 // lwe.cu
 cudaError_t launch_secret_key(uint64_t key_seed, uint32_t key_id, int64_t dim, uint8_t* d_key, cudaStream_t s);
 cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
-                               int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
-                               uint64_t* d_ct, cudaStream_t s);
+                               int shift, double sigma_abs, uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base,
+                               uint32_t purpose, uint64_t* d_ct, cudaStream_t s);
 cudaError_t launch_lwe_encrypt_packed(const uint32_t* d_kbits, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
-                                      int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
-                                      uint64_t* d_ct, cudaStream_t s);
+                                      int shift, double sigma_abs, uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base,
+                                      uint32_t purpose, uint64_t* d_ct, cudaStream_t s);
 cudaError_t launch_lwe_phase(const uint8_t* d_key, int n, int64_t stride, const uint64_t* d_ct, int64_t count,
                              int shift, bool decode, uint64_t* d_out, cudaStream_t s);
 cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_t stride, const int64_t* d_W, int M,
                            bool second_is_sum, int64_t bias0, int64_t bias1, int shift, uint64_t* d_out,
                            cudaStream_t s);
 cudaError_t launch_lwe_encrypt_seeded(const uint8_t* d_key, int n, const int64_t* d_msgs, int64_t count, int shift,
-                                      double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
-                                      uint64_t* d_bodies, cudaStream_t s);
+                                      double sigma_abs, uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base,
+                                      uint32_t purpose, uint64_t* d_bodies, cudaStream_t s);
 cudaError_t launch_lwe_encrypt_seeded_float(const uint8_t* d_key, int n, const float* d_X, int64_t count, double scale,
                                             int64_t zp, int64_t qmin, int64_t qmax, int shift, double sigma_abs,
-                                            uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, uint64_t* d_bodies,
-                                            cudaStream_t s);
+                                            uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base, uint32_t purpose,
+                                            uint64_t* d_bodies, cudaStream_t s);
 cudaError_t launch_lwe_expand_seeded(const uint64_t* d_bodies, int64_t count, int n, int64_t stride, uint64_t enc_seed,
                                      uint64_t ct_base, uint32_t purpose, uint64_t* d_out, cudaStream_t s);
 cudaError_t launch_lincomb_seeded(const uint64_t* d_bodies, int64_t B, int d, int n, int64_t stride, uint64_t enc_seed,
@@ -50,7 +50,7 @@ cudaError_t launch_accumulate(uint64_t* d_acc, const uint64_t* d_x, int64_t word
 cudaError_t launch_lwe_pair_addsub(const uint64_t* d_q, const uint64_t* d_y, int64_t B, int d, int words,
                                    int64_t in_stride, uint64_t offset, uint64_t* d_out, cudaStream_t s);
 cudaError_t launch_glwe_encrypt_rows(const fhe_b200_pbs_params& p, const uint8_t* d_S_big, const int64_t* d_msgs,
-                                     int64_t rows, int64_t msg_stride, int mode, int shift, uint64_t seed,
+                                     int64_t rows, int64_t msg_stride, int mode, int shift, uint64_t seed, uint64_t noise_seed,
                                      uint64_t id_base, uint64_t* d_out, cudaStream_t s);
 cudaError_t launch_glwe_dot(const fhe_b200_pbs_params& p, const double* d_ggswf, const uint64_t* d_in, int64_t G,
                             uint64_t* d_out, int sm_count, cudaStream_t s);

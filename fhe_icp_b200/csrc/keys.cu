@@ -126,7 +126,7 @@ bsk_gen_kernel(const uint8_t* __restrict__ s_small, const uint8_t* __restrict__ 
 __global__ void __launch_bounds__(BSK_THREADS)
 glwe_encrypt_rows_kernel(const uint8_t* __restrict__ S_big, const int64_t* __restrict__ msgs, int64_t msg_stride,
                          int mode, int shift, int k, int N, int l, int beta, double sigma_abs, uint64_t seed,
-                         uint64_t id_base, uint64_t* __restrict__ out) {
+                         uint64_t noise_seed, uint64_t id_base, uint64_t* __restrict__ out) {
     extern __shared__ uint64_t sm[];  // A[N] then S bits [N/32 words]
     uint64_t* A = sm;
     uint32_t* Sb = reinterpret_cast<uint32_t*>(sm + N);
@@ -141,7 +141,7 @@ glwe_encrypt_rows_kernel(const uint8_t* __restrict__ S_big, const int64_t* __res
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int x = threadIdx.x + u * BSK_THREADS;
-        body[u] = x < N ? (uint64_t)gaussian_i64(seed, FHE_B200_KIND_NOISE | (FHE_B200_PUR_GLWE << 8), id, (uint32_t)x,
+        body[u] = x < N ? (uint64_t)gaussian_i64(noise_seed, FHE_B200_KIND_NOISE | (FHE_B200_PUR_GLWE << 8), id, (uint32_t)x,
                                                  sigma_abs)
                         : 0;
     }
@@ -180,12 +180,12 @@ glwe_encrypt_rows_kernel(const uint8_t* __restrict__ S_big, const int64_t* __res
 
 cudaError_t launch_glwe_encrypt_rows(const fhe_b200_pbs_params& p, const uint8_t* d_S_big, const int64_t* d_msgs,
                                      int64_t rows, int64_t msg_stride, int mode, int shift, uint64_t seed,
-                                     uint64_t id_base, uint64_t* d_out, cudaStream_t s) {
+                                     uint64_t noise_seed, uint64_t id_base, uint64_t* d_out, cudaStream_t s) {
     if (p.N > BSK_THREADS * 16) return cudaErrorInvalidValue;
     if (rows <= 0) return cudaSuccess;
     size_t smem = (size_t)p.N * 8 + (size_t)p.N / 8;
     glwe_encrypt_rows_kernel<<<(unsigned)rows, BSK_THREADS, smem, s>>>(d_S_big, d_msgs, msg_stride, mode, shift, p.k, p.N,
-                                                                      p.l_pbs, p.beta_pbs, p.sigma_glwe_abs, seed, id_base,
+                                                                      p.l_pbs, p.beta_pbs, p.sigma_glwe_abs, seed, noise_seed, id_base,
                                                                       d_out);
     count_launch();
     return cudaGetLastError();

@@ -46,13 +46,15 @@ constexpr int ENC_WARPS = 8;
 #endif
 constexpr int LCS_UNROLL_N = LCS_UNROLL;   // independent Philox blocks in flight per thread (seeded dot product)
 
+// The error terms come from the client's SECRET noise seed -- never from the public mask seed that travels with seeded
+// ciphertexts: an evaluator who could regenerate e would learn <a,s> + Delta*m exactly and solve for the key.
 __global__ void lwe_body_noise_kernel(const int64_t* __restrict__ msgs, int64_t count, int shift, double sigma_abs,
-                                      uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, uint64_t* __restrict__ dst,
+                                      uint64_t noise_seed, uint64_t ct_base, uint32_t purpose, uint64_t* __restrict__ dst,
                                       int64_t dst_stride) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const uint32_t ndom = FHE_B200_KIND_NOISE | (purpose << 8);
-    dst[i * dst_stride] = ((uint64_t)msgs[i] << shift) + (uint64_t)gaussian_i64(enc_seed, ndom, ct_base + (uint64_t)i, 0, sigma_abs);
+    dst[i * dst_stride] = ((uint64_t)msgs[i] << shift) + (uint64_t)gaussian_i64(noise_seed, ndom, ct_base + (uint64_t)i, 0, sigma_abs);
 }
 
 template <typename Kernel>
@@ -95,12 +97,12 @@ lwe_encrypt_packed_kernel(const uint32_t* __restrict__ kbits, int n, int64_t str
 }
 
 cudaError_t launch_lwe_encrypt_packed(const uint32_t* d_kbits, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
-                                      int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
-                                      uint64_t* d_ct, cudaStream_t s) {
+                                      int shift, double sigma_abs, uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base,
+                                      uint32_t purpose, uint64_t* d_ct, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
     const int64_t grid = (count + ENC_WARPS - 1) / ENC_WARPS;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-    lwe_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_msgs, count, shift, sigma_abs, enc_seed, ct_base,
+    lwe_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_msgs, count, shift, sigma_abs, noise_seed, ct_base,
                                                                         purpose, d_ct + n, stride);
     count_launch();
     lwe_encrypt_packed_kernel<<<(unsigned)grid, ENC_WARPS * 32, 0, s>>>(d_kbits, n, stride, count, enc_seed, ct_base, purpose, d_ct);
@@ -109,10 +111,10 @@ cudaError_t launch_lwe_encrypt_packed(const uint32_t* d_kbits, int n, int64_t st
 }
 
 cudaError_t launch_lwe_encrypt(const uint8_t* d_key, int n, int64_t stride, const int64_t* d_msgs, int64_t count,
-                               int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
-                               uint64_t* d_ct, cudaStream_t s) {
+                               int shift, double sigma_abs, uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base,
+                               uint32_t purpose, uint64_t* d_ct, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
-    lwe_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_msgs, count, shift, sigma_abs, enc_seed, ct_base,
+    lwe_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_msgs, count, shift, sigma_abs, noise_seed, ct_base,
                                                                         purpose, d_ct + n, stride);
     count_launch();
     size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
@@ -407,23 +409,23 @@ lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, int64_t count,
 // quantize (the UniformQuantizer rule of quantize_kernel) + plaintext + error in one pass:
 // the client path from float features to seeded ciphertexts needs no integer staging buffer
 __global__ void quantize_body_noise_kernel(const float* __restrict__ X, int64_t count, double scale, double zp, double qmin,
-                                           double qmax, int shift, double sigma_abs, uint64_t enc_seed, uint64_t ct_base,
+                                           double qmax, int shift, double sigma_abs, uint64_t noise_seed, uint64_t ct_base,
                                            uint32_t purpose, uint64_t* __restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     double v = rint(__dadd_rn(__ddiv_rn((double)X[i], scale), zp));
     v = fmin(fmax(v, qmin), qmax);
     const uint32_t ndom = FHE_B200_KIND_NOISE | (purpose << 8);
-    dst[i] = ((uint64_t)(int64_t)v << shift) + (uint64_t)gaussian_i64(enc_seed, ndom, ct_base + (uint64_t)i, 0, sigma_abs);
+    dst[i] = ((uint64_t)(int64_t)v << shift) + (uint64_t)gaussian_i64(noise_seed, ndom, ct_base + (uint64_t)i, 0, sigma_abs);
 }
 
 cudaError_t launch_lwe_encrypt_seeded_float(const uint8_t* d_key, int n, const float* d_X, int64_t count, double scale,
                                             int64_t zp, int64_t qmin, int64_t qmax, int shift, double sigma_abs,
-                                            uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, uint64_t* d_bodies,
-                                            cudaStream_t s) {
+                                            uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base, uint32_t purpose,
+                                            uint64_t* d_bodies, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
     quantize_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_X, count, scale, (double)zp, (double)qmin,
-                                                                             (double)qmax, shift, sigma_abs, enc_seed, ct_base,
+                                                                             (double)qmax, shift, sigma_abs, noise_seed, ct_base,
                                                                              purpose, d_bodies);
     count_launch();
     size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
@@ -434,10 +436,10 @@ cudaError_t launch_lwe_encrypt_seeded_float(const uint8_t* d_key, int n, const f
 }
 
 cudaError_t launch_lwe_encrypt_seeded(const uint8_t* d_key, int n, const int64_t* d_msgs, int64_t count, int shift,
-                                      double sigma_abs, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
-                                      uint64_t* d_bodies, cudaStream_t s) {
+                                      double sigma_abs, uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base,
+                                      uint32_t purpose, uint64_t* d_bodies, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
-    lwe_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_msgs, count, shift, sigma_abs, enc_seed, ct_base,
+    lwe_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_msgs, count, shift, sigma_abs, noise_seed, ct_base,
                                                                         purpose, d_bodies, 1);
     count_launch();
     size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);

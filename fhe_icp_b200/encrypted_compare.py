@@ -33,6 +33,7 @@ import torch
 
 from . import _native as N
 from . import engine as E
+from .randomness import CiphertextIds, seed_or_fresh
 
 # n=742, N=2048 as the stated 4-bit set, but two decomposition levels in the bootstrap: one PBS output
 # carries noise std ~2^-22 of the torus (2^-15 with one level), so the sum of 2d = 256 outputs
@@ -66,15 +67,20 @@ class EncryptedCompare:
     the Fourier bootstrapping key).  `multibit=True` uses the two-bits-per-step blind rotation
     (l_pbs <= 2)."""
 
-    def __init__(self, input_dim: int = 128, params: dict | None = None, key_seed: int = 0x5EED0001,
-                 evk_seed: int = 0x5EED0002, device=None, multibit: bool = True, chunk_pbs: int = 148 * 2 * 32):
+    def __init__(self, input_dim: int = 128, params: dict | None = None, key_seed: int | None = None,
+                 evk_seed: int | None = None, device=None, multibit: bool = True, chunk_pbs: int = 148 * 2 * 32,
+                 noise_seed: int | None = None, enc_seed: int | None = None, ct_start: int | None = None):
+        """Seeds default to the OS CSPRNG (randomness.py); pass fixed values only for reproducible tests.  ``enc_seed``
+        is the public mask seed; ``ct_start`` the first ciphertext id (None: random origin)."""
         if input_dim * 16 >= (1 << (SCORE_BITS - 1)):
             raise ValueError("input_dim too large for the 13-bit score range")
         self.d = int(input_dim)
         self.pd = dict(params or COMPARE_PARAMS)
         self.p = E.make_pbs_params(**self.pd)
         self.dev = E._dev(device)
-        self.key_seed, self.evk_seed = key_seed, evk_seed
+        self.key_seed, self.evk_seed = seed_or_fresh(key_seed), seed_or_fresh(evk_seed)
+        self.noise_seed, self.enc_seed = seed_or_fresh(noise_seed), seed_or_fresh(enc_seed)
+        self.ids = CiphertextIds(ct_start)
         self.multibit = bool(multibit)
         if self.multibit and self.p.l_pbs > 2:
             raise ValueError("multi-bit blind rotation is implemented for l_pbs <= 2")
@@ -114,18 +120,23 @@ class EncryptedCompare:
     def dequantize(self, q_scores: np.ndarray) -> np.ndarray:
         return np.asarray(q_scores, dtype=np.float64) * (self.scale * self.scale)
 
-    def encrypt(self, Xq: np.ndarray, enc_seed: int, ct_base: int = 0) -> torch.Tensor:
-        """Xq int [.., d] -> small-key ciphertexts [.., d, stride] (one LWE per dimension)."""
+    def encrypt(self, Xq: np.ndarray, enc_seed: int | None = None, ct_base: int | None = None) -> torch.Tensor:
+        """Xq int [.., d] -> small-key ciphertexts [.., d, stride] (one LWE per dimension).  ``enc_seed`` (public mask
+        seed) defaults to the engine's; ``ct_base=None`` takes fresh, never-reused ciphertext ids."""
         self._need_keys()
         m = torch.as_tensor(np.ascontiguousarray(Xq, dtype=np.int64))
-        return E.lwe_encrypt(self.s, m, IN_SHIFT, self.p.sigma_lwe_abs, enc_seed, ct_base)
+        base = self.ids.take(m.numel()) if ct_base is None else ct_base
+        return E.lwe_encrypt(self.s, m, IN_SHIFT, self.p.sigma_lwe_abs, self.enc_seed if enc_seed is None else enc_seed,
+                             base, noise_seed=self.noise_seed)
 
-    def encrypt_norms(self, Xq: np.ndarray, enc_seed: int, ct_base: int = 0) -> torch.Tensor:
+    def encrypt_norms(self, Xq: np.ndarray, enc_seed: int | None = None, ct_base: int | None = None) -> torch.Tensor:
         """Xq int [.., d] -> big-key ciphertexts [.., kN+2] of sum_j xq_j^2 at 2^(OUT_SHIFT-1)."""
         self._need_keys()
         Xq = np.asarray(Xq, dtype=np.int64)
         m = torch.as_tensor(np.ascontiguousarray((Xq * Xq).sum(axis=-1)))
-        return E.lwe_encrypt(self.S, m, OUT_SHIFT - 1, self.p.sigma_glwe_abs, enc_seed, NORM_CT_BASE + ct_base)
+        base = self.ids.take(m.numel()) if ct_base is None else NORM_CT_BASE + ct_base
+        return E.lwe_encrypt(self.S, m, OUT_SHIFT - 1, self.p.sigma_glwe_abs,
+                             self.enc_seed if enc_seed is None else enc_seed, base, noise_seed=self.noise_seed)
 
     def decrypt(self, scores: torch.Tensor) -> np.ndarray:
         self._need_keys()
@@ -168,14 +179,14 @@ class EncryptedCompare:
         """The clear integer model this path must reproduce exactly: sum_j xq_j * yq_j."""
         return self.quantize(docs) @ self.quantize(q)
 
-    def similarity(self, q: np.ndarray, docs: np.ndarray, enc_seed: int = 1, norms: bool = True) -> np.ndarray:
+    def similarity(self, q: np.ndarray, docs: np.ndarray, enc_seed: int | None = None, norms: bool = True) -> np.ndarray:
         docs = np.atleast_2d(docs)
         xq, yq = self.quantize(q), self.quantize(docs)
-        ct_q = self.encrypt(xq, enc_seed, 0)
-        ct_d = self.encrypt(yq, enc_seed, self.d)
+        ct_q = self.encrypt(xq, enc_seed)          # fresh ciphertext ids on every call
+        ct_d = self.encrypt(yq, enc_seed)
         if not norms:
             return self.dequantize(self.decrypt(self.scores(ct_q, ct_d)))
-        nq, nd = self.encrypt_norms(xq, enc_seed, 0), self.encrypt_norms(yq, enc_seed, 1)
+        nq, nd = self.encrypt_norms(xq, enc_seed), self.encrypt_norms(yq, enc_seed)
         return self.dequantize(self.decrypt(self.scores(ct_q, ct_d, nq, nd)))
 
     def _need_keys(self):
@@ -300,7 +311,9 @@ class PackedEncryptedCompare:
     client: keygen / fit_scale / quantize / encrypt_documents / encrypt_query / decrypt / dequantize;
     server: scores (needs no key material at all -- the GGSW IS the query)."""
 
-    def __init__(self, input_dim: int = 128, params: dict | None = None, key_seed: int = 0x5EED0001, device=None):
+    def __init__(self, input_dim: int = 128, params: dict | None = None, key_seed: int | None = None, device=None,
+                 noise_seed: int | None = None, enc_seed: int | None = None, ct_start: int | None = None):
+        """Seeds default to the OS CSPRNG (randomness.py); pass fixed values only for reproducible tests."""
         self.d = int(input_dim)
         self.pd = dict(params or PACKED_PARAMS)
         self.p = E.make_pbs_params(**self.pd)
@@ -311,7 +324,9 @@ class PackedEncryptedCompare:
             raise ValueError("input_dim too large for the 17-bit score range")
         self.per = self.p.N // self.slot
         self.dev = E._dev(device)
-        self.key_seed = key_seed
+        self.key_seed = seed_or_fresh(key_seed)
+        self.noise_seed, self.enc_seed = seed_or_fresh(noise_seed), seed_or_fresh(enc_seed)
+        self.ids = CiphertextIds(ct_start)
         self.scale = None
         self.S = None
 
@@ -334,16 +349,21 @@ class PackedEncryptedCompare:
     def dequantize(self, q_scores: np.ndarray) -> np.ndarray:
         return np.asarray(q_scores, dtype=np.float64) * (self.scale * self.scale)
 
-    def encrypt_documents(self, Yq: np.ndarray, enc_seed: int, id_base: int = 1 << 20) -> torch.Tensor:
-        """int [B, d] -> GLWE [ceil(B/per), 2, N] (documents packed `per` to a ciphertext)."""
+    def encrypt_documents(self, Yq: np.ndarray, enc_seed: int | None = None, id_base: int | None = None) -> torch.Tensor:
+        """int [B, d] -> GLWE [ceil(B/per), 2, N] (documents packed `per` to a ciphertext).  ``id_base=None`` takes
+        fresh, never-reused ciphertext ids; ``enc_seed`` (public mask seed) defaults to the engine's."""
         self._need_keys()
         polys = torch.as_tensor(pack_documents(Yq, self.p.N, self.slot))
-        return E.glwe_encrypt_vectors(self.p, self.S, polys, PACKED_OUT_SHIFT, enc_seed, id_base)
+        base = self.ids.take(polys.shape[0]) if id_base is None else id_base
+        return E.glwe_encrypt_vectors(self.p, self.S, polys, PACKED_OUT_SHIFT, self.enc_seed if enc_seed is None else enc_seed,
+                                      base, noise_seed=self.noise_seed)
 
-    def encrypt_query(self, xq: np.ndarray, enc_seed: int, id_base: int = 0) -> torch.Tensor:
+    def encrypt_query(self, xq: np.ndarray, enc_seed: int | None = None, id_base: int | None = None) -> torch.Tensor:
         """int [d] -> Fourier GGSW of Q(X) (the only thing the server needs for this query)."""
         self._need_keys()
-        ggsw = E.ggsw_encrypt_poly(self.p, self.S, torch.as_tensor(query_polynomial(xq, self.p.N)), enc_seed, id_base)
+        base = self.ids.take((self.p.k + 1) * self.p.l_pbs) if id_base is None else id_base
+        ggsw = E.ggsw_encrypt_poly(self.p, self.S, torch.as_tensor(query_polynomial(xq, self.p.N)),
+                                   self.enc_seed if enc_seed is None else enc_seed, base, noise_seed=self.noise_seed)
         return E.ggsw_to_fourier(self.p, ggsw)
 
     def decrypt(self, products: torch.Tensor, n_docs: int) -> np.ndarray:
@@ -365,9 +385,9 @@ class PackedEncryptedCompare:
     def compare_clear(self, q: np.ndarray, docs: np.ndarray) -> np.ndarray:
         return self.quantize(docs) @ self.quantize(q)
 
-    def similarity(self, q: np.ndarray, docs: np.ndarray, enc_seed: int = 1) -> np.ndarray:
+    def similarity(self, q: np.ndarray, docs: np.ndarray, enc_seed: int | None = None) -> np.ndarray:
         docs = np.atleast_2d(docs)
-        gq = self.encrypt_query(self.quantize(q), enc_seed)
+        gq = self.encrypt_query(self.quantize(q), enc_seed)       # fresh ciphertext ids on every call
         gd = self.encrypt_documents(self.quantize(docs), enc_seed)
         return self.dequantize(self.decrypt(self.scores(gq, gd), docs.shape[0]))
 

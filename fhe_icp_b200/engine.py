@@ -4,6 +4,7 @@ carried in ``torch.int64`` tensors (same bits)."""
 from __future__ import annotations
 
 import ctypes as C
+import secrets
 
 import numpy as np
 import torch
@@ -36,6 +37,17 @@ def even_stride(n: int) -> int:
     return (n + 2) & ~1
 
 
+def fresh_seed() -> int:
+    """A 64-bit seed from the OS CSPRNG (secret keys, noise, evaluation keys, per-process ciphertext-id nonces)."""
+    return secrets.randbits(64)
+
+
+def _noise(noise_seed) -> int:
+    # the error terms must come from a SECRET seed, never from the public mask seed: an explicit value is for
+    # reproducible tests / benchmarks only
+    return fresh_seed() if noise_seed is None else int(noise_seed)
+
+
 def to_u64_numpy(t: torch.Tensor) -> np.ndarray:
     return t.detach().cpu().numpy().view(np.uint64)
 
@@ -53,14 +65,19 @@ def secret_key(key_seed: int, key_id: int, dim: int, device=None) -> torch.Tenso
 
 
 def lwe_encrypt(key: torch.Tensor, msgs: torch.Tensor, shift: int, sigma_abs: float, enc_seed: int,
-                ct_base: int = 0, purpose: int = N.PUR_INPUT, stride: int | None = None) -> torch.Tensor:
+                ct_base: int = 0, purpose: int = N.PUR_INPUT, stride: int | None = None,
+                noise_seed: int | None = None) -> torch.Tensor:
+    """``enc_seed`` is the PUBLIC mask seed; ``noise_seed`` the client's SECRET seed of the error terms (default: a
+    fresh one from the OS CSPRNG -- pass a value only to reproduce ciphertexts in tests).  Ciphertext ids
+    ``ct_base + i`` must never repeat under the same seeds."""
     dev = key.device
     n = key.numel()
     stride = stride or even_stride(n)
     m = msgs.to(device=dev, dtype=torch.int64).contiguous()
     ct = torch.empty(tuple(m.shape) + (stride,), dtype=torch.int64, device=dev)
     N.check(N.lib().fhe_b200_lwe_encrypt(_ctx(dev).handle, _ptr(key), n, stride, _ptr(m), m.numel(), shift,
-                                         float(sigma_abs), enc_seed, ct_base, purpose, _ptr(ct), _stream(dev)))
+                                         float(sigma_abs), enc_seed, _noise(noise_seed), ct_base, purpose, _ptr(ct),
+                                         _stream(dev)))
     return ct
 
 
@@ -104,13 +121,14 @@ def lincomb(ct: torch.Tensor, W: torch.Tensor, n: int, bias=None, shift: int = 0
 
 # ------------------------------------------------------------------------------- seeded ciphertexts
 def lwe_encrypt_seeded(key: torch.Tensor, msgs: torch.Tensor, shift: int, sigma_abs: float, enc_seed: int,
-                       ct_base: int = 0, purpose: int = N.PUR_INPUT) -> torch.Tensor:
+                       ct_base: int = 0, purpose: int = N.PUR_INPUT, noise_seed: int | None = None) -> torch.Tensor:
     """Bodies only (8 bytes per ciphertext); masks are regenerated from (enc_seed, ct_base + index)."""
     dev = key.device
     m = msgs.to(device=dev, dtype=torch.int64).contiguous()
     bodies = torch.empty(m.shape, dtype=torch.int64, device=dev)
     N.check(N.lib().fhe_b200_lwe_encrypt_seeded(_ctx(dev).handle, _ptr(key), key.numel(), _ptr(m), m.numel(), shift,
-                                                float(sigma_abs), enc_seed, ct_base, purpose, _ptr(bodies), _stream(dev)))
+                                                float(sigma_abs), enc_seed, _noise(noise_seed), ct_base, purpose,
+                                                _ptr(bodies), _stream(dev)))
     return bodies
 
 
@@ -402,7 +420,7 @@ def make_lut_poly(table, p_bits: int, N_poly: int, delta_out_log2: int) -> np.nd
 
 # ------------------------------------------------------------------------------- packed inner products (GLWE x GGSW)
 def glwe_encrypt_vectors(p: N.PBSParams, S_big: torch.Tensor, polys: torch.Tensor, shift: int, seed: int,
-                         id_base: int = 0) -> torch.Tensor:
+                         id_base: int = 0, noise_seed: int | None = None) -> torch.Tensor:
     """polys int64 [rows, N] (message polynomials) -> GLWE(poly << shift) [rows, k+1, N]."""
     dev = S_big.device
     polys = polys.to(device=dev, dtype=torch.int64).contiguous()
@@ -410,11 +428,12 @@ def glwe_encrypt_vectors(p: N.PBSParams, S_big: torch.Tensor, polys: torch.Tenso
     assert polys.shape[1] == p.N
     out = torch.empty((rows, p.k + 1, p.N), dtype=torch.int64, device=dev)
     N.check(N.lib().fhe_b200_glwe_encrypt_rows(_ctx(dev).handle, C.byref(p), _ptr(S_big), _ptr(polys), rows, p.N, 0, shift,
-                                               seed, id_base, _ptr(out), _stream(dev)))
+                                               seed, _noise(noise_seed), id_base, _ptr(out), _stream(dev)))
     return out
 
 
-def ggsw_encrypt_poly(p: N.PBSParams, S_big: torch.Tensor, poly: torch.Tensor, seed: int, id_base: int = 0) -> torch.Tensor:
+def ggsw_encrypt_poly(p: N.PBSParams, S_big: torch.Tensor, poly: torch.Tensor, seed: int, id_base: int = 0,
+                      noise_seed: int | None = None) -> torch.Tensor:
     """poly int64 [N] -> GGSW rows [(k+1)*l, k+1, N] (row t*l+lev carries poly << (64 - beta*(lev+1)) on component t)."""
     dev = S_big.device
     poly = poly.to(device=dev, dtype=torch.int64).contiguous()
@@ -422,7 +441,7 @@ def ggsw_encrypt_poly(p: N.PBSParams, S_big: torch.Tensor, poly: torch.Tensor, s
     rows = (p.k + 1) * p.l_pbs
     out = torch.empty((rows, p.k + 1, p.N), dtype=torch.int64, device=dev)
     N.check(N.lib().fhe_b200_glwe_encrypt_rows(_ctx(dev).handle, C.byref(p), _ptr(S_big), _ptr(poly), rows, 0, 1, 0, seed,
-                                               id_base, _ptr(out), _stream(dev)))
+                                               _noise(noise_seed), id_base, _ptr(out), _stream(dev)))
     return out
 
 

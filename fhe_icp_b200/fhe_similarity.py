@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from .linear_model import DEFAULT_ENC_SEED, DEFAULT_KEY_SEED, LinearRegression, SGDRegressor  # noqa: F401
+from .linear_model import LinearRegression, SGDRegressor  # noqa: F401
 
 
 class SeededCiphertexts:
@@ -34,8 +34,12 @@ class FHESimilarityModel:
     """Optimized FHE model for similarity computation."""
 
     def __init__(self, input_dim: int = 256, n_bits: int = 8, similarity_type: str = 'cosine',
-                 seed: Optional[int] = None, key_seed: int = DEFAULT_KEY_SEED, enc_seed: int = DEFAULT_ENC_SEED,
-                 device: Optional[int] = None, verbose: bool = True):
+                 seed: Optional[int] = None, key_seed: Optional[int] = None, enc_seed: Optional[int] = None,
+                 device: Optional[int] = None, verbose: bool = True, noise_seed: Optional[int] = None,
+                 ct_start: Optional[int] = None):
+        """``seed`` seeds the synthetic training data only.  ``key_seed`` / ``noise_seed`` (client secrets) and
+        ``enc_seed`` (public mask seed) default to the OS CSPRNG, as Concrete's key generation does; fixed values and
+        ``ct_start`` (first ciphertext id) are an opt-in for reproducible tests and benchmarks (randomness.py)."""
         self.input_dim = input_dim
         self.n_bits = n_bits
         self.similarity_type = similarity_type
@@ -44,6 +48,7 @@ class FHESimilarityModel:
         self.metrics = {}
         self.seed = seed
         self.key_seed, self.enc_seed, self.device = key_seed, enc_seed, device
+        self.noise_seed, self.ct_start = noise_seed, ct_start
         self.verbose = verbose
 
     def _log(self, msg: str):
@@ -103,7 +108,8 @@ class FHESimilarityModel:
         start = time.time()
         start_memory = self._get_memory_usage()
         try:
-            kw = dict(key_seed=self.key_seed, enc_seed=self.enc_seed, device=self.device)
+            kw = dict(key_seed=self.key_seed, enc_seed=self.enc_seed, device=self.device, noise_seed=self.noise_seed,
+                      ct_start=self.ct_start)
             kw.update(compile_kwargs)
             self.model.compile(X_sample, **kw)
             compile_time = time.time() - start
@@ -134,9 +140,9 @@ class FHESimilarityModel:
         start = time.time()
         pred = self.model.predict(X, fhe="execute")
         pred_time = time.time() - start
-        if 'fhe_prediction_time' not in self.metrics:
-            self._log(f"  First FHE prediction batch ({len(X)} rows) took {pred_time:.3f}s")
-            self.metrics['fhe_prediction_time'] = pred_time
+        # the reference records the first prediction of EVERY call (fhe_similarity.py:156-158)
+        self._log(f"  First FHE prediction batch ({len(X)} rows) took {pred_time:.3f}s")
+        self.metrics['fhe_prediction_time'] = pred_time
         return np.asarray(pred)
 
     def predict_clear(self, X: np.ndarray) -> np.ndarray:
@@ -184,21 +190,24 @@ class FHESimilarityModel:
         import ctypes as C
         import torch
         from . import _native as N
-        c = self.keygen().model.fhe_circuit
+        if not self.compiled:
+            raise RuntimeError("Model not compiled. Call compile() first.")
+        c = self.model.fhe_circuit
+        handle = c.evaluator_handle()      # the evaluator holds no key material: run() is the server's whole job
         M = 2 if c.two_outputs else 1
         if isinstance(ct, SeededCiphertexts):
             B, dev = ct.bodies.shape[0], ct.bodies.device
             if out is None:
                 out = torch.empty((B, M, c.lwe.stride), dtype=torch.int64, device=dev)
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            N.check(N.lib().fhe_b200_similarity_run_seeded(c.handle, C.c_void_p(ct.bodies.data_ptr()), B, ct.enc_seed,
+            N.check(N.lib().fhe_b200_similarity_run_seeded(handle, C.c_void_p(ct.bodies.data_ptr()), B, ct.enc_seed,
                                                            ct.ct_base, C.c_void_p(out.data_ptr()), st))
             return out
         B = ct.shape[0]
         if out is None:
             out = torch.empty((B, M, c.lwe.stride), dtype=torch.int64, device=ct.device)
         st = C.c_void_p(torch.cuda.current_stream(ct.device).cuda_stream)
-        N.check(N.lib().fhe_b200_similarity_run(c.handle, C.c_void_p(ct.data_ptr()), B, C.c_void_p(out.data_ptr()), st))
+        N.check(N.lib().fhe_b200_similarity_run(handle, C.c_void_p(ct.data_ptr()), B, C.c_void_p(out.data_ptr()), st))
         return out
 
     def decrypt(self, out, return_q: bool = False):
@@ -221,7 +230,12 @@ class FHESimilarityModel:
         import ctypes as C
         import torch
         from . import _native as N
-        c = self.keygen().model.fhe_circuit
+        if not self.compiled:
+            raise RuntimeError("Model not compiled. Call compile() first.")
+        c = self.model.fhe_circuit
+        if not c.wire32_supported:
+            raise ValueError("the 32-bit wire form would raise the decoding failure probability above p_error at these "
+                             "parameters; keep the 64-bit scores")
         if out32 is None:
             out32 = torch.empty(out.shape, dtype=torch.int32, device=out.device)
         st = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
@@ -244,6 +258,16 @@ class FHESimilarityModel:
         if not to_host:
             return (y, qy) if return_q else y
         return (y.cpu().numpy(), qy.cpu().numpy()) if return_q else y.cpu().numpy()
+
+    @property
+    def wire32_supported(self) -> bool:
+        return bool(self.compiled and self.model.fhe_circuit.wire32_supported)
+
+    @property
+    def dev(self):
+        import torch
+        from . import _native as N
+        return torch.device("cuda", N.context(self.device).device)
 
     # ---------------------------------------------------------------- misc (fhe_similarity.py:169-224)
     def _get_memory_usage(self) -> float:

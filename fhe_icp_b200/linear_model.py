@@ -20,8 +20,7 @@ import numpy as np
 from .params import DEFAULT_P_ERROR, LweParams, select_lwe_params
 from .quantization import QuantizedLinearSpec, signed_bit_width
 
-DEFAULT_KEY_SEED = 0x5EED_0001
-DEFAULT_ENC_SEED = 0x5EED_0002
+from .randomness import CiphertextIds, seed_or_fresh
 
 
 class _Graph:
@@ -36,13 +35,17 @@ class FHECircuit:
     """Compiled circuit: integer bounds, crypto parameters and (lazily) the device model."""
 
     def __init__(self, spec: QuantizedLinearSpec, inputset_q: np.ndarray, p_error: float, bound_mode: str,
-                 key_seed: int, enc_seed: int, device: Optional[int]):
+                 key_seed: Optional[int], enc_seed: Optional[int], device: Optional[int], noise_seed: Optional[int] = None,
+                 ct_start: Optional[int] = None):
         self.spec = spec
         self.p_error = p_error
-        self.key_seed = int(key_seed)
-        self.enc_seed = int(enc_seed)
+        # randomness.py: key_seed and noise_seed are client secrets, enc_seed is the PUBLIC mask seed that travels with
+        # seeded ciphertexts; all default to the OS CSPRNG, fixed values are for reproducible tests and benchmarks
+        self.key_seed = seed_or_fresh(key_seed)
+        self.noise_seed = seed_or_fresh(noise_seed)
+        self.enc_seed = seed_or_fresh(enc_seed)
         self.device = device
-        self.ct_counter = 0
+        self.ids = CiphertextIds(ct_start)     # never-reused ciphertext ids (persisted with the key set)
         # "seeded": fresh ciphertexts travel as 8-byte bodies + public mask seed (the evaluator regenerates
         # the masks); "expanded": full (n+1)-word ciphertexts are materialised in HBM.  Same results.
         self.ciphertext_format = "seeded"
@@ -95,7 +98,7 @@ class FHECircuit:
             two_outputs=1 if self.two_outputs else 0, sigma_abs=self.lwe.sigma_abs, x_scale=float(s.input_q.scale),
             x_zero_point=int(s.input_q.zero_point), x_offset=int(s.input_q.offset),
             w_zero_point=int(s.weight_q.zero_point), q_bias=int(s.q_bias), out_scale=float(s.out_scale),
-            out_zero_point=int(s.out_zero_point), key_seed=self.key_seed)
+            out_zero_point=int(s.out_zero_point), key_seed=self.key_seed, noise_seed=self.noise_seed)
 
     def keygen(self, force: bool = False):
         """Create the device-side model (secret key from ``key_seed``, weights).  Lazy, like
@@ -119,10 +122,13 @@ class FHECircuit:
         return self._sim
 
     def release(self):
+        from . import _native as N
         if self._sim is not None:
-            from . import _native as N
             N.lib().fhe_b200_similarity_destroy(self._sim)
             self._sim = None
+        if getattr(self, "_eval", None) is not None:
+            N.lib().fhe_b200_similarity_destroy(self._eval)
+            self._eval = None
 
     def __del__(self):
         try:
@@ -131,14 +137,52 @@ class FHECircuit:
             pass
 
     def next_ct_base(self, count: int) -> int:
-        base = self.ct_counter
-        self.ct_counter += int(count)
-        return base
+        return self.ids.take(count)
+
+    @property
+    def ct_counter(self) -> int:
+        return self.ids.next
+
+    @ct_counter.setter
+    def ct_counter(self, value: int):
+        self.ids.next = int(value)
+
+    def evaluator_handle(self):
+        """Server side: the device model WITHOUT secret material (fhe_b200_similarity_create_evaluator).  It can run
+        the encrypted dot products; encrypt / decrypt on it fail."""
+        if getattr(self, "_eval", None) is None:
+            from . import _native as N
+            ctx = N.context(self.device)
+            h = C.c_void_p()
+            spec = self.native_spec()
+            spec.key_seed = 0
+            spec.noise_seed = 0
+            qw = np.ascontiguousarray(self.spec.q_weights, dtype=np.int64)
+            N.check(N.lib().fhe_b200_similarity_create_evaluator(ctx.handle, C.byref(spec),
+                                                                 qw.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(h)))
+            self._eval, self._eval_ctx = h, ctx
+        return self._eval
+
+    @property
+    def wire32_supported(self) -> bool:
+        """Whether the scores may travel in the 32-bit wire form without raising the decoding failure probability
+        above p_error (the modulus switch adds (n/2 + 1) * 2^64 / 12 to the noise variance)."""
+        import math
+        from .params import z_score
+        w2 = max(float((self.spec.q_weights.astype(np.float64) ** 2).sum()), float(self.spec.d) if self.two_outputs else 0.0)
+        var = (self.lwe.sigma_abs ** 2) * w2 + (self.lwe.n / 2 + 1) * (2.0 ** 64) / 12.0
+        return self.lwe.shift >= 32 and z_score(self.p_error) * math.sqrt(var) < 2.0 ** (self.lwe.shift - 1)
 
     def encrypt_run_decrypt(self, X: np.ndarray, return_q: bool = False):
         """The reference's ``predict(..., fhe="execute")`` with HOST buffers: float32 rows in,
         float64 scores out; quantize/encrypt/dot/decrypt/dequantize all run on the device."""
         from . import _native as N
+        X = np.asarray(X)
+        if X.dtype != np.float32:
+            # the device quantizer reads float32; any other dtype is quantized on the host in that dtype -- the very
+            # expression predict_clear evaluates -- so that fhe="execute" == fhe="disable" for float64 inputs too
+            # (rint(x / scale + zp) can flip at a rounding boundary when x is first rounded to float32)
+            return self._run_quantized(self.spec.input_q.quant(X.reshape(-1, self.spec.d)), return_q)
         X = np.ascontiguousarray(X, dtype=np.float32).reshape(-1, self.spec.d)
         B = X.shape[0]
         y = np.empty(B, dtype=np.float64)
@@ -150,6 +194,33 @@ class FHECircuit:
             self.handle, X.ctypes.data_as(C.POINTER(C.c_float)), B, self.enc_seed, base,
             y.ctypes.data_as(C.POINTER(C.c_double)), qy.ctypes.data_as(C.POINTER(C.c_int64))))
         return (y, qy) if return_q else y
+
+
+def _run_quantized(self, q: np.ndarray, return_q: bool = False):
+    """encrypt -> dot -> decrypt of already quantized rows (int64 [B, d]), seeded ciphertexts, all on the device."""
+    import torch
+    from . import _native as N
+    from . import engine as E
+    dev = torch.device("cuda", N.context(self.device).device)
+    B = q.shape[0]
+    if getattr(self, "_key_t", None) is None or self._key_t.device != dev:
+        self._key_t = E.secret_key(self.key_seed, 2, self.lwe.n, dev)
+    base = self.next_ct_base(B * self.spec.d)
+    bodies = E.lwe_encrypt_seeded(self._key_t, torch.as_tensor(np.ascontiguousarray(q, dtype=np.int64)), self.lwe.shift,
+                                  self.lwe.sigma_abs, self.enc_seed, base, noise_seed=self.noise_seed)
+    M = 2 if self.two_outputs else 1
+    out = torch.empty((B, M, self.lwe.stride), dtype=torch.int64, device=dev)
+    y = torch.empty(B, dtype=torch.float64, device=dev)
+    qy = torch.empty(B, dtype=torch.int64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    N.check(N.lib().fhe_b200_similarity_run_seeded(self.handle, C.c_void_p(bodies.data_ptr()), B, self.enc_seed, base,
+                                                   C.c_void_p(out.data_ptr()), st))
+    N.check(N.lib().fhe_b200_similarity_decrypt(self.handle, C.c_void_p(out.data_ptr()), B, C.c_void_p(y.data_ptr()),
+                                                C.c_void_p(qy.data_ptr()), st))
+    return (y.cpu().numpy(), qy.cpu().numpy()) if return_q else y.cpu().numpy()
+
+
+FHECircuit._run_quantized = _run_quantized
 
 
 class LinearRegression:
@@ -216,8 +287,10 @@ class LinearRegression:
 
     # ------------------------------------------------------------------ compile
     def compile(self, X_sample, p_error: float = DEFAULT_P_ERROR, bound_mode: str = "guaranteed",
-                key_seed: int = DEFAULT_KEY_SEED, enc_seed: int = DEFAULT_ENC_SEED, device: Optional[int] = None):
-        """Bound the integer circuit on the calibration inputset and choose crypto parameters."""
+                key_seed: Optional[int] = None, enc_seed: Optional[int] = None, device: Optional[int] = None,
+                noise_seed: Optional[int] = None, ct_start: Optional[int] = None):
+        """Bound the integer circuit on the calibration inputset and choose crypto parameters.  Seeds default to the
+        OS CSPRNG (like Concrete's key generation); fixed seeds / ``ct_start`` are for reproducible tests."""
         self._check_fitted()
         if bound_mode not in ("guaranteed", "inputset"):
             raise ValueError("bound_mode must be 'guaranteed' or 'inputset'")
@@ -225,7 +298,8 @@ class LinearRegression:
         if X_sample.ndim != 2 or X_sample.shape[1] != self.spec.d:
             raise ValueError(f"inputset must be [rows, {self.spec.d}]")
         q = self.spec.input_q.quant(X_sample)
-        self.fhe_circuit = FHECircuit(self.spec, q, p_error, bound_mode, key_seed, enc_seed, device)
+        self.fhe_circuit = FHECircuit(self.spec, q, p_error, bound_mode, key_seed, enc_seed, device,
+                                      noise_seed=noise_seed, ct_start=ct_start)
         return self.fhe_circuit
 
     # ------------------------------------------------------------------ inference

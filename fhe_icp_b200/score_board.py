@@ -75,7 +75,12 @@ class PeerScoreBoard:
     group); afterwards no call of this class communicates through torch.distributed."""
 
     def __init__(self, model, rows_max: int, client_rank: int = 0, timeout_ms: int = 10000):
-        c = model.keygen().model.fhe_circuit
+        if not model.compiled:
+            raise RuntimeError("Model not compiled. Call compile() first.")
+        c = model.model.fhe_circuit            # no keygen here: pushing needs the evaluator handle only
+        if not c.wire32_supported:
+            raise ValueError("score board: the 32-bit wire form would raise the decoding failure probability above "
+                             "p_error at these parameters")
         self.model, self.circuit = model, c
         self.M = 2 if c.two_outputs else 1
         self.stride = int(c.lwe.stride)
@@ -216,7 +221,7 @@ class PeerScoreBoard:
             self._mark_pushed(main)
             return step
         push = N.Push(self.board_base + rows_off, self.board_base + arrive, step, self.ctrl + _CTRL_COUNTER)
-        h = self.circuit.handle
+        h = self.circuit.evaluator_handle()     # key-less: what a server rank holds
         if isinstance(ct, SeededCiphertexts):
             N.check(self._lib.fhe_b200_similarity_run_seeded_push(h, C.c_void_p(ct.bodies.data_ptr()), B, ct.enc_seed,
                                                                   ct.ct_base, C.byref(push), st))

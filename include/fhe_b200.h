@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FHE_B200_ABI_VERSION 1
+#define FHE_B200_ABI_VERSION 2
 
 enum {
     FHE_B200_OK = 0,
@@ -77,7 +77,11 @@ typedef struct {
     int64_t q_bias;
     double out_scale;   /* y = out_scale * (q_y - out_zero_point) */
     int64_t out_zero_point;
-    uint64_t key_seed;  /* client secret key seed (key_id 2) */
+    uint64_t key_seed;  /* CLIENT SECRET: secret key seed (key_id 2) */
+    uint64_t noise_seed;/* CLIENT SECRET: seed of the encryption error terms.  Never equal to, or derivable from, the
+                         * public mask seed (`enc_seed`) that travels with seeded ciphertexts: whoever can regenerate
+                         * the errors learns <a,s> + Delta*m exactly and solves for the key.  Both secrets are ignored
+                         * (and zeroed) by fhe_b200_similarity_create_evaluator. */
 } fhe_b200_similarity_spec;
 
 /* ---- context ---------------------------------------------------------------- */
@@ -97,10 +101,14 @@ int fhe_b200_probe_fp64(fhe_b200_ctx *ctx, double *tflops);
  * `fhe_circuit.encrypt_run_decrypt` reached from fhe_similarity.py:151 */
 int fhe_b200_secret_key(fhe_b200_ctx *ctx, uint64_t key_seed, uint32_t key_id, int64_t dim,
                         uint8_t *d_key, void *stream);
+/* Randomness of ciphertext number ct_base + i: the MASK is a public function of (enc_seed, purpose, id) -- it may be
+ * regenerated by anyone (seeded ciphertexts rely on that); the ERROR term is drawn from (noise_seed, purpose, id) and
+ * noise_seed is a client secret.  An id must never be reused under the same (enc_seed, noise_seed): two ciphertexts
+ * with equal mask and error differ exactly by Delta*(m1 - m2). */
 int fhe_b200_lwe_encrypt(fhe_b200_ctx *ctx, const uint8_t *d_key, int32_t n, int64_t stride,
                          const int64_t *d_msgs, int64_t count, int32_t shift, double sigma_abs,
-                         uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, uint64_t *d_ct,
-                         void *stream);
+                         uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base, uint32_t purpose,
+                         uint64_t *d_ct, void *stream);
 int fhe_b200_lwe_phase(fhe_b200_ctx *ctx, const uint8_t *d_key, int32_t n, int64_t stride,
                        const uint64_t *d_ct, int64_t count, uint64_t *d_phase, void *stream);
 int fhe_b200_lwe_decrypt(fhe_b200_ctx *ctx, const uint8_t *d_key, int32_t n, int64_t stride,
@@ -122,7 +130,8 @@ int fhe_b200_lincomb(fhe_b200_ctx *ctx, const uint64_t *d_ct, int64_t B, int32_t
  * the masks on the fly.  Bit-identical to the materialised path; 1 KB instead of 1.46 MB per row. */
 int fhe_b200_lwe_encrypt_seeded(fhe_b200_ctx *ctx, const uint8_t *d_key, int32_t n, const int64_t *d_msgs,
                                 int64_t count, int32_t shift, double sigma_abs, uint64_t enc_seed,
-                                uint64_t ct_base, uint32_t purpose, uint64_t *d_bodies, void *stream);
+                                uint64_t noise_seed, uint64_t ct_base, uint32_t purpose, uint64_t *d_bodies,
+                                void *stream);
 int fhe_b200_lwe_expand_seeded(fhe_b200_ctx *ctx, const uint64_t *d_bodies, int64_t count, int32_t n,
                                int64_t stride, uint64_t enc_seed, uint64_t ct_base, uint32_t purpose,
                                uint64_t *d_ct, void *stream);
@@ -159,7 +168,8 @@ int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx *ctx, const uint64_t *d_in, int64_t 
  *  glwe_encrypt_rows: row R of d_out [rows][k+1][N] = GLWE_S(0) + (msg_R << shift_R) on component comp_R;
  *    mode 0: msg_R = d_msgs + R*msg_stride (N coefficients), shift_R = shift, comp_R = k;
  *    mode 1 (GGSW of one polynomial, rows = (k+1)*l): R = t*l+lev, msg_R = d_msgs, shift_R = 64-beta*(lev+1),
- *    comp_R = t.  Row R draws mask / noise from object id_base + R, purpose FHE_B200_PUR_GLWE.
+ *    comp_R = t.  Row R draws its mask from (seed, id_base + R) -- public -- and its error from (noise_seed,
+ *    id_base + R) -- client secret; purpose FHE_B200_PUR_GLWE.
  *  The GGSW goes to the Fourier domain with fhe_b200_bsk_to_fourier and a parameter copy with n = 1
  *    (layout [t][lev][c][N/2] complex).
  *  glwe_ggsw_dot: d_out [G][k+1][N] = GGSW [.] d_in[g] for all g (k = 1, l_pbs = 2).
@@ -167,7 +177,8 @@ int fhe_b200_lwe_pair_diff_sum(fhe_b200_ctx *ctx, const uint64_t *d_in, int64_t 
  *  glwe_sample_extract: d_out [(g*count+q)][out_stride] = LWE (big key) of coefficient first+q*step. */
 int fhe_b200_glwe_encrypt_rows(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_S_big,
                                const int64_t *d_msgs, int64_t rows, int64_t msg_stride, int32_t mode,
-                               int32_t shift, uint64_t seed, uint64_t id_base, uint64_t *d_out, void *stream);
+                               int32_t shift, uint64_t seed, uint64_t noise_seed, uint64_t id_base, uint64_t *d_out,
+                               void *stream);
 int fhe_b200_glwe_ggsw_dot(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_ggswf,
                            const uint64_t *d_in, int64_t G, uint64_t *d_out, void *stream);
 int fhe_b200_glwe_decrypt_coeffs(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint8_t *d_S_big,
@@ -258,6 +269,14 @@ int fhe_b200_pbs(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *
  * every stage a kernel of this library, ciphertexts materialised in HBM between them. */
 int fhe_b200_similarity_create(fhe_b200_ctx *ctx, const fhe_b200_similarity_spec *spec,
                                const int64_t *h_q_w, fhe_b200_similarity **sim);
+/* Server side: the same model WITHOUT any secret material (key_seed / noise_seed of the spec are ignored and zeroed).
+ * run / run_seeded / run_push work on it; encrypt, decrypt and predict_host return FHE_B200_ERR_INVALID.  This is what
+ * the non-client ranks of a sharded search hold. */
+int fhe_b200_similarity_create_evaluator(fhe_b200_ctx *ctx, const fhe_b200_similarity_spec *spec,
+                                         const int64_t *h_q_w, fhe_b200_similarity **sim);
+/* 1 if the 32-bit wire form of the scores (lwe_modswitch32 / run_push / decrypt32) keeps the decoding failure
+ * probability at 2^-40 for this model: z * sqrt(sigma_out^2 + (n/2+1) * 2^64/12) < Delta/2; else 0 and those calls fail. */
+int fhe_b200_similarity_wire32_supported(const fhe_b200_similarity *sim);
 int fhe_b200_similarity_destroy(fhe_b200_similarity *sim);
 int fhe_b200_similarity_predict_host(fhe_b200_similarity *sim, const float *h_X, int64_t B,
                                      uint64_t enc_seed, uint64_t ct_base, double *h_y,

@@ -143,7 +143,7 @@ static inline uint64_t mask_word(uint64_t seed, uint32_t purpose, uint64_t obj, 
 
 void orc_lwe_encrypt_batch(const uint8_t *s, int32_t n, int64_t stride, const int64_t *msgs,
                            int64_t count, int32_t shift, double sigma_abs, uint64_t enc_seed,
-                           uint64_t ct_base, uint32_t purpose, uint64_t *out) {
+                           uint64_t noise_seed, uint64_t ct_base, uint32_t purpose, uint64_t *out) {
 #pragma omp parallel for schedule(static)
     for (int64_t c = 0; c < count; ++c) {
         uint64_t id = ct_base + (uint64_t)c;
@@ -161,7 +161,7 @@ void orc_lwe_encrypt_batch(const uint8_t *s, int32_t n, int64_t stride, const in
                 if (s[w + 1]) dot += a1;
             }
         }
-        int64_t e = orc_gaussian(enc_seed, ORC_KIND_NOISE | (purpose << 8), id, 0, sigma_abs);
+        int64_t e = orc_gaussian(noise_seed, ORC_KIND_NOISE | (purpose << 8), id, 0, sigma_abs);
         ct[n] = dot + ((uint64_t)msgs[c] << shift) + (uint64_t)e;
         for (int64_t w = n + 1; w < stride; ++w) ct[w] = 0;
     }
@@ -242,7 +242,7 @@ void orc_ksk_gen(const orc_pbs_params *p, const uint8_t *S_big, const uint8_t *s
         for (int lev = 0; lev < l; ++lev) {
             int64_t msg = S_big[j];
             orc_lwe_encrypt_batch(s_small, n, n + 1, &msg, 1, 64 - beta * (lev + 1),
-                                  p->sigma_lwe_abs, evk_seed, (uint64_t)(j * l + lev),
+                                  p->sigma_lwe_abs, evk_seed, evk_seed, (uint64_t)(j * l + lev),
                                   ORC_PUR_KSK, ksk + ((size_t)j * l + lev) * (n + 1));
         }
     }
@@ -468,8 +468,8 @@ void orc_bsk_gen(const orc_pbs_params *p, const uint8_t *s_small, const uint8_t 
 /* Randomness: mask words / noise of row R come from object id (id_base + R), purpose ORC_PUR_GLWE. */
 /* ------------------------------------------------------------------ */
 void orc_glwe_encrypt_rows(const orc_pbs_params *p, const uint8_t *S_big, const int64_t *msgs, int64_t rows,
-                           int64_t msg_stride, int32_t mode, int32_t shift, uint64_t seed, uint64_t id_base,
-                           uint64_t *out) {
+                           int64_t msg_stride, int32_t mode, int32_t shift, uint64_t seed, uint64_t noise_seed,
+                           uint64_t id_base, uint64_t *out) {
     int k = p->k, N = p->N, l = p->l_pbs, beta = p->beta_pbs;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int64_t R = 0; R < rows; ++R) {
@@ -477,7 +477,7 @@ void orc_glwe_encrypt_rows(const orc_pbs_params *p, const uint8_t *S_big, const 
         uint64_t *row = out + (size_t)R * (k + 1) * N;
         uint64_t *body = row + (size_t)k * N;
         for (int x = 0; x < N; ++x)
-            body[x] = (uint64_t)orc_gaussian(seed, ORC_KIND_NOISE | (ORC_PUR_GLWE << 8), id, (uint32_t)x,
+            body[x] = (uint64_t)orc_gaussian(noise_seed, ORC_KIND_NOISE | (ORC_PUR_GLWE << 8), id, (uint32_t)x,
                                              p->sigma_glwe_abs);
         for (int c = 0; c < k; ++c) {
             uint64_t *A = row + (size_t)c * N;

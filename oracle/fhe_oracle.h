@@ -54,7 +54,7 @@ int64_t orc_gaussian(uint64_t seed, uint32_t domain, uint64_t obj, uint32_t blk,
 void orc_secret_key(uint64_t key_seed, uint32_t key_id, int64_t dim, uint8_t *s);
 void orc_lwe_encrypt_batch(const uint8_t *s, int32_t n, int64_t stride, const int64_t *msgs,
                            int64_t count, int32_t shift, double sigma_abs, uint64_t enc_seed,
-                           uint64_t ct_base, uint32_t purpose, uint64_t *out);
+                           uint64_t noise_seed, uint64_t ct_base, uint32_t purpose, uint64_t *out);
 void orc_lwe_phase_batch(const uint8_t *s, int32_t n, int64_t stride, const uint64_t *ct,
                          int64_t count, uint64_t *phase);
 void orc_lwe_decrypt_batch(const uint8_t *s, int32_t n, int64_t stride, const uint64_t *ct,
@@ -83,8 +83,8 @@ void orc_bsk2_to_fourier(const orc_pbs_params *p, const uint64_t *bsk2, double *
 void orc_pbs_mb2_batch(const orc_pbs_params *p, const double *bskf2, const uint64_t *in, int64_t B,
                        const uint64_t *luts, const int32_t *lut_index, uint64_t *out);
 void orc_glwe_encrypt_rows(const orc_pbs_params *p, const uint8_t *S_big, const int64_t *msgs, int64_t rows,
-                           int64_t msg_stride, int32_t mode, int32_t shift, uint64_t seed, uint64_t id_base,
-                           uint64_t *out);
+                           int64_t msg_stride, int32_t mode, int32_t shift, uint64_t seed, uint64_t noise_seed,
+                           uint64_t id_base, uint64_t *out);
 void orc_glwe_external_product_batch(const orc_pbs_params *p, const double *ggswf, const uint64_t *in, int64_t B,
                                      uint64_t *out);
 void orc_glwe_sample_extract(const orc_pbs_params *p, const uint64_t *in, int64_t B, int32_t first, int32_t step,

@@ -59,7 +59,7 @@ def lib() -> C.CDLL:
         L.orc_gaussian.restype = C.c_int64
         L.orc_secret_key.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, u8p]
         L.orc_lwe_encrypt_batch.argtypes = [u8p, C.c_int32, C.c_int64, i64p, C.c_int64, C.c_int32,
-                                            C.c_double, C.c_uint64, C.c_uint64, C.c_uint32, u64p]
+                                            C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, u64p]
         L.orc_lwe_phase_batch.argtypes = [u8p, C.c_int32, C.c_int64, u64p, C.c_int64, u64p]
         L.orc_lwe_decrypt_batch.argtypes = [u8p, C.c_int32, C.c_int64, u64p, C.c_int64, C.c_int32, i64p]
         L.orc_lincomb_batch.argtypes = [u64p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, i64p,
@@ -76,7 +76,7 @@ def lib() -> C.CDLL:
         L.orc_bsk2_to_fourier.argtypes = [pp, u64p, f64p]
         L.orc_pbs_mb2_batch.argtypes = [pp, f64p, u64p, C.c_int64, u64p, i32p, u64p]
         L.orc_glwe_encrypt_rows.argtypes = [pp, u8p, i64p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
-                                            C.c_uint64, u64p]
+                                            C.c_uint64, C.c_uint64, u64p]
         L.orc_glwe_external_product_batch.argtypes = [pp, f64p, u64p, C.c_int64, u64p]
         L.orc_glwe_sample_extract.argtypes = [pp, u64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, u64p]
         L.orc_negacyclic_mul_fft.argtypes = [C.c_int32, i64p, u64p, u64p]
@@ -110,14 +110,18 @@ def secret_key(key_seed: int, key_id: int, dim: int) -> np.ndarray:
 
 
 def lwe_encrypt(s, msgs, shift: int, sigma_abs: float, enc_seed: int, ct_base: int = 0,
-                purpose: int = PUR_INPUT, stride: int | None = None) -> np.ndarray:
+                purpose: int = PUR_INPUT, stride: int | None = None, noise_seed: int | None = None) -> np.ndarray:
+    """``enc_seed``: public mask seed; ``noise_seed``: the client's secret seed of the error terms.  The oracle is a
+    checker, so ``noise_seed=None`` simply reuses ``enc_seed`` (the convention the committed goldens were made with);
+    the product never does that."""
+    noise_seed = enc_seed if noise_seed is None else noise_seed
     s = np.ascontiguousarray(s, dtype=np.uint8)
     m = np.ascontiguousarray(np.asarray(msgs).reshape(-1), dtype=np.int64)
     n = s.size
     stride = stride or n + 1
     out = np.zeros((m.size, stride), dtype=np.uint64)
     lib().orc_lwe_encrypt_batch(_p(s, C.c_uint8), n, stride, _p(m, C.c_int64), m.size, shift,
-                                float(sigma_abs), enc_seed, ct_base, purpose, _p(out, C.c_uint64))
+                                float(sigma_abs), enc_seed, noise_seed, ct_base, purpose, _p(out, C.c_uint64))
     return out
 
 
@@ -366,14 +370,15 @@ def query_polynomial(xq, N: int) -> np.ndarray:
     return Q
 
 
-def glwe_encrypt_rows(p: PBSParams, S_big, msgs, mode: int, shift: int, seed: int, id_base: int = 0) -> np.ndarray:
+def glwe_encrypt_rows(p: PBSParams, S_big, msgs, mode: int, shift: int, seed: int, id_base: int = 0,
+                      noise_seed: int | None = None) -> np.ndarray:
     """mode 0: msgs [rows][N] -> GLWE(msg << shift) [rows][k+1][N]; mode 1: msgs [N] -> GGSW rows [(k+1)*l][k+1][N]."""
     S_big = np.ascontiguousarray(S_big, dtype=np.uint8)
     msgs = np.ascontiguousarray(msgs, dtype=np.int64)
     rows = msgs.shape[0] if mode == 0 else (p.k + 1) * p.l_pbs
     out = np.zeros((rows, p.k + 1, p.N), dtype=np.uint64)
     lib().orc_glwe_encrypt_rows(C.byref(p), _p(S_big, C.c_uint8), _p(msgs, C.c_int64), rows, p.N if mode == 0 else 0,
-                                mode, shift, seed, id_base, _p(out, C.c_uint64))
+                                mode, shift, seed, seed if noise_seed is None else noise_seed, id_base, _p(out, C.c_uint64))
     return out
 
 

@@ -62,8 +62,9 @@ def _pipeline(O, cuda_dev, params, d, B, seed, multibit, with_oracle=True, tol_l
     if with_oracle:
         op = _oparams(O, params)
         os_, oS = O.secret_key(ec.key_seed, 0, op.n), O.secret_key(ec.key_seed, 1, op.k * op.N)
-        oq = O.lwe_encrypt(os_, xq, IN_SHIFT, op.sigma_lwe_abs, seed, 0, stride=ct_q.shape[-1])
-        od = O.lwe_encrypt(os_, yq, IN_SHIFT, op.sigma_lwe_abs, seed, d, stride=ct_q.shape[-1]).reshape(B, d, -1)
+        ns = ec.noise_seed       # client secret (OS CSPRNG); the oracle mirrors it to compare ciphertext words
+        oq = O.lwe_encrypt(os_, xq, IN_SHIFT, op.sigma_lwe_abs, seed, 0, stride=ct_q.shape[-1], noise_seed=ns)
+        od = O.lwe_encrypt(os_, yq, IN_SHIFT, op.sigma_lwe_abs, seed, d, stride=ct_q.shape[-1], noise_seed=ns).reshape(B, d, -1)
         assert np.array_equal(_u64(ct_q), oq) and np.array_equal(_u64(ct_d), od)   # inputs bit-identical
         if multibit:
             obskf = O.bsk2_to_fourier(op, O.bsk2_gen(op, os_, oS, ec.evk_seed))
@@ -71,9 +72,10 @@ def _pipeline(O, cuda_dev, params, d, B, seed, multibit, with_oracle=True, tol_l
             obskf = O.bsk_to_fourier(op, O.bsk_gen(op, os_, oS, ec.evk_seed))
         if norms:
             from fhe_icp_b200.encrypted_compare import NORM_CT_BASE
-            onq = O.lwe_encrypt(oS, (xq * xq).sum(), OUT_SHIFT - 1, op.sigma_glwe_abs, seed, NORM_CT_BASE, stride=n_q.shape[-1])
+            onq = O.lwe_encrypt(oS, (xq * xq).sum(), OUT_SHIFT - 1, op.sigma_glwe_abs, seed, NORM_CT_BASE, stride=n_q.shape[-1],
+                                noise_seed=ns)
             ond = O.lwe_encrypt(oS, (yq * yq).sum(axis=1), OUT_SHIFT - 1, op.sigma_glwe_abs, seed, NORM_CT_BASE + 1,
-                                stride=n_q.shape[-1])
+                                stride=n_q.shape[-1], noise_seed=ns)
             assert np.array_equal(_u64(n_q).reshape(onq.shape), onq) and np.array_equal(_u64(n_d), ond)
             ref = O.encrypted_product_scores_norms(op, obskf, oq, od, onq, ond, P_BITS, OUT_SHIFT, multibit=multibit)
         else:

@@ -26,8 +26,8 @@ def test_encrypt_words_match_oracle(O, cuda_dev, n):
     shift, sigma = 42, 2.0 ** (64 - 30.0)
     key = E.secret_key(99, 2, n, cuda_dev)
     stride = E.even_stride(n)
-    ct = E.lwe_encrypt(key, torch.as_tensor(msgs), shift, sigma, enc_seed=555, ct_base=1000, stride=stride)
-    ref = O.lwe_encrypt(O.secret_key(99, 2, n), msgs, shift, sigma, 555, ct_base=1000, stride=stride)
+    ct = E.lwe_encrypt(key, torch.as_tensor(msgs), shift, sigma, enc_seed=555, ct_base=1000, stride=stride, noise_seed=9001)
+    ref = O.lwe_encrypt(O.secret_key(99, 2, n), msgs, shift, sigma, 555, ct_base=1000, stride=stride, noise_seed=9001)
     assert np.array_equal(_u64(ct), ref)
     dec = E.lwe_decrypt(key, ct, shift).cpu().numpy()
     assert np.array_equal(dec, msgs)
@@ -42,8 +42,8 @@ def test_gaussian_noise_stream_matches_oracle(O, cuda_dev):
     n, shift, sigma = 16, 40, 2.0 ** 39.3
     key = E.secret_key(5, 2, n, cuda_dev)
     msgs = np.zeros(4096, dtype=np.int64)
-    ct = E.lwe_encrypt(key, torch.as_tensor(msgs), shift, sigma, enc_seed=77, ct_base=1 << 40)
-    ref = O.lwe_encrypt(O.secret_key(5, 2, n), msgs, shift, sigma, 77, ct_base=1 << 40, stride=E.even_stride(n))
+    ct = E.lwe_encrypt(key, torch.as_tensor(msgs), shift, sigma, enc_seed=77, ct_base=1 << 40, noise_seed=78)
+    ref = O.lwe_encrypt(O.secret_key(5, 2, n), msgs, shift, sigma, 77, ct_base=1 << 40, stride=E.even_stride(n), noise_seed=78)
     assert np.array_equal(_u64(ct), ref)
     noise = O.lwe_phase(O.secret_key(5, 2, n), ref).view(np.int64).astype(np.float64)
     assert abs(noise.std() / sigma - 1.0) < 0.05 and abs(noise.mean()) < 0.1 * sigma
@@ -113,15 +113,17 @@ def test_predict_encrypted_equals_clear_circuit(O, cuda_dev, fit_dtype, n_bits):
 def test_split_api_ciphertexts_match_oracle(O, cuda_dev):
     """keygen / encrypt / run / decrypt: every intermediate ciphertext equals the oracle's."""
     from fhe_icp_b200 import FHESimilarityModel
-    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=3, verbose=False)
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=3, verbose=False, ct_start=0)   # seeds from the OS CSPRNG
     X, _ = m.train(n_samples=300)
     m.compile(X[:10])
     c = m.model.fhe_circuit
+    assert len({c.key_seed, c.noise_seed, c.enc_seed}) == 3
     Xt = X[:6]
     ct = m.encrypt(Xt)
     s = O.secret_key(c.key_seed, 2, c.lwe.n)
     q = m.model.quantize_input(Xt)
-    ref_ct = O.lwe_encrypt(s, q, c.lwe.shift, c.lwe.sigma_abs, c.enc_seed, ct_base=0, stride=c.lwe.stride)
+    ref_ct = O.lwe_encrypt(s, q, c.lwe.shift, c.lwe.sigma_abs, c.enc_seed, ct_base=0, stride=c.lwe.stride,
+                           noise_seed=c.noise_seed)
     assert np.array_equal(_u64(ct).reshape(-1, c.lwe.stride), ref_ct)
     out = m.run(ct)
     W = np.stack([c.spec.q_weights, np.ones_like(c.spec.q_weights)]) if c.two_outputs else c.spec.q_weights[None]
@@ -179,11 +181,11 @@ def test_seeded_ciphertexts_bit_identical_to_expanded(O, cuda_dev, n, d, M):
     msgs = rng.randint(-128, 128, size=(B, d))
     key = E.secret_key(99, 2, n, cuda_dev)
     stride = E.even_stride(n)
-    bodies = E.lwe_encrypt_seeded(key, torch.as_tensor(msgs), shift, sigma, enc_seed=555, ct_base=12345)
-    full = E.lwe_encrypt(key, torch.as_tensor(msgs), shift, sigma, enc_seed=555, ct_base=12345, stride=stride)
+    bodies = E.lwe_encrypt_seeded(key, torch.as_tensor(msgs), shift, sigma, enc_seed=555, ct_base=12345, noise_seed=31337)
+    full = E.lwe_encrypt(key, torch.as_tensor(msgs), shift, sigma, enc_seed=555, ct_base=12345, stride=stride, noise_seed=31337)
     assert np.array_equal(_u64(bodies), _u64(full)[..., n])
     assert np.array_equal(_u64(E.lwe_expand_seeded(bodies, n, 555, 12345, stride=stride)), _u64(full))
-    ref_ct = O.lwe_encrypt(O.secret_key(99, 2, n), msgs, shift, sigma, 555, ct_base=12345, stride=stride)
+    ref_ct = O.lwe_encrypt(O.secret_key(99, 2, n), msgs, shift, sigma, 555, ct_base=12345, stride=stride, noise_seed=31337)
     assert np.array_equal(_u64(full).reshape(-1, stride), ref_ct)
     W = rng.randint(-128, 128, size=(M, d))
     bias = rng.randint(-50, 50, size=M)
@@ -338,3 +340,104 @@ def test_quantization_strategy_sweep_fhe_equals_clear(cuda_dev, n_bits):
     fhe = np.array([model.predict(X_test[i:i + 1], fhe="execute")[0] for i in range(5)])
     assert np.mean(np.abs(clear - fhe)) == 0.0
     assert np.array_equal(model.predict(X_test, fhe="execute"), model.predict(X_test))
+
+
+def test_public_material_does_not_reproduce_the_noise(O, cuda_dev):
+    """the error terms of seeded ciphertexts must not be derivable from what the evaluator sees
+    (bodies, public mask seed, ciphertext ids).  With the secret noise seed the oracle reproduces every body; with the
+    public mask seed in its place -- all the evaluator could try -- not one error term matches, and default seeds are
+    fresh for every compiled model."""
+    from fhe_icp_b200 import FHESimilarityModel
+    from fhe_icp_b200 import engine as E
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=4, verbose=False, ct_start=0)
+    X, _ = m.train(n_samples=300)
+    m.compile(X[:10])
+    c = m.model.fhe_circuit
+    m2 = FHESimilarityModel(input_dim=128, n_bits=8, seed=4, verbose=False)
+    m2.train(n_samples=300)
+    m2.compile(X[:10])
+    c2 = m2.model.fhe_circuit
+    assert {c.key_seed, c.noise_seed, c.enc_seed}.isdisjoint({c2.key_seed, c2.noise_seed, c2.enc_seed})
+    assert c2.ct_counter != 0                                  # random id origin unless ct_start is given
+    sc = m.encrypt(X[:4], seeded=True)
+    assert not hasattr(sc, "noise_seed") and sc.enc_seed == c.enc_seed
+    s = O.secret_key(c.key_seed, 2, c.lwe.n)
+    q = m.model.quantize_input(X[:4])
+    good = O.lwe_encrypt(s, q, c.lwe.shift, c.lwe.sigma_abs, sc.enc_seed, ct_base=sc.ct_base, stride=c.lwe.stride,
+                         noise_seed=c.noise_seed)[:, c.lwe.n]
+    guess = O.lwe_encrypt(s, q, c.lwe.shift, c.lwe.sigma_abs, sc.enc_seed, ct_base=sc.ct_base, stride=c.lwe.stride,
+                          noise_seed=sc.enc_seed)[:, c.lwe.n]
+    bodies = E.to_u64_numpy(sc.bodies).reshape(-1)
+    assert np.array_equal(bodies, good)
+    assert not np.any(bodies == guess)
+    # two encryptions of the same rows never share ciphertext ids (mask + error reuse would leak m1 - m2)
+    sc2 = m.encrypt(X[:4], seeded=True)
+    assert sc2.ct_base >= sc.ct_base + 4 * 128 and not np.any(E.to_u64_numpy(sc2.bodies).reshape(-1) == bodies)
+
+
+def test_evaluator_handle_runs_but_cannot_encrypt_or_decrypt(cuda_dev):
+    """the server side of the linear path is a key-less object."""
+    import ctypes as C
+    import torch
+    from fhe_icp_b200 import FHESimilarityModel
+    from fhe_icp_b200 import _native as N
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=6, verbose=False)
+    X, _ = m.train(n_samples=300)
+    m.compile(X[:10])
+    c = m.model.fhe_circuit
+    ct = m.encrypt(X[:5])
+    ev = c.evaluator_handle()
+    out = torch.empty((5, 2 if c.two_outputs else 1, c.lwe.stride), dtype=torch.int64, device=ct.device)
+    lib = N.lib()
+    assert lib.fhe_b200_similarity_run(ev, C.c_void_p(ct.data_ptr()), 5, C.c_void_p(out.data_ptr()), None) == N.OK
+    torch.cuda.synchronize()
+    assert torch.equal(out, m.run(ct))
+    assert np.array_equal(m.decrypt(out), m.predict_clear(X[:5]))
+    y = torch.empty(5, dtype=torch.float64, device=ct.device)
+    assert lib.fhe_b200_similarity_decrypt(ev, C.c_void_p(out.data_ptr()), 5, C.c_void_p(y.data_ptr()), None, None) == N.ERR_INVALID
+    assert b"evaluator-only" in lib.fhe_b200_last_error()
+    Xd = torch.as_tensor(X[:5]).to(ct.device)
+    assert lib.fhe_b200_similarity_encrypt(ev, C.c_void_p(Xd.data_ptr()), 5, 1, 0, C.c_void_p(ct.data_ptr()), None) == N.ERR_INVALID
+    hy = np.empty(5)
+    assert lib.fhe_b200_similarity_predict_host_seeded(ev, X[:5].ctypes.data_as(C.POINTER(C.c_float)), 5, 1, 0,
+                                                       hy.ctypes.data_as(C.POINTER(C.c_double)), None) == N.ERR_INVALID
+
+
+def test_float64_inputs_execute_equals_clear(cuda_dev):
+    """float64 rows (what the reference's reducer hands over) are quantized in float64, so
+    fhe="execute" equals the clear model even where rounding the input to float32 first would flip a quantized value."""
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=8, verbose=False)
+    X, _ = m.train(n_samples=400)
+    m.compile(X[:10])
+    q = m.model.spec.input_q
+    rng = np.random.RandomState(0)
+    # rows sitting a hair from the rounding boundaries of the input quantizer
+    k = rng.randint(q.qmin + 1, q.qmax - 1, size=(64, 128)).astype(np.float64)
+    X64 = (k + 0.5 - q.zero_point) * q.scale * (1 + rng.choice([-1, 1], size=k.shape) * 1e-9)
+    assert np.any(q.quant(X64) != q.quant(X64.astype(np.float32)))          # the float32 detour would differ
+    assert np.array_equal(m.predict_encrypted(X64), m.predict_clear(X64))
+    assert np.array_equal(m.model.predict(X64, fhe="execute"), m.model.predict(X64))
+
+
+def test_wire32_gate_counts_the_modswitch_noise(cuda_dev):
+    """the 32-bit wire form is allowed only where z * sqrt(sigma_out^2 + (n/2+1) 2^64/12) < Delta/2.
+    At 8 bits / d=128 it is; at a 12-bit quantization the message is too wide and compress_scores / the score board
+    refuse instead of returning wrong scores, while the 64-bit path stays exact."""
+    from fhe_icp_b200 import FHESimilarityModel
+    from fhe_icp_b200.score_board import PeerScoreBoard
+    ok = FHESimilarityModel(input_dim=128, n_bits=8, seed=5, verbose=False)
+    X, _ = ok.train(n_samples=300)
+    ok.compile(X[:10])
+    assert ok.wire32_supported
+    wide = FHESimilarityModel(input_dim=128, n_bits=12, seed=5, verbose=False)
+    Xw, _ = wide.train(n_samples=300)
+    wide.compile(Xw[:10])
+    c = wide.model.fhe_circuit
+    assert c.lwe.shift < 44 and not wide.wire32_supported
+    out = wide.run(wide.encrypt(Xw[:16]))
+    assert np.array_equal(wide.decrypt(out), wide.predict_clear(Xw[:16]))
+    with pytest.raises(ValueError, match="32-bit wire form"):
+        wide.compress_scores(out)
+    with pytest.raises(ValueError, match="32-bit wire form"):
+        PeerScoreBoard(wide, rows_max=16)

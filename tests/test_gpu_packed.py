@@ -28,13 +28,14 @@ def test_packed_scores_exact_and_match_oracle(O, cuda_dev, B, d):
         pe = PackedEncryptedCompare.__new__(PackedEncryptedCompare)
         pe.d, pe.pd = d, dict(M.PACKED_PARAMS); pe.p = E.make_pbs_params(**pe.pd); pe.slot, pe.per = 2048, 1
         pe.dev, pe.key_seed, pe.scale, pe.S = cuda_dev, 5, 1.0, None
+        pe.noise_seed, pe.enc_seed, pe.ids = 4242, 9, M.CiphertextIds(0)
         pe.keygen()
     else:
         pe = PackedEncryptedCompare(input_dim=d, device=cuda_dev, key_seed=5).keygen()
         xq, yq = rng.randint(-16, 16, size=d), rng.randint(-16, 16, size=(B, d))
         xq[0], yq[0, 0] = -16, -16
-    gq = pe.encrypt_query(xq, enc_seed=9)
-    gd = pe.encrypt_documents(yq, enc_seed=9)
+    gq = pe.encrypt_query(xq, enc_seed=9, id_base=0)
+    gd = pe.encrypt_documents(yq, enc_seed=9, id_base=1 << 20)
     assert gd.shape == ((B + pe.per - 1) // pe.per, 2, 2048)
     prod = pe.scores(gq, gd)
     got = pe.decrypt(prod, B)
@@ -42,9 +43,10 @@ def test_packed_scores_exact_and_match_oracle(O, cuda_dev, B, d):
     # oracle: identical fresh ciphertexts, products within FFT rounding, identical decryptions
     op = _op(O, pe.pd)
     oS = O.secret_key(5, 1, 2048)
-    odocs = O.glwe_encrypt_rows(op, oS, O.pack_documents(yq, 2048, pe.slot), 0, PACKED_OUT_SHIFT, 9, 1 << 20)
+    odocs = O.glwe_encrypt_rows(op, oS, O.pack_documents(yq, 2048, pe.slot), 0, PACKED_OUT_SHIFT, 9, 1 << 20,
+                                noise_seed=pe.noise_seed)
     assert np.array_equal(_u64(gd), odocs)
-    oggsw = O.glwe_encrypt_rows(op, oS, O.query_polynomial(xq, 2048), 1, 0, 9, 0)
+    oggsw = O.glwe_encrypt_rows(op, oS, O.query_polynomial(xq, 2048), 1, 0, 9, 0, noise_seed=pe.noise_seed)
     ogf = O.ggsw_to_fourier(op, oggsw)
     assert np.abs(gq.cpu().numpy() - ogf).max() / np.abs(ogf).max() < 1e-13
     oprod = O.glwe_external_product(op, ogf, odocs)

@@ -22,14 +22,14 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/fhe_b200.h but not exported"
     assert declared == set(N.SIGNATURES), "ctypes table and header disagree"
-    assert lib.fhe_b200_abi_version() == 1
+    assert lib.fhe_b200_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     from fhe_icp_b200 import _native as N
     assert C.sizeof(N.PBSParams) == 48          # 8 x int32 + 2 x double
-    assert C.sizeof(N.SimilaritySpec) == 6 * 4 + 2 * 8 + 4 * 8 + 8 + 8 + 8
-    assert N.SimilaritySpec.key_seed.offset == 88
+    assert C.sizeof(N.SimilaritySpec) == 6 * 4 + 2 * 8 + 4 * 8 + 8 + 8 + 8 + 8
+    assert N.SimilaritySpec.key_seed.offset == 88 and N.SimilaritySpec.noise_seed.offset == 96
 
 
 def test_no_cpu_fallback_without_device():

@@ -28,7 +28,8 @@ class OracleEngine:
     def encrypt(self, X):
         c, O = self.c, self.O
         q = self.m.model.quantize_input(X)
-        ct = O.lwe_encrypt(self.s, q, c.lwe.shift, c.lwe.sigma_abs, c.enc_seed, ct_base=self.ct_base, stride=c.lwe.stride)
+        ct = O.lwe_encrypt(self.s, q, c.lwe.shift, c.lwe.sigma_abs, c.enc_seed, ct_base=self.ct_base, stride=c.lwe.stride,
+                           noise_seed=c.noise_seed)
         self.ct_base += q.size
         return torch.from_numpy(ct.reshape(len(X), c.spec.d, -1).view(np.int64))
 
@@ -44,9 +45,9 @@ class OracleEngine:
         return c.spec.dequantize_output(qy)
 
 
-def _make_problem(n_docs):
+def _make_problem(n_docs, **seeds):
     from fhe_icp_b200 import FHESimilarityModel
-    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=3, verbose=False)
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=3, verbose=False, **seeds)
     X, _ = m.train(n_samples=300)
     m.compile(X[:10], bound_mode="inputset")
     rng = np.random.RandomState(9)
@@ -57,17 +58,36 @@ def _make_problem(n_docs):
     return m, q, docs
 
 
-def _worker(rank, world, port, n_docs, ret):
+class KeylessEngine(OracleEngine):
+    """What a server rank holds under key_holders='client': it can run, it must never encrypt or decrypt."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self.s = None
+
+    def encrypt(self, X):
+        raise AssertionError("a server rank tried to encrypt")
+
+    def decrypt(self, enc):
+        raise AssertionError("a server rank tried to decrypt")
+
+
+def _worker(rank, world, port, n_docs, ret, key_holders="client"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from fhe_icp_b200.sharded_search import ShardedSearch, broadcast_public_material, shard_bounds
-        m, q, docs = _make_problem(n_docs)
+        if key_holders == "all":   # every rank belongs to the key owner: all built from the SAME explicit key set
+            m, q, docs = _make_problem(n_docs, key_seed=11, noise_seed=12, enc_seed=13)
+            engine = OracleEngine(m, ct_base=rank << 40)
+        else:                      # default: seeds from the OS CSPRNG, different on every rank; only rank 0's matter
+            m, q, docs = _make_problem(n_docs)
+            engine = OracleEngine(m) if rank == 0 else KeylessEngine(m)
         spec = broadcast_public_material(m.model.spec.to_dict() if rank == 0 else None)
         assert spec["q_weights"] == m.model.spec.to_dict()["q_weights"]
-        ss = ShardedSearch(OracleEngine(m, ct_base=rank << 40), docs)
+        ss = ShardedSearch(engine, docs if (rank == 0 or key_holders == "all") else None, key_holders=key_holders)
         assert (ss.lo, ss.hi) == shard_bounds(n_docs, world, rank)
-        res = ss.search(q, top_k=4, min_similarity=0.2)
+        res = ss.search(q if (rank == 0 or key_holders == "all") else None, top_k=4, min_similarity=0.2)
         if rank == 0:
             ret["res"] = res
         else:
@@ -76,12 +96,14 @@ def _worker(rank, world, port, n_docs, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_docs", [7, 2, 1])
-def test_sharded_search_world2_matches_single_process(n_docs):
+@pytest.mark.parametrize("n_docs,key_holders", [(7, "client"), (2, "client"), (1, "client"), (7, "all"), (1, "all")])
+def test_sharded_search_world2_matches_single_process(n_docs, key_holders):
+    """key_holders='client': rank 1 holds no key (its engine raises on encrypt / decrypt) and the ranks' key seeds
+    differ (OS CSPRNG) -- the client encrypts every shard and ships the ciphertexts.  'all': same key set on both."""
     world, port = 2, _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, n_docs, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n_docs, ret, key_holders), nprocs=world, join=True)
     from fhe_icp_b200.batch_operations import rank_results
     m, q, docs = _make_problem(n_docs)
     ref = rank_results([f"doc_{i}" for i in range(n_docs)], m.predict_clear(q[None, :] * docs), 4, 0.2)
@@ -132,16 +154,26 @@ class OraclePairEngine:
     def dequantize(self, q):
         return np.asarray(q, dtype=np.float64) * self.scale ** 2
 
-    def encrypt(self, Xq, enc_seed, ct_base=0):
+    def _ids(self, count):   # fresh, never-reused ciphertext ids (what the GPU engines' CiphertextIds does)
+        base = getattr(self, "_next", 0)
+        self._next = base + int(count)
+        return base
+
+    def encrypt(self, Xq, enc_seed=None, ct_base=None):
         Xq = np.asarray(Xq)
-        ct = self.O.lwe_encrypt(self.s, Xq, self.IN_SHIFT, self.p.sigma_lwe_abs, enc_seed, ct_base, stride=self.p.n + 2)
+        enc_seed = 7 if enc_seed is None else enc_seed
+        ct_base = self._ids(Xq.size) if ct_base is None else ct_base
+        ct = self.O.lwe_encrypt(self.s, Xq, self.IN_SHIFT, self.p.sigma_lwe_abs, enc_seed, ct_base, stride=self.p.n + 2,
+                                noise_seed=1234)
         return torch.from_numpy(ct.reshape(Xq.shape + (-1,)).view(np.int64))
 
-    def encrypt_norms(self, Xq, enc_seed, ct_base=0):
+    def encrypt_norms(self, Xq, enc_seed=None, ct_base=None):
         Xq = np.asarray(Xq)
         m = (Xq * Xq).sum(axis=-1)
-        ct = self.O.lwe_encrypt(self.S, m, self.OUT_SHIFT - 1, self.p.sigma_glwe_abs, enc_seed, (1 << 40) + ct_base,
-                                stride=self.p.N + 2)
+        enc_seed = 7 if enc_seed is None else enc_seed
+        ct_base = self._ids(np.size(m)) if ct_base is None else (1 << 40) + ct_base
+        ct = self.O.lwe_encrypt(self.S, m, self.OUT_SHIFT - 1, self.p.sigma_glwe_abs, enc_seed, ct_base,
+                                stride=self.p.N + 2, noise_seed=1234)
         return torch.from_numpy(ct.reshape(np.shape(m) + (-1,)).view(np.int64))
 
     def scores(self, ct_q, ct_docs, n_q, n_docs):
@@ -215,13 +247,21 @@ class OraclePackedEngine:
     def dequantize(self, q):
         return np.asarray(q, dtype=np.float64) * self.scale ** 2
 
-    def encrypt_documents(self, Yq, enc_seed, id_base=1 << 20):
-        ct = self.O.glwe_encrypt_rows(self.p, self.S, self.O.pack_documents(Yq, 2048, self.slot), 0, self.OUT_SHIFT,
-                                      enc_seed, id_base)
+    def _ids(self, count):
+        base = getattr(self, "_next", 0)
+        self._next = base + int(count)
+        return base
+
+    def encrypt_documents(self, Yq, enc_seed=None, id_base=None):
+        polys = self.O.pack_documents(Yq, 2048, self.slot)
+        ct = self.O.glwe_encrypt_rows(self.p, self.S, polys, 0, self.OUT_SHIFT, 7 if enc_seed is None else enc_seed,
+                                      self._ids(len(polys)) if id_base is None else id_base, noise_seed=1234)
         return torch.from_numpy(ct.view(np.int64))
 
-    def encrypt_query(self, xq, enc_seed, id_base=0):
-        gg = self.O.glwe_encrypt_rows(self.p, self.S, self.O.query_polynomial(xq, 2048), 1, 0, enc_seed, id_base)
+    def encrypt_query(self, xq, enc_seed=None, id_base=None):
+        gg = self.O.glwe_encrypt_rows(self.p, self.S, self.O.query_polynomial(xq, 2048), 1, 0,
+                                      7 if enc_seed is None else enc_seed, self._ids(4) if id_base is None else id_base,
+                                      noise_seed=1234)
         return torch.from_numpy(self.O.ggsw_to_fourier(self.p, gg))
 
     def scores(self, gq, glwe):

@@ -20,22 +20,24 @@ X, _ = m.train(n_samples=500)
 m.compile(X[:10])
 spec = broadcast_public_material(m.model.spec.to_dict() if rank == 0 else None)
 assert spec["q_weights"] == m.model.spec.to_dict()["q_weights"]
-m.model.fhe_circuit.ct_counter = rank << 40
+# seeds come from the OS CSPRNG and differ per rank: only rank 0 (the client) ever uses its keys; the other ranks are
+# key-less evaluators (ShardedSearch's default key_holders="client") and get no documents and no query
 n_docs = 10007
 rng = np.random.RandomState(9)
 q = rng.randn(128).astype(np.float32); q /= np.linalg.norm(q)
 docs = rng.randn(n_docs, 128).astype(np.float32)
 docs[::3] = q + 0.3 * rng.randn(len(docs[::3]), 128)
 docs /= np.linalg.norm(docs, axis=1, keepdims=True)
-ss = ShardedSearch(m, docs)                       # seeded ciphertexts + 32-bit score gather (defaults)
-res = ss.search(q, top_k=5, min_similarity=0.5)
-res_plain = ShardedSearch(m, docs, seeded=False, wire32=False).search(q, top_k=5, min_similarity=0.5)
+cdocs, cq = (docs, q) if rank == 0 else (None, None)
+ss = ShardedSearch(m, cdocs)                      # seeded ciphertexts + 32-bit score gather (defaults)
+res = ss.search(cq, top_k=5, min_similarity=0.5)
+res_plain = ShardedSearch(m, cdocs, seeded=False, wire32=False).search(cq, top_k=5, min_similarity=0.5)
 assert res == res_plain
 # fused gather: scores pushed by the dot-product kernels into the client's score board (no collective)
 for seeded in (True, False):
-    sp = ShardedSearch(m, docs, seeded=seeded, gather="push")
+    sp = ShardedSearch(m, cdocs, seeded=seeded, gather="push")
     for rep in range(5):                            # > 2 steps: exercises the slot credits
-        res_push = sp.search(q, top_k=5, min_similarity=0.5)
+        res_push = sp.search(cq, top_k=5, min_similarity=0.5)
         assert res_push == res, (rank, seeded, rep, res_push, res)
     sp.close()
 if rank == 0:
