@@ -76,9 +76,15 @@ class IdentityReducer:
 
 
 class DocumentStore:
-    """Flat document store: one float32 matrix + a JSON index, insertion-ordered.  Replaces the
-    reference's one-pickle-per-document layout (encrypted_storage.py:40-47,73-108) for the fields
-    the compare path reads: ``load(doc_id).encrypted_embedding`` and ``list_documents()``."""
+    """Flat document store: a JSON index plus ONE of
+      * ``embeddings.f32`` -- a float32 matrix, insertion-ordered: what the reference stores as "encrypted" documents
+        (plaintext PCA vectors, encrypted_storage.py:40-47; batch_operations.py:175-178).  Used by fhe="execute" /
+        "disable", whose circuit encrypts the CLEAR product query * document per query, exactly as the reference does;
+      * ``collection.glwe`` -- packed GLWE ciphertexts (serialization.py): the collection encrypted at
+        rest, 16 documents per 32 KB ciphertext.  Used by fhe="both": no plaintext embedding is ever written, ``search``
+        / ``compare`` memory-map the ciphertexts and hand them to the GPU.
+    Replaces the reference's one-pickle-per-document layout (encrypted_storage.py:73-108) for the fields the compare
+    path reads: ``load(doc_id).encrypted_embedding`` and ``list_documents()``."""
 
     @dataclass
     class Doc:
@@ -93,12 +99,45 @@ class DocumentStore:
         self.dir = Path(storage_dir) if storage_dir else None
         self.index: Dict[str, dict] = {}
         self._rows: List[np.ndarray] = []
+        self.kind = "plain"                       # or "glwe" once ciphertexts are appended
+        self._glwe: List[np.ndarray] = []         # chunks [G_i, k+1, N] u64 (memory-mapped when loaded from disk)
+        self.glwe_meta: dict = {}
         if self.dir is not None and (self.dir / "index.json").exists():
             meta = json.loads((self.dir / "index.json").read_text())
             self.dim = meta["dim"]
+            self.kind = meta.get("kind", "plain")
             self.index = {d["doc_id"]: d for d in meta["documents"]}
-            mat = np.fromfile(self.dir / "embeddings.f32", dtype=np.float32).reshape(-1, self.dim)
-            self._rows = [mat[i] for i in range(mat.shape[0])]
+            if self.kind == "glwe":
+                from .serialization import load_ciphertexts
+                ct, header = load_ciphertexts(str(self.dir / "collection.glwe"), mmap=True)
+                self._glwe, self.glwe_meta = [ct], header["meta"]
+            else:
+                mat = np.fromfile(self.dir / "embeddings.f32", dtype=np.float32).reshape(-1, self.dim)
+                self._rows = [mat[i] for i in range(mat.shape[0])]
+
+    # ---- ciphertext collection (fhe="both")
+    def append_ciphertexts(self, glwe: np.ndarray, doc_ids: List[str], hashes: List[str], metadata: List[dict], per: int,
+                           meta: dict) -> None:
+        """``glwe`` [G, k+1, N] u64 holds ``len(doc_ids)`` documents, ``per`` to a ciphertext in order."""
+        if self._rows:
+            raise ValueError("this store holds plaintext embeddings (fhe='execute'); use a separate directory for fhe='both'")
+        self.kind, self.glwe_meta = "glwe", dict(meta)
+        g0 = self.n_groups
+        self._glwe.append(np.ascontiguousarray(glwe).view(np.uint64))
+        for i, (doc_id, h, md) in enumerate(zip(doc_ids, hashes, metadata)):
+            self.index[doc_id] = {"doc_id": doc_id, "row": len(self.index) if doc_id not in self.index else self.index[doc_id]["row"],
+                                  "group": g0 + i // per, "slot": i % per, "timestamp": datetime.now().isoformat(),
+                                  "content_hash": h, "size_bytes": int(glwe[0].nbytes // per), "metadata": md or {}}
+
+    @property
+    def n_groups(self) -> int:
+        return int(sum(c.shape[0] for c in self._glwe))
+
+    def ciphertexts(self) -> np.ndarray:
+        """The whole collection [G, k+1, N] u64 (a memory map when it came from disk)."""
+        if len(self._glwe) == 1:
+            return self._glwe[0]
+        return np.concatenate(self._glwe, axis=0) if self._glwe else np.zeros((0, 2, 0), np.uint64)
 
     def save(self, doc_id: str, embedding: np.ndarray, content_hash: str = "", metadata: Optional[dict] = None):
         emb = np.asarray(embedding, dtype=np.float32)
@@ -120,13 +159,24 @@ class DocumentStore:
         if self.dir is None:
             return
         self.dir.mkdir(parents=True, exist_ok=True)
-        self.matrix().tofile(self.dir / "embeddings.f32")
-        (self.dir / "index.json").write_text(json.dumps({"dim": self.dim, "documents": list(self.index.values())}))
+        if self.kind == "glwe":
+            from .serialization import save_ciphertexts
+            ct = np.array(self.ciphertexts())            # materialise before the file a memory map points at is rewritten
+            n_poly = ct.shape[-1]
+            save_ciphertexts(str(self.dir / "collection.glwe"), ct, n=n_poly - 1, shift=int(self.glwe_meta.get("shift", 0)),
+                             meta=self.glwe_meta)
+            self._glwe = [ct]
+        else:
+            self.matrix().tofile(self.dir / "embeddings.f32")
+        (self.dir / "index.json").write_text(json.dumps({"dim": self.dim, "kind": self.kind,
+                                                         "documents": list(self.index.values())}))
 
     def load(self, doc_id: str) -> "DocumentStore.Doc":
         if doc_id not in self.index:
             raise KeyError(f"Document {doc_id} not found")
         r = self.index[doc_id]
+        if self.kind == "glwe":     # the document's ciphertext (its GLWE group); the slot is in the index record
+            return DocumentStore.Doc(doc_id, r["content_hash"], r["timestamp"], self.ciphertexts()[r["group"]], r["metadata"])
         return DocumentStore.Doc(doc_id, r["content_hash"], r["timestamp"], self._rows[r["row"]], r["metadata"])
 
     def list_documents(self) -> List[dict]:
@@ -136,7 +186,7 @@ class DocumentStore:
         return np.stack(self._rows) if self._rows else np.zeros((0, self.dim), np.float32)
 
     def __len__(self):
-        return len(self._rows)
+        return len(self.index) if self.kind == "glwe" else len(self._rows)
 
 
 class BatchProcessor:
@@ -144,7 +194,14 @@ class BatchProcessor:
 
     def __init__(self, embedder=None, reducer=None, key_manager=None, storage: Optional[DocumentStore] = None,
                  config: Optional[BatchConfig] = None, fhe_model: Optional[FHESimilarityModel] = None,
-                 fhe: str = "execute", seed: Optional[int] = 0, device: Optional[int] = None, init_model: bool = True):
+                 fhe: str = "execute", seed: Optional[int] = 0, device: Optional[int] = None, init_model: bool = True,
+                 keys=None):
+        """``keys``: a :class:`serialization.KeySet` (e.g. ``load_keys(path, password)``) -- the persistent secret the
+        reference's key manager only pretends to store (key_management.py:148-166 pickles a config dict).  None: a fresh
+        key set from the OS CSPRNG, kept in ``self.keys`` (``save_keys`` writes it).  ``seed`` seeds the synthetic training
+        data of the model only."""
+        from .serialization import KeySet
+        self.keys = keys if keys is not None else KeySet.generate()
         self.embedder = embedder or SyntheticEmbedder(128)
         self.reducer = reducer or IdentityReducer()
         self.key_manager = key_manager
@@ -158,7 +215,9 @@ class BatchProcessor:
 
     def _init_model(self):
         """Train + compile the 128-d / 8-bit similarity model (batch_operations.py:78-93)."""
-        self.fhe_model = FHESimilarityModel(input_dim=128, n_bits=8, seed=self.seed, device=self.device, verbose=False)
+        k = self.keys
+        self.fhe_model = FHESimilarityModel(input_dim=128, n_bits=8, seed=self.seed, device=self.device, verbose=False,
+                                            key_seed=k.key_seed, noise_seed=k.noise_seed, enc_seed=k.enc_seed)
         X_train, _ = self.fhe_model.train()
         self.fhe_model.compile(X_train[:10])
         logger.info("FHE model initialized and compiled with similarity training data")
@@ -178,10 +237,52 @@ class BatchProcessor:
         packed GLWE x GGSW engine (16 documents per ciphertext, no bootstrap)."""
         if getattr(self, "_pair", None) is None:
             from .encrypted_compare import PackedEncryptedCompare
-            d = 128
-            self._pair = PackedEncryptedCompare(input_dim=d, device=self.device).keygen()
+            d, k = 128, self.keys
+            self._pair = PackedEncryptedCompare(input_dim=d, device=self.device, key_seed=k.key_seed, noise_seed=k.noise_seed,
+                                                enc_seed=k.enc_seed).keygen()
             self._pair.fit_scale(np.array([-1.0, 1.0]) / np.sqrt(d))  # unit-norm embeddings: std 1/sqrt(d)
+            if self.fhe_model is not None and self.fhe_model.compiled:    # one id allocator per key set
+                self._pair.ids = self.fhe_model.model.fhe_circuit.ids
         return self._pair
+
+    def save_keys(self, path: str, password: str) -> None:
+        """Persist the key set under the reference's wrapper (PBKDF2-HMAC-SHA256 -> Fernet, 0600)."""
+        from .serialization import save_keys
+        save_keys(path, self.keys, password)
+
+    # ---- fhe="both": the collection lives as packed GLWE ciphertexts (no plaintext at rest)
+    def _collection_tensor(self):
+        """The stored ciphertexts on the GPU (cached until the store grows)."""
+        import torch
+        eng = self._pair_engine()
+        n = self.storage.n_groups
+        cache = getattr(self, "_coll", None)
+        if cache is None or cache[0] != n:
+            ct = torch.from_numpy(np.ascontiguousarray(self.storage.ciphertexts()).view(np.int64)).to(eng.dev)
+            self._coll = cache = (n, ct)
+        return cache[1]
+
+    def _pair_scores(self, xq: np.ndarray) -> np.ndarray:
+        """Integer scores of every stored document against the quantized query, in index (row) order."""
+        eng = self._pair_engine()
+        products = eng.scores(eng.encrypt_query(xq), self._collection_tensor())     # fresh ciphertext ids per query
+        flat = eng.decrypt(products, self.storage.n_groups * eng.per)
+        docs = self.storage.list_documents()
+        return flat[[r["group"] * eng.per + r["slot"] for r in docs]]
+
+    def _decrypt_document(self, rec: dict) -> np.ndarray:
+        """Client side: the quantized embedding of ONE stored document (the key owner reading its own data)."""
+        from . import engine as E
+        from .encrypted_compare import PACKED_IN_BITS, PACKED_OUT_SHIFT
+        import torch
+        eng = self._pair_engine()
+        g = self._collection_tensor()[rec["group"]: rec["group"] + 1]
+        v = E.glwe_decrypt_coeffs(eng.p, eng.S, g, rec["slot"] * eng.slot, 1, eng.d, PACKED_OUT_SHIFT).cpu().numpy().reshape(-1)
+        width = 64 - PACKED_OUT_SHIFT
+        v = v & ((1 << width) - 1)
+        v = np.where(v >= (1 << (width - 1)), v - (1 << width), v)
+        assert np.abs(v).max() <= (1 << (PACKED_IN_BITS - 1))
+        return v.astype(np.int64)
 
     def encrypt_documents(self, texts: List[str], doc_ids: Optional[List[str]] = None,
                           metadata: Optional[List[Dict]] = None) -> List[str]:
@@ -194,6 +295,24 @@ class BatchProcessor:
         if metadata is None:
             metadata = [{} for _ in range(n_docs)]
         encrypted_ids = []
+        if self.fhe == "both":
+            # the documents are encrypted for real and only ciphertexts are stored (the reference stores
+            # plaintext vectors, batch_operations.py:175-178): quantize, pack 16 per GLWE ciphertext, encrypt on the GPU
+            from .encrypted_compare import PACKED_OUT_SHIFT
+            eng = self._pair_engine()
+            reduced = [self.reducer.transform(self.embedder.get_embeddings_batch(texts[i:i + self.config.batch_size]))
+                       for i in range(0, n_docs, self.config.batch_size)]
+            if n_docs:
+                yq = eng.quantize(np.concatenate(reduced, axis=0))
+                glwe = eng.encrypt_documents(yq).cpu().numpy().view(np.uint64)
+                self.storage.append_ciphertexts(glwe, doc_ids, [hashlib.sha256(t.encode()).hexdigest() for t in texts], metadata,
+                                                eng.per, {"scheme": "packed GLWE x GGSW", "d": eng.d, "slot": eng.slot,
+                                                          "per": eng.per, "shift": PACKED_OUT_SHIFT, "scale": eng.scale,
+                                                          "params": eng.pd, "enc_seed": eng.enc_seed})
+            encrypted_ids = list(doc_ids)
+            self.storage.flush()
+            logger.info(f"Encrypted {len(encrypted_ids)} documents")
+            return encrypted_ids
         for i in range(0, n_docs, self.config.batch_size):
             j = min(i + self.config.batch_size, n_docs)
             reduced = self.reducer.transform(self.embedder.get_embeddings_batch(texts[i:j]))
@@ -209,7 +328,14 @@ class BatchProcessor:
         doc1 = self.storage.load(doc_id1)
         doc2 = self.storage.load(doc_id2)
         if self.fhe == "both":
-            return float(self._pair_engine().similarity(doc1.encrypted_embedding, doc2.encrypted_embedding[None, :])[0])
+            # both documents are ciphertexts at rest.  The key owner decrypts document 1 (its own data), re-encrypts it
+            # as the GGSW query, and the server multiplies it into document 2's stored ciphertext.
+            eng = self._pair_engine()
+            r1, r2 = self.storage.index[doc_id1], self.storage.index[doc_id2]
+            gq = eng.encrypt_query(self._decrypt_document(r1))
+            g2 = self._collection_tensor()[r2["group"]: r2["group"] + 1]
+            ints = eng.decrypt(eng.scores(gq, g2), eng.per)
+            return float(eng.dequantize(ints[r2["slot"]: r2["slot"] + 1])[0])
         X = (doc1.encrypted_embedding * doc2.encrypted_embedding).reshape(1, -1)
         return float(self._predict(X)[0])
 
@@ -221,7 +347,8 @@ class BatchProcessor:
         if not all_docs:
             return []
         if self.fhe == "both":
-            scores = self._pair_engine().similarity(query_reduced, self.storage.matrix())
+            eng = self._pair_engine()
+            scores = eng.dequantize(self._pair_scores(eng.quantize(query_reduced)))
         else:
             X = query_reduced[None, :] * self.storage.matrix()    # dtype as in the reference (batch_operations.py:273)
             scores = self._predict(X)
@@ -246,9 +373,10 @@ class BatchProcessor:
                                            scale=eng.scale)
         q = self.reducer.transform(self.embedder.get_embedding(query_text).reshape(1, -1))[0]
         n_docs = len(all_docs)
-        products = eng.scores(eng.encrypt_query(eng.quantize(q)),           # fresh ciphertext ids on every call
-                              eng.encrypt_documents(eng.quantize(self.storage.matrix())))
-        scores = eng.scores_as_lwe(products)[:n_docs].contiguous()
+        products = eng.scores(eng.encrypt_query(eng.quantize(q)), self._collection_tensor())   # fresh ids per query
+        import torch
+        rows = torch.as_tensor([r["group"] * eng.per + r["slot"] for r in all_docs], device=products.device)
+        scores = eng.scores_as_lwe(products).index_select(0, rows).contiguous()
         bits = self._thr.decrypt(self._thr.ge(scores, self._thr.threshold_to_int(min_similarity)))
         return [d["doc_id"] for d, b in zip(all_docs, bits) if b]
 

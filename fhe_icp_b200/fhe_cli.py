@@ -1,26 +1,73 @@
 #!/usr/bin/env python3
 """``compare`` / ``search`` / ``encrypt-batch`` with the reference CLI's argument surface and output
-(/root/reference/fhe_cli.py:106-210,327-346).  Key management, stats, validate and estimate are
-outside the encrypted-compare path and are not provided."""
+(/root/reference/fhe_cli.py:106-210,327-346), plus ``keys generate`` (fhe_cli.py:42-60) for the one piece of key
+management the encrypted-compare path needs: a persistent key set.  The reference's key manager stores
+a config dict behind a master password (key_management.py:148-166); here the file holds the seeds every key is derived
+from, under the same PBKDF2 + Fernet wrapper.  The master password comes from ``FHE_MASTER_PASSWORD`` or, like the
+reference (key_management.py:69,87), from ``getpass``.  stats / validate / estimate / key rotation are outside the path
+and not provided."""
 from __future__ import annotations
 
 import argparse
 import json
+import os
 import sys
+from pathlib import Path
 
 from .batch_operations import BatchProcessor, DocumentStore
 
 
+def _master_password(confirm: bool = False) -> str:
+    pw = os.environ.get("FHE_MASTER_PASSWORD")
+    if pw is not None:
+        return pw
+    import getpass
+    pw = getpass.getpass("Enter master password: ")
+    if confirm and getpass.getpass("Confirm master password: ") != pw:
+        raise ValueError("Passwords don't match")
+    return pw
+
+
 class FHEDocumentCLI:
-    def __init__(self, storage_dir: str = "./encrypted_docs", fhe: str = "execute", seed: int = 0):
+    def __init__(self, storage_dir: str = "./encrypted_docs", fhe: str = "execute", seed: int = 0, keys_path: str = None):
         self.storage = DocumentStore(storage_dir)
         self.fhe, self.seed = fhe, seed
+        # fhe="both" keeps ciphertexts at rest, so the key set must outlive the process: default key file in the store
+        self.keys_path = keys_path or (str(Path(storage_dir) / "keys.fhe") if fhe == "both" else None)
         self._processor = None
+
+    def _load_or_create_keys(self):
+        from .serialization import KeySet, load_keys, save_keys
+        if self.keys_path is None:
+            return None                                   # ephemeral key set (fresh from the OS CSPRNG)
+        if Path(self.keys_path).exists():
+            return load_keys(self.keys_path, _master_password())
+        keys = KeySet.generate()
+        Path(self.keys_path).parent.mkdir(parents=True, exist_ok=True)
+        save_keys(self.keys_path, keys, _master_password(confirm=True))
+        print(f"Generated a new key set: {self.keys_path}")
+        return keys
 
     def _get_processor(self) -> BatchProcessor:
         if self._processor is None:
-            self._processor = BatchProcessor(storage=self.storage, fhe=self.fhe, seed=self.seed)
+            self._processor = BatchProcessor(storage=self.storage, fhe=self.fhe, seed=self.seed,
+                                             keys=self._load_or_create_keys())
         return self._processor
+
+    def cmd_keys(self, args):
+        from .serialization import KeySet, save_keys
+        if args.key_command != 'generate':
+            print("Only `keys generate` is provided (rotation / listing are outside the encrypted-compare path)")
+            return
+        if self.keys_path is None:
+            self.keys_path = str(Path(self.storage.dir or ".") / "keys.fhe")
+        if Path(self.keys_path).exists() and not args.force:
+            print(f"Error: {self.keys_path} exists (use --force to overwrite: stored ciphertexts become undecryptable)")
+            return
+        Path(self.keys_path).parent.mkdir(parents=True, exist_ok=True)
+        save_keys(self.keys_path, KeySet.generate(), _master_password(confirm=True))
+        print("Generating FHE keys...")
+        print(f"Keys generated successfully!\nKey file: {self.keys_path}")
 
     def cmd_encrypt_batch(self, args):
         processor = self._get_processor()
@@ -88,7 +135,14 @@ def build_parser() -> argparse.ArgumentParser:
                         help="execute = encrypted evaluation on the GPU (default); disable = the reference's clear path; "
                              "both = both vectors encrypted, products evaluated by programmable bootstraps")
     parser.add_argument('--seed', type=int, default=0)
+    parser.add_argument('--keys', default=None, metavar='FILE',
+                        help="key file (created on first use; master password from FHE_MASTER_PASSWORD or a prompt). "
+                             "Default: <storage-dir>/keys.fhe for --fhe both, an ephemeral key set otherwise")
     subparsers = parser.add_subparsers(dest='command', help='Available commands')
+    keys_parser = subparsers.add_parser('keys', help='Key management')
+    keys_sub = keys_parser.add_subparsers(dest='key_command')
+    gen = keys_sub.add_parser('generate', help='Generate new keys')
+    gen.add_argument('--force', action='store_true')
     batch_parser = subparsers.add_parser('encrypt-batch', help='Encrypt multiple documents')
     batch_parser.add_argument('input_file', help='JSON file with documents')
     batch_parser.add_argument('--output-file', '-o', help='Save IDs to file')
@@ -108,8 +162,9 @@ def main(argv=None):
     if not args.command:
         parser.print_help()
         return 0
-    cli = FHEDocumentCLI(args.storage_dir, args.fhe, args.seed)
-    handler = {'encrypt-batch': cli.cmd_encrypt_batch, 'compare': cli.cmd_compare, 'search': cli.cmd_search}[args.command]
+    cli = FHEDocumentCLI(args.storage_dir, args.fhe, args.seed, args.keys)
+    handler = {'encrypt-batch': cli.cmd_encrypt_batch, 'compare': cli.cmd_compare, 'search': cli.cmd_search,
+               'keys': cli.cmd_keys}[args.command]
     try:
         handler(args)
     except KeyboardInterrupt:

@@ -10,6 +10,10 @@ The reference stores *plaintext* float32 vectors as "encrypted" documents (pickl
   (DESIGN.md section 3), so the persistent secret is the seed set + parameters; it is wrapped with
   the reference's own scheme -- PBKDF2-HMAC-SHA256 (100 000 iterations, 16-byte salt) -> Fernet
   (key_management.py:49-58) -- and a wrong password raises ``ValueError`` like the reference.
+
+Both are used by the product: ``BatchProcessor(fhe="both")`` keeps the collection as packed GLWE ciphertexts in
+``<storage>/collection.glwe`` (written by ``encrypt-batch``, memory-mapped by ``search`` / ``compare`` -- no plaintext
+embedding is ever stored), and the CLI's ``--keys`` option / ``keys generate`` command persist the key set.
 """
 from __future__ import annotations
 
@@ -66,10 +70,12 @@ def load_ciphertexts(path: str, mmap: bool = False):
 
 @dataclass
 class KeySet:
-    """Everything needed to regenerate the client's secret keys and the evaluation keys."""
+    """Everything needed to regenerate the client's secret keys and the evaluation keys.  ``key_seed``, ``noise_seed``
+    and ``evk_seed`` are secrets; ``enc_seed`` is the public mask seed (randomness.py)."""
     key_seed: int
     enc_seed: int
     evk_seed: int = 0
+    noise_seed: int = 0
     lwe: dict = field(default_factory=dict)          # leveled path: n, stride, shift, log2_sigma
     pbs: dict = field(default_factory=dict)          # keyswitch / PBS parameter set, if used
     quantized_spec: Optional[dict] = None            # the compiled model's public part
@@ -80,6 +86,12 @@ class KeySet:
     @classmethod
     def from_json(cls, b: bytes) -> "KeySet":
         return cls(**json.loads(b.decode()))
+
+    @classmethod
+    def generate(cls, **kw) -> "KeySet":
+        """A fresh key set from the OS CSPRNG."""
+        from .randomness import fresh_seed
+        return cls(key_seed=fresh_seed(), enc_seed=fresh_seed(), evk_seed=fresh_seed(), noise_seed=fresh_seed(), **kw)
 
 
 def _derive(password: str, salt: bytes) -> bytes:
@@ -103,6 +115,9 @@ def load_keys(path: str, password: str) -> KeySet:
     raw = open(path, "rb").read()
     if raw[:8] != KEY_MAGIC:
         raise ValueError("not a fhe_b200 key file")
+    (version,) = struct.unpack("<I", raw[8:12])
+    if version != VERSION:
+        raise ValueError(f"unsupported key file version {version}")
     salt, token = raw[12:28], raw[28:]
     try:
         return KeySet.from_json(Fernet(_derive(password, salt)).decrypt(token))
@@ -112,4 +127,5 @@ def load_keys(path: str, password: str) -> KeySet:
 
 def keyset_from_model(model) -> KeySet:
     c = model.model.fhe_circuit
-    return KeySet(key_seed=c.key_seed, enc_seed=c.enc_seed, lwe=c.lwe.to_dict(), quantized_spec=c.spec.to_dict())
+    return KeySet(key_seed=c.key_seed, enc_seed=c.enc_seed, noise_seed=c.noise_seed, lwe=c.lwe.to_dict(),
+                  quantized_spec=c.spec.to_dict())

@@ -107,31 +107,86 @@ def test_32bit_wire_form_decrypts_identically(cuda_dev):
 
 
 def test_both_encrypted_mode_search_and_compare(processor):
-    """fhe="both": query and documents both encrypted.  Scores equal the clear
-    integer model of that path exactly and rank the topic's documents first."""
+    """fhe="both": query and documents both encrypted, the collection stored as ciphertexts only
+    (N2).  Scores equal the clear integer model of that path exactly and rank the topic's documents first."""
     from fhe_icp_b200.batch_operations import BatchProcessor, rank_results
-    bp = BatchProcessor(fhe="both", seed=0, init_model=False, fhe_model=processor.fhe_model, storage=processor.storage)
+    bp = BatchProcessor(fhe="both", seed=0, init_model=False, fhe_model=processor.fhe_model)
+    texts = [f"{['quantum', 'cooking', 'finance', 'biology', 'sailing'][i % 5]} document number {i} about things" for i in range(60)]
+    bp.encrypt_documents(texts[:37], [f"d{i}" for i in range(37)])       # two calls: ragged groups (37 = 2 x 16 + 5)
+    bp.encrypt_documents(texts[37:], [f"d{i}" for i in range(37, 60)])
+    assert bp.storage.kind == "glwe" and not bp.storage._rows and bp.storage.n_groups == 3 + 2 and len(bp.storage) == 60
     eng = bp._pair_engine()
-    q = bp.reducer.transform(bp.embedder.get_embedding("quantum entanglement").reshape(1, -1))[0]
-    M = bp.storage.matrix()[:60]
-    sim = eng.similarity(q, M)
-    assert np.array_equal(sim, eng.dequantize(eng.compare_clear(q, M)))
-    cos = M @ q
-    top = set(np.argsort(-cos)[:12])
-    assert top == set(np.argsort(-sim, kind="stable")[:12])       # the 12 "quantum" documents of the first 60
-    a, b = bp.storage.load("d0").encrypted_embedding, bp.storage.load("d5").encrypted_embedding
-    got = bp.compare_encrypted("d0", "d5")
+    M = bp.embedder.get_embeddings_batch(texts)                          # what the client knew before encrypting
+    q = bp.embedder.get_embedding("quantum entanglement")
+    ints = bp._pair_scores(eng.quantize(q))
+    assert np.array_equal(ints, eng.compare_clear(q, M))                 # exact: the clear integer model
+    got = bp.search_similar("quantum entanglement", top_k=12, min_similarity=-10.0)
+    assert got == rank_results([f"d{i}" for i in range(60)], eng.dequantize(eng.compare_clear(q, M)), 12, -10.0)
+    assert {i for i, _ in got} == {f"d{i}" for i in range(0, 60, 5)}     # the 12 "quantum" documents
+    a, b = M[0], M[5]
+    got = bp.compare_encrypted("d0", "d5")                               # document 1 decrypted client side -> GGSW query
     assert got == float(eng.dequantize(eng.compare_clear(a, b[None, :]))[0])
     assert abs(got - float(a @ b)) < 0.06 and got > bp.compare_encrypted("d0", "d1")
+    assert np.array_equal(bp._decrypt_document(bp.storage.index["d41"]), eng.quantize(M[41]))
     # encrypted threshold: same documents as thresholding the decrypted scores of the same path
-    small = BatchProcessor(fhe="both", seed=0, init_model=False, fhe_model=processor.fhe_model)
-    small._pair, small.embedder = eng, bp.embedder
+    small = BatchProcessor(fhe="both", seed=0, init_model=False, fhe_model=processor.fhe_model, keys=bp.keys)
     small.encrypt_documents([f"{t} document number {i} about things" for i, t in
                              enumerate(["quantum", "cooking", "finance", "quantum", "biology", "sailing", "quantum"])],
                             [f"s{i}" for i in range(7)])
     hits = small.filter_similar("quantum entanglement", 0.5)
     want = [i for i, _ in small.search_similar("quantum entanglement", top_k=10, min_similarity=0.5)]
     assert sorted(hits) == sorted(want) == ["s0", "s3", "s6"]
+
+
+def test_encrypt_batch_then_search_in_a_new_process_over_stored_ciphertexts(tmp_path, cuda_dev):
+    """VERDICT r1 task 7: `encrypt-batch` writes ciphertexts (collection.glwe) and a password-protected key file; a NEW
+    process runs `search` / `compare` over what is on disk -- no plaintext embedding exists there -- and gets the ranking
+    of the clear integer model."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    from fhe_icp_b200.batch_operations import DocumentStore, SyntheticEmbedder, rank_results
+    from fhe_icp_b200.encrypted_compare import PackedEncryptedCompare
+    from fhe_icp_b200.serialization import load_ciphertexts, load_keys
+    root = Path(__file__).resolve().parent.parent
+    sd = str(tmp_path / "store")
+    topics = ["quantum", "cooking", "finance", "biology", "sailing"]
+    docs = [{"id": f"doc{i}", "text": f"{topics[i % 5]} paper {i} on something", "metadata": {"n": i}} for i in range(45)]
+    src = tmp_path / "docs.json"
+    src.write_text(json.dumps(docs))
+    env = dict(os.environ, FHE_MASTER_PASSWORD="correct horse", PYTHONPATH=str(root))
+    run = lambda *a: subprocess.run([sys.executable, "-m", "fhe_icp_b200.fhe_cli", "--storage-dir", sd, "--fhe", "both", *a],
+                                    env=env, capture_output=True, text=True, timeout=600)   # noqa: E731
+    r = run("encrypt-batch", str(src))
+    assert r.returncode == 0 and "Encrypted 45 documents successfully!" in r.stdout, r.stdout + r.stderr
+    files = sorted(p.name for p in Path(sd).iterdir())
+    assert files == ["collection.glwe", "index.json", "keys.fhe"]            # no embeddings.f32: nothing in the clear
+    ct, header = load_ciphertexts(os.path.join(sd, "collection.glwe"), mmap=True)
+    assert ct.shape == (3, 2, 2048) and header["meta"]["per"] == 16
+    emb = SyntheticEmbedder(128)
+    M = emb.get_embeddings_batch([d["text"] for d in docs])
+    assert not any(np.float32(v).tobytes() in Path(sd, "collection.glwe").read_bytes() for v in M[0][:4])
+    with pytest.raises(ValueError, match="Invalid master password"):
+        load_keys(os.path.join(sd, "keys.fhe"), "wrong")
+    # a new process: search over the stored ciphertexts
+    r = run("search", "quantum entanglement", "--top-k", "4", "--min-similarity", "0.3")
+    assert r.returncode == 0, r.stdout + r.stderr
+    ref = PackedEncryptedCompare(input_dim=128, device=cuda_dev)             # only its quantizer is used (clear model)
+    ref.fit_scale(np.array([-1.0, 1.0]) / np.sqrt(128))
+    want = rank_results([d["id"] for d in docs], ref.dequantize(ref.compare_clear(emb.get_embedding("quantum entanglement"), M)), 4, 0.3)
+    assert f"Found {len(want)} similar documents" in r.stdout
+    for i, (doc_id, score) in enumerate(want, 1):
+        assert f"{i}. {doc_id} (similarity: {score:.4f})" in r.stdout, r.stdout
+    # ... and a third one: compare two stored documents
+    r = run("compare", "doc0", "doc5")
+    want_c = float(ref.dequantize(ref.compare_clear(M[0], M[5][None, :]))[0])
+    assert r.returncode == 0 and f"Similarity score: {want_c:.4f}" in r.stdout, r.stdout + r.stderr
+    # a wrong password cannot use the store
+    bad = subprocess.run([sys.executable, "-m", "fhe_icp_b200.fhe_cli", "--storage-dir", sd, "--fhe", "both", "search", "x"],
+                         env=dict(env, FHE_MASTER_PASSWORD="nope"), capture_output=True, text=True, timeout=600)
+    assert bad.returncode == 1 and "Invalid master password" in bad.stderr
+    assert DocumentStore(sd).kind == "glwe"
 
 
 def _board_model(seed=11, rows=300):
