@@ -428,7 +428,7 @@ def run_b200_arm(args):
     if seeded:   # no HBM roofline applies: the masks never touch memory
         line_extra = {"format": "seeded", "kernel": "lincomb_seeded_kernel", "kernel_ms": kern_ms,
                       "docs_per_sec_per_gpu": B / (kern_ms * 1e-3),
-                      "note": "integer-pipe bound: 10 Philox rounds per 16 mask bytes; equivalent expanded-ciphertext "
+                      "note": "integer-pipe bound: 7 Philox rounds per 16 mask bytes; equivalent expanded-ciphertext "
                               "stream would be %.0f GB/s" % achieved}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

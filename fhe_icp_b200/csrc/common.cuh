@@ -11,8 +11,13 @@
 
 namespace fhe {
 
-// ----------------------------------------------------------------------------- Philox4x32-10
+// ----------------------------------------------------------------------------- Philox4x32-R
+// Secret material (key bits, noise) is drawn with the standard 10 rounds.  PUBLIC masks -- which both the client and
+// the evaluator regenerate, 2 x 32x32->64 multiplies per round on the scarce wide-multiplier pipe -- use
+// MASK_ROUNDS = 7, the smallest round count Salmon et al. (SC'11, table 2) report as Crush-resistant (BigCrush clean);
+// a mask only has to be uniform, it is public.  Same (seed, kind, object, block) interface for both.
 struct u32x4 { uint32_t x, y, z, w; };
+constexpr int MASK_ROUNDS = FHE_B200_MASK_ROUNDS;
 
 __host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
     // one 32x32->64 multiply (IMAD.WIDE.U32 on the device) instead of separate lo / hi products
@@ -21,9 +26,10 @@ __host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint3
     hi = (uint32_t)(p >> 32);
 }
 
-__host__ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
+template <int ROUNDS>
+__host__ __device__ __forceinline__ u32x4 philox4x32(u32x4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         mulhilo32(0xD2511F53u, c.x, hi0, lo0);
         mulhilo32(0xCD9E8D57u, c.z, hi1, lo1);
@@ -39,13 +45,17 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, ui
     return c;
 }
 
-// Round keys k + r*(W0,W1) depend only on the seed: hot loops expand them once per thread.
+__host__ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
+    return philox4x32<10>(c, k0, k1);
+}
+
+// Round keys k + r*(W0,W1) of the MASK generator depend only on the seed: hot loops expand them once per thread.
 struct PhiloxKeys {
-    uint32_t k0[10], k1[10];
+    uint32_t k0[MASK_ROUNDS], k1[MASK_ROUNDS];
     __host__ __device__ __forceinline__ explicit PhiloxKeys(uint64_t seed) {
         uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
 #pragma unroll
-        for (int r = 0; r < 10; ++r) {
+        for (int r = 0; r < MASK_ROUNDS; ++r) {
             k0[r] = a;
             k1[r] = b;
             a += 0x9E3779B9u;
@@ -54,10 +64,11 @@ struct PhiloxKeys {
     }
 };
 
+// mask block (MASK_ROUNDS rounds) from pre-expanded round keys
 __host__ __device__ __forceinline__ u32x4 rng_block(const PhiloxKeys& K, uint32_t domain, uint64_t obj, uint32_t blk) {
     u32x4 c{blk, (uint32_t)obj, (uint32_t)(obj >> 32), domain};
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < MASK_ROUNDS; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         mulhilo32(0xD2511F53u, c.x, hi0, lo0);
         mulhilo32(0xCD9E8D57u, c.z, hi1, lo1);
@@ -71,7 +82,7 @@ __host__ __device__ __forceinline__ u32x4 rng_block(const PhiloxKeys& K, uint32_
     return c;
 }
 
-// counter = (blk, obj_lo, obj_hi, domain), key = seed
+// counter = (blk, obj_lo, obj_hi, domain), key = seed; 10 rounds (secret key bits, noise)
 __host__ __device__ __forceinline__ u32x4 rng_block(uint64_t seed, uint32_t domain, uint64_t obj, uint32_t blk) {
     u32x4 c{blk, (uint32_t)obj, (uint32_t)(obj >> 32), domain};
     return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -182,7 +193,8 @@ __host__ __device__ __forceinline__ int64_t gaussian_i64(uint64_t seed, uint32_t
 
 // mask word w of ciphertext/row `obj`
 __host__ __device__ __forceinline__ uint64_t mask_word(uint64_t seed, uint32_t purpose, uint64_t obj, int64_t w) {
-    u32x4 r = rng_block(seed, FHE_B200_KIND_MASK | (purpose << 8), obj, (uint32_t)(w >> 1));
+    u32x4 c{(uint32_t)(w >> 1), (uint32_t)obj, (uint32_t)(obj >> 32), FHE_B200_KIND_MASK | (purpose << 8)};
+    u32x4 r = philox4x32<MASK_ROUNDS>(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     return (w & 1) ? hi64(r) : lo64(r);
 }
 

@@ -45,6 +45,13 @@ constexpr int ENC_WARPS = 8;
 #define LCS_UNROLL 4
 #endif
 constexpr int LCS_UNROLL_N = LCS_UNROLL;   // independent Philox blocks in flight per thread (seeded dot product)
+#ifndef LCS_MIN_CTAS
+#define LCS_MIN_CTAS 5      // resident CTAs per SM the seeded dot product is compiled for (A/B: tools/build_variant.py)
+#endif
+#ifndef ENC_SEEDED_UNROLL
+#define ENC_SEEDED_UNROLL 4
+#endif
+constexpr int ENC_SEEDED_UNROLL_N = ENC_SEEDED_UNROLL;   // ... per lane (seeded encryption)
 
 // The error terms come from the client's SECRET noise seed -- never from the public mask seed that travels with seeded
 // ciphertexts: an evaluator who could regenerate e would learn <a,s> + Delta*m exactly and solve for the key.
@@ -374,14 +381,125 @@ cudaError_t launch_lincomb_push(const uint64_t* d_ct, int64_t B, int d, int n, i
 // A fresh LWE ciphertext is (mask, body) with the mask a pure function of (seed, ciphertext id): the
 // "seeded" form keeps only the 8-byte body and lets the evaluator regenerate the mask.  For this
 // path it turns 1.46 MB per document into 1 KB (1 M documents = 1 GB instead of 1.46 TB, SURVEY.md
-// section 7.2) and moves the dot product from the HBM roofline to the integer pipe (10 Philox rounds
+// section 7.2) and moves the dot product from the HBM roofline to the integer pipe (MASK_ROUNDS = 7 Philox rounds
 // per 16 mask bytes).  Results are bit-identical to the materialised form.
 
 // client: bodies only.  lwe_body_noise_kernel writes plaintext + error, then one warp per ciphertext adds <a, s>
 // (exactly the arithmetic of warp_lwe_encrypt, nothing stored but the 8-byte body).
+//
+// The kernel is bound by the wide-multiplier pipe (fmaheavy; ncu profiles/r2_ncu_e2e_seeded_v1.txt), so it only
+// generates what <a, s> needs.  Philox is counter-based and the key is fixed for the whole launch: a block both of
+// whose key bits are 0 is never generated (a quarter of them for a uniform binary key), and a block with ONE key
+// bit set needs one 64-bit word, which is one of the two products of the last round.  The CTA sorts the blocks
+// into three lists in shared memory (both words / low word only / high word only); every word that is generated is
+// then added unconditionally -- no per-word select.  Wrapping adds commute, so the (unordered) lists give the same
+// body bit for bit.
+constexpr int ENC_MAX_BLOCKS = 2048;     // mask blocks per ciphertext the shared-memory lists hold (n <= 4096)
+static_assert(MASK_ROUNDS >= 3, "the block lists carry the first two rounds");
+
+// What rounds 1-2 of mask block `blk` contribute that does not depend on the ciphertext id (counter =
+// (blk, id_lo, id_hi, dom)): after round 1, z = hi(M0*blk) ^ dom ^ k1[0] and w = lo(M0*blk); round 2 multiplies that
+// z by M1.  Computed once per CTA and list entry, so a (ciphertext, block) pair costs rounds 3..MASK_ROUNDS only.
+struct __align__(16) EncEntry { uint32_t p_hi, p_lo, w1, blk; };
+
+// the words of a mask block that the key selects, summed.  WORDS: 3 = both, 1 = low, 2 = high.
+// (x1q_hi, x1q_lo) = M0 * x1 and y1 are the ciphertext's own share of rounds 1-2 (see the kernel).
+// one IMAD.WIDE.U32, spelled in PTX so that ptxas cannot split it into IMAD.HI + IMAD (it does when the low half
+// feeds an add, and both halves then occupy the multiplier)
+__device__ __forceinline__ void mulwide32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+}
+
+// Accumulator of selected mask words in two limbs: lo64 += low 32 bits of a word, hi32 += its high 32 bits (mod 2^32);
+// the sum is lo64 + (hi32 << 32).  Keeps the adds three-input IADD3s on the ALU pipe.
+struct WordSum {
+    uint64_t lo = 0;
+    uint32_t hi = 0;
+    __device__ __forceinline__ uint64_t value() const { return lo + ((uint64_t)hi << 32); }
+};
+
+// adds the words of a mask block that the key selects.  WORDS: 3 = both, 1 = low, 2 = high.
+// (x1q_hi, x1q_lo) = M0 * x1 and y1 are the ciphertext's own share of rounds 1-2 (see the kernel).
+template <int WORDS>
+__device__ __forceinline__ void mask_block_sum(WordSum& acc, const PhiloxKeys& K, const EncEntry e, uint32_t y1,
+                                               uint32_t x1q_hi, uint32_t x1q_lo) {
+    u32x4 c{e.p_hi ^ y1 ^ K.k0[1], e.p_lo, x1q_hi ^ e.w1 ^ K.k1[1], x1q_lo};   // state after round 2
+#pragma unroll
+    for (int r = 2; r < MASK_ROUNDS - 1; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulwide32(0xD2511F53u, c.x, hi0, lo0);
+        mulwide32(0xCD9E8D57u, c.z, hi1, lo1);
+        c = u32x4{hi1 ^ c.y ^ K.k0[r], lo1, hi0 ^ c.w ^ K.k1[r], lo0};
+    }
+    uint32_t wl0 = 0, wh0 = 0, wl1 = 0, wh1 = 0;
+    if (WORDS & 1) {   // low word = (hi1 ^ c.y ^ k0, lo1) of the last round
+        uint32_t hi1;
+        mulwide32(0xCD9E8D57u, c.z, hi1, wh0);
+        wl0 = hi1 ^ c.y ^ K.k0[MASK_ROUNDS - 1];
+    }
+    if (WORDS & 2) {   // high word = (hi0 ^ c.w ^ k1, lo0)
+        uint32_t hi0;
+        mulwide32(0xD2511F53u, c.x, hi0, wh1);
+        wl1 = hi0 ^ c.w ^ K.k1[MASK_ROUNDS - 1];
+    }
+    acc.lo += (uint64_t)wl0 + wl1;
+    acc.hi += wh0 + wh1;
+}
+
 __global__ void __launch_bounds__(ENC_WARPS * 32)
 lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, int64_t count, uint64_t enc_seed, uint64_t ct_base,
                           uint32_t purpose, uint64_t* __restrict__ bodies) {
+    extern __shared__ __align__(16) uint32_t enc_smem[];     // [3][nblk] EncEntry lists, then the packed key bits
+    __shared__ int cnt[4];
+    const int nblk = (n + 1) / 2;
+    EncEntry* list = reinterpret_cast<EncEntry*>(enc_smem);   // categories 1 (low), 2 (high), 3 (both)
+    uint32_t* skey = enc_smem + 3 * (size_t)nblk * (sizeof(EncEntry) / sizeof(uint32_t));
+    if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+    pack_key_bits(key, n, skey);
+    __syncthreads();
+    const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
+    const PhiloxKeys K(enc_seed);
+    for (int blk = threadIdx.x; blk < nblk; blk += blockDim.x) {
+        const int w = 2 * blk;
+        uint32_t b = (skey[w >> 5] >> (w & 31)) & 3u;
+        if (w + 1 >= n) b &= 1u;
+        if (b) {
+            uint32_t hi0, lo0, p_hi, p_lo;
+            mulhilo32(0xD2511F53u, (uint32_t)blk, hi0, lo0);
+            mulhilo32(0xCD9E8D57u, hi0 ^ dom ^ K.k1[0], p_hi, p_lo);
+            list[(b - 1) * nblk + atomicAdd(&cnt[b], 1)] = EncEntry{p_hi, p_lo, lo0, (uint32_t)blk};
+        }
+    }
+    __syncthreads();
+    const int n_lo = cnt[1], n_hi = cnt[2], n_both = cnt[3];
+    const EncEntry *l_lo = list, *l_hi = list + nblk, *l_both = list + 2 * nblk;
+    const int lane = threadIdx.x & 31;
+    for (int64_t c = (int64_t)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5); c < count; c += (int64_t)gridDim.x * ENC_WARPS) {
+        const uint64_t id = ct_base + (uint64_t)c;
+        const uint64_t pre = lane == 0 ? bodies[c] : 0;
+        // the ciphertext's share of rounds 1-2: x1 = hi(M1*id_hi) ^ id_lo ^ k0[0], y1 = lo(M1*id_hi), then M0 * x1
+        uint32_t h1, y1, q_hi, q_lo;
+        mulhilo32(0xCD9E8D57u, (uint32_t)(id >> 32), h1, y1);
+        mulhilo32(0xD2511F53u, h1 ^ (uint32_t)id ^ K.k0[0], q_hi, q_lo);
+        WordSum acc;
+#pragma unroll ENC_SEEDED_UNROLL_N
+        for (int i = lane; i < n_both; i += 32) mask_block_sum<3>(acc, K, l_both[i], y1, q_hi, q_lo);
+#pragma unroll ENC_SEEDED_UNROLL_N
+        for (int i = lane; i < n_lo; i += 32) mask_block_sum<1>(acc, K, l_lo[i], y1, q_hi, q_lo);
+#pragma unroll ENC_SEEDED_UNROLL_N
+        for (int i = lane; i < n_hi; i += 32) mask_block_sum<2>(acc, K, l_hi[i], y1, q_hi, q_lo);
+        const uint64_t dot = warp_sum_u64(acc.value());
+        if (lane == 0) bodies[c] = pre + dot;
+    }
+}
+
+// any n: every block generated, words selected by AND masks (the form the lists replace)
+__global__ void __launch_bounds__(ENC_WARPS * 32)
+lwe_encrypt_seeded_generic_kernel(const uint8_t* __restrict__ key, int n, int64_t count, uint64_t enc_seed, uint64_t ct_base,
+                                  uint32_t purpose, uint64_t* __restrict__ bodies) {
     extern __shared__ uint32_t skey[];
     pack_key_bits(key, n, skey);
     __syncthreads();
@@ -406,6 +524,23 @@ lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, int64_t count,
     }
 }
 
+static cudaError_t launch_encrypt_seeded_masks(const uint8_t* d_key, int n, int64_t count, uint64_t enc_seed, uint64_t ct_base,
+                                               uint32_t purpose, uint64_t* d_bodies, cudaStream_t s) {
+    const int nblk = (n + 1) / 2;
+    if (nblk > ENC_MAX_BLOCKS) {
+        size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
+        lwe_encrypt_seeded_generic_kernel<<<enc_grid(lwe_encrypt_seeded_generic_kernel, smem, count), ENC_WARPS * 32, smem, s>>>(
+            d_key, n, count, enc_seed, ct_base, purpose, d_bodies);
+        count_launch();
+        return cudaGetLastError();
+    }
+    size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t) + 3 * (size_t)nblk * sizeof(EncEntry);
+    lwe_encrypt_seeded_kernel<<<enc_grid(lwe_encrypt_seeded_kernel, smem, count), ENC_WARPS * 32, smem, s>>>(
+        d_key, n, count, enc_seed, ct_base, purpose, d_bodies);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // quantize (the UniformQuantizer rule of quantize_kernel) + plaintext + error in one pass:
 // the client path from float features to seeded ciphertexts needs no integer staging buffer
 __global__ void quantize_body_noise_kernel(const float* __restrict__ X, int64_t count, double scale, double zp, double qmin,
@@ -428,11 +563,7 @@ cudaError_t launch_lwe_encrypt_seeded_float(const uint8_t* d_key, int n, const f
                                                                              (double)qmax, shift, sigma_abs, noise_seed, ct_base,
                                                                              purpose, d_bodies);
     count_launch();
-    size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
-    lwe_encrypt_seeded_kernel<<<enc_grid(lwe_encrypt_seeded_kernel, smem, count), ENC_WARPS * 32, smem, s>>>(
-        d_key, n, count, enc_seed, ct_base, purpose, d_bodies);
-    count_launch();
-    return cudaGetLastError();
+    return launch_encrypt_seeded_masks(d_key, n, count, enc_seed, ct_base, purpose, d_bodies, s);
 }
 
 cudaError_t launch_lwe_encrypt_seeded(const uint8_t* d_key, int n, const int64_t* d_msgs, int64_t count, int shift,
@@ -442,11 +573,7 @@ cudaError_t launch_lwe_encrypt_seeded(const uint8_t* d_key, int n, const int64_t
     lwe_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_msgs, count, shift, sigma_abs, noise_seed, ct_base,
                                                                         purpose, d_bodies, 1);
     count_launch();
-    size_t smem = ((size_t)(n + 31) / 32 + 1) * sizeof(uint32_t);
-    lwe_encrypt_seeded_kernel<<<enc_grid(lwe_encrypt_seeded_kernel, smem, count), ENC_WARPS * 32, smem, s>>>(
-        d_key, n, count, enc_seed, ct_base, purpose, d_bodies);
-    count_launch();
-    return cudaGetLastError();
+    return launch_encrypt_seeded_masks(d_key, n, count, enc_seed, ct_base, purpose, d_bodies, s);
 }
 
 // word w of the materialised ciphertext `id` whose body is `body`
@@ -483,25 +610,122 @@ cudaError_t launch_lwe_expand_seeded(const uint64_t* d_bodies, int64_t count, in
 
 // server: out[b][m][:] = sum_j W[m][j] * expand(seed, ct_base + b*d + j)[:], masks regenerated on the fly.
 // Same thread -> (document, column pair) mapping as lincomb_kernel; no global loads except the d bodies.
+//
+// The kernel is bound by the wide-multiplier pipe (ncu, profiles/r2_ncu_e2e_seeded_v1.txt: math-pipe throttle is the
+// top stall), and besides Philox the u64 x i64 MACs were on that pipe too (one IMAD.WIDE + two IMAD + an add each).
+// Quantized weights span far less than 2^32, so the CTA shifts them to unsigned 32-bit values w' = w - min(w) and
+// accumulates  lo64 += x_lo * w'  (one IMAD.WIDE with 64-bit addend)  and  hi32 += x_hi * w'  (one IMAD);
+// sum_j w_j x_j = lo64 + (hi32 << 32) + min(w) * sum_j x_j  (mod 2^64, exact), and sum_j x_j is the second output
+// the two-output circuit needs anyway.  Rows whose weights span 2^32 or more take the plain 64-bit MAC.
+struct SeededRow {       // per weight row, CTA-uniform
+    int64_t wmin;
+    int narrow;          // max - min < 2^32
+};
+
+// Rounds 1-2 of a mask block split into what depends on the block only and what depends on the ciphertext only
+// (see EncEntry): the CTA computes the ciphertext share once per (document, j) it touches -- every thread of a document
+// needs the same one -- together with the shifted weight, so that the inner loop is one broadcast LDS.128 plus rounds
+// 3..MASK_ROUNDS: 10 wide multiplies per block instead of 11 (+1 that ptxas split), on a kernel whose time is set by
+// the number of IMAD.WIDE it issues (~7 cycles each per scheduler, measured: profiles/r2_seeded_kernel_times.txt).
+struct __align__(16) CtShare { uint32_t y1, q_hi, q_lo, w; };
+constexpr int LCS_MAX_TABLE = 2048;      // (document, j) entries a CTA may hold: 32 KB
+
 template <int M, bool SECOND_IS_SUM, bool PUSH>
-__global__ void __launch_bounds__(LC_THREADS)
+__global__ void __launch_bounds__(LC_THREADS, PUSH ? 4 : LCS_MIN_CTAS)
 lincomb_seeded_kernel(const uint64_t* __restrict__ bodies, int d, int n, int64_t stride, int64_t total_vecs,
                       uint64_t enc_seed, uint64_t ct_base, uint32_t purpose, const int64_t* __restrict__ W,
-                      uint64_t bias0, uint64_t bias1, uint64_t* __restrict__ out, const PushArgs push) {
-    extern __shared__ int64_t sW[];
+                      uint64_t bias0, uint64_t bias1, uint64_t* __restrict__ out, const PushArgs push, int table_docs) {
+    extern __shared__ __align__(16) int64_t sW[];    // [M*d] i64 weights, [table_docs*d] CtShare, [d] u32 (second row)
+    __shared__ SeededRow rows[2];
+    CtShare* tab = reinterpret_cast<CtShare*>(sW + ((M * d + 1) & ~1));     // 16-byte aligned
+    uint32_t* sW32b = reinterpret_cast<uint32_t*>(tab + (size_t)table_docs * d);
     for (int i = threadIdx.x; i < M * d; i += blockDim.x) sW[i] = W[i];
     __syncthreads();
-    const int64_t g = (int64_t)blockIdx.x * LC_THREADS + threadIdx.x;
+    if (threadIdx.x < 32 * M) {                      // warp m: range of row m
+        const int m = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        int64_t lo = INT64_MAX, hi = INT64_MIN;
+        for (int j = lane; j < d; j += 32) { lo = min(lo, sW[m * d + j]); hi = max(hi, sW[m * d + j]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) { rows[m].wmin = lo; rows[m].narrow = ((uint64_t)hi - (uint64_t)lo) < (1ULL << 32); }
+    }
+    __syncthreads();
+    constexpr int MW = (M == 2 && !SECOND_IS_SUM) ? 2 : 1;    // rows that carry real weights
+    bool narrow = rows[0].narrow && table_docs > 0;
+    if (MW == 2) narrow = narrow && rows[1].narrow;
+    const int vecs = (int)(stride >> 1);
+    const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
+    const PhiloxKeys K(enc_seed);
+    const int64_t g0 = (int64_t)blockIdx.x * LC_THREADS;
+    const int64_t b_first = g0 / vecs;
+    if (narrow) {
+        const int64_t g_last = min(g0 + LC_THREADS, total_vecs) - 1;
+        const int nd = (int)(g_last / vecs - b_first) + 1;            // documents this CTA touches (<= table_docs)
+        for (int i = threadIdx.x; i < nd * d; i += blockDim.x) {
+            const int j = i % d;
+            const uint64_t id = ct_base + (uint64_t)(b_first * d + i);
+            uint32_t h1, y1, q_hi, q_lo;
+            mulwide32(0xCD9E8D57u, (uint32_t)(id >> 32), h1, y1);
+            mulwide32(0xD2511F53u, h1 ^ (uint32_t)id ^ K.k0[0], q_hi, q_lo);
+            tab[i] = CtShare{y1, q_hi, q_lo, (uint32_t)((uint64_t)sW[j] - (uint64_t)rows[0].wmin)};
+        }
+        if (MW == 2)
+            for (int j = threadIdx.x; j < d; j += blockDim.x) sW32b[j] = (uint32_t)((uint64_t)sW[d + j] - (uint64_t)rows[1].wmin);
+        __syncthreads();
+    }
+    const int64_t g = g0 + threadIdx.x;
     if (g < total_vecs) {
-        const int vecs = (int)(stride >> 1);
         const int64_t b = g / vecs;
         const int w0 = 2 * (int)(g - b * vecs);
-        const uint32_t dom = FHE_B200_KIND_MASK | (purpose << 8);
         const uint64_t id0 = ct_base + (uint64_t)b * d;
         const bool has_body = (w0 == n) || (w0 + 1 == n);
-        const PhiloxKeys K(enc_seed);
         uint64_t a0x = 0, a0y = 0, a1x = 0, a1y = 0;
-        if (w0 <= n) {
+        if (w0 <= n && narrow) {
+            // the block's share of rounds 1-2
+            uint32_t hi0, w1, p_hi, p_lo;
+            mulwide32(0xD2511F53u, (uint32_t)(w0 >> 1), hi0, w1);
+            mulwide32(0xCD9E8D57u, hi0 ^ dom ^ K.k1[0], p_hi, p_lo);
+            const CtShare* row = tab + (size_t)(b - b_first) * d;
+            uint64_t l0x = 0, l0y = 0, l1x = 0, l1y = 0, sx = 0, sy = 0;   // low-limb accumulators, plain sums
+            uint32_t h0x = 0, h0y = 0, h1x = 0, h1y = 0;                   // high-limb accumulators (mod 2^32)
+#pragma unroll LCS_UNROLL_N
+            for (int j = 0; j < d; ++j) {
+                const CtShare e = row[j];
+                u32x4 c{p_hi ^ e.y1 ^ K.k0[1], p_lo, e.q_hi ^ w1 ^ K.k1[1], e.q_lo};   // state after round 2
+#pragma unroll
+                for (int r = 2; r < MASK_ROUNDS; ++r) {
+                    uint32_t m0h, m0l, m1h, m1l;
+                    mulwide32(0xD2511F53u, c.x, m0h, m0l);
+                    mulwide32(0xCD9E8D57u, c.z, m1h, m1l);
+                    c = u32x4{m1h ^ c.y ^ K.k0[r], m1l, m0h ^ c.w ^ K.k1[r], m0l};
+                }
+                const uint64_t body = has_body ? bodies[b * d + j] : 0;
+                const uint64_t x = w0 < n ? lo64(c) : (w0 == n ? body : 0);
+                const uint64_t y = w0 + 1 < n ? hi64(c) : (w0 + 1 == n ? body : 0);
+                const uint32_t w = e.w;
+                l0x += (uint64_t)(uint32_t)x * w;  h0x += (uint32_t)(x >> 32) * w;
+                l0y += (uint64_t)(uint32_t)y * w;  h0y += (uint32_t)(y >> 32) * w;
+                sx += x;
+                sy += y;
+                if (MW == 2) {
+                    const uint32_t wb = sW32b[j];
+                    l1x += (uint64_t)(uint32_t)x * wb;  h1x += (uint32_t)(x >> 32) * wb;
+                    l1y += (uint64_t)(uint32_t)y * wb;  h1y += (uint32_t)(y >> 32) * wb;
+                }
+            }
+            const uint64_t m0 = (uint64_t)rows[0].wmin;
+            a0x = l0x + ((uint64_t)h0x << 32) + m0 * sx;
+            a0y = l0y + ((uint64_t)h0y << 32) + m0 * sy;
+            if (M == 2 && SECOND_IS_SUM) { a1x = sx; a1y = sy; }
+            if (MW == 2) {
+                const uint64_t m1 = (uint64_t)rows[1].wmin;
+                a1x = l1x + ((uint64_t)h1x << 32) + m1 * sx;
+                a1y = l1y + ((uint64_t)h1y << 32) + m1 * sy;
+            }
+        } else if (w0 <= n) {
 #pragma unroll LCS_UNROLL_N
             for (int j = 0; j < d; ++j) {
                 uint64_t x, y;
@@ -541,14 +765,18 @@ static cudaError_t launch_lincomb_seeded_impl(const uint64_t* d_bodies, int64_t 
     const int64_t grid64 = (total_vecs + LC_THREADS - 1) / LC_THREADS;
     if (grid64 > 0x7fffffffLL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)grid64;
-    const size_t smem = (size_t)M * d * sizeof(int64_t);
+    // documents a 256-thread CTA can touch: its first thread may sit anywhere inside a document
+    const int64_t vecs = stride / 2;
+    int table_docs = (int)((LC_THREADS + vecs - 2) / vecs) + 1;
+    if ((int64_t)table_docs * d > LCS_MAX_TABLE) table_docs = 0;       // tiny ciphertexts x huge d: plain path
+    const size_t smem = (size_t)((M * d + 1) & ~1) * sizeof(int64_t) + (size_t)table_docs * d * sizeof(CtShare) + (size_t)d * sizeof(uint32_t);
     const uint64_t b0 = (uint64_t)bias0 << shift, b1 = (uint64_t)bias1 << shift;
     if (M == 1)
-        lincomb_seeded_kernel<1, false, PUSH><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out, push);
+        lincomb_seeded_kernel<1, false, PUSH><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out, push, table_docs);
     else if (second_is_sum)
-        lincomb_seeded_kernel<2, true, PUSH><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out, push);
+        lincomb_seeded_kernel<2, true, PUSH><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out, push, table_docs);
     else
-        lincomb_seeded_kernel<2, false, PUSH><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out, push);
+        lincomb_seeded_kernel<2, false, PUSH><<<grid, LC_THREADS, smem, s>>>(d_bodies, d, n, stride, total_vecs, enc_seed, ct_base, purpose, d_W, b0, b1, d_out, push, table_docs);
     count_launch();
     return cudaGetLastError();
 }

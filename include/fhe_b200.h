@@ -36,7 +36,9 @@ enum {
     FHE_B200_ERR_STATE = 4    /* object used before it was initialised */
 };
 
-/* RNG stream tags (DESIGN.md "Deterministic randomness") */
+/* RNG stream tags (DESIGN.md "Deterministic randomness").  Philox4x32 counter = (block, object_lo, object_hi,
+ * kind | purpose << 8), key = seed.  Secret streams (SK, NOISE): 10 rounds; public MASK stream: FHE_B200_MASK_ROUNDS. */
+#define FHE_B200_MASK_ROUNDS 7
 enum { FHE_B200_KIND_SK = 1, FHE_B200_KIND_MASK = 2, FHE_B200_KIND_NOISE = 3 };
 enum { FHE_B200_PUR_INPUT = 0, FHE_B200_PUR_KSK = 1, FHE_B200_PUR_BSK = 2, FHE_B200_PUR_BSK2 = 3, FHE_B200_PUR_GLWE = 4 };
 

@@ -20,12 +20,14 @@
 #endif
 
 /* ------------------------------------------------------------------ */
-/* Philox4x32-10 (Salmon et al., SC'11), counter-based, reproducible    */
+/* Philox4x32-R (Salmon et al., SC'11), counter-based, reproducible.   */
+/* 10 rounds for secret streams (key bits, noise); ORC_MASK_ROUNDS = 7  */
+/* (the paper's smallest Crush-resistant count) for the PUBLIC masks.   */
 /* ------------------------------------------------------------------ */
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+void orc_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -39,11 +41,15 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* counter = (blk, obj_lo, obj_hi, domain); key = seed */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    orc_philox4x32_r(ctr, key, 10, out);
+}
+
+/* counter = (blk, obj_lo, obj_hi, domain); key = seed; round count by stream kind */
 void orc_rng_block(uint64_t seed, uint32_t domain, uint64_t obj, uint32_t blk, uint32_t out[4]) {
     uint32_t ctr[4] = {blk, (uint32_t)obj, (uint32_t)(obj >> 32), domain};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    orc_philox4x32_10(ctr, key, out);
+    orc_philox4x32_r(ctr, key, (domain & 0xff) == ORC_KIND_MASK ? ORC_MASK_ROUNDS : 10, out);
 }
 
 /* ------------------------------------------------------------------ */

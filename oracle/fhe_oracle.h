@@ -27,6 +27,7 @@ extern "C" {
 
 /* RNG domain tags (counter word c3 = kind | purpose << 8) -- the spec is in DESIGN.md */
 enum { ORC_KIND_SK = 1, ORC_KIND_MASK = 2, ORC_KIND_NOISE = 3 };
+#define ORC_MASK_ROUNDS 7 /* Philox rounds of the public mask stream; secret streams use 10 */
 enum { ORC_PUR_INPUT = 0, ORC_PUR_KSK = 1, ORC_PUR_BSK = 2, ORC_PUR_BSK2 = 3, ORC_PUR_GLWE = 4 };
 
 typedef struct {
@@ -44,6 +45,7 @@ typedef struct {
 
 /* ---- deterministic PRNG ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void orc_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]);
 void orc_rng_block(uint64_t seed, uint32_t domain, uint64_t obj, uint32_t blk, uint32_t out[4]);
 double orc_det_log(double x);
 double orc_det_cos2pi_k53(uint64_t k53);

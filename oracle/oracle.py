@@ -52,6 +52,7 @@ def lib() -> C.CDLL:
         u64p, i64p, f64p = C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_double)
         pp = C.POINTER(PBSParams)
         L.orc_philox4x32_10.argtypes = [u32p, u32p, u32p]
+        L.orc_philox4x32_r.argtypes = [u32p, u32p, C.c_int, u32p]
         L.orc_rng_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, u32p]
         L.orc_det_log.argtypes = [C.c_double]; L.orc_det_log.restype = C.c_double
         L.orc_det_cos2pi_k53.argtypes = [C.c_uint64]; L.orc_det_cos2pi_k53.restype = C.c_double
@@ -91,10 +92,11 @@ def _p(a: np.ndarray, ct):
 
 
 # ----------------------------------------------------------------------------- RNG
-def philox(ctr, key) -> np.ndarray:
+def philox(ctr, key, rounds: int = 10) -> np.ndarray:
+    """Philox4x32-R: 10 rounds for secret streams, MASK_ROUNDS for the public mask stream."""
     c = np.asarray(ctr, dtype=np.uint32); k = np.asarray(key, dtype=np.uint32)
     out = np.zeros(4, dtype=np.uint32)
-    lib().orc_philox4x32_10(_p(c, C.c_uint32), _p(k, C.c_uint32), _p(out, C.c_uint32))
+    lib().orc_philox4x32_r(_p(c, C.c_uint32), _p(k, C.c_uint32), int(rounds), _p(out, C.c_uint32))
     return out
 
 

@@ -32,6 +32,12 @@ def build() -> dict:
         {"ctr": [0xffffffff] * 4, "key": [0xffffffff] * 2, "out": [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]},
         {"ctr": [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], "key": [0xa4093822, 0x299f31d0],
          "out": [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]},
+        # Random123 kat_vectors, "philox4x32 7": the round count of the public mask stream (FHE_B200_MASK_ROUNDS)
+        {"rounds": 7, "ctr": [0, 0, 0, 0], "key": [0, 0], "out": [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]},
+        {"rounds": 7, "ctr": [0xffffffff] * 4, "key": [0xffffffff] * 2,
+         "out": [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]},
+        {"rounds": 7, "ctr": [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], "key": [0xa4093822, 0x299f31d0],
+         "out": [0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]},
     ]
     g["gaussian"] = {"seed": 123, "domain": 3, "sigma_abs": 1e6,
                      "first8": [O.gaussian(123, 3, i, 0, 1e6) for i in range(8)],

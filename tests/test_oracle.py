@@ -19,7 +19,8 @@ def h(a):
 
 def test_philox_random123_known_answers(O):
     for kat in GOLD["philox_kat"]:
-        assert O.philox(kat["ctr"], kat["key"]).tolist() == kat["out"]
+        assert O.philox(kat["ctr"], kat["key"], kat.get("rounds", 10)).tolist() == kat["out"]
+    assert {k.get("rounds", 10) for k in GOLD["philox_kat"]} == {7, 10}    # secret streams and the public mask stream
 
 
 def test_deterministic_log_and_cos_accuracy(O):
