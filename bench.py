@@ -5,14 +5,20 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the CPU arm (oracle port on the host cores)
 
-Workload (BASELINE.json configs[1]): `search` over DOCS synthetic encrypted documents per
-GPU, d=128 features, 8-bit quantization.  A *step* is one pass of the encrypted-compare hot
-path over all resident documents: the encrypted dot product of every document's
-ciphertexts with the quantized weights (server), then decrypt + dequantize of the encrypted
-scores (client kernels).  `value` times that with ciphertexts already resident in HBM;
-`e2e` times FHESimilarityModel.predict_encrypted-style calls with HOST float buffers
-(quantize -> encrypt -> dot -> decrypt on the device, H2D/D2H inside the timed region) plus
-the host-side threshold / sort / top-k of the search.
+A *step* is one pass of the encrypted-compare hot path over all resident documents: the encrypted
+dot product of every document's ciphertexts with the quantized weights (server), then decrypt +
+dequantize of the encrypted scores (client kernels).  `value` times that with ciphertexts already
+resident in HBM; `e2e` times the public call with HOST buffers (quantize -> encrypt -> dot -> decrypt on
+the device, H2D/D2H inside the timed region) plus the host-side threshold / sort / top-k.
+
+Workloads (--workload auto picks by N):
+  N = 1   BASELINE.json configs[1]: `search` top-k=3 over 1000 synthetic encrypted documents (d=128, 8-bit),
+          expanded ciphertexts, HBM-bound dot product.  e2e = FHESimilarityModel.predict_encrypted.
+          Sub-records: configs[3] on one GPU (1 M seeded documents) and one GPU's share of configs[4].
+  N > 1   BASELINE.json configs[3]: ONE collection of 1 M synthetic encrypted documents (seeded ciphertexts),
+          contiguous cost-weighted shards over the N GPUs (strong scaling), scores pushed to the client GPU's
+          score board.  e2e = ShardedSearch.search(): query in host memory -> ranked ids on the client.
+          Sub-records: the 1000-documents-per-GPU weak step of round 1, and configs[4] (d=256, 12-bit).
 """
 from __future__ import annotations
 
@@ -34,14 +40,20 @@ D_FEATURES = 128
 N_BITS = 8
 # fixed seeds are an explicit opt-in for a reproducible benchmark; the library's defaults come from the OS CSPRNG
 DATA_SEED, KEY_SEED, ENC_SEED, EVK_SEED, NOISE_SEED = 20261018, 0x5EED0001, 0x5EED0002, 0x5EED0003, 0x5EED0004
-NCU_DRAM_BYTES_PER_DOC = 1475986  # (1.458192 GB read + 17.794 MB written) / 1000 documents, profiles/r1_ncu_lincomb_decrypt_v3.txt
+# measured DRAM traffic of one lincomb_kernel launch per document, keyed by (lwe n, outputs M, d): dram__bytes_read.sum +
+# dram__bytes_write.sum of an `ncu --set full` capture; shapes without a capture report traffic = null
+NCU_TRAFFIC = {(1423, 2, 128): (1475986, "profiles/r1_ncu_lincomb_decrypt_v3.txt ((1.458192 GB read + 17.794 MB written) / 1000 documents)")}
+TOTAL_DOCS_CONFIG4 = 1_000_000       # BASELINE.json configs[3]
+TOTAL_DOCS_CONFIG5 = 100_000         # BASELINE.json configs[4], on 8 GPUs: 12 500 per GPU
+D_CONFIG5, BITS_CONFIG5 = 256, 12
+DOC_BLOCK = 8192                     # documents per generator block of the large synthetic collections
 METRIC = "encrypted_comparisons_per_sec"
 UNIT = "comparisons/s"
 
 
-def build_model(device=None):
+def build_model(device=None, d=D_FEATURES, n_bits=N_BITS):
     from fhe_icp_b200 import FHESimilarityModel
-    m = FHESimilarityModel(input_dim=D_FEATURES, n_bits=N_BITS, seed=DATA_SEED, key_seed=KEY_SEED, enc_seed=ENC_SEED,
+    m = FHESimilarityModel(input_dim=d, n_bits=n_bits, seed=DATA_SEED, key_seed=KEY_SEED, enc_seed=ENC_SEED,
                            noise_seed=NOISE_SEED, ct_start=0, device=device, verbose=False)
     X, _ = m.train()
     m.compile(X[:10])
@@ -61,6 +73,39 @@ def synthetic_docs(n_docs: int, seed: int):
     docs[mask] = q + 0.2 * rng.randn(int(mask.sum()), D_FEATURES)
     docs /= np.linalg.norm(docs, axis=1, keepdims=True)
     return q, docs, (q[None, :] * docs).astype(np.float32)
+
+
+def collection_query(d: int, seed: int) -> np.ndarray:
+    q = np.random.default_rng(seed).standard_normal(d, dtype=np.float32)
+    return q / np.linalg.norm(q)
+
+
+def collection_rows(lo: int, hi: int, d: int, seed: int, q: np.ndarray) -> np.ndarray:
+    """Documents [lo, hi) of a large synthetic collection (unit norm, half of them correlated with the query, as in
+    the reference's generator fhe_similarity.py:41-51).  Generated block by block from per-block seeds, so that any
+    rank can produce exactly its own rows -- and the client every row, for the exactness check -- whatever the
+    sharding."""
+    out = np.empty((max(hi - lo, 0), d), dtype=np.float32)
+    for blk in range(lo // DOC_BLOCK, (hi + DOC_BLOCK - 1) // DOC_BLOCK if hi > lo else 0):
+        rng = np.random.default_rng([seed, blk])
+        docs = rng.standard_normal((DOC_BLOCK, d), dtype=np.float32)
+        mask = rng.random(DOC_BLOCK) > 0.5
+        docs[mask] = q + np.float32(0.2) * rng.standard_normal((int(mask.sum()), d), dtype=np.float32)
+        docs /= np.linalg.norm(docs, axis=1, keepdims=True)
+        a, b = max(lo, blk * DOC_BLOCK), min(hi, (blk + 1) * DOC_BLOCK)
+        out[a - lo: b - lo] = docs[a - blk * DOC_BLOCK: b - blk * DOC_BLOCK]
+    return out
+
+
+def weak_collection_rows(lo: int, hi: int, docs_per_gpu: int) -> np.ndarray:
+    """Rows [lo, hi) of the weak-scaling collection: block r = synthetic_docs(docs_per_gpu, DATA_SEED + 1 + r), the
+    round-1 per-rank data, concatenated (so that N = 1 is exactly configs[1])."""
+    parts = []
+    for r in range(lo // docs_per_gpu, (hi + docs_per_gpu - 1) // docs_per_gpu if hi > lo else 0):
+        X = synthetic_docs(docs_per_gpu, DATA_SEED + 1 + r)[2]
+        a, b = max(lo, r * docs_per_gpu), min(hi, (r + 1) * docs_per_gpu)
+        parts.append(X[a - r * docs_per_gpu: b - r * docs_per_gpu])
+    return np.concatenate(parts) if parts else np.zeros((0, D_FEATURES), dtype=np.float32)
 
 
 def top_k(scores: np.ndarray, k: int, min_similarity: float):
@@ -177,7 +222,15 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     model, _ = build_model()
-    _, _, X = synthetic_docs(args.docs, DATA_SEED + 1)
+    wl = resolve_workload(args)
+    if wl == "config2":
+        X = weak_collection_rows(0, args.docs, args.docs)
+        what = f"the {args.docs}-document workload tiled"
+    else:   # a bounded sample of the same collection the GPU arm shards: its first documents
+        q4 = collection_query(D_FEATURES, DATA_SEED + 77)
+        n = min(args.total_docs, 4096)
+        X = q4[None, :] * collection_rows(0, n, D_FEATURES, DATA_SEED + 77, q4)
+        what = f"the first {n} of the {args.total_docs} documents, tiled"
     vals = []
     per_step = min(args.cpu_seconds, max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup))))
     rows = 0
@@ -190,11 +243,12 @@ def run_reference_arm(args):
     c = model.model.fhe_circuit
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * rows / value, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * rows / value, "higher_is_better": True,
+        "scaling": "weak" if wl == "config2" else "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args, c),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{rows} documents per step (the {args.docs}-document workload tiled), quantize+encrypt+dot+decrypt, "
+                         "sample": f"{rows} documents per step ({what}), quantize+encrypt+dot+decrypt, "
                                    "oracle/fhe_oracle.c with OpenMP on all host cores (Concrete itself is not installable)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "published_reference": {"value": 5.0, "unit": UNIT, "note": "1/0.20 s per 8-bit sample, hardware unstated "
@@ -204,99 +258,159 @@ def run_reference_arm(args):
     return 0
 
 
+def resolve_workload(args) -> str:
+    """config2 = BASELINE.json configs[1] (1000 documents per GPU, weak); config4 = configs[3] (one 1 M-document
+    collection sharded over the GPUs, strong).  auto: config2 on one GPU, config4 on several."""
+    if args.workload != "auto":
+        return args.workload
+    return "config2" if args.gpus <= 1 else "config4"
+
+
 def workload_config(args, c):
-    return {"workload": f"search top-k=3 over {args.docs} synthetic encrypted documents per GPU "
-                        "(BASELINE.json configs[1])",
-            "docs_per_gpu": args.docs, "d": D_FEATURES, "n_bits": N_BITS, "lwe_n": c.lwe.n,
-            "ciphertext_words": c.lwe.stride, "log2_delta": c.lwe.shift, "log2_sigma": round(c.lwe.log2_sigma, 2),
-            "outputs_per_comparison": 2 if c.two_outputs else 1,
-            "bytes_per_comparison": comparison_bytes(c),
-            "multi_gpu": {
-                "push": "contiguous document shards; the dot-product kernel of every rank stores its encrypted scores "
-                        "(32-bit wire form) into the client GPU's score board over NVLink (cudaIpc peer memory) and flags "
-                        "their arrival; the client decrypts them under the next step's dot products; no collective",
-                "local": "single GPU: scores decrypted in place",
-            }.get(getattr(args, "_gather_mode", "local"),
-                  "contiguous document shards; encrypted scores (32-bit wire form) gathered to the client rank "
-                  "over NCCL and decrypted there, overlapped with the next step"),
-            "gather_mode": getattr(args, "_gather_mode", "local"),
-            "l2_policy": "inputs larger than L2 (ciphertext set per step >= 1 GB vs 126 MB L2), no flush",
-            "seeds": {"data": DATA_SEED, "key": KEY_SEED, "enc": ENC_SEED}}
+    """The `config` object of the JSON line.  A pure function of the command line and the compiled circuit, so that
+    the GPU arm and the CPU reference arm print the same object for the same N."""
+    wl = resolve_workload(args)
+    M = 2 if c.two_outputs else 1
+    cfg = {"d": D_FEATURES, "n_bits": N_BITS, "lwe_n": c.lwe.n, "ciphertext_words": c.lwe.stride,
+           "log2_delta": c.lwe.shift, "log2_sigma": round(c.lwe.log2_sigma, 2), "outputs_per_comparison": M,
+           "bytes_per_comparison": comparison_bytes(c), "mask_generator": "Philox4x32-7 (public masks), Philox4x32-10 (secret streams)",
+           "seeds": {"data": DATA_SEED, "key": KEY_SEED, "enc": ENC_SEED}}
+    if wl == "config2":
+        cfg.update({"workload": f"search top-k=3 over {args.docs} synthetic encrypted documents per GPU "
+                                "(BASELINE.json configs[1])",
+                    "docs_per_gpu": args.docs, "total_docs": args.docs * max(1, args.gpus), "ciphertext_format": "expanded",
+                    "l2_policy": "inputs larger than L2 (ciphertext set per step >= 1 GB vs 126 MB L2), no flush"})
+    else:
+        cfg.update({"workload": f"search top-k=3 over ONE collection of {args.total_docs} synthetic encrypted documents, "
+                                f"contiguous document shards over {max(1, args.gpus)} GPU(s) (BASELINE.json configs[3])",
+                    "total_docs": args.total_docs, "ciphertext_format": "seeded (8 B per ciphertext + public mask seed)",
+                    "l2_policy": "no reuse between steps: masks are regenerated, never read; bodies 1 KB per document"})
+    if args.gpus > 1:
+        cfg["multi_gpu"] = ("one process per GPU; every rank evaluates its shard and its dot-product kernel stores the encrypted "
+                            "scores (32-bit wire form) into the client GPU's score board over NVLink (cudaIpc peer memory) and "
+                            "flags their arrival; the client decrypts them under the next step's dot products; no data-path "
+                            "collective (NCCL: setup and the max-over-ranks timing only)")
+    return cfg
 
 
 def comparison_bytes(c) -> int:
     M = 2 if c.two_outputs else 1
-    return (D_FEATURES + M) * (c.lwe.n + 1) * 8
+    return (c.spec.d + M) * (c.lwe.n + 1) * 8
 
 
 # ------------------------------------------------------------------------------------- GPU arm
-def run_b200_arm(args):
+class Ranks:
+    """Process-group facts of this run (one process per GPU)."""
+
+    def __init__(self):
+        import torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dev = torch.device("cuda", self.local_rank)
+
+    def barrier(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+
+    def max_over_ranks(self, x: float) -> float:
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure_client_rho(model, fmt: str, sample_docs: int = 4000) -> float:
+    """Client cost per document / server cost per document, measured on this GPU: the fused decrypt of the 32-bit wire
+    form against the dot product of the same documents.  Feeds sharded_search.client_cost_weights: the client rank
+    decrypts every document of the collection, so it takes a smaller shard."""
+    import torch
+    c = model.model.fhe_circuit
+    M = 2 if c.two_outputs else 1
+    dev = model.dev
+    X = weak_collection_rows(0, sample_docs, sample_docs) if c.spec.d == D_FEATURES else \
+        np.zeros((sample_docs, c.spec.d), dtype=np.float32)
+    saved = c.ct_counter
+    c.ct_counter = 1 << 50
+    ct = model.encrypt(X, seeded=(fmt == "seeded"))
+    c.ct_counter = saved
+    out = torch.empty((sample_docs, M, c.lwe.stride), dtype=torch.int64, device=dev)
+    out32 = torch.empty((sample_docs, M, c.lwe.stride), dtype=torch.int32, device=dev)
+
+    def ev(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    t_srv = ev(lambda: model.run(ct, out=out))
+    model.compress_scores(out, out32)
+    t_cli = ev(lambda: _decrypt_device(model, out32, wire32=True))
+    return t_cli / t_srv
+
+
+def sharded_steps(R: Ranks, model, rows_fn, total_docs: int, fmt: str, steps: int, warmup: int, gather_mode: str,
+                  rho: float, ctx, verify_chunk: int = 65536):
+    """The device-resident measurement: `total_docs` documents in contiguous (cost-weighted) shards, every rank's
+    ciphertexts resident; K timed steps of dot products (+ gather to the client + client decrypt).  Returns a dict;
+    `value` = total_docs * K / max-over-ranks time.
+
+    rows_fn(lo, hi) -> float32 [hi-lo, d]: the clear products X of documents [lo, hi) (what the reference feeds the
+    circuit, batch_operations.py:273)."""
     import torch
     import torch.distributed as dist
-    from fhe_icp_b200 import _native as N
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the contract is ONE JSON line on stdout, and NCCL logs to stdout by default: its log (INFO unless the caller
-        # chose a level) goes to stderr instead, where a driver can still read the communicator / rank lines
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        # NCCL's stream (and the post stream below) run at high priority: the dot-product kernel keeps
-        # thousands of CTAs queued, and equal-priority kernels only start once those are all dispatched
-        opts = dist.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = True
-        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-
-    model, _ = build_model(device=local_rank)
+    from fhe_icp_b200.sharded_search import client_cost_weights, shard_bounds
     c = model.model.fhe_circuit
-    ctx = N.context(local_rank)
-    # each rank owns a contiguous shard of the collection (weak scaling: DOCS per GPU)
-    _, _, X = synthetic_docs(args.docs, DATA_SEED + 1 + rank)
-    B = args.docs
-    M = 2 if c.two_outputs else 1
-
-    # resident ciphertexts (client-side encryption happens once, outside the timed region)
-    c.ct_counter = rank * (1 << 40)
-    seeded = args.format == "seeded"
-    ct = model.encrypt(X, seeded=seeded)
-    out = torch.empty((B, M, c.lwe.stride), dtype=torch.int64, device=dev)
+    d, M = c.spec.d, (2 if c.two_outputs else 1)
+    rank, world, dev = R.rank, R.world, R.dev
+    weights = client_cost_weights(world, 0, rho)
+    spans = [shard_bounds(total_docs, world, r, weights) for r in range(world)]
+    lo, hi = spans[rank]
+    B = hi - lo
+    rows_max = max(h - l for l, h in spans)
+    X = rows_fn(lo, hi)
+    seeded = fmt == "seeded"
+    c.ct_counter = lo * d                 # ciphertext (document, j) has id document*d + j whatever the sharding
+    ct = model.encrypt(X, seeded=seeded) if B else None
     torch.cuda.synchronize()
 
-    # Multi-GPU step: every rank evaluates its shard (server) and the encrypted scores reach the client
-    # rank, which decrypts all of them.
-    #   push (default): the dot-product kernel itself stores the scores, in the 32-bit wire form, into the
-    #     client GPU's score board over NVLink and flags their arrival (fhe_icp_b200/score_board.py); the
-    #     client's wait + decrypt + credit kernels of step i run on a second stream under the dot products
-    #     of step i+1.  No collective, no extra pass over the scores.
-    #   all_gather / gather: scores written locally, compressed (modulus switch to 32 bits) and moved by
-    #     NCCL on a high-priority stream, overlapped with step i+1 (double-buffered outputs).
-    mode = args.gather_mode if world > 1 else "local"
+    mode = gather_mode if world > 1 else "local"
+    if mode == "push" and not c.wire32_supported:
+        mode = "gather"                   # the score board carries the 32-bit wire form only
+    wire32 = bool(c.wire32_supported)
     board = None
     if mode == "push":
         from fhe_icp_b200.score_board import PeerScoreBoard
         try:   # setup is collective and fails on every rank together (score_board.py), so all ranks take the same path
-            board = PeerScoreBoard(model, B, client_rank=0)
+            board = PeerScoreBoard(model, rows_max, client_rank=0)
         except Exception as e:  # e.g. no peer access between the GPUs of this box: NCCL path instead
             print(f"bench.py: rank {rank}: peer score board unavailable ({e}); using all_gather", file=sys.stderr)
             board, mode = None, "all_gather"
     nccl = mode in ("gather", "all_gather")
-    outs = [out, torch.empty_like(out)] if nccl else [out]
-    # scores travel in the 32-bit wire form (modulus switch 2^64 -> 2^32) and only to the client rank:
-    # at 8 GPUs the client's inbound NVLink would otherwise carry 160 MB per 0.22 ms step
-    outs32 = [torch.empty(o.shape, dtype=torch.int32, device=dev) for o in outs] if nccl else None
+    nbuf = 2 if nccl else 1
+    # NCCL forms need equal contributions: outputs padded to the largest shard
+    outs = [torch.zeros((rows_max if nccl else max(B, 1), M, c.lwe.stride), dtype=torch.int64, device=dev) for _ in range(nbuf)] \
+        if mode != "push" else []
+    wdt = torch.int32 if wire32 else torch.int64
+    outs32 = [torch.zeros(o.shape, dtype=torch.int32, device=dev) for o in outs] if (nccl and wire32) else None
     allg = mode == "all_gather"
-    gathered = [torch.empty((world * B, M, c.lwe.stride), dtype=torch.int32, device=dev) for _ in outs] \
+    gathered = [torch.empty((world * rows_max, M, c.lwe.stride), dtype=wdt, device=dev) for _ in outs] \
         if (nccl and (rank == 0 or allg)) else None
     post = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     done = [None, None]
-    last_board = [None]
+    last = [None]
+
+    def client_decrypt(buf):
+        for r, (l, h) in enumerate(spans):
+            if h > l:
+                _decrypt_device(model, buf[r * rows_max: r * rows_max + (h - l)], wire32=wire32, slot=r)
 
     def step(i, ev=None):
         cur = torch.cuda.current_stream(dev)
@@ -308,8 +422,8 @@ def run_b200_arm(args):
                 ev[1].record()
             if rank == 0:
                 with torch.cuda.stream(post):
-                    last_board[0] = board.collect()      # client: wait for every shard's arrival flag,
-                    _decrypt_device(model, last_board[0], wire32=True)   # decrypt every shard's scores,
+                    last[0] = board.collect()            # client: wait for every shard's arrival flag,
+                    client_decrypt(last[0])              # decrypt every shard's scores,
                     board.release()                      # hand the slot back
             return
         k = i % len(outs)
@@ -317,144 +431,314 @@ def run_b200_arm(args):
             cur.wait_event(done[k])                      # buffer k was consumed by the post stream
         if ev:
             ev[0].record()
-        model.run(ct, out=outs[k])                       # server: encrypted dot products of this shard
+        if B:
+            model.run(ct, out=outs[k][:B])               # server: encrypted dot products of this shard
         if ev:
             ev[1].record()
         if world == 1:
-            _decrypt_device(model, outs[k])              # client kernels: decrypt + dequantize
+            _decrypt_device(model, outs[k][:B])          # client kernels: decrypt + dequantize
             return
         ready = torch.cuda.Event()
         ready.record(cur)
         with torch.cuda.stream(post):
             post.wait_event(ready)
-            model.compress_scores(outs[k], outs32[k])
+            send = outs[k]
+            if wire32:
+                model.compress_scores(outs[k], outs32[k])
+                send = outs32[k]
             if allg:
-                dist.all_gather_into_tensor(gathered[k], outs32[k])
+                dist.all_gather_into_tensor(gathered[k], send)
             else:
-                dist.gather(outs32[k], list(gathered[k].chunk(world)) if rank == 0 else None, dst=0)
+                dist.gather(send, list(gathered[k].chunk(world)) if rank == 0 else None, dst=0)
             if rank == 0:
-                _decrypt_device(model, gathered[k], wire32=True)   # client: decrypt every shard's scores
+                last[0] = gathered[k]
+                client_decrypt(gathered[k])              # client: decrypt every shard's scores
             done[k] = torch.cuda.Event()
             done[k].record(post)
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(warmup, 3)):
         step(i)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ref = model.predict_clear(X)
+    R.barrier()
+    # exactness: every shard's scores, as the client decrypted them, equal the clear quantized circuit
     if mode == "push":
         board.check()
-        if rank == 0:   # the pushed scores of every shard decrypt to each shard's clear result
-            y_all = model.decrypt_compressed(last_board[0])
-            assert np.array_equal(y_all[:B], ref), "pushed scores differ from the clear quantized circuit"
-            refs = [model.predict_clear(synthetic_docs(args.docs, DATA_SEED + 1 + r)[2]) for r in range(1, world)]
-            for r, rr in enumerate(refs, start=1):
-                assert np.array_equal(y_all[r * B:(r + 1) * B], rr), f"rank {r}'s pushed scores differ from its clear result"
-    else:
-        y_dev = model.decrypt(outs[0])
-        assert np.array_equal(y_dev, ref), "GPU scores differ from the clear quantized circuit"
-        if world > 1 and rank == 0:   # the gathered scores of every shard decrypt to each shard's clear result
-            y_all = model.decrypt_compressed(gathered[0])
-            assert np.array_equal(y_all[:B], ref)
+    if rank == 0:
+        for r, (l, h) in enumerate(spans):
+            for a in range(l, h, verify_chunk):
+                b = min(h, a + verify_chunk)
+                ref = model.predict_clear(X[a - lo: b - lo] if r == rank else rows_fn(a, b))
+                if world == 1:
+                    got = model.decrypt(outs[0][a - l: b - l])
+                else:
+                    enc = last[0][r * rows_max + (a - l): r * rows_max + (b - l)]
+                    got = model.decrypt_compressed(enc) if wire32 else model.decrypt(enc)
+                assert np.array_equal(got, ref), f"shard {r}, documents [{a},{b}): GPU scores differ from the clear quantized circuit"
+    R.barrier()
 
-    # --- timed region: K steps, device-resident inputs
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sampler = ClockSampler(R.local_rank)
     if rank == 0:
         sampler.start()
-    if world > 1:
-        dist.barrier()
+    R.barrier()
     torch.cuda.synchronize()
     launches0 = ctx.launch_count()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(i, evs[i])
     if world > 1:
         torch.cuda.current_stream(dev).wait_stream(post)
     t1.record()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    R.barrier()
     launches = ctx.launch_count() - launches0
-    elapsed_ms = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = R.max_over_ranks(t0.elapsed_time(t1))
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms * 1e-3)
-
-    # --- e2e: host float buffers in, host scores out, + host top-k
-    e2e_steps = max(3, min(args.steps, 10))
-
-    def e2e_run(fmt):
-        c.ciphertext_format = fmt
-        for _ in range(2):
-            model.predict_encrypted(X)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        w0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            sc = model.predict_encrypted(X)
-            hk = top_k(sc, 3, -np.inf)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - w0
-        if world > 1:
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        return world * B * e2e_steps / dt, hk
-
-    e2e_expanded, _ = e2e_run("expanded")     # full ciphertexts materialised in HBM between the stages
-    e2e_value, hits = e2e_run("seeded")       # the default: fresh ciphertexts as 8-byte bodies + public mask seed
-    clocks = sampler.stop() if rank == 0 else None  # sampled over the timed region and the e2e region
     if board is not None:
         board.check()      # no in-stream wait timed out
         board.close()
-    args._gather_mode = mode
-    assert [i for i, _ in hits] == [i for i, _ in top_k(ref, 3, -np.inf)], "top-k ranking differs from the clear circuit"
+    return {"value": total_docs * steps / (elapsed_ms * 1e-3), "elapsed_ms": elapsed_ms, "ms_per_step": elapsed_ms / steps,
+            "kern_ms": kern_ms, "kern_docs": B, "launches": int(launches), "mode": mode, "clocks": clocks,
+            "shards": [h - l for l, h in spans], "client_rho": rho, "X": X, "wire32": wire32}
+
+
+def e2e_single_gpu(model, X, steps):
+    """FHESimilarityModel.predict_encrypted with host float32 rows in / float64 scores out + host top-k."""
+    import torch
+    c = model.model.fhe_circuit
+    res = {}
+    for fmt in ("expanded", "seeded"):        # seeded (the default format) last: its ranking is the one checked
+        c.ciphertext_format = fmt
+        for _ in range(2):
+            model.predict_encrypted(X)
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            sc = model.predict_encrypted(X)
+            hits = top_k(sc, 3, -np.inf)
+        torch.cuda.synchronize()
+        res[fmt] = len(X) * steps / (time.perf_counter() - w0)
+    return res, hits
+
+
+def e2e_sharded(R: Ranks, model, total_docs, rho, steps, seed):
+    """ShardedSearch.search(): the query and the collection are in HOST memory (pinned); per query every rank uploads
+    its shard's rows, the encryption kernel forms the clear products query * doc, quantizes and encrypts them, the rank
+    evaluates and pushes; the client decrypts, reads the scores back and ranks.  All GPUs belong to the key owner
+    (key_holders='all', the reference's one-machine trust model), so the client-side encryption is sharded too.
+    A second figure keeps the (plaintext, client-owned) collection resident on the GPUs: only the query is uploaded."""
+    import torch
+    from fhe_icp_b200.sharded_search import ShardedSearch, client_cost_weights, shard_bounds
+    c = model.model.fhe_circuit
+    d = c.spec.d
+    weights = client_cost_weights(R.world, 0, rho)
+    lo, hi = shard_bounds(total_docs, R.world, R.rank, weights)
+    q = collection_query(d, seed)
+    docs = collection_rows(lo, hi, d, seed, q)
+    c.ct_counter = (1 << 44) + R.rank * (1 << 40)       # fresh ids, disjoint between the ranks
+    c.ciphertext_format = "seeded"
+    gather = "push" if (R.world > 1 and c.wire32_supported) else "nccl"
+    vals = {}
+    for placement in ("device", "host"):        # "host" (everything uploaded per query) last: it is the headline
+        ss = ShardedSearch(model, docs, key_holders="all", gather=gather, shard_weights=weights, n_docs=total_docs,
+                           collection=placement)
+        res = None
+        for _ in range(2):
+            res = ss.search(q, top_k=3, min_similarity=-np.inf)
+        R.barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            res = ss.search(q, top_k=3, min_similarity=-np.inf)
+        torch.cuda.synchronize()
+        vals[placement] = total_docs * steps / R.max_over_ranks(time.perf_counter() - w0)
+        ss.close()
+        del ss
+    ok = None
+    if R.rank == 0:     # the ranking equals the clear circuit's over the whole collection
+        ref = np.concatenate([model.predict_clear(q[None, :] * collection_rows(a, min(total_docs, a + 65536), d, seed, q))
+                              for a in range(0, total_docs, 65536)])
+        ok = [i for i, _ in top_k(ref, 3, -np.inf)] == [int(name.split("_")[1]) for name, _ in res]
+        assert ok, "sharded search ranking differs from the clear circuit"
+    return {"value": vals["host"], "unit": UNIT, "steps": steps,
+            "h2d_bytes_per_step": int(total_docs * d * 4 + d * 4), "d2h_bytes_per_step": int(total_docs * 8),
+            "call": f"ShardedSearch(key_holders='all', gather='{gather}', cost-weighted shards).search(query, top_k=3): query "
+                    "and documents in pinned host memory -> H2D of every shard's rows -> product + quantize + encrypt "
+                    "(seeded) -> dot products -> scores pushed to the client GPU -> client decrypt -> D2H -> host top-k",
+            "resident_collection_value": vals["device"],
+            "resident_collection_note": "same call with collection='device': the client-owned plaintext rows stay on the "
+                                        f"GPUs, {d * 4} B of query go up per step",
+            "ranking_equals_clear_circuit": ok}
+
+
+def hbm_roofline(c, kern_ms, kern_docs, peak, peak_src):
+    M = 2 if c.two_outputs else 1
+    bytes_per_launch = comparison_bytes(c) * kern_docs
+    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    t = NCU_TRAFFIC.get((c.lwe.n, M, c.spec.d))
+    return {"bound": "hbm", "kernel": "lincomb_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": t[0] * kern_docs if t else None,
+            "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, " + t[1]) if t else None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms": kern_ms,
+            "documents_per_launch": int(kern_docs)}
+
+
+def seeded_roofline(c, kern_ms, kern_docs, sm_mhz):
+    """The seeded dot product reads 1 KB per document: no HBM roofline applies.  It is bound by the wide integer
+    multiplier (IMAD.WIDE.U32 on the fmaheavy pipe): 12 per Philox block of two mask words (10 of Philox4x32-7's 14
+    -- rounds 1-2 are shared per block and per ciphertext -- plus 2 for the weighted sums)."""
+    d, n = c.spec.d, c.lwe.n
+    blocks = kern_docs * d * ((n + 2) // 2)
+    wide = 12.0 * blocks
+    achieved = wide / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+    mhz = sm_mhz or 1965.0
+    peak = 148 * 4 * 32 / 4.0 * mhz * 1e6 / 1e12        # one IMAD.WIDE per 4 cycles per scheduler, 32 lanes
+    return {"bound": "integer (wide-multiplier pipe, fmaheavy)", "kernel": "lincomb_seeded_kernel", "achieved": achieved,
+            "peak": peak, "unit": "T wide-multiplies/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": "issue rate of IMAD.WIDE.U32 taken as 1 per 4 cycles per scheduler (16-lane fmaheavy pipe) at the "
+                           "sampled SM clock; ncu: sm__pipe_fmaheavy_cycles_active 86 % (profiles/r2_ncu_e2e_seeded_v1.txt), "
+                           "sustained rate inside Philox rounds 1 per 7 cycles (profiles/r2_seeded_kernel_times.txt)",
+            "kernel_ms": kern_ms, "documents_per_launch": int(kern_docs), "philox_blocks_per_launch": int(blocks),
+            "docs_per_sec_per_gpu": kern_docs / (kern_ms * 1e-3) if kern_ms > 0 else None,
+            "equivalent_expanded_stream_gbs": comparison_bytes(c) * kern_docs / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None}
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from fhe_icp_b200 import _native as N
+
+    R = Ranks()
+    rank, world, dev = R.rank, R.world, R.dev
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(R.local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the contract is ONE JSON line on stdout, and NCCL logs to stdout by default: its log (INFO unless the caller
+        # chose a level) goes to stderr instead, where a driver can still read the communicator / rank lines
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's stream (and the post stream) run at high priority: the dot-product kernel keeps
+        # thousands of CTAs queued, and equal-priority kernels only start once those are all dispatched
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    args.gpus = world
+    wl = resolve_workload(args)
+    model, _ = build_model(device=R.local_rank)
+    c = model.model.fhe_circuit
+    ctx = N.context(R.local_rank)
+    peak, peak_src = measured_peak_gbs()
+    warm = max(args.warmup, 3)
+
+    rho_cache = {}
+
+    def rho_for(fmt):
+        if world == 1 or args.client_rho == 0:
+            return 0.0
+        if args.client_rho > 0:
+            return args.client_rho
+        # measured on the client GPU, padded for what the measurement cannot see (inbound NVLink stores landing in the
+        # client's HBM while it streams its own shard, the decrypt CTAs' SM slots), same value on every rank
+        if fmt not in rho_cache:
+            r = measure_client_rho(model, fmt) * args.client_rho_pad if rank == 0 else 0.0
+            rho_cache[fmt] = R.max_over_ranks(r)
+        return rho_cache[fmt]
+
+    sub = {}
+    if wl == "config2":
+        fmt = args.format
+        total = args.docs * world
+        res = sharded_steps(R, model, lambda lo, hi: weak_collection_rows(lo, hi, args.docs), total, fmt, args.steps, warm,
+                            args.gather_mode, rho_for(fmt), ctx)
+        scaling = "weak"
+    else:
+        fmt = "seeded"
+        total = args.total_docs
+        q4 = collection_query(D_FEATURES, DATA_SEED + 77)
+        rows4 = lambda lo, hi: q4[None, :] * collection_rows(lo, hi, D_FEATURES, DATA_SEED + 77, q4)   # noqa: E731
+        res = sharded_steps(R, model, rows4, total, fmt, args.steps, warm, args.gather_mode, rho_for(fmt), ctx)
+        scaling = "strong"
+    X = res.pop("X")
+
+    # --- e2e: host buffers in, ranked ids out
+    e2e_steps = max(3, min(args.steps, 10))
+    if world == 1 and wl == "config2":
+        e2e_vals, hits = e2e_single_gpu(model, X, e2e_steps)
+        assert [i for i, _ in hits] == [i for i, _ in top_k(model.predict_clear(X), 3, -np.inf)], \
+            "top-k ranking differs from the clear circuit"
+        e2e = {"value": e2e_vals["seeded"], "unit": UNIT, "h2d_bytes_per_step": int(len(X) * D_FEATURES * 4),
+               "d2h_bytes_per_step": int(len(X) * 16), "steps": e2e_steps,
+               "call": "fhe_b200_similarity_predict_host_seeded (FHESimilarityModel.predict_encrypted, default "
+                       "ciphertext_format='seeded') + host top-k",
+               "expanded_ciphertexts_value": e2e_vals["expanded"]}
+    else:
+        del X
+        e2e = e2e_sharded(R, model, total if wl == "config4" else args.docs * world, rho_for("seeded"),
+                          max(3, min(e2e_steps, 5)), DATA_SEED + 77)
+
+    # --- sub-records: the other configurations BASELINE.json names, each with its own exactness check
+    if not args.no_sub_records:
+        torch.cuda.empty_cache()
+        if wl == "config4":      # the round-1 weak step (1000 expanded documents per GPU), for the scaling history
+            r2 = sharded_steps(R, model, lambda lo, hi: weak_collection_rows(lo, hi, args.docs), args.docs * world, "expanded",
+                               args.steps, warm, args.gather_mode, rho_for("expanded"), ctx)
+            r2.pop("X")
+            sub["config2_weak_1000_docs_per_gpu"] = dict(
+                {k: r2[k] for k in ("value", "ms_per_step", "mode", "shards", "client_rho")}, unit=UNIT, scaling="weak",
+                docs_per_gpu=args.docs, roofline=hbm_roofline(c, r2["kern_ms"], r2["kern_docs"], peak, peak_src))
+        elif args.total_docs > 0:   # configs[3] on this one GPU: the N = 1 point of the strong-scaling curve
+            q4 = collection_query(D_FEATURES, DATA_SEED + 77)
+            rows4 = lambda lo, hi: q4[None, :] * collection_rows(lo, hi, D_FEATURES, DATA_SEED + 77, q4)   # noqa: E731
+            r4 = sharded_steps(R, model, rows4, args.total_docs, "seeded", max(3, min(args.steps, 5)), 3, "local", 0.0, ctx)
+            r4.pop("X")
+            sub["config4_1M_docs_seeded_one_gpu"] = dict(
+                {k: r4[k] for k in ("value", "ms_per_step")}, unit=UNIT, total_docs=args.total_docs,
+                roofline=seeded_roofline(c, r4["kern_ms"], r4["kern_docs"], (res["clocks"] or {}).get("sm_mhz")))
+        torch.cuda.empty_cache()
+        docs5 = args.docs5_per_gpu
+        if docs5 > 0:            # configs[4]: d = 256, 12-bit; 100 k documents over 8 GPUs = 12 500 per GPU
+            m5, _ = build_model(device=R.local_rank, d=D_CONFIG5, n_bits=BITS_CONFIG5)
+            c5 = m5.model.fhe_circuit
+            q5 = collection_query(D_CONFIG5, DATA_SEED + 78)
+            rows5 = lambda lo, hi: q5[None, :] * collection_rows(lo, hi, D_CONFIG5, DATA_SEED + 78, q5)   # noqa: E731
+            r5 = sharded_steps(R, m5, rows5, docs5 * world, "expanded", max(3, min(args.steps, 10)), 3, args.gather_mode,
+                               0.0, ctx, verify_chunk=4096)
+            r5.pop("X")
+            sub["config5_d256_12bit"] = dict(
+                {k: r5[k] for k in ("value", "ms_per_step", "mode", "shards", "wire32")}, unit=UNIT,
+                workload=f"search over {docs5 * world} synthetic encrypted documents, d={D_CONFIG5}, n_bits={BITS_CONFIG5}, "
+                         f"{docs5} per GPU ({TOTAL_DOCS_CONFIG5} on 8 GPUs is BASELINE.json configs[4])",
+                lwe_n=c5.lwe.n, log2_delta=c5.lwe.shift, bytes_per_comparison=comparison_bytes(c5),
+                exact_vs_clear_circuit=True, roofline=hbm_roofline(c5, r5["kern_ms"], r5["kern_docs"], peak, peak_src))
+            del m5, c5
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = measured_peak_gbs()
-    bytes_per_launch = comparison_bytes(c) * B
-    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
-    if seeded:   # no HBM roofline applies: the masks never touch memory
-        line_extra = {"format": "seeded", "kernel": "lincomb_seeded_kernel", "kernel_ms": kern_ms,
-                      "docs_per_sec_per_gpu": B / (kern_ms * 1e-3),
-                      "note": "integer-pipe bound: 7 Philox rounds per 16 mask bytes; equivalent expanded-ciphertext "
-                              "stream would be %.0f GB/s" % achieved}
+    args._gather_mode = res["mode"]
+    clocks = res["clocks"]
+    roof = seeded_roofline(c, res["kern_ms"], res["kern_docs"], (clocks or {}).get("sm_mhz")) if fmt == "seeded" \
+        else hbm_roofline(c, res["kern_ms"], res["kern_docs"], peak, peak_src)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": workload_config(args, c),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * D_FEATURES * 4),
-                "d2h_bytes_per_step": int(B * 16), "steps": e2e_steps,
-                "call": "fhe_b200_similarity_predict_host_seeded (FHESimilarityModel.predict_encrypted, default "
-                        "ciphertext_format='seeded') + host top-k",
-                "expanded_ciphertexts_value": e2e_expanded},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "lincomb_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_DOC * B if c.lwe.n == 1423 and M == 2 else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
-                                       "profiles/r1_ncu_lincomb_decrypt_v3.txt (1000 documents, n=1423)",
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms": kern_ms},
-        "clocks": clocks,
+        "e2e": e2e, "gpu_launches": res["launches"], "roofline": roof, "clocks": clocks,
+        "gather_mode": res["mode"], "shards": res["shards"], "client_rho": res["client_rho"],
+        "exact_vs_clear_circuit": True, "sub_records": sub,
     }
-    if seeded:
-        line["roofline"] = dict(line["roofline"], bound="integer", traffic=None, **line_extra)
-        line["config"]["ciphertext_format"] = "seeded (8 B per ciphertext + public mask seed)"
     if not args.no_cpu_baseline and world == 1:
-        v, rows, t, threads = cpu_reference(model, X, args.cpu_seconds)
+        Xc = weak_collection_rows(0, args.docs, args.docs)
+        v, rows, t, threads = cpu_reference(model, Xc, args.cpu_seconds)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{rows} documents (the {B}-document workload tiled), quantize+encrypt+dot+decrypt in {t:.1f} s, "
+                                "sample": f"{rows} documents (the {args.docs}-document workload tiled), quantize+encrypt+dot+decrypt in {t:.1f} s, "
                                           "oracle/fhe_oracle.c (OpenMP)"}
     try:
         if args.no_extras:
@@ -537,20 +821,20 @@ def cpu_packed_reference(params, sm):
             "agrees_with_gpu": bool(np.array_equal(dec[:n], np.asarray(sm["expect"])))}
 
 
-def _decrypt_device(model, out, wire32=False):
+def _decrypt_device(model, out, wire32=False, slot=0):
     """decrypt + dequantize kernels without the device->host copy (device-resident timing)."""
     import ctypes as C
     import torch
     from fhe_icp_b200 import _native as N
     c = model.model.fhe_circuit
     B = out.shape[0]
-    if not hasattr(model, "_bench_y") or model._bench_y.shape[0] != B:
-        model._bench_y = torch.empty(B, dtype=torch.float64, device=out.device)
-        model._bench_qy = torch.empty(B, dtype=torch.int64, device=out.device)
+    bufs = model.__dict__.setdefault("_bench_bufs", {})
+    if slot not in bufs or bufs[slot][0].shape[0] < B:
+        bufs[slot] = (torch.empty(B, dtype=torch.float64, device=out.device), torch.empty(B, dtype=torch.int64, device=out.device))
+    y, qy = bufs[slot]
     st = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
     fn = N.lib().fhe_b200_similarity_decrypt32 if wire32 else N.lib().fhe_b200_similarity_decrypt
-    N.check(fn(c.handle, C.c_void_p(out.data_ptr()), B, C.c_void_p(model._bench_y.data_ptr()),
-               C.c_void_p(model._bench_qy.data_ptr()), st))
+    N.check(fn(c.handle, C.c_void_p(out.data_ptr()), B, C.c_void_p(y.data_ptr()), C.c_void_p(qy.data_ptr()), st))
 
 
 def main():
@@ -559,7 +843,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--docs", type=int, default=1000, help="documents per GPU")
+    ap.add_argument("--docs", type=int, default=1000, help="documents per GPU of the configs[1] (weak) workload")
+    ap.add_argument("--workload", default="auto", choices=["auto", "config2", "config4"],
+                    help="auto: BASELINE.json configs[1] on one GPU, configs[3] (one 1 M-document collection, sharded) on several")
+    ap.add_argument("--total-docs", type=int, default=TOTAL_DOCS_CONFIG4, help="documents of the configs[3] collection")
+    ap.add_argument("--docs5-per-gpu", type=int, default=TOTAL_DOCS_CONFIG5 // 8,
+                    help="documents per GPU of the configs[4] sub-record (d=256, 12-bit); 0 skips it")
+    ap.add_argument("--client-rho", type=float, default=-1.0,
+                    help="client cost per document / server cost per document for the cost-weighted shards "
+                         "(sharded_search.client_cost_weights); < 0: measured on the client GPU, 0: equal shards")
+    ap.add_argument("--client-rho-pad", type=float, default=1.5,
+                    help="factor on the measured client/server cost ratio (inbound NVLink stores and decrypt CTAs compete "
+                         "with the client's own shard)")
+    ap.add_argument("--no-sub-records", action="store_true", help="only the headline workload")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--format", default="expanded", choices=["expanded", "seeded"],

@@ -161,6 +161,7 @@ SIGNATURES = {
     "fhe_b200_lincomb_seeded": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64,
                                           C.c_uint32, _vp, C.c_int32, C.POINTER(C.c_int64), C.c_int32, _vp, _vp]),
     "fhe_b200_similarity_encrypt_seeded": (C.c_int, [_vp, _vp, C.c_int64, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "fhe_b200_similarity_encrypt_seeded_products": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "fhe_b200_similarity_run_seeded": (C.c_int, [_vp, _vp, C.c_int64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "fhe_b200_similarity_predict_host_seeded": (C.c_int, [_vp, C.POINTER(C.c_float), C.c_int64, C.c_uint64, C.c_uint64,
                                                           C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -771,8 +771,25 @@ int fhe_b200_similarity_encrypt_seeded(fhe_b200_similarity* s, const float* d_X,
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t cnt = B * sp.d;
     const int64_t qmin = -sp.x_offset, qmax = (1LL << sp.n_bits) - 1 - sp.x_offset;
-    CU(fhe::launch_lwe_encrypt_seeded_float(s->d_key, sp.n, d_X, cnt, sp.x_scale, sp.x_zero_point, qmin, qmax, sp.shift,
-                                            sp.sigma_abs, enc_seed, sp.noise_seed, ct_base, FHE_B200_PUR_INPUT, d_bodies, st));
+    CU(fhe::launch_lwe_encrypt_seeded_float(s->d_key, sp.n, d_X, nullptr, sp.d, cnt, sp.x_scale, sp.x_zero_point, qmin, qmax,
+                                            sp.shift, sp.sigma_abs, enc_seed, sp.noise_seed, ct_base, FHE_B200_PUR_INPUT,
+                                            d_bodies, st));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_similarity_encrypt_seeded_products(fhe_b200_similarity* s, const float* d_query, const float* d_docs, int64_t B,
+                                                uint64_t enc_seed, uint64_t ct_base, uint64_t* d_bodies, void* stream) {
+    REQUIRE(s, "null model");
+    REQUIRE_CLIENT(s);
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_query && d_docs && d_bodies, "null device pointer");
+    const auto& sp = s->spec;
+    CU(cudaSetDevice(s->ctx->device));
+    const int64_t qmin = -sp.x_offset, qmax = (1LL << sp.n_bits) - 1 - sp.x_offset;
+    CU(fhe::launch_lwe_encrypt_seeded_float(s->d_key, sp.n, d_docs, d_query, sp.d, B * sp.d, sp.x_scale, sp.x_zero_point, qmin,
+                                            qmax, sp.shift, sp.sigma_abs, enc_seed, sp.noise_seed, ct_base, FHE_B200_PUR_INPUT,
+                                            d_bodies, (cudaStream_t)stream));
     return FHE_B200_OK;
 }
 

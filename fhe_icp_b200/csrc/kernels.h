@@ -24,7 +24,8 @@ cudaError_t launch_lincomb(const uint64_t* d_ct, int64_t B, int d, int n, int64_
 cudaError_t launch_lwe_encrypt_seeded(const uint8_t* d_key, int n, const int64_t* d_msgs, int64_t count, int shift,
                                       double sigma_abs, uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base,
                                       uint32_t purpose, uint64_t* d_bodies, cudaStream_t s);
-cudaError_t launch_lwe_encrypt_seeded_float(const uint8_t* d_key, int n, const float* d_X, int64_t count, double scale,
+cudaError_t launch_lwe_encrypt_seeded_float(const uint8_t* d_key, int n, const float* d_X, const float* d_query, int d,
+                                            int64_t count, double scale,
                                             int64_t zp, int64_t qmin, int64_t qmax, int shift, double sigma_abs,
                                             uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base, uint32_t purpose,
                                             uint64_t* d_bodies, cudaStream_t s);

@@ -543,23 +543,30 @@ static cudaError_t launch_encrypt_seeded_masks(const uint8_t* d_key, int n, int6
 
 // quantize (the UniformQuantizer rule of quantize_kernel) + plaintext + error in one pass:
 // the client path from float features to seeded ciphertexts needs no integer staging buffer
-__global__ void quantize_body_noise_kernel(const float* __restrict__ X, int64_t count, double scale, double zp, double qmin,
+// With `query` (d floats) the feature is the clear product query[j] * X[i] the reference forms on the host before it
+// calls the circuit (emb1 * emb2, batch_operations.py:226,273): one IEEE single-precision multiply, round to nearest --
+// the same float32 value numpy produces -- so a search uploads the query and its documents instead of a product matrix
+// built by the host.
+__global__ void quantize_body_noise_kernel(const float* __restrict__ X, const float* __restrict__ query, int d, int64_t count,
+                                           double scale, double zp, double qmin,
                                            double qmax, int shift, double sigma_abs, uint64_t noise_seed, uint64_t ct_base,
                                            uint32_t purpose, uint64_t* __restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    double v = rint(__dadd_rn(__ddiv_rn((double)X[i], scale), zp));
+    const float x = query ? __fmul_rn(query[i % d], X[i]) : X[i];
+    double v = rint(__dadd_rn(__ddiv_rn((double)x, scale), zp));
     v = fmin(fmax(v, qmin), qmax);
     const uint32_t ndom = FHE_B200_KIND_NOISE | (purpose << 8);
     dst[i] = ((uint64_t)(int64_t)v << shift) + (uint64_t)gaussian_i64(noise_seed, ndom, ct_base + (uint64_t)i, 0, sigma_abs);
 }
 
-cudaError_t launch_lwe_encrypt_seeded_float(const uint8_t* d_key, int n, const float* d_X, int64_t count, double scale,
+cudaError_t launch_lwe_encrypt_seeded_float(const uint8_t* d_key, int n, const float* d_X, const float* d_query, int d,
+                                            int64_t count, double scale,
                                             int64_t zp, int64_t qmin, int64_t qmax, int shift, double sigma_abs,
                                             uint64_t enc_seed, uint64_t noise_seed, uint64_t ct_base, uint32_t purpose,
                                             uint64_t* d_bodies, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
-    quantize_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_X, count, scale, (double)zp, (double)qmin,
+    quantize_body_noise_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_X, d_query, d, count, scale, (double)zp, (double)qmin,
                                                                              (double)qmax, shift, sigma_abs, noise_seed, ct_base,
                                                                              purpose, d_bodies);
     count_launch();

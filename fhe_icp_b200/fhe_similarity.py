@@ -185,6 +185,30 @@ class FHESimilarityModel:
                                                     c.next_ct_base(B * c.spec.d), C.c_void_p(ct.data_ptr()), st))
         return ct
 
+    def encrypt_products(self, query: np.ndarray, docs):
+        """Client: seeded ciphertexts of X = query * docs -- the clear product the reference forms on the host before
+        every circuit call (batch_operations.py:226,273) -- with the multiply done by the encryption kernel (IEEE
+        float32, bit-identical to numpy's).  ``docs``: float32 rows [B,d] as a numpy array, a (pinned) host tensor --
+        uploaded here -- or a tensor already resident on this GPU."""
+        import ctypes as C
+        import torch
+        from . import _native as N
+        c = self.keygen().model.fhe_circuit
+        dev = torch.device("cuda", N.context(self.device).device)
+        if not isinstance(docs, torch.Tensor):
+            docs = torch.from_numpy(np.ascontiguousarray(docs, dtype=np.float32))
+        if docs.dtype != torch.float32 or docs.dim() != 2 or docs.shape[1] != c.spec.d:
+            raise ValueError(f"docs must be float32 [rows, {c.spec.d}]")
+        Dd = docs.to(dev, non_blocking=True).contiguous()
+        qd = torch.from_numpy(np.ascontiguousarray(query, dtype=np.float32).reshape(c.spec.d)).to(dev)
+        B = Dd.shape[0]
+        bodies = torch.empty((B, c.spec.d), dtype=torch.int64, device=dev)
+        base = c.next_ct_base(B * c.spec.d)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        N.check(N.lib().fhe_b200_similarity_encrypt_seeded_products(c.handle, C.c_void_p(qd.data_ptr()), C.c_void_p(Dd.data_ptr()),
+                                                                    B, c.enc_seed, base, C.c_void_p(bodies.data_ptr()), st))
+        return SeededCiphertexts(bodies, c.enc_seed, base)
+
     def run(self, ct, out=None):
         """Server: ciphertexts [B,d,stride] -> encrypted scores [B,M,stride] (M = 1 or 2)."""
         import ctypes as C

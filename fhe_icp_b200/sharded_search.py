@@ -19,11 +19,31 @@ import torch.distributed as dist
 from .batch_operations import rank_results
 
 
-def shard_bounds(n_items: int, world: int, rank: int) -> Tuple[int, int]:
-    """Contiguous balanced ranges: the first n % world ranks hold one extra item."""
-    base, extra = divmod(n_items, world)
-    lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+def shard_bounds(n_items: int, world: int, rank: int, weights: Optional[Sequence[float]] = None) -> Tuple[int, int]:
+    """Contiguous ranges, one per rank.  Without ``weights``: balanced by count (the first n % world ranks hold one
+    extra item).  With ``weights`` (one non-negative number per rank): sizes proportional to them, edges rounded from
+    the cumulative weights so that the ranges tile [0, n_items) exactly for every rank."""
+    if weights is None:
+        base, extra = divmod(n_items, world)
+        lo = rank * base + min(rank, extra)
+        return lo, lo + base + (1 if rank < extra else 0)
+    if len(weights) != world or min(weights) < 0 or sum(weights) <= 0:
+        raise ValueError("weights: one non-negative number per rank, not all zero")
+    total = float(sum(weights))
+    edge = lambda r: int(round(n_items * (float(sum(weights[:r])) / total)))  # noqa: E731
+    return (0 if rank == 0 else edge(rank)), (n_items if rank == world - 1 else edge(rank + 1))
+
+
+def client_cost_weights(world: int, client_rank: int, rho: float) -> Optional[List[float]]:
+    """Shard weights that equalise the per-query time of the ranks when the client rank, besides evaluating its own
+    shard, decrypts EVERY document's scores: with rho = (client cost per document) / (server cost per document) the
+    ranks finish together when the client holds 1 - (world-1)*rho of an equal share and every other rank 1 + rho of
+    one (sharded_search.ShardedSearch(shard_weights=...), bench.py).  rho <= 0 or a single rank: None (equal shards)."""
+    if world <= 1 or rho <= 0:
+        return None
+    w = [1.0 + rho] * world
+    w[client_rank] = max(0.0, 1.0 - (world - 1) * rho)
+    return w
 
 
 def broadcast_public_material(obj, src: int = 0):
@@ -43,6 +63,24 @@ def broadcast_keys(tensors: Sequence[torch.Tensor], src: int = 0):
     return tensors
 
 
+class _LazyDocIds:
+    """doc_<i> names without a million-entry list (the default ids of a large synthetic collection)."""
+
+    def __init__(self, n: int):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [f"doc_{j}" for j in range(*i.indices(self.n))]
+        i = int(i)
+        if not -self.n <= i < self.n:
+            raise IndexError(i)
+        return f"doc_{i % self.n}"
+
+
 class ShardedSearch:
     """``engine`` needs ``encrypt(X) -> ct``, ``run(ct) -> enc_scores [rows, M, stride]`` and
     ``decrypt(enc_scores) -> float64 scores``; FHESimilarityModel provides all three on the GPU.
@@ -58,14 +96,25 @@ class ShardedSearch:
         must have been built from the SAME key set (explicit seeds or a loaded key file)."""
 
     def __init__(self, engine, docs: Optional[np.ndarray], doc_ids: Optional[List[str]] = None, client_rank: int = 0,
-                 seeded: bool = True, wire32: bool = True, gather: str = "nccl", key_holders: str = "client"):
+                 seeded: bool = True, wire32: bool = True, gather: str = "nccl", key_holders: str = "client",
+                 shard_weights: Optional[Sequence[float]] = None, n_docs: Optional[int] = None,
+                 collection: str = "host"):
         """``gather``: "nccl" -- scores written locally, then all-gathered; "push" -- the dot-product kernel
         of every rank stores its scores into the client GPU's score board over NVLink (score_board.py; the
-        engine must be an FHESimilarityModel on a CUDA device, scores travel in the 32-bit wire form)."""
+        engine must be an FHESimilarityModel on a CUDA device, scores travel in the 32-bit wire form).
+        ``shard_weights``: relative shard sizes (see :func:`client_cost_weights`; None: equal).  ``n_docs`` (only with
+        key_holders='all'): size of the whole collection when ``docs`` holds just THIS rank's shard, so that no rank
+        has to materialise documents it never encrypts.  ``collection`` (engines with ``encrypt_products``, ranks that
+        encrypt their own shard): "host" -- the shard stays in pinned host memory and is uploaded with every query;
+        "device" -- it is uploaded once and stays resident on the rank's GPU (the key owner's GPU: it is plaintext)."""
         if gather not in ("nccl", "push"):
             raise ValueError(f"Unknown gather mode: {gather}")
         if key_holders not in ("client", "all"):
             raise ValueError(f"Unknown key_holders: {key_holders}")
+        if collection not in ("host", "device"):
+            raise ValueError(f"Unknown collection placement: {collection}")
+        self.collection = collection
+        self._shard_t = None
         self.engine = engine
         self.key_holders = key_holders
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -83,14 +132,21 @@ class ShardedSearch:
             raise ValueError("the client rank needs the documents")
         if key_holders == "all" and not has_docs:
             raise ValueError("key_holders='all': every rank encrypts its own shard and needs the documents")
-        meta = (int(docs.shape[0]), int(docs.shape[1])) if (has_docs and self.is_client) else None
+        if n_docs is not None and key_holders != "all":
+            raise ValueError("n_docs (docs = this rank's shard only) needs key_holders='all'")
+        meta = (int(n_docs if n_docs is not None else docs.shape[0]), int(docs.shape[1])) if (has_docs and self.is_client) else None
         self.n_docs, self.d = broadcast_public_material(meta, client_rank)
-        self.doc_ids = doc_ids if doc_ids is not None else [f"doc_{i}" for i in range(self.n_docs)]
-        self.lo, self.hi = shard_bounds(self.n_docs, self.world, self.rank)
+        self.shard_weights = list(shard_weights) if shard_weights is not None else None
+        self.doc_ids = doc_ids if doc_ids is not None else _LazyDocIds(self.n_docs)
+        self.lo, self.hi = self._bounds(self.rank)
         self.docs = np.ascontiguousarray(docs, dtype=np.float32) if (has_docs and (self.is_client or key_holders == "all")) else None
-        self.shard = self.docs[self.lo:self.hi] if self.docs is not None else None
-        self.max_rows = max(shard_bounds(self.n_docs, self.world, r)[1] - shard_bounds(self.n_docs, self.world, r)[0]
-                            for r in range(self.world))
+        if n_docs is not None:
+            if self.docs.shape[0] != self.hi - self.lo:
+                raise ValueError(f"rank {self.rank}: docs holds {self.docs.shape[0]} rows, its shard has {self.hi - self.lo}")
+            self.shard = self.docs
+        else:
+            self.shard = self.docs[self.lo:self.hi] if self.docs is not None else None
+        self.max_rows = max(self._bounds(r)[1] - self._bounds(r)[0] for r in range(self.world))
         self._ct = None
         self._query = None
         self._score_shape = None      # (M, stride) of one document's encrypted scores; the client probes it once
@@ -100,6 +156,9 @@ class ShardedSearch:
                 raise ValueError("gather='push' moves scores in the 32-bit wire form, which these parameters do not support")
             from .score_board import PeerScoreBoard
             self.board = PeerScoreBoard(engine, max(self.max_rows, 1), client_rank=client_rank)
+
+    def _bounds(self, r: int) -> Tuple[int, int]:
+        return shard_bounds(self.n_docs, self.world, r, self.shard_weights)
 
     # ---- client side
     def _encrypt(self, X: np.ndarray):
@@ -119,15 +178,23 @@ class ShardedSearch:
         ``query`` is needed where the encryption happens (the client rank; every rank for key_holders='all')."""
         if self.key_holders == "all" or self.world == 1:
             self._query = np.asarray(query, dtype=np.float32)
-            X = (self._query[None, :] * self.shard).astype(np.float32)
-            self._ct = self._encrypt(X) if len(X) else None
+            if not len(self.shard):
+                self._ct = None
+            elif self.seeded and hasattr(self.engine, "encrypt_products"):
+                # the product query * docs is taken by the encryption kernel; the host only hands over its rows
+                if self._shard_t is None:
+                    t = torch.from_numpy(self.shard)
+                    self._shard_t = t.to(self._device()) if self.collection == "device" else t.pin_memory()
+                self._ct = self.engine.encrypt_products(self._query, self._shard_t)
+            else:
+                self._ct = self._encrypt((self._query[None, :] * self.shard).astype(np.float32))
             return self._ct
         metas = [None] * self.world
         mine, outgoing = None, []
         if self.is_client:
             self._query = np.asarray(query, dtype=np.float32)
             for r in range(self.world):
-                lo, hi = shard_bounds(self.n_docs, self.world, r)
+                lo, hi = self._bounds(r)
                 if hi == lo:
                     continue
                 ct = self._encrypt((self._query[None, :] * self.docs[lo:hi]).astype(np.float32))
@@ -192,7 +259,7 @@ class ShardedSearch:
         dist.all_gather_into_tensor(gathered, padded)
         parts = []
         for r in range(self.world):
-            lo, hi = shard_bounds(self.n_docs, self.world, r)
+            lo, hi = self._bounds(r)
             parts.append(gathered[r * self.max_rows: r * self.max_rows + (hi - lo)])
         return torch.cat(parts, dim=0)
 
@@ -205,11 +272,31 @@ class ShardedSearch:
         slot = self.board.collect()
         parts = []
         for r in range(self.world):
-            lo, hi = shard_bounds(self.n_docs, self.world, r)
+            lo, hi = self._bounds(r)
             parts.append(slot[r * self.board.rows_max: r * self.board.rows_max + (hi - lo)])
         enc = torch.cat(parts, dim=0)     # copy out of the slot, then hand it back to the servers
         self.board.release()
         return enc
+
+    def _push_and_decrypt(self, rows: int) -> Optional[np.ndarray]:
+        """Push-mode query without a copy of the gathered ciphertexts: the client decrypts every rank's rows straight
+        out of the score-board slot (one fused decrypt kernel per rank), returns the slot, and reads back 8 bytes per
+        document."""
+        self.board.push(self._ct if rows else None)
+        self._is32 = True
+        if not self.is_client:
+            return None
+        slot = self.board.collect()
+        ys = []
+        for r in range(self.world):
+            lo, hi = self._bounds(r)
+            if hi > lo:
+                ys.append(self.engine.decrypt_compressed(slot[r * self.board.rows_max: r * self.board.rows_max + (hi - lo)],
+                                                         to_host=False))
+        self.board.release()               # stream-ordered after the decrypt kernels
+        if not ys:
+            return np.zeros(0)
+        return (torch.cat(ys) if len(ys) > 1 else ys[0]).cpu().numpy()
 
     def close(self):
         """Collective: unmap / free the score board (push mode)."""
@@ -221,6 +308,8 @@ class ShardedSearch:
     def search_scores(self, query: Optional[np.ndarray]) -> Optional[np.ndarray]:
         """Decrypted scores of the whole collection on the client rank (None elsewhere)."""
         self.encrypt_shard(query)
+        if self.board is not None:
+            return self._push_and_decrypt(self.hi - self.lo)
         enc = self.evaluate_and_gather()
         if not self.is_client:
             return None

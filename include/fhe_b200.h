@@ -293,6 +293,11 @@ int fhe_b200_similarity_decrypt(fhe_b200_similarity *sim, const uint64_t *d_out,
 /* seeded variants: d_bodies [B][d] u64, ciphertext ids ct_base + b*d + j */
 int fhe_b200_similarity_encrypt_seeded(fhe_b200_similarity *sim, const float *d_X, int64_t B,
                                        uint64_t enc_seed, uint64_t ct_base, uint64_t *d_bodies, void *stream);
+/* same with the clear product fused in: feature (b, j) = d_query[j] * d_docs[b*d + j] in IEEE float32, the array the
+ * reference builds on the host before every call (emb1 * emb2, /root/reference/batch_operations.py:226,273) */
+int fhe_b200_similarity_encrypt_seeded_products(fhe_b200_similarity *sim, const float *d_query, const float *d_docs,
+                                                int64_t B, uint64_t enc_seed, uint64_t ct_base, uint64_t *d_bodies,
+                                                void *stream);
 int fhe_b200_similarity_run_seeded(fhe_b200_similarity *sim, const uint64_t *d_bodies, int64_t B,
                                    uint64_t enc_seed, uint64_t ct_base, uint64_t *d_out, void *stream);
 int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity *sim, const float *h_X, int64_t B,

@@ -304,3 +304,30 @@ def test_sharded_search_push_mode_equals_nccl_mode(processor):
             assert sp.search(q, top_k=4, min_similarity=0.5) == want
     finally:
         sp.close()
+
+
+def test_encrypt_products_equals_host_product_bit_for_bit(cuda_dev):
+    """The fused product + quantize + encrypt kernel (fhe_b200_similarity_encrypt_seeded_products) yields the bodies of
+    encrypt(query * docs): the float32 multiply on the device is numpy's, including values that sit near a quantizer
+    rounding boundary; numpy rows, pinned host tensors and device-resident tensors are the same input."""
+    import torch
+    from fhe_icp_b200 import FHESimilarityModel
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=4, key_seed=21, enc_seed=22, noise_seed=23, ct_start=0, verbose=False)
+    X, _ = m.train(n_samples=300)
+    m.compile(X[:10])
+    c = m.model.fhe_circuit
+    rng = np.random.RandomState(7)
+    q = rng.randn(128).astype(np.float32)
+    docs = (rng.randn(777, 128) * rng.choice([1e-3, 0.05, 1.0, 30.0], size=(777, 1))).astype(np.float32)
+    docs[5] = 0.0
+    docs[6, ::2] = np.float32(1e-30)          # products underflow to denormals / zero exactly as on the host
+    c.ct_counter = 1000
+    ref = m.encrypt((q[None, :] * docs).astype(np.float32), seeded=True)
+    for src in (docs, torch.from_numpy(docs).pin_memory(), torch.from_numpy(docs).to(m.dev)):
+        c.ct_counter = 1000
+        got = m.encrypt_products(q, src)
+        assert got.ct_base == ref.ct_base and got.enc_seed == ref.enc_seed
+        assert torch.equal(got.bodies, ref.bodies)
+    assert np.array_equal(m.decrypt(m.run(got)), m.predict_clear((q[None, :] * docs).astype(np.float32)))
+    with pytest.raises(ValueError):
+        m.encrypt_products(q, docs[:, :64])

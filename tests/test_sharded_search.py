@@ -72,7 +72,7 @@ class KeylessEngine(OracleEngine):
         raise AssertionError("a server rank tried to decrypt")
 
 
-def _worker(rank, world, port, n_docs, ret, key_holders="client"):
+def _worker(rank, world, port, n_docs, ret, key_holders="client", weights=None, shard_only=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -85,8 +85,12 @@ def _worker(rank, world, port, n_docs, ret, key_holders="client"):
             engine = OracleEngine(m) if rank == 0 else KeylessEngine(m)
         spec = broadcast_public_material(m.model.spec.to_dict() if rank == 0 else None)
         assert spec["q_weights"] == m.model.spec.to_dict()["q_weights"]
-        ss = ShardedSearch(engine, docs if (rank == 0 or key_holders == "all") else None, key_holders=key_holders)
-        assert (ss.lo, ss.hi) == shard_bounds(n_docs, world, rank)
+        mine = docs if (rank == 0 or key_holders == "all") else None
+        if shard_only:      # every rank is handed just the rows it will encrypt
+            lo, hi = shard_bounds(n_docs, world, rank, weights)
+            mine = docs[lo:hi]
+        ss = ShardedSearch(engine, mine, key_holders=key_holders, shard_weights=weights, n_docs=n_docs if shard_only else None)
+        assert (ss.lo, ss.hi) == shard_bounds(n_docs, world, rank, weights)
         res = ss.search(q if (rank == 0 or key_holders == "all") else None, top_k=4, min_similarity=0.2)
         if rank == 0:
             ret["res"] = res
@@ -108,6 +112,41 @@ def test_sharded_search_world2_matches_single_process(n_docs, key_holders):
     m, q, docs = _make_problem(n_docs)
     ref = rank_results([f"doc_{i}" for i in range(n_docs)], m.predict_clear(q[None, :] * docs), 4, 0.2)
     assert ret["res"] == ref
+
+
+@pytest.mark.parametrize("weights,shard_only", [([0.25, 1.0], False), ([0.0, 1.0], True), ([1.0, 3.0], True)])
+def test_sharded_search_world2_cost_weighted_shards(weights, shard_only):
+    """Uneven (cost-weighted) contiguous shards -- including a client that keeps no documents -- and ranks that hold
+    only their own rows give the single-process ranking."""
+    world, port, n_docs = 2, _free_port(), 9
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, n_docs, ret, "all", weights, shard_only), nprocs=world, join=True)
+    from fhe_icp_b200.batch_operations import rank_results
+    m, q, docs = _make_problem(n_docs)
+    assert ret["res"] == rank_results([f"doc_{i}" for i in range(n_docs)], m.predict_clear(q[None, :] * docs), 4, 0.2)
+
+
+def test_weighted_shard_bounds_and_client_cost_weights():
+    from fhe_icp_b200.sharded_search import client_cost_weights, shard_bounds
+    assert client_cost_weights(1, 0, 0.1) is None and client_cost_weights(8, 0, 0.0) is None
+    w = client_cost_weights(8, 0, 0.05)
+    assert w[0] == pytest.approx(0.65) and w[1:] == [1.05] * 7 and sum(w) == pytest.approx(8.0)
+    assert client_cost_weights(8, 3, 0.5)[3] == 0.0           # the client can be left without a shard, never negative
+    for n in (0, 1, 7, 1000, 1_000_003):
+        for weights in ([1.0, 1.0], w, [0.0, 2.0, 1.0], client_cost_weights(4, 2, 0.12)):
+            world = len(weights)
+            spans = [shard_bounds(n, world, r, weights) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] and a[0] <= a[1] for a, b in zip(spans, spans[1:]))
+            for (lo, hi), wt in zip(spans, weights):          # proportional up to rounding
+                assert abs((hi - lo) - n * wt / sum(weights)) <= 1.0
+    # time model: with rho the ranks finish together
+    n, rho, world = 1_000_000, 0.02, 8
+    sizes = [hi - lo for lo, hi in (shard_bounds(n, world, r, client_cost_weights(world, 0, rho)) for r in range(world))]
+    assert sizes[0] + rho * n == pytest.approx(sizes[1], abs=2)
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 0, [1.0])
 
 
 def test_shard_bounds_cover_everything():
