@@ -619,8 +619,27 @@ def run_b200_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # the contract is ONE JSON line on stdout, and NCCL logs to stdout by default: its log (INFO unless the caller
         # chose a level) goes to stderr instead, where a driver can still read the communicator / rank lines
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (the GPU boxes export NCCL_DEBUG=VERSION, whose banner would land on stdout: anything below INFO is raised).
+        # Every rank logs into its own file and copies it to stderr when it is done: N processes that each open
+        # /dev/stderr themselves overwrite one another when stderr is a regular file.
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")     # communicator / rank / transport lines only
+        if "NCCL_DEBUG_FILE" not in os.environ:
+            import atexit
+            import tempfile
+            nccl_log = os.path.join(tempfile.gettempdir(), f"bench_nccl_{os.getpid()}.log")
+            os.environ["NCCL_DEBUG_FILE"] = nccl_log
+
+            def _dump_nccl_log(path=nccl_log):
+                try:
+                    with open(path, errors="replace") as f:
+                        sys.stderr.write(f.read())
+                    sys.stderr.flush()
+                    os.unlink(path)
+                except OSError:
+                    pass
+            atexit.register(_dump_nccl_log)
         # NCCL's stream (and the post stream) run at high priority: the dot-product kernel keeps
         # thousands of CTAs queued, and equal-priority kernels only start once those are all dispatched
         opts = dist.ProcessGroupNCCL.Options()

@@ -37,3 +37,31 @@ def test_reference_arm_json_contract():
     assert line["impl"] == "reference" and line["metric"] == "encrypted_comparisons_per_sec" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
     assert "workload" in line["config"]
+
+
+def test_collection_rows_are_sharding_independent():
+    import bench
+    q = bench.collection_query(128, 5)
+    whole = bench.collection_rows(0, 3 * bench.DOC_BLOCK + 17, 128, 5, q)
+    assert np.allclose(np.linalg.norm(whole, axis=1), 1.0, atol=1e-5)
+    for lo, hi in [(0, 1), (bench.DOC_BLOCK - 3, bench.DOC_BLOCK + 5), (100, 2 * bench.DOC_BLOCK + 1), (7, 7)]:
+        assert np.array_equal(bench.collection_rows(lo, hi, 128, 5, q), whole[lo:hi])
+    w = bench.weak_collection_rows(500, 2100, 1000)
+    assert w.shape == (1600, 128)
+    assert np.array_equal(w[:500], bench.synthetic_docs(1000, bench.DATA_SEED + 1)[2][500:])
+    assert np.array_equal(w[1500:], bench.synthetic_docs(1000, bench.DATA_SEED + 3)[2][:100])
+
+
+def test_both_arms_print_the_same_config_object():
+    """`config` is a pure function of the command line and the circuit: the driver compares the two arms' objects."""
+    import argparse
+    import bench
+    model, _ = bench.build_model()
+    c = model.model.fhe_circuit
+    for gpus, wl in [(1, "config2"), (2, "config4"), (8, "config4")]:
+        a = argparse.Namespace(workload="auto", gpus=gpus, docs=1000, total_docs=bench.TOTAL_DOCS_CONFIG4)
+        assert bench.resolve_workload(a) == wl
+        cfg = bench.workload_config(a, c)
+        assert cfg == bench.workload_config(argparse.Namespace(**vars(a)), c) and "workload" in cfg
+        assert ("multi_gpu" in cfg) == (gpus > 1)
+        assert cfg["bytes_per_comparison"] == (128 + 2) * (c.lwe.n + 1) * 8
