@@ -645,7 +645,10 @@ static cudaError_t launch_pbs_tmem_t(const fhe_b200_pbs_params& p, const cplx* b
 #define MB2_L2_SLICES 3
 #endif
 #define MB2_SLICE_K1(L) ((L) == 1 ? 2 : MB2_L2_K1)
-#define MB2_SLICE_COUNT(L) ((L) == 1 ? 4 : MB2_L2_SLICES)
+#ifndef MB2_L1_SLICES
+#define MB2_L1_SLICES 4
+#endif
+#define MB2_SLICE_COUNT(L) ((L) == 1 ? MB2_L1_SLICES : MB2_L2_SLICES)
 constexpr int MB2_LAG = 1;                       // refill a ring slot this many slices after warp 0 left it
 template <int L>
 struct PbsMb2Smem {

@@ -35,20 +35,31 @@ constexpr int PS_N = nfft::NPOLY;
 constexpr int PS_TILE = nfft::TILE_ELEMS;
 constexpr int PS_HALF = nfft::HALF_TILE_ELEMS;
 constexpr int PS_OMEGA = 128;
-constexpr int PS_SLICES = 4;                                     // ring slots
+// ring slots per ciphertexts-per-CTA.  Deeper rings were measured and change nothing (B200, batch 1: 4 slots 2.88 ms, 8 slots
+// 2.86 ms, 12 slots 2.99 ms -- a lone ciphertext's step is bound by its own dependent FP64 / shared-memory chain, not by
+// the key stream), while the larger footprint stops two CTAs from sharing an SM (batch 296: 3.68 -> 6.18 ms); so 4.
+#ifndef PS_SLICES_1
+#define PS_SLICES_1 4
+#endif
+#ifndef PS_SLICES_2
+#define PS_SLICES_2 4
+#endif
+__host__ __device__ constexpr int ps_slices(int nct) { return nct == 1 ? PS_SLICES_1 : (nct == 2 ? PS_SLICES_2 : 4); }
 constexpr int PS_SLICE_ELEMS = 2 * nfft::MB2_BLOCK_ELEMS;        // two frequency blocks per slice: 768 complex = 12 KB
 constexpr int PS_SPI = 16;                                       // slices per blind-rotation step
 constexpr int PS_LAG = 1;
 
+template <int NCT>
 struct PsSmem {
+    static constexpr int slices = ps_slices(NCT);
     static constexpr size_t tw_bytes = (size_t)PS_TILE * 16;
-    static constexpr size_t ring_bytes = (size_t)PS_SLICES * PS_SLICE_ELEMS * 16;
+    static constexpr size_t ring_bytes = (size_t)slices * PS_SLICE_ELEMS * 16;
     static constexpr size_t omega_bytes = (size_t)PS_OMEGA * 16;
     static constexpr size_t bar_bytes = 256;
     static constexpr size_t head_bytes = tw_bytes + ring_bytes + omega_bytes + bar_bytes;
     static constexpr size_t region_bytes = (size_t)2 * PS_TILE * 16;   // one region per polynomial
     __host__ __device__ static size_t per_ct(int n) { return region_bytes + (((size_t)(n + 1) * 2 + 127) & ~(size_t)127); }
-    static size_t total(int n, int nct) { return head_bytes + (size_t)nct * per_ct(n); }
+    static size_t total(int n) { return head_bytes + (size_t)NCT * per_ct(n); }
 };
 
 __device__ __forceinline__ void ps_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -83,7 +94,8 @@ __global__ void __launch_bounds__(NCT * 128, 1)
 pbs_kernel_mb2_split(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
                      const uint64_t* __restrict__ luts, const int32_t* __restrict__ lut_index,
                      const cplx* __restrict__ g_tw, uint64_t* __restrict__ out) {
-    using S = PsSmem;
+    using S = PsSmem<NCT>;
+    constexpr int PS_SLICES = S::slices;
     constexpr int WARPS = NCT * 4;
     constexpr uint32_t TMEM_COLS = WARPS <= 4 ? 64 : (WARPS <= 8 ? 128 : 256);   // 64 columns per warp, 4 warps share a quadrant
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -287,7 +299,7 @@ template <int NCT>
 static cudaError_t launch_split_t(const fhe_b200_pbs_params& p, const cplx* bskf2, const uint64_t* d_in, int64_t B,
                                   const uint64_t* d_luts, const int32_t* d_lut_index, const cplx* tables, uint64_t* d_out,
                                   cudaStream_t s) {
-    const size_t smem = PsSmem::total(p.n, NCT);
+    const size_t smem = PsSmem<NCT>::total(p.n);
     cudaError_t e = cudaFuncSetAttribute(pbs_kernel_mb2_split<NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((B + NCT - 1) / NCT);
