@@ -86,7 +86,9 @@ def measure(dev, args, batches=None):
         ok2 = bool(np.array_equal(E.lwe_decrypt(S, _pad(out2), 59).cpu().numpy() & 15, table[msgs]))
         fastest = min(ms, mb2_ms)
         row = {"batch": int(B), "pbs_ms": fastest, "pbs_per_sec": B / (fastest * 1e-3),
-               "kernel": "pbs_kernel_mb2 (two key bits per step)" if mb2_ms < ms else "pbs_kernel_tmem (one key bit per step)",
+               "kernel": (("pbs_kernel_mb2_split<1> (two key bits per step, four warps per ciphertext)" if B <= 2 * sm
+                           else "pbs_kernel_mb2<1,4> (two key bits per step)") if mb2_ms < ms
+                          else "pbs_kernel_tmem (one key bit per step)"),
                "single_bit_ms": ms, "single_bit_per_sec": B / (ms * 1e-3),
                "multi_bit_ms": mb2_ms, "multi_bit_per_sec": B / (mb2_ms * 1e-3),
                "ks_ms": ks_ms, "ks32_int_pipe_ms": ks32_ms, "ks64_ms": ks64_ms,
@@ -117,8 +119,9 @@ def measure(dev, args, batches=None):
                      "frac": best["fp64_tflops"] / fp64_peak if fp64_peak else None,
                      "peak_source": "measured live (fhe_b200_probe_fp64, dependent-FMA chains)",
                      "flops_per_pbs": flops, "bsk_fourier_bytes": int(bsk_bytes),
-                     "fp64_pipe_active_ncu": 0.523, "smem_wavefronts_of_peak_ncu": 0.43,
-                     "ncu_source": "profiles/r1_ncu_pbs_mb2_v1.txt (multi-bit, batch 592); single-bit: profiles/r1_ncu_pbs_v5_dit.txt",
+                     "fp64_pipe_active_ncu": 0.502, "smem_wavefronts_of_peak_ncu": 0.519, "issue_active_ncu": 0.354,
+                     "ncu_source": "profiles/r2_ncu_pbs_mb2_v10.txt (the shipped pbs_kernel_mb2<1,4>, batch 1184); small-batch "
+                                   "kernel pbs_kernel_mb2_split: profiles/r2_ncu_pbs_split_v1.txt",
                      "hbm_term": {"bytes_per_batch": int(bsk_bytes + best["batch"] * (p.n + 1 + p.k * p.N + 1 + p.N) * 8),
                                   "note": "the Fourier key is read from HBM once per launch and then served from L2 "
                                           "(ncu: 52 MB DRAM reads per launch); key streaming never binds once batched"},
