@@ -806,6 +806,24 @@ int fhe_b200_similarity_run_seeded(fhe_b200_similarity* s, const uint64_t* d_bod
     return FHE_B200_OK;
 }
 
+}  // extern "C"
+
+// second stream + events of the host-buffer entry points (created on first use)
+static int ensure_side_stream(fhe_b200_similarity* s) {
+    if (s->enc_stream) return FHE_B200_OK;
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&s->enc_stream, cudaStreamNonBlocking, lo));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&s->ev_enc[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&s->ev_q, cudaEventDisableTiming));
+    return FHE_B200_OK;
+}
+
+extern "C" {
+
 int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity* s, const float* h_X, int64_t B, uint64_t enc_seed,
                                             uint64_t ct_base, double* h_y, int64_t* h_q_y) {
     REQUIRE(s, "null model");
@@ -826,6 +844,9 @@ int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity* s, const float*
     CU(s->hy.reserve(16 * (size_t)B));
     double* d_y = (double*)s->y.p;
     int64_t* d_qy = (int64_t*)((char*)s->y.p + 8 * (size_t)B);
+    // One piece, one stream.  Splitting the batch in two so that the upload of the second half and the read-back of
+    // the first run under the kernels was measured and is SLOWER at the bench size (1000 documents: 0.412 -> 0.452 ms per
+    // call): the copies are 20 us of a 410 us call, and two half-size launches of each kernel lose more to their tails.
     memcpy(s->hX.p, h_X, xbytes);   // staged through pinned memory so the copy is truly asynchronous
     CU(cudaMemcpyAsync(s->X.p, s->hX.p, xbytes, cudaMemcpyHostToDevice, st));
     if (int r = fhe_b200_similarity_encrypt_seeded(s, (const float*)s->X.p, B, enc_seed, ct_base, (uint64_t*)s->ct.p, st)) return r;
@@ -974,16 +995,7 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
     const auto& sp = s->spec;
     CU(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->stream;
-    if (!s->enc_stream) {
-        int lo = 0, hi = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CU(cudaStreamCreateWithPriority(&s->enc_stream, cudaStreamNonBlocking, lo));
-        for (int i = 0; i < 2; ++i) {
-            CU(cudaEventCreateWithFlags(&s->ev_enc[i], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming));
-        }
-        CU(cudaEventCreateWithFlags(&s->ev_q, cudaEventDisableTiming));
-    }
+    if (int r = ensure_side_stream(s)) return r;
     const size_t xbytes = sizeof(float) * (size_t)B * sp.d;
     CU(s->X.reserve(xbytes));
     CU(s->hX.reserve(xbytes));
