@@ -507,8 +507,10 @@ def sharded_steps(R: Ranks, model, rows_fn, total_docs: int, fmt: str, steps: in
 def e2e_single_gpu(model, X, steps):
     """FHESimilarityModel.predict_encrypted with host float32 rows in / float64 scores out + host top-k."""
     import torch
+    from fhe_icp_b200._native import pinned_copy
     c = model.model.fhe_circuit
     res = {}
+    X = pinned_copy(np.ascontiguousarray(X, dtype=np.float32))    # the step's inputs sit in pinned host memory
     for fmt in ("expanded", "seeded"):        # seeded (the default format) last: its ranking is the one checked
         c.ciphertext_format = fmt
         for _ in range(2):

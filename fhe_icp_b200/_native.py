@@ -13,11 +13,13 @@ import shutil
 import subprocess
 from pathlib import Path
 
+import numpy as np
+
 _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 _SO = _PKG / "libfhe_b200.so"
-_SOURCES = ["api.cu", "lwe.cu", "keys.cu", "keyswitch.cu", "ks_mma.cu", "pbs.cu", "pbs_split.cu", "probe.cu"]
-_HEADERS = ["common.cuh", "kernels.h", "fft.cuh", "lwe_device.cuh", "ks_mma_layout.cuh", "fft_split.cuh", "pbs_split.cuh", "../../include/fhe_b200.h"]
+_SOURCES = ["api.cu", "lwe.cu", "keys.cu", "keyswitch.cu", "ks_mma.cu", "pbs.cu", "pbs_split.cu", "pbs_wide.cu", "probe.cu"]
+_HEADERS = ["common.cuh", "kernels.h", "fft.cuh", "lwe_device.cuh", "ks_mma_layout.cuh", "fft_split.cuh", "pbs_split.cuh", "pbs_wide.cuh", "../../include/fhe_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -180,6 +182,7 @@ SIGNATURES = {
     "fhe_b200_ksk_to_32": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, _vp]),
     "fhe_b200_keyswitch32": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp]),
     "fhe_b200_pbs_mb2_split": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, C.c_int32, _vp, _vp]),
+    "fhe_b200_pbs_mb2_wide": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "fhe_b200_ksk_mma_bytes": (C.c_uint64, [C.POINTER(PBSParams)]),
     "fhe_b200_keyswitch_mma_workspace_bytes": (C.c_uint64, [C.POINTER(PBSParams), C.c_int64]),
     "fhe_b200_ksk_to_mma": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, _vp]),
@@ -194,6 +197,8 @@ SIGNATURES = {
     "fhe_b200_similarity_encrypt": (C.c_int, [_vp, _vp, C.c_int64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "fhe_b200_similarity_run": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
     "fhe_b200_similarity_decrypt": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp]),
+    "fhe_b200_host_alloc": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
+    "fhe_b200_host_free": (C.c_int, [_vp, _vp]),
     "fhe_b200_peer_alloc": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp), _u8p]),
     "fhe_b200_peer_open": (C.c_int, [_vp, _u8p, C.POINTER(_vp)]),
     "fhe_b200_peer_close": (C.c_int, [_vp, _vp]),
@@ -273,3 +278,26 @@ def context(device: int | None = None) -> Context:
     if device not in _CTX:
         _CTX[device] = Context(device)
     return _CTX[device]
+
+
+def pinned_empty(shape, dtype=np.float32, device: int | None = None) -> np.ndarray:
+    """A numpy array over page-locked host memory (``fhe_b200_host_alloc``).  Rows passed to ``predict_encrypted`` /
+    ``fhe_b200_similarity_predict_host[_seeded]`` from such an array are uploaded from where they are (no staging copy).
+    The memory is released when the array -- and every view of it -- is garbage collected."""
+    import weakref
+    ctx = context(device)
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = _vp()
+    check(lib().fhe_b200_host_alloc(ctx.handle, max(n, 1), C.byref(p)))
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lambda h=ctx.handle, q=p.value: lib().fhe_b200_host_free(h, _vp(q)))
+    return arr
+
+
+def pinned_copy(a: np.ndarray, device: int | None = None) -> np.ndarray:
+    a = np.ascontiguousarray(a)
+    out = pinned_empty(a.shape, a.dtype, device)
+    out[...] = a
+    return out

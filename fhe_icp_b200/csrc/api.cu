@@ -571,6 +571,19 @@ int fhe_b200_pbs_mb2_split(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, cons
     return FHE_B200_OK;
 }
 
+int fhe_b200_pbs_mb2_wide(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_bskf2, const uint64_t* d_in,
+                          int64_t B, const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_bskf2 && d_in && d_luts && d_out, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    REQUIRE(p->l_pbs == 1 && p->k == 1 && (p->n & 1) == 0, "the wide kernel covers k = 1, l_pbs = 1, even n");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_pbs_mb2_wide(*p, d_bskf2, d_in, B, d_luts, d_lut_index, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
 // ---- tensor-core keyswitch (ks_mma.cu)
 uint64_t fhe_b200_ksk_mma_bytes(const fhe_b200_pbs_params* p) {
     return (p && fhe::keyswitch_mma_supported(*p)) ? (uint64_t)fhe::keyswitch_mma_key_bytes(*p) : 0;
@@ -808,6 +821,27 @@ int fhe_b200_similarity_run_seeded(fhe_b200_similarity* s, const uint64_t* d_bod
 
 }  // extern "C"
 
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / fhe_b200_host_alloc)?  Then it can be the
+// source of an asynchronous copy as it is.
+static bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// A/B switches of predict_host_seeded (FHE_B200_E2E_MODE, a bit mask; unset = the shipped path)
+enum : unsigned { E2E_ASSUME_PAGEABLE = 1, E2E_ZERO_COPY_IN = 2, E2E_COPY_OUT = 4 };
+static unsigned e2e_mode() {
+    static const unsigned m = [] {
+        const char* v = getenv("FHE_B200_E2E_MODE");
+        return v ? (unsigned)strtoul(v, nullptr, 0) : 0u;
+    }();
+    return m;
+}
+
 // second stream + events of the host-buffer entry points (created on first use)
 static int ensure_side_stream(fhe_b200_similarity* s) {
     if (s->enc_stream) return FHE_B200_OK;
@@ -836,7 +870,6 @@ int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity* s, const float*
     cudaStream_t st = s->stream;
     const size_t xbytes = sizeof(float) * (size_t)B * sp.d;
     CU(s->X.reserve(xbytes));
-    CU(s->hX.reserve(xbytes));
     CU(s->ct.reserve(sizeof(uint64_t) * (size_t)B * sp.d));       // bodies only
     CU(s->out.reserve(sizeof(uint64_t) * (size_t)B * s->M * sp.stride));
     // scores and integers share one device / one pinned buffer: a single device->host copy
@@ -847,15 +880,51 @@ int fhe_b200_similarity_predict_host_seeded(fhe_b200_similarity* s, const float*
     // One piece, one stream.  Splitting the batch in two so that the upload of the second half and the read-back of
     // the first run under the kernels was measured and is SLOWER at the bench size (1000 documents: 0.412 -> 0.452 ms per
     // call): the copies are 20 us of a 410 us call, and two half-size launches of each kernel lose more to their tails.
-    memcpy(s->hX.p, h_X, xbytes);   // staged through pinned memory so the copy is truly asynchronous
-    CU(cudaMemcpyAsync(s->X.p, s->hX.p, xbytes, cudaMemcpyHostToDevice, st));
-    if (int r = fhe_b200_similarity_encrypt_seeded(s, (const float*)s->X.p, B, enc_seed, ct_base, (uint64_t*)s->ct.p, st)) return r;
+    // What the call does shed is fixed overhead around the kernels: rows that already sit in pinned memory
+    // (fhe_b200_host_alloc, torch pin_memory) are uploaded from where they are -- pageable rows are staged through the
+    // model's pinned buffer so that the copy is truly asynchronous -- and the fused client kernel stores the B scores
+    // and integers straight into the model's pinned result buffer (mapped, 16 B per document over PCIe), so no
+    // device->host copy operation follows it.
+    const unsigned mode = e2e_mode();
+    const float* src = h_X;
+    if (!(mode & E2E_ASSUME_PAGEABLE) && !host_ptr_is_pinned(h_X)) src = nullptr;
+    if (!src) {
+        CU(s->hX.reserve(xbytes));
+        memcpy(s->hX.p, h_X, xbytes);
+        src = (const float*)s->hX.p;
+    }
+    const float* d_X = (const float*)s->X.p;
+    if (mode & E2E_ZERO_COPY_IN) d_X = src;         // A/B: the encryption kernel reads the pinned rows over PCIe itself
+    else CU(cudaMemcpyAsync(s->X.p, src, xbytes, cudaMemcpyHostToDevice, st));
+    if (int r = fhe_b200_similarity_encrypt_seeded(s, d_X, B, enc_seed, ct_base, (uint64_t*)s->ct.p, st)) return r;
     if (int r = fhe_b200_similarity_run_seeded(s, (const uint64_t*)s->ct.p, B, enc_seed, ct_base, (uint64_t*)s->out.p, st)) return r;
-    if (int r = fhe_b200_similarity_decrypt(s, (const uint64_t*)s->out.p, B, d_y, d_qy, st)) return r;
-    CU(cudaMemcpyAsync(s->hy.p, s->y.p, 16 * (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (mode & E2E_COPY_OUT) {
+        if (int r = fhe_b200_similarity_decrypt(s, (const uint64_t*)s->out.p, B, d_y, d_qy, st)) return r;
+        CU(cudaMemcpyAsync(s->hy.p, s->y.p, 16 * (size_t)B, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (int r = fhe_b200_similarity_decrypt(s, (const uint64_t*)s->out.p, B, (double*)s->hy.p,
+                                                (int64_t*)((char*)s->hy.p + 8 * (size_t)B), st)) return r;
+    }
     CU(cudaStreamSynchronize(st));
     if (h_y) memcpy(h_y, s->hy.p, sizeof(double) * (size_t)B);
     if (h_q_y) memcpy(h_q_y, (char*)s->hy.p + 8 * (size_t)B, sizeof(int64_t) * (size_t)B);
+    return FHE_B200_OK;
+}
+
+int fhe_b200_host_alloc(fhe_b200_ctx* ctx, uint64_t bytes, void** h_ptr) {
+    REQUIRE(ctx && h_ptr, "host_alloc: null argument");
+    *h_ptr = nullptr;
+    REQUIRE(bytes > 0, "host_alloc: empty allocation");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_host_free(fhe_b200_ctx* ctx, void* h_ptr) {
+    REQUIRE(ctx, "host_free: null context");
+    if (!h_ptr) return FHE_B200_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFreeHost(h_ptr));
     return FHE_B200_OK;
 }
 
@@ -998,7 +1067,6 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
     if (int r = ensure_side_stream(s)) return r;
     const size_t xbytes = sizeof(float) * (size_t)B * sp.d;
     CU(s->X.reserve(xbytes));
-    CU(s->hX.reserve(xbytes));
     // Full ciphertexts are materialised in HBM in chunks (two buffers of <= 1 GiB).  Encryption is
     // integer-pipe bound and the dot product HBM bound, so chunk i+1 is encrypted on a second stream
     // while chunk i is evaluated and decrypted.
@@ -1020,12 +1088,15 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
     CU(s->ct.reserve(2 * row_bytes * (size_t)chunk));
     CU(s->out.reserve(sizeof(uint64_t) * (size_t)chunk * s->M * sp.stride));
     CU(s->q.reserve(sizeof(int64_t) * (size_t)cnt));
-    CU(s->y.reserve(sizeof(double) * (size_t)B));
-    CU(s->qy.reserve(sizeof(int64_t) * (size_t)B));
-    CU(s->hy.reserve(sizeof(double) * (size_t)B));
+    CU(s->hy.reserve(sizeof(double) * (size_t)B));      // the client kernel stores into these mapped pinned buffers
     CU(s->hqy.reserve(sizeof(int64_t) * (size_t)B));
-    memcpy(s->hX.p, h_X, xbytes);  // stage through pinned memory so the copy is truly async
-    CU(cudaMemcpyAsync(s->X.p, s->hX.p, xbytes, cudaMemcpyHostToDevice, st));
+    const void* src = h_X;             // pinned rows go up from where they are, pageable ones through the pinned stage
+    if (!host_ptr_is_pinned(h_X)) {
+        CU(s->hX.reserve(xbytes));
+        memcpy(s->hX.p, h_X, xbytes);
+        src = s->hX.p;
+    }
+    CU(cudaMemcpyAsync(s->X.p, src, xbytes, cudaMemcpyHostToDevice, st));
     const int64_t qmin = -sp.x_offset, qmax = (1LL << sp.n_bits) - 1 - sp.x_offset;
     CU(fhe::launch_quantize((const float*)s->X.p, cnt, sp.x_scale, sp.x_zero_point, qmin, qmax, (int64_t*)s->q.p, st));
     CU(cudaEventRecord(s->ev_q, st));
@@ -1050,10 +1121,8 @@ int fhe_b200_similarity_predict_host(fhe_b200_similarity* s, const float* h_X, i
         CU(cudaEventRecord(s->ev_free[k & 1], st));
         CU(fhe::launch_similarity_decrypt(s->d_key_bits, sp.n, sp.stride, s->out.p, false, rows, s->M, sp.shift,
                                           sp.w_zero_point, sp.q_bias, sp.out_scale, sp.out_zero_point,
-                                          (double*)s->y.p + r0, (int64_t*)s->qy.p + r0, st));
+                                          (double*)s->hy.p + r0, (int64_t*)s->hqy.p + r0, st));
     }
-    CU(cudaMemcpyAsync(s->hy.p, s->y.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(s->hqy.p, s->qy.p, sizeof(int64_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (h_y) memcpy(h_y, s->hy.p, sizeof(double) * (size_t)B);
     if (h_q_y) memcpy(h_q_y, s->hqy.p, sizeof(int64_t) * (size_t)B);

@@ -121,6 +121,11 @@ cudaError_t launch_pbs_mb2_split(const fhe_b200_pbs_params& p, const double* d_b
                                  const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
                                  int cts_per_cta, cudaStream_t s);
 
+// pbs_wide.cu -- four-warps-per-polynomial multi-bit blind rotation, one ciphertext per CTA (256 threads, accumulator
+// and twiddles in registers): the latency kernel, dispatched by launch_pbs_mb2 up to one ciphertext per SM.
+cudaError_t launch_pbs_mb2_wide(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
+                                const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, cudaStream_t s);
+
 // probe.cu
 cudaError_t probe_fp64(int sm_count, double* tflops, cudaStream_t s);
 

@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <mutex>
 
+#include <cstdio>
+
 #include "common.cuh"
 #include "fft.cuh"
 #include "kernels.h"
@@ -62,8 +64,19 @@ static cudaError_t get_tables(const cplx** tw) {
     return cudaSuccess;
 }
 
+// Named barrier `id` (1..8) with an IMMEDIATE barrier number: with a register operand ptxas reserves all 16 hardware
+// barriers for the CTA ("used 16 barriers"), and barriers are an occupancy limit of the SM.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    switch (id) {
+        case 1: asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); break;
+        case 2: asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); break;
+        case 3: asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); break;
+        case 4: asm volatile("bar.sync 4, %0;" ::"r"(nthreads) : "memory"); break;
+        case 5: asm volatile("bar.sync 5, %0;" ::"r"(nthreads) : "memory"); break;
+        case 6: asm volatile("bar.sync 6, %0;" ::"r"(nthreads) : "memory"); break;
+        case 7: asm volatile("bar.sync 7, %0;" ::"r"(nthreads) : "memory"); break;
+        default: asm volatile("bar.sync 8, %0;" ::"r"(nthreads) : "memory"); break;
+    }
 }
 
 __device__ __forceinline__ uint64_t f64_to_torus(double x) {
@@ -666,6 +679,9 @@ struct PbsMb2Smem {
     static size_t total(int n, int nct) { return head_bytes + (size_t)nct * per_ct(n); }
 };
 
+#ifndef MB2_L1_NCT
+#define MB2_L1_NCT 4                 // ciphertexts per CTA of the large-batch kernel (A/B: 2 per CTA, one CTA per SM: 74.5 k PBS/s vs 108 k)
+#endif
 template <int L, int NCT>
 __global__ void __launch_bounds__(NCT * 64 * L, 1)
 pbs_kernel_mb2(const cplx* __restrict__ bskf2, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
@@ -993,6 +1009,13 @@ static cudaError_t launch_pbs_mb2_t(const fhe_b200_pbs_params& p, const cplx* bs
     const size_t smem = PbsMb2Smem<L>::total(p.n, NCT);
     cudaError_t e = cudaFuncSetAttribute(pbs_kernel_mb2<L, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(pbs_kernel_mb2<L, NCT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    if (getenv("FHE_B200_PBS_DEBUG")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pbs_kernel_mb2<L, NCT>, NCT * 64 * L, smem);
+        fprintf(stderr, "pbs_kernel_mb2<%d,%d>: smem %zu B, %d CTA(s) per SM\n", L, NCT, smem, nb);
+    }
     const unsigned grid = (unsigned)((B + NCT - 1) / NCT);
     pbs_kernel_mb2<L, NCT><<<grid, NCT * 64 * L, smem, s>>>(bskf2, d_in, B, p.n, p.beta_pbs, d_luts, d_lut_index, tw, d_out);
     count_launch();
@@ -1014,7 +1037,7 @@ cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, 
     // ciphertext win; from four ciphertexts per SM on, two fat warps per ciphertext are ahead (107 k vs 102 k PBS/s)
     if (B <= 2 * (int64_t)sm_count && p.beta_pbs <= 31)
         return launch_pbs_mb2_split(p, d_bskf2, d_in, B, d_luts, d_lut_index, d_out, sm_count, 1, s);
-    return launch_pbs_mb2_t<1, 4>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    return launch_pbs_mb2_t<1, MB2_L1_NCT>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
 }
 
 // ------------------------------------------------------------------------------- packed encrypted inner products

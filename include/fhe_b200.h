@@ -243,6 +243,13 @@ int fhe_b200_pbs_mb2(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const doub
 int fhe_b200_pbs_mb2_split(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
                            const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
                            const int32_t *d_lut_index, int32_t cts_per_cta, uint64_t *d_out, void *stream);
+/* The same multi-bit blind rotation with FOUR warps per polynomial (8 points per thread, accumulator and twiddles in
+ * registers; pbs_wide.cu): one ciphertext per CTA of 256 threads -- the latency kernel.  fhe_b200_pbs_mb2 itself runs
+ * it while there is at most one ciphertext per SM; this entry point forces it for the tests and the batch sweep.
+ * Same key, inputs and outputs as fhe_b200_pbs_mb2; k = 1, l_pbs = 1, n even. */
+int fhe_b200_pbs_mb2_wide(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
+                          const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
+                          const int32_t *d_lut_index, uint64_t *d_out, void *stream);
 /* 32-bit keyswitch ("KS32"): key rounded to the top 32 torus bits, u32 accumulation; d_scratch32 holds
  * B*(n+1) u32 words; the result is written as u64 words with the low half zero. */
 int fhe_b200_ksk_to_32(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_ksk,
@@ -293,6 +300,13 @@ int fhe_b200_similarity_decrypt(fhe_b200_similarity *sim, const uint64_t *d_out,
 /* seeded variants: d_bodies [B][d] u64, ciphertext ids ct_base + b*d + j */
 int fhe_b200_similarity_encrypt_seeded(fhe_b200_similarity *sim, const float *d_X, int64_t B,
                                        uint64_t enc_seed, uint64_t ct_base, uint64_t *d_bodies, void *stream);
+/* Page-locked host memory for the host-buffer entry points.  Rows handed to predict_host[_seeded] from such a
+ * buffer (or from any cudaHostAlloc / cudaHostRegister'ed range, e.g. a torch pinned tensor) are uploaded from where
+ * they are; pageable rows are first staged through the model's own pinned buffer.  The reference passes plain numpy
+ * arrays (fhe_similarity.py:151); this is the buffer a caller allocates when it wants the upload off its critical path. */
+int fhe_b200_host_alloc(fhe_b200_ctx *ctx, uint64_t bytes, void **h_ptr);
+int fhe_b200_host_free(fhe_b200_ctx *ctx, void *h_ptr);
+
 /* same with the clear product fused in: feature (b, j) = d_query[j] * d_docs[b*d + j] in IEEE float32, the array the
  * reference builds on the host before every call (emb1 * emb2, /root/reference/batch_operations.py:226,273) */
 int fhe_b200_similarity_encrypt_seeded_products(fhe_b200_similarity *sim, const float *d_query, const float *d_docs,

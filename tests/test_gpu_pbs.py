@@ -326,3 +326,34 @@ def test_multibit_pbs_split_kernel(O, cuda_dev, which, B, nct):
     err = (O.lwe_phase(K.oS, got) - (table[msgs].astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
     assert np.log2(err.std() + 1) - 64 < -13.5
     assert E.pbs_mb2_split(K.p, K.bskf2, ct[:0], lut_d, cts_per_cta=nct).shape == (0, K.p.N + 1)
+
+
+@pytest.mark.parametrize("which,B", [("toy", 16), ("toy", 3), ("p4", 16), ("p4", 1), ("p4", 148 + 9)])
+def test_multibit_pbs_wide_kernel(O, cuda_dev, which, B):
+    """Same acceptance as test_multibit_pbs for the four-warps-per-polynomial latency kernel (pbs_wide.cu, one
+    ciphertext per CTA): every message maps to LUT[m], phases agree with the oracle's multi-bit PBS within the noise
+    bound, per-ciphertext LUT selection works, and more CTAs than SMs (a second wave) changes nothing."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    d = {"toy": TOY, "p4": P4}[which]
+    K = KeysMB2(O, cuda_dev, d)
+    rng = np.random.RandomState(1000 + B)
+    msgs = rng.randint(0, 16, size=B)
+    msgs[: min(B, 16)] = np.arange(16)[: min(B, 16)]
+    ct = E.lwe_encrypt(K.s, torch.as_tensor(msgs), 59, K.op.sigma_lwe_abs, enc_seed=B, ct_base=100,
+                       stride=K.p.n + 2 - (K.p.n % 2))[:, : K.p.n + 1].contiguous()
+    tables = np.stack([(np.arange(16) * 5 + 2) % 16, (np.arange(16) * 3 + 7) % 16])
+    luts = np.stack([E.make_lut_poly(tb, 4, K.p.N, 59) for tb in tables])
+    lut_d = E.from_u64_numpy(luts, cuda_dev)
+    which_lut = rng.randint(0, 2, size=B).astype(np.int32)
+    got = _u64(E.pbs_mb2_wide(K.p, K.bskf2, ct, lut_d, lut_index=torch.as_tensor(which_lut)))
+    want = tables[which_lut, msgs]
+    assert np.array_equal(O.lwe_decrypt(K.oS, got, 59) & 15, want)
+    of = O.bsk2_to_fourier(K.op, O.bsk2_gen(K.op, K.os, K.oS, K.evk_seed))
+    m = min(B, 8)
+    ref = np.concatenate([O.pbs_mb2(K.op, of, _u64(ct)[i:i + 1], luts[which_lut[i]]) for i in range(m)])
+    diff = (O.lwe_phase(K.oS, got[:m]) - O.lwe_phase(K.oS, ref)).view(np.int64).astype(np.float64)
+    assert np.log2(np.abs(diff).max() + 1) - 64 < -12
+    err = (O.lwe_phase(K.oS, got) - (want.astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
+    assert np.log2(np.abs(err).max() + 1) - 64 < -11
+    assert E.pbs_mb2_wide(K.p, K.bskf2, ct[:0], lut_d).shape == (0, K.p.N + 1)
