@@ -15,11 +15,12 @@
 // stage, where each polynomial reads the other's spectrum).  tests/emul/pbs_wide_emul.cpp replays this plan in several
 // thread orders.
 //
-// Key stream: the Fourier key of fhe_b200_bsk2_to_fourier as it is ([pair][32 frequency blocks][384 complex]).  The bins
-// of slice kL sit in the four consecutive blocks 4kL .. 4kL + 3 (24 KB, one bulk copy); a ring of WIDE_SLOTS slices is
-// kept full by thread 0 (full / empty mbarriers, the pattern of pbs_kernel_mb2).  One SM draws ~64 B per clock from L2,
-// so the 192 KB of a step stream for ~3000 clocks: most of it arrives under the transforms, the rest paces the
-// pointwise stage.
+// Key stream: the Fourier key of fhe_b200_bsk2_to_fourier as it is ([pair][32 frequency blocks][384 complex]).  Ring
+// slice q of a step is the eight consecutive blocks 8q .. 8q + 7 (48 KB, ONE bulk copy: a bulk copy takes ~1200 clocks
+// from L2 whatever its size up to 48 KB, tools/stream_probe.cu, so few large copies in flight beat many small ones);
+// three slots.  A slot is refilled by the LAST warp that leaves it (a shared counter per slot), i.e. at the earliest
+// possible moment and without anybody spinning; the wait on a slice's full-barrier is issued one turn early so that
+// the ~90 clocks a try_wait takes even on a completed barrier overlap the arithmetic.
 //
 // Memory safety: compute-sanitizer is closed on this pool; the plan above is emulated on the CPU and the
 // kernel is covered by the acceptance of the other blind-rotation kernels on ragged batches.
@@ -37,7 +38,7 @@ constexpr int PW_N = nfft::NPOLY;
 constexpr int PW_TILE = nfft::TILE_ELEMS;     // offset of the omega table inside pbs_tables()
 constexpr int PW_OMEGA = 128;
 #ifndef WIDE_SLOTS
-#define WIDE_SLOTS 6
+#define WIDE_SLOTS 3
 #endif
 constexpr int PW_SLOTS = WIDE_SLOTS;
 constexpr int PW_THREADS = 2 * wfft::WT;
@@ -69,7 +70,7 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
     cplx* xbufs = reinterpret_cast<cplx*>(smem_raw + S::ring_bytes);
     cplx* omega = reinterpret_cast<cplx*>(smem_raw + S::ring_bytes + S::x_bytes);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + S::ring_bytes + S::x_bytes + S::omega_bytes);
-    uint64_t* bar_empty = bar_full + PW_SLOTS;
+    unsigned* left = reinterpret_cast<unsigned*>(bar_full + PW_SLOTS);      // warps that have left each slot
     uint16_t* a_tilde = reinterpret_cast<uint16_t*>(smem_raw + S::ring_bytes + S::x_bytes + S::omega_bytes + S::bar_bytes);
 
     const int tid = threadIdx.x, t = tid >> 7, u = tid & 127, lane = tid & 31, wp = u >> 5;
@@ -77,7 +78,7 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
     if (b >= B) return;
     for (int i = tid; i < PW_OMEGA; i += PW_THREADS) omega[i] = g_tw[PW_TILE + i];
     if (tid == 0) {
-        for (int q = 0; q < PW_SLOTS; ++q) { mbar_init(&bar_full[q], 1); mbar_init(&bar_empty[q], PW_WARPS); }
+        for (int q = 0; q < PW_SLOTS; ++q) { mbar_init(&bar_full[q], 1); left[q] = 0; }
         mbar_fence_init();
     }
     const uint64_t* ct = in + (size_t)b * (n + 1);
@@ -87,7 +88,7 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
     const int pairs = n >> 1;
     const int total_slices = pairs * wfft::SLICES_PER_STEP;
     constexpr uint32_t SLICE_BYTES = (uint32_t)(wfft::SLICE_ELEMS * 16);
-    auto load_slice = [&](int slot, int q) {     // slice q of the whole key walk is contiguous: blocks 4(q%8).. of pair q/8
+    auto load_slice = [&](int slot, int q) {     // slice q of the whole key walk is contiguous: blocks 8(q%4).. of pair q/4
         mbar_expect_tx(&bar_full[slot], SLICE_BYTES);
         tma_load_1d(ring + (size_t)slot * wfft::SLICE_ELEMS, bskf2 + (size_t)q * wfft::SLICE_ELEMS, SLICE_BYTES, &bar_full[slot]);
     };
@@ -152,27 +153,37 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
         __syncthreads();
         // ---- pointwise stage
         double gre[8], gim[8];
+        uint32_t ready = mbar_try_wait(&bar_full[(i * wfft::SLICES_PER_STEP) % PW_SLOTS],
+                                       (uint32_t)(((i * wfft::SLICES_PER_STEP) / PW_SLOTS) & 1));
 #pragma unroll
-        for (int kL = 0; kL < 8; ++kL) {
-            const int sidx = i * wfft::SLICES_PER_STEP + kL;
+        for (int q = 0; q < wfft::SLICES_PER_STEP; ++q) {     // two bins (one ring slice) per turn
+            const int sidx = i * wfft::SLICES_PER_STEP + q;
             const int slot = sidx % PW_SLOTS;
-            const cplx fo = o0[kL * wfft::WT + u];
-            cplx fa;
-            fa.x = re[kL];
-            fa.y = im[kL];
-            mbar_wait(&bar_full[slot], (uint32_t)((sidx / PW_SLOTS) & 1));
-            const cplx* blk = ring + (size_t)slot * wfft::SLICE_ELEMS + (size_t)wp * nfft::MB2_BLOCK_ELEMS;
-            nfft::split_pointwise_bin(t, lane, fa, fo, blk, mo, gre[kL], gim[kL]);
+            const cplx fo0 = o0[(2 * q) * wfft::WT + u], fo1 = o0[(2 * q + 1) * wfft::WT + u];
+            cplx fa0, fa1;
+            fa0.x = re[2 * q]; fa0.y = im[2 * q];
+            fa1.x = re[2 * q + 1]; fa1.y = im[2 * q + 1];
+#ifndef WIDE_NOSTREAM      // (timing experiment: WIDE_NOSTREAM computes on whatever the ring holds -- invalid results)
+            if (!ready) mbar_wait(&bar_full[slot], (uint32_t)((sidx / PW_SLOTS) & 1));
+            if (q + 1 < wfft::SLICES_PER_STEP)      // the next turn's wait, issued now: its latency hides under this turn
+                ready = mbar_try_wait(&bar_full[(sidx + 1) % PW_SLOTS], (uint32_t)(((sidx + 1) / PW_SLOTS) & 1));
+#endif
+            const cplx* blk0 = ring + (size_t)slot * wfft::SLICE_ELEMS + (size_t)wp * nfft::MB2_BLOCK_ELEMS;
+            const cplx* blk1 = blk0 + 4 * nfft::MB2_BLOCK_ELEMS;
+            nfft::split_pointwise_bin(t, lane, fa0, fo0, blk0, mo, gre[2 * q], gim[2 * q]);
+            nfft::split_pointwise_bin(t, lane, fa1, fo1, blk1, mo, gre[2 * q + 1], gim[2 * q + 1]);
+#ifndef WIDE_NOSTREAM
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[slot]);
-            if (tid == 0) {          // keep the ring full: refill the slot every warp left one slice ago
-                const int done = sidx - 1, next = done + PW_SLOTS;
-                if (done >= 0 && next < total_slices) {
-                    const int ds = done % PW_SLOTS;
-                    mbar_wait(&bar_empty[ds], (uint32_t)((done / PW_SLOTS) & 1));
-                    load_slice(ds, next);
+            if (lane == 0) {       // the last warp to leave the slot refills it (its own reads are done: their values are used above)
+                __threadfence_block();
+                if (atomicAdd(&left[slot], 1u) == PW_WARPS - 1) {
+                    __threadfence_block();
+                    left[slot] = 0;
+                    const int next = sidx + PW_SLOTS;
+                    if (next < total_slices) load_slice(slot, next);
                 }
             }
+#endif
         }
         wfft::inv_stage3(u, gre, gim, e1);
         __syncthreads();                               // also: nobody reads the published spectra any more

@@ -213,11 +213,11 @@ FHE_HD void inv_stage1(const Twiddles& tw, int u, const cplx* x1, double (&re)[8
 }
 
 // ---- pointwise stage of thread v of output polynomial t: bins k = v + 128 kL.  The key of bin k sits in frequency
-// block k >> 5 = (v >> 5) + 4 kL at lane v & 31 (layout of bsk2_to_fourier_kernel, see pbs_split.cuh); one ring slice
-// holds the four consecutive blocks 4kL .. 4kL + 3.
-constexpr int SLICE_BLOCKS = 4;
-constexpr int SLICE_ELEMS = SLICE_BLOCKS * nfft::MB2_BLOCK_ELEMS;    // 1536 complex = 24 KB
-constexpr int SLICES_PER_STEP = 8;
+// block k >> 5 = (v >> 5) + 4 kL at lane v & 31 (layout of bsk2_to_fourier_kernel, see pbs_split.cuh); ring slice q
+// holds the eight consecutive blocks 8q .. 8q + 7, i.e. the bins kL = 2q and 2q + 1 of every thread.
+constexpr int SLICE_BLOCKS = 8;                                      // two bins per thread (kL = 2q, 2q + 1)
+constexpr int SLICE_ELEMS = SLICE_BLOCKS * nfft::MB2_BLOCK_ELEMS;    // 3072 complex = 48 KB
+constexpr int SLICES_PER_STEP = 4;
 
 // monomial factors c_g = rho_k^(e_g) - 1 at k = v (kL = 0) and the step r_g = omega^(512 e_g) = exp(2*pi*i*e_g/8)
 // from one slice to the next: rho_k^e = omega^((4k+1)e).  omega: pbs.cu's two-level table ([0,64) omega^x, [64,128)

@@ -20,6 +20,9 @@ kernels = {"wide": lambda ct, out: E.pbs_mb2_wide(p, bskf2, ct, lut, out=out),
            "split<1>": lambda ct, out: E.pbs_mb2_split(p, bskf2, ct, lut, out=out, cts_per_cta=1),
            "split<4>": lambda ct, out: E.pbs_mb2_split(p, bskf2, ct, lut, out=out, cts_per_cta=4),
            "dispatch": lambda ct, out: E.pbs_mb2(p, bskf2, ct, lut, out=out)}
+import os
+if os.environ.get("SWEEP_ONLY"):
+    kernels = {k: v for k, v in kernels.items() if k in os.environ["SWEEP_ONLY"].split(",")}
 for B in batches:
     msgs = np.random.RandomState(B).randint(0, 16, size=B)
     ct_big = E.lwe_encrypt(S, torch.as_tensor(msgs), 59, p.sigma_glwe_abs, enc_seed=303, stride=p.N + 2)[:, : p.N + 1].contiguous()
