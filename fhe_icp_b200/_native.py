@@ -18,8 +18,8 @@ import numpy as np
 _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 _SO = _PKG / "libfhe_b200.so"
-_SOURCES = ["api.cu", "lwe.cu", "keys.cu", "keyswitch.cu", "ks_mma.cu", "pbs.cu", "pbs_split.cu", "pbs_wide.cu", "probe.cu"]
-_HEADERS = ["common.cuh", "kernels.h", "fft.cuh", "lwe_device.cuh", "ks_mma_layout.cuh", "fft_split.cuh", "pbs_split.cuh", "pbs_wide.cuh", "../../include/fhe_b200.h"]
+_SOURCES = ["api.cu", "lwe.cu", "keys.cu", "keyswitch.cu", "ks_mma.cu", "pbs.cu", "pbs_wide.cu", "probe.cu"]
+_HEADERS = ["common.cuh", "kernels.h", "fft.cuh", "lwe_device.cuh", "ks_mma_layout.cuh", "pbs_wide.cuh", "../../include/fhe_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -181,7 +181,6 @@ SIGNATURES = {
     "fhe_b200_pbs_mb2": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "fhe_b200_ksk_to_32": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, _vp]),
     "fhe_b200_keyswitch32": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp]),
-    "fhe_b200_pbs_mb2_split": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, C.c_int32, _vp, _vp]),
     "fhe_b200_pbs_mb2_wide": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "fhe_b200_ksk_mma_bytes": (C.c_uint64, [C.POINTER(PBSParams)]),
     "fhe_b200_keyswitch_mma_workspace_bytes": (C.c_uint64, [C.POINTER(PBSParams), C.c_int64]),

@@ -555,22 +555,6 @@ int fhe_b200_keyswitch32(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const 
 
 // ---- two-warps-per-polynomial multi-bit blind rotation (pbs_split.cu): what fhe_b200_pbs_mb2 runs for small batches,
 // exposed with an explicit ciphertexts-per-CTA choice for tests and the batch sweep of the benchmark
-int fhe_b200_pbs_mb2_split(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_bskf2, const uint64_t* d_in,
-                           int64_t B, const uint64_t* d_luts, const int32_t* d_lut_index, int32_t cts_per_cta, uint64_t* d_out,
-                           void* stream) {
-    REQUIRE(ctx, "null ctx");
-    REQUIRE(B >= 0, "negative batch");
-    if (B == 0) return FHE_B200_OK;
-    REQUIRE(d_bskf2 && d_in && d_luts && d_out, "null device pointer");
-    if (int r = check_pbs_params(p, __func__)) return r;
-    REQUIRE(p->l_pbs == 1 && p->k == 1 && (p->n & 1) == 0, "the split kernel covers k = 1, l_pbs = 1, even n");
-    REQUIRE(cts_per_cta == 0 || cts_per_cta == 1 || cts_per_cta == 2 || cts_per_cta == 4, "cts_per_cta must be 0, 1, 2 or 4");
-    CU(cudaSetDevice(ctx->device));
-    CU(fhe::launch_pbs_mb2_split(*p, d_bskf2, d_in, B, d_luts, d_lut_index, d_out, ctx->prop.multiProcessorCount, cts_per_cta,
-                                 (cudaStream_t)stream));
-    return FHE_B200_OK;
-}
-
 int fhe_b200_pbs_mb2_wide(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_bskf2, const uint64_t* d_in,
                           int64_t B, const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, void* stream) {
     REQUIRE(ctx, "null ctx");

@@ -115,12 +115,6 @@ cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, 
 bool pbs_params_supported(const fhe_b200_pbs_params& p, const char** why);
 cudaError_t pbs_tables(const void** tables);
 
-// pbs_split.cu -- two-warps-per-polynomial multi-bit blind rotation: the small-batch kernel (launch_pbs_mb2 dispatches
-// it for B <= 2 x SMs).  cts_per_cta: 1, 2, 4, or 0 = best measured form for the batch.
-cudaError_t launch_pbs_mb2_split(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
-                                 const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, int sm_count,
-                                 int cts_per_cta, cudaStream_t s);
-
 // pbs_wide.cu -- four-warps-per-polynomial multi-bit blind rotation, one ciphertext per CTA (256 threads, accumulator
 // and twiddles in registers): the latency kernel, dispatched by launch_pbs_mb2 up to one ciphertext per SM.
 cudaError_t launch_pbs_mb2_wide(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,

@@ -1032,12 +1032,26 @@ cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, 
     if (e != cudaSuccess) return e;
     const cplx* bskf2 = reinterpret_cast<const cplx*>(d_bskf2);
     if (p.l_pbs == 2) return launch_pbs_mb2_t<2, 2>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
-    // up to two ciphertexts per SM the two-warps-per-polynomial kernel (pbs_split.cu: four warps per ciphertext, one
-    // ciphertext per CTA) is 1.3-1.7x faster -- a lone ciphertext's step is latency-bound, so more warps per
-    // ciphertext win; from four ciphertexts per SM on, two fat warps per ciphertext are ahead (107 k vs 102 k PBS/s)
-    if (B <= 2 * (int64_t)sm_count && p.beta_pbs <= 31)
-        return launch_pbs_mb2_split(p, d_bskf2, d_in, B, d_luts, d_lut_index, d_out, sm_count, 1, s);
-    return launch_pbs_mb2_t<1, MB2_L1_NCT>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
+    // Two kernels share a batch (measured on B200, profiles/r2_pbs_wide_times.txt):
+    //   pbs_kernel_mb2<1,4>  four ciphertexts per CTA, two fat warps each: a full wave of 4 x SMs ciphertexts takes 5.47 ms
+    //                        (108 k PBS/s) -- the throughput kernel;
+    //   pbs_kernel_mb2_wide  one ciphertext per CTA, eight warps (pbs_wide.cu): a wave of SMs ciphertexts takes 1.78 ms
+    //                        (83 k PBS/s, batch 1 in 1.78 ms) -- the latency kernel.
+    // Full waves of 4 x SMs go to the first; what is left goes to the second while it needs at most three of its waves
+    // (3 x 1.78 < 5.47), so no batch size pays for a mostly empty wave of four-ciphertext CTAs.
+    const int64_t wave4 = (int64_t)MB2_L1_NCT * sm_count;
+    int64_t full = (B / wave4) * wave4;
+    int64_t rest = B - full;
+    const bool wide_ok = p.beta_pbs <= 31 && !getenv("FHE_B200_PBS_NO_WIDE");
+    if (!wide_ok || rest > 3 * (int64_t)sm_count) { full = B; rest = 0; }
+    if (full > 0) {
+        e = launch_pbs_mb2_t<1, MB2_L1_NCT>(p, bskf2, d_in, full, d_luts, d_lut_index, tw, d_out, s);
+        if (e != cudaSuccess) return e;
+    }
+    if (rest > 0)
+        return launch_pbs_mb2_wide(p, d_bskf2, d_in + (size_t)full * (p.n + 1), rest, d_luts,
+                                   d_lut_index ? d_lut_index + full : nullptr, d_out + (size_t)full * ((size_t)p.k * p.N + 1), s);
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------- packed encrypted inner products
@@ -1270,7 +1284,7 @@ cudaError_t launch_pbs(const fhe_b200_pbs_params& p, const double* d_bskf, const
     }
 }
 
-// the per-device twiddle + omega table, for kernels in other translation units (pbs_split.cu)
+// the per-device twiddle + omega table, for kernels in other translation units (pbs_wide.cu)
 cudaError_t pbs_tables(const void** tables) {
     const cplx* tw = nullptr;
     cudaError_t e = get_tables(&tw);

@@ -1,7 +1,7 @@
 // pbs_wide.cu -- multi-bit blind rotation with FOUR WARPS PER POLYNOMIAL: one ciphertext per CTA, 256 threads, 8 complex
 // points per thread (pbs_wide.cuh).  The latency kernel: launch_pbs_mb2 dispatches it while there is at most one
-// ciphertext per SM (the step of a lone ciphertext is a dependent chain; eight warps walk it ~2x faster than the four of
-// pbs_kernel_mb2_split and ~3x faster than the two of pbs_kernel_mb2).
+// ciphertext per SM (the step of a lone ciphertext is a dependent chain; eight warps walk it 2.4x faster than the two of
+// pbs_kernel_mb2 -- and 1.65x faster than the four warps of the round-2 "split" kernel this one replaced).
 //
 // Thread tid: polynomial t = tid >> 7, u = tid & 127.  It owns the accumulator coefficients j = u + 128a and j + 1024
 // (a = 0..7) of polynomial t IN REGISTERS (16 torus words) and, in the Fourier domain, the bins k = u + 128 kL of
@@ -24,6 +24,8 @@
 //
 // Memory safety: compute-sanitizer is closed on this pool; the plan above is emulated on the CPU and the
 // kernel is covered by the acceptance of the other blind-rotation kernels on ragged batches.
+#include <cstdio>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "pbs_wide.cuh"
@@ -42,7 +44,7 @@ constexpr int PW_OMEGA = 128;
 #endif
 constexpr int PW_SLOTS = WIDE_SLOTS;
 constexpr int PW_THREADS = 2 * wfft::WT;
-constexpr int PW_WARPS = PW_THREADS / 32;
+constexpr unsigned PW_WARPS = PW_THREADS / 32;
 
 struct PwSmem {
     static constexpr size_t xbuf_bytes = (size_t)wfft::XBUF_ELEMS * 16;                 // 17,408
@@ -125,6 +127,12 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
     const cplx* oa = xbufs + (size_t)(2 * (1 - t)) * wfft::XBUF_ELEMS;  // the other polynomial's
     const cplx* ob = oa + wfft::XBUF_ELEMS;
 
+#ifdef WIDE_TIMING      // debug builds: clocks per phase of a step, printed by one warp of each polynomial of CTA 0
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define WIDE_TICK(k) { const unsigned long long now = clock64(); tacc[k] += now - tprev; tprev = now; }
+#else
+#define WIDE_TICK(k)
+#endif
     double re[8], im[8];
     for (int i = 0; i < pairs; ++i) {
         // exchange buffers of this step in write order: w0 r0 w1 r1 w2(spectrum) ...; five per step, so the roles swap
@@ -133,13 +141,15 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
         const cplx* o0 = (i & 1) ? ob : oa;
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
-            re[a] = nfft::split_digit((uint32_t)(acc_re[a] >> 32), beta);
-            im[a] = nfft::split_digit((uint32_t)(acc_im[a] >> 32), beta);
+            re[a] = wfft::top_digit((uint32_t)(acc_re[a] >> 32), beta);
+            im[a] = wfft::top_digit((uint32_t)(acc_im[a] >> 32), beta);
         }
         wfft::fwd_stage1(re, im, tw, u, e0);
         pw_bar_poly(t);
+        WIDE_TICK(0)
         wfft::fwd_stage2(tw, u, e0, e1);
         pw_bar_poly(t);
+        WIDE_TICK(1)
         wfft::fwd_stage3(u, e1, re, im);
 #pragma unroll
         for (int kL = 0; kL < 8; ++kL) {          // publish the spectrum: the other polynomial's pointwise stage reads it
@@ -148,9 +158,10 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
             v.y = im[kL];
             e0[kL * wfft::WT + u] = v;
         }
-        nfft::SplitMonomials mo;
+        wfft::Monomials mo;
         wfft::monomials_init(mo, omega, a_tilde[2 * i], a_tilde[2 * i + 1], u);
         __syncthreads();
+        WIDE_TICK(2)
         // ---- pointwise stage
         double gre[8], gim[8];
         uint32_t ready = mbar_try_wait(&bar_full[(i * wfft::SLICES_PER_STEP) % PW_SLOTS],
@@ -168,16 +179,17 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
             if (q + 1 < wfft::SLICES_PER_STEP)      // the next turn's wait, issued now: its latency hides under this turn
                 ready = mbar_try_wait(&bar_full[(sidx + 1) % PW_SLOTS], (uint32_t)(((sidx + 1) / PW_SLOTS) & 1));
 #endif
-            const cplx* blk0 = ring + (size_t)slot * wfft::SLICE_ELEMS + (size_t)wp * nfft::MB2_BLOCK_ELEMS;
-            const cplx* blk1 = blk0 + 4 * nfft::MB2_BLOCK_ELEMS;
-            nfft::split_pointwise_bin(t, lane, fa0, fo0, blk0, mo, gre[2 * q], gim[2 * q]);
-            nfft::split_pointwise_bin(t, lane, fa1, fo1, blk1, mo, gre[2 * q + 1], gim[2 * q + 1]);
+            const cplx* blk0 = ring + (size_t)slot * wfft::SLICE_ELEMS + (size_t)wp * wfft::MB2_BLOCK_ELEMS;
+            const cplx* blk1 = blk0 + 4 * wfft::MB2_BLOCK_ELEMS;
+            wfft::pointwise_bin(t, lane, fa0, fo0, blk0, mo, gre[2 * q], gim[2 * q]);
+            wfft::pointwise_bin(t, lane, fa1, fo1, blk1, mo, gre[2 * q + 1], gim[2 * q + 1]);
 #ifndef WIDE_NOSTREAM
             __syncwarp();
-            if (lane == 0) {       // the last warp to leave the slot refills it (its own reads are done: their values are used above)
-                __threadfence_block();
+            if (lane == 0) {
+                // The last warp to leave the slot refills it.  No fence: a warp issues in order and every load from the
+                // slot has returned before the FMAs above could issue, so when this atomic issues the warp's reads of
+                // the slot are complete (a __threadfence_block here is a MEMBAR.SC per turn: ~6 % of the step).
                 if (atomicAdd(&left[slot], 1u) == PW_WARPS - 1) {
-                    __threadfence_block();
                     left[slot] = 0;
                     const int next = sidx + PW_SLOTS;
                     if (next < total_slices) load_slice(slot, next);
@@ -185,17 +197,26 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
             }
 #endif
         }
+        WIDE_TICK(3)
         wfft::inv_stage3(u, gre, gim, e1);
-        __syncthreads();                               // also: nobody reads the published spectra any more
+        __syncthreads();
+        WIDE_TICK(4)                               // also: nobody reads the published spectra any more
         wfft::inv_stage2(tw, u, e1, e0);
         pw_bar_poly(t);
+        WIDE_TICK(5)
         wfft::inv_stage1(tw, u, e0, re, im);
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
-            acc_re[a] += nfft::split_f64_to_torus(re[a]);
-            acc_im[a] += nfft::split_f64_to_torus(im[a]);
+            acc_re[a] += wfft::f64_to_torus_u64(re[a]);
+            acc_im[a] += wfft::f64_to_torus_u64(im[a]);
         }
+        WIDE_TICK(6)
     }
+#ifdef WIDE_TIMING
+    if (blockIdx.x == 0 && (tid & 31) == 0 && (tid >> 5) % 4 == 0)
+        printf("warp %d clocks per step: stage1+bar %llu | stage2+bar %llu | stage3+publish+bar %llu | pointwise %llu | inv3+bar %llu | inv2+bar %llu | inv1+acc+digits %llu\n",
+               tid >> 5, tacc[0] / pairs, tacc[1] / pairs, tacc[2] / pairs, tacc[3] / pairs, tacc[4] / pairs, tacc[5] / pairs, tacc[6] / pairs);
+#endif
     // ---- sample extract coefficient 0: o[0] = A_0[0], o[N - x] = -A_0[x] (x >= 1), o[N] = A_1[0]
     uint64_t* o = out + (size_t)b * ((size_t)PW_N + 1);
 #pragma unroll

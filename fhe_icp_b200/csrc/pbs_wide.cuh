@@ -20,7 +20,7 @@
 // Everything is __host__ __device__: tests/emul/pbs_wide_emul.cpp runs the transforms and a whole blind rotation on the
 // CPU, phase by phase in several thread orders (a missing barrier would make the result order dependent).
 #pragma once
-#include "pbs_split.cuh"
+#include "fft.cuh"
 
 namespace fhe {
 namespace wfft {
@@ -34,6 +34,53 @@ using nfft::d_W32_RE;
 #endif
 
 constexpr int WT = 128;                    // threads per polynomial
+constexpr int MB2_BLOCK_ELEMS = 3 * 2 * 1 * 2 * 32;   // complex elements per frequency block (l_pbs = 1)
+
+// x mod 2^64, rounded to the nearest integer (pbs.cu's f64_to_torus)
+FHE_HD uint64_t f64_to_torus_u64(double x) {
+    const double r = rint(x * 0x1p-64);
+    const double y = fma(-r, 0x1p64, x);
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double2ll_rn(y);
+#else
+    return (uint64_t)(int64_t)llrint(y);
+#endif
+}
+
+// balanced beta-bit digit of the top of a torus word, from its HIGH 32 bits (pbs_kernel_mb2, L = 1)
+FHE_HD double top_digit(uint32_t hi, int beta) {
+    const uint32_t rnd32 = 1u << (31 - beta);
+    return (double)((int32_t)(hi + rnd32) >> (32 - beta));
+}
+
+// monomial factors c_g = rho_k^(e_g) - 1 of a bin and the factor r_g that takes them to the thread's next bin:
+// rho_(k+128)^e = rho_k^e * omega^(512 e), so c' = c*r + (r - 1).
+struct Monomials {
+    double cx[3], cy[3], rx[3], ry[3], qx[3];
+};
+
+// one bin of the pointwise stage: G = F_t * sum_g c_g K_g[t][t] + F_t' * sum_g c_g K_g[t'][t] with the key block `blk`
+// of this bin's frequency block (layout of bsk2_to_fourier_kernel: blk[((g*2 + t')*2 + c)*32 + lane], g = 0..2 for
+// s_a s_b, s_a(1-s_b), (1-s_a)s_b, t' = decomposed polynomial, c = output column); advances the monomial factors.
+FHE_HD void pointwise_bin(int t, int lane, const cplx fa, const cplx fo, const cplx* blk, Monomials& mo, double& out_re,
+                          double& out_im) {
+    double kox = 0, koy = 0, ktx = 0, kty = 0;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        const cplx bt = blk[((g * 2 + t) * 2 + t) * 32 + lane];
+        const cplx bo = blk[((g * 2 + (1 - t)) * 2 + t) * 32 + lane];
+        kox = fma(mo.cx[g], bt.x, fma(-mo.cy[g], bt.y, kox));
+        koy = fma(mo.cx[g], bt.y, fma(mo.cy[g], bt.x, koy));
+        ktx = fma(mo.cx[g], bo.x, fma(-mo.cy[g], bo.y, ktx));
+        kty = fma(mo.cx[g], bo.y, fma(mo.cy[g], bo.x, kty));
+        const double nx = fma(mo.cx[g], mo.rx[g], fma(-mo.cy[g], mo.ry[g], mo.qx[g]));
+        mo.cy[g] = fma(mo.cx[g], mo.ry[g], fma(mo.cy[g], mo.rx[g], mo.ry[g]));
+        mo.cx[g] = nx;
+    }
+    out_re = fma(fa.x, kox, fma(-fa.y, koy, fma(fo.x, ktx, -(fo.y * kty))));
+    out_im = fma(fa.x, koy, fma(fa.y, kox, fma(fo.x, kty, fo.y * ktx)));
+}
+
 constexpr int PITCH = 17;                  // row pitch of the exchange-2 layout (16 elements + 1: conflict-free columns)
 constexpr int XBUF_ELEMS = 64 * PITCH;     // one exchange buffer: 1088 elements = 17,408 B (the natural layout uses 1024)
 constexpr double RSQRT2 = 0x1.6a09e667f3bcdp-1;
@@ -213,16 +260,16 @@ FHE_HD void inv_stage1(const Twiddles& tw, int u, const cplx* x1, double (&re)[8
 }
 
 // ---- pointwise stage of thread v of output polynomial t: bins k = v + 128 kL.  The key of bin k sits in frequency
-// block k >> 5 = (v >> 5) + 4 kL at lane v & 31 (layout of bsk2_to_fourier_kernel, see pbs_split.cuh); ring slice q
+// block k >> 5 = (v >> 5) + 4 kL at lane v & 31 (layout of bsk2_to_fourier_kernel); ring slice q
 // holds the eight consecutive blocks 8q .. 8q + 7, i.e. the bins kL = 2q and 2q + 1 of every thread.
 constexpr int SLICE_BLOCKS = 8;                                      // two bins per thread (kL = 2q, 2q + 1)
-constexpr int SLICE_ELEMS = SLICE_BLOCKS * nfft::MB2_BLOCK_ELEMS;    // 3072 complex = 48 KB
+constexpr int SLICE_ELEMS = SLICE_BLOCKS * MB2_BLOCK_ELEMS;    // 3072 complex = 48 KB
 constexpr int SLICES_PER_STEP = 4;
 
 // monomial factors c_g = rho_k^(e_g) - 1 at k = v (kL = 0) and the step r_g = omega^(512 e_g) = exp(2*pi*i*e_g/8)
 // from one slice to the next: rho_k^e = omega^((4k+1)e).  omega: pbs.cu's two-level table ([0,64) omega^x, [64,128)
 // omega^(64y)).
-FHE_HD void monomials_init(nfft::SplitMonomials& mo, const cplx* omega, int ea, int eb, int v) {
+FHE_HD void monomials_init(Monomials& mo, const cplx* omega, int ea, int eb, int v) {
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
         const int e = g == 0 ? ((ea + eb) & 4095) : (g == 1 ? ea : eb);

@@ -382,27 +382,6 @@ def pbs_mb2(p: N.PBSParams, bskf2: torch.Tensor, ct: torch.Tensor, luts: torch.T
     return out
 
 
-# ---- two warps per polynomial (csrc/pbs_split.cu): the small-batch kernel pbs_mb2 dispatches for B <= 2 x SMs
-def pbs_mb2_split(p: N.PBSParams, bskf2: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor,
-                  lut_index: torch.Tensor | None = None, out: torch.Tensor | None = None, cts_per_cta: int = 0) -> torch.Tensor:
-    """:func:`pbs_mb2` through the two-warps-per-polynomial kernel with an explicit number of ciphertexts per CTA
-    (1, 2, 4; 0 = the dispatcher's choice).  Same key layout as :func:`pbs_mb2`."""
-    dev = ct.device
-    ct = ct.contiguous()
-    B = ct.shape[0]
-    assert ct.shape[1] == p.n + 1
-    luts = luts.to(device=dev, dtype=torch.int64).reshape(-1, p.N).contiguous()
-    if out is None:
-        out = torch.empty((B, p.k * p.N + 1), dtype=torch.int64, device=dev)
-    li = None
-    if lut_index is not None:
-        lut_index = lut_index.to(device=dev, dtype=torch.int32).contiguous()
-        li = _ptr(lut_index)
-    N.check(N.lib().fhe_b200_pbs_mb2_split(_ctx(dev).handle, C.byref(p), _ptr(bskf2), _ptr(ct), B, _ptr(luts), li,
-                                           int(cts_per_cta), _ptr(out), _stream(dev)))
-    return out
-
-
 def pbs_mb2_wide(p: N.PBSParams, bskf2: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor,
                  lut_index: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """:func:`pbs_mb2` through the four-warps-per-polynomial latency kernel (one ciphertext per CTA, pbs_wide.cu)

@@ -86,9 +86,7 @@ def measure(dev, args, batches=None):
         ok2 = bool(np.array_equal(E.lwe_decrypt(S, _pad(out2), 59).cpu().numpy() & 15, table[msgs]))
         fastest = min(ms, mb2_ms)
         row = {"batch": int(B), "pbs_ms": fastest, "pbs_per_sec": B / (fastest * 1e-3),
-               "kernel": (("pbs_kernel_mb2_split<1> (two key bits per step, four warps per ciphertext)" if B <= 2 * sm
-                           else "pbs_kernel_mb2<1,4> (two key bits per step)") if mb2_ms < ms
-                          else "pbs_kernel_tmem (one key bit per step)"),
+               "kernel": (_mb2_kernels(B, sm) if mb2_ms < ms else "pbs_kernel_tmem (one key bit per step)"),
                "single_bit_ms": ms, "single_bit_per_sec": B / (ms * 1e-3),
                "multi_bit_ms": mb2_ms, "multi_bit_per_sec": B / (mb2_ms * 1e-3),
                "ks_ms": ks_ms, "ks32_int_pipe_ms": ks32_ms, "ks64_ms": ks64_ms,
@@ -121,7 +119,7 @@ def measure(dev, args, batches=None):
                      "flops_per_pbs": flops, "bsk_fourier_bytes": int(bsk_bytes),
                      "fp64_pipe_active_ncu": 0.502, "smem_wavefronts_of_peak_ncu": 0.519, "issue_active_ncu": 0.354,
                      "ncu_source": "profiles/r2_ncu_pbs_mb2_v10.txt (the shipped pbs_kernel_mb2<1,4>, batch 1184); small-batch "
-                                   "kernel pbs_kernel_mb2_split: profiles/r2_ncu_pbs_split_v1.txt",
+                                   "kernel pbs_kernel_mb2_wide: profiles/r2_ncu_pbs_wide_v2.txt",
                      "hbm_term": {"bytes_per_batch": int(bsk_bytes + best["batch"] * (p.n + 1 + p.k * p.N + 1 + p.N) * 8),
                                   "note": "the Fourier key is read from HBM once per launch and then served from L2 "
                                           "(ncu: 52 MB DRAM reads per launch); key streaming never binds once batched"},
@@ -130,11 +128,26 @@ def measure(dev, args, batches=None):
                              "flops = 5*M*log2(M) per FFT + 8 per complex MAC; the kernel's instruction mix "
                              "(DADD/DMUL/DFMA ~ 45/25/30 %) caps it at ~65 % of the FMA peak even with a saturated "
                              "pipe.  Small batches are neither HBM nor FP64 bound: one ciphertext's blind rotation is a "
-                             "serial chain of 371 (multi-bit) / 742 CMuxes on one SM (batch 1: ~4.5 ms), and the key "
+                             "serial chain of 371 (multi-bit) / 742 CMuxes on one SM (batch 1: ~1.8 ms with eight warps on it), and the key "
                              "(49-73 MB) sits in the 126 MB L2 after its first read, so key streaming from HBM never binds "
                              "(by_batch[].roofline_terms gives both terms per batch)."},
     }
     return res
+
+
+def _mb2_kernels(B: int, sm: int) -> str:
+    """Which kernels fhe_b200_pbs_mb2 launches for a batch (the dispatch of csrc/pbs.cu::launch_pbs_mb2): full waves of
+    4 x SMs ciphertexts on pbs_kernel_mb2<1,4>, a remainder of up to 3 x SMs on the latency kernel pbs_kernel_mb2_wide."""
+    full = B // (4 * sm) * (4 * sm)
+    rest = B - full
+    if rest > 3 * sm:
+        full, rest = B, 0
+    parts = []
+    if full:
+        parts.append(f"pbs_kernel_mb2<1,4> x {full} (two key bits per step, four ciphertexts per CTA)")
+    if rest:
+        parts.append(f"pbs_kernel_mb2_wide x {rest} (two key bits per step, one ciphertext per CTA, eight warps)")
+    return " + ".join(parts)
 
 
 def _keyswitch_summary(rows, p, bf16_peak_tflops):

@@ -235,17 +235,9 @@ int fhe_b200_bsk2_to_fourier(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, co
 int fhe_b200_pbs_mb2(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
                      const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
                      const int32_t *d_lut_index, uint64_t *d_out, void *stream);
-/* The same multi-bit blind rotation with two warps per polynomial (16 points per lane, 128 registers; pbs_split.cu):
- * four warps per ciphertext make it the small-batch kernel -- fhe_b200_pbs_mb2 itself runs it for B <= 2 x SMs (batch 1:
- * 2.6 ms instead of 4.2 ms; batch 148: 52 k instead of 31 k PBS/s).  This entry point exposes the choice of
- * ciphertexts per CTA (1, 2 or 4; 0 = the dispatcher's choice) for the tests and the benchmark's batch sweep.  Same key
- * (fhe_b200_bsk2_to_fourier), inputs and outputs as fhe_b200_pbs_mb2; k = 1, l_pbs = 1, n even. */
-int fhe_b200_pbs_mb2_split(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
-                           const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
-                           const int32_t *d_lut_index, int32_t cts_per_cta, uint64_t *d_out, void *stream);
 /* The same multi-bit blind rotation with FOUR warps per polynomial (8 points per thread, accumulator and twiddles in
  * registers; pbs_wide.cu): one ciphertext per CTA of 256 threads -- the latency kernel.  fhe_b200_pbs_mb2 itself runs
- * it while there is at most one ciphertext per SM; this entry point forces it for the tests and the batch sweep.
+ * it for what is left of a batch after full waves of 4 x SMs ciphertexts (up to 3 x SMs); this entry point forces it for the tests and the batch sweep.
  * Same key, inputs and outputs as fhe_b200_pbs_mb2; k = 1, l_pbs = 1, n even. */
 int fhe_b200_pbs_mb2_wide(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
                           const uint64_t *d_in, int64_t B, const uint64_t *d_luts,

@@ -16,7 +16,7 @@ struct Thread {
     Twiddles tw;
     uint64_t acc_re[8], acc_im[8];
     double re[8], im[8], gre[8], gim[8];
-    SplitMonomials mo;
+    Monomials mo;
 };
 int thread_at(int order, int i) { return order == 1 ? 127 - i : (order == 2 ? (i * 37 + 5) & 127 : i); }
 }  // namespace
@@ -98,12 +98,12 @@ extern "C" int emul_pbs_mb2_wide(const double* key_blocks /* [pairs][32][3][2][1
             FOR_THREADS(t)
                 if (i > 0) {    // e0 of step i-1 == e1 of step i
                     inv_stage1(T.tw, u, e1, T.re, T.im);
-                    for (int a = 0; a < 8; ++a) { T.acc_re[a] += split_f64_to_torus(T.re[a]); T.acc_im[a] += split_f64_to_torus(T.im[a]); }
+                    for (int a = 0; a < 8; ++a) { T.acc_re[a] += f64_to_torus_u64(T.re[a]); T.acc_im[a] += f64_to_torus_u64(T.im[a]); }
                 }
                 if (i < pairs) {
                     for (int a = 0; a < 8; ++a) {
-                        T.re[a] = split_digit((uint32_t)(T.acc_re[a] >> 32), beta);
-                        T.im[a] = split_digit((uint32_t)(T.acc_im[a] >> 32), beta);
+                        T.re[a] = top_digit((uint32_t)(T.acc_re[a] >> 32), beta);
+                        T.im[a] = top_digit((uint32_t)(T.acc_im[a] >> 32), beta);
                     }
                     fwd_stage1(T.re, T.im, T.tw, u, e0);
                 }
@@ -128,7 +128,7 @@ extern "C" int emul_pbs_mb2_wide(const double* key_blocks /* [pairs][32][3][2][1
                     const cplx fo = o0[kL * WT + u];
                     cplx fa; fa.x = T.re[kL]; fa.y = T.im[kL];
                     const cplx* blk = key_pair + (size_t)(4 * kL + (u >> 5)) * MB2_BLOCK_ELEMS;   // slice kL, block of this warp
-                    split_pointwise_bin(t, u & 31, fa, fo, blk, T.mo, T.gre[kL], T.gim[kL]);
+                    pointwise_bin(t, u & 31, fa, fo, blk, T.mo, T.gre[kL], T.gim[kL]);
                 }
                 inv_stage3(u, T.gre, T.gim, e1);
             END_THREADS

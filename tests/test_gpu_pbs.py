@@ -224,11 +224,13 @@ class KeysMB2:
 P4_L2 = dict(P4, l_pbs=2, beta_pbs=15)
 
 
-@pytest.mark.parametrize("which,B", [("toy", 16), ("toy", 3), ("p4", 16), ("p4", 2 * 148 + 5),
-                                     ("toy_l2", 16), ("toy_l2", 5), ("p4_l2", 16), ("p4_l2", 2 * 148 + 3)])
+@pytest.mark.parametrize("which,B", [("toy", 16), ("toy", 3), ("p4", 16), ("p4", 2 * 148 + 5), ("p4", 4 * 148 + 21),
+                                     ("p4", 7 * 148 + 1), ("toy_l2", 16), ("toy_l2", 5), ("p4_l2", 16), ("p4_l2", 2 * 148 + 3)])
 def test_multibit_pbs(O, cuda_dev, which, B):
     """Multi-bit blind rotation (two key bits per CMux): key bit-exact vs the oracle, every message
-    maps to LUT[m], phases agree with the oracle's multi-bit evaluation within the PBS noise bound."""
+    maps to LUT[m], phases agree with the oracle's multi-bit evaluation within the PBS noise bound.  The batch sizes
+    cover the dispatcher (csrc/pbs.cu::launch_pbs_mb2): latency kernel only, a full wave of four-ciphertext CTAs plus a
+    remainder on the latency kernel, and a remainder too large for it (everything on the throughput kernel)."""
     import torch
     from fhe_icp_b200 import engine as E
     d = {"toy": TOY, "p4": P4, "toy_l2": TOY_L2, "p4_l2": P4_L2}[which]
@@ -296,36 +298,6 @@ def test_keyswitch_tensor_core_other_gadgets(O, cuda_dev):
         out = E.keyswitch_mma(K.p, E.ksk_to_mma(K.p, ksk32), rnd)
         assert np.array_equal(_u64(out), _u64(E.keyswitch32(K.p, ksk32, rnd)))
         assert np.array_equal(_u64(out), O.keyswitch32(K.op, O.ksk_to_32(K.op, _u64(K.ksk)), _u64(rnd)))
-
-
-@pytest.mark.parametrize("which,B,nct", [("toy", 16, 4), ("toy", 3, 1), ("toy", 5, 2), ("p4", 16, 1), ("p4", 2 * 148 + 5, 4),
-                                         ("p4", 149, 2), ("p4", 7, 0)])
-def test_multibit_pbs_split_kernel(O, cuda_dev, which, B, nct):
-    """Same acceptance as test_multibit_pbs for the two-warps-per-polynomial kernel (pbs_split.cu), at every
-    ciphertexts-per-CTA form and with ragged last CTAs: every message maps to LUT[m], phases agree with the oracle-checked
-    pbs_kernel_mb2 within the noise bound.  nct = 0 is the dispatcher's choice; pbs_mb2 itself runs this kernel for
-    B <= 2 x SMs (covered by test_multibit_pbs' small batches)."""
-    import torch
-    from fhe_icp_b200 import engine as E
-    d = {"toy": TOY, "p4": P4}[which]
-    K = KeysMB2(O, cuda_dev, d)
-    rng = np.random.RandomState(B)
-    msgs = rng.randint(0, 16, size=B)
-    msgs[: min(B, 16)] = np.arange(16)[: min(B, 16)]
-    ct = E.lwe_encrypt(K.s, torch.as_tensor(msgs), 59, K.op.sigma_lwe_abs, enc_seed=B, ct_base=100,
-                       stride=K.p.n + 2 - (K.p.n % 2))[:, : K.p.n + 1].contiguous()
-    table = (np.arange(16) * 5 + 2) % 16
-    lut = E.make_lut_poly(table, 4, K.p.N, 59)
-    lut_d = E.from_u64_numpy(lut, cuda_dev)
-    got = _u64(E.pbs_mb2_split(K.p, K.bskf2, ct, lut_d, cts_per_cta=nct))
-    assert np.array_equal(O.lwe_decrypt(K.oS, got, 59) & 15, table[msgs])
-    of = O.bsk2_to_fourier(K.op, O.bsk2_gen(K.op, K.os, K.oS, K.evk_seed))
-    ref = O.pbs_mb2(K.op, of, _u64(ct)[: min(B, 32)], lut)
-    diff = (O.lwe_phase(K.oS, got[: min(B, 32)]) - O.lwe_phase(K.oS, ref)).view(np.int64).astype(np.float64)
-    assert np.log2(np.abs(diff).max() + 1) - 64 < -12
-    err = (O.lwe_phase(K.oS, got) - (table[msgs].astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
-    assert np.log2(err.std() + 1) - 64 < -13.5
-    assert E.pbs_mb2_split(K.p, K.bskf2, ct[:0], lut_d, cts_per_cta=nct).shape == (0, K.p.N + 1)
 
 
 @pytest.mark.parametrize("which,B", [("toy", 16), ("toy", 3), ("p4", 16), ("p4", 1), ("p4", 148 + 9)])

@@ -1,5 +1,7 @@
 """PBS latency / throughput by batch size for the three multi-bit blind-rotation kernels (one key set-up, many batches).
-usage: pbs_batch_sweep.py [batches...]   prints ms per launch (best of 3) and correctness for mb2<1,4>, split<1>, wide."""
+usage: pbs_batch_sweep.py [batches...]   prints ms per launch (best of 4) and correctness for the latency kernel (wide), the throughput kernel (mb2<1,4>)
+and the dispatcher (FHE_B200_PBS_NO_WIDE=1 in the environment makes the dispatcher use mb2<1,4> only)."""
+import os
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -16,11 +18,17 @@ ksk = E.ksk_gen(p, S, s, 202)
 bskf2 = E.bsk2_to_fourier(p, E.bsk2_gen(p, s, S, 202))
 table = (np.arange(16) * 7 + 3) % 16
 lut = E.from_u64_numpy(E.make_lut_poly(table, 4, p.N, 59), dev)
+def _no_wide(fn):
+    os.environ["FHE_B200_PBS_NO_WIDE"] = "1"      # read by the dispatcher at every call
+    try:
+        return fn()
+    finally:
+        del os.environ["FHE_B200_PBS_NO_WIDE"]
+
+
 kernels = {"wide": lambda ct, out: E.pbs_mb2_wide(p, bskf2, ct, lut, out=out),
-           "split<1>": lambda ct, out: E.pbs_mb2_split(p, bskf2, ct, lut, out=out, cts_per_cta=1),
-           "split<4>": lambda ct, out: E.pbs_mb2_split(p, bskf2, ct, lut, out=out, cts_per_cta=4),
+           "mb2<1,4>": lambda ct, out: _no_wide(lambda: E.pbs_mb2(p, bskf2, ct, lut, out=out)),
            "dispatch": lambda ct, out: E.pbs_mb2(p, bskf2, ct, lut, out=out)}
-import os
 if os.environ.get("SWEEP_ONLY"):
     kernels = {k: v for k, v in kernels.items() if k in os.environ["SWEEP_ONLY"].split(",")}
 for B in batches:

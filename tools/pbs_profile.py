@@ -26,24 +26,20 @@ ct = E.keyswitch(p, ksk, ct_big)
 out = torch.empty((B, p.N + 1), dtype=torch.int64, device=dev)
 import os
 MB2 = os.environ.get("PBS_MB2", "0") == "1"
-SPLIT = os.environ.get("PBS_SPLIT", "0") == "1"
 WIDE = os.environ.get("PBS_WIDE", "0") == "1"
-if MB2 or SPLIT or WIDE:
+if MB2 or WIDE:
     bskf2 = E.bsk2_to_fourier(p, E.bsk2_gen(p, s, S, 202))
-NCT = int(os.environ.get("PBS_SPLIT_NCT", "0"))
 for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if WIDE:
         E.pbs_mb2_wide(p, bskf2, ct, lut, out=out)
-    elif SPLIT:
-        E.pbs_mb2_split(p, bskf2, ct, lut, out=out, cts_per_cta=NCT)
     elif MB2:
         E.pbs_mb2(p, bskf2, ct, lut, out=out)
     else:
         E.pbs(p, bskf, ct, lut, out=out)
     e1.record(); torch.cuda.synchronize()
-    print(f"B={B} {'wide' if WIDE else 'split' if SPLIT else 'mb2' if MB2 else 'pbs'} {e0.elapsed_time(e1):.3f} ms -> {B / e0.elapsed_time(e1) * 1e3:.0f} PBS/s")
+    print(f"B={B} {'wide' if WIDE else 'mb2' if MB2 else 'pbs'} {e0.elapsed_time(e1):.3f} ms -> {B / e0.elapsed_time(e1) * 1e3:.0f} PBS/s")
 z = torch.zeros((B, p.N + 2), dtype=torch.int64, device=dev); z[:, : p.N + 1] = out
 dec = E.lwe_decrypt(S, z, 59).cpu().numpy() & 15
 print("correct:", bool(np.array_equal(dec, table[msgs])))
