@@ -182,6 +182,7 @@ SIGNATURES = {
     "fhe_b200_ksk_to_32": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, _vp]),
     "fhe_b200_keyswitch32": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp]),
     "fhe_b200_pbs_mb2_wide": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
+    "fhe_b200_pbs_mb2_pair": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "fhe_b200_ksk_mma_bytes": (C.c_uint64, [C.POINTER(PBSParams)]),
     "fhe_b200_keyswitch_mma_workspace_bytes": (C.c_uint64, [C.POINTER(PBSParams), C.c_int64]),
     "fhe_b200_ksk_to_mma": (C.c_int, [_vp, C.POINTER(PBSParams), _vp, _vp, _vp]),

@@ -110,6 +110,15 @@ extern "C" {
 int fhe_b200_abi_version(void) { return FHE_B200_ABI_VERSION; }
 const char* fhe_b200_last_error(void) { return g_err.c_str(); }
 
+static void keep_pool_memory(int device) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;      // scratch of cudaMallocAsync users (pbs_kernel_mb2_pair's column key) stays cached
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+}
+
 int fhe_b200_ctx_create(int device, fhe_b200_ctx** ctx) {
     if (!ctx) return fail(FHE_B200_ERR_INVALID, "ctx_create: null out pointer");
     *ctx = nullptr;
@@ -132,6 +141,7 @@ int fhe_b200_ctx_create(int device, fhe_b200_ctx** ctx) {
         return fail(FHE_B200_ERR_NO_DEVICE, "ctx_create: device is sm_%d%d; this library is built for sm_100a only", maj, min);
     }
     c->launches_at_create = g_launches.load();
+    keep_pool_memory(device);
     *ctx = c;
     return FHE_B200_OK;
 }
@@ -565,6 +575,20 @@ int fhe_b200_pbs_mb2_wide(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const
     REQUIRE(p->l_pbs == 1 && p->k == 1 && (p->n & 1) == 0, "the wide kernel covers k = 1, l_pbs = 1, even n");
     CU(cudaSetDevice(ctx->device));
     CU(fhe::launch_pbs_mb2_wide(*p, d_bskf2, d_in, B, d_luts, d_lut_index, d_out, (cudaStream_t)stream));
+    return FHE_B200_OK;
+}
+
+int fhe_b200_pbs_mb2_pair(fhe_b200_ctx* ctx, const fhe_b200_pbs_params* p, const double* d_bskf2, const uint64_t* d_in,
+                          int64_t B, const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, void* stream) {
+    REQUIRE(ctx, "null ctx");
+    REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return FHE_B200_OK;
+    REQUIRE(d_bskf2 && d_in && d_luts && d_out, "null device pointer");
+    if (int r = check_pbs_params(p, __func__)) return r;
+    REQUIRE(p->l_pbs == 1 && p->k == 1 && (p->n & 1) == 0, "the pair kernel covers k = 1, l_pbs = 1, even n");
+    REQUIRE(ctx->prop.major >= 9, "thread-block clusters need sm_90 or later");
+    CU(cudaSetDevice(ctx->device));
+    CU(fhe::launch_pbs_mb2_pair(*p, d_bskf2, d_in, B, d_luts, d_lut_index, d_out, (cudaStream_t)stream));
     return FHE_B200_OK;
 }
 

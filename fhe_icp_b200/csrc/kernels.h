@@ -120,6 +120,11 @@ cudaError_t pbs_tables(const void** tables);
 cudaError_t launch_pbs_mb2_wide(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
                                 const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, cudaStream_t s);
 
+// one ciphertext on a cluster of two CTAs (polynomial t and key column t on CTA t, spectra exchanged through distributed
+// shared memory): the lowest latency, for batches up to half the SM count
+cudaError_t launch_pbs_mb2_pair(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
+                                const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, cudaStream_t s);
+
 // probe.cu
 cudaError_t probe_fp64(int sm_count, double* tflops, cudaStream_t s);
 

@@ -1032,13 +1032,15 @@ cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, 
     if (e != cudaSuccess) return e;
     const cplx* bskf2 = reinterpret_cast<const cplx*>(d_bskf2);
     if (p.l_pbs == 2) return launch_pbs_mb2_t<2, 2>(p, bskf2, d_in, B, d_luts, d_lut_index, tw, d_out, s);
-    // Two kernels share a batch (measured on B200, profiles/r2_pbs_wide_times.txt):
+    // Three kernels share a batch (measured on B200, profiles/r2_pbs_wide_times.txt):
     //   pbs_kernel_mb2<1,4>  four ciphertexts per CTA, two fat warps each: a full wave of 4 x SMs ciphertexts takes 5.47 ms
     //                        (108 k PBS/s) -- the throughput kernel;
     //   pbs_kernel_mb2_wide  one ciphertext per CTA, eight warps (pbs_wide.cu): a wave of SMs ciphertexts takes 1.78 ms
-    //                        (83 k PBS/s, batch 1 in 1.78 ms) -- the latency kernel.
+    //                        (83 k PBS/s) -- the latency kernel;
+    //   pbs_kernel_mb2_pair  one ciphertext per cluster of two CTAs (pbs_wide.cu): SMs / 2 ciphertexts in 1.28 ms.
     // Full waves of 4 x SMs go to the first; what is left goes to the second while it needs at most three of its waves
-    // (3 x 1.78 < 5.47), so no batch size pays for a mostly empty wave of four-ciphertext CTAs.
+    // (3 x 1.78 < 5.47), so no batch size pays for a mostly empty wave of four-ciphertext CTAs -- and to the third
+    // when there are two SMs for every remaining ciphertext.
     const int64_t wave4 = (int64_t)MB2_L1_NCT * sm_count;
     int64_t full = (B / wave4) * wave4;
     int64_t rest = B - full;
@@ -1048,6 +1050,9 @@ cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, 
         e = launch_pbs_mb2_t<1, MB2_L1_NCT>(p, bskf2, d_in, full, d_luts, d_lut_index, tw, d_out, s);
         if (e != cudaSuccess) return e;
     }
+    if (rest > 0 && 2 * rest <= (int64_t)sm_count && !getenv("FHE_B200_PBS_NO_PAIR"))     // two SMs per ciphertext while they are free
+        return launch_pbs_mb2_pair(p, d_bskf2, d_in + (size_t)full * (p.n + 1), rest, d_luts,
+                                   d_lut_index ? d_lut_index + full : nullptr, d_out + (size_t)full * ((size_t)p.k * p.N + 1), s);
     if (rest > 0)
         return launch_pbs_mb2_wide(p, d_bskf2, d_in + (size_t)full * (p.n + 1), rest, d_luts,
                                    d_lut_index ? d_lut_index + full : nullptr, d_out + (size_t)full * ((size_t)p.k * p.N + 1), s);

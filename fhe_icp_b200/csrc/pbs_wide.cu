@@ -235,6 +235,279 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// pbs_kernel_mb2_pair -- ONE ciphertext on a CLUSTER OF TWO CTAs (two SMs): CTA t owns polynomial t (128 threads, the same
+// four warps and the same 8 x 8 x 16 transform as above), streams only COLUMN t of the Fourier key (half the bytes, from
+// the column layout of bsk2_column_split_kernel) and hands its spectrum to the other CTA through distributed shared
+// memory: after the forward transform it stores the 1024 bins in a send buffer and one thread issues a 16 KB bulk copy
+// shared::cta -> shared::cluster that completes on an mbarrier IN THE PEER's shared memory.  The pointwise stage first
+// forms, per bin, S_own = sum c_g K_g[t][t], S_oth = sum c_g K_g[1-t][t] and F_t * S_own -- none of which needs the peer --
+// and only then waits for the peer's spectrum to add F_(1-t) * S_oth, so the ~1 us the exchange takes hides under the
+// stage.  Send and receive buffers alternate with the step's parity: the two CTAs can never be more than one exchange
+// apart (each needs the other's spectrum every step), so a buffer is rewritten two exchanges after it was last read.
+// Shared-memory exchange buffers: A for forward stage 1 / inverse stage 3, B for forward stage 2 / inverse stage 2,
+// four CTA-wide barriers per step.  A cluster barrier after the mbarrier initialisation (nobody sends into a barrier
+// that does not exist yet) and one before exit (nobody's shared memory disappears under an in-flight copy).
+namespace {
+
+constexpr int PP_THREADS = wfft::WT;
+constexpr unsigned PP_WARPS = PP_THREADS / 32;
+constexpr int PP_SLOTS = 3;
+constexpr uint32_t PP_SPEC_BYTES = 1024 * 16;
+
+struct PpSmem {
+    static constexpr size_t ring_bytes = (size_t)PP_SLOTS * wfft::COL_SLICE_ELEMS * 16;      // 72 KB
+    static constexpr size_t x_bytes = 2 * (size_t)wfft::XBUF_ELEMS * 16;                     // A, B
+    static constexpr size_t spec_bytes = 4 * (size_t)PP_SPEC_BYTES;                          // send[2], recv[2]
+    static constexpr size_t omega_bytes = (size_t)PW_OMEGA * 16;
+    static constexpr size_t bar_bytes = 256;
+    static size_t total(int n) { return ring_bytes + x_bytes + spec_bytes + omega_bytes + bar_bytes + (((size_t)(n + 1) * 2 + 127) & ~(size_t)127); }
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_peer(const void* local_smem, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16 KB of this CTA's shared memory -> the peer's, completing (bytes) on the peer's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t peer_dst, const void* local_src, uint32_t bytes, uint32_t peer_bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(peer_dst),
+                 "r"(smem_u32(local_src)), "r"(bytes), "r"(peer_bar) : "memory");
+}
+
+// keycol[((pair*2 + c)*32 + k1)*6 + (g*2 + t')][lane] = bskf2[((pair*32 + k1)*12 + ((g*2 + t')*2 + c))][lane]
+__global__ void bsk2_column_split_kernel(const cplx* __restrict__ bskf2, int64_t rows /* pairs*32*12 */, cplx* __restrict__ keycol) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = idx >> 5;
+    const int lane = (int)(idx & 31);
+    if (row >= rows) return;
+    const int within = (int)(row % 12);          // (g*2 + t')*2 + c
+    const int64_t pk = row / 12;                 // pair*32 + k1
+    const int c = within & 1, gt = within >> 1;
+    const int64_t pair = pk >> 5;
+    const int k1 = (int)(pk & 31);
+    keycol[((((pair * 2 + c) * 32 + k1) * 6) + gt) * 32 + lane] = bskf2[row * 32 + lane];
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+pbs_kernel_mb2_pair(const cplx* __restrict__ keycol, const uint64_t* __restrict__ in, int64_t B, int n, int beta,
+                    const uint64_t* __restrict__ luts, const int32_t* __restrict__ lut_index,
+                    const cplx* __restrict__ g_tw, uint64_t* __restrict__ out) {
+    using S = PpSmem;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* ring = reinterpret_cast<cplx*>(smem_raw);
+    cplx* xa = reinterpret_cast<cplx*>(smem_raw + S::ring_bytes);
+    cplx* xb = xa + wfft::XBUF_ELEMS;
+    cplx* send = reinterpret_cast<cplx*>(smem_raw + S::ring_bytes + S::x_bytes);          // [2][1024]
+    cplx* recv = send + 2 * 1024;                                                          // [2][1024]
+    cplx* omega = reinterpret_cast<cplx*>(smem_raw + S::ring_bytes + S::x_bytes + S::spec_bytes);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + S::ring_bytes + S::x_bytes + S::spec_bytes + S::omega_bytes);
+    uint64_t* bar_recv = bar_full + PP_SLOTS;                                              // [2]
+    unsigned* left = reinterpret_cast<unsigned*>(bar_recv + 2);
+    uint16_t* a_tilde = reinterpret_cast<uint16_t*>(smem_raw + S::ring_bytes + S::x_bytes + S::spec_bytes + S::omega_bytes + S::bar_bytes);
+
+    const int u = threadIdx.x, lane = u & 31, wp = u >> 5;
+    const int t = (int)cluster_ctarank();
+    const uint32_t peer = (uint32_t)(1 - t);
+    const int64_t b = blockIdx.x >> 1;
+    for (int i = u; i < PW_OMEGA; i += PP_THREADS) omega[i] = g_tw[PW_TILE + i];
+    if (u == 0) {
+        for (int q = 0; q < PP_SLOTS; ++q) { mbar_init(&bar_full[q], 1); left[q] = 0; }
+        mbar_init(&bar_recv[0], 1);
+        mbar_init(&bar_recv[1], 1);
+        mbar_fence_init();
+    }
+    const uint64_t* ct = in + (size_t)b * (n + 1);
+    for (int i = u; i <= n; i += PP_THREADS) a_tilde[i] = (uint16_t)((((ct[i] >> 51) + 1) >> 1) & 4095);
+    __syncthreads();
+    cluster_sync_all();
+
+    const int pairs = n >> 1;
+    const int total_slices = pairs * wfft::SLICES_PER_STEP;
+    constexpr uint32_t SLICE_BYTES = (uint32_t)(wfft::COL_SLICE_ELEMS * 16);
+    auto load_slice = [&](int slot, int sidx) {   // slice sidx = 4*pair + q of column t: blocks 8q .. 8q + 7, contiguous
+        const int pair = sidx >> 2, q = sidx & 3;
+        mbar_expect_tx(&bar_full[slot], SLICE_BYTES);
+        tma_load_1d(ring + (size_t)slot * wfft::COL_SLICE_ELEMS,
+                    keycol + ((size_t)(pair * 2 + t) * 32 + 8 * q) * wfft::COL_BLOCK_ELEMS, SLICE_BYTES, &bar_full[slot]);
+    };
+    if (u == 0) {
+        for (int q = 0; q < PP_SLOTS && q < total_slices; ++q) load_slice(q, q);
+        mbar_expect_tx(&bar_recv[0], PP_SPEC_BYTES);          // the peer's spectra of steps 0 and 1
+        if (pairs > 1) mbar_expect_tx(&bar_recv[1], PP_SPEC_BYTES);
+    }
+    const uint32_t peer_recv = map_to_peer(recv, peer), peer_bar = map_to_peer(bar_recv, peer);
+
+    wfft::Twiddles tw;
+    wfft::twiddles_init(tw, u);
+    uint64_t acc_re[8], acc_im[8];
+    {
+        const uint64_t* lut = luts + (size_t)(lut_index ? lut_index[b] : 0) * PW_N;
+        const int rot = (4096 - (int)a_tilde[n]) & 4095;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int j = u + 128 * a;
+            uint64_t v0 = 0, v1 = 0;
+            if (t == 1) {
+                int src = (j - rot) & 4095;
+                v0 = lut[src & 2047];
+                if (src & 2048) v0 = 0 - v0;
+                src = (j + 1024 - rot) & 4095;
+                v1 = lut[src & 2047];
+                if (src & 2048) v1 = 0 - v1;
+            }
+            acc_re[a] = v0;
+            acc_im[a] = v1;
+        }
+    }
+
+    double re[8], im[8];
+    for (int i = 0; i < pairs; ++i) {
+        const int par = i & 1;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            re[a] = wfft::top_digit((uint32_t)(acc_re[a] >> 32), beta);
+            im[a] = wfft::top_digit((uint32_t)(acc_im[a] >> 32), beta);
+        }
+        wfft::fwd_stage1(re, im, tw, u, xa);
+        __syncthreads();
+        wfft::fwd_stage2(tw, u, xa, xb);
+        __syncthreads();
+        wfft::fwd_stage3(u, xb, re, im);
+        // ---- hand the spectrum to the peer
+        cplx* sb = send + (size_t)par * 1024;
+#pragma unroll
+        for (int kL = 0; kL < 8; ++kL) {
+            cplx v;
+            v.x = re[kL];
+            v.y = im[kL];
+            sb[kL * wfft::WT + u] = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the bulk copy
+        __syncthreads();
+        if (u == 0) dsmem_bulk_copy(peer_recv + (uint32_t)par * PP_SPEC_BYTES, sb, PP_SPEC_BYTES, peer_bar + (uint32_t)par * 8);
+        wfft::Monomials mo;
+        wfft::monomials_init(mo, omega, a_tilde[2 * i], a_tilde[2 * i + 1], u);
+        // ---- pointwise, part 1: everything that needs only this CTA's spectrum
+        double pre[8], pim[8], sre[8], sim[8];
+        const int s0 = i * wfft::SLICES_PER_STEP;
+        uint32_t ready = mbar_try_wait(&bar_full[s0 % PP_SLOTS], (uint32_t)((s0 / PP_SLOTS) & 1));
+#pragma unroll
+        for (int q = 0; q < wfft::SLICES_PER_STEP; ++q) {
+            const int sidx = s0 + q, slot = sidx % PP_SLOTS;
+            if (!ready) mbar_wait(&bar_full[slot], (uint32_t)((sidx / PP_SLOTS) & 1));
+            if (q + 1 < wfft::SLICES_PER_STEP)
+                ready = mbar_try_wait(&bar_full[(sidx + 1) % PP_SLOTS], (uint32_t)(((sidx + 1) / PP_SLOTS) & 1));
+            const cplx* blk0 = ring + (size_t)slot * wfft::COL_SLICE_ELEMS + (size_t)wp * wfft::COL_BLOCK_ELEMS;
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const int kL = 2 * q + d;
+                cplx so, st;
+                wfft::pointwise_sums(t, lane, blk0 + (size_t)d * 4 * wfft::COL_BLOCK_ELEMS, mo, so, st);
+                pre[kL] = fma(re[kL], so.x, -(im[kL] * so.y));
+                pim[kL] = fma(re[kL], so.y, im[kL] * so.x);
+                sre[kL] = st.x;
+                sim[kL] = st.y;
+            }
+            __syncwarp();
+            if (lane == 0) {       // the last warp to leave the slot refills it (see pbs_kernel_mb2_wide)
+                if (atomicAdd(&left[slot], 1u) == PP_WARPS - 1) {
+                    left[slot] = 0;
+                    const int next = sidx + PP_SLOTS;
+                    if (next < total_slices) load_slice(slot, next);
+                }
+            }
+        }
+        // ---- part 2: the peer's spectrum
+        mbar_wait(&bar_recv[par], (uint32_t)((i >> 1) & 1));
+        if (u == 0 && i + 2 < pairs) mbar_expect_tx(&bar_recv[par], PP_SPEC_BYTES);    // arm the phase of step i + 2
+        const cplx* rb = recv + (size_t)par * 1024;
+#pragma unroll
+        for (int kL = 0; kL < 8; ++kL) {
+            const cplx fo = rb[kL * wfft::WT + u];
+            re[kL] = fma(fo.x, sre[kL], fma(-fo.y, sim[kL], pre[kL]));
+            im[kL] = fma(fo.x, sim[kL], fma(fo.y, sre[kL], pim[kL]));
+        }
+        wfft::inv_stage3(u, re, im, xa);
+        __syncthreads();
+        wfft::inv_stage2(tw, u, xa, xb);
+        __syncthreads();
+        wfft::inv_stage1(tw, u, xb, re, im);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            acc_re[a] += wfft::f64_to_torus_u64(re[a]);
+            acc_im[a] += wfft::f64_to_torus_u64(im[a]);
+        }
+    }
+    uint64_t* o = out + (size_t)b * ((size_t)PW_N + 1);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const int x = u + 128 * a + 1024 * part;
+            const uint64_t v = part ? acc_im[a] : acc_re[a];
+            if (t == 0) {
+                if (x == 0) o[0] = v;
+                else o[PW_N - x] = 0 - v;
+            } else if (x == 0) {
+                o[PW_N] = v;
+            }
+        }
+    }
+    cluster_sync_all();     // the peer's last copy out of / into this CTA's shared memory has long completed; be explicit
+}
+
+cudaError_t launch_pbs_mb2_pair(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
+                                const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, cudaStream_t s) {
+    if (B <= 0) return cudaSuccess;
+    if (p.k != 1 || p.l_pbs != 1 || (p.n & 1) || p.N != PW_N || p.beta_pbs < 1 || p.beta_pbs > 31) return cudaErrorInvalidValue;
+    if (B > 0x3fffffffLL) return cudaErrorInvalidValue;
+    const void* tables = nullptr;
+    cudaError_t e = pbs_tables(&tables);
+    if (e != cudaSuccess) return e;
+    // the key by output column (73 MB at the stated set, a 20 us permutation): scratch from the stream-ordered pool
+    const int64_t rows = (int64_t)(p.n / 2) * 32 * 12;
+    cplx* keycol = nullptr;
+    e = cudaMallocAsync(reinterpret_cast<void**>(&keycol), (size_t)rows * 32 * sizeof(cplx), s);
+    if (e != cudaSuccess) return e;
+    bsk2_column_split_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const cplx*>(d_bskf2), rows, keycol);
+    count_launch();
+    const size_t smem = PpSmem::total(p.n);
+    e = cudaFuncSetAttribute(pbs_kernel_mb2_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * B));
+        cfg.blockDim = dim3(PP_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const cplx* kc = keycol;
+        const cplx* tb = reinterpret_cast<const cplx*>(tables);
+        int n = p.n, beta = p.beta_pbs;
+        e = cudaLaunchKernelEx(&cfg, pbs_kernel_mb2_pair, kc, d_in, B, n, beta, d_luts, d_lut_index, tb, d_out);
+        count_launch();
+    }
+    cudaError_t e2 = cudaFreeAsync(keycol, s);
+    return e != cudaSuccess ? e : e2;
+}
+
 cudaError_t launch_pbs_mb2_wide(const fhe_b200_pbs_params& p, const double* d_bskf2, const uint64_t* d_in, int64_t B,
                                 const uint64_t* d_luts, const int32_t* d_lut_index, uint64_t* d_out, cudaStream_t s) {
     if (B <= 0) return cudaSuccess;

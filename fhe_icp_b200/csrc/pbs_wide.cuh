@@ -284,5 +284,32 @@ FHE_HD void monomials_init(Monomials& mo, const cplx* omega, int ea, int eb, int
     }
 }
 
+// ---- the same stage for ONE output column held apart (pbs_kernel_mb2_pair: a cluster of two CTAs per ciphertext, CTA t
+// owns polynomial t and streams only column t of the key).  Column layout, written by bsk2_column_split_kernel:
+//   keycol[((pair*2 + c)*32 + k1)*6 + (g*2 + t')][32 lanes]
+// so that the bins of slice q (frequency blocks 8q .. 8q + 7) of column c are 24 KB contiguous.
+constexpr int COL_BLOCK_ELEMS = 3 * 2 * 32;                          // complex elements per (column, frequency block)
+constexpr int COL_SLICE_ELEMS = SLICE_BLOCKS * COL_BLOCK_ELEMS;      // 1536 complex = 24 KB
+
+// the two key combinations of a bin, S_own = sum_g c_g K_g[t][t] and S_oth = sum_g c_g K_g[1-t][t]; advances the
+// monomials.  The output bin is F_t * S_own + F_(1-t) * S_oth: the first product needs nothing from the other CTA.
+FHE_HD void pointwise_sums(int t, int lane, const cplx* blkc, Monomials& mo, cplx& s_own, cplx& s_oth) {
+    double kox = 0, koy = 0, ktx = 0, kty = 0;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        const cplx bt = blkc[(g * 2 + t) * 32 + lane];
+        const cplx bo = blkc[(g * 2 + (1 - t)) * 32 + lane];
+        kox = fma(mo.cx[g], bt.x, fma(-mo.cy[g], bt.y, kox));
+        koy = fma(mo.cx[g], bt.y, fma(mo.cy[g], bt.x, koy));
+        ktx = fma(mo.cx[g], bo.x, fma(-mo.cy[g], bo.y, ktx));
+        kty = fma(mo.cx[g], bo.y, fma(mo.cy[g], bo.x, kty));
+        const double nx = fma(mo.cx[g], mo.rx[g], fma(-mo.cy[g], mo.ry[g], mo.qx[g]));
+        mo.cy[g] = fma(mo.cx[g], mo.ry[g], fma(mo.cy[g], mo.rx[g], mo.ry[g]));
+        mo.cx[g] = nx;
+    }
+    s_own.x = kox; s_own.y = koy;
+    s_oth.x = ktx; s_oth.y = kty;
+}
+
 }  // namespace wfft
 }  // namespace fhe

@@ -402,6 +402,26 @@ def pbs_mb2_wide(p: N.PBSParams, bskf2: torch.Tensor, ct: torch.Tensor, luts: to
     return out
 
 
+def pbs_mb2_pair(p: N.PBSParams, bskf2: torch.Tensor, ct: torch.Tensor, luts: torch.Tensor,
+                 lut_index: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """:func:`pbs_mb2` with every ciphertext on a cluster of two CTAs (polynomial t on CTA t, spectra exchanged through
+    distributed shared memory; pbs_wide.cu) whatever the batch size.  Same key layout as :func:`pbs_mb2`."""
+    dev = ct.device
+    ct = ct.contiguous()
+    B = ct.shape[0]
+    assert ct.shape[1] == p.n + 1
+    luts = luts.to(device=dev, dtype=torch.int64).reshape(-1, p.N).contiguous()
+    if out is None:
+        out = torch.empty((B, p.k * p.N + 1), dtype=torch.int64, device=dev)
+    li = None
+    if lut_index is not None:
+        lut_index = lut_index.to(device=dev, dtype=torch.int32).contiguous()
+        li = _ptr(lut_index)
+    N.check(N.lib().fhe_b200_pbs_mb2_pair(_ctx(dev).handle, C.byref(p), _ptr(bskf2), _ptr(ct), B, _ptr(luts), li,
+                                          _ptr(out), _stream(dev)))
+    return out
+
+
 def make_lut_poly(table, p_bits: int, N_poly: int, delta_out_log2: int) -> np.ndarray:
     """Accumulator polynomial of a p-bit table lookup (message + 1 padding bit): box m holds
     table[m] << delta_out_log2 and the polynomial is multiplied by X^(-box/2)."""

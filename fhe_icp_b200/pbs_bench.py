@@ -137,7 +137,8 @@ def measure(dev, args, batches=None):
 
 def _mb2_kernels(B: int, sm: int) -> str:
     """Which kernels fhe_b200_pbs_mb2 launches for a batch (the dispatch of csrc/pbs.cu::launch_pbs_mb2): full waves of
-    4 x SMs ciphertexts on pbs_kernel_mb2<1,4>, a remainder of up to 3 x SMs on the latency kernel pbs_kernel_mb2_wide."""
+    4 x SMs ciphertexts on pbs_kernel_mb2<1,4>, a remainder of up to 3 x SMs on the latency kernel pbs_kernel_mb2_wide, or -- up to SMs / 2 -- on
+    pbs_kernel_mb2_pair (two SMs per ciphertext)."""
     full = B // (4 * sm) * (4 * sm)
     rest = B - full
     if rest > 3 * sm:
@@ -145,7 +146,9 @@ def _mb2_kernels(B: int, sm: int) -> str:
     parts = []
     if full:
         parts.append(f"pbs_kernel_mb2<1,4> x {full} (two key bits per step, four ciphertexts per CTA)")
-    if rest:
+    if rest and 2 * rest <= sm:
+        parts.append(f"pbs_kernel_mb2_pair x {rest} (two key bits per step, one ciphertext per cluster of two CTAs)")
+    elif rest:
         parts.append(f"pbs_kernel_mb2_wide x {rest} (two key bits per step, one ciphertext per CTA, eight warps)")
     return " + ".join(parts)
 

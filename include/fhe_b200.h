@@ -242,6 +242,13 @@ int fhe_b200_pbs_mb2(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const doub
 int fhe_b200_pbs_mb2_wide(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
                           const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
                           const int32_t *d_lut_index, uint64_t *d_out, void *stream);
+/* The same blind rotation with ONE ciphertext on a cluster of two CTAs (two SMs): CTA t owns polynomial t and streams
+ * column t of the key, the spectra cross through distributed shared memory (pbs_wide.cu).  The lowest latency;
+ * fhe_b200_pbs_mb2 runs it for batches up to half the SM count.  Same key, inputs and outputs as fhe_b200_pbs_mb2 (the
+ * key is re-sliced by output column into stream-ordered scratch at every call). */
+int fhe_b200_pbs_mb2_pair(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const double *d_bskf2,
+                          const uint64_t *d_in, int64_t B, const uint64_t *d_luts,
+                          const int32_t *d_lut_index, uint64_t *d_out, void *stream);
 /* 32-bit keyswitch ("KS32"): key rounded to the top 32 torus bits, u32 accumulation; d_scratch32 holds
  * B*(n+1) u32 words; the result is written as u64 words with the low half zero. */
 int fhe_b200_ksk_to_32(fhe_b200_ctx *ctx, const fhe_b200_pbs_params *p, const uint64_t *d_ksk,

@@ -54,8 +54,22 @@ extern "C" int emul_wide_fft(const double* in, int dir, int order, double* out) 
     return 0;
 }
 
+static int emul_wide_impl(const double* key_blocks, const double* key_cols, const uint64_t* ct, int n, int beta, const uint64_t* lut,
+                          int order, uint64_t* out);
+
 extern "C" int emul_pbs_mb2_wide(const double* key_blocks /* [pairs][32][3][2][1][2][32][2] */, const uint64_t* ct, int n,
                                  int beta, const uint64_t* lut, int order, uint64_t* out /* N + 1 */) {
+    return emul_wide_impl(key_blocks, nullptr, ct, n, beta, lut, order, out);
+}
+// the pointwise stage of pbs_kernel_mb2_pair: key by output column ([pairs][2][32][6][32][2], the layout of
+// bsk2_column_split_kernel), S_own / S_oth first, the other polynomial's spectrum last
+extern "C" int emul_pbs_mb2_pair(const double* key_cols, const uint64_t* ct, int n, int beta, const uint64_t* lut, int order,
+                                 uint64_t* out) {
+    return emul_wide_impl(nullptr, key_cols, ct, n, beta, lut, order, out);
+}
+
+static int emul_wide_impl(const double* key_blocks, const double* key_cols, const uint64_t* ct, int n, int beta, const uint64_t* lut,
+                          int order, uint64_t* out) {
     if (n % 2) return 1;
     std::vector<cplx> omega(128);
     const long double two_pi = 6.283185307179586476925286766559005768L;
@@ -118,7 +132,7 @@ extern "C" int emul_pbs_mb2_wide(const double* key_blocks /* [pairs][32][3][2][1
         }
         if (i == pairs) break;
         // ---- __syncthreads; segment B: pointwise (reads the other polynomial's spectrum) -> inverse stage 3
-        const cplx* key_pair = reinterpret_cast<const cplx*>(key_blocks) + (size_t)i * 32 * MB2_BLOCK_ELEMS;
+        const cplx* key_pair = key_blocks ? reinterpret_cast<const cplx*>(key_blocks) + (size_t)i * 32 * MB2_BLOCK_ELEMS : nullptr;
         for (int pi = 0; pi < 2; ++pi) {
             const int t = polys[pi];
             const cplx* o0 = xbuf[1 - t][i & 1].data();
@@ -127,8 +141,18 @@ extern "C" int emul_pbs_mb2_wide(const double* key_blocks /* [pairs][32][3][2][1
                 for (int kL = 0; kL < 8; ++kL) {
                     const cplx fo = o0[kL * WT + u];
                     cplx fa; fa.x = T.re[kL]; fa.y = T.im[kL];
-                    const cplx* blk = key_pair + (size_t)(4 * kL + (u >> 5)) * MB2_BLOCK_ELEMS;   // slice kL, block of this warp
-                    pointwise_bin(t, u & 31, fa, fo, blk, T.mo, T.gre[kL], T.gim[kL]);
+                    if (key_pair) {
+                        const cplx* blk = key_pair + (size_t)(4 * kL + (u >> 5)) * MB2_BLOCK_ELEMS;   // slice kL / 2, block of this warp
+                        pointwise_bin(t, u & 31, fa, fo, blk, T.mo, T.gre[kL], T.gim[kL]);
+                    } else {
+                        const cplx* blkc = reinterpret_cast<const cplx*>(key_cols) +
+                                           ((size_t)(i * 2 + t) * 32 + (size_t)(4 * kL + (u >> 5))) * COL_BLOCK_ELEMS;
+                        cplx so, st;
+                        pointwise_sums(t, u & 31, blkc, T.mo, so, st);
+                        const double pre = fma(fa.x, so.x, -(fa.y * so.y)), pim = fma(fa.x, so.y, fa.y * so.x);
+                        T.gre[kL] = fma(fo.x, st.x, fma(-fo.y, st.y, pre));
+                        T.gim[kL] = fma(fo.x, st.y, fma(fo.y, st.x, pim));
+                    }
                 }
                 inv_stage3(u, T.gre, T.gim, e1);
             END_THREADS

@@ -300,11 +300,13 @@ def test_keyswitch_tensor_core_other_gadgets(O, cuda_dev):
         assert np.array_equal(_u64(out), O.keyswitch32(K.op, O.ksk_to_32(K.op, _u64(K.ksk)), _u64(rnd)))
 
 
-@pytest.mark.parametrize("which,B", [("toy", 16), ("toy", 3), ("p4", 16), ("p4", 1), ("p4", 148 + 9)])
-def test_multibit_pbs_wide_kernel(O, cuda_dev, which, B):
-    """Same acceptance as test_multibit_pbs for the four-warps-per-polynomial latency kernel (pbs_wide.cu, one
-    ciphertext per CTA): every message maps to LUT[m], phases agree with the oracle's multi-bit PBS within the noise
-    bound, per-ciphertext LUT selection works, and more CTAs than SMs (a second wave) changes nothing."""
+@pytest.mark.parametrize("kernel,which,B", [("wide", "toy", 16), ("wide", "toy", 3), ("wide", "p4", 16), ("wide", "p4", 1), ("wide", "p4", 148 + 9),
+                                            ("pair", "toy", 16), ("pair", "toy", 3), ("pair", "p4", 16), ("pair", "p4", 1), ("pair", "p4", 74 + 9)])
+def test_multibit_pbs_latency_kernels(O, cuda_dev, kernel, which, B):
+    """Same acceptance as test_multibit_pbs for the two latency kernels of pbs_wide.cu -- "wide": one ciphertext per CTA,
+    four warps per polynomial; "pair": one ciphertext per cluster of two CTAs, spectra exchanged through distributed
+    shared memory: every message maps to LUT[m], phases agree with the oracle's multi-bit PBS within the noise bound,
+    per-ciphertext LUT selection works, and more CTAs / clusters than fit at once (a second wave) changes nothing."""
     import torch
     from fhe_icp_b200 import engine as E
     d = {"toy": TOY, "p4": P4}[which]
@@ -318,7 +320,8 @@ def test_multibit_pbs_wide_kernel(O, cuda_dev, which, B):
     luts = np.stack([E.make_lut_poly(tb, 4, K.p.N, 59) for tb in tables])
     lut_d = E.from_u64_numpy(luts, cuda_dev)
     which_lut = rng.randint(0, 2, size=B).astype(np.int32)
-    got = _u64(E.pbs_mb2_wide(K.p, K.bskf2, ct, lut_d, lut_index=torch.as_tensor(which_lut)))
+    run = E.pbs_mb2_wide if kernel == "wide" else E.pbs_mb2_pair
+    got = _u64(run(K.p, K.bskf2, ct, lut_d, lut_index=torch.as_tensor(which_lut)))
     want = tables[which_lut, msgs]
     assert np.array_equal(O.lwe_decrypt(K.oS, got, 59) & 15, want)
     of = O.bsk2_to_fourier(K.op, O.bsk2_gen(K.op, K.os, K.oS, K.evk_seed))
@@ -328,4 +331,4 @@ def test_multibit_pbs_wide_kernel(O, cuda_dev, which, B):
     assert np.log2(np.abs(diff).max() + 1) - 64 < -12
     err = (O.lwe_phase(K.oS, got) - (want.astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
     assert np.log2(np.abs(err).max() + 1) - 64 < -11
-    assert E.pbs_mb2_wide(K.p, K.bskf2, ct[:0], lut_d).shape == (0, K.p.N + 1)
+    assert run(K.p, K.bskf2, ct[:0], lut_d).shape == (0, K.p.N + 1)

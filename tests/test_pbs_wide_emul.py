@@ -22,6 +22,8 @@ def emul(tmp_path_factory):
     lib.emul_wide_fft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.emul_pbs_mb2_wide.restype = C.c_int
     lib.emul_pbs_mb2_wide.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.emul_pbs_mb2_pair.restype = C.c_int
+    lib.emul_pbs_mb2_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     return lib
 
 
@@ -85,3 +87,24 @@ def test_wide_memory_plan_is_order_independent(emul, O):
             outs.append(got)
         assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]), b
         assert (O.lwe_decrypt(S, outs[0][None, :], 59) & 15)[0] == table[msgs[b]]
+
+
+def test_pair_kernel_pointwise_on_the_column_layout(emul, O):
+    """pbs_kernel_mb2_pair (two CTAs per ciphertext) reads the key by output column and forms S_own, S_oth and F_t * S_own
+    before the other polynomial's spectrum arrives: the same decryptions, and phases within rounding of the one-CTA form."""
+    n = 8
+    msgs = np.array([1, 6, 10, 15])
+    p, S, of, blocks, ct = _setup(O, n, 5, 6, msgs, 9)
+    # [i][k1][g][t'][l=1][c][32][2] -> [i][c][k1][g][t'][32][2]  (bsk2_column_split_kernel)
+    cols = np.ascontiguousarray(blocks[:, :, :, :, 0].transpose(0, 4, 1, 2, 3, 5, 6))
+    table = (np.arange(16) * 7 + 3) % 16
+    lut = O.make_lut_poly(table, 4, 2048, 59)
+    for b in range(len(msgs)):
+        row = np.ascontiguousarray(ct[b])
+        one = np.zeros(2049, dtype=np.uint64)
+        two = np.zeros(2049, dtype=np.uint64)
+        assert emul.emul_pbs_mb2_wide(blocks.ctypes.data, row.ctypes.data, n, 23, lut.ctypes.data, 0, one.ctypes.data) == 0
+        assert emul.emul_pbs_mb2_pair(cols.ctypes.data, row.ctypes.data, n, 23, lut.ctypes.data, 1, two.ctypes.data) == 0
+        assert (O.lwe_decrypt(S, two[None, :], 59) & 15)[0] == table[msgs[b]]
+        diff = (O.lwe_phase(S, one[None, :]) - O.lwe_phase(S, two[None, :])).view(np.int64).astype(np.float64)
+        assert np.log2(np.abs(diff).max() + 1) - 64 < -12

@@ -26,7 +26,8 @@ def _no_wide(fn):
         del os.environ["FHE_B200_PBS_NO_WIDE"]
 
 
-kernels = {"wide": lambda ct, out: E.pbs_mb2_wide(p, bskf2, ct, lut, out=out),
+kernels = {"pair": lambda ct, out: E.pbs_mb2_pair(p, bskf2, ct, lut, out=out),
+           "wide": lambda ct, out: E.pbs_mb2_wide(p, bskf2, ct, lut, out=out),
            "mb2<1,4>": lambda ct, out: _no_wide(lambda: E.pbs_mb2(p, bskf2, ct, lut, out=out)),
            "dispatch": lambda ct, out: E.pbs_mb2(p, bskf2, ct, lut, out=out)}
 if os.environ.get("SWEEP_ONLY"):
