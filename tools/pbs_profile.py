@@ -27,19 +27,22 @@ out = torch.empty((B, p.N + 1), dtype=torch.int64, device=dev)
 import os
 MB2 = os.environ.get("PBS_MB2", "0") == "1"
 WIDE = os.environ.get("PBS_WIDE", "0") == "1"
-if MB2 or WIDE:
+PAIR = os.environ.get("PBS_PAIR", "0") == "1"
+if MB2 or WIDE or PAIR:
     bskf2 = E.bsk2_to_fourier(p, E.bsk2_gen(p, s, S, 202))
 for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    if WIDE:
+    if PAIR:
+        E.pbs_mb2_pair(p, bskf2, ct, lut, out=out)
+    elif WIDE:
         E.pbs_mb2_wide(p, bskf2, ct, lut, out=out)
     elif MB2:
         E.pbs_mb2(p, bskf2, ct, lut, out=out)
     else:
         E.pbs(p, bskf, ct, lut, out=out)
     e1.record(); torch.cuda.synchronize()
-    print(f"B={B} {'wide' if WIDE else 'mb2' if MB2 else 'pbs'} {e0.elapsed_time(e1):.3f} ms -> {B / e0.elapsed_time(e1) * 1e3:.0f} PBS/s")
+    print(f"B={B} {'pair' if PAIR else 'wide' if WIDE else 'mb2' if MB2 else 'pbs'} {e0.elapsed_time(e1):.3f} ms -> {B / e0.elapsed_time(e1) * 1e3:.0f} PBS/s")
 z = torch.zeros((B, p.N + 2), dtype=torch.int64, device=dev); z[:, : p.N + 1] = out
 dec = E.lwe_decrypt(S, z, 59).cpu().numpy() & 15
 print("correct:", bool(np.array_equal(dec, table[msgs])))
