@@ -119,7 +119,7 @@ def measure(dev, args, batches=None):
                      "flops_per_pbs": flops, "bsk_fourier_bytes": int(bsk_bytes),
                      "fp64_pipe_active_ncu": 0.502, "smem_wavefronts_of_peak_ncu": 0.519, "issue_active_ncu": 0.354,
                      "ncu_source": "profiles/r2_ncu_pbs_mb2_v10.txt (the shipped pbs_kernel_mb2<1,4>, batch 1184); small-batch "
-                                   "kernel pbs_kernel_mb2_wide: profiles/r2_ncu_pbs_wide_v2.txt",
+                                   "kernels pbs_kernel_mb2_wide / pbs_kernel_mb2_pair: profiles/r2_ncu_pbs_wide_v2.txt, profiles/r2_ncu_pbs_pair_v1.txt",
                      "hbm_term": {"bytes_per_batch": int(bsk_bytes + best["batch"] * (p.n + 1 + p.k * p.N + 1 + p.N) * 8),
                                   "note": "the Fourier key is read from HBM once per launch and then served from L2 "
                                           "(ncu: 52 MB DRAM reads per launch); key streaming never binds once batched"},
@@ -128,7 +128,7 @@ def measure(dev, args, batches=None):
                              "flops = 5*M*log2(M) per FFT + 8 per complex MAC; the kernel's instruction mix "
                              "(DADD/DMUL/DFMA ~ 45/25/30 %) caps it at ~65 % of the FMA peak even with a saturated "
                              "pipe.  Small batches are neither HBM nor FP64 bound: one ciphertext's blind rotation is a "
-                             "serial chain of 371 (multi-bit) / 742 CMuxes on one SM (batch 1: ~1.8 ms with eight warps on it), and the key "
+                             "serial chain of 371 (multi-bit) / 742 CMuxes on one SM (batch 1: 1.3 ms on a cluster of two SMs, 1.8 ms on one), and the key "
                              "(49-73 MB) sits in the 126 MB L2 after its first read, so key streaming from HBM never binds "
                              "(by_batch[].roofline_terms gives both terms per batch)."},
     }
@@ -294,7 +294,8 @@ def measure_packed(dev, args, docs: int = 262144):
                         "algorithmic_bytes_per_launch": int(hbm),
                         "flops_per_ciphertext": float(6 * 5 * 1024 * 10 + 2 * 4 * 1024 * 8),
                         "achieved_tflops": float(6 * 5 * 1024 * 10 + 2 * 4 * 1024 * 8) * G / (ms * 1e-3) / 1e12,
-                        "fp64_pipe_active_ncu": 0.32, "ncu_source": "profiles/r1_ncu_glwe_dot_v1.txt",
+                        "fp64_pipe_active_ncu": 0.40, "dram_throughput_of_peak_ncu": 0.217, "issue_active_ncu": 0.32,
+                        "ncu_source": "profiles/r2_ncu_glwe_dot_v2.txt (the shipped kernel)",
                         "note": "32 KB in + 32 KB out per ciphertext is a third of the HBM roof; the six 1024-point f64 "
                                 "FFTs per ciphertext bind (6 warps per SM at 255 registers, latency-exposed)"}}
     res["_sample"] = {"xq": xq, "yq": yq[:1024], "key_seed": pe.key_seed, "slot": pe.slot, "per": pe.per,

@@ -65,3 +65,20 @@ def test_both_arms_print_the_same_config_object():
         assert cfg == bench.workload_config(argparse.Namespace(**vars(a)), c) and "workload" in cfg
         assert ("multi_gpu" in cfg) == (gpus > 1)
         assert cfg["bytes_per_comparison"] == (128 + 2) * (c.lwe.n + 1) * 8
+
+
+def test_pbs_dispatch_labels_follow_the_dispatcher():
+    """pbs_bench._mb2_kernels mirrors csrc/pbs.cu::launch_pbs_mb2: full waves of 4 x SMs ciphertexts on the throughput
+    kernel, a remainder on the cluster kernel up to SMs / 2, on the one-CTA latency kernel up to 3 x SMs, else on the
+    throughput kernel."""
+    from fhe_icp_b200.pbs_bench import _mb2_kernels
+    sm = 148
+    assert _mb2_kernels(1, sm).startswith("pbs_kernel_mb2_pair x 1")
+    assert _mb2_kernels(74, sm).startswith("pbs_kernel_mb2_pair x 74")
+    assert _mb2_kernels(75, sm).startswith("pbs_kernel_mb2_wide x 75")
+    assert _mb2_kernels(444, sm).startswith("pbs_kernel_mb2_wide x 444")
+    assert _mb2_kernels(445, sm).startswith("pbs_kernel_mb2<1,4> x 445")
+    assert _mb2_kernels(592, sm).startswith("pbs_kernel_mb2<1,4> x 592") and "+" not in _mb2_kernels(592, sm)
+    both = _mb2_kernels(612, sm)
+    assert "pbs_kernel_mb2<1,4> x 592" in both and "pbs_kernel_mb2_pair x 20" in both
+    assert "pbs_kernel_mb2_wide x 148" in _mb2_kernels(740, sm)
