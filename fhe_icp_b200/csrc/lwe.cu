@@ -8,6 +8,8 @@
 // aligned), so a warp reads 512 contiguous bytes per 128-bit load instruction.
 #include <algorithm>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "lwe_device.cuh"
@@ -684,6 +686,14 @@ lincomb_seeded_kernel(const uint64_t* __restrict__ bodies, int d, int n, int64_t
         __syncthreads();
     }
     const int64_t g = g0 + threadIdx.x;
+    // Does every lane of this warp that will run the table loop hold two MASK words?  Voted here, where the warp is
+    // still converged (lanes past the end of the batch or in the padding behind the body do not enter the loop).
+    bool plain;
+    {
+        const int64_t bq = g / vecs;
+        const int wq = 2 * (int)(g - bq * vecs);
+        plain = __all_sync(0xffffffffu, g >= total_vecs || wq > n || wq + 1 < n);
+    }
     if (g < total_vecs) {
         const int64_t b = g / vecs;
         const int w0 = 2 * (int)(g - b * vecs);
@@ -698,30 +708,58 @@ lincomb_seeded_kernel(const uint64_t* __restrict__ bodies, int d, int n, int64_t
             const CtShare* row = tab + (size_t)(b - b_first) * d;
             uint64_t l0x = 0, l0y = 0, l1x = 0, l1y = 0, sx = 0, sy = 0;   // low-limb accumulators, plain sums
             uint32_t h0x = 0, h0y = 0, h1x = 0, h1y = 0;                   // high-limb accumulators (mod 2^32)
+            // The loop below generates MASK words only.  Which of a thread's two words are mask words is a per-thread
+            // constant (all of them except in the one or two threads per document that hold the body / the padding), so
+            // a warp without such a thread runs the loop with no selects at all and the others AND their words with
+            // constant masks; the body's own term sum_j w_j body_j is added after the loop by the thread that holds it.
+            // (Selecting mask / body / zero per word inside the loop cost ~10 predicated instructions per iteration,
+            // several of them IMAD.MOVs on the very pipe that bounds the kernel.)
+            const uint64_t mx = w0 < n ? ~0ULL : 0ULL, my = w0 + 1 < n ? ~0ULL : 0ULL;
+            auto mac_loop = [&](auto masked) {
 #pragma unroll LCS_UNROLL_N
-            for (int j = 0; j < d; ++j) {
-                const CtShare e = row[j];
-                u32x4 c{p_hi ^ e.y1 ^ K.k0[1], p_lo, e.q_hi ^ w1 ^ K.k1[1], e.q_lo};   // state after round 2
+                for (int j = 0; j < d; ++j) {
+                    const CtShare e = row[j];
+                    u32x4 c{p_hi ^ e.y1 ^ K.k0[1], p_lo, e.q_hi ^ w1 ^ K.k1[1], e.q_lo};   // state after round 2
 #pragma unroll
-                for (int r = 2; r < MASK_ROUNDS; ++r) {
-                    uint32_t m0h, m0l, m1h, m1l;
-                    mulwide32(0xD2511F53u, c.x, m0h, m0l);
-                    mulwide32(0xCD9E8D57u, c.z, m1h, m1l);
-                    c = u32x4{m1h ^ c.y ^ K.k0[r], m1l, m0h ^ c.w ^ K.k1[r], m0l};
+                    for (int r = 2; r < MASK_ROUNDS; ++r) {
+                        uint32_t m0h, m0l, m1h, m1l;
+                        mulwide32(0xD2511F53u, c.x, m0h, m0l);
+                        mulwide32(0xCD9E8D57u, c.z, m1h, m1l);
+                        c = u32x4{m1h ^ c.y ^ K.k0[r], m1l, m0h ^ c.w ^ K.k1[r], m0l};
+                    }
+                    uint64_t x = lo64(c), y = hi64(c);
+                    if (decltype(masked)::value) { x &= mx; y &= my; }
+                    const uint32_t w = e.w;
+                    l0x += (uint64_t)(uint32_t)x * w;  h0x += (uint32_t)(x >> 32) * w;
+                    l0y += (uint64_t)(uint32_t)y * w;  h0y += (uint32_t)(y >> 32) * w;
+                    sx += x;
+                    sy += y;
+                    if (MW == 2) {
+                        const uint32_t wb = sW32b[j];
+                        l1x += (uint64_t)(uint32_t)x * wb;  h1x += (uint32_t)(x >> 32) * wb;
+                        l1y += (uint64_t)(uint32_t)y * wb;  h1y += (uint32_t)(y >> 32) * wb;
+                    }
                 }
-                const uint64_t body = has_body ? bodies[b * d + j] : 0;
-                const uint64_t x = w0 < n ? lo64(c) : (w0 == n ? body : 0);
-                const uint64_t y = w0 + 1 < n ? hi64(c) : (w0 + 1 == n ? body : 0);
-                const uint32_t w = e.w;
-                l0x += (uint64_t)(uint32_t)x * w;  h0x += (uint32_t)(x >> 32) * w;
-                l0y += (uint64_t)(uint32_t)y * w;  h0y += (uint32_t)(y >> 32) * w;
-                sx += x;
-                sy += y;
-                if (MW == 2) {
-                    const uint32_t wb = sW32b[j];
-                    l1x += (uint64_t)(uint32_t)x * wb;  h1x += (uint32_t)(x >> 32) * wb;
-                    l1y += (uint64_t)(uint32_t)y * wb;  h1y += (uint32_t)(y >> 32) * wb;
+            };
+            if (plain) mac_loop(std::false_type{});
+            else mac_loop(std::true_type{});
+            if (has_body) {          // this thread's word at index n is the body: add sum_j w_j body_j to that word's sums
+                uint64_t lb = 0, l1b = 0, sb = 0;
+                uint32_t hb = 0, h1b = 0;
+                for (int j = 0; j < d; ++j) {
+                    const uint64_t body = bodies[b * d + j];
+                    const uint32_t w = row[j].w;
+                    lb += (uint64_t)(uint32_t)body * w;
+                    hb += (uint32_t)(body >> 32) * w;
+                    sb += body;
+                    if (MW == 2) {
+                        const uint32_t wb = sW32b[j];
+                        l1b += (uint64_t)(uint32_t)body * wb;
+                        h1b += (uint32_t)(body >> 32) * wb;
+                    }
                 }
+                if (w0 == n) { l0x += lb; h0x += hb; sx += sb; l1x += l1b; h1x += h1b; }
+                else { l0y += lb; h0y += hb; sy += sb; l1y += l1b; h1y += h1b; }
             }
             const uint64_t m0 = (uint64_t)rows[0].wmin;
             a0x = l0x + ((uint64_t)h0x << 32) + m0 * sx;
