@@ -441,3 +441,27 @@ def test_wire32_gate_counts_the_modswitch_noise(cuda_dev):
         wide.compress_scores(out)
     with pytest.raises(ValueError, match="32-bit wire form"):
         PeerScoreBoard(wide, rows_max=16)
+
+
+def test_pinned_and_pageable_rows_give_the_same_scores(cuda_dev):
+    """predict_host[_seeded] uploads page-locked rows (fhe_b200_host_alloc / _native.pinned_copy) from where they are and
+    stages pageable ones; both forms, and a strided (non-contiguous) view, return the clear circuit's scores -- and the
+    results land in the caller's arrays although the client kernel stores them zero-copy into the library's buffer."""
+    from fhe_icp_b200 import FHESimilarityModel
+    from fhe_icp_b200 import _native as N
+    m = FHESimilarityModel(input_dim=128, n_bits=8, seed=23, verbose=False)
+    X, _ = m.train(n_samples=300)
+    m.compile(X[:10])
+    ref = m.predict_clear(X)
+    Xp = N.pinned_copy(X)
+    assert Xp.dtype == np.float32 and Xp.shape == X.shape and np.array_equal(Xp, X)
+    for fmt in ("seeded", "expanded"):
+        m.model.fhe_circuit.ciphertext_format = fmt
+        assert np.array_equal(m.predict_encrypted(Xp), ref)
+        assert np.array_equal(m.predict_encrypted(X), ref)
+        assert np.array_equal(m.predict_encrypted(Xp[::2]), ref[::2])        # a view: made contiguous by the host mirror
+        assert np.array_equal(m.predict_encrypted(Xp[7:8]), ref[7:8])        # one row from the middle of a pinned buffer
+    del Xp                                                                    # the finalizer frees the pinned allocation
+    import gc
+    gc.collect()
+    assert np.array_equal(m.predict_encrypted(X[:5]), ref[:5])
