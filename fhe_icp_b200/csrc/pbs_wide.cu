@@ -42,6 +42,9 @@ constexpr int PW_OMEGA = 128;
 #ifndef WIDE_SLOTS
 #define WIDE_SLOTS 3
 #endif
+#ifndef WIDE_SKEW
+#define WIDE_SKEW 200       // clocks polynomial 1 is held back per step (see the kernel)
+#endif
 constexpr int PW_SLOTS = WIDE_SLOTS;
 constexpr int PW_THREADS = 2 * wfft::WT;
 constexpr unsigned PW_WARPS = PW_THREADS / 32;
@@ -201,6 +204,17 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
         wfft::inv_stage3(u, gre, gim, e1);
         __syncthreads();
         WIDE_TICK(4)                               // also: nobody reads the published spectra any more
+        // Phase offset between the two polynomials.  Their warps run every phase of a step in lock step (load burst,
+        // arithmetic, store burst, barrier), so the shared-memory pipe and the FP64 pipe take turns.  Holding polynomial 1
+        // back by a fraction of a phase after this barrier makes its bursts fall under polynomial 0's arithmetic for the
+        // five phases up to the next CTA-wide barrier (where polynomial 0 then waits the same time): batch 148 measured
+        // 1.780 ms without, 1.709 / 1.697 / 1.611 / 1.598 / 1.641 ms at 50 / 100 / 150 / 200 / 250 clocks.  (Letting the
+        // polynomials run free of each other -- flags instead of CTA-wide barriers -- settles at an offset of a WHOLE
+        // phase and gains nothing: 1.78 ms; profiles/r2_pbs_wide_times.txt.)
+        if (WIDE_SKEW > 0 && t == 1) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < WIDE_SKEW) { }
+        }
         wfft::inv_stage2(tw, u, e1, e0);
         pw_bar_poly(t);
         WIDE_TICK(5)
