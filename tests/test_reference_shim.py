@@ -59,3 +59,33 @@ def test_committed_trace_fixture_is_current(traces):
     assert sorted(want) == sorted(have.files)
     for k in want:
         assert np.array_equal(want[k], have[k]), k
+
+
+def test_reference_fixed_similarity_script_runs_unmodified_and_its_conclusion_holds():
+    """/root/reference/test_fixed_similarity.py (the script behind SESSION5_FIXES.md) run as it is on the shim: the
+    estimator it builds itself -- `LinearRegression(n_bits=8)` on element-wise products, fit / score / predict, the very
+    circuit of the hot path -- gives what the script concludes: "Fixed model: predictions match true cosine
+    similarities" (identical ~ 1, opposite ~ -1, every pair within the 8-bit quantization error), while the 256-d
+    model fed concatenated embeddings does not."""
+    import contextlib
+    import io
+    import re
+    import make_reference_traces as M
+    M._paths()
+    import test_fixed_similarity as ref
+    assert Path(ref.__file__).parent == M.REFERENCE
+    np.random.seed(104)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ref.test_comparison()
+    txt = buf.getvalue()
+    num = r"(-?\d+\.\d+)"
+    true = [float(x) for x in re.search(rf"Identical: {num}\s+Similar: {num}\s+Different: {num}\s+Opposite: {num}", txt).groups()]
+    blocks = re.findall(rf"Predictions:\s+Identical: {num}\s+Similar: {num}\s+Different: {num}\s+Opposite: {num}", txt)
+    assert len(blocks) == 2
+    orig, fixed = ([float(x) for x in b] for b in blocks)
+    assert true[0] == 1.0 and true[3] == -1.0
+    assert max(abs(p - t) for p, t in zip(fixed, true)) < 0.05            # "predictions match true cosine similarities"
+    assert abs(orig[0] - 1.0) > 0.3        # the 256-d model fed concatenated embeddings does not see identical vectors as 1
+    r2 = float(re.findall(r"Training R² score: (-?\d+\.\d+)", txt)[-1])
+    assert r2 > 0.99                                                       # the product features are an exact linear model
