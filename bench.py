@@ -42,7 +42,7 @@ N_BITS = 8
 DATA_SEED, KEY_SEED, ENC_SEED, EVK_SEED, NOISE_SEED = 20261018, 0x5EED0001, 0x5EED0002, 0x5EED0003, 0x5EED0004
 # measured DRAM traffic of one lincomb_kernel launch per document, keyed by (lwe n, outputs M, d): dram__bytes_read.sum +
 # dram__bytes_write.sum of an `ncu --set full` capture; shapes without a capture report traffic = null
-NCU_TRAFFIC = {(1423, 2, 128): (1475986, "profiles/r1_ncu_lincomb_decrypt_v3.txt ((1.458192 GB read + 17.794 MB written) / 1000 documents)")}
+NCU_TRAFFIC = {(1423, 2, 128): (1475440, "profiles/r2_ncu_lincomb_decrypt_v4.txt ((1.458192 GB read + 17.248 MB written) / 1000 documents)")}
 TOTAL_DOCS_CONFIG4 = 1_000_000       # BASELINE.json configs[3]
 TOTAL_DOCS_CONFIG5 = 100_000         # BASELINE.json configs[4], on 8 GPUs: 12 500 per GPU
 D_CONFIG5, BITS_CONFIG5 = 256, 12
