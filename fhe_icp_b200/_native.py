@@ -292,7 +292,8 @@ def pinned_empty(shape, dtype=np.float32, device: int | None = None) -> np.ndarr
     check(lib().fhe_b200_host_alloc(ctx.handle, max(n, 1), C.byref(p)))
     buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
-    weakref.finalize(buf, lambda h=ctx.handle, q=p.value: lib().fhe_b200_host_free(h, _vp(q)))
+    fin = weakref.finalize(buf, lambda q=p.value: lib().fhe_b200_host_free(None, _vp(q)))
+    fin.atexit = False          # at interpreter shutdown the CUDA runtime may already be gone: the OS reclaims the pages
     return arr
 
 

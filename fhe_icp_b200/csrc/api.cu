@@ -929,9 +929,9 @@ int fhe_b200_host_alloc(fhe_b200_ctx* ctx, uint64_t bytes, void** h_ptr) {
 }
 
 int fhe_b200_host_free(fhe_b200_ctx* ctx, void* h_ptr) {
-    REQUIRE(ctx, "host_free: null context");
+    (void)ctx;      // page-locked memory belongs to no device: the context is not consulted (it may already be gone when a
+                    // garbage collector returns the buffer)
     if (!h_ptr) return FHE_B200_OK;
-    CU(cudaSetDevice(ctx->device));
     CU(cudaFreeHost(h_ptr));
     return FHE_B200_OK;
 }

@@ -304,7 +304,7 @@ int fhe_b200_similarity_encrypt_seeded(fhe_b200_similarity *sim, const float *d_
  * they are; pageable rows are first staged through the model's own pinned buffer.  The reference passes plain numpy
  * arrays (fhe_similarity.py:151); this is the buffer a caller allocates when it wants the upload off its critical path. */
 int fhe_b200_host_alloc(fhe_b200_ctx *ctx, uint64_t bytes, void **h_ptr);
-int fhe_b200_host_free(fhe_b200_ctx *ctx, void *h_ptr);
+int fhe_b200_host_free(fhe_b200_ctx *ctx, void *h_ptr);   /* ctx may be NULL */
 
 /* same with the clear product fused in: feature (b, j) = d_query[j] * d_docs[b*d + j] in IEEE float32, the array the
  * reference builds on the host before every call (emb1 * emb2, /root/reference/batch_operations.py:226,273) */
