@@ -331,3 +331,49 @@ def test_encrypt_products_equals_host_product_bit_for_bit(cuda_dev):
     assert np.array_equal(m.decrypt(m.run(got)), m.predict_clear((q[None, :] * docs).astype(np.float32)))
     with pytest.raises(ValueError):
         m.encrypt_products(q, docs[:, :64])
+
+
+def test_one_million_seeded_documents_full_size_properties(cuda_dev):
+    """BASELINE.json configs[3] at its full size on one GPU: a collection of 1 M documents as seeded ciphertexts (1 GB of
+    bodies), searched chunk by chunk.  Size-independent checks: (1) every one of the 1 M decrypted scores equals the clear
+    quantized circuit and so does the top-10 ranking; (2) linearity on the raw score ciphertexts of a chunk -- the weighted
+    row equals w_min * (plain-sum row) + the row of the shifted weights, word for word, i.e. what the kernel's split
+    accumulation assumes; (3) the score ciphertexts of a chunk do not depend on how the collection is cut into launches."""
+    import torch
+    from bench import collection_query, collection_rows, build_model
+    from fhe_icp_b200.batch_operations import top_indices
+    m, _ = build_model(0)
+    c = m.model.fhe_circuit
+    d, total, chunk, seed = c.spec.d, 1_000_000, 62_500, 4242
+    q = collection_query(d, seed)
+    base = c.next_ct_base(total * d)
+    scores = np.empty(total)
+    clear = np.empty(total)
+    first_out = None
+    for lo in range(0, total, chunk):
+        X = q[None, :] * collection_rows(lo, lo + chunk, d, seed, q)
+        c.ct_counter = base + lo * d                     # ciphertext ids laid out as ONE collection
+        sc = m.encrypt(X, seeded=True)
+        out = m.run(sc)
+        scores[lo:lo + chunk] = m.decrypt(out)
+        clear[lo:lo + chunk] = m.predict_clear(X)
+        if lo == 0:
+            first_out = out[:1000].clone()
+            # (3) the same 1000 documents evaluated in a launch of their own: identical ciphertext words
+            c.ct_counter = base
+            sc_small = m.encrypt(X[:1000], seeded=True)
+            assert torch.equal(m.run(sc_small), first_out)
+        del sc, out
+    assert np.array_equal(scores, clear)                                           # (1) all 1 M scores
+    assert np.array_equal(top_indices(scores, 10, -np.inf), top_indices(clear, 10, -np.inf))
+    if c.two_outputs:                                                              # (2) linearity, on 1000 documents
+        from fhe_icp_b200 import engine as E
+        c.ct_counter = base
+        X = q[None, :] * collection_rows(0, 1000, d, seed, q)
+        ct = m.encrypt(X)                                                          # expanded form of the same ciphertexts
+        qw = c.spec.q_weights.astype(np.int64)
+        wmin = int(qw.min())
+        shifted = torch.as_tensor(np.stack([qw - wmin, np.ones_like(qw)]), device=ct.device)
+        parts = E.lincomb(ct, shifted, c.lwe.n, shift=c.lwe.shift)                          # rows: sum (w - wmin) ct, sum ct
+        want = parts[:, 0] + wmin * parts[:, 1]                                    # wrapping int64 arithmetic == mod 2^64
+        assert torch.equal(first_out[:, 0], want) and torch.equal(first_out[:, 1], parts[:, 1])
