@@ -332,3 +332,47 @@ def test_multibit_pbs_latency_kernels(O, cuda_dev, kernel, which, B):
     err = (O.lwe_phase(K.oS, got) - (want.astype(np.uint64) << np.uint64(59))).view(np.int64).astype(np.float64)
     assert np.log2(np.abs(err).max() + 1) - 64 < -11
     assert run(K.p, K.bskf2, ct[:0], lut_d).shape == (0, K.p.N + 1)
+
+
+def test_full_size_batch_keyswitch_pbs_composition(cuda_dev):
+    """BASELINE.json configs[2] at its upper end: 65 536 ciphertexts through keyswitch + PBS twice (the atomic pattern,
+    tensor-core keyswitch, the dispatcher's mix of kernels: 110 full waves of the throughput kernel and a remainder on
+    the latency kernel).  Size-independent properties: every ciphertext decrypts to table1[m] after the first bootstrap and
+    to table2[table1[m]] after the second (a table lookup composes); re-running part of the batch reproduces the same words
+    where the dispatcher picks the same kernel (deterministic whatever the CTA grouping) and the same values where it
+    picks another (a different FFT schedule rounds differently, inside the noise)."""
+    import ctypes as C
+    import torch
+    from fhe_icp_b200 import _native as N_
+    from fhe_icp_b200 import engine as E
+    dev = cuda_dev
+    p = E.make_pbs_params(**P4)
+    s, S = E.secret_key(31, 0, p.n, dev), E.secret_key(31, 1, p.k * p.N, dev)
+    ksk = E.ksk_gen(p, S, s, 32)
+    key_mma = E.ksk_to_mma(p, E.ksk_to_32(p, ksk))
+    bskf2 = E.bsk2_to_fourier(p, E.bsk2_gen(p, s, S, 32))
+    B = 65536
+    rng = np.random.RandomState(7)
+    msgs = rng.randint(0, 16, size=B)
+    t1, t2 = (np.arange(16) * 7 + 3) % 16, (np.arange(16) * 5 + 1) % 16
+    lut1 = E.from_u64_numpy(E.make_lut_poly(t1, 4, p.N, 59), dev)
+    lut2 = E.from_u64_numpy(E.make_lut_poly(t2, 4, p.N, 59), dev)
+    ct_big = E.lwe_encrypt(S, torch.as_tensor(msgs), 59, p.sigma_glwe_abs, enc_seed=33, stride=p.N + 2)[:, : p.N + 1].contiguous()
+    work = torch.empty(int(N_.lib().fhe_b200_keyswitch_mma_workspace_bytes(C.byref(p), B)), dtype=torch.int8, device=dev)
+
+    def dec(x):
+        z = torch.zeros((B, p.N + 2), dtype=torch.int64, device=dev)
+        z[:, : p.N + 1] = x
+        return E.lwe_decrypt(S, z, 59).cpu().numpy() & 15
+
+    small = E.keyswitch_mma(p, key_mma, ct_big, work=work)
+    out1 = E.pbs_mb2(p, bskf2, small, lut1)
+    assert np.array_equal(dec(out1), t1[msgs])
+    nsub = 4 * 148 * 3 + 17                                                    # a different partition of the same inputs:
+    again = E.pbs_mb2(p, bskf2, small[:nsub], lut1)                            # 3 full waves + 17 on the cluster kernel
+    assert torch.equal(again[: nsub - 17], out1[: nsub - 17])                  # same kernel: the same words
+    z = torch.zeros((nsub, p.N + 2), dtype=torch.int64, device=dev)
+    z[:, : p.N + 1] = again
+    assert np.array_equal(E.lwe_decrypt(S, z, 59).cpu().numpy() & 15, t1[msgs[:nsub]])   # another kernel: the same values
+    out2 = E.pbs_mb2(p, bskf2, E.keyswitch_mma(p, key_mma, out1, work=work), lut2)
+    assert np.array_equal(dec(out2), t2[t1[msgs]])
