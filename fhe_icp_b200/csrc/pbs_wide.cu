@@ -58,6 +58,29 @@ struct PwSmem {
     static size_t total(int n) { return ring_bytes + x_bytes + omega_bytes + bar_bytes + (((size_t)(n + 1) * 2 + 127) & ~(size_t)127); }
 };
 
+// tensor memory as a lane-aligned mailbox between the two polynomials (warps w and w + 4 share a lane quadrant)
+__device__ __forceinline__ void pw_tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void pw_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void pw_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :
+                 : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                   "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+__device__ __forceinline__ void pw_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void pw_bar_poly(int t) {
     if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
     else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -76,6 +99,7 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
     cplx* omega = reinterpret_cast<cplx*>(smem_raw + S::ring_bytes + S::x_bytes);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + S::ring_bytes + S::x_bytes + S::omega_bytes);
     unsigned* left = reinterpret_cast<unsigned*>(bar_full + PW_SLOTS);      // warps that have left each slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(left + PW_SLOTS + 1);
     uint16_t* a_tilde = reinterpret_cast<uint16_t*>(smem_raw + S::ring_bytes + S::x_bytes + S::omega_bytes + S::bar_bytes);
 
     const int tid = threadIdx.x, t = tid >> 7, u = tid & 127, lane = tid & 31, wp = u >> 5;
@@ -88,7 +112,16 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
     }
     const uint64_t* ct = in + (size_t)b * (n + 1);
     for (int i = tid; i <= n; i += PW_THREADS) a_tilde[i] = (uint16_t)((((ct[i] >> 51) + 1) >> 1) & 4095);
+    if (tid < 32) pw_tmem_alloc(tmem_slot, 64);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // The spectrum mailbox: thread (t, u) and thread (1 - t, u) are the same lane of two warps that share a TMEM lane
+    // quadrant (warps w and w + 4), and what one publishes -- its 8 bins u + 128 kL -- is exactly what the other needs.
+    // 32 columns per polynomial: tcgen05.st / tcgen05.ld instead of 8 shared-memory stores + 8 loads per thread and step
+    // (the shared-memory pipe is this kernel's busiest).
+    const uint32_t tmail = *tmem_slot + ((uint32_t)((tid >> 5 & 3) * 32) << 16);
+    const uint32_t tmail_own = tmail + 32u * (uint32_t)t, tmail_oth = tmail + 32u * (uint32_t)(1 - t);
 
     const int pairs = n >> 1;
     const int total_slices = pairs * wfft::SLICES_PER_STEP;
@@ -125,10 +158,10 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
         }
     }
 
-    cplx* xa = xbufs + (size_t)(2 * t) * wfft::XBUF_ELEMS;              // this polynomial's two exchange buffers
-    cplx* xb = xa + wfft::XBUF_ELEMS;
-    const cplx* oa = xbufs + (size_t)(2 * (1 - t)) * wfft::XBUF_ELEMS;  // the other polynomial's
-    const cplx* ob = oa + wfft::XBUF_ELEMS;
+    // this polynomial's two exchange buffers: e0 carries forward stage 1 and inverse stage 3, e1 forward stage 2 and inverse
+    // stage 2 -- four exchanges per step, every rewrite behind a barrier all readers of the buffer have passed
+    cplx* const e0 = xbufs + (size_t)(2 * t) * wfft::XBUF_ELEMS;
+    cplx* const e1 = e0 + wfft::XBUF_ELEMS;
 
 #ifdef WIDE_TIMING      // debug builds: clocks per phase of a step, printed by one warp of each polynomial of CTA 0
     unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
@@ -138,10 +171,6 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
 #endif
     double re[8], im[8];
     for (int i = 0; i < pairs; ++i) {
-        // exchange buffers of this step in write order: w0 r0 w1 r1 w2(spectrum) ...; five per step, so the roles swap
-        cplx* e0 = (i & 1) ? xb : xa;
-        cplx* e1 = (i & 1) ? xa : xb;
-        const cplx* o0 = (i & 1) ? ob : oa;
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
             re[a] = wfft::top_digit((uint32_t)(acc_re[a] >> 32), beta);
@@ -154,16 +183,28 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
         pw_bar_poly(t);
         WIDE_TICK(1)
         wfft::fwd_stage3(u, e1, re, im);
+        {   // publish the spectrum: the other polynomial's pointwise stage reads it (tensor-memory mailbox)
 #pragma unroll
-        for (int kL = 0; kL < 8; ++kL) {          // publish the spectrum: the other polynomial's pointwise stage reads it
-            cplx v;
-            v.x = re[kL];
-            v.y = im[kL];
-            e0[kL * wfft::WT + u] = v;
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                uint32_t w[16];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const unsigned long long xr = (unsigned long long)__double_as_longlong(re[4 * hlf + k4]);
+                    const unsigned long long xi = (unsigned long long)__double_as_longlong(im[4 * hlf + k4]);
+                    w[4 * k4 + 0] = (uint32_t)xr;
+                    w[4 * k4 + 1] = (uint32_t)(xr >> 32);
+                    w[4 * k4 + 2] = (uint32_t)xi;
+                    w[4 * k4 + 3] = (uint32_t)(xi >> 32);
+                }
+                pw_tmem_st16(tmail_own + 16u * (uint32_t)hlf, w);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         wfft::Monomials mo;
         wfft::monomials_init(mo, omega, a_tilde[2 * i], a_tilde[2 * i + 1], u);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         WIDE_TICK(2)
         // ---- pointwise stage
         double gre[8], gim[8];
@@ -173,7 +214,15 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
         for (int q = 0; q < wfft::SLICES_PER_STEP; ++q) {     // two bins (one ring slice) per turn
             const int sidx = i * wfft::SLICES_PER_STEP + q;
             const int slot = sidx % PW_SLOTS;
-            const cplx fo0 = o0[(2 * q) * wfft::WT + u], fo1 = o0[(2 * q + 1) * wfft::WT + u];
+            cplx fo0, fo1;
+            {
+                uint32_t w[8];
+                pw_tmem_ld8(tmail_oth + 8u * (uint32_t)q, w);      // the other polynomial's bins 2q, 2q + 1 of this thread
+                fo0.x = __longlong_as_double((long long)(((unsigned long long)w[1] << 32) | w[0]));
+                fo0.y = __longlong_as_double((long long)(((unsigned long long)w[3] << 32) | w[2]));
+                fo1.x = __longlong_as_double((long long)(((unsigned long long)w[5] << 32) | w[4]));
+                fo1.y = __longlong_as_double((long long)(((unsigned long long)w[7] << 32) | w[6]));
+            }
             cplx fa0, fa1;
             fa0.x = re[2 * q]; fa0.y = im[2 * q];
             fa1.x = re[2 * q + 1]; fa1.y = im[2 * q + 1];
@@ -201,8 +250,10 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
 #endif
         }
         WIDE_TICK(3)
-        wfft::inv_stage3(u, gre, gim, e1);
+        wfft::inv_stage3(u, gre, gim, e0);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         WIDE_TICK(4)                               // also: nobody reads the published spectra any more
         // Phase offset between the two polynomials.  Their warps run every phase of a step in lock step (load burst,
         // arithmetic, store burst, barrier), so the shared-memory pipe and the FP64 pipe take turns.  Holding polynomial 1
@@ -215,10 +266,10 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
             const long long t0 = clock64();
             while (clock64() - t0 < WIDE_SKEW) { }
         }
-        wfft::inv_stage2(tw, u, e1, e0);
+        wfft::inv_stage2(tw, u, e0, e1);
         pw_bar_poly(t);
         WIDE_TICK(5)
-        wfft::inv_stage1(tw, u, e0, re, im);
+        wfft::inv_stage1(tw, u, e1, re, im);
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
             acc_re[a] += wfft::f64_to_torus_u64(re[a]);
@@ -247,6 +298,9 @@ pbs_kernel_mb2_wide(const cplx* __restrict__ bskf2, const uint64_t* __restrict__
             }
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) pw_tmem_dealloc(*tmem_slot, 64);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

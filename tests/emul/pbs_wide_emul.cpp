@@ -93,7 +93,10 @@ static int emul_wide_impl(const double* key_blocks, const double* key_cols, cons
             th[t][u].acc_re[a] = v0; th[t][u].acc_im[a] = v1;
         }
     }
-    // exchange buffers [t][2], poisoned so that a read of something never written shows
+    // exchange buffers [t][2] (e0: forward stage 1 / inverse stage 3, e1: forward stage 2 / inverse stage 2) and the spectrum
+    // mailbox [t] (tensor memory in the kernel), poisoned so that a read of something never written shows
+    std::vector<cplx> mail[2] = {std::vector<cplx>(1024), std::vector<cplx>(1024)};
+    for (int t = 0; t < 2; ++t) for (auto& e : mail[t]) e.x = e.y = NAN;
     std::vector<cplx> xbuf[2][2];
     for (int t = 0; t < 2; ++t) for (int q = 0; q < 2; ++q) { xbuf[t][q].resize(XBUF_ELEMS); for (auto& e : xbuf[t][q]) e.x = e.y = NAN; }
     const int pairs = n / 2;
@@ -104,13 +107,13 @@ static int emul_wide_impl(const double* key_blocks, const double* key_cols, cons
         // ---- segment A: [inverse stage 2 | bar t | inverse stage 1 + accumulate of step i-1] -> stage 1 | bar t | stage 2 | bar t | stage 3 + publish
         for (int pi = 0; pi < 2; ++pi) {
             const int t = polys[pi];
-            cplx* e0 = xbuf[t][i & 1].data();           // the kernel's e0 / e1 of step i
-            cplx* e1 = xbuf[t][1 - (i & 1)].data();
-            if (i > 0) {    // inverse stage 2 of step i-1: its e1 is this step's e0 and vice versa
+            cplx* e0 = xbuf[t][0].data();
+            cplx* e1 = xbuf[t][1].data();
+            if (i > 0) {    // inverse stage 2 of step i-1
                 FOR_THREADS(t) inv_stage2(T.tw, u, e0, e1); END_THREADS   // bar t
             }
             FOR_THREADS(t)
-                if (i > 0) {    // e0 of step i-1 == e1 of step i
+                if (i > 0) {
                     inv_stage1(T.tw, u, e1, T.re, T.im);
                     for (int a = 0; a < 8; ++a) { T.acc_re[a] += f64_to_torus_u64(T.re[a]); T.acc_im[a] += f64_to_torus_u64(T.im[a]); }
                 }
@@ -126,7 +129,7 @@ static int emul_wide_impl(const double* key_blocks, const double* key_cols, cons
             FOR_THREADS(t) fwd_stage2(T.tw, u, e0, e1); END_THREADS   // bar t
             FOR_THREADS(t)
                 fwd_stage3(u, e1, T.re, T.im);
-                for (int kL = 0; kL < 8; ++kL) { cplx v; v.x = T.re[kL]; v.y = T.im[kL]; e0[kL * WT + u] = v; }
+                for (int kL = 0; kL < 8; ++kL) { cplx v; v.x = T.re[kL]; v.y = T.im[kL]; mail[t][kL * WT + u] = v; }
                 monomials_init(T.mo, omega.data(), a_tilde[2 * i], a_tilde[2 * i + 1], u);
             END_THREADS
         }
@@ -135,8 +138,8 @@ static int emul_wide_impl(const double* key_blocks, const double* key_cols, cons
         const cplx* key_pair = key_blocks ? reinterpret_cast<const cplx*>(key_blocks) + (size_t)i * 32 * MB2_BLOCK_ELEMS : nullptr;
         for (int pi = 0; pi < 2; ++pi) {
             const int t = polys[pi];
-            const cplx* o0 = xbuf[1 - t][i & 1].data();
-            cplx* e1 = xbuf[t][1 - (i & 1)].data();
+            const cplx* o0 = mail[1 - t].data();
+            cplx* e0 = xbuf[t][0].data();
             FOR_THREADS(t)
                 for (int kL = 0; kL < 8; ++kL) {
                     const cplx fo = o0[kL * WT + u];
@@ -154,7 +157,7 @@ static int emul_wide_impl(const double* key_blocks, const double* key_cols, cons
                         T.gim[kL] = fma(fo.x, st.y, fma(fo.y, st.x, pim));
                     }
                 }
-                inv_stage3(u, T.gre, T.gim, e1);
+                inv_stage3(u, T.gre, T.gim, e0);
             END_THREADS
         }
         // ---- __syncthreads; the rest of the step (inverse stage 2 | bar t | inverse stage 1 + accumulate) runs into the next
