@@ -1035,11 +1035,11 @@ cudaError_t launch_pbs_mb2(const fhe_b200_pbs_params& p, const double* d_bskf2, 
     // Three kernels share a batch (measured on B200, profiles/r2_pbs_wide_times.txt):
     //   pbs_kernel_mb2<1,4>  four ciphertexts per CTA, two fat warps each: a full wave of 4 x SMs ciphertexts takes 5.47 ms
     //                        (108 k PBS/s) -- the throughput kernel;
-    //   pbs_kernel_mb2_wide  one ciphertext per CTA, eight warps (pbs_wide.cu): a wave of SMs ciphertexts takes 1.60 ms
-    //                        (92 k PBS/s) -- the latency kernel;
+    //   pbs_kernel_mb2_wide  one ciphertext per CTA, eight warps (pbs_wide.cu): a wave of SMs ciphertexts takes 1.55 ms
+    //                        (96 k PBS/s) -- the latency kernel;
     //   pbs_kernel_mb2_pair  one ciphertext per cluster of two CTAs (pbs_wide.cu): SMs / 2 ciphertexts in 1.28 ms.
     // Full waves of 4 x SMs go to the first; what is left goes to the second while it needs at most three of its waves
-    // (3 x 1.60 < 5.47), so no batch size pays for a mostly empty wave of four-ciphertext CTAs -- and to the third
+    // (3 x 1.55 < 5.47), so no batch size pays for a mostly empty wave of four-ciphertext CTAs -- and to the third
     // when there are two SMs for every remaining ciphertext.
     const int64_t wave4 = (int64_t)MB2_L1_NCT * sm_count;
     int64_t full = (B / wave4) * wave4;

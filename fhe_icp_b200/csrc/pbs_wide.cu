@@ -7,13 +7,13 @@
 // (a = 0..7) of polynomial t IN REGISTERS (16 torus words) and, in the Fourier domain, the bins k = u + 128 kL of
 // output polynomial t.  Twiddles are per-thread constants of the launch, held in registers.
 //
-// Shared memory: two exchange buffers per polynomial (17 KB each), written alternately -- a step has five exchanges
+// Shared memory: two exchange buffers per polynomial (17 KB each) with fixed roles -- e0: forward stage 1 and inverse
+// stage 3, e1: forward stage 2 and inverse stage 2:
 //   stage1 -> [bar t] -> stage2 -> [bar t] -> stage3, spectrum -> [bar all] -> pointwise, inverse stage3 -> [bar all] ->
 //   inverse stage2 -> [bar t] -> inverse stage1, accumulate
-// and because five is odd the alternation simply continues into the next step: a buffer is rewritten only after a
-// barrier that every one of its readers has passed (the two 256-thread barriers are the ones around the pointwise
-// stage, where each polynomial reads the other's spectrum).  tests/emul/pbs_wide_emul.cpp replays this plan in several
-// thread orders.
+// so a buffer is rewritten only after a barrier that every one of its readers has passed.  The spectrum itself -- the one
+// thing the two polynomials exchange -- goes through TENSOR MEMORY (a lane-aligned mailbox, see the kernel) between the
+// two 256-thread barriers.  tests/emul/pbs_wide_emul.cpp replays this plan in several thread orders.
 //
 // Key stream: the Fourier key of fhe_b200_bsk2_to_fourier as it is ([pair][32 frequency blocks][384 complex]).  Ring
 // slice q of a step is the eight consecutive blocks 8q .. 8q + 7 (48 KB, ONE bulk copy: a bulk copy takes ~1200 clocks
