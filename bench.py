@@ -504,24 +504,32 @@ def sharded_steps(R: Ranks, model, rows_fn, total_docs: int, fmt: str, steps: in
             "shards": [h - l for l, h in spans], "client_rho": rho, "X": X, "wire32": wire32}
 
 
-def e2e_single_gpu(model, X, steps):
-    """FHESimilarityModel.predict_encrypted with host float32 rows in / float64 scores out + host top-k."""
+def e2e_single_gpu(model, X, steps, blocks=5):
+    """FHESimilarityModel.predict_encrypted with host float32 rows in / float64 scores out + host top-k.
+    The call takes ~0.36 ms, so ONE host hiccup (a descheduled thread, a page fault) inside a 10-call loop moves the figure
+    by tens of percent (2.0 vs 2.8 M/s were both seen on the pool's boxes).  The loop is therefore timed in `blocks`
+    blocks of `steps` calls and the MEDIAN block is reported; every block's figure is kept in the record."""
     import torch
     from fhe_icp_b200._native import pinned_copy
     c = model.model.fhe_circuit
-    res = {}
+    res, per_block = {}, {}
     X = pinned_copy(np.ascontiguousarray(X, dtype=np.float32))    # the step's inputs sit in pinned host memory
     for fmt in ("expanded", "seeded"):        # seeded (the default format) last: its ranking is the one checked
         c.ciphertext_format = fmt
-        for _ in range(2):
+        for _ in range(3):
             model.predict_encrypted(X)
-        torch.cuda.synchronize()
-        w0 = time.perf_counter()
-        for _ in range(steps):
-            sc = model.predict_encrypted(X)
-            hits = top_k(sc, 3, -np.inf)
-        torch.cuda.synchronize()
-        res[fmt] = len(X) * steps / (time.perf_counter() - w0)
+        vals = []
+        for _ in range(blocks):
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            for _ in range(steps):
+                sc = model.predict_encrypted(X)
+                hits = top_k(sc, 3, -np.inf)
+            torch.cuda.synchronize()
+            vals.append(len(X) * steps / (time.perf_counter() - w0))
+        res[fmt] = float(np.median(vals))
+        per_block[fmt] = [float(v) for v in vals]
+    res["blocks"] = per_block
     return res, hits
 
 
@@ -686,13 +694,16 @@ def run_b200_arm(args):
     X = res.pop("X")
 
     # --- e2e: host buffers in, ranked ids out
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
     if world == 1 and wl == "config2":
         e2e_vals, hits = e2e_single_gpu(model, X, e2e_steps)
         assert [i for i, _ in hits] == [i for i, _ in top_k(model.predict_clear(X), 3, -np.inf)], \
             "top-k ranking differs from the clear circuit"
         e2e = {"value": e2e_vals["seeded"], "unit": UNIT, "h2d_bytes_per_step": int(len(X) * D_FEATURES * 4),
                "d2h_bytes_per_step": int(len(X) * 16), "steps": e2e_steps,
+               "timing": f"median of {len(e2e_vals['blocks']['seeded'])} timed blocks of {e2e_steps} calls each (wall clock, "
+                         "synchronised on both sides of a block)",
+               "blocks": e2e_vals["blocks"]["seeded"],
                "call": "fhe_b200_similarity_predict_host_seeded (FHESimilarityModel.predict_encrypted, default "
                        "ciphertext_format='seeded') + host top-k",
                "expanded_ciphertexts_value": e2e_vals["expanded"]}
