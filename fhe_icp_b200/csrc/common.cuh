@@ -258,6 +258,15 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                      smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// The same sum (mod 2^64) with three REDUX instructions instead of five dependent shuffle rounds: the word is cut into
+// limbs of 22 / 22 / 20 bits, whose 32-lane sums fit 32 bits, and the three hardware reductions are independent.
+__device__ __forceinline__ uint64_t warp_sum_u64_redux(uint64_t v) {
+    const uint32_t a = (uint32_t)v & 0x3fffffu, b = (uint32_t)(v >> 22) & 0x3fffffu, c = (uint32_t)(v >> 44);
+    const uint64_t sa = __reduce_add_sync(0xffffffffu, a), sb = __reduce_add_sync(0xffffffffu, b),
+                   sc = __reduce_add_sync(0xffffffffu, c);
+    return sa + (sb << 22) + (sc << 44);
+}
+
 __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -493,7 +493,7 @@ lwe_encrypt_seeded_kernel(const uint8_t* __restrict__ key, int n, int64_t count,
         for (int i = lane; i < n_lo; i += 32) mask_block_sum<1>(acc, K, l_lo[i], y1, q_hi, q_lo);
 #pragma unroll ENC_SEEDED_UNROLL_N
         for (int i = lane; i < n_hi; i += 32) mask_block_sum<2>(acc, K, l_hi[i], y1, q_hi, q_lo);
-        const uint64_t dot = warp_sum_u64(acc.value());
+        const uint64_t dot = warp_sum_u64_redux(acc.value());
         if (lane == 0) bodies[c] = pre + dot;
     }
 }
