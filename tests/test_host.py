@@ -215,3 +215,41 @@ def test_published_circuit_bit_widths(n_bits, published):
     assert model.fhe_circuit.graph.maximum_integer_bit_width() == published
     # the sizing input stays separate: only encrypted values enter the parameter selection
     assert circuit.inputset_bits == published - 2 and circuit.guaranteed_bits >= circuit.inputset_bits
+
+
+def test_quantized_circuit_obeys_affine_quantization_algebra():
+    """Checks of the quantizer and of the integer circuit that do not go through oracle/oracle.py (whose restatement of
+    SURVEY Appendix A is necessarily close to the product's): they follow from what affine quantization IS.
+    (1) the calibration range maps onto the whole integer range, monotonically, and dequant(quant(x)) is within half a
+    step of x inside the range; (2) the integer circuit equals the real-valued dot product of the DEQUANTIZED operands
+    plus the intercept up to the rounding of the bias: |y - (X_deq @ W_deq + b)| <= s_X s_W / 2; (3) the exact rational
+    value of the circuit (fractions, no floating point) agrees with (2)."""
+    from fractions import Fraction
+    from fhe_icp_b200.quantization import QuantizedLinearSpec, UniformQuantizer
+    rng = np.random.default_rng(12)
+    for n_bits in (2, 4, 8, 12):
+        for trial in range(6):
+            d = int(rng.integers(1, 40))
+            X = rng.normal(scale=rng.choice([1e-3, 0.1, 3.0]), size=(50, d)) + rng.normal()
+            coef = rng.normal(scale=rng.choice([1e-2, 1.0, 7.0]), size=d)
+            b = float(rng.normal())
+            q = UniformQuantizer.from_values(X, n_bits)
+            lo, hi = X.min(), X.max()
+            assert q.quant(np.array([lo]))[0] == q.qmin and q.quant(np.array([hi]))[0] == q.qmax
+            xs = np.sort(rng.uniform(lo, hi, size=400))
+            qx = q.quant(xs)
+            assert np.all(np.diff(qx) >= 0)
+            assert np.max(np.abs(q.dequant(qx) - xs)) <= q.scale * (0.5 + 1e-9)
+            spec = QuantizedLinearSpec.from_fit(coef, b, X, n_bits)
+            Xt = rng.uniform(lo, hi, size=(20, d))
+            qX = spec.input_q.quant(Xt)
+            X_deq = spec.input_q.dequant(qX)
+            W_deq = spec.weight_q.dequant(spec.q_weights)
+            y = spec.predict_clear(Xt)
+            s = spec.input_q.scale * spec.weight_q.scale
+            assert np.max(np.abs(y - (X_deq @ W_deq + b))) <= s * 0.5 + 1e-9 * max(1.0, np.abs(y).max())
+            # exact rational evaluation of the first row
+            sx, sw = Fraction(spec.input_q.scale), Fraction(spec.weight_q.scale)
+            exact = sum(sx * (int(a) - spec.input_q.zero_point) * sw * (int(w) - spec.weight_q.zero_point)
+                        for a, w in zip(qX[0], spec.q_weights))
+            assert abs(float(exact) + b - y[0]) <= float(sx * sw) * 0.5 + 1e-9 * max(1.0, abs(y[0]))
