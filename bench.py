@@ -749,6 +749,14 @@ def run_b200_arm(args):
             del m5, c5
             torch.cuda.empty_cache()
 
+    # --- keyswitch + PBS over one batch sharded across the ranks (the metric's "PBS/sec at 1/2/4/8 B200"): every rank takes part
+    pbs_sharded = None
+    if not args.no_extras:
+        from fhe_icp_b200 import pbs_bench as _pbs_bench
+        torch.cuda.empty_cache()
+        pbs_sharded = _pbs_bench.measure_sharded(R, dev, args)
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -782,6 +790,9 @@ def run_b200_arm(args):
         except Exception:
             args._bf16_peak = None
         line["pbs"] = pbs_bench.measure(dev, args)
+        line["pbs_sharded"] = pbs_sharded
+        if world == 1 and not args.no_cpu_baseline:
+            line["pbs"]["cpu_baseline"] = cpu_pbs_reference(line["pbs"]["params"])
         if world == 1:
             pair = pbs_bench.measure_pair(dev, args)
             sample = pair.pop("_sample")
@@ -799,6 +810,38 @@ def run_b200_arm(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def cpu_pbs_reference(params, per_thread: int = 16):
+    """CPU baseline of configs[2] (keyswitch + PBS at the stated set): the oracle port, OpenMP over the host cores, on a
+    bounded batch (``per_thread`` ciphertexts per thread), multi-bit blind rotation like the GPU path; every output is
+    decrypted and compared with the table."""
+    import numpy as np
+    from oracle import oracle as O
+    op = O.make_params(n=params["n"], k=params["k"], N=params["N_poly"], l_pbs=params["l_pbs"],
+                       beta_pbs=params["beta_pbs"], l_ks=params["l_ks"], beta_ks=params["beta_ks"],
+                       log2_sigma_lwe=params["log2_sigma_lwe"], log2_sigma_glwe=params["log2_sigma_glwe"])
+    s, S = O.secret_key(101, 0, op.n), O.secret_key(101, 1, op.k * op.N)
+    ksk = O.ksk_gen(op, S, s, 202)
+    bskf2 = O.bsk2_to_fourier(op, O.bsk2_gen(op, s, S, 202))
+    B = per_thread * O.num_threads()
+    msgs = np.random.RandomState(B).randint(0, 16, size=B)
+    table = (np.arange(16) * 7 + 3) % 16
+    lut = O.make_lut_poly(table, 4, op.N, 59)
+    ct = O.lwe_encrypt(S, msgs, 59, op.sigma_glwe_abs, 303, ct_base=0, stride=op.N + 2)[:, : op.N + 1]
+    O.pbs_mb2(op, bskf2, O.keyswitch(op, ksk, ct[: O.num_threads()]), lut)      # warm-up (thread pool, key pages)
+    t0 = time.perf_counter()
+    small = O.keyswitch(op, ksk, ct)
+    t1 = time.perf_counter()
+    out = O.pbs_mb2(op, bskf2, small, lut)
+    t2 = time.perf_counter()
+    pad = np.zeros((B, op.N + 2), dtype=np.uint64)
+    pad[:, : op.N + 1] = out
+    ok = bool(np.array_equal(O.lwe_decrypt(S, pad, 59) & 15, table[msgs]))
+    return {"value": B / (t2 - t0), "unit": "keyswitch+PBS/s", "pbs_per_sec": B / (t2 - t1), "cores": O.num_threads(),
+            "kind": "port", "all_correct": ok,
+            "sample": f"{B} ciphertexts: keyswitch {t1 - t0:.2f} s + multi-bit PBS {t2 - t1:.2f} s, oracle/fhe_oracle.c (OpenMP; a "
+                      "plain radix-2 f64 FFT restatement, not a tuned CPU library)"}
 
 
 def cpu_pair_reference(params, sm):

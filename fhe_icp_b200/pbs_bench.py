@@ -312,3 +312,103 @@ def _pad(out):
     z = torch.zeros((B, w + 1), dtype=out.dtype, device=out.device)
     z[:, :w] = out
     return z
+
+
+def measure_sharded(R, dev, args, total: int = 65536, per_gpu: int = 4736):
+    """BASELINE.json's "PBS/sec at 1/2/4/8 B200": keyswitch + PBS over ONE batch cut into contiguous ranges, one per GPU
+    (sharded_search.ShardedBootstrap).  The client rank (0) owns the secret keys, generates the evaluation keys and
+    broadcasts them once over NCCL (timed); the server ranks hold nothing else.  The data path has no collective:
+    ciphertexts are independent, rank r receives its rows, runs the tensor-core keyswitch and the multi-bit blind
+    rotation, and sends the outputs back.  Two workloads: configs[2]'s upper end (``total`` ciphertexts, strong scaling)
+    and ``per_gpu`` ciphertexts per GPU (weak).  Kernel time is CUDA events on every rank, max over ranks; the round trip
+    (scatter + evaluate + collect on the client) is wall clock between barriers, max over ranks.  Every output is
+    decrypted on the client and compared with the table.  Called on EVERY rank."""
+    import time
+    import torch
+    from . import engine as E
+    from .sharded_search import BootstrapEngine, ShardedBootstrap, broadcast_keys
+    d = dict(PBS_PARAMS_4BIT)
+    p = E.make_pbs_params(**d)
+    client = R.rank == 0
+    S = None
+    if client:
+        s, S = E.secret_key(101, 0, p.n, dev), E.secret_key(101, 1, p.k * p.N, dev)
+        key_mma = E.ksk_to_mma(p, E.ksk_to_32(p, E.ksk_gen(p, S, s, 202)))
+        bskf2 = E.bsk2_to_fourier(p, E.bsk2_gen(p, s, S, 202))
+        eng = BootstrapEngine(d, dev, key_mma, bskf2)
+    else:
+        eng = BootstrapEngine(d, dev)          # parameter set only: no secret key on a server rank
+    sb = ShardedBootstrap(eng, client_rank=0, device=dev)
+    # the key broadcast once more, alone, between device events (the first one carried NCCL's lazy channel setup)
+    torch.cuda.synchronize()
+    R.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    broadcast_keys(eng.key_tensors(), 0)
+    e1.record()
+    torch.cuda.synchronize()
+    bcast_ms = R.max_over_ranks(e0.elapsed_time(e1))
+    table = (np.arange(16) * 7 + 3) % 16
+    lut = E.from_u64_numpy(E.make_lut_poly(table, 4, p.N, 59), dev)
+    flops = flops_per_pbs(p.n, p.k, p.N, p.l_pbs)
+    fp64_peak = None
+    if client:
+        from . import _native as N_
+        fp64_peak = N_.context(dev.index).probe_fp64_tflops()
+    rows = []
+    for label, B in (("strong", int(total)), ("weak", int(per_gpu) * R.world)):
+        ct_big, msgs = None, None
+        if client:
+            msgs = np.random.RandomState(B).randint(0, 16, size=B)
+            ct_big = E.lwe_encrypt(S, torch.as_tensor(msgs), 59, p.sigma_glwe_abs, enc_seed=303, ct_base=B * 7919,
+                                   stride=p.N + 2)[:, : p.N + 1].contiguous()
+        _, mine, _ = sb.scatter(ct_big)
+        eng.bootstrap(mine, lut)                       # warm-up (first touch of the keys into this GPU's L2)
+        torch.cuda.synchronize()
+        R.barrier()
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            eng.bootstrap(mine, lut)
+        e1.record()
+        torch.cuda.synchronize()
+        kern_ms = R.max_over_ranks(e0.elapsed_time(e1) / reps)
+        full = sb.evaluate(ct_big, lut)               # warm-up of the whole round trip (buffers, NCCL's lazy p2p channels)
+        del full
+        torch.cuda.synchronize()
+        trips = 2
+        R.barrier()
+        w0 = time.perf_counter()
+        for _ in range(trips):
+            full = sb.evaluate(ct_big, lut)
+        torch.cuda.synchronize()
+        trip_ms = R.max_over_ranks((time.perf_counter() - w0) * 1e3 / trips)
+        ok = None
+        if client:
+            z = torch.zeros((B, p.N + 2), dtype=torch.int64, device=dev)
+            z[:, : p.N + 1] = full
+            ok = bool(np.array_equal(E.lwe_decrypt(S, z, 59).cpu().numpy() & 15, table[msgs]))
+            assert ok, "sharded keyswitch + PBS: a decrypted output differs from the table"
+            del z
+        rows.append({"scaling": label, "batch_total": B, "per_rank": [sb.bounds(B, r)[1] - sb.bounds(B, r)[0] for r in range(R.world)],
+                     "ks_pbs_ms": kern_ms, "ks_pbs_per_sec": B / (kern_ms * 1e-3),
+                     "round_trip_ms": trip_ms, "round_trip_per_sec": B / (trip_ms * 1e-3),
+                     "fp64_tflops": flops * B / (kern_ms * 1e-3) / 1e12,
+                     "frac_of_fp64_term": (flops * B / (kern_ms * 1e-3) / 1e12) / (fp64_peak * R.world) if fp64_peak else None,
+                     "all_correct": ok})
+        del full, mine, ct_big
+        torch.cuda.empty_cache()
+    if not client:
+        return None
+    return {"metric": "ks_pbs_per_sec", "unit": "keyswitch+PBS/s", "n_gpus": R.world, "value": rows[0]["ks_pbs_per_sec"],
+            "workloads": rows,
+            "key_broadcast": None if R.world == 1 else
+                             {"bytes": sb.key_bytes, "ms": bcast_ms, "gb_per_s": sb.key_bytes / (bcast_ms * 1e-3) / 1e9,
+                              "what": "tensor-core keyswitch key (int8 MMA blocks) + multi-bit Fourier bootstrapping key, "
+                                      "dist.broadcast over NCCL from the client rank, once per key set"},
+            "data_path": "no collective: the client sends rank r its contiguous rows (point-to-point), every rank runs "
+                         "fhe_b200_keyswitch_mma + fhe_b200_pbs_mb2 on them, outputs return point-to-point; "
+                         "ks_pbs_ms is device time of those two calls (CUDA events, max over ranks), round_trip_ms adds "
+                         "the transfers (wall clock between barriers, max over ranks)",
+            "server_ranks_hold": "evaluation keys only (no secret key)",
+            "all_correct": all(r["all_correct"] for r in rows)}

@@ -534,3 +534,120 @@ class ShardedPackedSearch:
         if ints is None:
             return None
         return rank_results(self.doc_ids, self.engine.dequantize(ints), top_k, min_similarity)
+
+
+class ShardedBootstrap:
+    """Keyswitch + programmable bootstrap (the atomic pattern) over a batch of ciphertexts cut into
+    contiguous ranges, one per rank (BASELINE.json: "PBS/sec at 1/2/4/8 B200", "the bootstrapping and
+    keyswitch keys are broadcast once via NCCL over NVLink, each rank evaluates its shard").
+
+    Ciphertexts are independent units, so the data path has NO collective: the client rank sends rank r its rows
+    (point-to-point), every rank runs keyswitch + blind rotation on what it received, and the outputs travel back the same
+    way.  Once, at construction, the client broadcasts the evaluation keys; server ranks hold nothing else.
+
+    ``engine``: on the client ``key_tensors()`` returns the evaluation keys (device tensors); on every rank
+    ``adopt_keys(list)`` installs them and ``bootstrap(ct, luts, lut_index)`` maps ``[rows, kN+1]`` big-key ciphertexts to
+    ``[rows, kN+1]`` bootstrapped ones.  ``device`` is where this rank's buffers live."""
+
+    def __init__(self, engine, client_rank: int = 0, device=None):
+        self.engine = engine
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.client_rank = client_rank
+        self.dev = torch.device(device) if device is not None else torch.device("cpu")
+        self.key_bytes = 0
+        self._distribute_keys()
+
+    def _distribute_keys(self):
+        e = self.engine
+        is_client = self.rank == self.client_rank
+        keys = list(e.key_tensors()) if is_client else None
+        meta = broadcast_public_material([(tuple(t.shape), t.dtype) for t in keys] if is_client else None, self.client_rank)
+        if not is_client:
+            keys = [torch.empty(shape, dtype=dtype, device=self.dev) for shape, dtype in meta]
+        self.key_bytes = int(sum(t.numel() * t.element_size() for t in keys))
+        broadcast_keys(keys, self.client_rank)
+        e.adopt_keys(keys)
+
+    def bounds(self, B: int, r: int) -> Tuple[int, int]:
+        return shard_bounds(B, self.world, r)
+
+    def scatter(self, ct: Optional[torch.Tensor], lut_index: Optional[torch.Tensor] = None):
+        """Client: ``ct [B, words]`` (and optionally one table index per ciphertext).  Returns this rank's rows."""
+        is_client = self.rank == self.client_rank
+        meta = broadcast_public_material((int(ct.shape[0]), int(ct.shape[1]), lut_index is not None) if is_client else None,
+                                         self.client_rank)
+        B, words, has_index = meta
+        lo, hi = self.bounds(B, self.rank)
+        if is_client:
+            for r in range(self.world):
+                a, b = self.bounds(B, r)
+                if r == self.rank or a == b:
+                    continue
+                dist.send(ct[a:b].contiguous(), dst=r)
+                if has_index:
+                    dist.send(lut_index[a:b].to(torch.int32).contiguous(), dst=r)
+            return B, ct[lo:hi], (lut_index[lo:hi] if has_index else None)
+        mine = torch.empty((hi - lo, words), dtype=torch.int64, device=self.dev)
+        idx = torch.empty(hi - lo, dtype=torch.int32, device=self.dev) if has_index else None
+        if hi > lo:
+            dist.recv(mine, src=self.client_rank)
+            if has_index:
+                dist.recv(idx, src=self.client_rank)
+        return B, mine, idx
+
+    def collect(self, B: int, out: torch.Tensor) -> Optional[torch.Tensor]:
+        """Every rank's outputs back on the client, in the order of the batch (None elsewhere)."""
+        if self.rank != self.client_rank:
+            if out.shape[0]:
+                dist.send(out.contiguous(), dst=self.client_rank)
+            return None
+        if self.world == 1:
+            return out
+        full = torch.empty((B, out.shape[1]), dtype=out.dtype, device=out.device)
+        lo, hi = self.bounds(B, self.rank)
+        full[lo:hi] = out
+        for r in range(self.world):
+            a, b = self.bounds(B, r)
+            if r != self.rank and b > a:
+                dist.recv(full[a:b], src=r)
+        return full
+
+    def evaluate(self, ct: Optional[torch.Tensor], luts: torch.Tensor, lut_index: Optional[torch.Tensor] = None):
+        """Client: the bootstrapped batch ``[B, kN+1]``; server ranks: None.  ``luts`` (public) is passed on every rank."""
+        B, mine, idx = self.scatter(ct, lut_index)
+        out = self.engine.bootstrap(mine, luts, idx)
+        return self.collect(B, out)
+
+
+class BootstrapEngine:
+    """What :class:`ShardedBootstrap` drives on a GPU: the tensor-core keyswitch followed by the multi-bit blind rotation
+    (``fhe_b200_keyswitch_mma`` + ``fhe_b200_pbs_mb2``).  The client builds it from its evaluation keys; a server rank
+    builds it from the public parameter set alone and receives the keys by broadcast."""
+
+    def __init__(self, params: dict, device, key_mma: Optional[torch.Tensor] = None, bskf2: Optional[torch.Tensor] = None):
+        from . import engine as E
+        self.E = E
+        self.p = E.make_pbs_params(**params)
+        self.dev = torch.device(device)
+        self.key_mma, self.bskf2 = key_mma, bskf2
+        self._work = None
+
+    def key_tensors(self):
+        return [self.key_mma, self.bskf2]
+
+    def adopt_keys(self, keys):
+        self.key_mma, self.bskf2 = keys
+
+    def bootstrap(self, ct: torch.Tensor, luts: torch.Tensor, lut_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+        E, p = self.E, self.p
+        rows = ct.shape[0]
+        if rows == 0:
+            return torch.empty((0, p.k * p.N + 1), dtype=torch.int64, device=self.dev)
+        import ctypes as C
+        from . import _native as N
+        need = int(N.lib().fhe_b200_keyswitch_mma_workspace_bytes(C.byref(p), rows))
+        if self._work is None or self._work.numel() < need:
+            self._work = torch.empty(need, dtype=torch.int8, device=self.dev)
+        small = E.keyswitch_mma(p, self.key_mma, ct, work=self._work)
+        return E.pbs_mb2(p, self.bskf2, small, luts, lut_index)

@@ -376,3 +376,37 @@ def test_full_size_batch_keyswitch_pbs_composition(cuda_dev):
     assert np.array_equal(E.lwe_decrypt(S, z, 59).cpu().numpy() & 15, t1[msgs[:nsub]])   # another kernel: the same values
     out2 = E.pbs_mb2(p, bskf2, E.keyswitch_mma(p, key_mma, out1, work=work), lut2)
     assert np.array_equal(dec(out2), t2[t1[msgs]])
+
+
+def test_sharded_bootstrap_on_one_rank_equals_the_direct_calls(cuda_dev):
+    """sharded_search.ShardedBootstrap / BootstrapEngine (what bench.py's pbs_sharded record drives at N GPUs; the two-rank
+    plumbing is tests/test_sharded_search.py::test_sharded_bootstrap_world2): on one rank it returns exactly the words of
+    fhe_b200_keyswitch_mma + fhe_b200_pbs_mb2, per-ciphertext tables included, and a key-less engine that adopts the
+    evaluation keys computes the same."""
+    import torch
+    from fhe_icp_b200 import engine as E
+    from fhe_icp_b200.sharded_search import BootstrapEngine, ShardedBootstrap
+    dev = cuda_dev
+    p = E.make_pbs_params(**P4)
+    s, S = E.secret_key(41, 0, p.n, dev), E.secret_key(41, 1, p.k * p.N, dev)
+    key_mma = E.ksk_to_mma(p, E.ksk_to_32(p, E.ksk_gen(p, S, s, 42)))
+    bskf2 = E.bsk2_to_fourier(p, E.bsk2_gen(p, s, S, 42))
+    B = 37
+    rng = np.random.RandomState(3)
+    msgs, which = rng.randint(0, 16, size=B), rng.randint(0, 2, size=B)
+    tables = np.stack([(np.arange(16) * 7 + 3) % 16, (np.arange(16) * 5 + 1) % 16])
+    luts = torch.stack([E.from_u64_numpy(E.make_lut_poly(t, 4, p.N, 59), dev) for t in tables])
+    idx = torch.as_tensor(which, dtype=torch.int32, device=dev)
+    ct = E.lwe_encrypt(S, torch.as_tensor(msgs), 59, p.sigma_glwe_abs, enc_seed=43, stride=p.N + 2)[:, : p.N + 1].contiguous()
+    eng = BootstrapEngine(P4, dev, key_mma, bskf2)
+    sb = ShardedBootstrap(eng, client_rank=0, device=dev)
+    assert sb.key_bytes == key_mma.numel() * key_mma.element_size() + bskf2.numel() * bskf2.element_size()
+    out = sb.evaluate(ct, luts, idx)
+    assert torch.equal(out, E.pbs_mb2(p, bskf2, E.keyswitch_mma(p, key_mma, ct), luts, idx))
+    z = torch.zeros((B, p.N + 2), dtype=torch.int64, device=dev)
+    z[:, : p.N + 1] = out
+    assert np.array_equal(E.lwe_decrypt(S, z, 59).cpu().numpy() & 15, tables[which, msgs])
+    server = BootstrapEngine(P4, dev)
+    server.adopt_keys(eng.key_tensors())
+    assert torch.equal(server.bootstrap(ct, luts, idx), out)
+    assert server.bootstrap(ct[:0], luts).shape == (0, p.k * p.N + 1)

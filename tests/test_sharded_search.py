@@ -348,6 +348,89 @@ def test_sharded_packed_search_world2(n_docs):
     assert ret["res"] == rank_results([f"doc_{i}" for i in range(n_docs)], eng.dequantize(clear), 4, -100.0)
 
 
+BOOT_TOY = dict(n=24, k=1, N=2048, l_pbs=1, beta_pbs=23, l_ks=5, beta_ks=3, log2_sigma_lwe=-30.0, log2_sigma_glwe=-51.6)
+
+
+class OracleBootstrapEngine:
+    """keyswitch + multi-bit PBS on CPU tensors via the oracle: what sharded_search.BootstrapEngine is on a GPU.
+    The client is built with the secret keys; a server rank only ever sees what key_tensors() carries."""
+
+    def __init__(self, client: bool):
+        from oracle import oracle as O
+        self.O, self.p = O, O.make_params(**BOOT_TOY)
+        self.ksk = self.bskf2 = None
+        if client:
+            self.s, self.S = O.secret_key(5, 0, self.p.n), O.secret_key(5, 1, self.p.k * self.p.N)
+            self.ksk = O.ksk_gen(self.p, self.S, self.s, 6)
+            self.bskf2 = O.bsk2_to_fourier(self.p, O.bsk2_gen(self.p, self.s, self.S, 6))
+
+    def key_tensors(self):
+        return [torch.from_numpy(self.ksk.view(np.int64)), torch.from_numpy(self.bskf2)]
+
+    def adopt_keys(self, keys):
+        self.ksk, self.bskf2 = keys[0].numpy().view(np.uint64), keys[1].numpy()
+
+    def bootstrap(self, ct, luts, lut_index=None):
+        p, O = self.p, self.O
+        if ct.shape[0] == 0:
+            return torch.empty((0, p.k * p.N + 1), dtype=torch.int64)
+        small = O.keyswitch(p, self.ksk, ct.numpy().view(np.uint64))
+        li = None if lut_index is None else lut_index.numpy()
+        return torch.from_numpy(O.pbs_mb2(p, self.bskf2, small, luts.numpy().view(np.uint64), li).view(np.int64))
+
+
+def _boot_problem(B):
+    from oracle import oracle as O
+    eng = OracleBootstrapEngine(client=True)
+    rng = np.random.RandomState(B)
+    msgs, which = rng.randint(0, 16, size=B), rng.randint(0, 2, size=B).astype(np.int32)
+    tables = np.stack([(np.arange(16) * 7 + 3) % 16, (np.arange(16) * 5 + 1) % 16])
+    luts = np.stack([O.make_lut_poly(t, 4, eng.p.N, 59) for t in tables])
+    ct = O.lwe_encrypt(eng.S, msgs, 59, eng.p.sigma_glwe_abs, 77, ct_base=0, stride=eng.p.N + 2)[:, : eng.p.N + 1]
+    return eng, msgs, which, tables, torch.from_numpy(luts.view(np.int64)), torch.from_numpy(np.ascontiguousarray(ct).view(np.int64))
+
+
+def _boot_worker(rank, world, port, B, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fhe_icp_b200.sharded_search import ShardedBootstrap
+        if rank == 0:
+            eng, msgs, which, tables, luts, ct = _boot_problem(B)
+        else:
+            eng, ct, which = OracleBootstrapEngine(client=False), None, None
+            luts = _boot_problem(B)[4]                        # the tables are public
+        sb = ShardedBootstrap(eng, client_rank=0)
+        assert rank == 0 or not hasattr(eng, "s")             # a server rank holds evaluation keys only
+        assert sb.key_bytes == sum(t.numel() * t.element_size() for t in eng.key_tensors())
+        out = sb.evaluate(ct, luts, torch.from_numpy(which) if rank == 0 else None)
+        one = sb.evaluate(ct, luts[:1])                       # one table for the whole batch, no index
+        if rank == 0:
+            ret["out"], ret["one"] = out.numpy().copy(), one.numpy().copy()
+        else:
+            assert out is None and one is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [5, 2, 1])
+def test_sharded_bootstrap_world2(B):
+    """Keyswitch + PBS over a batch cut across two ranks (ragged shards, a rank without rows): the client gets back, in
+    order, exactly the words a single process computes, and they decrypt to the chosen table's entry."""
+    from oracle import oracle as O
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_boot_worker, args=(world, port, B, ret), nprocs=world, join=True)
+    eng, msgs, which, tables, luts, ct = _boot_problem(B)
+    single = eng.bootstrap(ct, luts, torch.from_numpy(which)).numpy()
+    assert np.array_equal(ret["out"], single)
+    assert np.array_equal(ret["one"], eng.bootstrap(ct, luts[:1]).numpy())
+    pad = np.zeros((B, eng.p.N + 2), dtype=np.uint64)
+    pad[:, : eng.p.N + 1] = ret["out"].view(np.uint64)
+    assert np.array_equal(O.lwe_decrypt(eng.S, pad, 59) & 15, tables[which, msgs])
+
+
 def test_score_board_layout_and_credits():
     """Host logic of the peer score board (no GPU): slots alternate, a slot is reused only after the step
     two back was consumed, and the (slot, rank) regions of the client allocation tile it without overlap."""
