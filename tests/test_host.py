@@ -253,3 +253,46 @@ def test_quantized_circuit_obeys_affine_quantization_algebra():
             exact = sum(sx * (int(a) - spec.input_q.zero_point) * sw * (int(w) - spec.weight_q.zero_point)
                         for a, w in zip(qX[0], spec.q_weights))
             assert abs(float(exact) + b - y[0]) <= float(sx * sw) * 0.5 + 1e-9 * max(1.0, abs(y[0]))
+
+
+def test_cli_clear_mode_on_cpu_and_loud_failure_of_execute_without_a_gpu(tmp_path, capsys):
+    """The three sub-commands the reference's CLI keeps (`/root/reference/fhe_cli.py:106-210,327-346`) in `--fhe disable` --
+    the clear quantized model, which is what the reference's own CLI evaluates (`batch_operations.py:233,276`) -- need no
+    GPU: same arguments, same printed lines, ids file, metadata, threshold and top-k.  `--fhe execute` without a CUDA device
+    must fail loudly (exit status 1, as the reference's handler does on any error) and never fall back to the CPU."""
+    import json
+    import torch
+    from fhe_icp_b200.fhe_cli import main
+    docs = [{"text": "quantum computing with qubits", "id": "q1", "metadata": {"tag": "physics"}},
+            {"text": "quantum error correction", "id": "q2"}, {"text": "cooking pasta recipes", "id": "c1"}, "cooking garlic"]
+    (tmp_path / "docs.json").write_text(json.dumps(docs))
+    sd = str(tmp_path / "store")
+    assert main(["--storage-dir", sd, "--fhe", "disable", "encrypt-batch", str(tmp_path / "docs.json"),
+                 "-o", str(tmp_path / "ids.json")]) == 0
+    ids = json.loads((tmp_path / "ids.json").read_text())
+    assert ids[:3] == ["q1", "q2", "c1"] and len(ids) == 4
+    assert "Encrypted 4 documents successfully!" in capsys.readouterr().out
+    assert main(["--storage-dir", sd, "--fhe", "disable", "compare", "q1", "q2"]) == 0
+    out = capsys.readouterr().out
+    assert "Document 1: q1" in out and "Similarity score:" in out and "Interpretation: Very similar" in out
+    assert main(["--storage-dir", sd, "--fhe", "disable", "compare", "q1", "c1"]) == 0
+    far = capsys.readouterr().out
+    score = lambda s: float([l for l in s.splitlines() if "Similarity score" in l][0].split(":")[1])   # noqa: E731
+    assert score(far) < score(out)
+    assert main(["--storage-dir", sd, "--fhe", "disable", "search", "quantum supremacy", "--top-k", "3"]) == 0
+    s = capsys.readouterr().out
+    assert "Found 2 similar documents" in s and "1. q" in s and "Metadata: {'tag': 'physics'}" in s
+    assert main(["--storage-dir", sd, "--fhe", "disable", "search", "quantum supremacy", "--top-k", "1",
+                 "--min-similarity", "0.0"]) == 0
+    assert "Found 1 similar documents" in capsys.readouterr().out
+    assert main(["--storage-dir", sd, "--fhe", "disable", "search", "quantum supremacy", "--min-similarity", "0.9999"]) == 0
+    assert "No similar documents found." in capsys.readouterr().out
+    if not torch.cuda.is_available():
+        # compare: the reference's handler prints the error itself and returns (`fhe_cli.py:180-181`); search has no handler of
+        # its own, so the error reaches main(), which reports it and exits 1 (`fhe_cli.py:384-390`)
+        assert main(["--storage-dir", sd, "compare", "q1", "q2"]) == 0
+        o = capsys.readouterr().out
+        assert "no CPU fallback" in o and "Similarity score" not in o
+        assert main(["--storage-dir", sd, "search", "quantum supremacy"]) == 1
+        c = capsys.readouterr()
+        assert "no CPU fallback" in c.err and "Found" not in c.out
