@@ -45,7 +45,7 @@ class FHECircuit:
         self.noise_seed = seed_or_fresh(noise_seed)
         self.enc_seed = seed_or_fresh(enc_seed)
         self.device = device
-        self.ids = CiphertextIds(ct_start)     # never-reused ciphertext ids (persisted with the key set)
+        self.ids = CiphertextIds(ct_start)     # never-reused ciphertext ids (random 62-bit origin per process)
         # "seeded": fresh ciphertexts travel as 8-byte bodies + public mask seed (the evaluator regenerates
         # the masks); "expanded": full (n+1)-word ciphertexts are materialised in HBM.  Same results.
         self.ciphertext_format = "seeded"

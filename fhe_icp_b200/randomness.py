@@ -13,7 +13,9 @@ policy is about seeds and ids:
 All four default to the OS CSPRNG (``secrets``).  Fixed values are an explicit opt-in for reproducible tests and
 benchmarks.  Ciphertext ids (the ``object id`` of a mask / error stream) must never repeat under one seed pair -- two
 ciphertexts with equal mask and error differ exactly by ``Delta*(m1 - m2)`` -- so they come from one monotonic counter per
-key set, started at a random 62-bit nonce in the default (non-deterministic) mode and persisted with the key set.
+key set and process, started at a random 62-bit origin in the default (non-deterministic) mode: a persisted key set that
+another process loads draws a fresh origin there (two processes overlap with probability ~ count / 2^62), so nothing has
+to be written back to the key file after an encryption.
 """
 from __future__ import annotations
 

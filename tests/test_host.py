@@ -296,3 +296,42 @@ def test_cli_clear_mode_on_cpu_and_loud_failure_of_execute_without_a_gpu(tmp_pat
         assert main(["--storage-dir", sd, "search", "quantum supremacy"]) == 1
         c = capsys.readouterr()
         assert "no CPU fallback" in c.err and "Found" not in c.out
+
+
+def test_seed_policy_secrets_are_fresh_public_parts_carry_no_secret_and_ids_never_repeat():
+    """The seed policy of randomness.py (what Concrete's CSPRNG key generation gives the reference for free): without explicit
+    seeds every model draws its own key / noise / mask seeds and its own ciphertext-id origin; what travels to an evaluator
+    (a SeededCiphertexts object, the evaluator-side C signatures) names the public mask seed only; the id allocator is
+    monotonic and hands out disjoint ranges; explicit seeds reproduce."""
+    import inspect
+    from pathlib import Path
+    from fhe_icp_b200 import FHESimilarityModel
+    from fhe_icp_b200.fhe_similarity import SeededCiphertexts
+    from fhe_icp_b200.randomness import CiphertextIds, seed_or_fresh
+
+    def circuit(**kw):
+        m = FHESimilarityModel(input_dim=16, n_bits=8, seed=1, verbose=False, **kw)      # `seed` seeds the data only
+        X, _ = m.train(n_samples=60)
+        m.compile(X[:10])
+        return m.model.fhe_circuit
+
+    a, b = circuit(), circuit()
+    secrets_a = {a.key_seed, a.noise_seed, a.enc_seed}
+    assert len(secrets_a) == 3 and not secrets_a & {b.key_seed, b.noise_seed, b.enc_seed}
+    assert a.ct_counter != b.ct_counter and a.ct_counter < 2 ** 62
+    assert np.array_equal(a.spec.q_weights, b.spec.q_weights)          # same data seed: same public model
+    c1, c2 = circuit(key_seed=5, noise_seed=6, enc_seed=7, ct_start=0), circuit(key_seed=5, noise_seed=6, enc_seed=7, ct_start=0)
+    assert (c1.key_seed, c1.noise_seed, c1.enc_seed, c1.ct_counter) == (5, 6, 7, 0) == (c2.key_seed, c2.noise_seed, c2.enc_seed, c2.ct_counter)
+    # the compressed ciphertext object and the evaluator-side entry points carry the public mask seed only
+    assert set(inspect.signature(SeededCiphertexts.__init__).parameters) == {"self", "bodies", "enc_seed", "ct_base"}
+    header = (Path(__file__).resolve().parent.parent / "include" / "fhe_b200.h").read_text()
+    for fn in ("fhe_b200_similarity_run_seeded", "fhe_b200_similarity_run_seeded_push", "fhe_b200_similarity_create_evaluator"):
+        decl = header[header.index(fn + "("):]
+        decl = decl[: decl.index(";")]
+        assert "noise_seed" not in decl and "key_seed" not in decl, fn
+    # ids: monotonic, disjoint, random origin by default
+    ids = CiphertextIds(10)
+    assert [ids.take(3), ids.take(0), ids.take(5), ids.take(1)] == [10, 13, 13, 18] and ids.next == 19
+    assert CiphertextIds().next != CiphertextIds().next
+    assert c1.next_ct_base(4) == 0 and c1.next_ct_base(2) == 4 and c1.ct_counter == 6
+    assert seed_or_fresh(None) != seed_or_fresh(None) and seed_or_fresh(-1) == 2 ** 64 - 1
