@@ -82,3 +82,13 @@ def test_pbs_dispatch_labels_follow_the_dispatcher():
     both = _mb2_kernels(612, sm)
     assert "pbs_kernel_mb2<1,4> x 592" in both and "pbs_kernel_mb2_pair x 20" in both
     assert "pbs_kernel_mb2_wide x 148" in _mb2_kernels(740, sm)
+
+
+def test_cpu_pbs_baseline_is_correct_on_a_small_sample():
+    """bench.py's `pbs.cpu_baseline`: the oracle's keyswitch + multi-bit PBS at the stated parameter set on one ciphertext
+    per host thread; every output must decrypt to the table entry."""
+    import bench
+    from fhe_icp_b200.params import PBS_PARAMS_4BIT as P
+    params = {k: P[k] for k in ("n", "k", "N_poly", "l_pbs", "beta_pbs", "l_ks", "beta_ks", "log2_sigma_lwe", "log2_sigma_glwe")}
+    r = bench.cpu_pbs_reference(params, per_thread=1)
+    assert r["all_correct"] and r["value"] > 0 and r["pbs_per_sec"] >= r["value"] and r["kind"] == "port" and r["cores"] >= 1
